@@ -1,0 +1,123 @@
+/* onetrans_b200.h — C-ABI of libonetrans_sm100.so: the B200 (sm_100a) kernels behind the OneTrans
+ * ranking block of ScottHCL/recommend (rank/scaling_up/oneTrans/practice, "OT/" below).
+ *
+ * The reference has no FFI or plugin layer: its hot path is a Keras Model whose arithmetic is
+ * TensorFlow library calls.  Each entry point below therefore replaces a group of
+ * TensorFlow call sites of OT/model.py (cited per function); the host side that keeps the reference's
+ * module API (recommend_b200/model.py) binds them with ctypes (INTEGRATION.md shows the stub).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller; the library never allocates or frees
+ *     device memory and never synchronises the host;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*);
+ *   - activations are bf16, row-major `[rows, cols]` with an element leading dimension (`ld*`);
+ *     rows are TOKEN-MAJOR: row = token_position * B + sample  (DESIGN.md §3);
+ *   - return value 0 = ok; negative = error (ot_last_error_string() describes it).  An unsupported
+ *     shape is an error, never a fallback.
+ */
+#ifndef ONETRANS_B200_H_
+#define ONETRANS_B200_H_
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OT_ABI_VERSION 1
+
+int ot_version(void);
+const char* ot_last_error_string(void);
+/* SM count of the current device (0 if no device). */
+int ot_num_sms(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Mixed-parameter GEMM  (tcgen05 / TMEM / TMA, persistent, grouped)
+ *   out[row, :] = epilogue( A[row, :K] . W[group(row)]^T )           W[g] is [N, K] (K contiguous)
+ * Replaces the per-position Dense loops of MixedMHA (OT/model.py:84-92), Wo (:117), MixedFFN
+ * (:154-163), the sequence projections of the Tokenizer (:262-265) and, with transposed weights, their
+ * input gradients.  "group(row)" is data: rows are described by up to 3 segments; a segment is
+ * `n_units` runs of `rows_per_unit` rows; unit u uses weight group `group_start + u*group_stride`.
+ *   shared S-token run : n_units=1, rows_per_unit=n_S*B, group_stride=0
+ *   NS-token run       : n_units=n_NS, rows_per_unit=B,  group_stride=1     (OT/model.py:67-74, D4)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct ot_gemm_seg {
+  int32_t row_start;     /* first output row of unit 0 */
+  int32_t n_units;
+  int32_t rows_per_unit;
+  int32_t group_start;
+  int32_t group_stride;
+  int32_t a_row_start;   /* A row of unit 0 row 0 (2-D mode) or first unit coordinate (transposed mode) */
+} ot_gemm_seg;
+
+enum {
+  OT_EPI_BIAS = 1,        /* + bias[group*bias_group_stride + n]                                   */
+  OT_EPI_GELU = 2,        /* out = gelu_erf(v); if out2 != NULL, out2 = v (pre-activation)          */
+  OT_EPI_RESIDUAL = 4,    /* + res[row, n]                                                          */
+  OT_EPI_GELU_GRAD = 8,   /* v *= gelu_erf'(aux[row, n])                                            */
+  OT_EPI_ROW_SCALE = 16   /* v *= row_scale[row]   (applied first)                                  */
+};
+
+typedef struct ot_gemm_params {
+  /* A operand.  2-D mode: element (row,k) at A[row*a_stride1 + k], a_dim1 rows.
+   * transposed mode (a_transposed=1): element (unit,row_in_unit,k) at
+   * A[row_in_unit*a_stride2 + unit*a_stride1 + k], a_dim1 units, a_dim2 rows per unit
+   * (the tokenizer reads `[B, L_i, 64]` events token-major this way). Strides in elements. */
+  const void* A;
+  int64_t a_dim1, a_dim2, a_stride1, a_stride2;
+  int32_t a_transposed;
+  int32_t n_groups;
+  const void* W;         /* [n_groups, N, K] bf16, K contiguous, leading dimension ldw */
+  int64_t ldw;
+  int32_t N, K;
+  int32_t n_segs;
+  int32_t flags;
+  ot_gemm_seg segs[3];
+  void* out;   int64_t ldo;
+  void* out2;  int64_t ldo2;
+  const void* res; int64_t ldr;
+  const void* aux; int64_t ldaux;
+  const float* bias; int64_t bias_group_stride;
+  const float* row_scale;
+  int32_t block_n;       /* 0 = choose */
+  int32_t swizzle;       /* 0 = 128-byte swizzle (default); 64 selects the 64-byte variant */
+} ot_gemm_params;
+
+int ot_mixed_gemm(const ot_gemm_params* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Weight gradient  (tcgen05, both operands MN-major, split over rows, fp32 atomic accumulate)
+ *   C[group][m, n] += sum_rows P[row, m] * Q[row, n]
+ * Replaces tape.gradient (OT/train.py:131) for every Dense kernel on the path.
+ * A segment is `n_units` runs of `rows_per_unit` rows.  group_stride=1: unit u accumulates into
+ * group group_start+u; group_stride=0: all units accumulate into group_start.
+ * P/Q element (unit, row, col) at base[unit*stride_unit + row*stride_row + col]  (elements).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct ot_wgrad_seg {
+  const void* P; int64_t p_stride_row, p_stride_unit;
+  const void* Q; int64_t q_stride_row, q_stride_unit;
+  int32_t n_units;
+  int32_t rows_per_unit;
+  int32_t group_start;
+  int32_t group_stride;
+} ot_wgrad_seg;
+
+typedef struct ot_wgrad_params {
+  int32_t Mdim, Ndim;        /* Mdim % 128 == 0, Ndim % 64 == 0 */
+  int32_t n_segs;
+  int32_t swizzle;           /* 0 = 128 */
+  ot_wgrad_seg segs[2];
+  float* C;                  /* fp32, accumulated with atomics (caller zeroes) */
+  int64_t c_group_stride, c_stride_m, c_stride_n;
+  const float* p_row_scale;  /* optional: P rows scaled... reserved, must be NULL */
+  int32_t block_n;           /* 0 = choose */
+  int32_t target_ctas;       /* 0 = 2 waves of the device */
+} ot_wgrad_params;
+
+int ot_wgrad(const ot_wgrad_params* p, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ONETRANS_B200_H_ */

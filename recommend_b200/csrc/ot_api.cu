@@ -1,0 +1,59 @@
+// ot_api.cu — the C-ABI surface of libonetrans_sm100.so (include/onetrans_b200.h): thin extern "C"
+// wrappers that validate, build tensor maps and enqueue the sm_100a kernels on the caller's stream.
+// No C++ exception crosses this boundary, nothing here allocates device memory or synchronises.
+#include "ot_host.h"
+#include "../../include/onetrans_b200.h"
+
+namespace ot {
+
+char* error_slot() {
+  static thread_local char buf[512] = {0};
+  return buf;
+}
+
+PFN_cuTensorMapEncodeTiled get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess) {
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(ptr);
+    }
+  }
+  return fn;
+}
+
+int num_sms() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+int mixed_gemm_impl(const ot_gemm_params* p, cudaStream_t st);
+int wgrad_impl(const ot_wgrad_params* p, cudaStream_t st);
+
+}  // namespace ot
+
+extern "C" {
+
+int ot_version(void) { return OT_ABI_VERSION; }
+const char* ot_last_error_string(void) { return ot::error_slot(); }
+int ot_num_sms(void) { return ot::num_sms(); }
+
+int ot_mixed_gemm(const ot_gemm_params* p, void* stream) {
+  return ot::mixed_gemm_impl(p, static_cast<cudaStream_t>(stream));
+}
+int ot_wgrad(const ot_wgrad_params* p, void* stream) {
+  return ot::wgrad_impl(p, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

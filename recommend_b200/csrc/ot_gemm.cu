@@ -1,0 +1,423 @@
+// ot_gemm.cu — mixed-parameter grouped GEMM for sm_100a.
+//
+//   out[row, n] = epilogue( sum_k A[row, k] * W[group(row)][n, k] )
+//
+// Replaces the per-position Dense loops of the reference (OT/model.py:84-92 QKV, :117 Wo,
+// :154-163 FFN, :262-265 sequence projections) and their input gradients.  The rule "which rows use
+// which weight set" (OT/model.py:67-74) arrives as data (ot_gemm_seg), so the shared S-token run and
+// the per-token NS runs are tiles of ONE persistent launch.
+//
+// Kernel structure (one CTA per SM, persistent over a static tile list; 6 warps):
+//   warp 0   : TMA producer   — A tile [128 x BK] and W tile [BN x BK] into a STAGES-deep smem ring
+//   warp 1   : MMA issuer     — tcgen05.mma (M=128, N=BN, K=16) into one of two TMEM accumulators
+//   warps 2-5: epilogue       — tcgen05.ld -> fp32 math (row scale, bias, GELU, GELU', residual)
+//                               -> bf16 -> swizzled smem staging -> coalesced 16-byte global stores
+// The two TMEM accumulators (2*BN <= 512 columns) let the epilogue of tile i overlap the MMAs of
+// tile i+1.  Roofline: at d=256 every GEMM of the block is HBM-bound, so the
+// epilogue reads/writes each activation byte exactly once and in full 128-byte lines.
+#include "ot_common.cuh"
+#include "ot_host.h"
+#include "../../include/onetrans_b200.h"
+
+namespace ot {
+
+static constexpr int BM = 128;
+static constexpr int GEMM_THREADS = 192;
+static constexpr int EPI_THREADS = 128;
+static constexpr int EPI_BAR_ID = 1;
+static constexpr int CHUNK = 64;  // epilogue column chunk (128 bytes of bf16 per row)
+
+struct GemmSegDev {
+  int row_start, n_units, rows_per_unit, group_start, group_stride, a_row_start;
+  int mblk_start, mblk_per_unit;
+};
+
+struct GemmKParams {
+  int N, K;
+  int n_segs;
+  int total_mblks, n_nblks;
+  int a_transposed;
+  int flags;
+  GemmSegDev segs[3];
+  __nv_bfloat16* out;  long long ldo;
+  __nv_bfloat16* out2; long long ldo2;
+  const __nv_bfloat16* res; long long ldr;
+  const __nv_bfloat16* aux; long long ldaux;
+  const float* bias; long long bias_group_stride;
+  const float* row_scale;
+};
+
+struct TileInfo {
+  int row0, valid, group, a_c1, a_c2;
+};
+
+__device__ __forceinline__ TileInfo decode_tile(const GemmKParams& p, int mblk) {
+  int s = 0;
+  while (s + 1 < p.n_segs && mblk >= p.segs[s + 1].mblk_start) ++s;
+  const GemmSegDev& sg = p.segs[s];
+  const int local = mblk - sg.mblk_start;
+  const int unit = local / sg.mblk_per_unit;
+  const int sub = local - unit * sg.mblk_per_unit;
+  const int riu = sub * BM;
+  TileInfo t;
+  t.row0 = sg.row_start + unit * sg.rows_per_unit + riu;
+  t.valid = min(BM, sg.rows_per_unit - riu);
+  t.group = sg.group_start + unit * sg.group_stride;
+  if (!p.a_transposed) {
+    t.a_c1 = sg.a_row_start + unit * sg.rows_per_unit + riu;
+    t.a_c2 = 0;
+  } else {
+    t.a_c1 = sg.a_row_start + unit;
+    t.a_c2 = riu;
+  }
+  return t;
+}
+
+template <int BN, int SWB>
+struct GemmCfg {
+  static constexpr int BK = SWB / 2;                 // bf16 elements per swizzle row
+  static constexpr int A_BYTES = BM * SWB;
+  static constexpr int B_BYTES = BN * SWB;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGING_BYTES = 2 * BM * CHUNK * 2;  // two 128x64 bf16 buffers
+  static constexpr int BIAS_BYTES = BN * 4;
+  static constexpr int BUDGET = 227 * 1024 - STAGING_BYTES - BIAS_BYTES - 256;
+  static constexpr int STAGES_RAW = BUDGET / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + BIAS_BYTES + 256;
+  static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
+                                   : (2 * BN <= 256) ? 256 : 512;
+};
+
+template <int BN, int SWB>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+ot_mixed_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                     const __grid_constant__ GemmKParams p) {
+  using Cfg = GemmCfg<BN, SWB>;
+  constexpr int BK = Cfg::BK;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ __align__(1024) uint8_t smem[];
+
+  uint8_t* stage_base = smem;
+  uint8_t* staging = smem + STAGES * Cfg::STAGE_BYTES;
+  float* bias_s = reinterpret_cast<float*>(staging + Cfg::STAGING_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + Cfg::STAGING_BYTES + Cfg::BIAS_BYTES);
+  uint64_t* full_bar = bars;                 // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;       // [STAGES]
+  uint64_t* tfull_bar = bars + 2 * STAGES;   // [2]
+  uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = p.total_mblks * p.n_nblks;
+  const int num_kb = p.K / BK;
+
+  if (threadIdx.x == 0) {
+    if ((smem_u32(smem) & 1023u) != 0) __trap();  // swizzled tiles need a 1024-byte aligned base
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int mblk = tile / p.n_nblks;
+        const int nblk = tile - mblk * p.n_nblks;
+        const TileInfo t = decode_tile(p, mblk);
+        const int w_row = t.group * p.N + nblk * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = stage_base + stage * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + Cfg::A_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          tma_load_3d(sa, &tmA, &full_bar[stage], kb * BK, t.a_c1, t.a_c2);
+          tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, w_row);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(stage_base + stage * Cfg::STAGE_BYTES);
+          const uint32_t sb = sa + Cfg::A_BYTES;
+          const uint64_t adesc = make_smem_desc<SWB>(sa, 16);
+          const uint64_t bdesc = make_smem_desc<SWB>(sb, 16);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in the 16-byte address field
+            umma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[acc]);
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int et = threadIdx.x - 64;           // 0..127
+    const int lgrp = warp & 3;                 // TMEM lane group this warp may read
+    const int r_own = lgrp * 32 + lane;        // accumulator row owned by this thread
+    const int ld_row = et >> 3;                // cooperative copy: 16 rows per pass, 8 x 16 B per row
+    const int ld_ch = et & 7;
+    int sbuf = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int mblk = tile / p.n_nblks;
+      const int nblk = tile - mblk * p.n_nblks;
+      const TileInfo t = decode_tile(p, mblk);
+      const int n0 = nblk * BN;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+
+      if (p.flags & OT_EPI_BIAS) {
+        named_bar_sync(EPI_BAR_ID, EPI_THREADS);  // previous tile's readers of bias_s are done
+        for (int j = et; j < BN; j += EPI_THREADS)
+          bias_s[j] = p.bias[(long long)t.group * p.bias_group_stride + n0 + j];
+        named_bar_sync(EPI_BAR_ID, EPI_THREADS);
+      }
+      float rs = 1.0f;
+      if ((p.flags & OT_EPI_ROW_SCALE) && r_own < t.valid) rs = p.row_scale[t.row0 + r_own];
+
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(lgrp * 32) << 16) + acc * BN;
+
+#pragma unroll 1
+      for (int c = 0; c < BN / CHUNK; ++c) {
+        uint32_t v[64];
+        {
+          uint32_t (&lo)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[0]);
+          uint32_t (&hi)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[32]);
+          tmem_ld_x32(t_row + c * CHUNK, lo);
+          tmem_ld_x32(t_row + c * CHUNK + 32, hi);
+          tmem_ld_wait();
+        }
+        const int col0 = n0 + c * CHUNK;
+        if (p.flags & OT_EPI_ROW_SCALE) {
+#pragma unroll
+          for (int j = 0; j < 64; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * rs);
+        }
+        if (p.flags & OT_EPI_BIAS) {
+#pragma unroll
+          for (int j = 0; j < 64; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + bias_s[c * CHUNK + j]);
+        }
+
+        // ---- helper lambdas over the staging buffers ----
+        auto coop_load = [&](const __nv_bfloat16* src, long long ld, uint8_t* buf) {
+#pragma unroll
+          for (int i = 0; i < BM / 16; ++i) {
+            const int r = i * 16 + ld_row;
+            uint4 q = make_uint4(0, 0, 0, 0);
+            if (r < t.valid)
+              q = *reinterpret_cast<const uint4*>(src + (long long)(t.row0 + r) * ld + col0 + ld_ch * 8);
+            *reinterpret_cast<uint4*>(buf + swz_off<128>(r, ld_ch)) = q;
+          }
+        };
+        auto coop_store = [&](__nv_bfloat16* dst, long long ld, const uint8_t* buf) {
+#pragma unroll
+          for (int i = 0; i < BM / 16; ++i) {
+            const int r = i * 16 + ld_row;
+            if (r < t.valid) {
+              const uint4 q = *reinterpret_cast<const uint4*>(buf + swz_off<128>(r, ld_ch));
+              *reinterpret_cast<uint4*>(dst + (long long)(t.row0 + r) * ld + col0 + ld_ch * 8) = q;
+            }
+          }
+        };
+        auto write_own_row = [&](uint8_t* buf) {
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch) {
+            uint4 q;
+            q.x = pack_bf16x2(__uint_as_float(v[ch * 8 + 0]), __uint_as_float(v[ch * 8 + 1]));
+            q.y = pack_bf16x2(__uint_as_float(v[ch * 8 + 2]), __uint_as_float(v[ch * 8 + 3]));
+            q.z = pack_bf16x2(__uint_as_float(v[ch * 8 + 4]), __uint_as_float(v[ch * 8 + 5]));
+            q.w = pack_bf16x2(__uint_as_float(v[ch * 8 + 6]), __uint_as_float(v[ch * 8 + 7]));
+            *reinterpret_cast<uint4*>(buf + swz_off<128>(r_own, ch)) = q;
+          }
+        };
+
+        if (p.flags & OT_EPI_GELU) {
+          if (p.out2 != nullptr) {  // keep the pre-activation for the backward pass
+            uint8_t* buf = staging + sbuf * (BM * CHUNK * 2);
+            write_own_row(buf);
+            named_bar_sync(EPI_BAR_ID, EPI_THREADS);
+            coop_store(p.out2, p.ldo2, buf);
+            sbuf ^= 1;
+          }
+#pragma unroll
+          for (int j = 0; j < 64; ++j) v[j] = __float_as_uint(gelu_erf(__uint_as_float(v[j])));
+        }
+        uint8_t* buf = staging + sbuf * (BM * CHUNK * 2);
+        if (p.flags & OT_EPI_GELU_GRAD) {
+          coop_load(p.aux, p.ldaux, buf);
+          named_bar_sync(EPI_BAR_ID, EPI_THREADS);
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch) {
+            const uint4 q = *reinterpret_cast<const uint4*>(buf + swz_off<128>(r_own, ch));
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              v[ch * 8 + 2 * e] = __float_as_uint(__uint_as_float(v[ch * 8 + 2 * e]) * gelu_erf_grad(bf16lo(w[e])));
+              v[ch * 8 + 2 * e + 1] =
+                  __float_as_uint(__uint_as_float(v[ch * 8 + 2 * e + 1]) * gelu_erf_grad(bf16hi(w[e])));
+            }
+          }
+          if (p.flags & OT_EPI_RESIDUAL) named_bar_sync(EPI_BAR_ID, EPI_THREADS);  // before buf is reloaded
+        }
+        if (p.flags & OT_EPI_RESIDUAL) {
+          coop_load(p.res, p.ldr, buf);
+          named_bar_sync(EPI_BAR_ID, EPI_THREADS);
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch) {
+            const uint4 q = *reinterpret_cast<const uint4*>(buf + swz_off<128>(r_own, ch));
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              v[ch * 8 + 2 * e] = __float_as_uint(__uint_as_float(v[ch * 8 + 2 * e]) + bf16lo(w[e]));
+              v[ch * 8 + 2 * e + 1] = __float_as_uint(__uint_as_float(v[ch * 8 + 2 * e + 1]) + bf16hi(w[e]));
+            }
+          }
+        }
+        // each thread overwrites only its own row of `buf`, then the tile chunk leaves coalesced
+        write_own_row(buf);
+        named_bar_sync(EPI_BAR_ID, EPI_THREADS);
+        coop_store(p.out, p.ldo, buf);
+        sbuf ^= 1;
+      }
+      // all TMEM reads of this accumulator are complete -> hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+// -------------------------------------------------------------------------------------------------
+// host launcher
+// -------------------------------------------------------------------------------------------------
+template <int BN, int SWB>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKParams& kp, cudaStream_t st) {
+  using Cfg = GemmCfg<BN, SWB>;
+  static bool attr_done = false;
+  auto kern = ot_mixed_gemm_kernel<BN, SWB>;
+  if (!attr_done) {
+    OT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_done = true;
+  }
+  const int total_tiles = kp.total_mblks * kp.n_nblks;
+  const int grid = total_tiles < num_sms() ? total_tiles : num_sms();
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, kp);
+  OT_CUDA_CHECK(cudaGetLastError());
+  return OT_OK;
+}
+
+int mixed_gemm_impl(const ot_gemm_params* p, cudaStream_t st) {
+  if (!p || !p->A || !p->W || !p->out) OT_FAIL(OT_ERR_INVALID_ARG, "ot_mixed_gemm: null pointer");
+  const int swb = p->swizzle == 0 ? 128 : p->swizzle;
+  if (swb != 128 && swb != 64) OT_FAIL(OT_ERR_INVALID_ARG, "ot_mixed_gemm: swizzle must be 0, 64 or 128");
+  const int bk = swb / 2;
+  if (p->K <= 0 || p->K % bk != 0) OT_FAIL(OT_ERR_UNSUPPORTED_SHAPE, "ot_mixed_gemm: K=%d not a multiple of %d", p->K, bk);
+  if (p->N <= 0 || p->N % 64 != 0) OT_FAIL(OT_ERR_UNSUPPORTED_SHAPE, "ot_mixed_gemm: N=%d not a multiple of 64", p->N);
+  if (p->n_segs < 1 || p->n_segs > 3) OT_FAIL(OT_ERR_INVALID_ARG, "ot_mixed_gemm: n_segs=%d", p->n_segs);
+  if ((p->flags & OT_EPI_BIAS) && !p->bias) OT_FAIL(OT_ERR_INVALID_ARG, "ot_mixed_gemm: bias flag without bias");
+  if ((p->flags & OT_EPI_RESIDUAL) && !p->res) OT_FAIL(OT_ERR_INVALID_ARG, "ot_mixed_gemm: residual flag without res");
+  if ((p->flags & OT_EPI_GELU_GRAD) && !p->aux) OT_FAIL(OT_ERR_INVALID_ARG, "ot_mixed_gemm: gelu-grad flag without aux");
+  if ((p->flags & OT_EPI_ROW_SCALE) && !p->row_scale) OT_FAIL(OT_ERR_INVALID_ARG, "ot_mixed_gemm: row-scale flag without row_scale");
+  if ((p->ldo % 8) || (p->out2 && (p->ldo2 % 8)) || (p->res && (p->ldr % 8)) || (p->aux && (p->ldaux % 8)))
+    OT_FAIL(OT_ERR_UNSUPPORTED_SHAPE, "ot_mixed_gemm: leading dimensions must be multiples of 8 elements");
+
+  int bn = p->block_n;
+  if (bn == 0) bn = (p->N % 256 == 0) ? 256 : (p->N % 128 == 0) ? 128 : 64;
+  if ((bn != 64 && bn != 128 && bn != 256) || p->N % bn != 0)
+    OT_FAIL(OT_ERR_UNSUPPORTED_SHAPE, "ot_mixed_gemm: block_n=%d does not tile N=%d", bn, p->N);
+
+  GemmKParams kp;
+  memset(&kp, 0, sizeof(kp));
+  kp.N = p->N; kp.K = p->K; kp.n_segs = p->n_segs; kp.a_transposed = p->a_transposed; kp.flags = p->flags;
+  int mb = 0;
+  for (int s = 0; s < p->n_segs; ++s) {
+    const ot_gemm_seg& sg = p->segs[s];
+    if (sg.n_units <= 0 || sg.rows_per_unit <= 0) OT_FAIL(OT_ERR_INVALID_ARG, "ot_mixed_gemm: empty segment %d", s);
+    GemmSegDev& d = kp.segs[s];
+    d.row_start = sg.row_start; d.n_units = sg.n_units; d.rows_per_unit = sg.rows_per_unit;
+    d.group_start = sg.group_start; d.group_stride = sg.group_stride; d.a_row_start = sg.a_row_start;
+    d.mblk_start = mb; d.mblk_per_unit = (sg.rows_per_unit + BM - 1) / BM;
+    mb += d.mblk_per_unit * sg.n_units;
+    const int last_group = sg.group_start + (sg.n_units - 1) * sg.group_stride;
+    if (sg.group_start < 0 || last_group >= p->n_groups)
+      OT_FAIL(OT_ERR_INVALID_ARG, "ot_mixed_gemm: segment %d addresses weight group %d of %d", s, last_group, p->n_groups);
+  }
+  kp.total_mblks = mb; kp.n_nblks = p->N / bn;
+  kp.out = (__nv_bfloat16*)p->out; kp.ldo = p->ldo; kp.out2 = (__nv_bfloat16*)p->out2; kp.ldo2 = p->ldo2;
+  kp.res = (const __nv_bfloat16*)p->res; kp.ldr = p->ldr; kp.aux = (const __nv_bfloat16*)p->aux; kp.ldaux = p->ldaux;
+  kp.bias = p->bias; kp.bias_group_stride = p->bias_group_stride; kp.row_scale = p->row_scale;
+
+  // tensor maps: A always rank 3 (k, c1, c2); W rank 2 (k, group*N + n)
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[3]; uint64_t str[2]; uint32_t box[3];
+    dims[0] = (uint64_t)p->K; dims[1] = (uint64_t)p->a_dim1; dims[2] = (uint64_t)(p->a_dim2 > 0 ? p->a_dim2 : 1);
+    str[0] = (uint64_t)p->a_stride1 * 2; str[1] = (uint64_t)(p->a_dim2 > 1 ? p->a_stride2 : p->a_stride1 * p->a_dim1) * 2;
+    box[0] = bk;
+    if (!p->a_transposed) { box[1] = BM; box[2] = 1; } else { box[1] = 1; box[2] = BM; }
+    int rc = make_tmap_bf16(&tmA, p->A, 3, dims, str, box, swb);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)p->K, (uint64_t)p->n_groups * (uint64_t)p->N};
+    uint64_t str[1] = {(uint64_t)p->ldw * 2};
+    uint32_t box[2] = {(uint32_t)bk, (uint32_t)bn};
+    int rc = make_tmap_bf16(&tmB, p->W, 2, dims, str, box, swb);
+    if (rc) return rc;
+  }
+  if (swb == 128) {
+    if (bn == 256) return launch_gemm<256, 128>(tmA, tmB, kp, st);
+    if (bn == 128) return launch_gemm<128, 128>(tmA, tmB, kp, st);
+    return launch_gemm<64, 128>(tmA, tmB, kp, st);
+  } else {
+    if (bn == 256) return launch_gemm<256, 64>(tmA, tmB, kp, st);
+    if (bn == 128) return launch_gemm<128, 64>(tmA, tmB, kp, st);
+    return launch_gemm<64, 64>(tmA, tmB, kp, st);
+  }
+}
+
+}  // namespace ot

@@ -1,0 +1,266 @@
+// ot_wgrad.cu — weight-gradient GEMM for sm_100a:   C[g][m, n] += sum_rows P[row, m] * Q[row, n]
+//
+// Replaces tape.gradient (OT/train.py:131) for the Dense kernels of the OneTrans path: the shared
+// S-token weights contract over up to ~10^6 rows, each NS-token weight set over the B rows of its token
+// (OT/model.py:43-54, 142-147).  Both operands are read exactly as the forward pass left them in HBM
+// (row-major activations); the contraction runs over rows, so both are MN-major UMMA operands:
+// a TMA box of [64 rows x 64 columns] (128-byte swizzle) is one MN-major slab, no transposes anywhere.
+//
+// Work split: one CTA per (output group, 128 x BN tile, row slice).  The row range of an output is cut
+// into slices so that the launch fills the device about twice; every CTA keeps its accumulator in
+// TMEM for its whole slice and flushes once with fp32 atomics (the caller zeroes C).
+//   warp 0 lane*: TMA producer     warp 1 lane*: MMA issuer     all 4 warps: epilogue
+#include "ot_common.cuh"
+#include "ot_host.h"
+#include "../../include/onetrans_b200.h"
+
+namespace ot {
+
+static constexpr int WG_THREADS = 128;
+static constexpr int WG_KROWS = 64;  // rows (contraction) per pipeline stage
+
+struct WgradSegDev {
+  int n_units, rows_per_unit, group_start, group_stride;
+  int kb_per_unit;     // ceil(rows_per_unit / 64)
+  int n_out;           // outputs of this segment
+  int kb_per_out;      // k-blocks contracted per output
+  int slices_per_out, kb_per_slice;
+  int item_start;      // first work item of this segment
+};
+
+struct WgradKParams {
+  int Mdim, Ndim, m_tiles, n_tiles;
+  int n_segs;
+  WgradSegDev segs[2];
+  float* C;
+  long long c_group_stride, c_stride_m, c_stride_n;
+};
+
+template <int BN, int SWB>
+struct WgradCfg {
+  static constexpr int SLAB_COLS = SWB / 2;                  // columns per MN-major slab
+  static constexpr int SLAB_BYTES = WG_KROWS * SWB;          // 64 rows x SWB bytes
+  static constexpr int P_SLABS = 128 / SLAB_COLS;
+  static constexpr int Q_SLABS = BN / SLAB_COLS;
+  static constexpr int P_BYTES = P_SLABS * SLAB_BYTES;       // 16 KB
+  static constexpr int Q_BYTES = Q_SLABS * SLAB_BYTES;
+  static constexpr int STAGE_BYTES = P_BYTES + Q_BYTES;
+  static constexpr int STAGES_RAW = (227 * 1024 - 256) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256;
+  static constexpr int TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+};
+
+template <int BN, int SWB>
+__global__ void __launch_bounds__(WG_THREADS, 1)
+ot_wgrad_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constant__ CUtensorMap tmQ0,
+                const __grid_constant__ CUtensorMap tmP1, const __grid_constant__ CUtensorMap tmQ1,
+                const __grid_constant__ WgradKParams p) {
+  using Cfg = WgradCfg<BN, SWB>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* done_bar = bars + 2 * STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // ---- decode the work item ----
+  int item = blockIdx.x;
+  int s = (p.n_segs > 1 && item >= p.segs[1].item_start) ? 1 : 0;
+  const WgradSegDev& sg = p.segs[s];
+  item -= sg.item_start;
+  const int tiles = p.m_tiles * p.n_tiles;
+  // order: slice-major so that the CTAs running together read different rows of the same tiles
+  const int tile = item % tiles;
+  const int rest = item / tiles;
+  const int slice = rest % sg.slices_per_out;
+  const int out_idx = rest / sg.slices_per_out;
+  const int mt = tile / p.n_tiles;
+  const int nt = tile - mt * p.n_tiles;
+  const int kb_begin = slice * sg.kb_per_slice;
+  const int kb_end = min(sg.kb_per_out, kb_begin + sg.kb_per_slice);
+  const int num_kb = kb_end - kb_begin;
+  const int group = sg.group_start + out_idx * sg.group_stride;
+  const CUtensorMap* tmP = s == 0 ? &tmP0 : &tmP1;
+  const CUtensorMap* tmQ = s == 0 ? &tmQ0 : &tmQ1;
+
+  if (threadIdx.x == 0) {
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
+    tma_prefetch_desc(tmP);
+    tma_prefetch_desc(tmQ);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(done_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (num_kb > 0) {
+    if (warp == 0) {
+      if (elect_one()) {
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+          int unit, r0;
+          if (sg.group_stride != 0) { unit = out_idx; r0 = kb * WG_KROWS; }
+          else { unit = kb / sg.kb_per_unit; r0 = (kb - unit * sg.kb_per_unit) * WG_KROWS; }
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sp = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sq = sp + Cfg::P_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+#pragma unroll
+          for (int i = 0; i < Cfg::P_SLABS; ++i)
+            tma_load_3d(sp + i * Cfg::SLAB_BYTES, tmP, &full_bar[stage], mt * 128 + i * Cfg::SLAB_COLS, r0, unit);
+#pragma unroll
+          for (int i = 0; i < Cfg::Q_SLABS; ++i)
+            tma_load_3d(sq + i * Cfg::SLAB_BYTES, tmQ, &full_bar[stage], nt * BN + i * Cfg::SLAB_COLS, r0, unit);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    } else if (warp == 1) {
+      if (elect_one()) {
+        constexpr uint32_t idesc = make_idesc_bf16(128, BN, 1, 1);  // both operands MN-major
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int i = 0; i < num_kb; ++i) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sp = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t sq = sp + Cfg::P_BYTES;
+          // LBO = distance between slabs along M/N; each UMMA consumes 16 rows = 16*SWB bytes
+          const uint64_t adesc = make_smem_desc<SWB>(sp, Cfg::SLAB_BYTES);
+          const uint64_t bdesc = make_smem_desc<SWB>(sq, Cfg::SLAB_BYTES);
+#pragma unroll
+          for (int k = 0; k < WG_KROWS / 16; ++k) {
+            const uint64_t adv = static_cast<uint64_t>((16 * SWB) >> 4) * k;
+            umma_bf16_ss(tmem_base, adesc + adv, bdesc + adv, idesc, (i | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(done_bar);
+      }
+    }
+    // ---- epilogue: every warp flushes its 32 accumulator rows ----
+    mbar_wait(done_bar, 0);
+    tc_fence_after();
+    const int m = mt * 128 + warp * 32 + lane;
+    float* crow = p.C + (long long)group * p.c_group_stride + (long long)m * p.c_stride_m +
+                  (long long)(nt * BN) * p.c_stride_n;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t v[32];
+      tmem_ld_x32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + c * 32, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) atomicAdd(crow + (long long)(c * 32 + j) * p.c_stride_n, __uint_as_float(v[j]));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+template <int BN, int SWB>
+static int launch_wgrad(const CUtensorMap* tm, const WgradKParams& kp, int items, cudaStream_t st) {
+  using Cfg = WgradCfg<BN, SWB>;
+  static bool attr_done = false;
+  auto kern = ot_wgrad_kernel<BN, SWB>;
+  if (!attr_done) {
+    OT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_done = true;
+  }
+  kern<<<items, WG_THREADS, Cfg::SMEM_BYTES, st>>>(tm[0], tm[1], tm[2], tm[3], kp);
+  OT_CUDA_CHECK(cudaGetLastError());
+  return OT_OK;
+}
+
+int wgrad_impl(const ot_wgrad_params* p, cudaStream_t st) {
+  if (!p || !p->C) OT_FAIL(OT_ERR_INVALID_ARG, "ot_wgrad: null pointer");
+  if (p->p_row_scale) OT_FAIL(OT_ERR_INVALID_ARG, "ot_wgrad: p_row_scale is reserved");
+  const int swb = p->swizzle == 0 ? 128 : p->swizzle;
+  if (swb != 128 && swb != 64) OT_FAIL(OT_ERR_INVALID_ARG, "ot_wgrad: swizzle must be 0, 64 or 128");
+  if (p->Mdim <= 0 || p->Mdim % 128) OT_FAIL(OT_ERR_UNSUPPORTED_SHAPE, "ot_wgrad: Mdim=%d not a multiple of 128", p->Mdim);
+  if (p->Ndim <= 0 || p->Ndim % 64) OT_FAIL(OT_ERR_UNSUPPORTED_SHAPE, "ot_wgrad: Ndim=%d not a multiple of 64", p->Ndim);
+  if (p->n_segs < 1 || p->n_segs > 2) OT_FAIL(OT_ERR_INVALID_ARG, "ot_wgrad: n_segs=%d", p->n_segs);
+  int bn = p->block_n;
+  if (bn == 0) bn = (p->Ndim % 256 == 0) ? 256 : (p->Ndim % 128 == 0) ? 128 : 64;
+  if ((bn != 64 && bn != 128 && bn != 256) || p->Ndim % bn) OT_FAIL(OT_ERR_UNSUPPORTED_SHAPE, "ot_wgrad: block_n=%d", bn);
+
+  WgradKParams kp;
+  memset(&kp, 0, sizeof(kp));
+  kp.Mdim = p->Mdim; kp.Ndim = p->Ndim; kp.m_tiles = p->Mdim / 128; kp.n_tiles = p->Ndim / bn;
+  kp.n_segs = p->n_segs; kp.C = p->C;
+  kp.c_group_stride = p->c_group_stride; kp.c_stride_m = p->c_stride_m; kp.c_stride_n = p->c_stride_n;
+  const int tiles = kp.m_tiles * kp.n_tiles;
+  const int target = p->target_ctas > 0 ? p->target_ctas : 2 * num_sms();
+
+  // total k-blocks over all outputs, to size the slices evenly
+  long long total_kb = 0;
+  for (int s = 0; s < p->n_segs; ++s) {
+    const ot_wgrad_seg& sg = p->segs[s];
+    if (!sg.P || !sg.Q || sg.n_units <= 0 || sg.rows_per_unit <= 0) OT_FAIL(OT_ERR_INVALID_ARG, "ot_wgrad: bad segment %d", s);
+    total_kb += (long long)sg.n_units * ((sg.rows_per_unit + WG_KROWS - 1) / WG_KROWS);
+  }
+  long long kb_target = (total_kb * tiles + target - 1) / target;  // k-blocks per CTA
+  if (kb_target < 8) kb_target = 8;
+
+  CUtensorMap tm[4];
+  int items = 0;
+  for (int s = 0; s < p->n_segs; ++s) {
+    const ot_wgrad_seg& sg = p->segs[s];
+    WgradSegDev& d = kp.segs[s];
+    d.n_units = sg.n_units; d.rows_per_unit = sg.rows_per_unit; d.group_start = sg.group_start; d.group_stride = sg.group_stride;
+    d.kb_per_unit = (sg.rows_per_unit + WG_KROWS - 1) / WG_KROWS;
+    if (sg.group_stride != 0) { d.n_out = sg.n_units; d.kb_per_out = d.kb_per_unit; }
+    else { d.n_out = 1; d.kb_per_out = d.kb_per_unit * sg.n_units; }
+    d.slices_per_out = (int)((d.kb_per_out + kb_target - 1) / kb_target);
+    if (d.slices_per_out < 1) d.slices_per_out = 1;
+    d.kb_per_slice = (d.kb_per_out + d.slices_per_out - 1) / d.slices_per_out;
+    d.slices_per_out = (d.kb_per_out + d.kb_per_slice - 1) / d.kb_per_slice;
+    d.item_start = items;
+    items += d.n_out * d.slices_per_out * tiles;
+    // rank-3 maps (col, row_in_unit, unit); rows past rows_per_unit are zero-filled by TMA
+    const int slab_cols = swb / 2;
+    {
+      uint64_t dims[3] = {(uint64_t)p->Mdim, (uint64_t)sg.rows_per_unit, (uint64_t)sg.n_units};
+      uint64_t str[2] = {(uint64_t)sg.p_stride_row * 2, (uint64_t)(sg.n_units > 1 ? sg.p_stride_unit : sg.p_stride_row * sg.rows_per_unit) * 2};
+      uint32_t box[3] = {(uint32_t)slab_cols, (uint32_t)WG_KROWS, 1};
+      int rc = make_tmap_bf16(&tm[2 * s], sg.P, 3, dims, str, box, swb);
+      if (rc) return rc;
+    }
+    {
+      uint64_t dims[3] = {(uint64_t)p->Ndim, (uint64_t)sg.rows_per_unit, (uint64_t)sg.n_units};
+      uint64_t str[2] = {(uint64_t)sg.q_stride_row * 2, (uint64_t)(sg.n_units > 1 ? sg.q_stride_unit : sg.q_stride_row * sg.rows_per_unit) * 2};
+      uint32_t box[3] = {(uint32_t)slab_cols, (uint32_t)WG_KROWS, 1};
+      int rc = make_tmap_bf16(&tm[2 * s + 1], sg.Q, 3, dims, str, box, swb);
+      if (rc) return rc;
+    }
+  }
+  if (p->n_segs == 1) { tm[2] = tm[0]; tm[3] = tm[1]; }
+
+  if (swb == 128) {
+    if (bn == 256) return launch_wgrad<256, 128>(tm, kp, items, st);
+    if (bn == 128) return launch_wgrad<128, 128>(tm, kp, items, st);
+    return launch_wgrad<64, 128>(tm, kp, items, st);
+  } else {
+    if (bn == 256) return launch_wgrad<256, 64>(tm, kp, items, st);
+    if (bn == 128) return launch_wgrad<128, 64>(tm, kp, items, st);
+    return launch_wgrad<64, 64>(tm, kp, items, st);
+  }
+}
+
+}  // namespace ot
