@@ -117,6 +117,89 @@ typedef struct ot_wgrad_params {
 
 int ot_wgrad(const ot_wgrad_params* p, void* stream);
 
+
+/* ------------------------------------------------------------------------------------------------
+ * Causal attention with pyramid query pruning  (tcgen05 flash-style; forward and backward)
+ * Replaces einsum/where/softmax/einsum of MixedMHA.call (OT/model.py:101-114) for the retained query
+ * tail only (OT/model.py:356-371 computes every query and gathers; same values).
+ *   queries: the last Lq positions; keys/values: all Lk positions (Lq <= Lk);
+ *   query i attends keys 0 .. (Lk-Lq)+i; scores scaled by 1/sqrt(head_dim) (OT/model.py:106).
+ * Buffers are token-major: element (l, b, h, e) at base[(l*B + b)*ld + h*head_dim + e].
+ * lse / delta: fp32 [B, H, Lq].  ot_attn_bwd needs q,k,v,o,lse,d_o and writes dq,dk,dv (+ delta scratch).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct ot_attn_params {
+  const void* q; int64_t ldq;
+  const void* k; int64_t ldk;
+  const void* v; int64_t ldv;
+  void* o;       int64_t ldo;
+  float* lse;
+  const void* d_o; int64_t lddo;
+  void* dq; int64_t lddq;
+  void* dk; int64_t lddk;
+  void* dv; int64_t lddv;
+  float* delta;
+  int32_t B, H, Lq, Lk;
+  int32_t head_dim;      /* 64 or 96 */
+  int32_t swizzle;       /* 0 = default; 64 forces the 64-byte-swizzle variant for head_dim 64 */
+} ot_attn_params;
+
+int ot_attn_fwd(const ot_attn_params* p, void* stream);
+int ot_attn_bwd(const ot_attn_params* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * RMSNorm (OT/model.py:19-23):  y = x * rsqrt(mean(x^2,-1) + eps) * gain.   HBM-bound, one warp per row.
+ * forward : x, gain -> y, rstd (fp32 per row; may be NULL)
+ * backward: dy, x, rstd, gain -> dx (+= dres if dres != NULL), dgain += sum_rows dy * x * rstd (fp32 atomics)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct ot_rmsnorm_params {
+  const void* x;  int64_t ldx;
+  void* y;        int64_t ldy;
+  const float* gain;
+  float* rstd;
+  const void* dy;   int64_t lddy;
+  const void* dres; int64_t lddres;
+  void* dx;         int64_t lddx;
+  float* dgain;
+  int64_t rows;
+  int32_t d;
+  float eps;
+} ot_rmsnorm_params;
+
+int ot_rmsnorm_fwd(const ot_rmsnorm_params* p, void* stream);
+int ot_rmsnorm_bwd(const ot_rmsnorm_params* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Non-sequence tokenizer (OT/model.py:211-214, 239-254): concat of scalar features -> Dense(d*L_NS)
+ * with bias -> Reshape [L_NS, d], written straight into the token-major X0 rows row0 + j*B + b.
+ * fp32 math (ids enter as magnitudes).  x: [B, n_feat] fp32, W: [n_feat, L_NS*d] fp32.
+ * backward: dW += x^T dX0_ns, dbias += colsum(dX0_ns)  (fp32 atomics; caller zeroes)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct ot_ns_tokenizer_params {
+  const float* x; const float* W; const float* bias;
+  void* out; const void* dout; int64_t ldo;
+  float* dW; float* dbias;
+  int64_t row0;
+  int32_t B, L_ns, d, n_feat;
+} ot_ns_tokenizer_params;
+
+int ot_ns_tokenizer_fwd(const ot_ns_tokenizer_params* p, void* stream);
+int ot_ns_tokenizer_bwd(const ot_ns_tokenizer_params* p, void* stream);
+
+/* rows [row0, row0+n_rows) of out <- bf16(vec[0..d)) : the [SEP] embedding rows (OT/model.py:269-272). */
+int ot_fill_rows(const float* vec, void* out, int64_t ldo, int64_t row0, int64_t n_rows, int32_t d, void* stream);
+
+/* Column sums for bias / [SEP] gradients: out[group_start + u*group_stride][n] += sum over the
+ * rows of unit u of in[row, n]   (fp32 atomics; caller zeroes). */
+typedef struct ot_colsum_params {
+  const void* in; int64_t ld;
+  int64_t row_start;
+  int32_t n_units, rows_per_unit, group_start, group_stride;
+  float* out; int64_t out_group_stride;
+  int32_t N;
+} ot_colsum_params;
+
+int ot_colsum(const ot_colsum_params* p, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,18 @@
+#!/bin/bash
+# Builds libonetrans_sm100.so in-tree (recommend_b200/lib/). nvcc cross-compiles sm_100a without a GPU.
+set -e
+cd "$(dirname "$0")"
+mkdir -p ../lib obj
+FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC ${OT_NVCC_EXTRA}"
+pids=()
+for f in ot_api ot_gemm ot_wgrad ot_attn_fwd ot_attn_bwd ot_elementwise; do
+  if [ -f $f.cu ]; then
+    if [ ! -f obj/$f.o ] || [ $f.cu -nt obj/$f.o ] || [ ot_common.cuh -nt obj/$f.o ] || [ ot_attn.cuh -nt obj/$f.o ] || [ ot_host.h -nt obj/$f.o ] || [ ../../include/onetrans_b200.h -nt obj/$f.o ]; then
+      nvcc $FLAGS -c $f.cu -o obj/$f.o &
+      pids+=($!)
+    fi
+  fi
+done
+for p in "${pids[@]}"; do wait $p; done
+nvcc -gencode arch=compute_100a,code=sm_100a --shared -o ../lib/libonetrans_sm100.so obj/*.o
+echo "built $(realpath ../lib/libonetrans_sm100.so)"

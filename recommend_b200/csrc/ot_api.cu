@@ -40,6 +40,14 @@ int num_sms() {
 
 int mixed_gemm_impl(const ot_gemm_params* p, cudaStream_t st);
 int wgrad_impl(const ot_wgrad_params* p, cudaStream_t st);
+int attn_fwd_impl(const ot_attn_params* p, cudaStream_t st);
+int attn_bwd_impl(const ot_attn_params* p, cudaStream_t st);
+int rmsnorm_fwd_impl(const ot_rmsnorm_params* p, cudaStream_t st);
+int rmsnorm_bwd_impl(const ot_rmsnorm_params* p, cudaStream_t st);
+int ns_tokenizer_fwd_impl(const ot_ns_tokenizer_params* p, cudaStream_t st);
+int ns_tokenizer_bwd_impl(const ot_ns_tokenizer_params* p, cudaStream_t st);
+int fill_rows_impl(const float* vec, void* out, long long ldo, long long row0, long long n_rows, int d, cudaStream_t st);
+int colsum_impl(const ot_colsum_params* p, cudaStream_t st);
 
 }  // namespace ot
 
@@ -55,5 +63,21 @@ int ot_mixed_gemm(const ot_gemm_params* p, void* stream) {
 int ot_wgrad(const ot_wgrad_params* p, void* stream) {
   return ot::wgrad_impl(p, static_cast<cudaStream_t>(stream));
 }
+
+int ot_attn_fwd(const ot_attn_params* p, void* stream) {
+  return ot::attn_fwd_impl(p, static_cast<cudaStream_t>(stream));
+}
+int ot_attn_bwd(const ot_attn_params* p, void* stream) {
+  return ot::attn_bwd_impl(p, static_cast<cudaStream_t>(stream));
+}
+
+int ot_rmsnorm_fwd(const ot_rmsnorm_params* p, void* stream) { return ot::rmsnorm_fwd_impl(p, static_cast<cudaStream_t>(stream)); }
+int ot_rmsnorm_bwd(const ot_rmsnorm_params* p, void* stream) { return ot::rmsnorm_bwd_impl(p, static_cast<cudaStream_t>(stream)); }
+int ot_ns_tokenizer_fwd(const ot_ns_tokenizer_params* p, void* stream) { return ot::ns_tokenizer_fwd_impl(p, static_cast<cudaStream_t>(stream)); }
+int ot_ns_tokenizer_bwd(const ot_ns_tokenizer_params* p, void* stream) { return ot::ns_tokenizer_bwd_impl(p, static_cast<cudaStream_t>(stream)); }
+int ot_fill_rows(const float* vec, void* out, int64_t ldo, int64_t row0, int64_t n_rows, int32_t d, void* stream) {
+  return ot::fill_rows_impl(vec, out, ldo, row0, n_rows, d, static_cast<cudaStream_t>(stream));
+}
+int ot_colsum(const ot_colsum_params* p, void* stream) { return ot::colsum_impl(p, static_cast<cudaStream_t>(stream)); }
 
 }  // extern "C"

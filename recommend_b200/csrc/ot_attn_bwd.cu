@@ -1,0 +1,459 @@
+// ot_attn_bwd.cu — backward of the pruned causal attention (tape.gradient of OT/model.py:101-114),
+// sm_100a tcgen05.  Two kernels, both recompute P from the saved log-sum-exp, neither uses atomics:
+//
+//   dq kernel  (one work item = query tile, head, sample; loops over key blocks)
+//       S = Q K^T, dP = dO V^T          -> TMEM [0,128), [128,256)
+//       dS = P o (dP - delta) * scale   -> bf16 smem tile
+//       dQ += dS K                      -> TMEM [256,256+DH)  (K tile reused MN-major)
+//       also produces delta = rowsum(dO o O) for the second kernel
+//   dkv kernel (one work item = key tile, head, sample; loops over the query tiles that see it)
+//       S, dP as above; P and dS tiles in smem
+//       dV += P^T dO,  dK += dS^T Q     -> TMEM, P/dS/dO/Q tiles reused MN-major (no transposes)
+//
+// 256 threads: thread (r, half) owns row r of the tile and half of its 128 score columns; the row
+// statistics (lse, delta) are inputs, so no cross-thread reduction is needed.
+#include "ot_attn.cuh"
+#include "ot_host.h"
+#include "../../include/onetrans_b200.h"
+
+namespace ot {
+
+struct AttnBwdKParams {
+  int B, H, Lq, Lk, n_qt, n_kt, total_items;
+  float scale, scale_log2;
+  const __nv_bfloat16* o; long long ldo;
+  const __nv_bfloat16* d_o; long long lddo;
+  const float* lse;   // [B,H,Lq]
+  float* delta;       // [B,H,Lq]
+  __nv_bfloat16* dq; long long lddq;
+  __nv_bfloat16* dk; long long lddk;
+  __nv_bfloat16* dv; long long lddv;
+};
+
+static constexpr float kLog2e = 1.4426950408889634f;
+
+// p and dS for 32 score columns of one row; writes bf16 into the P / dS tiles.
+__device__ __forceinline__ void bwd_chunk(uint32_t t_s, uint32_t t_dp, int col0, int key0, int pq, bool row_valid,
+                                          float lse2, float delta, float scale, float scale_log2, int row,
+                                          uint8_t* sP, uint8_t* sdS) {
+  uint32_t vs[32], vd[32];
+  tmem_ld_x32(t_s + col0, vs);
+  tmem_ld_x32(t_dp + col0, vd);
+  tmem_ld_wait();
+  float pr[32], ds[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    float pv = exp2f(__uint_as_float(vs[i]) * scale_log2 - lse2);
+    if (!row_valid || (key0 + col0 + i > pq)) pv = 0.0f;
+    pr[i] = pv;
+    ds[i] = pv * (__uint_as_float(vd[i]) - delta) * scale;
+  }
+  if (sP != nullptr) ptile_store32(sP, row, col0, pr);
+  ptile_store32(sdS, row, col0, ds);
+}
+
+// =================================================================================================
+// dQ kernel
+// =================================================================================================
+template <int DH, int SWB>
+struct AttnDqCfg {
+  using T = AttnTile<DH, SWB>;
+  static constexpr int SMEM_BYTES = T::TILE_BYTES * 6 + PT_BYTES + 128 * 4 + 256;
+};
+
+template <int DH, int SWB>
+__global__ void __launch_bounds__(256, 1)
+ot_attn_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                  const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
+                  const __grid_constant__ AttnBwdKParams p) {
+  using T = AttnTile<DH, SWB>;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sQ = smem;
+  uint8_t* sdO = sQ + T::TILE_BYTES;
+  uint8_t* sK = sdO + T::TILE_BYTES;        // [2]
+  uint8_t* sV = sK + 2 * T::TILE_BYTES;     // [2]
+  uint8_t* sdS = sV + 2 * T::TILE_BYTES;
+  float* s_delta = reinterpret_cast<float*>(sdS + PT_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sdS + PT_BYTES + 128 * 4);
+  uint64_t* bar_q = bars;
+  uint64_t* bar_kv = bars + 1;  // [2]
+  uint64_t* bar_s = bars + 3;
+  uint64_t* bar_d = bars + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  const int half = warp >> 2;                 // column half handled by this thread
+  const int row = (warp & 3) * 32 + lane;     // tile row == TMEM lane
+
+  if (tid == 0) {
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmdO);
+    mbar_init(bar_q, 1);
+    mbar_init(&bar_kv[0], 1);
+    mbar_init(&bar_kv[1], 1);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_d, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t t_row = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+
+  constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+  constexpr uint32_t idesc_dq = make_idesc_bf16(128, DH, 0, 1);
+
+  uint32_t n_items_done = 0, blk_count = 0;
+  uint32_t kv_uses[2] = {0, 0};
+  const int off = p.Lk - p.Lq;
+
+  for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+    const int qt = p.n_qt - 1 - (item % p.n_qt);
+    const int bh = item / p.n_qt;
+    const int h = bh % p.H;
+    const int b = bh / p.H;
+    const int q0 = qt * 128;
+    const int q_last = min(q0 + 127, p.Lq - 1);
+    const int nkv = min((p.Lk + 127) / 128, (off + q_last) / 128 + 1);
+    const int pq = off + q0 + row;
+    const bool row_valid = (q0 + row) < p.Lq;
+
+    if (tid == 0) {
+      mbar_arrive_expect_tx(bar_q, 2 * T::TILE_BYTES);
+      load_head_tile<DH, SWB>(sQ, &tmQ, bar_q, h, b, q0);
+      load_head_tile<DH, SWB>(sdO, &tmdO, bar_q, h, b, q0);
+      mbar_arrive_expect_tx(&bar_kv[0], 2 * T::TILE_BYTES);
+      load_head_tile<DH, SWB>(sK, &tmK, &bar_kv[0], h, b, 0);
+      load_head_tile<DH, SWB>(sV, &tmV, &bar_kv[0], h, b, 0);
+    }
+    // delta = rowsum(dO o O) for this row (computed by the half-0 thread, shared through smem)
+    if (half == 0) {
+      float acc = 0.0f;
+      if (row_valid) {
+        const long long grow = (long long)(q0 + row) * p.B + b;
+        const uint4* po = reinterpret_cast<const uint4*>(p.o + grow * p.ldo + h * DH);
+        const uint4* pd = reinterpret_cast<const uint4*>(p.d_o + grow * p.lddo + h * DH);
+#pragma unroll
+        for (int ch = 0; ch < DH / 8; ++ch) {
+          const uint4 a = po[ch], g = pd[ch];
+          acc += bf16lo(a.x) * bf16lo(g.x) + bf16hi(a.x) * bf16hi(g.x) + bf16lo(a.y) * bf16lo(g.y) + bf16hi(a.y) * bf16hi(g.y) +
+                 bf16lo(a.z) * bf16lo(g.z) + bf16hi(a.z) * bf16hi(g.z) + bf16lo(a.w) * bf16lo(g.w) + bf16hi(a.w) * bf16hi(g.w);
+        }
+        p.delta[((long long)b * p.H + h) * p.Lq + q0 + row] = acc;
+      }
+      s_delta[row] = acc;
+    }
+    float lse2 = 0.0f;
+    if (row_valid) lse2 = p.lse[((long long)b * p.H + h) * p.Lq + q0 + row] * kLog2e;
+    __syncthreads();
+    const float delta = s_delta[row];
+
+    for (int j = 0; j < nkv; ++j) {
+      const int st = j & 1;
+      if (tid == 0) {
+        if (j + 1 < nkv) {
+          const int ns = st ^ 1;
+          mbar_arrive_expect_tx(&bar_kv[ns], 2 * T::TILE_BYTES);
+          load_head_tile<DH, SWB>(sK + ns * T::TILE_BYTES, &tmK, &bar_kv[ns], h, b, (j + 1) * 128);
+          load_head_tile<DH, SWB>(sV + ns * T::TILE_BYTES, &tmV, &bar_kv[ns], h, b, (j + 1) * 128);
+        }
+        if (j == 0) mbar_wait(bar_q, n_items_done & 1);
+        mbar_wait(&bar_kv[st], kv_uses[st] & 1);
+        tc_fence_after();
+        const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK + st * T::TILE_BYTES);
+        const uint32_t adO = smem_u32(sdO), aV = smem_u32(sV + st * T::TILE_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < DH / 16; ++kk)
+          umma_bf16_ss(tmem_base, tile_desc_kmajor<DH, SWB>(aQ, kk), tile_desc_kmajor<DH, SWB>(aK, kk), idesc_s, kk != 0);
+#pragma unroll
+        for (int kk = 0; kk < DH / 16; ++kk)
+          umma_bf16_ss(tmem_base + 128, tile_desc_kmajor<DH, SWB>(adO, kk), tile_desc_kmajor<DH, SWB>(aV, kk), idesc_s, kk != 0);
+        umma_commit(bar_s);
+      }
+      kv_uses[st]++;
+      mbar_wait(bar_s, blk_count & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c)
+        bwd_chunk(t_row, t_row + 128, half * 64 + c * 32, j * 128, pq, row_valid, lse2, delta, p.scale, p.scale_log2, row, nullptr, sdS);
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+        const uint32_t adS = smem_u32(sdS), aK = smem_u32(sK + st * T::TILE_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)
+          umma_bf16_ss(tmem_base + 256, ptile_desc_kmajor(adS, kk), tile_desc_mnmajor<DH, SWB>(aK, kk), idesc_dq, (j | kk) != 0);
+        umma_commit(bar_d);
+      }
+      mbar_wait(bar_d, blk_count & 1);
+      tc_fence_after();
+      ++blk_count;
+    }
+    // ---- dQ tile -> global (32-column chunks alternate between the two halves) ----
+#pragma unroll
+    for (int c = 0; c < DH / 32; ++c) {
+      if ((c & 1) == half) {
+        uint32_t v[32];
+        tmem_ld_x32(t_row + 256 + c * 32, v);
+        tmem_ld_wait();
+        if (row_valid) {
+          __nv_bfloat16* dst = p.dq + ((long long)(q0 + row) * p.B + b) * p.lddq + h * DH + c * 32;
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch) {
+            uint4 q;
+            q.x = pack_bf16x2(__uint_as_float(v[ch * 8 + 0]), __uint_as_float(v[ch * 8 + 1]));
+            q.y = pack_bf16x2(__uint_as_float(v[ch * 8 + 2]), __uint_as_float(v[ch * 8 + 3]));
+            q.z = pack_bf16x2(__uint_as_float(v[ch * 8 + 4]), __uint_as_float(v[ch * 8 + 5]));
+            q.w = pack_bf16x2(__uint_as_float(v[ch * 8 + 6]), __uint_as_float(v[ch * 8 + 7]));
+            *reinterpret_cast<uint4*>(dst + ch * 8) = q;
+          }
+        }
+      }
+    }
+    ++n_items_done;
+    tc_fence_before();
+    __syncthreads();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+// =================================================================================================
+// dK/dV kernel
+// =================================================================================================
+template <int DH, int SWB>
+struct AttnDkvCfg {
+  using T = AttnTile<DH, SWB>;
+  static constexpr int SMEM_BYTES = T::TILE_BYTES * 6 + 2 * PT_BYTES + 256;
+};
+
+template <int DH, int SWB>
+__global__ void __launch_bounds__(256, 1)
+ot_attn_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                   const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
+                   const __grid_constant__ AttnBwdKParams p) {
+  using T = AttnTile<DH, SWB>;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sK = smem;
+  uint8_t* sV = sK + T::TILE_BYTES;
+  uint8_t* sQ = sV + T::TILE_BYTES;          // [2]
+  uint8_t* sdO = sQ + 2 * T::TILE_BYTES;     // [2]
+  uint8_t* sP = sdO + 2 * T::TILE_BYTES;
+  uint8_t* sdS = sP + PT_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sdS + PT_BYTES);
+  uint64_t* bar_kv = bars;
+  uint64_t* bar_q = bars + 1;   // [2]
+  uint64_t* bar_s = bars + 3;
+  uint64_t* bar_d = bars + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  const int half = warp >> 2;
+  const int row = (warp & 3) * 32 + lane;
+
+  if (tid == 0) {
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmdO);
+    mbar_init(bar_kv, 1);
+    mbar_init(&bar_q[0], 1);
+    mbar_init(&bar_q[1], 1);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_d, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t t_row = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+  constexpr uint32_t T_DV = 256, T_DK = 256 + DH;
+
+  constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+  constexpr uint32_t idesc_t = make_idesc_bf16(128, DH, 1, 1);   // both operands MN-major
+
+  uint32_t n_items_done = 0, blk_count = 0;
+  uint32_t q_uses[2] = {0, 0};
+  const int off = p.Lk - p.Lq;
+
+  for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+    const int kt = item % p.n_kt;   // early key tiles are seen by the most query tiles -> first
+    const int bh = item / p.n_kt;
+    const int h = bh % p.H;
+    const int b = bh / p.H;
+    const int k0 = kt * 128;
+    int i_min = (k0 - off) / 128;
+    if (k0 - off < 0) i_min = 0;
+    const int n_i = p.n_qt - i_min;
+
+    if (tid == 0) {
+      mbar_arrive_expect_tx(bar_kv, 2 * T::TILE_BYTES);
+      load_head_tile<DH, SWB>(sK, &tmK, bar_kv, h, b, k0);
+      load_head_tile<DH, SWB>(sV, &tmV, bar_kv, h, b, k0);
+      mbar_arrive_expect_tx(&bar_q[0], 2 * T::TILE_BYTES);
+      load_head_tile<DH, SWB>(sQ, &tmQ, &bar_q[0], h, b, i_min * 128);
+      load_head_tile<DH, SWB>(sdO, &tmdO, &bar_q[0], h, b, i_min * 128);
+    }
+
+    for (int ii = 0; ii < n_i; ++ii) {
+      const int q0 = (i_min + ii) * 128;
+      const int st = ii & 1;
+      if (tid == 0) {
+        if (ii + 1 < n_i) {
+          const int ns = st ^ 1;
+          mbar_arrive_expect_tx(&bar_q[ns], 2 * T::TILE_BYTES);
+          load_head_tile<DH, SWB>(sQ + ns * T::TILE_BYTES, &tmQ, &bar_q[ns], h, b, q0 + 128);
+          load_head_tile<DH, SWB>(sdO + ns * T::TILE_BYTES, &tmdO, &bar_q[ns], h, b, q0 + 128);
+        }
+        if (ii == 0) mbar_wait(bar_kv, n_items_done & 1);
+        mbar_wait(&bar_q[st], q_uses[st] & 1);
+        tc_fence_after();
+        const uint32_t aQ = smem_u32(sQ + st * T::TILE_BYTES), aK = smem_u32(sK);
+        const uint32_t adO = smem_u32(sdO + st * T::TILE_BYTES), aV = smem_u32(sV);
+#pragma unroll
+        for (int kk = 0; kk < DH / 16; ++kk)
+          umma_bf16_ss(tmem_base, tile_desc_kmajor<DH, SWB>(aQ, kk), tile_desc_kmajor<DH, SWB>(aK, kk), idesc_s, kk != 0);
+#pragma unroll
+        for (int kk = 0; kk < DH / 16; ++kk)
+          umma_bf16_ss(tmem_base + 128, tile_desc_kmajor<DH, SWB>(adO, kk), tile_desc_kmajor<DH, SWB>(aV, kk), idesc_s, kk != 0);
+        umma_commit(bar_s);
+      }
+      q_uses[st]++;
+      const bool row_valid = (q0 + row) < p.Lq;
+      const int pq = off + q0 + row;
+      float lse2 = 0.0f, delta = 0.0f;
+      if (row_valid) {
+        const long long si = ((long long)b * p.H + h) * p.Lq + q0 + row;
+        lse2 = p.lse[si] * kLog2e;
+        delta = p.delta[si];
+      }
+      mbar_wait(bar_s, blk_count & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c)
+        bwd_chunk(t_row, t_row + 128, half * 64 + c * 32, k0, pq, row_valid, lse2, delta, p.scale, p.scale_log2, row, sP, sdS);
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+        const uint32_t aP = smem_u32(sP), adS = smem_u32(sdS);
+        const uint32_t aQ = smem_u32(sQ + st * T::TILE_BYTES), adO = smem_u32(sdO + st * T::TILE_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)   // dV[key, e] += sum_q P[q, key] dO[q, e]
+          umma_bf16_ss(tmem_base + T_DV, ptile_desc_mnmajor(aP, kk), tile_desc_mnmajor<DH, SWB>(adO, kk), idesc_t, (ii | kk) != 0);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)   // dK[key, e] += sum_q dS[q, key] Q[q, e]
+          umma_bf16_ss(tmem_base + T_DK, ptile_desc_mnmajor(adS, kk), tile_desc_mnmajor<DH, SWB>(aQ, kk), idesc_t, (ii | kk) != 0);
+        umma_commit(bar_d);
+      }
+      mbar_wait(bar_d, blk_count & 1);
+      tc_fence_after();
+      ++blk_count;
+    }
+
+    // ---- dV, dK tiles -> global; thread row == key index inside the tile ----
+    const bool key_valid = (k0 + row) < p.Lk;
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+#pragma unroll
+      for (int c = 0; c < DH / 32; ++c) {
+        if ((c & 1) == half) {
+          uint32_t v[32];
+          tmem_ld_x32(t_row + (which == 0 ? T_DV : T_DK) + c * 32, v);
+          tmem_ld_wait();
+          if (key_valid) {
+            __nv_bfloat16* base = which == 0 ? p.dv : p.dk;
+            const long long ld = which == 0 ? p.lddv : p.lddk;
+            __nv_bfloat16* dst = base + ((long long)(k0 + row) * p.B + b) * ld + h * DH + c * 32;
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) {
+              uint4 q;
+              q.x = pack_bf16x2(__uint_as_float(v[ch * 8 + 0]), __uint_as_float(v[ch * 8 + 1]));
+              q.y = pack_bf16x2(__uint_as_float(v[ch * 8 + 2]), __uint_as_float(v[ch * 8 + 3]));
+              q.z = pack_bf16x2(__uint_as_float(v[ch * 8 + 4]), __uint_as_float(v[ch * 8 + 5]));
+              q.w = pack_bf16x2(__uint_as_float(v[ch * 8 + 6]), __uint_as_float(v[ch * 8 + 7]));
+              *reinterpret_cast<uint4*>(dst + ch * 8) = q;
+            }
+          }
+        }
+      }
+    }
+    ++n_items_done;
+    tc_fence_before();
+    __syncthreads();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+// =================================================================================================
+// host
+// =================================================================================================
+int make_head_tmap(CUtensorMap* tm, const void* base, int cols, int B, int L, long long ld, int swb);
+
+template <int DH, int SWB>
+static int launch_attn_bwd(const CUtensorMap* tm, AttnBwdKParams kp, cudaStream_t st) {
+  static bool attr_done = false;
+  auto kdq = ot_attn_dq_kernel<DH, SWB>;
+  auto kdkv = ot_attn_dkv_kernel<DH, SWB>;
+  if (!attr_done) {
+    OT_CUDA_CHECK(cudaFuncSetAttribute(kdq, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnDqCfg<DH, SWB>::SMEM_BYTES));
+    OT_CUDA_CHECK(cudaFuncSetAttribute(kdkv, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnDkvCfg<DH, SWB>::SMEM_BYTES));
+    attr_done = true;
+  }
+  const int sms = num_sms();
+  kp.total_items = kp.n_qt * kp.H * kp.B;
+  int grid = kp.total_items < sms ? kp.total_items : sms;
+  kdq<<<grid, 256, AttnDqCfg<DH, SWB>::SMEM_BYTES, st>>>(tm[0], tm[1], tm[2], tm[3], kp);
+  OT_CUDA_CHECK(cudaGetLastError());
+  kp.total_items = kp.n_kt * kp.H * kp.B;
+  grid = kp.total_items < sms ? kp.total_items : sms;
+  kdkv<<<grid, 256, AttnDkvCfg<DH, SWB>::SMEM_BYTES, st>>>(tm[0], tm[1], tm[2], tm[3], kp);
+  OT_CUDA_CHECK(cudaGetLastError());
+  return OT_OK;
+}
+
+int attn_bwd_impl(const ot_attn_params* p, cudaStream_t st) {
+  if (!p || !p->q || !p->k || !p->v || !p->o || !p->lse || !p->d_o || !p->dq || !p->dk || !p->dv || !p->delta)
+    OT_FAIL(OT_ERR_INVALID_ARG, "ot_attn_bwd: null pointer");
+  if (p->Lq <= 0 || p->Lk < p->Lq || p->B <= 0 || p->H <= 0) OT_FAIL(OT_ERR_INVALID_ARG, "ot_attn_bwd: bad sizes");
+  if (p->head_dim != 64 && p->head_dim != 96) OT_FAIL(OT_ERR_UNSUPPORTED_SHAPE, "ot_attn_bwd: head_dim=%d (64 and 96 are built)", p->head_dim);
+  if ((p->ldq % 8) || (p->ldk % 8) || (p->ldv % 8) || (p->ldo % 8) || (p->lddo % 8) || (p->lddq % 8) || (p->lddk % 8) || (p->lddv % 8))
+    OT_FAIL(OT_ERR_UNSUPPORTED_SHAPE, "ot_attn_bwd: leading dimensions must be multiples of 8");
+  const int swb = (p->head_dim == 64 && p->swizzle != 64) ? 128 : 64;
+  const int cols = p->H * p->head_dim;
+  CUtensorMap tm[4];
+  int rc;
+  if ((rc = make_head_tmap(&tm[0], p->q, cols, p->B, p->Lq, p->ldq, swb))) return rc;
+  if ((rc = make_head_tmap(&tm[1], p->k, cols, p->B, p->Lk, p->ldk, swb))) return rc;
+  if ((rc = make_head_tmap(&tm[2], p->v, cols, p->B, p->Lk, p->ldv, swb))) return rc;
+  if ((rc = make_head_tmap(&tm[3], p->d_o, cols, p->B, p->Lq, p->lddo, swb))) return rc;
+  AttnBwdKParams kp;
+  memset(&kp, 0, sizeof(kp));
+  kp.B = p->B; kp.H = p->H; kp.Lq = p->Lq; kp.Lk = p->Lk;
+  kp.n_qt = (p->Lq + 127) / 128; kp.n_kt = (p->Lk + 127) / 128;
+  kp.scale = 1.0f / sqrtf((float)p->head_dim);
+  kp.scale_log2 = kp.scale * kLog2e;
+  kp.o = (const __nv_bfloat16*)p->o; kp.ldo = p->ldo; kp.d_o = (const __nv_bfloat16*)p->d_o; kp.lddo = p->lddo;
+  kp.lse = p->lse; kp.delta = p->delta;
+  kp.dq = (__nv_bfloat16*)p->dq; kp.lddq = p->lddq; kp.dk = (__nv_bfloat16*)p->dk; kp.lddk = p->lddk;
+  kp.dv = (__nv_bfloat16*)p->dv; kp.lddv = p->lddv;
+  if (p->head_dim == 64) {
+    if (swb == 128) return launch_attn_bwd<64, 128>(tm, kp, st);
+    return launch_attn_bwd<64, 64>(tm, kp, st);
+  }
+  return launch_attn_bwd<96, 64>(tm, kp, st);
+}
+
+}  // namespace ot

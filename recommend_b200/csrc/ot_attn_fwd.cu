@@ -1,0 +1,274 @@
+// ot_attn_fwd.cu — causal attention forward with pyramid query pruning, sm_100a tcgen05.
+//
+// Replaces the einsum / where / softmax / einsum of MixedMHA.call (OT/model.py:101-114): only the
+// retained query tail is computed, the [B,H,Lq,Lk] score tensor never exists.
+//
+// One CTA (128 threads, thread r owns query row r of the tile) walks a static list of work items
+// (query tile, head, sample).  Per 128-key block:
+//     S  = Q K^T      tcgen05.mma  (M=128, N=128, K=DH)      -> TMEM columns [0,128)
+//     online softmax  tcgen05.ld, fp32 exp2, running max / sum in registers
+//     P  -> bf16 -> swizzled smem (K-major A operand)
+//     PV = P V        tcgen05.mma  (M=128, N=DH,  K=128, V used MN-major as loaded) -> TMEM [128,128+DH)
+//     O += PV (registers, rescaled by the running max)
+// K/V blocks are TMA-prefetched one block ahead.  256 TMEM columns and <=113 KB smem per CTA let two
+// CTAs share an SM, so one CTA's softmax overlaps the other's MMAs.
+#include "ot_attn.cuh"
+#include "ot_host.h"
+#include "../../include/onetrans_b200.h"
+
+namespace ot {
+
+struct AttnFwdKParams {
+  int B, H, Lq, Lk, n_qt, total_items;
+  float scale, scale_log2;
+  __nv_bfloat16* o; long long ldo;
+  float* lse;  // [B, H, Lq]
+};
+
+template <int DH, int SWB, int KVS>
+struct AttnFwdCfg {
+  using T = AttnTile<DH, SWB>;
+  static constexpr int SMEM_BYTES = T::TILE_BYTES * (1 + 2 * KVS) + PT_BYTES + 256;
+  static constexpr int TMEM_COLS = 256;
+};
+
+template <int DH, int SWB, int KVS>
+__global__ void __launch_bounds__(128, 2)
+ot_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                   const __grid_constant__ CUtensorMap tmV, const __grid_constant__ AttnFwdKParams p) {
+  using T = AttnTile<DH, SWB>;
+  using Cfg = AttnFwdCfg<DH, SWB, KVS>;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + T::TILE_BYTES;                 // [KVS]
+  uint8_t* sV = sK + KVS * T::TILE_BYTES;           // [KVS]
+  uint8_t* sP = sV + KVS * T::TILE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + PT_BYTES);
+  uint64_t* bar_q = bars;          // Q tile landed
+  uint64_t* bar_kv = bars + 1;     // [KVS] K+V block landed
+  uint64_t* bar_s = bars + 3;      // S MMA complete
+  uint64_t* bar_pv = bars + 4;     // PV MMA complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+
+  if (tid == 0) {
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(bar_q, 1);
+    for (int i = 0; i < KVS; ++i) mbar_init(&bar_kv[i], 1);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_pv, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t t_S = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+  const uint32_t t_PV = t_S + 128;
+
+  constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+  constexpr uint32_t idesc_pv = make_idesc_bf16(128, DH, 0, 1);   // V is MN-major
+
+  uint32_t n_items_done = 0;   // phase of bar_q
+  uint32_t kv_uses[2] = {0, 0};  // completed uses per K/V stage
+  uint32_t blk_count = 0;      // phase of bar_s / bar_pv
+  const int off = p.Lk - p.Lq;
+
+  for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+    const int qt = p.n_qt - 1 - (item % p.n_qt);  // long tiles first
+    const int bh = item / p.n_qt;
+    const int h = bh % p.H;
+    const int b = bh / p.H;
+    const int q0 = qt * 128;
+    const int q_last = min(q0 + 127, p.Lq - 1);
+    const int nkv = min((p.Lk + 127) / 128, (off + q_last) / 128 + 1);
+    const int pq = off + q0 + tid;  // absolute position of this thread's query
+
+    if (tid == 0) {
+      mbar_arrive_expect_tx(bar_q, T::TILE_BYTES);
+      load_head_tile<DH, SWB>(sQ, &tmQ, bar_q, h, b, q0);
+      mbar_arrive_expect_tx(&bar_kv[0], 2 * T::TILE_BYTES);
+      load_head_tile<DH, SWB>(sK, &tmK, &bar_kv[0], h, b, 0);
+      load_head_tile<DH, SWB>(sV, &tmV, &bar_kv[0], h, b, 0);
+    }
+
+    float m_run = -INFINITY, l_run = 0.0f;
+    float o_acc[DH];
+#pragma unroll
+    for (int i = 0; i < DH; ++i) o_acc[i] = 0.0f;
+
+    for (int j = 0; j < nkv; ++j) {
+      const int st = (KVS == 2) ? (j & 1) : 0;
+      if (tid == 0) {
+        if (KVS == 2 && j + 1 < nkv) {  // prefetch the next block into the other stage (its PV finished last iteration)
+          const int ns = st ^ 1;
+          mbar_arrive_expect_tx(&bar_kv[ns], 2 * T::TILE_BYTES);
+          load_head_tile<DH, SWB>(sK + ns * T::TILE_BYTES, &tmK, &bar_kv[ns], h, b, (j + 1) * 128);
+          load_head_tile<DH, SWB>(sV + ns * T::TILE_BYTES, &tmV, &bar_kv[ns], h, b, (j + 1) * 128);
+        }
+        if (j == 0) mbar_wait(bar_q, n_items_done & 1);
+        mbar_wait(&bar_kv[st], kv_uses[st] & 1);
+        tc_fence_after();
+        const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK + st * T::TILE_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < DH / 16; ++kk)
+          umma_bf16_ss(tmem_base, tile_desc_kmajor<DH, SWB>(aQ, kk), tile_desc_kmajor<DH, SWB>(aK, kk), idesc_s, kk != 0);
+        umma_commit(bar_s);
+      }
+      kv_uses[st]++;
+      mbar_wait(bar_s, blk_count & 1);
+      tc_fence_after();
+
+      // ---- online softmax over the 128 scores of this row ----
+      const bool need_mask = (j * 128 + 127 > pq);
+      float m_new = m_run;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld_x32(t_S + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float s = __uint_as_float(v[i]);
+          if (need_mask && (j * 128 + c * 32 + i > pq)) s = -INFINITY;
+          m_new = fmaxf(m_new, s);
+        }
+      }
+      const float alpha = exp2f((m_run - m_new) * p.scale_log2);
+      const float mb = m_new * p.scale_log2;
+      float rowsum = 0.0f;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld_x32(t_S + c * 32, v);
+        tmem_ld_wait();
+        float pr[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float e = exp2f(__uint_as_float(v[i]) * p.scale_log2 - mb);
+          if (need_mask && (j * 128 + c * 32 + i > pq)) e = 0.0f;
+          pr[i] = e;
+          rowsum += e;
+        }
+        ptile_store32(sP, tid, c * 32, pr);
+      }
+      l_run = l_run * alpha + rowsum;
+      m_run = m_new;
+#pragma unroll
+      for (int i = 0; i < DH; ++i) o_acc[i] *= alpha;
+
+      fence_proxy_async_smem();   // P (generic-proxy stores) -> visible to tcgen05.mma
+      tc_fence_before();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+        const uint32_t aP = smem_u32(sP), aV = smem_u32(sV + st * T::TILE_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)
+          umma_bf16_ss(tmem_base + 128, ptile_desc_kmajor(aP, kk), tile_desc_mnmajor<DH, SWB>(aV, kk), idesc_pv, kk != 0);
+        umma_commit(bar_pv);
+        if (KVS == 1 && j + 1 < nkv) {
+          // single K/V stage: the next block can only be fetched once this block's MMAs have read it
+          mbar_wait(bar_pv, blk_count & 1);
+          mbar_arrive_expect_tx(&bar_kv[0], 2 * T::TILE_BYTES);
+          load_head_tile<DH, SWB>(sK, &tmK, &bar_kv[0], h, b, (j + 1) * 128);
+          load_head_tile<DH, SWB>(sV, &tmV, &bar_kv[0], h, b, (j + 1) * 128);
+        }
+      }
+      mbar_wait(bar_pv, blk_count & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < DH / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_x32(t_PV + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] += __uint_as_float(v[i]);
+      }
+      ++blk_count;
+      tc_fence_before();
+    }
+
+    // ---- write O (bf16) and the log-sum-exp of the scaled scores ----
+    if (q0 + tid < p.Lq) {
+      const float inv = 1.0f / l_run;
+      __nv_bfloat16* orow = p.o + ((long long)(q0 + tid) * p.B + b) * p.ldo + h * DH;
+#pragma unroll
+      for (int ch = 0; ch < DH / 8; ++ch) {
+        uint4 q;
+        q.x = pack_bf16x2(o_acc[ch * 8 + 0] * inv, o_acc[ch * 8 + 1] * inv);
+        q.y = pack_bf16x2(o_acc[ch * 8 + 2] * inv, o_acc[ch * 8 + 3] * inv);
+        q.z = pack_bf16x2(o_acc[ch * 8 + 4] * inv, o_acc[ch * 8 + 5] * inv);
+        q.w = pack_bf16x2(o_acc[ch * 8 + 6] * inv, o_acc[ch * 8 + 7] * inv);
+        *reinterpret_cast<uint4*>(orow + ch * 8) = q;
+      }
+      p.lse[((long long)b * p.H + h) * p.Lq + q0 + tid] = m_run * p.scale + logf(l_run);
+    }
+    ++n_items_done;
+    __syncthreads();  // every thread is past its last TMEM / smem read before the next item's loads
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+template <int DH, int SWB, int KVS>
+static int launch_attn_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnFwdKParams& kp, cudaStream_t st) {
+  using Cfg = AttnFwdCfg<DH, SWB, KVS>;
+  static bool attr_done = false;
+  auto kern = ot_attn_fwd_kernel<DH, SWB, KVS>;
+  if (!attr_done) {
+    OT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_done = true;
+  }
+  const int max_ctas = 2 * num_sms();
+  const int grid = kp.total_items < max_ctas ? kp.total_items : max_ctas;
+  kern<<<grid, 128, Cfg::SMEM_BYTES, st>>>(tq, tk, tv, kp);
+  OT_CUDA_CHECK(cudaGetLastError());
+  return OT_OK;
+}
+
+// rank-3 map over a token-major buffer: dims (cols, B, L), box (slab cols, 1, 128 rows)
+int make_head_tmap(CUtensorMap* tm, const void* base, int cols, int B, int L, long long ld, int swb) {
+  uint64_t dims[3] = {(uint64_t)cols, (uint64_t)B, (uint64_t)L};
+  uint64_t str[2] = {(uint64_t)ld * 2, (uint64_t)ld * 2 * (uint64_t)B};
+  uint32_t box[3] = {(uint32_t)(swb / 2), 1, 128};
+  return make_tmap_bf16(tm, base, 3, dims, str, box, swb);
+}
+
+int attn_fwd_impl(const ot_attn_params* p, cudaStream_t st) {
+  if (!p || !p->q || !p->k || !p->v || !p->o || !p->lse) OT_FAIL(OT_ERR_INVALID_ARG, "ot_attn_fwd: null pointer");
+  if (p->Lq <= 0 || p->Lk < p->Lq || p->B <= 0 || p->H <= 0) OT_FAIL(OT_ERR_INVALID_ARG, "ot_attn_fwd: bad sizes B=%d H=%d Lq=%d Lk=%d", p->B, p->H, p->Lq, p->Lk);
+  if (p->head_dim != 64 && p->head_dim != 96) OT_FAIL(OT_ERR_UNSUPPORTED_SHAPE, "ot_attn_fwd: head_dim=%d (64 and 96 are built)", p->head_dim);
+  if ((p->ldq % 8) || (p->ldk % 8) || (p->ldv % 8) || (p->ldo % 8)) OT_FAIL(OT_ERR_UNSUPPORTED_SHAPE, "ot_attn_fwd: leading dimensions must be multiples of 8");
+  const int swb = (p->head_dim == 64 && p->swizzle != 64) ? 128 : 64;
+  const int cols = p->H * p->head_dim;
+  CUtensorMap tq, tk, tv;
+  int rc;
+  if ((rc = make_head_tmap(&tq, p->q, cols, p->B, p->Lq, p->ldq, swb))) return rc;
+  if ((rc = make_head_tmap(&tk, p->k, cols, p->B, p->Lk, p->ldk, swb))) return rc;
+  if ((rc = make_head_tmap(&tv, p->v, cols, p->B, p->Lk, p->ldv, swb))) return rc;
+  AttnFwdKParams kp;
+  kp.B = p->B; kp.H = p->H; kp.Lq = p->Lq; kp.Lk = p->Lk; kp.n_qt = (p->Lq + 127) / 128;
+  kp.total_items = kp.n_qt * p->H * p->B;
+  kp.scale = 1.0f / sqrtf((float)p->head_dim);
+  kp.scale_log2 = kp.scale * 1.4426950408889634f;
+  kp.o = (__nv_bfloat16*)p->o; kp.ldo = p->ldo; kp.lse = p->lse;
+  if (p->head_dim == 64) {
+    if (swb == 128) return launch_attn_fwd<64, 128, 2>(tq, tk, tv, kp, st);
+    return launch_attn_fwd<64, 64, 2>(tq, tk, tv, kp, st);
+  }
+  return launch_attn_fwd<96, 64, 1>(tq, tk, tv, kp, st);
+}
+
+}  // namespace ot
