@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the OneTrans hot path on B200 (contract in the task statement).
+
+Metric (BASELINE.json): OneTrans samples/sec, fwd+bwd bf16.  Workload at N GPUs (weak scaling, batch is the
+shard): BASELINE config 2 — OneTrans-S, batch 2048 per GPU, 512 S + 32 NS tokens, pyramid pruning
+``linear_to_ns`` down to the NS tokens — one step = zero grads + forward + BCE + backward (+ gradient
+all-reduce over NCCL when N > 1).
+
+  python bench.py --gpus 1 --steps 10 --warmup 3
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+  python bench.py --impl reference ...      (CPU oracle port on the host cores; rank 0 only)
+
+Prints ONE JSON line (rank 0).  `value` = device-resident inputs; `e2e` = same step fed from pinned host
+buffers through the public module API with the loss read back every step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+
+def workload(name: str):
+    """BASELINE.json configs made concrete."""
+    if name == 'c2':   # OneTrans-S training, B 2048, 512 S + 32 NS
+        return dict(model='small', B=2048, seq_lens=(170, 170, 170), L_ns=32, schedule='linear_to_ns')
+    if name == 'c3':   # OneTrans-L (d 384, 8 blocks), B 2048 per GPU
+        return dict(model='default', B=2048, seq_lens=(170, 170, 170), L_ns=32, schedule='linear_to_ns')
+    if name == 'c4':   # long sequence, halving schedule
+        return dict(model='small', B=256, seq_lens=(672, 672, 672), L_ns=32, schedule='halving')
+    if name == 'c1':   # the reference's CPU-runnable case
+        return dict(model='small', B=32, seq_lens=(86, 84, 84), L_ns=16, schedule='reference_ratio')
+    raise ValueError(name)
+
+
+def fwd_flops_per_sample(d, F, H, n_layers, L0, keep_lens, L_s_events, n_ns_feat, L_ns, E=64):
+    """Algorithmic forward FLOPs per sample: discarded work is not counted."""
+    tot = 0.0
+    cur = L0
+    for keep in keep_lens:
+        pairs = keep * cur - keep * (keep - 1) / 2.0
+        tot += 4.0 * cur * d * d + 2.0 * keep * d * d + 4.0 * d * pairs + 2.0 * keep * d * d + 4.0 * keep * d * F
+        cur = keep
+    tot += 2.0 * L_s_events * E * d + 2.0 * n_ns_feat * d * L_ns
+    return tot
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, gpu_index: int):
+        self.rows = []
+        self.proc = None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--id={self.gpu_index}', f'--query-gpu={q}', '--format=csv,noheader,nounits',
+                                          '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            parts = [x.strip() for x in r.split(',')]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); smax.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(smax) if smax else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=p['hbm_gbs'], tf_burst=p['bf16_tflops'], tf_sustained=p.get('bf16_tflops_sustained', p['bf16_tflops']), src='measured')
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src='fallback')
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port timed on the host cores (cpu_baseline, and --impl reference)
+# ---------------------------------------------------------------------------------------------------
+
+def cpu_oracle_samples_per_sec(wl, sample_B: int, steps: int, warmup: int):
+    from oracle import onetrans_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    ocfg = O.small_config(num_ns_tokens=wl['L_ns']) if wl['model'] == 'small' else O.default_config(num_ns_tokens=wl['L_ns'])
+    ocfg.dropout_rate = 0.0
+    L0 = sum(wl['seq_lens']) + 2 + wl['L_ns']
+    ocfg.pyramid_keep_lens = resolve_schedule(wl, ocfg.num_layers, L0)
+    P = O.init_params(ocfg, seed=0)
+    non_seq, seq, labels = O.synthetic_batch(ocfg, sample_B, wl['seq_lens'], seed=1234)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        O.loss_and_grads(P, ocfg, non_seq, seq, labels)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    total = sum(times)
+    return sample_B * len(times) / total, total / len(times) * 1e3, torch.get_num_threads()
+
+
+def resolve_schedule(wl, n_layers, L0):
+    from recommend_b200.schedule import keep_lens_halving, keep_lens_linear_to_ns, keep_lens_reference_ratio
+    if wl['schedule'] == 'linear_to_ns':
+        return keep_lens_linear_to_ns(L0, n_layers, wl['L_ns'])
+    if wl['schedule'] == 'halving':
+        return keep_lens_halving(L0, n_layers, wl['L_ns'])
+    return keep_lens_reference_ratio(L0, n_layers, [0.5, 0.3, 0.2, 0.1, 0.05, 0.03, 0.02, 0.01])
+
+
+def run_reference_arm(args, wl, rank):
+    if rank != 0:
+        return
+    sample_B = args.cpu_sample_batch
+    v, ms, cores = cpu_oracle_samples_per_sec(wl, sample_B, max(1, args.steps), max(0, args.warmup))
+    line = {
+        'impl': 'reference', 'metric': 'OneTrans samples/sec (fwd+bwd)', 'value': v, 'unit': 'samples/s', 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': config_dict(args, wl, sample_B),
+        'cpu_baseline': {'value': v, 'unit': 'samples/s', 'cores': cores, 'kind': 'port',
+                         'sample': f'oracle (PyTorch CPU fp32 restatement of OT/model.py; TensorFlow reference not installable) fwd+BCE+bwd on {sample_B} '
+                                   f'samples of the same workload per step'},
+        'e2e': {'value': v, 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def config_dict(args, wl, B):
+    return {'workload': f"{args.workload}: OneTrans-{'S' if wl['model'] == 'small' else 'L'} fwd+BCE+bwd, batch {B}/GPU, "
+                        f"{sum(wl['seq_lens']) + 2} S + {wl['L_ns']} NS tokens, schedule {wl['schedule']}",
+            'global_batch': B * args.gpus, 'seq_tokens': sum(wl['seq_lens']) + 2, 'ns_tokens': wl['L_ns'],
+            'parallelism': f'dp{args.gpus}', 'dropout': 0.0, 'optimizer': 'none (metric is fwd+bwd)',
+            'l2_policy': 'activations per step (>20 GB) far exceed the 126 MB L2; no explicit flush'}
+
+
+# ---------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='c2')
+    ap.add_argument('--batch', type=int, default=0, help='override per-GPU batch')
+    ap.add_argument('--cpu-sample-batch', type=int, default=8)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-kernel-profile', action='store_true')
+    args = ap.parse_args()
+
+    wl = workload(args.workload)
+    if args.batch:
+        wl['B'] = args.batch
+    rank = int(os.environ.get('RANK', 0))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+
+    if args.impl == 'reference':
+        run_reference_arm(args, wl, rank)
+        return
+
+    import torch.distributed as dist
+    import recommend_b200 as R
+    from recommend_b200 import _lib, ops
+    from recommend_b200.train import FlatGradBuffer, bce_loss, train_step
+    from oracle import onetrans_oracle as O  # synthetic input generator only (and the cpu_baseline leg below)
+
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device; the product path has no CPU fallback')
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    dev = torch.device('cuda', local_rank)
+
+    cfg = R.get_model_config(wl['model'])
+    cfg.num_ns_tokens = wl['L_ns']
+    cfg.pyramid_schedule = wl['schedule']
+    cfg.dropout_rate = 0.0
+    torch.manual_seed(0)
+    model = R.OneTransModel(cfg).to(dev)
+    grads = FlatGradBuffer(model.parameters())
+
+    B = wl['B']
+    ocfg = O.small_config(num_ns_tokens=wl['L_ns']) if wl['model'] == 'small' else O.default_config(num_ns_tokens=wl['L_ns'])
+    non_seq, seq, labels = O.synthetic_batch(ocfg, B, wl['seq_lens'], seed=1234 + rank)
+    # host (pinned) copies for the e2e arm; device copies for the device-resident arm
+    h_ns = {k: v.pin_memory() for k, v in non_seq.items()}
+    h_seq = {k: v.to(torch.bfloat16).pin_memory() for k, v in seq.items()}
+    h_lab = {k: v.pin_memory() for k, v in labels.items()}
+    d_ns = {k: v.to(dev) for k, v in h_ns.items()}
+    d_seq = {k: v.to(dev) for k, v in h_seq.items()}
+    d_lab = {k: v.to(dev) for k, v in h_lab.items()}
+    h2d_bytes = sum(v.numel() * v.element_size() for d_ in (h_ns, h_seq, h_lab) for v in d_.values())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        return train_step(model, grads, d_ns, d_seq, d_lab, world)
+
+    def step_e2e():
+        ns = {k: v.to(dev, non_blocking=True) for k, v in h_ns.items()}
+        sq = {k: v.to(dev, non_blocking=True) for k, v in h_seq.items()}
+        lb = {k: v.to(dev, non_blocking=True) for k, v in h_lab.items()}
+        loss = train_step(model, grads, ns, sq, lb, world)
+        return float(loss)     # device->host read of the step's result
+
+    # ---- device-resident timing ----
+    for _ in range(max(3, args.warmup)):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.launch_count
+    prof = None if args.no_kernel_profile else ops.KernelProfiler()
+    ops.set_profiler(prof)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        loss = step_device()
+    e1.record()
+    barrier()
+    ops.set_profiler(None)
+    ms_total = e0.elapsed_time(e1)
+    launches = _lib.launch_count - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms_total], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    value = B * world / (ms_step * 1e-3)
+
+    # ---- end-to-end timing (host buffers -> public API -> loss on host) ----
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step_e2e()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = B * world / (float(t.item()) / args.steps * 1e-3)
+
+    if rank == 0:
+        peaks = measured_peaks()
+        L0 = sum(wl['seq_lens']) + 2 + wl['L_ns']
+        keep = R.resolve_keep_lens(cfg, L0)
+        fwd_fl = fwd_flops_per_sample(cfg.hidden_dim, cfg.ffn_dim, cfg.num_heads, cfg.num_layers, L0, keep, sum(wl['seq_lens']),
+                                      len(cfg.ns_features), wl['L_ns'])
+        step_tflop = 3.0 * fwd_fl * B / 1e12
+        line = {
+            'metric': 'OneTrans samples/sec (fwd+bwd bf16)', 'value': value, 'unit': 'samples/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': max(3, args.warmup), 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'bf16', 'data': 'synthetic', 'config': config_dict(args, wl, B),
+            'clocks': clocks,
+            'e2e': {'value': e2e_value, 'unit': 'samples/s', 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': 4},
+            'gpu_launches': launches,
+            'loss': float(loss),
+            'model_flops': {'algorithmic_tflop_per_step_per_gpu': step_tflop, 'achieved_tflops_per_gpu': step_tflop / (ms_step * 1e-3),
+                            'frac_of_bf16_sustained_peak': step_tflop / (ms_step * 1e-3) / peaks['tf_sustained'], 'peak_source': peaks['src']},
+        }
+        if prof is not None:
+            summ = prof.summary()
+            fam = {}
+            for (name, tag), d_ in summ.items():
+                f = fam.setdefault(name, dict(launches=0, ms=0.0, flops=0.0, bytes=0.0))
+                for k in f:
+                    f[k] += d_[k]
+            kern_ms = sum(f['ms'] for f in fam.values())
+            kernels = []
+            for name, f in sorted(fam.items(), key=lambda kv: -kv[1]['ms']):
+                kernels.append({'kernel': name, 'launches_per_step': f['launches'] / args.steps, 'ms_per_step': f['ms'] / args.steps,
+                                'share': f['ms'] / kern_ms, 'tflops': f['flops'] / (f['ms'] * 1e-3) / 1e12, 'gbs': f['bytes'] / (f['ms'] * 1e-3) / 1e9})
+            line['kernels'] = kernels
+            try:   # per-shape detail for profiling notes (not part of the JSON line)
+                os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
+                det = [{'kernel': n, 'tag': tg, 'launches_per_step': d_['launches'] / args.steps, 'ms_per_step': d_['ms'] / args.steps,
+                        'us_per_launch': d_['ms'] * 1e3 / d_['launches'], 'tflops': d_['flops'] / (d_['ms'] * 1e-3) / 1e12,
+                        'gbs': d_['bytes'] / (d_['ms'] * 1e-3) / 1e9} for (n, tg), d_ in sorted(summ.items(), key=lambda kv: -kv[1]['ms'])]
+                json.dump(det, open(os.path.join(ROOT, 'gpurun_out', 'kernels_detail.json'), 'w'), indent=1)
+            except Exception:
+                pass
+            # dominant kernel: the (family, shape) bucket with the largest total time
+            (name, tag), dmn = max(summ.items(), key=lambda kv: kv[1]['ms'])
+            secs = dmn['ms'] * 1e-3
+            t_flops = dmn['flops'] / (peaks['tf_sustained'] * 1e12)
+            t_bytes = dmn['bytes'] / (peaks['hbm'] * 1e9)
+            if t_bytes >= t_flops:
+                roof = {'bound': 'hbm', 'achieved': dmn['bytes'] / secs / 1e9, 'peak': peaks['hbm'], 'unit': 'GB/s'}
+            else:
+                roof = {'bound': 'tensor', 'achieved': dmn['flops'] / secs / 1e12, 'peak': peaks['tf_sustained'], 'unit': 'TFLOP/s'}
+            roof['frac'] = roof['achieved'] / roof['peak']
+            roof.update({'kernel': f'{name}[{tag}]', 'launches': dmn['launches'], 'avg_launch_us': dmn['ms'] * 1e3 / dmn['launches'],
+                         'algorithmic_bytes_per_launch': dmn['bytes'] / dmn['launches'], 'algorithmic_flops_per_launch': dmn['flops'] / dmn['launches'],
+                         'peak_source': peaks['src'] + (' (sustained bf16)' if roof['bound'] == 'tensor' else ' (copy bandwidth)'),
+                         'traffic': load_ncu_traffic(name)})
+            line['roofline'] = roof
+        if world == 1 and not args.no_cpu_baseline:
+            v, ms, cores = cpu_oracle_samples_per_sec(wl, args.cpu_sample_batch, 2, 1)
+            line['cpu_baseline'] = {'value': v, 'unit': 'samples/s', 'cores': cores, 'kind': 'port',
+                                    'sample': f'oracle (PyTorch CPU fp32 restatement of OT/model.py) fwd+BCE+bwd, 2 timed steps of '
+                                              f'{args.cpu_sample_batch} samples of the same workload'}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def load_ncu_traffic(kernel_name):
+    """dram bytes per launch of the dominant kernel from the committed ncu capture (profiles/), or None."""
+    path = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
+    if os.path.exists(path):
+        try:
+            return json.load(open(path)).get(kernel_name)
+        except Exception:
+            return None
+    return None
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,16 @@
+"""recommend_b200 — B200-native (sm_100a) implementation of the OneTrans ranking path of
+ScottHCL/recommend (``rank/scaling_up/oneTrans/practice``).  Exports mirror the reference package
+(``OT/__init__.py:9-26``) for the classes on the hot path."""
+__version__ = "0.1.0"
+
+from .config import OneTransConfig, OneTransSmallConfig, OneTransLargeConfig, get_model_config
+from .schedule import PyramidScheduler, resolve_keep_lens
+from .model import (RMSNorm, MixedMHA, MixedFFN, OneTransBlock, Tokenizer, OneTransModel, TaskHead,
+                    create_onetrans_model)
+from .state import load_reference_style_params, export_reference_style_params
+
+__all__ = [
+    'OneTransModel', 'OneTransConfig', 'OneTransSmallConfig', 'OneTransLargeConfig', 'get_model_config',
+    'RMSNorm', 'MixedMHA', 'MixedFFN', 'OneTransBlock', 'Tokenizer', 'PyramidScheduler', 'TaskHead',
+    'create_onetrans_model', 'resolve_keep_lens', 'load_reference_style_params', 'export_reference_style_params',
+]

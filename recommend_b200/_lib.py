@@ -1,0 +1,123 @@
+"""ctypes binding of ``libonetrans_sm100.so`` (C-ABI declared in ``include/onetrans_b200.h``).
+
+The structures below mirror the header field by field.  There is no fallback: if the shared library is
+missing or a call fails, the error is raised (north_star: no CPU fallback, no dispatch)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'lib', 'libonetrans_sm100.so')
+
+i32, i64, vp, fp = C.c_int32, C.c_int64, C.c_void_p, C.c_void_p  # float* passed as raw address
+
+OT_EPI_BIAS, OT_EPI_GELU, OT_EPI_RESIDUAL, OT_EPI_GELU_GRAD, OT_EPI_ROW_SCALE = 1, 2, 4, 8, 16
+
+
+class GemmSeg(C.Structure):
+    _fields_ = [('row_start', i32), ('n_units', i32), ('rows_per_unit', i32), ('group_start', i32),
+                ('group_stride', i32), ('a_row_start', i32)]
+
+
+class GemmParams(C.Structure):
+    _fields_ = [('A', vp), ('a_dim1', i64), ('a_dim2', i64), ('a_stride1', i64), ('a_stride2', i64),
+                ('a_transposed', i32), ('n_groups', i32), ('W', vp), ('ldw', i64), ('N', i32), ('K', i32),
+                ('n_segs', i32), ('flags', i32), ('segs', GemmSeg * 3),
+                ('out', vp), ('ldo', i64), ('out2', vp), ('ldo2', i64), ('res', vp), ('ldr', i64),
+                ('aux', vp), ('ldaux', i64), ('bias', fp), ('bias_group_stride', i64), ('row_scale', fp),
+                ('block_n', i32), ('swizzle', i32)]
+
+
+class WgradSeg(C.Structure):
+    _fields_ = [('P', vp), ('p_stride_row', i64), ('p_stride_unit', i64), ('Q', vp), ('q_stride_row', i64),
+                ('q_stride_unit', i64), ('n_units', i32), ('rows_per_unit', i32), ('group_start', i32),
+                ('group_stride', i32)]
+
+
+class WgradParams(C.Structure):
+    _fields_ = [('Mdim', i32), ('Ndim', i32), ('n_segs', i32), ('swizzle', i32), ('segs', WgradSeg * 2),
+                ('C', fp), ('c_group_stride', i64), ('c_stride_m', i64), ('c_stride_n', i64),
+                ('p_row_scale', fp), ('block_n', i32), ('target_ctas', i32)]
+
+
+class AttnParams(C.Structure):
+    _fields_ = [('q', vp), ('ldq', i64), ('k', vp), ('ldk', i64), ('v', vp), ('ldv', i64), ('o', vp), ('ldo', i64),
+                ('lse', fp), ('d_o', vp), ('lddo', i64), ('dq', vp), ('lddq', i64), ('dk', vp), ('lddk', i64),
+                ('dv', vp), ('lddv', i64), ('delta', fp), ('B', i32), ('H', i32), ('Lq', i32), ('Lk', i32),
+                ('head_dim', i32), ('swizzle', i32)]
+
+
+class RmsnormParams(C.Structure):
+    _fields_ = [('x', vp), ('ldx', i64), ('y', vp), ('ldy', i64), ('gain', fp), ('rstd', fp),
+                ('dy', vp), ('lddy', i64), ('dres', vp), ('lddres', i64), ('dx', vp), ('lddx', i64),
+                ('dgain', fp), ('rows', i64), ('d', i32), ('eps', C.c_float)]
+
+
+class NsTokenizerParams(C.Structure):
+    _fields_ = [('x', fp), ('W', fp), ('bias', fp), ('out', vp), ('dout', vp), ('ldo', i64), ('dW', fp),
+                ('dbias', fp), ('row0', i64), ('B', i32), ('L_ns', i32), ('d', i32), ('n_feat', i32)]
+
+
+class ColsumParams(C.Structure):
+    _fields_ = [('in_', vp), ('ld', i64), ('row_start', i64), ('n_units', i32), ('rows_per_unit', i32),
+                ('group_start', i32), ('group_stride', i32), ('out', fp), ('out_group_stride', i64), ('N', i32)]
+
+
+# every symbol include/onetrans_b200.h declares (tests check that the library exports all of them)
+EXPORTED_SYMBOLS = [
+    'ot_version', 'ot_last_error_string', 'ot_num_sms', 'ot_mixed_gemm', 'ot_wgrad', 'ot_attn_fwd', 'ot_attn_bwd',
+    'ot_rmsnorm_fwd', 'ot_rmsnorm_bwd', 'ot_ns_tokenizer_fwd', 'ot_ns_tokenizer_bwd', 'ot_fill_rows', 'ot_colsum',
+]
+
+_lib = None
+_lock = threading.Lock()
+
+
+class OneTransLibraryError(RuntimeError):
+    pass
+
+
+def load() -> C.CDLL:
+    """Load the CUDA extension, or raise.  Never substitutes anything else."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise OneTransLibraryError(
+                f'{LIB_PATH} not found: build it with `python -c "import __graft_entry__ as g; g.build()"` '
+                f'or recommend_b200/csrc/build.sh — there is no CPU fallback')
+        lib = C.CDLL(LIB_PATH)
+        lib.ot_version.restype = C.c_int
+        lib.ot_last_error_string.restype = C.c_char_p
+        lib.ot_num_sms.restype = C.c_int
+        for name, st in [('ot_mixed_gemm', GemmParams), ('ot_wgrad', WgradParams), ('ot_attn_fwd', AttnParams),
+                         ('ot_attn_bwd', AttnParams), ('ot_rmsnorm_fwd', RmsnormParams), ('ot_rmsnorm_bwd', RmsnormParams),
+                         ('ot_ns_tokenizer_fwd', NsTokenizerParams), ('ot_ns_tokenizer_bwd', NsTokenizerParams),
+                         ('ot_colsum', ColsumParams)]:
+            fn = getattr(lib, name)
+            fn.argtypes = [C.POINTER(st), C.c_void_p]
+            fn.restype = C.c_int
+        lib.ot_fill_rows.argtypes = [C.c_void_p, C.c_void_p, i64, i64, i64, i32, C.c_void_p]
+        lib.ot_fill_rows.restype = C.c_int
+        _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().ot_last_error_string()
+        raise OneTransLibraryError(f'{what} failed (rc={rc}): {msg.decode() if msg else ""}')
+
+
+# number of kernels this process has enqueued through the library (bench.py reports it as gpu_launches)
+launch_count = 0
+
+
+def count_launch(n: int = 1) -> None:
+    global launch_count
+    launch_count += n

@@ -424,6 +424,8 @@ static int launch_attn_bwd(const CUtensorMap* tm, AttnBwdKParams kp, cudaStream_
   return OT_OK;
 }
 
+int attn_bwd_fused_impl(const ot_attn_params* p, cudaStream_t st);   // ot_attn_bwd_fused.cu (head_dim 64)
+
 int attn_bwd_impl(const ot_attn_params* p, cudaStream_t st) {
   if (!p || !p->q || !p->k || !p->v || !p->o || !p->lse || !p->d_o || !p->dq || !p->dk || !p->dv || !p->delta)
     OT_FAIL(OT_ERR_INVALID_ARG, "ot_attn_bwd: null pointer");
@@ -432,6 +434,7 @@ int attn_bwd_impl(const ot_attn_params* p, cudaStream_t st) {
   if ((p->ldq % 8) || (p->ldk % 8) || (p->ldv % 8) || (p->ldo % 8) || (p->lddo % 8) || (p->lddq % 8) || (p->lddk % 8) || (p->lddv % 8))
     OT_FAIL(OT_ERR_UNSUPPORTED_SHAPE, "ot_attn_bwd: leading dimensions must be multiples of 8");
   const int swb = (p->head_dim == 64 && p->swizzle != 64) ? 128 : 64;
+  if (p->head_dim == 64 && swb == 128 && p->swizzle != 128) return attn_bwd_fused_impl(p, st);   // swizzle=128 forces the two-kernel path
   const int cols = p->H * p->head_dim;
   CUtensorMap tm[4];
   int rc;

@@ -29,6 +29,7 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 // ---------------------------------------------------------------------------------------------
 // RMSNorm forward:  y = x * rsqrt(mean(x^2) + eps) * g ;  rstd saved for the backward pass
 // ---------------------------------------------------------------------------------------------
+template <int NCH>
 __global__ void __launch_bounds__(256)
 rmsnorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const float* __restrict__ g,
                    __nv_bfloat16* __restrict__ y, long long ldy, float* __restrict__ rstd, long long rows, int d,
@@ -39,10 +40,10 @@ rmsnorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const flo
   const int nch = d >> 3;
   for (long long row = warp_global; row < rows; row += n_warps) {
     const uint4* xr = reinterpret_cast<const uint4*>(x + row * ldx);
-    float v[MAX_CHUNKS][8];
+    float v[NCH][8];
     float ss = 0.0f;
 #pragma unroll
-    for (int i = 0; i < MAX_CHUNKS; ++i) {
+    for (int i = 0; i < NCH; ++i) {
       const int ch = lane + 32 * i;
       if (ch < nch) {
         unpack8(xr[ch], v[i]);
@@ -55,7 +56,7 @@ rmsnorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const flo
     if (lane == 0 && rstd != nullptr) rstd[row] = r;
     uint4* yr = reinterpret_cast<uint4*>(y + row * ldy);
 #pragma unroll
-    for (int i = 0; i < MAX_CHUNKS; ++i) {
+    for (int i = 0; i < NCH; ++i) {
       const int ch = lane + 32 * i;
       if (ch < nch) {
         float o[8];
@@ -72,6 +73,7 @@ rmsnorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const flo
 // RMSNorm backward:  xh = x*rstd ; dxh = dy*g ; dx = rstd*(dxh - xh*mean(dxh*xh)) (+ dres)
 //                    dg += sum_rows dy*xh   (fp32 atomics, one flush per block)
 // ---------------------------------------------------------------------------------------------
+template <int NCH>
 __global__ void __launch_bounds__(256)
 rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long lddy, const __nv_bfloat16* __restrict__ x,
                    long long ldx, const float* __restrict__ rstd, const float* __restrict__ g,
@@ -84,9 +86,9 @@ rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long lddy, const _
   const int nch = d >> 3;
   for (int i = threadIdx.x; i < d; i += blockDim.x) s_dg[i] = 0.0f;
   __syncthreads();
-  float dg_acc[MAX_CHUNKS][8];
+  float dg_acc[NCH][8];
 #pragma unroll
-  for (int i = 0; i < MAX_CHUNKS; ++i)
+  for (int i = 0; i < NCH; ++i)
 #pragma unroll
     for (int e = 0; e < 8; ++e) dg_acc[i][e] = 0.0f;
 
@@ -94,10 +96,10 @@ rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long lddy, const _
     const uint4* xr = reinterpret_cast<const uint4*>(x + row * ldx);
     const uint4* dyr = reinterpret_cast<const uint4*>(dy + row * lddy);
     const float r = rstd[row];
-    float xh[MAX_CHUNKS][8], dxh[MAX_CHUNKS][8];
+    float xh[NCH][8], dxh[NCH][8];
     float dot = 0.0f;
 #pragma unroll
-    for (int i = 0; i < MAX_CHUNKS; ++i) {
+    for (int i = 0; i < NCH; ++i) {
       const int ch = lane + 32 * i;
       if (ch < nch) {
         float xv[8], dv[8];
@@ -117,7 +119,7 @@ rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long lddy, const _
     dot = warp_sum(dot) / (float)d;
     uint4* dxr = reinterpret_cast<uint4*>(dx + row * lddx);
 #pragma unroll
-    for (int i = 0; i < MAX_CHUNKS; ++i) {
+    for (int i = 0; i < NCH; ++i) {
       const int ch = lane + 32 * i;
       if (ch < nch) {
         float o[8];
@@ -134,7 +136,7 @@ rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long lddy, const _
     }
   }
 #pragma unroll
-  for (int i = 0; i < MAX_CHUNKS; ++i) {
+  for (int i = 0; i < NCH; ++i) {
     const int ch = lane + 32 * i;
     if (ch < nch) {
 #pragma unroll
@@ -278,8 +280,13 @@ int rmsnorm_fwd_impl(const ot_rmsnorm_params* p, cudaStream_t st) {
   if (p->d <= 0 || p->d % 8 || p->d > 8 * 32 * MAX_CHUNKS) OT_FAIL(OT_ERR_UNSUPPORTED_SHAPE, "ot_rmsnorm_fwd: d=%d", p->d);
   if ((p->ldx % 8) || (p->ldy % 8)) OT_FAIL(OT_ERR_UNSUPPORTED_SHAPE, "ot_rmsnorm_fwd: leading dimensions must be multiples of 8");
   if (p->rows <= 0) return OT_OK;
-  rmsnorm_fwd_kernel<<<grid_for_rows(p->rows, 8), 256, 0, st>>>((const __nv_bfloat16*)p->x, p->ldx, p->gain, (__nv_bfloat16*)p->y, p->ldy,
-                                                                 p->rstd, p->rows, p->d, p->eps);
+  const int nch = (p->d / 8 + 31) / 32;
+  const int grid = grid_for_rows(p->rows, 8);
+#define OT_LAUNCH_RMS_FWD(N)                                                                                             \
+  rmsnorm_fwd_kernel<N><<<grid, 256, 0, st>>>((const __nv_bfloat16*)p->x, p->ldx, p->gain, (__nv_bfloat16*)p->y, p->ldy, \
+                                              p->rstd, p->rows, p->d, p->eps)
+  if (nch <= 1) OT_LAUNCH_RMS_FWD(1); else if (nch == 2) OT_LAUNCH_RMS_FWD(2); else OT_LAUNCH_RMS_FWD(4);
+#undef OT_LAUNCH_RMS_FWD
   OT_CUDA_CHECK(cudaGetLastError());
   return OT_OK;
 }
@@ -291,11 +298,15 @@ int rmsnorm_bwd_impl(const ot_rmsnorm_params* p, cudaStream_t st) {
     OT_FAIL(OT_ERR_UNSUPPORTED_SHAPE, "ot_rmsnorm_bwd: leading dimensions must be multiples of 8");
   if (p->rows <= 0) return OT_OK;
   int grid = grid_for_rows(p->rows, 8);
-  const int cap = num_sms() * 4;  // fewer blocks -> fewer dgain flushes
+  const int cap = num_sms() * 8;  // a few resident blocks per SM; every block flushes dgain once
   if (grid > cap) grid = cap;
-  rmsnorm_bwd_kernel<<<grid, 256, p->d * sizeof(float), st>>>((const __nv_bfloat16*)p->dy, p->lddy, (const __nv_bfloat16*)p->x, p->ldx, p->rstd,
-                                                               p->gain, (const __nv_bfloat16*)p->dres, p->lddres, (__nv_bfloat16*)p->dx,
-                                                               p->lddx, p->dgain, p->rows, p->d);
+  const int nch = (p->d / 8 + 31) / 32;
+#define OT_LAUNCH_RMS_BWD(N)                                                                                                         \
+  rmsnorm_bwd_kernel<N><<<grid, 256, p->d * sizeof(float), st>>>((const __nv_bfloat16*)p->dy, p->lddy, (const __nv_bfloat16*)p->x, p->ldx, \
+                                                                 p->rstd, p->gain, (const __nv_bfloat16*)p->dres, p->lddres,          \
+                                                                 (__nv_bfloat16*)p->dx, p->lddx, p->dgain, p->rows, p->d)
+  if (nch <= 1) OT_LAUNCH_RMS_BWD(1); else if (nch == 2) OT_LAUNCH_RMS_BWD(2); else OT_LAUNCH_RMS_BWD(4);
+#undef OT_LAUNCH_RMS_BWD
   OT_CUDA_CHECK(cudaGetLastError());
   return OT_OK;
 }

@@ -7,11 +7,12 @@
 // which weight set" (OT/model.py:67-74) arrives as data (ot_gemm_seg), so the shared S-token run and
 // the per-token NS runs are tiles of ONE persistent launch.
 //
-// Kernel structure (one CTA per SM, persistent over a static tile list; 6 warps):
+// Kernel structure (one CTA per SM, persistent over a static tile list; 10 warps):
 //   warp 0   : TMA producer   — A tile [128 x BK] and W tile [BN x BK] into a STAGES-deep smem ring
 //   warp 1   : MMA issuer     — tcgen05.mma (M=128, N=BN, K=16) into one of two TMEM accumulators
-//   warps 2-5: epilogue       — tcgen05.ld -> fp32 math (row scale, bias, GELU, GELU', residual)
+//   warps 2-9: epilogue       — tcgen05.ld -> fp32 math (row scale, bias, GELU, GELU', residual)
 //                               -> bf16 -> swizzled smem staging -> coalesced 16-byte global stores
+//                               (two sets of four warps split the 64-column chunks of a tile)
 // The two TMEM accumulators (2*BN <= 512 columns) let the epilogue of tile i overlap the MMAs of
 // tile i+1.  Roofline: at d=256 every GEMM of the block is HBM-bound, so the
 // epilogue reads/writes each activation byte exactly once and in full 128-byte lines.
@@ -22,10 +23,13 @@
 namespace ot {
 
 static constexpr int BM = 128;
-static constexpr int GEMM_THREADS = 192;
-static constexpr int EPI_THREADS = 128;
-static constexpr int EPI_BAR_ID = 1;
-static constexpr int CHUNK = 64;  // epilogue column chunk (128 bytes of bf16 per row)
+static constexpr int GEMM_THREADS = 320;     // producer warp + MMA warp + 8 epilogue warps
+static constexpr int EPI_THREADS = 256;
+static constexpr int EPI_SET_THREADS = 128;
+static constexpr int EPI_BAR_ID = 1;         // named barriers 1, 2: one per epilogue set
+static constexpr int EPI_BAR_ALL = 3;        // all epilogue warps (bias tile reload)
+static constexpr int CHUNK = 64;             // epilogue column chunk (128 bytes of bf16 per row)
+static constexpr int CH_BYTES = 128 * 64 * 2;   // one staged chunk: 128 rows x 128 bytes
 
 struct GemmSegDev {
   int row_start, n_units, rows_per_unit, group_start, group_stride, a_row_start;
@@ -79,7 +83,7 @@ struct GemmCfg {
   static constexpr int A_BYTES = BM * SWB;
   static constexpr int B_BYTES = BN * SWB;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGING_BYTES = 2 * BM * CHUNK * 2;  // two 128x64 bf16 buffers
+  static constexpr int STAGING_BYTES = 4 * BM * CHUNK * 2;  // two epilogue sets x two 128x64 bf16 buffers
   static constexpr int BIAS_BYTES = BN * 4;
   static constexpr int BUDGET = 227 * 1024 - STAGING_BYTES - BIAS_BYTES - 256;
   static constexpr int STAGES_RAW = BUDGET / STAGE_BYTES;
@@ -123,7 +127,7 @@ ot_mixed_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);
+      mbar_init(&tempty_bar[i], 8);
     }
     fence_mbar_init();
   }
@@ -189,12 +193,23 @@ ot_mixed_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
-    const int et = threadIdx.x - 64;           // 0..127
-    const int lgrp = warp & 3;                 // TMEM lane group this warp may read
-    const int r_own = lgrp * 32 + lane;        // accumulator row owned by this thread
+    // ===================== epilogue (warps 2..9: two sets of four) =====================
+    // Set s handles the 64-column chunks c = s, s+2, ... of every tile with its own pair of staging buffers
+    // and its own named barrier; inside a set, warp w may read TMEM lanes 32*(w%4)..+31 (one row per thread).
+    const int set = (warp - 2) >> 2;
+    const int et = threadIdx.x - 64 - set * EPI_SET_THREADS;   // 0..127 inside the set
+    const int lgrp = warp & 3;
+    const int r_own = lgrp * 32 + lane;
     const int ld_row = et >> 3;                // cooperative copy: 16 rows per pass, 8 x 16 B per row
     const int ld_ch = et & 7;
+    const uint32_t bar_id = EPI_BAR_ID + set;
+    uint8_t* stg = staging + set * (2 * CH_BYTES);
+    const bool f_bias = p.flags & OT_EPI_BIAS, f_gelu = p.flags & OT_EPI_GELU, f_res = p.flags & OT_EPI_RESIDUAL;
+    const bool f_ggrad = p.flags & OT_EPI_GELU_GRAD, f_rs = p.flags & OT_EPI_ROW_SCALE;
+    const bool has_in = f_res || f_ggrad;
+    const bool dual = f_gelu && (p.out2 != nullptr);
+    const __nv_bfloat16* in_ptr = f_res ? p.res : p.aux;
+    const long long in_ld = f_res ? p.ldr : p.ldaux;
     int sbuf = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -205,119 +220,110 @@ ot_mixed_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
 
-      if (p.flags & OT_EPI_BIAS) {
-        named_bar_sync(EPI_BAR_ID, EPI_THREADS);  // previous tile's readers of bias_s are done
-        for (int j = et; j < BN; j += EPI_THREADS)
+      if (f_bias) {
+        named_bar_sync(EPI_BAR_ALL, EPI_THREADS);  // previous tile's readers of bias_s are done
+        for (int j = threadIdx.x - 64; j < BN; j += EPI_THREADS)
           bias_s[j] = p.bias[(long long)t.group * p.bias_group_stride + n0 + j];
-        named_bar_sync(EPI_BAR_ID, EPI_THREADS);
+        named_bar_sync(EPI_BAR_ALL, EPI_THREADS);
       }
       float rs = 1.0f;
-      if ((p.flags & OT_EPI_ROW_SCALE) && r_own < t.valid) rs = p.row_scale[t.row0 + r_own];
+      if (f_rs && r_own < t.valid) rs = p.row_scale[t.row0 + r_own];
 
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(lgrp * 32) << 16) + acc * BN;
 
 #pragma unroll 1
-      for (int c = 0; c < BN / CHUNK; ++c) {
-        uint32_t v[64];
-        {
-          uint32_t (&lo)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[0]);
-          uint32_t (&hi)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[32]);
-          tmem_ld_x32(t_row + c * CHUNK, lo);
-          tmem_ld_x32(t_row + c * CHUNK + 32, hi);
-          tmem_ld_wait();
-        }
+      for (int c = set; c < BN / CHUNK; c += 2) {
         const int col0 = n0 + c * CHUNK;
-        if (p.flags & OT_EPI_ROW_SCALE) {
-#pragma unroll
-          for (int j = 0; j < 64; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * rs);
-        }
-        if (p.flags & OT_EPI_BIAS) {
-#pragma unroll
-          for (int j = 0; j < 64; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + bias_s[c * CHUNK + j]);
-        }
-
-        // ---- helper lambdas over the staging buffers ----
-        auto coop_load = [&](const __nv_bfloat16* src, long long ld, uint8_t* buf) {
+        uint8_t* buf = stg + sbuf * CH_BYTES;
+        uint8_t* buf2 = stg + (sbuf ^ 1) * CH_BYTES;
+        if (has_in) {   // residual / GELU' input chunk: coalesced global -> staging
 #pragma unroll
           for (int i = 0; i < BM / 16; ++i) {
             const int r = i * 16 + ld_row;
             uint4 q = make_uint4(0, 0, 0, 0);
             if (r < t.valid)
-              q = *reinterpret_cast<const uint4*>(src + (long long)(t.row0 + r) * ld + col0 + ld_ch * 8);
+              q = *reinterpret_cast<const uint4*>(in_ptr + (long long)(t.row0 + r) * in_ld + col0 + ld_ch * 8);
             *reinterpret_cast<uint4*>(buf + swz_off<128>(r, ld_ch)) = q;
           }
-        };
-        auto coop_store = [&](__nv_bfloat16* dst, long long ld, const uint8_t* buf) {
+          named_bar_sync(bar_id, EPI_SET_THREADS);
+        }
 #pragma unroll
-          for (int i = 0; i < BM / 16; ++i) {
-            const int r = i * 16 + ld_row;
-            if (r < t.valid) {
-              const uint4 q = *reinterpret_cast<const uint4*>(buf + swz_off<128>(r, ld_ch));
-              *reinterpret_cast<uint4*>(dst + (long long)(t.row0 + r) * ld + col0 + ld_ch * 8) = q;
+        for (int half = 0; half < 2; ++half) {
+          uint32_t v[32];
+          tmem_ld_x32(t_row + c * CHUNK + half * 32, v);
+          tmem_ld_wait();
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          if (f_rs) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] *= rs;
+          }
+          if (f_bias) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] += bias_s[c * CHUNK + half * 32 + j];
+          }
+          if (f_gelu) {
+            if (dual) {   // keep the pre-activation for the backward pass
+#pragma unroll
+              for (int ch = 0; ch < 4; ++ch) {
+                uint4 q;
+                q.x = pack_bf16x2(f[ch * 8 + 0], f[ch * 8 + 1]);
+                q.y = pack_bf16x2(f[ch * 8 + 2], f[ch * 8 + 3]);
+                q.z = pack_bf16x2(f[ch * 8 + 4], f[ch * 8 + 5]);
+                q.w = pack_bf16x2(f[ch * 8 + 6], f[ch * 8 + 7]);
+                *reinterpret_cast<uint4*>(buf2 + swz_off<128>(r_own, half * 4 + ch)) = q;
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+          }
+          if (has_in) {
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) {
+              const uint4 q = *reinterpret_cast<const uint4*>(buf + swz_off<128>(r_own, half * 4 + ch));
+              const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                if (f_ggrad) {
+                  f[ch * 8 + 2 * e] *= gelu_erf_grad(bf16lo(w[e]));
+                  f[ch * 8 + 2 * e + 1] *= gelu_erf_grad(bf16hi(w[e]));
+                } else {
+                  f[ch * 8 + 2 * e] += bf16lo(w[e]);
+                  f[ch * 8 + 2 * e + 1] += bf16hi(w[e]);
+                }
+              }
             }
           }
-        };
-        auto write_own_row = [&](uint8_t* buf) {
+          // each thread (over)writes only its own row of `buf`
 #pragma unroll
-          for (int ch = 0; ch < 8; ++ch) {
+          for (int ch = 0; ch < 4; ++ch) {
             uint4 q;
-            q.x = pack_bf16x2(__uint_as_float(v[ch * 8 + 0]), __uint_as_float(v[ch * 8 + 1]));
-            q.y = pack_bf16x2(__uint_as_float(v[ch * 8 + 2]), __uint_as_float(v[ch * 8 + 3]));
-            q.z = pack_bf16x2(__uint_as_float(v[ch * 8 + 4]), __uint_as_float(v[ch * 8 + 5]));
-            q.w = pack_bf16x2(__uint_as_float(v[ch * 8 + 6]), __uint_as_float(v[ch * 8 + 7]));
-            *reinterpret_cast<uint4*>(buf + swz_off<128>(r_own, ch)) = q;
+            q.x = pack_bf16x2(f[ch * 8 + 0], f[ch * 8 + 1]);
+            q.y = pack_bf16x2(f[ch * 8 + 2], f[ch * 8 + 3]);
+            q.z = pack_bf16x2(f[ch * 8 + 4], f[ch * 8 + 5]);
+            q.w = pack_bf16x2(f[ch * 8 + 6], f[ch * 8 + 7]);
+            *reinterpret_cast<uint4*>(buf + swz_off<128>(r_own, half * 4 + ch)) = q;
           }
-        };
-
-        if (p.flags & OT_EPI_GELU) {
-          if (p.out2 != nullptr) {  // keep the pre-activation for the backward pass
-            uint8_t* buf = staging + sbuf * (BM * CHUNK * 2);
-            write_own_row(buf);
-            named_bar_sync(EPI_BAR_ID, EPI_THREADS);
-            coop_store(p.out2, p.ldo2, buf);
-            sbuf ^= 1;
-          }
-#pragma unroll
-          for (int j = 0; j < 64; ++j) v[j] = __float_as_uint(gelu_erf(__uint_as_float(v[j])));
         }
-        uint8_t* buf = staging + sbuf * (BM * CHUNK * 2);
-        if (p.flags & OT_EPI_GELU_GRAD) {
-          coop_load(p.aux, p.ldaux, buf);
-          named_bar_sync(EPI_BAR_ID, EPI_THREADS);
+        named_bar_sync(bar_id, EPI_SET_THREADS);
+        // the chunk leaves in full 128-byte rows
 #pragma unroll
-          for (int ch = 0; ch < 8; ++ch) {
-            const uint4 q = *reinterpret_cast<const uint4*>(buf + swz_off<128>(r_own, ch));
-            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              v[ch * 8 + 2 * e] = __float_as_uint(__uint_as_float(v[ch * 8 + 2 * e]) * gelu_erf_grad(bf16lo(w[e])));
-              v[ch * 8 + 2 * e + 1] =
-                  __float_as_uint(__uint_as_float(v[ch * 8 + 2 * e + 1]) * gelu_erf_grad(bf16hi(w[e])));
-            }
-          }
-          if (p.flags & OT_EPI_RESIDUAL) named_bar_sync(EPI_BAR_ID, EPI_THREADS);  // before buf is reloaded
-        }
-        if (p.flags & OT_EPI_RESIDUAL) {
-          coop_load(p.res, p.ldr, buf);
-          named_bar_sync(EPI_BAR_ID, EPI_THREADS);
-#pragma unroll
-          for (int ch = 0; ch < 8; ++ch) {
-            const uint4 q = *reinterpret_cast<const uint4*>(buf + swz_off<128>(r_own, ch));
-            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              v[ch * 8 + 2 * e] = __float_as_uint(__uint_as_float(v[ch * 8 + 2 * e]) + bf16lo(w[e]));
-              v[ch * 8 + 2 * e + 1] = __float_as_uint(__uint_as_float(v[ch * 8 + 2 * e + 1]) + bf16hi(w[e]));
+        for (int i = 0; i < BM / 16; ++i) {
+          const int r = i * 16 + ld_row;
+          if (r < t.valid) {
+            const uint4 q = *reinterpret_cast<const uint4*>(buf + swz_off<128>(r, ld_ch));
+            *reinterpret_cast<uint4*>(p.out + (long long)(t.row0 + r) * p.ldo + col0 + ld_ch * 8) = q;
+            if (dual) {
+              const uint4 q2 = *reinterpret_cast<const uint4*>(buf2 + swz_off<128>(r, ld_ch));
+              *reinterpret_cast<uint4*>(p.out2 + (long long)(t.row0 + r) * p.ldo2 + col0 + ld_ch * 8) = q2;
             }
           }
         }
-        // each thread overwrites only its own row of `buf`, then the tile chunk leaves coalesced
-        write_own_row(buf);
-        named_bar_sync(EPI_BAR_ID, EPI_THREADS);
-        coop_store(p.out, p.ldo, buf);
-        sbuf ^= 1;
+        if (dual) named_bar_sync(bar_id, EPI_SET_THREADS);  // both buffers were in use
+        else sbuf ^= 1;
       }
       // all TMEM reads of this accumulator are complete -> hand it back to the MMA warp
       tc_fence_before();
@@ -362,6 +368,8 @@ int mixed_gemm_impl(const ot_gemm_params* p, cudaStream_t st) {
   if ((p->flags & OT_EPI_RESIDUAL) && !p->res) OT_FAIL(OT_ERR_INVALID_ARG, "ot_mixed_gemm: residual flag without res");
   if ((p->flags & OT_EPI_GELU_GRAD) && !p->aux) OT_FAIL(OT_ERR_INVALID_ARG, "ot_mixed_gemm: gelu-grad flag without aux");
   if ((p->flags & OT_EPI_ROW_SCALE) && !p->row_scale) OT_FAIL(OT_ERR_INVALID_ARG, "ot_mixed_gemm: row-scale flag without row_scale");
+  if ((p->flags & OT_EPI_RESIDUAL) && (p->flags & OT_EPI_GELU_GRAD))
+    OT_FAIL(OT_ERR_INVALID_ARG, "ot_mixed_gemm: residual and gelu-grad epilogues cannot be combined (one auxiliary input per launch)");
   if ((p->ldo % 8) || (p->out2 && (p->ldo2 % 8)) || (p->res && (p->ldr % 8)) || (p->aux && (p->ldaux % 8)))
     OT_FAIL(OT_ERR_UNSUPPORTED_SHAPE, "ot_mixed_gemm: leading dimensions must be multiples of 8 elements");
 

@@ -1,0 +1,249 @@
+"""Forward / backward of the OneTrans block and tokenizer on token-major 2-D activations.
+
+Everything here enqueues kernels of ``libonetrans_sm100.so`` (through ``ops``); torch only allocates the
+buffers.  Shapes: ``x`` is ``[cur*B, d]`` bf16 with ``row = position*B + sample``; the block keeps the last
+``keep`` positions (pyramid tail, OT/model.py:351-371) and returns ``[keep*B, d]``.
+
+Backward accumulates parameter gradients straight into the fp32 ``.grad`` buffers of the parameters
+(weight-gradient kernels use fp32 atomics), so a flat gradient buffer can be all-reduced as is."""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import ops
+from ._lib import OT_EPI_BIAS, OT_EPI_GELU, OT_EPI_GELU_GRAD, OT_EPI_RESIDUAL
+
+bf16 = torch.bfloat16
+
+
+def _grad_buf(p: torch.Tensor) -> torch.Tensor:
+    """fp32 gradient buffer of a parameter (created zeroed on first use, then accumulated into)."""
+    if p.grad is None:
+        p.grad = torch.zeros_like(p, dtype=torch.float32)
+    return p.grad
+
+
+class BlockWeights:
+    """bf16 compute copies of one block's parameters, rebuilt when the fp32 masters change.
+
+    Masters use the Keras ``[in, out]`` kernel layout, packed over weight groups (0 = shared, 1+j = NS
+    token j):  Wqkv [G, d, 3d] (q | k | v), Wo [d, d], W1 [G, d, F], W2 [G, F, d].
+    The forward GEMM wants ``[G, N=out, K=in]`` (transposed copy); the input-gradient GEMM wants
+    ``[G, N=in, K=out]``, which is the master layout itself (plain cast)."""
+
+    def __init__(self):
+        self.key = None
+
+    def refresh(self, Wqkv, Wo, W1, W2):
+        key = (Wqkv._version, Wo._version, W1._version, W2._version, Wqkv.data_ptr(), W1.data_ptr())
+        if key == self.key:
+            return
+        d = Wqkv.shape[1]
+        with torch.no_grad():
+            self.Wqkv_b = Wqkv.detach().to(bf16)                                   # [G, d, 3d]
+            self.Wq_f = self.Wqkv_b[:, :, :d].transpose(1, 2).contiguous()          # [G, d(out), d(in)]
+            self.Wkv_f = self.Wqkv_b[:, :, d:].transpose(1, 2).contiguous()         # [G, 2d, d]
+            self.Wo_b = Wo.detach().to(bf16).unsqueeze(0)                           # [1, d, d]
+            self.Wo_f = self.Wo_b.transpose(1, 2).contiguous()
+            self.W1_b = W1.detach().to(bf16)                                       # [G, d, F]
+            self.W1_f = self.W1_b.transpose(1, 2).contiguous()                      # [G, F, d]
+            self.W2_b = W2.detach().to(bf16)                                       # [G, F, d]
+            self.W2_f = self.W2_b.transpose(1, 2).contiguous()                      # [G, d, F]
+        self.key = key
+
+
+def mha_forward(xn: torch.Tensor, res: Optional[torch.Tensor], w: BlockWeights, B: int, cur: int, keep: int, H: int,
+                L_ns: int, alignment: str, kv_prefix: Optional[torch.Tensor] = None):
+    """MixedMHA.call (OT/model.py:76-122) on normalised ``xn [cur*B, d]``; queries for the last ``keep``
+    positions.  ``res`` (``[keep*B, d]``) is added to the Wo output (the block's residual, OT/model.py:193).
+    ``kv_prefix [Lc*B, 2d]``: cached K|V rows placed in front of the new ones (OT/model.py:95-98).
+    Returns (z, saved) with z = res + attn_out @ Wo."""
+    d = xn.shape[1]
+    dh = d // H
+    dev = xn.device
+    rows, rows_t, off = cur * B, keep * B, (cur - keep) * B
+    segs_all = ops.position_segments(0, cur, cur, L_ns, alignment, B)
+    segs_tail = ops.position_segments(cur - keep, cur, cur, L_ns, alignment, B)
+    Lc = 0 if kv_prefix is None else kv_prefix.shape[0] // B
+    kv = torch.empty((Lc + cur) * B, 2 * d, dtype=bf16, device=dev)
+    if Lc:
+        kv[:Lc * B].copy_(kv_prefix)
+    ops.mixed_gemm(xn, w.Wkv_f, segs_all, kv[Lc * B:])
+    q = torch.empty(rows_t, d, dtype=bf16, device=dev)
+    ops.mixed_gemm(xn[off:], w.Wq_f, segs_tail, q)
+    o = torch.empty(rows_t, d, dtype=bf16, device=dev)
+    lse = torch.empty(B * H * keep, dtype=torch.float32, device=dev)
+    ops.attn_fwd(q, kv[:, :d], kv[:, d:], o, lse, B, H, keep, Lc + cur, dh)
+    z = torch.empty(rows_t, d, dtype=bf16, device=dev)
+    ops.mixed_gemm(o, w.Wo_f, [(0, 1, rows_t, 0, 0)], z, flags=OT_EPI_RESIDUAL if res is not None else 0, res=res)
+    return z, (q, kv, o, lse, segs_all, segs_tail)
+
+
+def mha_backward(dz: torch.Tensor, xn: torch.Tensor, saved, w: BlockWeights, Wqkv_grad: torch.Tensor, Wo_grad: torch.Tensor,
+                 B: int, cur: int, keep: int, H: int) -> torch.Tensor:
+    """Gradients of mha_forward w.r.t. xn (returned, ``[cur*B, d]``) and the weights (accumulated).
+    The residual path is the caller's business.  (No kv_prefix support: training never uses a cache.)"""
+    q, kv, o, lse, segs_all, segs_tail = saved
+    d = xn.shape[1]
+    dh = d // H
+    dev = xn.device
+    rows, rows_t, off = cur * B, keep * B, (cur - keep) * B
+    # Wo:  attn_out = o @ Wo
+    ops.wgrad_rows(o, dz, [(0, 1, rows_t, 0, 0)], Wo_grad, 0, d, 1)
+    do = torch.empty(rows_t, d, dtype=bf16, device=dev)
+    ops.mixed_gemm(dz, w.Wo_b, [(0, 1, rows_t, 0, 0)], do)
+    # attention
+    dq = torch.empty(rows_t, d, dtype=bf16, device=dev)
+    dkv = torch.empty(rows, 2 * d, dtype=bf16, device=dev)
+    delta = torch.empty(B * H * keep, dtype=torch.float32, device=dev)
+    ops.attn_bwd(q, kv[:, :d], kv[:, d:], o, lse, do, dq, dkv[:, :d], dkv[:, d:], delta, B, H, keep, cur, dh)
+    # projections:  q = xn_tail @ Wq[g],  k|v = xn @ Wkv[g]
+    G = Wqkv_grad.shape[0]
+    ops.wgrad_rows(xn[off:], dq, segs_tail, Wqkv_grad, d * 3 * d, 3 * d, 1)
+    ops.wgrad_rows(xn, dkv, segs_all, Wqkv_grad[:, :, d:], d * 3 * d, 3 * d, 1)
+    dxn = torch.empty(rows, d, dtype=bf16, device=dev)
+    ops.mixed_gemm(dkv, w.Wqkv_b[:, :, d:], segs_all, dxn)
+    ops.mixed_gemm(dq, w.Wqkv_b[:, :, :d], segs_tail, dxn[off:], flags=OT_EPI_RESIDUAL, res=dxn[off:])
+    return dxn
+
+
+def ffn_forward(zn: torch.Tensor, res: Optional[torch.Tensor], w: BlockWeights, b1: torch.Tensor, b2: torch.Tensor,
+                segs: Sequence[ops.Seg], save: bool):
+    """MixedFFN.call (OT/model.py:149-163): ``gelu(zn W1 + b1) W2 + b2`` (+ res)."""
+    rows_t, d = zn.shape
+    F = w.W1_f.shape[1]
+    dev = zn.device
+    h = torch.empty(rows_t, F, dtype=bf16, device=dev)
+    pre = torch.empty(rows_t, F, dtype=bf16, device=dev) if save else None
+    ops.mixed_gemm(zn, w.W1_f, segs, h, flags=OT_EPI_BIAS | OT_EPI_GELU, bias=b1, out2=pre)
+    y = torch.empty(rows_t, d, dtype=bf16, device=dev)
+    flags = OT_EPI_BIAS | (OT_EPI_RESIDUAL if res is not None else 0)
+    ops.mixed_gemm(h, w.W2_f, segs, y, flags=flags, bias=b2, res=res)
+    return y, (pre, h)
+
+
+def ffn_backward(dy: torch.Tensor, zn: torch.Tensor, saved, w: BlockWeights, segs: Sequence[ops.Seg], W1_grad, b1_grad,
+                 W2_grad, b2_grad) -> torch.Tensor:
+    """Gradient w.r.t. zn (returned) and the FFN parameters (accumulated)."""
+    pre, h = saved
+    rows_t, d = zn.shape
+    F = pre.shape[1]
+    dev = zn.device
+    ops.colsum(dy, segs, b2_grad, d)
+    ops.wgrad_rows(h, dy, segs, W2_grad, F * d, d, 1)
+    dpre = torch.empty(rows_t, F, dtype=bf16, device=dev)
+    ops.mixed_gemm(dy, w.W2_b, segs, dpre, flags=OT_EPI_GELU_GRAD, aux=pre)
+    ops.colsum(dpre, segs, b1_grad, F)
+    ops.wgrad_rows(zn, dpre, segs, W1_grad, d * F, F, 1)
+    dzn = torch.empty(rows_t, d, dtype=bf16, device=dev)
+    ops.mixed_gemm(dpre, w.W1_b, segs, dzn)
+    return dzn
+
+
+def block_forward(x: torch.Tensor, P: Dict[str, torch.Tensor], w: BlockWeights, B: int, cur: int, keep: int, H: int,
+                  L_ns: int, alignment: str, eps: float, save: bool, kv_prefix: Optional[torch.Tensor] = None):
+    """OneTransBlock.call (OT/model.py:186-200) + tail keep (:371).  P: norm1, norm2, b1, b2 (fp32)."""
+    rows, d = x.shape
+    assert rows == cur * B
+    dev = x.device
+    rows_t, off = keep * B, (cur - keep) * B
+    xn = torch.empty(rows, d, dtype=bf16, device=dev)
+    r1 = torch.empty(rows, dtype=torch.float32, device=dev)
+    ops.rmsnorm_fwd(x, P['norm1'], xn, r1, eps)                                           # OT/model.py:191
+    z, mha_saved = mha_forward(xn, x[off:], w, B, cur, keep, H, L_ns, alignment, kv_prefix)  # :192-193
+    zn = torch.empty(rows_t, d, dtype=bf16, device=dev)
+    r2 = torch.empty(rows_t, dtype=torch.float32, device=dev)
+    ops.rmsnorm_fwd(z, P['norm2'], zn, r2, eps)                                           # :196
+    segs_tail = mha_saved[5]
+    y, ffn_saved = ffn_forward(zn, z, w, P['b1'], P['b2'], segs_tail, save)                 # :197-198
+    kv = mha_saved[1]
+    saved = (x, xn, r1, mha_saved, z, zn, r2, ffn_saved) if save else None
+    return y, kv, saved
+
+
+def block_backward(dy: torch.Tensor, saved, Pm: Dict[str, torch.Tensor], w: BlockWeights, B: int, cur: int, keep: int,
+                   H: int) -> torch.Tensor:
+    """Backward of block_forward.  Pm maps names to the fp32 master parameters (their .grad buffers
+    receive the gradients).  Returns dx ``[cur*B, d]``."""
+    x, xn, r1, mha_saved, z, zn, r2, ffn_saved = saved
+    rows, d = x.shape
+    dev = x.device
+    rows_t, off = keep * B, (cur - keep) * B
+    segs_tail = mha_saved[5]
+    if not dy.is_contiguous():
+        dy = dy.contiguous()
+    # y = z + FFN(norm2(z))
+    dzn = ffn_backward(dy, zn, ffn_saved, w, segs_tail, _grad_buf(Pm['W1']), _grad_buf(Pm['b1']), _grad_buf(Pm['W2']),
+                       _grad_buf(Pm['b2']))
+    dz = torch.empty(rows_t, d, dtype=bf16, device=dev)
+    ops.rmsnorm_bwd(dzn, z, r2, Pm['norm2'].detach(), dz, _grad_buf(Pm['norm2']), dres=dy)
+    # z = x_tail + MHA(norm1(x))
+    dxn = mha_backward(dz, xn, mha_saved, w, _grad_buf(Pm['Wqkv']), _grad_buf(Pm['Wo']), B, cur, keep, H)
+    dx = torch.empty(rows, d, dtype=bf16, device=dev)
+    g1, dg1 = Pm['norm1'].detach(), _grad_buf(Pm['norm1'])
+    if off > 0:
+        ops.rmsnorm_bwd(dxn[:off], x[:off], r1[:off], g1, dx[:off], dg1, dres=None)
+    ops.rmsnorm_bwd(dxn[off:], x[off:], r1[off:], g1, dx[off:], dg1, dres=dz)
+    return dx
+
+
+# ---------------------------------------------------------------------------------------------------
+# tokenizer
+# ---------------------------------------------------------------------------------------------------
+
+
+def tokenizer_forward(ns_x: Optional[torch.Tensor], seq_list: Sequence[Optional[torch.Tensor]], B: int, d: int, L_ns: int,
+                      Ws_f: Sequence[torch.Tensor], bs: Sequence[torch.Tensor], sep: torch.Tensor, Wns: torch.Tensor,
+                      bns: torch.Tensor):
+    """Tokenizer.call (OT/model.py:224-277) written token-major: rows of sequence i, its [SEP] row, ...,
+    then the L_NS non-sequence tokens (S first, NS last, OT/model.py:235).  ``seq_list[i]`` is the bf16
+    ``[B, L_i, E]`` events of configured sequence i or None when absent."""
+    n_seq = len(seq_list)
+    layout = []  # (kind, index, first position, length)
+    pos = 0
+    for i, e in enumerate(seq_list):
+        if e is None:
+            continue
+        layout.append(('seq', i, pos, e.shape[1]))
+        pos += e.shape[1]
+        if i < n_seq - 1:                                          # OT/model.py:269
+            layout.append(('sep', i, pos, 1))
+            pos += 1
+    L_s = pos
+    L = L_s + L_ns
+    dev = sep.device
+    X0 = torch.empty(L * B, d, dtype=bf16, device=dev)
+    for kind, i, p0, n in layout:
+        if kind == 'seq':
+            ops.mixed_gemm(seq_list[i], Ws_f[i], [(p0 * B, n, B, 0, 0)], X0, flags=OT_EPI_BIAS, bias=bs[i],
+                           a_transposed_events=True)                # OT/model.py:265
+        else:
+            ops.fill_rows(sep.reshape(-1), X0, p0 * B, B)           # OT/model.py:270-272
+    if ns_x is None:
+        X0[L_s * B:].zero_()                                        # OT/model.py:249-251
+    else:
+        ops.ns_tokenizer_fwd(ns_x, Wns, bns, X0, L_s * B, B, L_ns, d)  # OT/model.py:211-214,253-254
+    return X0, L, layout
+
+
+def tokenizer_backward(dX0: torch.Tensor, ns_x, seq_list, layout, B: int, d: int, L_ns: int, Ws, bs, sep, Wns, bns) -> None:
+    """Accumulate the tokenizer's parameter gradients from dX0 (no input gradients: inputs are data)."""
+    if not dX0.is_contiguous():
+        dX0 = dX0.contiguous()
+    L_s = sum(n for _, _, _, n in layout)
+    for kind, i, p0, n in layout:
+        rows = dX0[p0 * B:(p0 + n) * B]
+        if kind == 'seq':
+            e = seq_list[i]
+            E = e.shape[2]
+            # dWs[i][k, m] += sum_{l,b} e[b,l,k] * dX0[(p0+l)B+b, m]  -> C[m, k] written transposed
+            ops.wgrad([dict(P=rows, p_stride_row=dX0.stride(0), p_stride_unit=B * dX0.stride(0), Q=e, q_stride_row=n * E,
+                            q_stride_unit=E, n_units=n, rows_per_unit=B, group_start=0, group_stride=0)],
+                      _grad_buf(Ws[i]), d, E, 0, 1, d)
+            ops.colsum(dX0, [(p0 * B, 1, n * B, 0, 0)], _grad_buf(bs[i]), 0)
+        else:
+            ops.colsum(dX0, [(p0 * B, 1, B, 0, 0)], _grad_buf(sep), 0)
+    if ns_x is not None:
+        ops.ns_tokenizer_bwd(ns_x, dX0, _grad_buf(Wns), _grad_buf(bns), L_s * B, B, L_ns, d)

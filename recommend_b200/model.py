@@ -1,0 +1,480 @@
+"""OneTrans model — the reference's module API (``rank/scaling_up/oneTrans/practice/model.py``,
+"OT/model.py") as ``torch.nn.Module``s whose arithmetic runs in hand-written sm_100a kernels.
+
+Same class names, constructor arguments and call signatures as the Keras classes:
+``RMSNorm(dim, eps)``, ``MixedMHA(config)``, ``MixedFFN(config)``, ``OneTransBlock(config)``,
+``Tokenizer(config)``, ``PyramidScheduler(config)``, ``OneTransModel(config)``,
+``create_onetrans_model(model_type)``.  Tensors at module boundaries are ``[B, L, d]`` like the
+reference's; physically they are views of token-major ``[L, B, d]`` buffers, so chaining
+modules never copies.  Parameters keep the Keras ``[in, out]`` kernel layout, packed over weight groups
+(index 0 = shared S-token weights, 1+j = NS token j).
+
+There is no CPU path: every module raises if its input is not on a CUDA device."""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F_
+
+from . import engine, ops
+from .config import OneTransConfig, get_model_config
+from .schedule import PyramidScheduler, resolve_keep_lens
+
+bf16 = torch.bfloat16
+
+
+def _glorot_(t: torch.Tensor, fan_in: int, fan_out: int, gen: Optional[torch.Generator] = None) -> torch.Tensor:
+    """Keras ``glorot_uniform`` (Dense default)."""
+    lim = math.sqrt(6.0 / (fan_in + fan_out))
+    with torch.no_grad():
+        t.copy_((torch.rand(t.shape, generator=gen, dtype=torch.float32) * 2 - 1) * lim)
+    return t
+
+
+def _require_cuda(t: torch.Tensor, who: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f'{who}: input is on {t.device}; the OneTrans kernels are sm_100a-only and there is no CPU fallback')
+
+
+def _to_token_major(x: torch.Tensor) -> Tuple[torch.Tensor, int, int]:
+    """``[B, L, d]`` (any strides) -> contiguous token-major 2-D ``[L*B, d]`` bf16; free when ``x`` already is
+    a ``[B, L, d]`` view of such a buffer."""
+    B, L, d = x.shape
+    xt = x.transpose(0, 1)
+    if xt.dtype != bf16:
+        xt = xt.to(bf16)
+    if not xt.is_contiguous():
+        xt = xt.contiguous()
+    return xt.reshape(L * B, d), B, L
+
+
+def _from_token_major(x2: torch.Tensor, B: int, L: int) -> torch.Tensor:
+    return x2.view(L, B, x2.shape[1]).transpose(0, 1)
+
+
+# ---------------------------------------------------------------------------------------------------
+# RMSNorm  (OT/model.py:11-23)
+# ---------------------------------------------------------------------------------------------------
+
+
+class _RMSNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x2, scale, eps):
+        y = torch.empty_like(x2)
+        rstd = torch.empty(x2.shape[0], dtype=torch.float32, device=x2.device)
+        ops.rmsnorm_fwd(x2, scale.detach(), y, rstd, eps)
+        ctx.save_for_backward(x2, rstd)
+        ctx.scale = scale
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, rstd = ctx.saved_tensors
+        dx = torch.empty_like(x2)
+        ops.rmsnorm_bwd(dy.contiguous(), x2, rstd, ctx.scale.detach(), dx, engine._grad_buf(ctx.scale))
+        return dx, None, None
+
+
+class RMSNorm(nn.Module):
+    """``x * rsqrt(mean(x^2, -1) + eps) * scale`` (OT/model.py:19-23)."""
+
+    def __init__(self, dim: int, eps: float = 1e-6):
+        super().__init__()
+        self.scale = nn.Parameter(torch.ones(dim))
+        self.eps = eps
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        _require_cuda(x, 'RMSNorm')
+        shp, dt = x.shape, x.dtype
+        x2 = x.reshape(-1, shp[-1]).to(bf16).contiguous()
+        y = _RMSNormFn.apply(x2, self.scale, self.eps)
+        return y.reshape(shp).to(dt)
+
+
+# ---------------------------------------------------------------------------------------------------
+# MixedMHA / MixedFFN  (OT/model.py:26-163)
+# ---------------------------------------------------------------------------------------------------
+
+
+class MixedMHA(nn.Module):
+    """Mixed-parameter causal multi-head attention (OT/model.py:26-122).
+
+    Parameters: ``Wqkv [1+L_NS, d, 3d]`` = (Wq | Wk | Wv) per weight group, no bias (OT/model.py:38-54);
+    ``Wo [d, d]`` shared, no bias (:57)."""
+
+    def __init__(self, config: OneTransConfig):
+        super().__init__()
+        self.config = config
+        self.hidden_dim = config.hidden_dim
+        self.num_heads = config.num_heads
+        self.head_dim = config.hidden_dim // config.num_heads
+        self.num_ns_tokens = config.num_ns_tokens
+        d, G = self.hidden_dim, 1 + config.num_ns_tokens
+        self.Wqkv = nn.Parameter(torch.empty(G, d, 3 * d))
+        self.Wo = nn.Parameter(torch.empty(d, d))
+        for part in range(3):
+            _glorot_(self.Wqkv.data[:, :, part * d:(part + 1) * d], d, d)
+        _glorot_(self.Wo.data, d, d)
+
+    # reference-style accessors (OT/model.py:38-54)
+    def _slice(self, part: int, j: Optional[int]) -> torch.Tensor:
+        d = self.hidden_dim
+        return self.Wqkv[0 if j is None else 1 + j, :, part * d:(part + 1) * d]
+
+    @property
+    def Wq_shared(self): return self._slice(0, None)
+    @property
+    def Wk_shared(self): return self._slice(1, None)
+    @property
+    def Wv_shared(self): return self._slice(2, None)
+
+    def forward(self, x: torch.Tensor, training: bool = False,
+                kv_cache: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, query_len: Optional[int] = None):
+        """x: normalised tokens ``[B, L, d]``.  Returns ``(output [B, Lq, d], (k, v))`` with k, v ``[B, Lk, d]``
+        (OT/model.py:76-122).  ``kv_cache=(k, v)``: cached keys/values placed in front (OT/model.py:95-98, with
+        the causal mask aligned to the sequence tail, repair D6).  ``query_len``: only the last rows query."""
+        _require_cuda(x, 'MixedMHA')
+        x2, B, L = _to_token_major(x)
+        keep = L if query_len is None else int(query_len)
+        prefix = None
+        if kv_cache is not None:
+            k2, _, Lc = _to_token_major(kv_cache[0])
+            v2, _, _ = _to_token_major(kv_cache[1])
+            prefix = torch.cat([k2, v2], dim=1)
+        out, kv = _MHAFn.apply(x2, self.Wqkv, self.Wo, self, B, L, keep, prefix)
+        d = self.hidden_dim
+        Lk = kv.shape[0] // B
+        k = _from_token_major(kv[:, :d], B, Lk)
+        v = _from_token_major(kv[:, d:], B, Lk)
+        return _from_token_major(out, B, keep), (k, v)
+
+
+class _MHAFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x2, Wqkv, Wo, mod: MixedMHA, B, cur, keep, prefix):
+        w = _weights_of(mod, None)
+        cfg = mod.config
+        out, saved = engine.mha_forward(x2, None, w, B, cur, keep, cfg.num_heads, cfg.num_ns_tokens,
+                                        cfg.ns_param_alignment, prefix)
+        kv = saved[1]
+        ctx.mark_non_differentiable(kv)
+        if prefix is not None and any(ctx.needs_input_grad):
+            raise RuntimeError('MixedMHA: kv_cache is an inference feature; call it under torch.no_grad()')
+        ctx.saved = (x2, saved, w, mod, B, cur, keep)
+        return out, kv
+
+    @staticmethod
+    def backward(ctx, dout, _dkv):
+        x2, saved, w, mod, B, cur, keep = ctx.saved
+        dxn = engine.mha_backward(dout.contiguous(), x2, saved, w, engine._grad_buf(mod.Wqkv), engine._grad_buf(mod.Wo),
+                                  B, cur, keep, mod.config.num_heads)
+        return dxn, None, None, None, None, None, None, None
+
+
+class MixedFFN(nn.Module):
+    """Mixed-parameter feed-forward (OT/model.py:125-163): ``Dense(F, gelu) -> Dense(d)`` with biases.
+    Parameters packed over weight groups: ``W1 [G, d, F]``, ``b1 [G, F]``, ``W2 [G, F, d]``, ``b2 [G, d]``."""
+
+    def __init__(self, config: OneTransConfig):
+        super().__init__()
+        self.config = config
+        self.hidden_dim = config.hidden_dim
+        self.ffn_dim = config.ffn_dim
+        self.num_ns_tokens = config.num_ns_tokens
+        d, Fd, G = config.hidden_dim, config.ffn_dim, 1 + config.num_ns_tokens
+        self.W1 = nn.Parameter(_glorot_(torch.empty(G, d, Fd), d, Fd))
+        self.b1 = nn.Parameter(torch.zeros(G, Fd))
+        self.W2 = nn.Parameter(_glorot_(torch.empty(G, Fd, d), Fd, d))
+        self.b2 = nn.Parameter(torch.zeros(G, d))
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        _require_cuda(x, 'MixedFFN')
+        x2, B, L = _to_token_major(x)
+        y = _FFNFn.apply(x2, self.W1, self, B, L)
+        return _from_token_major(y, B, L)
+
+
+class _FFNFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x2, W1, mod: MixedFFN, B, cur):
+        w = _weights_of(None, mod)
+        cfg = mod.config
+        segs = ops.position_segments(0, cur, cur, cfg.num_ns_tokens, cfg.ns_param_alignment, B)
+        y, saved = engine.ffn_forward(x2, None, w, mod.b1.detach(), mod.b2.detach(), segs, save=True)
+        ctx.saved = (x2, saved, w, mod, segs)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, saved, w, mod, segs = ctx.saved
+        g = engine._grad_buf
+        dx = engine.ffn_backward(dy.contiguous(), x2, saved, w, segs, g(mod.W1), g(mod.b1), g(mod.W2), g(mod.b2))
+        return dx, None, None, None, None
+
+
+class _PartialWeights:
+    """bf16 compute copies for a stand-alone MixedMHA or MixedFFN (the block keeps a joint cache)."""
+
+    def __init__(self):
+        self.key = None
+
+
+def _weights_of(mha: Optional[MixedMHA], ffn: Optional[MixedFFN]):
+    mod = mha if mha is not None else ffn
+    w = getattr(mod, '_ot_weights', None)
+    if w is None:
+        w = _PartialWeights()
+        object.__setattr__(mod, '_ot_weights', w)
+    if mha is not None:
+        key = (mha.Wqkv._version, mha.Wo._version, mha.Wqkv.data_ptr())
+        if key != w.key:
+            d = mha.hidden_dim
+            with torch.no_grad():
+                w.Wqkv_b = mha.Wqkv.detach().to(bf16)
+                w.Wq_f = w.Wqkv_b[:, :, :d].transpose(1, 2).contiguous()
+                w.Wkv_f = w.Wqkv_b[:, :, d:].transpose(1, 2).contiguous()
+                w.Wo_b = mha.Wo.detach().to(bf16).unsqueeze(0)
+                w.Wo_f = w.Wo_b.transpose(1, 2).contiguous()
+            w.key = key
+    else:
+        key = (ffn.W1._version, ffn.W2._version, ffn.W1.data_ptr())
+        if key != w.key:
+            with torch.no_grad():
+                w.W1_b = ffn.W1.detach().to(bf16)
+                w.W1_f = w.W1_b.transpose(1, 2).contiguous()
+                w.W2_b = ffn.W2.detach().to(bf16)
+                w.W2_f = w.W2_b.transpose(1, 2).contiguous()
+            w.key = key
+    return w
+
+
+# ---------------------------------------------------------------------------------------------------
+# OneTransBlock  (OT/model.py:166-200)
+# ---------------------------------------------------------------------------------------------------
+
+
+class OneTransBlock(nn.Module):
+    """Pre-norm causal block: ``z = x + drop(MHA(norm1(x)))``, ``y = z + drop(FFN(norm2(z)))`` (OT/model.py:186-200)."""
+
+    def __init__(self, config: OneTransConfig):
+        super().__init__()
+        self.config = config
+        self.norm1 = RMSNorm(config.hidden_dim, getattr(config, 'rms_eps', 1e-6))
+        self.norm2 = RMSNorm(config.hidden_dim, getattr(config, 'rms_eps', 1e-6))
+        self.attention = MixedMHA(config)
+        self.ffn = MixedFFN(config)
+        self.dropout_rate = config.dropout_rate
+        self._w = engine.BlockWeights()
+
+    def _weights(self) -> engine.BlockWeights:
+        self._w.refresh(self.attention.Wqkv, self.attention.Wo, self.ffn.W1, self.ffn.W2)
+        return self._w
+
+    def _params(self) -> Dict[str, torch.Tensor]:
+        return {'norm1': self.norm1.scale, 'norm2': self.norm2.scale, 'Wqkv': self.attention.Wqkv, 'Wo': self.attention.Wo,
+                'W1': self.ffn.W1, 'b1': self.ffn.b1, 'W2': self.ffn.W2, 'b2': self.ffn.b2}
+
+    def forward_token_major(self, x2: torch.Tensor, B: int, cur: int, keep: int, training: bool = False,
+                            kv_prefix: Optional[torch.Tensor] = None):
+        """Token-major entry used by OneTransModel: ``x2 [cur*B, d]`` -> ``([keep*B, d], kv [Lk*B, 2d])``."""
+        if training and self.dropout_rate > 0.0:
+            raise NotImplementedError(
+                'dropout inside the fused block is not built yet; set config.dropout_rate = 0 for training '
+                '(SURVEY.md §8d: parity runs use dropout 0)')
+        return _BlockFn.apply(x2, self.norm1.scale, self, B, cur, keep, kv_prefix)
+
+    def forward(self, x: torch.Tensor, training: bool = False,
+                kv_cache: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, query_len: Optional[int] = None):
+        """``x [B, L, d]`` -> ``(x' [B, Lq, d], (k, v))`` (OT/model.py:186-200).  ``query_len`` keeps only the last
+        rows (the pyramid tail, OT/model.py:351-371)."""
+        _require_cuda(x, 'OneTransBlock')
+        x2, B, L = _to_token_major(x)
+        keep = L if query_len is None else int(query_len)
+        prefix = None
+        if kv_cache is not None:
+            k2, _, _ = _to_token_major(kv_cache[0])
+            v2, _, _ = _to_token_major(kv_cache[1])
+            prefix = torch.cat([k2, v2], dim=1)
+        y, kv = self.forward_token_major(x2, B, L, keep, training, prefix)
+        d = self.config.hidden_dim
+        Lk = kv.shape[0] // B
+        return _from_token_major(y, B, keep), (_from_token_major(kv[:, :d], B, Lk), _from_token_major(kv[:, d:], B, Lk))
+
+
+class _BlockFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x2, anchor, blk: OneTransBlock, B, cur, keep, kv_prefix):
+        cfg = blk.config
+        need_grad = any(ctx.needs_input_grad)
+        if need_grad and kv_prefix is not None:
+            raise RuntimeError('OneTransBlock: kv_cache is an inference feature; call it under torch.no_grad()')
+        w = blk._weights()
+        P = {'norm1': blk.norm1.scale.detach(), 'norm2': blk.norm2.scale.detach(), 'b1': blk.ffn.b1.detach(),
+             'b2': blk.ffn.b2.detach()}
+        y, kv, saved = engine.block_forward(x2, P, w, B, cur, keep, cfg.num_heads, cfg.num_ns_tokens, cfg.ns_param_alignment,
+                                            blk.norm1.eps, need_grad, kv_prefix)
+        ctx.mark_non_differentiable(kv)
+        ctx.saved = (saved, w, blk, B, cur, keep)
+        return y, kv
+
+    @staticmethod
+    def backward(ctx, dy, _dkv):
+        saved, w, blk, B, cur, keep = ctx.saved
+        dx = engine.block_backward(dy, saved, blk._params(), w, B, cur, keep, blk.config.num_heads)
+        ctx.saved = None
+        return dx, None, None, None, None, None, None
+
+
+# ---------------------------------------------------------------------------------------------------
+# Tokenizer  (OT/model.py:203-277)
+# ---------------------------------------------------------------------------------------------------
+
+
+class Tokenizer(nn.Module):
+    """Unified tokenizer: non-sequence scalars -> Dense(d*L_NS)+Reshape (OT/model.py:211-214); each behaviour
+    sequence ``[B, L_i, 64]`` -> Dense(d) (:217-219), ``[SEP]`` after every present sequence except the last
+    configured one (:269-272); output ``concat([S, NS])`` (:235)."""
+
+    def __init__(self, config: OneTransConfig):
+        super().__init__()
+        self.config = config
+        d, L_ns, E = config.hidden_dim, config.num_ns_tokens, getattr(config, 'seq_feature_dim', 64)
+        n_feat = len(config.ns_features)
+        self.ns_kernel = nn.Parameter(_glorot_(torch.empty(n_feat, d * L_ns), n_feat, d * L_ns))
+        self.ns_bias = nn.Parameter(torch.zeros(d * L_ns))
+        n_seq = len(config.feature_config['sequence_features'])
+        self.seq_kernels = nn.ParameterList([nn.Parameter(_glorot_(torch.empty(E, d), E, d)) for _ in range(n_seq)])
+        self.seq_biases = nn.ParameterList([nn.Parameter(torch.zeros(d)) for _ in range(n_seq)])
+        self.sep_embedding = nn.Parameter((torch.rand(1, d) - 0.5) * 0.1)     # Keras Embedding default U(-.05,.05)
+        self._cache_key = None
+
+    def _seq_weights(self) -> List[torch.Tensor]:
+        key = tuple(p._version for p in self.seq_kernels) + (self.seq_kernels[0].data_ptr(),)
+        if key != self._cache_key:
+            with torch.no_grad():
+                self._Ws_f = [p.detach().t().contiguous().to(bf16).unsqueeze(0) for p in self.seq_kernels]  # [1, d, E]
+            self._cache_key = key
+        return self._Ws_f
+
+    def _gather_inputs(self, non_seq_features: Dict[str, torch.Tensor], seq_features: Dict[str, torch.Tensor]):
+        cfg = self.config
+        feats = [non_seq_features[n] for n in cfg.ns_features if n in non_seq_features]      # OT/model.py:243-247
+        ref = feats[0] if feats else next(iter(seq_features.values()))
+        _require_cuda(ref, 'Tokenizer')
+        B = ref.shape[0]
+        ns_x = None
+        if feats:
+            if len(feats) != len(cfg.ns_features):
+                raise ValueError(f'Tokenizer was built for non-sequence features {cfg.ns_features}; got '
+                                 f'{[n for n in cfg.ns_features if n in non_seq_features]} (set config.ns_feature_names)')
+            ns_x = torch.cat([f.reshape(B, 1).to(torch.float32) for f in feats], dim=1).contiguous()  # :253 (+D9 cast)
+        seq_list = []
+        for name in cfg.feature_config['sequence_features']:
+            e = seq_features.get(name)
+            if e is not None:
+                e = e.to(bf16).contiguous()
+            seq_list.append(e)
+        return ns_x, seq_list, B
+
+    def forward_token_major(self, non_seq_features, seq_features):
+        ns_x, seq_list, B = self._gather_inputs(non_seq_features, seq_features)
+        X0, L = _TokenizerFn.apply(self.ns_kernel, self, ns_x, seq_list, B)
+        return X0, B, L
+
+    def forward(self, non_seq_features: Dict[str, torch.Tensor], seq_features: Dict[str, torch.Tensor]) -> torch.Tensor:
+        X0, B, L = self.forward_token_major(non_seq_features, seq_features)
+        return _from_token_major(X0, B, L)
+
+
+class _TokenizerFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, anchor, tok: Tokenizer, ns_x, seq_list, B):
+        cfg = tok.config
+        d, L_ns = cfg.hidden_dim, cfg.num_ns_tokens
+        X0, L, layout = engine.tokenizer_forward(ns_x, seq_list, B, d, L_ns, tok._seq_weights(),
+                                                 [b.detach() for b in tok.seq_biases], tok.sep_embedding.detach(),
+                                                 tok.ns_kernel.detach(), tok.ns_bias.detach())
+        ctx.saved = (tok, ns_x, seq_list, layout, B)
+        return X0, L
+
+    @staticmethod
+    def backward(ctx, dX0, _dL=None):
+        tok, ns_x, seq_list, layout, B = ctx.saved
+        cfg = tok.config
+        engine.tokenizer_backward(dX0, ns_x, seq_list, layout, B, cfg.hidden_dim, cfg.num_ns_tokens, list(tok.seq_kernels),
+                                  list(tok.seq_biases), tok.sep_embedding, tok.ns_kernel, tok.ns_bias)
+        return None, None, None, None, None
+
+
+# ---------------------------------------------------------------------------------------------------
+# OneTransModel  (OT/model.py:305-416)
+# ---------------------------------------------------------------------------------------------------
+
+
+class TaskHead(nn.Module):
+    """``Dense(d/2, gelu) -> Dense(1, sigmoid)`` (OT/model.py:327-330), Keras ``[in, out]`` kernels, fp32."""
+
+    def __init__(self, d: int):
+        super().__init__()
+        self.kernel0 = nn.Parameter(_glorot_(torch.empty(d, d // 2), d, d // 2))
+        self.bias0 = nn.Parameter(torch.zeros(d // 2))
+        self.kernel1 = nn.Parameter(_glorot_(torch.empty(d // 2, 1), d // 2, 1))
+        self.bias1 = nn.Parameter(torch.zeros(1))
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:  # returns logits
+        h = F_.gelu(x @ self.kernel0 + self.bias0)
+        return h @ self.kernel1 + self.bias1
+
+
+class OneTransModel(nn.Module):
+    """OneTrans unified ranking model (OT/model.py:305-408): tokenizer -> pyramid-stacked blocks -> output
+    RMSNorm -> task heads on the last token.  Returns ``{task: probabilities [B, 1]}`` like the reference
+    (``return_logits=True`` returns the pre-sigmoid values)."""
+
+    def __init__(self, config: OneTransConfig):
+        super().__init__()
+        self.config = config
+        self.tokenizer = Tokenizer(config)
+        self.blocks = nn.ModuleList([OneTransBlock(config) for _ in range(config.num_layers)])
+        self.pyramid_scheduler = PyramidScheduler(config)
+        self.output_norm = RMSNorm(config.hidden_dim, getattr(config, 'rms_eps', 1e-6))
+        self.task_heads = nn.ModuleDict({t: TaskHead(config.hidden_dim) for t in config.tasks})
+        self.kv_cache = None
+
+    def forward(self, non_seq_features: Dict[str, torch.Tensor], seq_features: Dict[str, torch.Tensor],
+                training: bool = False, use_kv_cache: bool = False, return_logits: bool = False) -> Dict[str, torch.Tensor]:
+        x2, B, L = self.tokenizer.forward_token_major(non_seq_features, seq_features)       # OT/model.py:342
+        keep_lens = resolve_keep_lens(self.config, L)                                      # :349 (+D2, D5)
+        cur = L
+        for block, keep in zip(self.blocks, keep_lens):                                    # :348
+            x2, _ = block.forward_token_major(x2, B, cur, keep, training)                   # :366-371
+            cur = keep
+        return self._heads(x2[(cur - 1) * B:cur * B], return_logits)
+
+    def _heads(self, x_last: torch.Tensor, return_logits: bool) -> Dict[str, torch.Tensor]:
+        # output norm (OT/model.py:384) and heads (:388-391) on the last token, in fp32
+        xf = x_last.float()
+        xn = xf * torch.rsqrt(xf.square().mean(dim=-1, keepdim=True) + self.output_norm.eps) * self.output_norm.scale
+        out = {}
+        for task, head in self.task_heads.items():
+            logit = head(xn)
+            out[task] = logit if return_logits else torch.sigmoid(logit)
+        return out
+
+    def reset_kv_cache(self):
+        """OT/model.py:395-397."""
+        self.kv_cache = None
+
+    def get_model_info(self) -> Dict:
+        """OT/model.py:399-408."""
+        return {'total_parameters': sum(p.numel() for p in self.parameters() if p.requires_grad),
+                'num_layers': self.config.num_layers, 'hidden_dim': self.config.hidden_dim,
+                'num_heads': self.config.num_heads}
+
+
+def create_onetrans_model(model_type: str = 'default') -> OneTransModel:
+    """OT/model.py:411-416."""
+    return OneTransModel(get_model_config(model_type))

@@ -1,0 +1,289 @@
+"""Torch-tensor front end of the C-ABI kernels.  PyTorch supplies device memory and the current stream;
+every computation below is a kernel of ``libonetrans_sm100.so``.  All activations are bf16 2-D
+``[rows, cols]`` tensors whose rows are token-major (``row = position * B + sample``)."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib as L
+
+Seg = Tuple[int, int, int, int, int]  # (row_start, n_units, rows_per_unit, group_start, group_stride)
+
+
+class KernelProfiler:
+    """Optional per-launch CUDA-event timing on the launching stream (bench.py's roofline numbers).
+    Each record: (kernel family, shape tag, start event, end event, algorithmic flops, algorithmic bytes)."""
+
+    def __init__(self):
+        self.records = []
+
+    def summary(self):
+        """{(family, tag): dict(launches, ms, flops, bytes)} — call after torch.cuda.synchronize()."""
+        out = {}
+        for fam, tag, e0, e1, fl, by in self.records:
+            d = out.setdefault((fam, tag), dict(launches=0, ms=0.0, flops=0.0, bytes=0.0))
+            d['launches'] += 1
+            d['ms'] += e0.elapsed_time(e1)
+            d['flops'] += fl
+            d['bytes'] += by
+        return out
+
+
+_PROFILER: Optional[KernelProfiler] = None
+
+
+def set_profiler(p: Optional[KernelProfiler]) -> None:
+    global _PROFILER
+    _PROFILER = p
+
+
+def _run(name: str, fn, p, tag: str = '', flops: float = 0.0, nbytes: float = 0.0, n_launch: int = 1) -> None:
+    prof = _PROFILER
+    if prof is not None:
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+    L.check(fn(C.byref(p), _stream()), name)
+    if prof is not None:
+        e1.record()
+        prof.records.append((name, tag, e0, e1, flops, nbytes))
+    L.count_launch(n_launch)
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _check_bf16(t: torch.Tensor, name: str) -> None:
+    if t.dtype != torch.bfloat16 or not t.is_cuda:
+        raise TypeError(f'{name} must be a CUDA bfloat16 tensor, got {t.dtype} on {t.device}')
+    if t.dim() < 1 or t.stride(-1) != 1:
+        raise ValueError(f'{name} must be contiguous in its last dimension')
+
+
+def position_segments(p0: int, p1: int, cur: int, L_ns: int, alignment: str, B: int) -> List[Seg]:
+    """Weight-group segments for positions ``[p0, p1)`` of a length-``cur`` sequence, rows relative to
+    position ``p0``.  Mirrors ``_get_projection_weights`` (OT/model.py:67-74):
+    'head_literal' = as written (position i < L_NS uses dedicated[i]); 'tail' = repair D4 (the NS tokens
+    are the last L_NS positions of the ORIGINAL sequence and keep their own weights as the pyramid
+    shortens the sequence in front of them).  Group 0 = shared, 1+j = dedicated j."""
+    segs: List[Seg] = []
+    if alignment == 'tail':
+        ns_begin = max(cur - L_ns, 0)           # first position that is an NS token
+        first_j = L_ns - (cur - ns_begin)       # its NS index
+        a, b = p0, min(p1, ns_begin)
+        if b > a:
+            segs.append(((a - p0) * B, 1, (b - a) * B, 0, 0))
+        a, b = max(p0, ns_begin), p1
+        if b > a:
+            segs.append(((a - p0) * B, b - a, B, 1 + first_j + (a - ns_begin), 1))
+    elif alignment == 'head_literal':
+        ded_end = min(L_ns, cur)
+        a, b = p0, min(p1, ded_end)
+        if b > a:
+            segs.append(((a - p0) * B, b - a, B, 1 + a, 1))
+        a, b = max(p0, ded_end), p1
+        if b > a:
+            segs.append(((a - p0) * B, 1, (b - a) * B, 0, 0))
+    else:
+        raise ValueError(f'unknown ns_param_alignment {alignment!r}')
+    return segs
+
+
+def mixed_gemm(A: torch.Tensor, W: torch.Tensor, segs: Sequence[Seg], out: torch.Tensor, *, flags: int = 0,
+               bias: Optional[torch.Tensor] = None, res: Optional[torch.Tensor] = None,
+               aux: Optional[torch.Tensor] = None, out2: Optional[torch.Tensor] = None,
+               row_scale: Optional[torch.Tensor] = None, a_transposed_events: bool = False,
+               block_n: int = 0, swizzle: int = 0) -> torch.Tensor:
+    """``out[row] = epilogue(A[row] @ W[group(row)].T)``.  W: ``[G, N, K]`` bf16 (rows may be strided).
+    With ``a_transposed_events`` A is ``[B, L_i, K]`` and output rows are ``(l, b)`` token-major."""
+    _check_bf16(W, 'W')
+    _check_bf16(out, 'out')
+    G, N, K = W.shape
+    p = L.GemmParams()
+    p.A = A.data_ptr()
+    if a_transposed_events:
+        _check_bf16(A, 'A')
+        Bsz, Li, Ka = A.shape
+        assert Ka == K and A.is_contiguous()
+        p.a_dim1, p.a_dim2, p.a_stride1, p.a_stride2, p.a_transposed = Li, Bsz, K, Li * K, 1
+    else:
+        _check_bf16(A, 'A')
+        assert A.dim() == 2 and A.shape[1] == K
+        p.a_dim1, p.a_dim2, p.a_stride1, p.a_stride2, p.a_transposed = A.shape[0], 1, A.stride(0), 0, 0
+    assert W.stride(2) == 1 and W.stride(0) == N * W.stride(1), 'W groups must be evenly strided rows'
+    p.n_groups, p.W, p.ldw, p.N, p.K = G, W.data_ptr(), W.stride(1), N, K
+    p.n_segs, p.flags = len(segs), flags
+    for i, s in enumerate(segs):
+        sg = p.segs[i]
+        sg.row_start, sg.n_units, sg.rows_per_unit, sg.group_start, sg.group_stride = s[:5]
+        sg.a_row_start = s[5] if len(s) > 5 else (0 if a_transposed_events else s[0])
+    p.out, p.ldo = out.data_ptr(), out.stride(0)
+    if out2 is not None:
+        _check_bf16(out2, 'out2')
+        p.out2, p.ldo2 = out2.data_ptr(), out2.stride(0)
+    if res is not None:
+        _check_bf16(res, 'res')
+        p.res, p.ldr = res.data_ptr(), res.stride(0)
+    if aux is not None:
+        _check_bf16(aux, 'aux')
+        p.aux, p.ldaux = aux.data_ptr(), aux.stride(0)
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.is_cuda
+        p.bias = bias.data_ptr()
+        p.bias_group_stride = bias.stride(0) if bias.dim() == 2 else 0
+    if row_scale is not None:
+        assert row_scale.dtype == torch.float32
+        p.row_scale = row_scale.data_ptr()
+    p.block_n, p.swizzle = block_n, swizzle
+    rows = sum(s[1] * s[2] for s in segs)
+    groups = sum((s[1] if s[4] else 1) for s in segs)
+    n_io = 1 + (out2 is not None) + (res is not None) + (aux is not None)
+    _run('ot_mixed_gemm', L.load().ot_mixed_gemm, p, f'N{N}_K{K}_f{flags}', 2.0 * rows * N * K,
+         rows * K * 2.0 + n_io * rows * N * 2.0 + groups * N * K * 2.0)
+    return out
+
+
+WSeg = Tuple[torch.Tensor, int, int, torch.Tensor, int, int, int, int, int, int]
+
+
+def wgrad(segs: Sequence[dict], Cout: torch.Tensor, Mdim: int, Ndim: int, c_group_stride: int, c_stride_m: int,
+          c_stride_n: int, *, block_n: int = 0, swizzle: int = 0, target_ctas: int = 0) -> None:
+    """``Cout[g][m, n] += sum_rows P[row, m] * Q[row, n]``; each seg is a dict with keys
+    P, p_stride_row, p_stride_unit, Q, q_stride_row, q_stride_unit, n_units, rows_per_unit, group_start,
+    group_stride.  ``Cout`` is an fp32 tensor (any view); strides in elements."""
+    assert Cout.dtype == torch.float32 and Cout.is_cuda
+    p = L.WgradParams()
+    p.Mdim, p.Ndim, p.n_segs, p.swizzle = Mdim, Ndim, len(segs), swizzle
+    for i, s in enumerate(segs):
+        sg = p.segs[i]
+        _check_bf16(s['P'], 'P')
+        _check_bf16(s['Q'], 'Q')
+        sg.P, sg.p_stride_row, sg.p_stride_unit = s['P'].data_ptr(), s['p_stride_row'], s['p_stride_unit']
+        sg.Q, sg.q_stride_row, sg.q_stride_unit = s['Q'].data_ptr(), s['q_stride_row'], s['q_stride_unit']
+        sg.n_units, sg.rows_per_unit, sg.group_start, sg.group_stride = (
+            s['n_units'], s['rows_per_unit'], s['group_start'], s['group_stride'])
+    p.C = Cout.data_ptr()
+    p.c_group_stride, p.c_stride_m, p.c_stride_n = c_group_stride, c_stride_m, c_stride_n
+    p.block_n, p.target_ctas = block_n, target_ctas
+    rows = sum(s['n_units'] * s['rows_per_unit'] for s in segs)
+    groups = sum((s['n_units'] if s['group_stride'] else 1) for s in segs)
+    _run('ot_wgrad', L.load().ot_wgrad, p, f'M{Mdim}_N{Ndim}', 2.0 * rows * Mdim * Ndim,
+         rows * (Mdim + Ndim) * 2.0 + groups * Mdim * Ndim * 4.0)
+
+
+def wgrad_rows(P: torch.Tensor, Q: torch.Tensor, segs: Sequence[Seg], Cout: torch.Tensor, c_group_stride: int,
+               c_stride_m: int, c_stride_n: int) -> None:
+    """Weight gradient for row-aligned 2-D activations ``P [rows, Mdim]`` and ``Q [rows, Ndim]`` whose
+    rows are described by the same position segments the forward GEMM used."""
+    wsegs = []
+    for (row_start, n_units, rpu, g0, gs) in segs:
+        wsegs.append(dict(P=P[row_start:], p_stride_row=P.stride(0), p_stride_unit=rpu * P.stride(0),
+                          Q=Q[row_start:], q_stride_row=Q.stride(0), q_stride_unit=rpu * Q.stride(0),
+                          n_units=n_units, rows_per_unit=rpu, group_start=g0, group_stride=gs))
+    wgrad(wsegs, Cout, P.shape[1], Q.shape[1], c_group_stride, c_stride_m, c_stride_n)
+
+
+def attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, o: torch.Tensor, lse: torch.Tensor, B: int, H: int,
+             Lq: int, Lk: int, head_dim: int, swizzle: int = 0) -> None:
+    for t, n in ((q, 'q'), (k, 'k'), (v, 'v'), (o, 'o')):
+        _check_bf16(t, n)
+    assert lse.dtype == torch.float32 and lse.numel() == B * H * Lq
+    p = L.AttnParams()
+    p.q, p.ldq, p.k, p.ldk, p.v, p.ldv, p.o, p.ldo = (q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0),
+                                                      v.data_ptr(), v.stride(0), o.data_ptr(), o.stride(0))
+    p.lse = lse.data_ptr()
+    p.B, p.H, p.Lq, p.Lk, p.head_dim, p.swizzle = B, H, Lq, Lk, head_dim, swizzle
+    pairs = Lq * Lk - Lq * (Lq - 1) / 2.0
+    d = H * head_dim
+    _run('ot_attn_fwd', L.load().ot_attn_fwd, p, f'Lq{Lq}_Lk{Lk}', 4.0 * B * H * head_dim * pairs,
+         (2.0 * Lq + 2.0 * Lk) * B * d * 2.0)
+
+
+def attn_bwd(q, k, v, o, lse, d_o, dq, dk, dv, delta, B: int, H: int, Lq: int, Lk: int, head_dim: int,
+             swizzle: int = 0) -> None:
+    for t, n in ((q, 'q'), (k, 'k'), (v, 'v'), (o, 'o'), (d_o, 'd_o'), (dq, 'dq'), (dk, 'dk'), (dv, 'dv')):
+        _check_bf16(t, n)
+    p = L.AttnParams()
+    p.q, p.ldq, p.k, p.ldk, p.v, p.ldv, p.o, p.ldo = (q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0),
+                                                      v.data_ptr(), v.stride(0), o.data_ptr(), o.stride(0))
+    p.lse, p.delta = lse.data_ptr(), delta.data_ptr()
+    p.d_o, p.lddo, p.dq, p.lddq = d_o.data_ptr(), d_o.stride(0), dq.data_ptr(), dq.stride(0)
+    p.dk, p.lddk, p.dv, p.lddv = dk.data_ptr(), dk.stride(0), dv.data_ptr(), dv.stride(0)
+    p.B, p.H, p.Lq, p.Lk, p.head_dim, p.swizzle = B, H, Lq, Lk, head_dim, swizzle
+    pairs = Lq * Lk - Lq * (Lq - 1) / 2.0
+    d = H * head_dim
+    _run('ot_attn_bwd', L.load().ot_attn_bwd, p, f'Lq{Lq}_Lk{Lk}', 10.0 * B * H * head_dim * pairs,
+         (4.0 * Lq + 4.0 * Lk) * B * d * 2.0, n_launch=2)
+
+
+def rmsnorm_fwd(x: torch.Tensor, gain: torch.Tensor, y: torch.Tensor, rstd: Optional[torch.Tensor], eps: float = 1e-6) -> None:
+    _check_bf16(x, 'x')
+    _check_bf16(y, 'y')
+    assert gain.dtype == torch.float32 and gain.is_cuda and gain.is_contiguous()
+    p = L.RmsnormParams()
+    p.x, p.ldx, p.y, p.ldy, p.gain, p.rstd = x.data_ptr(), x.stride(0), y.data_ptr(), y.stride(0), gain.data_ptr(), _ptr(rstd)
+    p.rows, p.d, p.eps = x.shape[0], x.shape[1], eps
+    _run('ot_rmsnorm_fwd', L.load().ot_rmsnorm_fwd, p, f'd{x.shape[1]}', 3.0 * x.numel(), x.numel() * 4.0 + x.shape[0] * 4.0)
+
+
+def rmsnorm_bwd(dy: torch.Tensor, x: torch.Tensor, rstd: torch.Tensor, gain: torch.Tensor, dx: torch.Tensor,
+                dgain: torch.Tensor, dres: Optional[torch.Tensor] = None) -> None:
+    for t, n in ((dy, 'dy'), (x, 'x'), (dx, 'dx')):
+        _check_bf16(t, n)
+    assert dgain.dtype == torch.float32 and rstd.dtype == torch.float32
+    p = L.RmsnormParams()
+    p.x, p.ldx, p.gain, p.rstd = x.data_ptr(), x.stride(0), gain.data_ptr(), rstd.data_ptr()
+    p.dy, p.lddy, p.dx, p.lddx, p.dgain = dy.data_ptr(), dy.stride(0), dx.data_ptr(), dx.stride(0), dgain.data_ptr()
+    if dres is not None:
+        _check_bf16(dres, 'dres')
+        p.dres, p.lddres = dres.data_ptr(), dres.stride(0)
+    p.rows, p.d, p.eps = x.shape[0], x.shape[1], 0.0
+    if p.rows > 0:
+        _run('ot_rmsnorm_bwd', L.load().ot_rmsnorm_bwd, p, f'd{x.shape[1]}', 8.0 * x.numel(),
+             x.numel() * 2.0 * (3 + (dres is not None)) + x.shape[0] * 4.0)
+
+
+def ns_tokenizer_fwd(x: torch.Tensor, W: torch.Tensor, bias: torch.Tensor, out: torch.Tensor, row0: int, B: int,
+                     L_ns: int, d: int) -> None:
+    assert x.dtype == torch.float32 and x.is_contiguous() and W.dtype == torch.float32 and W.is_contiguous()
+    p = L.NsTokenizerParams()
+    p.x, p.W, p.bias, p.out, p.ldo = x.data_ptr(), W.data_ptr(), bias.data_ptr(), out.data_ptr(), out.stride(0)
+    p.row0, p.B, p.L_ns, p.d, p.n_feat = row0, B, L_ns, d, x.shape[1]
+    _run('ot_ns_tokenizer_fwd', L.load().ot_ns_tokenizer_fwd, p, '', 2.0 * B * L_ns * d * x.shape[1], B * L_ns * d * 2.0)
+
+
+def ns_tokenizer_bwd(x: torch.Tensor, dout: torch.Tensor, dW: torch.Tensor, dbias: torch.Tensor, row0: int, B: int,
+                     L_ns: int, d: int) -> None:
+    assert x.dtype == torch.float32 and x.is_contiguous() and dW.dtype == torch.float32 and dW.is_contiguous()
+    p = L.NsTokenizerParams()
+    p.x, p.dout, p.ldo, p.dW, p.dbias = x.data_ptr(), dout.data_ptr(), dout.stride(0), dW.data_ptr(), dbias.data_ptr()
+    p.row0, p.B, p.L_ns, p.d, p.n_feat = row0, B, L_ns, d, x.shape[1]
+    _run('ot_ns_tokenizer_bwd', L.load().ot_ns_tokenizer_bwd, p, '', 2.0 * B * L_ns * d * x.shape[1], B * L_ns * d * 2.0)
+
+
+def fill_rows(vec: torch.Tensor, out: torch.Tensor, row0: int, n_rows: int) -> None:
+    assert vec.dtype == torch.float32 and vec.is_contiguous()
+    L.check(L.load().ot_fill_rows(vec.data_ptr(), out.data_ptr(), out.stride(0), row0, n_rows, out.shape[1], _stream()),
+            'ot_fill_rows')
+    L.count_launch()
+
+
+def colsum(inp: torch.Tensor, segs: Sequence[Seg], out: torch.Tensor, out_group_stride: int) -> None:
+    """``out[group][n] += sum_rows inp[row, n]`` for each unit of each segment (bias gradients)."""
+    _check_bf16(inp, 'inp')
+    assert out.dtype == torch.float32
+    for (row_start, n_units, rpu, g0, gs) in segs:
+        p = L.ColsumParams()
+        p.in_, p.ld, p.row_start = inp.data_ptr(), inp.stride(0), row_start
+        p.n_units, p.rows_per_unit, p.group_start, p.group_stride = n_units, rpu, g0, gs
+        p.out, p.out_group_stride, p.N = out.data_ptr(), out_group_stride, inp.shape[1]
+        _run('ot_colsum', L.load().ot_colsum, p, f'N{inp.shape[1]}', float(n_units * rpu * inp.shape[1]),
+             n_units * rpu * inp.shape[1] * 2.0)

@@ -237,7 +237,7 @@ int main(int argc, char** argv) {
     case 7: return test_gemm("gemm_gelu_dual", 500, 1024, 256, 1, {{0, 1, 500, 0, 0}}, OT_EPI_BIAS | OT_EPI_GELU, 0, 0, true);
     case 8: return test_gemm("gemm_residual", 500, 256, 1024, 1, {{0, 1, 500, 0, 0}}, OT_EPI_BIAS | OT_EPI_RESIDUAL, 0, 0, false);
     case 9: return test_gemm("gemm_gelugrad", 300, 1024, 256, 1, {{0, 1, 300, 0, 0}}, OT_EPI_GELU_GRAD, 0, 0, false);
-    case 10: return test_gemm("gemm_gelugrad_res", 300, 256, 256, 1, {{0, 1, 300, 0, 0}}, OT_EPI_GELU_GRAD | OT_EPI_RESIDUAL | OT_EPI_ROW_SCALE, 0, 0, false);
+    case 10: return test_gemm("gemm_res_rowscale", 300, 256, 256, 1, {{0, 1, 300, 0, 0}}, OT_EPI_RESIDUAL | OT_EPI_ROW_SCALE, 0, 0, false);
     case 11: return test_gemm("gemm_hole", 640, 128, 64, 2, {{0, 1, 200, 0, 0}, {384, 2, 100, 0, 1}}, 0, 0, 0, false);
     case 12: return test_gemm("gemm_swz64", 300, 256, 96, 1, {{0, 1, 300, 0, 0}}, OT_EPI_BIAS, 0, 64, false);
     case 13: return test_gemm_transposed(200, 7, 64, 256, 0);

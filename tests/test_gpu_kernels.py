@@ -1,0 +1,241 @@
+"""GPU parity of every kernel behind the C-ABI (called through recommend_b200.ops -> ctypes -> libonetrans_sm100.so)
+against plain PyTorch fp32 references of the same op on the same seeded inputs, including edge cases (ragged
+tiles, partial groups, tails shorter than a tile) and BASELINE.json's full sizes."""
+import math
+
+import pytest
+import torch
+
+from recommend_b200 import ops, _lib
+from recommend_b200._lib import OT_EPI_BIAS, OT_EPI_GELU, OT_EPI_GELU_GRAD, OT_EPI_RESIDUAL, OT_EPI_ROW_SCALE
+
+pytestmark = pytest.mark.gpu
+bf16 = torch.bfloat16
+TOL = 2e-2   # bf16 outputs vs fp32 reference: |got-ref| <= TOL * (1 + |ref|)
+
+
+def close(got, ref, tol=TOL):
+    got, ref = got.float(), ref.float()
+    err = ((got - ref).abs() / (1 + ref.abs())).max().item()
+    assert err <= tol, f'max scaled err {err:.3e}'
+
+
+def rnd(*shape, scale=1.0, seed=0):
+    g = torch.Generator(device='cuda').manual_seed(seed)
+    return (torch.randn(*shape, generator=g, device='cuda') * scale).to(bf16)
+
+
+def ref_rows_gemm(A, W, segs):
+    out = torch.zeros(A.shape[0], W.shape[1], device='cuda')
+    for (r0, n_units, rpu, g0, gs) in segs:
+        for u in range(n_units):
+            sl = slice(r0 + u * rpu, r0 + (u + 1) * rpu)
+            out[sl] = A[sl].float() @ W[g0 + u * gs].float().t()
+    return out
+
+
+@pytest.mark.parametrize('rows,N,K,bn', [(128, 64, 64, 0), (1000, 256, 256, 256), (777, 768, 256, 0), (300, 384, 384, 128),
+                                         (4096 + 13, 1536, 384, 0)])
+def test_gemm_plain(rows, N, K, bn):
+    A, W = rnd(rows, K, seed=1), rnd(1, N, K, scale=0.1, seed=2)
+    out = torch.empty(rows, N, dtype=bf16, device='cuda')
+    ops.mixed_gemm(A, W, [(0, 1, rows, 0, 0)], out, block_n=bn)
+    close(out, A.float() @ W[0].float().t())
+
+
+@pytest.mark.parametrize('B', [32, 128, 200])
+def test_gemm_grouped_mixed_parameters(B):
+    """Shared S run + per-token NS runs in one launch (OT/model.py:84-92), partial tiles when B % 128 != 0."""
+    n_s, n_ns, K, N = 5, 6, 256, 512
+    rows = (n_s + n_ns) * B
+    A, W = rnd(rows, K, seed=3), rnd(1 + 8, N, K, scale=0.1, seed=4)
+    segs = [(0, 1, n_s * B, 0, 0), (n_s * B, n_ns, B, 3, 1)]     # NS tokens 2..7 -> groups 3..8
+    out = torch.full((rows, N), float('nan'), dtype=bf16, device='cuda')
+    ops.mixed_gemm(A, W, segs, out)
+    close(out, ref_rows_gemm(A, W, segs))
+
+
+def test_gemm_epilogues():
+    rows, N, K, G = 600, 1024, 256, 3
+    A, W = rnd(rows, K, seed=5), rnd(G, N, K, scale=0.1, seed=6)
+    bias = torch.randn(G, N, device='cuda')
+    res, aux = rnd(rows, N, seed=7), rnd(rows, N, seed=8)
+    rs = torch.rand(rows, device='cuda') + 0.5
+    segs = [(0, 1, 344, 0, 0), (344, 2, 128, 1, 1)]
+    base = ref_rows_gemm(A, W, segs)
+    gidx = torch.cat([torch.zeros(344), torch.ones(128), 2 * torch.ones(128)]).long().cuda()
+    # bias + gelu with the pre-activation kept
+    out, pre = torch.empty(rows, N, dtype=bf16, device='cuda'), torch.empty(rows, N, dtype=bf16, device='cuda')
+    ops.mixed_gemm(A, W, segs, out, flags=OT_EPI_BIAS | OT_EPI_GELU, bias=bias, out2=pre)
+    close(pre, base + bias[gidx])
+    close(out, torch.nn.functional.gelu(base + bias[gidx]))
+    # bias + residual
+    ops.mixed_gemm(A, W, segs, out, flags=OT_EPI_BIAS | OT_EPI_RESIDUAL, bias=bias, res=res)
+    close(out, base + bias[gidx] + res.float())
+    # gelu' multiply (backward of the FFN activation), row scale
+    x = aux.float().requires_grad_(True)
+    torch.nn.functional.gelu(x).sum().backward()
+    ops.mixed_gemm(A, W, segs, out, flags=OT_EPI_GELU_GRAD | OT_EPI_ROW_SCALE, aux=aux, row_scale=rs)
+    close(out, base * rs[:, None] * x.grad)
+    # in-place residual accumulation (out aliases res), as the Q-projection input gradient uses it
+    acc = res.clone()
+    ops.mixed_gemm(A, W, segs, acc, flags=OT_EPI_RESIDUAL, res=acc)
+    close(acc, base + res.float())
+
+
+def test_gemm_transposed_events_tokenizer_layout():
+    """[B, L_i, 64] events -> token-major rows (l, b) (OT/model.py:262-265 + DESIGN.md layout)."""
+    B, Li, E, d, off = 200, 7, 64, 256, 3
+    e, W = rnd(B, Li, E, seed=9), rnd(1, d, E, scale=0.2, seed=10)
+    bias = torch.randn(d, device='cuda')
+    out = torch.zeros((off + Li + 1) * B, d, dtype=bf16, device='cuda')
+    ops.mixed_gemm(e, W, [(off * B, Li, B, 0, 0)], out, flags=OT_EPI_BIAS, bias=bias, a_transposed_events=True)
+    ref = (e.float() @ W[0].float().t() + bias).transpose(0, 1).reshape(Li * B, d)
+    close(out[off * B:(off + Li) * B], ref)
+    assert out[:off * B].abs().max() == 0 and out[(off + Li) * B:].abs().max() == 0
+
+
+def test_gemm_rejects_unsupported_shapes():
+    A, W = rnd(128, 72), rnd(1, 64, 72)
+    with pytest.raises(_lib.OneTransLibraryError, match='K=72'):
+        ops.mixed_gemm(A, W, [(0, 1, 128, 0, 0)], torch.empty(128, 64, dtype=bf16, device='cuda'))
+    A, W = rnd(128, 64), rnd(1, 40, 64)
+    with pytest.raises(_lib.OneTransLibraryError, match='N=40'):
+        ops.mixed_gemm(A, W, [(0, 1, 128, 0, 0)], torch.empty(128, 40, dtype=bf16, device='cuda'))
+
+
+@pytest.mark.parametrize('B,n_s,n_ns', [(32, 9, 4), (256, 20, 3), (2048, 6, 2)])
+def test_wgrad_grouped(B, n_s, n_ns):
+    M, N = 256, 512
+    rows = (n_s + n_ns) * B
+    P, Q = rnd(rows, M, seed=11), rnd(rows, N, seed=12)
+    C = torch.zeros(1 + n_ns, M, N, device='cuda')
+    segs = [(0, 1, n_s * B, 0, 0), (n_s * B, n_ns, B, 1, 1)]
+    ops.wgrad_rows(P, Q, segs, C, M * N, N, 1)
+    ref = torch.zeros_like(C)
+    ref[0] = P[:n_s * B].float().t() @ Q[:n_s * B].float()
+    for j in range(n_ns):
+        sl = slice((n_s + j) * B, (n_s + j + 1) * B)
+        ref[1 + j] = P[sl].float().t() @ Q[sl].float()
+    err = ((C - ref).abs().max() / ref.abs().max()).item()
+    assert err < 2e-3, err
+    # accumulates (does not overwrite)
+    ops.wgrad_rows(P, Q, segs, C, M * N, N, 1)
+    assert ((C - 2 * ref).abs().max() / ref.abs().max()).item() < 2e-3
+
+
+def attn_ref(q, k, v, B, H, Lq, Lk, dh):
+    d = H * dh
+    q4 = q.float().view(Lq, B, H, dh).permute(1, 2, 0, 3)
+    k4 = k.float().view(Lk, B, H, dh).permute(1, 2, 0, 3)
+    v4 = v.float().view(Lk, B, H, dh).permute(1, 2, 0, 3)
+    s = q4 @ k4.transpose(-1, -2) / math.sqrt(dh)
+    qi = torch.arange(Lq, device='cuda')[:, None] + (Lk - Lq)
+    ki = torch.arange(Lk, device='cuda')[None, :]
+    s = torch.where(ki <= qi, s, torch.full_like(s, -1e9))       # OT/model.py:109-110
+    p = torch.softmax(s, -1)
+    o = (p @ v4).permute(2, 0, 1, 3).reshape(Lq * B, d)
+    lse = torch.logsumexp(s, -1)                                  # [B, H, Lq]
+    return o, lse
+
+
+@pytest.mark.parametrize('B,H,dh,Lq,Lk', [(3, 4, 64, 202, 288), (2, 4, 64, 458, 544), (5, 4, 64, 13, 27), (1, 4, 64, 8, 13),
+                                           (2, 4, 96, 224, 288), (2, 2, 64, 1, 1), (1, 4, 64, 1024, 2048)])
+def test_attention_forward_backward(B, H, dh, Lq, Lk):
+    d = H * dh
+    q = rnd(Lq * B, d, seed=13)
+    kv = rnd(Lk * B, 2 * d, seed=14)
+    do = rnd(Lq * B, d, seed=15)
+    o = torch.empty(Lq * B, d, dtype=bf16, device='cuda')
+    lse = torch.empty(B * H * Lq, device='cuda')
+    ops.attn_fwd(q, kv[:, :d], kv[:, d:], o, lse, B, H, Lq, Lk, dh)
+    qf, kf, vf = (t.float().requires_grad_(True) for t in (q, kv[:, :d], kv[:, d:]))
+    o_ref, lse_ref = attn_ref(qf, kf, vf, B, H, Lq, Lk, dh)
+    close(o, o_ref)
+    assert (lse.view(B, H, Lq) - lse_ref).abs().max().item() < 2e-3
+    (o_ref * do.float()).sum().backward()
+    dq = torch.empty_like(q)
+    dkv = torch.empty_like(kv)
+    delta = torch.empty(B * H * Lq, device='cuda')
+    ops.attn_bwd(q, kv[:, :d], kv[:, d:], o, lse, do, dq, dkv[:, :d], dkv[:, d:], delta, B, H, Lq, Lk, dh)
+    for got, ref in ((dq, qf.grad), (dkv[:, :d], kf.grad), (dkv[:, d:], vf.grad)):
+        # relative L2 error; the floor covers gradients that are identically zero (a single key: dS == 0)
+        assert ((got.float() - ref).norm() / (ref.norm() + 1e-3 * do.float().norm())).item() < 2e-2
+
+
+def test_attention_full_size_properties():
+    """BASELINE config 2, layer 0 (B=2048, H=4, Lq=458, Lk=544): with V == 1 every output is exactly 1 (softmax rows
+    sum to one) and lse matches a sampled fp32 reference."""
+    B, H, dh, Lq, Lk = 2048, 4, 64, 458, 544
+    d = H * dh
+    q = rnd(Lq * B, d, seed=16)
+    kv = rnd(Lk * B, 2 * d, seed=17)
+    kv[:, d:] = 1.0
+    o = torch.empty(Lq * B, d, dtype=bf16, device='cuda')
+    lse = torch.empty(B * H * Lq, device='cuda')
+    ops.attn_fwd(q, kv[:, :d], kv[:, d:], o, lse, B, H, Lq, Lk, dh)
+    assert (o.float() - 1.0).abs().max().item() < 1e-2
+    bsel = torch.tensor([0, 777, 2047], device='cuda')
+    qs = q.view(Lq, B, d)[:, bsel].reshape(Lq * 3, d)
+    ks = kv[:, :d].reshape(Lk, B, d)[:, bsel].reshape(Lk * 3, d)
+    _, lse_ref = attn_ref(qs, ks, ks, 3, H, Lq, Lk, dh)
+    assert (lse.view(B, H, Lq)[bsel] - lse_ref).abs().max().item() < 2e-3
+
+
+@pytest.mark.parametrize('rows,d', [(1000, 256), (333, 384), (64, 1024)])
+def test_rmsnorm_forward_backward(rows, d):
+    x, dy, dres = rnd(rows, d, seed=18), rnd(rows, d, seed=19), rnd(rows, d, seed=20)
+    g = torch.rand(d, device='cuda') + 0.5
+    y = torch.empty_like(x)
+    rstd = torch.empty(rows, device='cuda')
+    ops.rmsnorm_fwd(x, g, y, rstd, 1e-6)
+    xf = x.float().requires_grad_(True)
+    gf = g.clone().requires_grad_(True)
+    yr = xf * torch.rsqrt(xf.square().mean(-1, keepdim=True) + 1e-6) * gf     # OT/model.py:19-23
+    close(y, yr)
+    (yr * dy.float()).sum().backward()
+    dx = torch.empty_like(x)
+    dg = torch.zeros(d, device='cuda')
+    ops.rmsnorm_bwd(dy, x, rstd, g, dx, dg, dres=dres)
+    close(dx, xf.grad + dres.float())
+    assert ((dg - gf.grad).abs().max() / gf.grad.abs().max()).item() < 1e-2
+
+
+def test_ns_tokenizer_fill_rows_colsum():
+    B, L_ns, d, nf, row0 = 100, 5, 256, 11, 300
+    x = torch.randn(B, nf, device='cuda') * 30      # raw id-like magnitudes
+    W = torch.randn(nf, L_ns * d, device='cuda') * 0.05
+    b = torch.randn(L_ns * d, device='cuda')
+    out = torch.zeros(row0 + L_ns * B, d, dtype=bf16, device='cuda')
+    ops.ns_tokenizer_fwd(x, W, b, out, row0, B, L_ns, d)
+    ref = (x @ W + b).view(B, L_ns, d).transpose(0, 1).reshape(L_ns * B, d)     # OT/model.py:211-214 -> token-major
+    close(out[row0:], ref, 1e-2)
+    dout = rnd(row0 + L_ns * B, d, seed=21)
+    dW, db = torch.zeros_like(W), torch.zeros_like(b)
+    ops.ns_tokenizer_bwd(x, dout, dW, db, row0, B, L_ns, d)
+    g = dout[row0:].float().view(L_ns, B, d).transpose(0, 1).reshape(B, L_ns * d)
+    assert ((dW - x.t() @ g).abs().max() / (x.t() @ g).abs().max()).item() < 1e-4
+    assert ((db - g.sum(0)).abs().max() / g.sum(0).abs().max()).item() < 1e-4
+    vec = torch.randn(d, device='cuda')
+    ops.fill_rows(vec, out, 10, 7)
+    assert torch.equal(out[10:17], vec.to(bf16).expand(7, d)) and out[:10].abs().max() == 0 and out[17:row0].abs().max() == 0
+    inp = rnd(900, 384, seed=22)
+    o2 = torch.zeros(4, 384, device='cuda')
+    ops.colsum(inp, [(0, 1, 500, 0, 0), (500, 2, 200, 2, 1)], o2, 384)
+    ref = torch.stack([inp[:500].float().sum(0), torch.zeros(384, device='cuda'), inp[500:700].float().sum(0), inp[700:].float().sum(0)])
+    assert ((o2 - ref).abs().max() / ref.abs().max()).item() < 1e-4
+
+
+def test_full_size_gemm_c2_ffn():
+    """BASELINE config 2, layer 0 FFN-1 at full size: 458*2048 rows, K=256 -> N=1024, 33 weight groups,
+    checked against fp32 matmul on sampled row blocks (bit-for-bit layout check at scale)."""
+    B, n_s, n_ns, K, N = 2048, 426, 32, 256, 1024
+    rows = (n_s + n_ns) * B
+    A, W = rnd(rows, K, seed=23), rnd(33, N, K, scale=0.1, seed=24)
+    bias = torch.randn(33, N, device='cuda')
+    out = torch.empty(rows, N, dtype=bf16, device='cuda')
+    segs = [(0, 1, n_s * B, 0, 0), (n_s * B, n_ns, B, 1, 1)]
+    ops.mixed_gemm(A, W, segs, out, flags=OT_EPI_BIAS, bias=bias)
+    for r0, g in [(0, 0), (n_s * B - 300, 0), (n_s * B, 1), ((n_s + 31) * B + 1000, 32), (rows - 128, 32), (500000, 0)]:
+        sl = slice(r0, r0 + 128)
+        close(out[sl], A[sl].float() @ W[g].float().t() + bias[g])

@@ -1,0 +1,139 @@
+"""CPU tests of the host logic: configuration mirror, pyramid scheduler (bit-exact index selection),
+weight-group segments, and the C-ABI library (loads, exports every declared symbol, struct layouts match
+the ctypes mirror).  No kernel is launched here."""
+import ctypes
+import os
+import re
+import subprocess
+import tempfile
+
+import pytest
+import torch
+
+from oracle import onetrans_oracle as O
+import recommend_b200 as R
+from recommend_b200 import _lib, ops
+from recommend_b200.schedule import (keep_lens_halving, keep_lens_linear_to_ns, keep_lens_reference_ratio)
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, 'include', 'onetrans_b200.h')
+
+
+def test_config_mirrors_reference_defaults():
+    c = R.OneTransConfig()   # OT/config.py:14-69
+    assert (c.hidden_dim, c.num_layers, c.num_heads, c.ffn_dim) == (384, 8, 4, 1536)
+    assert c.num_ns_tokens == 12 and c.max_seq_len == 2048 and c.dropout_rate == 0.1
+    assert c.pyramid_ratios == [0.5, 0.3, 0.2, 0.1, 0.05, 0.03, 0.02, 0.01]
+    assert c.feature_config['sequence_features'] == ['click_seq', 'cart_seq', 'purchase_seq']
+    assert c.tasks == ['ctr', 'cvr'] and c.gradient_clip_norm == 90.0
+    s = R.get_model_config('small')
+    assert (s.hidden_dim, s.num_layers, s.ffn_dim, s.num_heads) == (256, 6, 1024, 4)
+    l = R.get_model_config('large')
+    assert (l.hidden_dim, l.num_layers, l.num_heads, l.ffn_dim) == (512, 12, 8, 2048)
+    assert type(R.get_model_config('base')) is R.OneTransConfig          # D8 alias
+    with pytest.raises(ValueError):
+        R.get_model_config('nope')
+    d = c.to_dict()
+    c2 = R.OneTransConfig.from_dict({**d, 'hidden_dim': 128, 'unknown_key': 1})
+    assert c2.hidden_dim == 128 and not hasattr(c2, 'unknown_key')
+    assert len(c.ns_features) == 11
+
+
+def test_scheduler_matches_reference_and_oracle():
+    cfg = R.get_model_config('small')
+    sch = R.PyramidScheduler(cfg)
+    for L0 in [1, 2, 21, 272, 544, 1202, 2048]:
+        for l in range(10):
+            got = sch.get_layer_config(l, L0)
+            want = O.reference_query_indices(l, L0, cfg.pyramid_ratios)
+            assert got['query_indices'] == want
+            if want is not None:
+                assert got['keep_len'] == len(want)
+    assert keep_lens_reference_ratio(544, 6, cfg.pyramid_ratios) == O.keep_lens_reference_ratio(544, 6, cfg.pyramid_ratios)
+    assert keep_lens_linear_to_ns(544, 6, 32) == [458, 373, 288, 202, 117, 32]
+    assert keep_lens_halving(2048, 6, 32) == [1024, 512, 256, 128, 64, 32]
+    cfg.pyramid_enabled = False
+    assert sch.get_layer_config(0, 100)['query_indices'] is None
+    assert R.resolve_keep_lens(cfg, 100) == [100] * 6
+    cfg.pyramid_enabled = True
+    cfg.pyramid_keep_lens = [50, 60, 10, 10, 10, 3]
+    assert R.resolve_keep_lens(cfg, 55) == [50, 50, 10, 10, 10, 3]     # clamped to the current length
+
+
+@pytest.mark.parametrize('alignment', ['tail', 'head_literal'])
+def test_position_segments_match_oracle_rule(alignment):
+    """The segment table handed to the grouped GEMM covers every position exactly once with the group the
+    per-position rule of OT/model.py:67-74 (or its D4 repair) assigns."""
+    B = 3
+    for L_ns in (1, 4, 16):
+        for cur in (1, 3, 5, 16, 17, 40):
+            for p0 in sorted({0, cur // 3, max(cur - L_ns, 0), max(cur - 2, 0), cur - 1}):
+                segs = ops.position_segments(p0, cur, cur, L_ns, alignment, B)
+                got = {}
+                for (row_start, n_units, rpu, g0, gs) in segs:
+                    for u in range(n_units):
+                        for r in range(rpu):
+                            row = row_start + u * rpu + r
+                            assert row not in got
+                            got[row] = g0 + u * gs
+                assert sorted(got) == list(range((cur - p0) * B))
+                for p in range(p0, cur):
+                    for b in range(B):
+                        assert got[(p - p0) * B + b] == O.group_of_position(p, cur, L_ns, alignment)
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    lib = _lib.load()
+    assert lib.ot_version() == 1
+    declared = set(re.findall(r'^\s*(?:int|const char\*)\s+(ot_\w+)\s*\(', open(HEADER).read(), re.M))
+    assert declared == set(_lib.EXPORTED_SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), name
+
+
+def test_ctypes_structs_match_header_layout():
+    """Compile a C probe that prints sizeof/offsetof for every params struct and compare with ctypes."""
+    pairs = [('ot_gemm_seg', _lib.GemmSeg), ('ot_gemm_params', _lib.GemmParams), ('ot_wgrad_seg', _lib.WgradSeg),
+             ('ot_wgrad_params', _lib.WgradParams), ('ot_attn_params', _lib.AttnParams), ('ot_rmsnorm_params', _lib.RmsnormParams),
+             ('ot_ns_tokenizer_params', _lib.NsTokenizerParams), ('ot_colsum_params', _lib.ColsumParams)]
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', 'int main(void){']
+    for cname, st in pairs:
+        lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in st._fields_:
+            lines.append(f'printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname.rstrip("_")}));')
+    lines += ['return 0;}']
+    with tempfile.TemporaryDirectory() as td:
+        src, exe = os.path.join(td, 'p.c'), os.path.join(td, 'p')
+        open(src, 'w').write('\n'.join(lines))
+        subprocess.check_call(['gcc', '-o', exe, src])
+        out = dict(l.split() for l in subprocess.check_output([exe]).decode().splitlines())
+    for cname, st in pairs:
+        assert int(out[cname]) == ctypes.sizeof(st), cname
+        for fname, _ in st._fields_:
+            assert int(out[f'{cname}.{fname}']) == getattr(st, fname).offset, (cname, fname)
+
+
+def test_modules_refuse_cpu_tensors():
+    cfg = R.get_model_config('small')
+    cfg.num_layers, cfg.num_ns_tokens = 1, 2
+    m = R.OneTransModel(cfg)
+    non_seq, seq, _ = O.synthetic_batch(O.small_config(num_ns_tokens=2), 2, (3, 3, 3))
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        m(non_seq, seq)
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        R.RMSNorm(8)(torch.zeros(2, 8))
+
+
+def test_param_name_map_roundtrip_and_counts():
+    ocfg = O.small_config(num_ns_tokens=32)
+    cfg = R.get_model_config('small')
+    cfg.num_ns_tokens = 32
+    m = R.OneTransModel(cfg)
+    info = m.get_model_info()
+    assert info['total_parameters'] == O.count_params(O.init_params(O.small_config(num_ns_tokens=32))) 
+    assert abs(info['total_parameters'] / 1e6 - 143.6) < 0.1
+    P = O.init_params(ocfg, seed=3)
+    R.load_reference_style_params(m, P)
+    E = R.export_reference_style_params(m)
+    assert set(E) == set(P)
+    assert all(torch.equal(E[k], P[k].reshape(E[k].shape)) for k in P)
