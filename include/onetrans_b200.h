@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define OT_ABI_VERSION 1
+#define OT_ABI_VERSION 2
 
 int ot_version(void);
 const char* ot_last_error_string(void);
@@ -82,6 +82,13 @@ typedef struct ot_gemm_params {
   const float* row_scale;
   int32_t block_n;       /* 0 = choose */
   int32_t swizzle;       /* 0 = 128-byte swizzle (default); 64 selects the 64-byte variant */
+  /* High-precision residual stream of the NS-token rows: output rows >= hp_row0 (must be the
+   * row_start of an NS segment) take their residual from res_hp (fp32, row 0 <-> output row hp_row0) instead
+   * of `res`, and also write the fp32 result to out_hp.  Only with OT_EPI_RESIDUAL.  NULL = off. */
+  const float* res_hp;
+  float* out_hp;
+  int64_t ld_hp;
+  int64_t hp_row0;
 } ot_gemm_params;
 
 int ot_mixed_gemm(const ot_gemm_params* p, void* stream);
@@ -147,6 +154,27 @@ int ot_attn_fwd(const ot_attn_params* p, void* stream);
 int ot_attn_bwd(const ot_attn_params* p, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Inference attention with a cross-candidate cache of the sequence-side K/V (PAPER:144-151; the reference's
+ * own cache branch OT/model.py:95-98 is unusable).  One user, C candidates:
+ *   shared keys/values : [Ls, ld_shared] rows of the S tokens, identical for every candidate (B = 1 layout)
+ *   own keys/values    : [Tn*C, ld_own]  rows (token-major: row = t*C + c) of the Tn surviving NS tokens
+ *   queries            : [Tq*C, ldq]     the last Tq NS tokens;  output o [Tq*C, ldo]
+ * Query token i attends every shared key and own keys 0 .. (Tn-Tq)+i of ITS candidate.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct ot_attn_cached_params {
+  const void* q; int64_t ldq;
+  const void* k_own; int64_t ld_own_k;
+  const void* v_own; int64_t ld_own_v;
+  const void* k_shared; int64_t ld_shared_k;
+  const void* v_shared; int64_t ld_shared_v;
+  void* o; int64_t ldo;
+  int32_t C, H, Tq, Tn, Ls;
+  int32_t head_dim;
+} ot_attn_cached_params;
+
+int ot_attn_ns_cached_fwd(const ot_attn_cached_params* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * RMSNorm (OT/model.py:19-23):  y = x * rsqrt(mean(x^2,-1) + eps) * gain.   HBM-bound, one warp per row.
  * forward : x, gain -> y, rstd (fp32 per row; may be NULL)
  * backward: dy, x, rstd, gain -> dx (+= dres if dres != NULL), dgain += sum_rows dy * x * rstd (fp32 atomics)
@@ -163,6 +191,9 @@ typedef struct ot_rmsnorm_params {
   int64_t rows;
   int32_t d;
   float eps;
+  /* forward only: rows >= hp_row0 are read from x_hp (fp32 [rows-hp_row0, d]) instead of x.  NULL = off. */
+  const float* x_hp;
+  int64_t hp_row0;
 } ot_rmsnorm_params;
 
 int ot_rmsnorm_fwd(const ot_rmsnorm_params* p, void* stream);
@@ -180,6 +211,7 @@ typedef struct ot_ns_tokenizer_params {
   float* dW; float* dbias;
   int64_t row0;
   int32_t B, L_ns, d, n_feat;
+  float* out_hp;         /* optional fp32 copy of the NS rows, [L_ns*B, d] (forward) */
 } ot_ns_tokenizer_params;
 
 int ot_ns_tokenizer_fwd(const ot_ns_tokenizer_params* p, void* stream);

@@ -1,0 +1,46 @@
+"""Launches the hot kernels once each at BASELINE config 2 / layer 0 sizes (B 2048, 458 query rows of 544) so that
+ncu can capture them in isolation:  python profiles/prof_kernels.py [gemm|attn|all]"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from recommend_b200 import ops
+from recommend_b200._lib import OT_EPI_BIAS, OT_EPI_GELU, OT_EPI_GELU_GRAD, OT_EPI_RESIDUAL
+
+what = sys.argv[1] if len(sys.argv) > 1 else 'all'
+bf16 = torch.bfloat16
+B, Lq, Lk, d, F, H = 2048, 458, 544, 256, 1024, 4
+rows = Lq * B
+g = torch.Generator(device='cuda').manual_seed(0)
+rnd = lambda *s: (torch.randn(*s, generator=g, device='cuda')).to(bf16)
+segs = ops.position_segments(Lk - Lq, Lk, Lk, 32, 'tail', B)
+if what in ('gemm', 'all'):
+    zn, W1 = rnd(rows, d), rnd(33, F, d) * 0.1
+    b1 = torch.randn(33, F, device='cuda')
+    h, pre = torch.empty(rows, F, dtype=bf16, device='cuda'), torch.empty(rows, F, dtype=bf16, device='cuda')
+    for _ in range(2):
+        ops.mixed_gemm(zn, W1, segs, h, flags=OT_EPI_BIAS | OT_EPI_GELU, bias=b1, out2=pre)          # FFN-1 forward
+    dy, W2b = rnd(rows, d), rnd(33, F, d) * 0.1
+    dpre = torch.empty(rows, F, dtype=bf16, device='cuda')
+    for _ in range(2):
+        ops.mixed_gemm(dy, W2b, segs, dpre, flags=OT_EPI_GELU_GRAD, aux=pre)                          # FFN-2 input gradient
+    W2 = rnd(33, d, F) * 0.1
+    y = torch.empty(rows, d, dtype=bf16, device='cuda')
+    for _ in range(2):
+        ops.mixed_gemm(h, W2, segs, y, flags=OT_EPI_BIAS | OT_EPI_RESIDUAL, bias=b1[:, :d].contiguous(), res=zn)   # FFN-2 forward
+    dW = torch.zeros(33, d, F, device='cuda')
+    for _ in range(2):
+        ops.wgrad_rows(zn, dpre, segs, dW, d * F, F, 1)                                               # dW1
+if what in ('attn', 'all'):
+    q, kv, do = rnd(rows, d), rnd(Lk * B, 2 * d), rnd(rows, d)
+    o = torch.empty(rows, d, dtype=bf16, device='cuda')
+    lse = torch.empty(B * H * Lq, device='cuda')
+    for _ in range(2):
+        ops.attn_fwd(q, kv[:, :d], kv[:, d:], o, lse, B, H, Lq, Lk, d // H)
+    dq, dkv = torch.empty_like(q), torch.empty_like(kv)
+    delta = torch.empty(B * H * Lq, device='cuda')
+    for _ in range(2):
+        ops.attn_bwd(q, kv[:, :d], kv[:, d:], o, lse, do, dq, dkv[:, :d], dkv[:, d:], delta, B, H, Lq, Lk, d // H)
+torch.cuda.synchronize()
+print('done')

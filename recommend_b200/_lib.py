@@ -27,7 +27,7 @@ class GemmParams(C.Structure):
                 ('n_segs', i32), ('flags', i32), ('segs', GemmSeg * 3),
                 ('out', vp), ('ldo', i64), ('out2', vp), ('ldo2', i64), ('res', vp), ('ldr', i64),
                 ('aux', vp), ('ldaux', i64), ('bias', fp), ('bias_group_stride', i64), ('row_scale', fp),
-                ('block_n', i32), ('swizzle', i32)]
+                ('block_n', i32), ('swizzle', i32), ('res_hp', fp), ('out_hp', fp), ('ld_hp', i64), ('hp_row0', i64)]
 
 
 class WgradSeg(C.Structure):
@@ -49,15 +49,21 @@ class AttnParams(C.Structure):
                 ('head_dim', i32), ('swizzle', i32)]
 
 
+class AttnCachedParams(C.Structure):
+    _fields_ = [('q', vp), ('ldq', i64), ('k_own', vp), ('ld_own_k', i64), ('v_own', vp), ('ld_own_v', i64),
+                ('k_shared', vp), ('ld_shared_k', i64), ('v_shared', vp), ('ld_shared_v', i64), ('o', vp), ('ldo', i64),
+                ('C', i32), ('H', i32), ('Tq', i32), ('Tn', i32), ('Ls', i32), ('head_dim', i32)]
+
+
 class RmsnormParams(C.Structure):
     _fields_ = [('x', vp), ('ldx', i64), ('y', vp), ('ldy', i64), ('gain', fp), ('rstd', fp),
                 ('dy', vp), ('lddy', i64), ('dres', vp), ('lddres', i64), ('dx', vp), ('lddx', i64),
-                ('dgain', fp), ('rows', i64), ('d', i32), ('eps', C.c_float)]
+                ('dgain', fp), ('rows', i64), ('d', i32), ('eps', C.c_float), ('x_hp', fp), ('hp_row0', i64)]
 
 
 class NsTokenizerParams(C.Structure):
     _fields_ = [('x', fp), ('W', fp), ('bias', fp), ('out', vp), ('dout', vp), ('ldo', i64), ('dW', fp),
-                ('dbias', fp), ('row0', i64), ('B', i32), ('L_ns', i32), ('d', i32), ('n_feat', i32)]
+                ('dbias', fp), ('row0', i64), ('B', i32), ('L_ns', i32), ('d', i32), ('n_feat', i32), ('out_hp', fp)]
 
 
 class ColsumParams(C.Structure):
@@ -67,7 +73,7 @@ class ColsumParams(C.Structure):
 
 # every symbol include/onetrans_b200.h declares (tests check that the library exports all of them)
 EXPORTED_SYMBOLS = [
-    'ot_version', 'ot_last_error_string', 'ot_num_sms', 'ot_mixed_gemm', 'ot_wgrad', 'ot_attn_fwd', 'ot_attn_bwd',
+    'ot_version', 'ot_last_error_string', 'ot_num_sms', 'ot_mixed_gemm', 'ot_wgrad', 'ot_attn_fwd', 'ot_attn_bwd', 'ot_attn_ns_cached_fwd',
     'ot_rmsnorm_fwd', 'ot_rmsnorm_bwd', 'ot_ns_tokenizer_fwd', 'ot_ns_tokenizer_bwd', 'ot_fill_rows', 'ot_colsum',
 ]
 
@@ -96,7 +102,7 @@ def load() -> C.CDLL:
         lib.ot_last_error_string.restype = C.c_char_p
         lib.ot_num_sms.restype = C.c_int
         for name, st in [('ot_mixed_gemm', GemmParams), ('ot_wgrad', WgradParams), ('ot_attn_fwd', AttnParams),
-                         ('ot_attn_bwd', AttnParams), ('ot_rmsnorm_fwd', RmsnormParams), ('ot_rmsnorm_bwd', RmsnormParams),
+                         ('ot_attn_bwd', AttnParams), ('ot_attn_ns_cached_fwd', AttnCachedParams), ('ot_rmsnorm_fwd', RmsnormParams), ('ot_rmsnorm_bwd', RmsnormParams),
                          ('ot_ns_tokenizer_fwd', NsTokenizerParams), ('ot_ns_tokenizer_bwd', NsTokenizerParams),
                          ('ot_colsum', ColsumParams)]:
             fn = getattr(lib, name)

@@ -66,6 +66,7 @@ class OneTransConfig:
         self.pyramid_schedule = 'reference_ratio'      # 'reference_ratio' | 'linear_to_ns' | 'halving'
         self.ns_feature_names: Optional[List[str]] = None    # features the NS Dense is built with (None = all)
         self.rms_eps = 1e-6                            # OT/model.py:14
+        self.hp_ns_residual = True                     # fp32 residual stream for the NS-token rows
 
     # OT/config.py:71-82
     def to_dict(self) -> Dict:

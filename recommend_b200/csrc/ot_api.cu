@@ -42,6 +42,7 @@ int mixed_gemm_impl(const ot_gemm_params* p, cudaStream_t st);
 int wgrad_impl(const ot_wgrad_params* p, cudaStream_t st);
 int attn_fwd_impl(const ot_attn_params* p, cudaStream_t st);
 int attn_bwd_impl(const ot_attn_params* p, cudaStream_t st);
+int attn_cached_impl(const ot_attn_cached_params* p, cudaStream_t st);
 int rmsnorm_fwd_impl(const ot_rmsnorm_params* p, cudaStream_t st);
 int rmsnorm_bwd_impl(const ot_rmsnorm_params* p, cudaStream_t st);
 int ns_tokenizer_fwd_impl(const ot_ns_tokenizer_params* p, cudaStream_t st);
@@ -71,6 +72,9 @@ int ot_attn_bwd(const ot_attn_params* p, void* stream) {
   return ot::attn_bwd_impl(p, static_cast<cudaStream_t>(stream));
 }
 
+int ot_attn_ns_cached_fwd(const ot_attn_cached_params* p, void* stream) {
+  return ot::attn_cached_impl(p, static_cast<cudaStream_t>(stream));
+}
 int ot_rmsnorm_fwd(const ot_rmsnorm_params* p, void* stream) { return ot::rmsnorm_fwd_impl(p, static_cast<cudaStream_t>(stream)); }
 int ot_rmsnorm_bwd(const ot_rmsnorm_params* p, void* stream) { return ot::rmsnorm_bwd_impl(p, static_cast<cudaStream_t>(stream)); }
 int ot_ns_tokenizer_fwd(const ot_ns_tokenizer_params* p, void* stream) { return ot::ns_tokenizer_fwd_impl(p, static_cast<cudaStream_t>(stream)); }

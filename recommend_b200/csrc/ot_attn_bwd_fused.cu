@@ -10,9 +10,11 @@
 // dV_j / dK_j stay in TMEM for the whole item; the dQ partial of every step leaves through vectorised
 // bf16x2 reductions (REDG.ADD.BF16x8) into a zero-initialised dQ.
 //
-// Warp roles: warps 0-7 element-wise (thread = one score row x 64 columns), warp 8 = control (TMA + MMA
-// issue by one elected lane).  The control warp issues S/dP of step i+1 as soon as the element-wise warps
-// have pulled S/dP of step i out of TMEM, so the tensor pipe works under the exp/convert phase.
+// Warp roles: warps 0-7 element-wise (thread = one score row x 64 columns); warp 8 issues every tcgen05.mma
+// (descriptors hoisted, S/dP of step i+1 issued as soon as the element-wise warps have pulled S/dP of step i out
+// of TMEM, so the tensor pipe works under the exp/convert phase); warp 9 walks the work list, publishes a step
+// ring in smem and keeps TMA two steps (Q, dO) and one item (K, V) ahead through full/empty mbarrier rings.
+#include <stdlib.h>
 #include "ot_attn.cuh"
 #include "ot_host.h"
 #include "../../include/onetrans_b200.h"
@@ -27,21 +29,70 @@ struct AttnBwdFusedKParams {
   __nv_bfloat16* dq; long long lddq;
   __nv_bfloat16* dk; long long lddk;
   __nv_bfloat16* dv; long long lddv;
+  int dbg;   // profiling experiments only (env OT_DEBUG_ATTN_BWD): bit0 = skip the dQ reductions, bit1 = phase timers
+  unsigned long long* dbg_buf;
 };
 
 static constexpr float kLog2eF = 1.4426950408889634f;
-static constexpr int FB_THREADS = 288;
+static constexpr int FB_THREADS = 320;   // 8 element-wise warps + MMA warp + loader warp
 static constexpr int FB_DH = 64;
 
 struct AttnBwdFusedCfg {
   using T = AttnTile<FB_DH, 128>;
-  static constexpr int SMEM_BYTES = T::TILE_BYTES * 6 + 2 * PT_BYTES + 256;
+  static constexpr int KV_BUFS = 2;     // K_j/V_j of the next item are fetched while this item runs
+  static constexpr int Q_STAGES = 2;    // Q_i/dO_i are fetched one step ahead
+  static constexpr int INFO_SLOTS = 8;
+  static constexpr int STG_BYTES = 128 * 128;   // one [128 x 64] bf16 output tile staged for coalesced stores
+  static constexpr int TILES_BYTES = T::TILE_BYTES * (2 * KV_BUFS + 2 * Q_STAGES) + 2 * PT_BYTES + STG_BYTES;
+  static constexpr int SMEM_BYTES = TILES_BYTES + INFO_SLOTS * 32 + 256;
   static constexpr uint32_t T_S = 0, T_DP = 128, T_DV = 256, T_DK = 320, T_DQ = 384;
 };
 
 __device__ __forceinline__ void red_add_bf16x8(__nv_bfloat16* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("red.global.add.noftz.v4.bf16x2 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
+
+// One entry of the step ring the loader warp publishes for the MMA warp and the element-wise warps.
+struct __align__(16) StepInfo {
+  int q0, k0, b, h;
+  int flags;        // bit0 first step of its item, bit1 last step of its item, bit2 last step of this CTA, bit3 K/V buffer
+  int next_q0;      // query tile of the NEXT step (row statistics are fetched one step ahead), -1 if none
+  int next_bh;      // b*H + h of the next step
+  int pad;
+};
+enum { SI_FIRST = 1, SI_LAST = 2, SI_END = 4, SI_KVBUF = 8 };
+
+// Walks the (item, query tile) steps of one CTA in launch order (loader warp only).
+struct StepCursor {
+  int item, ii, n_i, i_min, h, b, k0, item_idx;
+  bool valid;
+  __device__ __forceinline__ void load_item(const AttnBwdFusedKParams& p) {
+    valid = item < p.total_items;
+    if (!valid) return;
+    const int kt = item % p.n_kt;   // early key tiles are seen by the most query tiles
+    const int bh = item / p.n_kt;
+    h = bh % p.H;
+    b = bh / p.H;
+    k0 = kt * 128;
+    const int off = p.Lk - p.Lq;
+    i_min = (k0 - off) < 0 ? 0 : (k0 - off) / 128;
+    n_i = p.n_qt - i_min;
+    ii = 0;
+  }
+  __device__ __forceinline__ void init(const AttnBwdFusedKParams& p) {
+    item = blockIdx.x;
+    item_idx = 0;
+    load_item(p);
+  }
+  __device__ __forceinline__ void next(const AttnBwdFusedKParams& p) {
+    if (++ii == n_i) {
+      item += gridDim.x;
+      ++item_idx;
+      load_item(p);
+    }
+  }
+  __device__ __forceinline__ int q0() const { return (i_min + ii) * 128; }
+};
 
 __global__ void __launch_bounds__(FB_THREADS, 1)
 ot_attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -52,22 +103,26 @@ ot_attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   using T = AttnTile<DH, SWB>;
   using Cfg = AttnBwdFusedCfg;
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* sK = smem;
-  uint8_t* sV = sK + T::TILE_BYTES;
-  uint8_t* sQ = sV + T::TILE_BYTES;          // [2]
-  uint8_t* sdO = sQ + 2 * T::TILE_BYTES;     // [2]
-  uint8_t* sP = sdO + 2 * T::TILE_BYTES;
+  uint8_t* sK = smem;                                      // [KV_BUFS]
+  uint8_t* sV = sK + Cfg::KV_BUFS * T::TILE_BYTES;         // [KV_BUFS]
+  uint8_t* sQ = sV + Cfg::KV_BUFS * T::TILE_BYTES;         // [Q_STAGES]
+  uint8_t* sdO = sQ + Cfg::Q_STAGES * T::TILE_BYTES;       // [Q_STAGES]
+  uint8_t* sP = sdO + Cfg::Q_STAGES * T::TILE_BYTES;
   uint8_t* sdS = sP + PT_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sdS + PT_BYTES);
-  uint64_t* bar_kv = bars;          // K_j, V_j landed                 (per item)
-  uint64_t* bar_q = bars + 1;       // [2] Q_i, dO_i landed            (per stage use)
-  uint64_t* bar_s = bars + 3;       // S, dP MMAs complete             (per step)
-  uint64_t* bar_sread = bars + 4;   // E warps pulled S, dP out of TMEM (per step, 8 arrivals)
-  uint64_t* bar_pds = bars + 5;     // P, dS tiles written             (per step, 8 arrivals)
-  uint64_t* bar_d = bars + 6;       // dV, dK, dQp MMAs complete       (per step)
-  uint64_t* bar_dqfree = bars + 7;  // E warps pulled dQp out of TMEM  (per step, 8 arrivals)
-  uint64_t* bar_accfree = bars + 8; // E warps pulled dV, dK out       (per item, 8 arrivals)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  uint8_t* sStg = sdS + PT_BYTES;
+  StepInfo* info = reinterpret_cast<StepInfo*>(smem + Cfg::TILES_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::TILES_BYTES + Cfg::INFO_SLOTS * 32);
+  uint64_t* bar_kv = bars;            // [2] K_j, V_j landed                     (loader -> MMA)
+  uint64_t* bar_kvfree = bars + 2;    // [2] MMAs of the item's last step done   (MMA commit -> loader)
+  uint64_t* bar_q = bars + 4;         // [Q_STAGES] Q_i, dO_i landed (+ step info) (loader -> MMA)
+  uint64_t* bar_qfree = bars + 7;     // [Q_STAGES] MMAs of the step done          (MMA commit -> loader)
+  uint64_t* bar_s = bars + 10;        // S, dP MMAs complete                     (per step)
+  uint64_t* bar_sread = bars + 11;    // E warps pulled S, dP out of TMEM        (per step, 8 arrivals)
+  uint64_t* bar_pds = bars + 12;      // P, dS tiles written                     (per step, 8 arrivals)
+  uint64_t* bar_d = bars + 13;        // dV, dK, dQp MMAs complete               (per step)
+  uint64_t* bar_dqfree = bars + 14;   // E warps pulled dQp out of TMEM          (per step, 8 arrivals)
+  uint64_t* bar_accfree = bars + 15;  // E warps pulled dV, dK out               (per item, 8 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -76,9 +131,8 @@ ot_attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   if (tid == 0) {
     if ((smem_u32(smem) & 1023u) != 0) __trap();
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmdO);
-    mbar_init(bar_kv, 1);
-    mbar_init(&bar_q[0], 1);
-    mbar_init(&bar_q[1], 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&bar_kv[i], 1); mbar_init(&bar_kvfree[i], 1); }
+    for (int i = 0; i < Cfg::Q_STAGES; ++i) { mbar_init(&bar_q[i], 1); mbar_init(&bar_qfree[i], 1); }
     mbar_init(bar_s, 1);
     mbar_init(bar_sread, 8);
     mbar_init(bar_pds, 8);
@@ -94,80 +148,111 @@ ot_attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   const uint32_t tmem_base = *tmem_slot;
   const int off = p.Lk - p.Lq;
 
-  if (warp == 8) {
-    // ============================== control warp: TMA + MMA issue ==============================
+  if (warp == 9) {
+    // ============================== loader warp: step ring + TMA ==============================
+    if (elect_one()) {
+      StepCursor c;
+      c.init(p);
+      uint32_t t = 0;
+      while (c.valid) {
+        const int st = t % Cfg::Q_STAGES;
+        const int kb = c.item_idx & 1;
+        const bool first = c.ii == 0, last = c.ii == c.n_i - 1;
+        if (t >= Cfg::Q_STAGES) mbar_wait(&bar_qfree[st], ((t / Cfg::Q_STAGES) - 1) & 1);   // stage's previous reader done
+        if (first && c.item_idx >= 2) mbar_wait(&bar_kvfree[kb], ((c.item_idx >> 1) - 1) & 1);   // buffer's previous item done
+        StepCursor n = c;
+        n.next(p);
+        StepInfo si;
+        si.q0 = c.q0(); si.k0 = c.k0; si.b = c.b; si.h = c.h;
+        si.flags = (first ? SI_FIRST : 0) | (last ? SI_LAST : 0) | (n.valid ? 0 : SI_END) | (kb ? SI_KVBUF : 0);
+        si.next_q0 = n.valid ? n.q0() : -1;
+        si.next_bh = n.valid ? n.b * p.H + n.h : 0;
+        si.pad = 0;
+        info[t & (Cfg::INFO_SLOTS - 1)] = si;     // published by the release-arrive on bar_q below
+        if (first) {
+          mbar_arrive_expect_tx(&bar_kv[kb], 2 * T::TILE_BYTES);
+          load_head_tile<DH, SWB>(sK + kb * T::TILE_BYTES, &tmK, &bar_kv[kb], c.h, c.b, c.k0);
+          load_head_tile<DH, SWB>(sV + kb * T::TILE_BYTES, &tmV, &bar_kv[kb], c.h, c.b, c.k0);
+        }
+        mbar_arrive_expect_tx(&bar_q[st], 2 * T::TILE_BYTES);
+        load_head_tile<DH, SWB>(sQ + st * T::TILE_BYTES, &tmQ, &bar_q[st], c.h, c.b, si.q0);
+        load_head_tile<DH, SWB>(sdO + st * T::TILE_BYTES, &tmdO, &bar_q[st], c.h, c.b, si.q0);
+        c = n;
+        ++t;
+      }
+    }
+  } else if (warp == 8) {
+    // ============================== MMA warp ==============================
     if (elect_one()) {
       constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
       constexpr uint32_t idesc_t = make_idesc_bf16(128, DH, 1, 1);   // P^T dO, dS^T Q: both operands MN-major
       constexpr uint32_t idesc_q = make_idesc_bf16(128, DH, 0, 1);   // dS K: A K-major, B MN-major
-      uint32_t g = 0;               // global step counter of this CTA
-      uint32_t q_uses[2] = {0, 0};
-      uint32_t n_items = 0;
-      auto issue_s_dp = [&](int st) {
-        const uint32_t aQ = smem_u32(sQ + st * T::TILE_BYTES), aK = smem_u32(sK);
-        const uint32_t adO = smem_u32(sdO + st * T::TILE_BYTES), aV = smem_u32(sV);
+      // descriptor bases (the per-k advance is a compile-time constant added to the 14-bit address field)
+      const uint64_t dP_mn = make_smem_desc<128>(smem_u32(sP), PT_SLAB_BYTES);
+      const uint64_t dS_mn = make_smem_desc<128>(smem_u32(sdS), PT_SLAB_BYTES);
+      const uint64_t dS_k0 = make_smem_desc<128>(smem_u32(sdS), 16);
+      const uint64_t dS_k1 = make_smem_desc<128>(smem_u32(sdS) + PT_SLAB_BYTES, 16);
+      const uint64_t tileK = make_smem_desc<SWB>(0, 16);                // K-major [128 x 64] tile, address added below
+      const uint64_t tileMN = make_smem_desc<SWB>(0, T::SLAB_BYTES);    // MN-major use of the same tile
+      auto addr14 = [](uint32_t a) -> uint64_t { return static_cast<uint64_t>((a & 0x3FFFFu) >> 4); };
+      uint32_t g = 0;
+      uint32_t n_items = 0;      // items whose first step has been issued
+      bool end = false;
+
+      auto issue_sdp = [&](uint32_t t) {   // S = Q K^T, dP = dO V^T of step t
+        const int st = t % Cfg::Q_STAGES;
+        mbar_wait(&bar_q[st], (t / Cfg::Q_STAGES) & 1);           // also publishes info[t]
+        const StepInfo si = info[t & (Cfg::INFO_SLOTS - 1)];
+        const int kb = (si.flags & SI_KVBUF) ? 1 : 0;
+        if (si.flags & SI_FIRST) {
+          const uint32_t idx = n_items;                           // per-CTA item index of this item
+          mbar_wait(&bar_kv[kb], (idx >> 1) & 1);
+          ++n_items;
+        }
+        if (t >= 1) mbar_wait(bar_sread, (t - 1) & 1);            // S/dP columns free
+        tc_fence_after();
+        const uint64_t aQ = tileK + addr14(smem_u32(sQ + st * T::TILE_BYTES)), aK = tileK + addr14(smem_u32(sK + kb * T::TILE_BYTES));
+        const uint64_t adO = tileK + addr14(smem_u32(sdO + st * T::TILE_BYTES)), aV = tileK + addr14(smem_u32(sV + kb * T::TILE_BYTES));
 #pragma unroll
         for (int kk = 0; kk < DH / 16; ++kk)
-          umma_bf16_ss(tmem_base + Cfg::T_S, tile_desc_kmajor<DH, SWB>(aQ, kk), tile_desc_kmajor<DH, SWB>(aK, kk), idesc_s, kk != 0);
+          umma_bf16_ss(tmem_base + Cfg::T_S, aQ + 2 * kk, aK + 2 * kk, idesc_s, kk != 0);
 #pragma unroll
         for (int kk = 0; kk < DH / 16; ++kk)
-          umma_bf16_ss(tmem_base + Cfg::T_DP, tile_desc_kmajor<DH, SWB>(adO, kk), tile_desc_kmajor<DH, SWB>(aV, kk), idesc_s, kk != 0);
+          umma_bf16_ss(tmem_base + Cfg::T_DP, adO + 2 * kk, aV + 2 * kk, idesc_s, kk != 0);
         umma_commit(bar_s);
       };
-      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++n_items) {
-        const int kt = item % p.n_kt;
-        const int bh = item / p.n_kt;
-        const int h = bh % p.H;
-        const int b = bh / p.H;
-        const int k0 = kt * 128;
-        const int i_min = (k0 - off) < 0 ? 0 : (k0 - off) / 128;
-        const int n_i = p.n_qt - i_min;
-        // K/V of the previous item are no longer read once its last MMAs completed (bar_d of step g-1)
-        if (g > 0) mbar_wait(bar_d, (g - 1) & 1);
-        mbar_arrive_expect_tx(bar_kv, 2 * T::TILE_BYTES);
-        load_head_tile<DH, SWB>(sK, &tmK, bar_kv, h, b, k0);
-        load_head_tile<DH, SWB>(sV, &tmV, bar_kv, h, b, k0);
-        mbar_arrive_expect_tx(&bar_q[0], 2 * T::TILE_BYTES);
-        load_head_tile<DH, SWB>(sQ, &tmQ, &bar_q[0], h, b, i_min * 128);
-        load_head_tile<DH, SWB>(sdO, &tmdO, &bar_q[0], h, b, i_min * 128);
-        mbar_wait(bar_kv, n_items & 1);
-        mbar_wait(&bar_q[0], q_uses[0] & 1);
-        q_uses[0]++;
-        if (g > 0) mbar_wait(bar_sread, (g - 1) & 1);   // S/dP columns free
-        tc_fence_after();
-        issue_s_dp(0);
-        for (int ii = 0; ii < n_i; ++ii, ++g) {
-          const int st = ii & 1;
-          if (ii + 1 < n_i) {
-            const int ns = st ^ 1;
-            // stage ns was read by the MMAs of step ii-1
-            if (ii >= 1) mbar_wait(bar_d, (g - 1) & 1);
-            mbar_arrive_expect_tx(&bar_q[ns], 2 * T::TILE_BYTES);
-            load_head_tile<DH, SWB>(sQ + ns * T::TILE_BYTES, &tmQ, &bar_q[ns], h, b, (i_min + ii + 1) * 128);
-            load_head_tile<DH, SWB>(sdO + ns * T::TILE_BYTES, &tmdO, &bar_q[ns], h, b, (i_min + ii + 1) * 128);
-            mbar_wait(bar_sread, g & 1);                // E pulled S/dP of this step
-            mbar_wait(&bar_q[ns], q_uses[ns] & 1);
-            q_uses[ns]++;
-            tc_fence_after();
-            issue_s_dp(ns);                             // S/dP of step ii+1 run under the exp phase of step ii
-          }
-          mbar_wait(bar_pds, g & 1);                    // P, dS of this step are in smem
-          if (g > 0) mbar_wait(bar_dqfree, (g - 1) & 1);  // dQp columns free
-          if (ii == 0 && n_items > 0) mbar_wait(bar_accfree, (n_items - 1) & 1);  // dV/dK of the previous item read
-          tc_fence_after();
-          const uint32_t aP = smem_u32(sP), adS = smem_u32(sdS);
-          const uint32_t aQ = smem_u32(sQ + st * T::TILE_BYTES), adO = smem_u32(sdO + st * T::TILE_BYTES), aK = smem_u32(sK);
-#pragma unroll
-          for (int kk = 0; kk < 8; ++kk)   // dV[key, e] += sum_q P[q, key] dO[q, e]
-            umma_bf16_ss(tmem_base + Cfg::T_DV, ptile_desc_mnmajor(aP, kk), tile_desc_mnmajor<DH, SWB>(adO, kk), idesc_t, (ii | kk) != 0);
-#pragma unroll
-          for (int kk = 0; kk < 8; ++kk)   // dK[key, e] += sum_q dS[q, key] Q[q, e]
-            umma_bf16_ss(tmem_base + Cfg::T_DK, ptile_desc_mnmajor(adS, kk), tile_desc_mnmajor<DH, SWB>(aQ, kk), idesc_t, (ii | kk) != 0);
-#pragma unroll
-          for (int kk = 0; kk < 8; ++kk)   // dQp[q, e] = sum_key dS[q, key] K[key, e]
-            umma_bf16_ss(tmem_base + Cfg::T_DQ, ptile_desc_kmajor(adS, kk), tile_desc_mnmajor<DH, SWB>(aK, kk), idesc_q, kk != 0);
-          umma_commit(bar_d);
+
+      issue_sdp(0);
+      uint32_t items_main = 0;   // items whose first main step has been issued
+      while (!end) {
+        const StepInfo si = info[g & (Cfg::INFO_SLOTS - 1)];      // visible: bar_q of step g was waited in issue_sdp(g)
+        end = (si.flags & SI_END) != 0;
+        if (!end) issue_sdp(g + 1);                               // runs under the exp phase of step g
+        mbar_wait(bar_pds, g & 1);                                // P, dS of this step are in smem
+        if (g > 0) mbar_wait(bar_dqfree, (g - 1) & 1);            // dQp columns free
+        if (si.flags & SI_FIRST) {
+          if (items_main > 0) mbar_wait(bar_accfree, (items_main - 1) & 1);   // previous dV/dK read out
+          ++items_main;
         }
+        tc_fence_after();
+        const int st = g % Cfg::Q_STAGES;
+        const int kb = (si.flags & SI_KVBUF) ? 1 : 0;
+        const uint32_t acc = (si.flags & SI_FIRST) ? 0u : 1u;
+        const uint64_t mQ = tileMN + addr14(smem_u32(sQ + st * T::TILE_BYTES)), mdO = tileMN + addr14(smem_u32(sdO + st * T::TILE_BYTES));
+        const uint64_t mK = tileMN + addr14(smem_u32(sK + kb * T::TILE_BYTES));
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)   // dV[key, e] += sum_q P[q, key] dO[q, e]
+          umma_bf16_ss(tmem_base + Cfg::T_DV, dP_mn + 128 * kk, mdO + 128 * kk, idesc_t, (kk != 0) ? 1u : acc);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)   // dK[key, e] += sum_q dS[q, key] Q[q, e]
+          umma_bf16_ss(tmem_base + Cfg::T_DK, dS_mn + 128 * kk, mQ + 128 * kk, idesc_t, (kk != 0) ? 1u : acc);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)   // dQp[q, e] = sum_key dS[q, key] K[key, e]
+          umma_bf16_ss(tmem_base + Cfg::T_DQ, (kk < 4 ? dS_k0 : dS_k1) + 2 * (kk & 3), mK + 128 * kk, idesc_q, kk != 0);
+        umma_commit(bar_d);
+        umma_commit(&bar_qfree[st]);
+        if (si.flags & SI_LAST) umma_commit(&bar_kvfree[kb]);
+        ++g;
       }
     }
   } else {
@@ -176,134 +261,168 @@ ot_attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     const int row = (warp & 3) * 32 + lane;
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
     uint32_t g = 0;
-    uint32_t n_items = 0;
-
-    auto flush_dq = [&](int q0, int b, int h) {
-      // dQ partial of the finished step: columns [half*32, +32) of this thread's query row
-      uint32_t v[32];
-      tmem_ld_x32(t_row + Cfg::T_DQ + half * 32, v);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_dqfree);
-      if (q0 + row < p.Lq) {
-        __nv_bfloat16* dst = p.dq + ((long long)(q0 + row) * p.B + b) * p.lddq + h * DH + half * 32;
-#pragma unroll
-        for (int ch = 0; ch < 4; ++ch)
-          red_add_bf16x8(dst + ch * 8, pack_bf16x2(__uint_as_float(v[ch * 8 + 0]), __uint_as_float(v[ch * 8 + 1])),
-                         pack_bf16x2(__uint_as_float(v[ch * 8 + 2]), __uint_as_float(v[ch * 8 + 3])),
-                         pack_bf16x2(__uint_as_float(v[ch * 8 + 4]), __uint_as_float(v[ch * 8 + 5])),
-                         pack_bf16x2(__uint_as_float(v[ch * 8 + 6]), __uint_as_float(v[ch * 8 + 7])));
-      }
-    };
-
-    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++n_items) {
-      const int kt = item % p.n_kt;
-      const int bh = item / p.n_kt;
-      const int h = bh % p.H;
-      const int b = bh / p.H;
-      const int k0 = kt * 128;
-      const int i_min = (k0 - off) < 0 ? 0 : (k0 - off) / 128;
-      const int n_i = p.n_qt - i_min;
-      for (int ii = 0; ii < n_i; ++ii, ++g) {
-        const int q0 = (i_min + ii) * 128;
-        const bool row_valid = (q0 + row) < p.Lq;
-        const int pq = off + q0 + row;
-        float lse2 = 0.0f, delta = 0.0f;
-        if (row_valid) {
-          const long long si = ((long long)b * p.H + h) * p.Lq + q0 + row;
-          lse2 = p.lse[si] * kLog2eF;
-          delta = p.delta[si];
-        }
-        mbar_wait(bar_s, g & 1);
-        tc_fence_after();
-        uint32_t pk[2][16], dk_[2][16];   // packed bf16 P and dS, 2 x 32 columns
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          const int col0 = half * 64 + c * 32;
-          uint32_t vs[32], vd[32];
-          tmem_ld_x32(t_row + Cfg::T_S + col0, vs);
-          tmem_ld_x32(t_row + Cfg::T_DP + col0, vd);
-          tmem_ld_wait();
-          if (c == 1) {   // S and dP are out of TMEM: the control warp may issue the next S/dP
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_sread);
-          }
-#pragma unroll
-          for (int i2 = 0; i2 < 16; ++i2) {
-            float pv0 = exp2f(__uint_as_float(vs[2 * i2]) * p.scale_log2 - lse2);
-            float pv1 = exp2f(__uint_as_float(vs[2 * i2 + 1]) * p.scale_log2 - lse2);
-            if (!row_valid || (k0 + col0 + 2 * i2 > pq)) pv0 = 0.0f;
-            if (!row_valid || (k0 + col0 + 2 * i2 + 1 > pq)) pv1 = 0.0f;
-            const float ds0 = pv0 * (__uint_as_float(vd[2 * i2]) - delta) * p.scale;
-            const float ds1 = pv1 * (__uint_as_float(vd[2 * i2 + 1]) - delta) * p.scale;
-            pk[c][i2] = pack_bf16x2(pv0, pv1);
-            dk_[c][i2] = pack_bf16x2(ds0, ds1);
-          }
-        }
-        // P/dS tiles are free once the MMAs of the previous step have read them
-        if (ii > 0) {
-          mbar_wait(bar_d, (g - 1) & 1);
-          tc_fence_after();
-        }
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          const int col0 = half * 64 + c * 32;
-          uint8_t* slabP = sP + (col0 >> 6) * PT_SLAB_BYTES;
-          uint8_t* slabD = sdS + (col0 >> 6) * PT_SLAB_BYTES;
-          const int ch0 = (col0 & 63) >> 3;
-#pragma unroll
-          for (int ch = 0; ch < 4; ++ch) {
-            *reinterpret_cast<uint4*>(slabP + swz_off<128>(row, ch0 + ch)) =
-                make_uint4(pk[c][ch * 4 + 0], pk[c][ch * 4 + 1], pk[c][ch * 4 + 2], pk[c][ch * 4 + 3]);
-            *reinterpret_cast<uint4*>(slabD + swz_off<128>(row, ch0 + ch)) =
-                make_uint4(dk_[c][ch * 4 + 0], dk_[c][ch * 4 + 1], dk_[c][ch * 4 + 2], dk_[c][ch * 4 + 3]);
-          }
-        }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_pds);
-        if (ii > 0) flush_dq(q0 - 128, b, h);   // dQ partial of the previous step (its MMAs completed above)
-      }
-      // ---- item epilogue: last dQ partial, then dV / dK of this key tile ----
-      mbar_wait(bar_d, (g - 1) & 1);
-      tc_fence_after();
-      flush_dq((i_min + n_i - 1) * 128, b, h);
-      const bool key_valid = (k0 + row) < p.Lk;
-      uint32_t v[32];
-      tmem_ld_x32(t_row + Cfg::T_DV + half * 32, v);
-      tmem_ld_wait();
-      if (key_valid) {
-        __nv_bfloat16* dst = p.dv + ((long long)(k0 + row) * p.B + b) * p.lddv + h * DH + half * 32;
-#pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          uint4 q;
-          q.x = pack_bf16x2(__uint_as_float(v[ch * 8 + 0]), __uint_as_float(v[ch * 8 + 1]));
-          q.y = pack_bf16x2(__uint_as_float(v[ch * 8 + 2]), __uint_as_float(v[ch * 8 + 3]));
-          q.z = pack_bf16x2(__uint_as_float(v[ch * 8 + 4]), __uint_as_float(v[ch * 8 + 5]));
-          q.w = pack_bf16x2(__uint_as_float(v[ch * 8 + 6]), __uint_as_float(v[ch * 8 + 7]));
-          *reinterpret_cast<uint4*>(dst + ch * 8) = q;
-        }
-      }
-      tmem_ld_x32(t_row + Cfg::T_DK + half * 32, v);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_accfree);
-      if (key_valid) {
-        __nv_bfloat16* dst = p.dk + ((long long)(k0 + row) * p.B + b) * p.lddk + h * DH + half * 32;
-#pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          uint4 q;
-          q.x = pack_bf16x2(__uint_as_float(v[ch * 8 + 0]), __uint_as_float(v[ch * 8 + 1]));
-          q.y = pack_bf16x2(__uint_as_float(v[ch * 8 + 2]), __uint_as_float(v[ch * 8 + 3]));
-          q.z = pack_bf16x2(__uint_as_float(v[ch * 8 + 4]), __uint_as_float(v[ch * 8 + 5]));
-          q.w = pack_bf16x2(__uint_as_float(v[ch * 8 + 6]), __uint_as_float(v[ch * 8 + 7]));
-          *reinterpret_cast<uint4*>(dst + ch * 8) = q;
-        }
+    // row statistics of the current step, fetched one step ahead so that their latency hides under the math
+    float lse_raw = 0.0f, delta = 0.0f;
+    {
+      StepCursor c0;
+      c0.init(p);
+      if (c0.q0() + row < p.Lq) {
+        const long long si0 = ((long long)c0.b * p.H + c0.h) * p.Lq + c0.q0() + row;
+        lse_raw = p.lse[si0];
+        delta = p.delta[si0];
       }
     }
+    bool end = false;
+    unsigned long long tph[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // phase timers (dbg bit1)
+    long long tc0 = clock64();
+#define OT_TICK(i) do { if (p.dbg & 2) { const long long t1_ = clock64(); tph[i] += (unsigned long long)(t1_ - tc0); tc0 = t1_; } } while (0)
+    while (!end) {
+      mbar_wait(bar_s, g & 1);
+      OT_TICK(0);   // wait for S/dP
+      tc_fence_after();
+      const StepInfo si = info[g & (Cfg::INFO_SLOTS - 1)];
+      end = (si.flags & SI_END) != 0;
+      const bool first_of_item = si.flags & SI_FIRST, last_of_item = si.flags & SI_LAST;
+      const int q0 = si.q0, k0 = si.k0, b = si.b, h = si.h;
+      const bool row_valid = (q0 + row) < p.Lq;
+      const int pq = off + q0 + row;
+      const float lse2 = lse_raw * kLog2eF;
+      const float dlt = delta;
+      if (si.next_q0 >= 0 && si.next_q0 + row < p.Lq) {   // next step's row statistics (used one step later)
+        const long long sn = (long long)si.next_bh * p.Lq + si.next_q0 + row;
+        lse_raw = p.lse[sn];
+        delta = p.delta[sn];
+      }
+      uint32_t pk[32], dsk[32];   // packed bf16 P and dS of this thread's 64 columns
+      // Tiles strictly below the diagonal with only valid rows need no mask (the common case).  Otherwise column
+      // j of the tile is visible to this row iff j <= lim.
+      const bool fast = (q0 + 127 < p.Lq) && (k0 + 127 <= off + q0);
+      const int lim = row_valid ? (pq - k0) : -1;
+      const float dlt_s = dlt * p.scale;
+      uint32_t vs[2][16], vd[2][16];   // double-buffered TMEM reads: chunk c+1 is in flight while chunk c is processed
+      tmem_ld_x16(t_row + Cfg::T_S + half * 64, vs[0]);
+      tmem_ld_x16(t_row + Cfg::T_DP + half * 64, vd[0]);
+      tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int cb = c & 1;
+        if (c < 3) {
+          tmem_ld_x16(t_row + Cfg::T_S + half * 64 + (c + 1) * 16, vs[cb ^ 1]);
+          tmem_ld_x16(t_row + Cfg::T_DP + half * 64 + (c + 1) * 16, vd[cb ^ 1]);
+        }
+        const int j0 = half * 64 + c * 16;
+#pragma unroll
+        for (int i2 = 0; i2 < 8; ++i2) {
+          float pv0 = ex2_approx(fmaf(__uint_as_float(vs[cb][2 * i2]), p.scale_log2, -lse2));
+          float pv1 = ex2_approx(fmaf(__uint_as_float(vs[cb][2 * i2 + 1]), p.scale_log2, -lse2));
+          if (!fast) {
+            pv0 = (j0 + 2 * i2 <= lim) ? pv0 : 0.0f;
+            pv1 = (j0 + 2 * i2 + 1 <= lim) ? pv1 : 0.0f;
+          }
+          const float ds0 = pv0 * fmaf(__uint_as_float(vd[cb][2 * i2]), p.scale, -dlt_s);
+          const float ds1 = pv1 * fmaf(__uint_as_float(vd[cb][2 * i2 + 1]), p.scale, -dlt_s);
+          pk[c * 8 + i2] = pack_bf16x2(pv0, pv1);
+          dsk[c * 8 + i2] = pack_bf16x2(ds0, ds1);
+        }
+        if (c < 3) tmem_ld_wait();
+        if (c == 2) {   // every S/dP column of this thread is in registers: the MMA warp may issue the next S/dP
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_sread);
+        }
+      }
+      OT_TICK(1);   // TMEM loads + exp math
+      // P/dS tiles are free once the MMAs of the previous step have read them
+      if (!first_of_item) {
+        mbar_wait(bar_d, (g - 1) & 1);
+        tc_fence_after();
+      }
+      OT_TICK(2);   // wait for the previous step's MMAs
+      {
+        // this thread's 64 columns are one 128-byte row of slab `half` of the P / dS tiles
+        uint8_t* slabP = sP + half * PT_SLAB_BYTES;
+        uint8_t* slabD = sdS + half * PT_SLAB_BYTES;
+        // recompute the 8 swizzled offsets here (2 ALU ops each): hoisted out of the step loop they get spilled to
+        // local memory, which is an L2 round trip in a kernel that leaves L1 almost no capacity
+        uint32_t row_v = row;
+        asm volatile("" : "+r"(row_v));
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) {
+          const uint32_t o = swz_off<128>(row_v, ch);
+          *reinterpret_cast<uint4*>(slabP + o) = make_uint4(pk[ch * 4 + 0], pk[ch * 4 + 1], pk[ch * 4 + 2], pk[ch * 4 + 3]);
+          *reinterpret_cast<uint4*>(slabD + o) = make_uint4(dsk[ch * 4 + 0], dsk[ch * 4 + 1], dsk[ch * 4 + 2], dsk[ch * 4 + 3]);
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_pds);
+      OT_TICK(3);   // P/dS stores
+
+      // ---- outputs: dQ partial of the previous step; on the item's last step also this step's dQ partial, dV, dK.
+      // Each [128 x 64] tile goes TMEM -> registers -> bf16 -> swizzled smem staging -> global in full 128-byte rows
+      // (row-per-thread stores would cost 32 memory transactions per instruction).
+      const int et = tid;                       // 0..255 among the element-wise warps
+#pragma unroll 1
+      for (int pass = 0; pass < 4; ++pass) {
+        // pass 0: dQp of step g-1 | pass 1: dQp of step g | pass 2: dV | pass 3: dK   (1..3 only on the last step)
+        if (pass == 0 && first_of_item) continue;
+        if (pass >= 1 && !last_of_item) break;
+        if (pass == 1) {
+          OT_TICK(4);   // dQ flush of the previous step
+          mbar_wait(bar_d, g & 1);              // MMAs of this (last) step
+          tc_fence_after();
+          OT_TICK(5);   // wait for the last step's MMAs
+        }
+        const uint32_t tcol = pass <= 1 ? Cfg::T_DQ : (pass == 2 ? Cfg::T_DV : Cfg::T_DK);
+        uint32_t v[32];
+        tmem_ld_x32(t_row + tcol + half * 32, v);
+        tmem_ld_wait();
+        if (pass <= 1 || pass == 3) {           // dQp / (dV, dK) columns are free again
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(pass == 3 ? bar_accfree : bar_dqfree);
+        }
+        named_bar_sync(1, 256);                 // previous readers of the staging tile are done
+        {
+          uint32_t row_v = row;
+          asm volatile("" : "+r"(row_v));
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch)
+            *reinterpret_cast<uint4*>(sStg + swz_off<128>(row_v, half * 4 + ch)) =
+                make_uint4(pack_bf16x2(__uint_as_float(v[ch * 8 + 0]), __uint_as_float(v[ch * 8 + 1])),
+                           pack_bf16x2(__uint_as_float(v[ch * 8 + 2]), __uint_as_float(v[ch * 8 + 3])),
+                           pack_bf16x2(__uint_as_float(v[ch * 8 + 4]), __uint_as_float(v[ch * 8 + 5])),
+                           pack_bf16x2(__uint_as_float(v[ch * 8 + 6]), __uint_as_float(v[ch * 8 + 7])));
+        }
+        named_bar_sync(1, 256);
+        // tile row r <-> query (pass 0/1) or key (pass 2/3) position base+r; 8 lanes x 16 B cover one row
+        const int base = pass == 0 ? q0 - 128 : (pass == 1 ? q0 : k0);
+        const int limit = pass <= 1 ? p.Lq : p.Lk;
+        __nv_bfloat16* gptr = pass <= 1 ? p.dq : (pass == 2 ? p.dv : p.dk);
+        const long long gld = pass <= 1 ? p.lddq : (pass == 2 ? p.lddv : p.lddk);
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int r = it * 32 + (et >> 3);
+          const int ch = et & 7;
+          if (base + r < limit) {
+            const uint4 q = *reinterpret_cast<const uint4*>(sStg + swz_off<128>(r, ch));
+            __nv_bfloat16* dst = gptr + ((long long)(base + r) * p.B + b) * gld + h * DH + ch * 8;
+            if (pass <= 1) {
+              if (!(p.dbg & 1)) red_add_bf16x8(dst, q.x, q.y, q.z, q.w);
+            } else {
+              *reinterpret_cast<uint4*>(dst) = q;
+            }
+          }
+        }
+      }
+      OT_TICK(6);   // dQ flush (+ dV/dK epilogue on the last step of an item)
+      ++g;
+    }
+    if ((p.dbg & 2) && p.dbg_buf != nullptr && warp == 0 && lane == 0 && blockIdx.x < 8) {
+      for (int i = 0; i < 7; ++i) p.dbg_buf[blockIdx.x * 8 + i] = tph[i];
+      p.dbg_buf[blockIdx.x * 8 + 7] = g;
+    }
+#undef OT_TICK
   }
   tc_fence_before();
   __syncthreads();
@@ -352,6 +471,16 @@ int attn_bwd_fused_impl(const ot_attn_params* p, cudaStream_t st) {
   kp.lse = p->lse; kp.delta = p->delta;
   kp.dq = (__nv_bfloat16*)p->dq; kp.lddq = p->lddq; kp.dk = (__nv_bfloat16*)p->dk; kp.lddk = p->lddk;
   kp.dv = (__nv_bfloat16*)p->dv; kp.lddv = p->lddv;
+  {
+    const char* e = getenv("OT_DEBUG_ATTN_BWD");
+    kp.dbg = e ? atoi(e) : 0;
+    kp.dbg_buf = nullptr;
+    if (kp.dbg & 2) {
+      static unsigned long long* buf = nullptr;
+      if (!buf) cudaMalloc(&buf, 64 * sizeof(unsigned long long));
+      kp.dbg_buf = buf;
+    }
+  }
 
   static bool attr_done = false;
   if (!attr_done) {
@@ -376,6 +505,17 @@ int attn_bwd_fused_impl(const ot_attn_params* p, cudaStream_t st) {
   const int grid = kp.total_items < sms ? kp.total_items : sms;
   ot_attn_bwd_fused_kernel<<<grid, FB_THREADS, AttnBwdFusedCfg::SMEM_BYTES, st>>>(tm[0], tm[1], tm[2], tm[3], kp);
   OT_CUDA_CHECK(cudaGetLastError());
+  if (kp.dbg & 2) {   // debugging aid only: synchronises and prints the element-wise warps' phase timers
+    unsigned long long h[64];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, kp.dbg_buf, sizeof(h), cudaMemcpyDeviceToHost);
+    static const char* names[7] = {"wait S/dP", "tmem+exp", "wait prev MMAs", "P/dS stores", "dQ flush(prev)", "wait last MMAs", "flush+epilogue"};
+    for (int c = 0; c < 2; ++c) {
+      fprintf(stderr, "[attn_bwd cta %d] steps=%llu cycles/step:", c, h[c * 8 + 7]);
+      for (int i = 0; i < 7; ++i) fprintf(stderr, " %s=%.0f", names[i], (double)h[c * 8 + i] / (double)(h[c * 8 + 7] ? h[c * 8 + 7] : 1));
+      fprintf(stderr, "\n");
+    }
+  }
   return OT_OK;
 }
 

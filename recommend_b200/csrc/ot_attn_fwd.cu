@@ -129,21 +129,24 @@ ot_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tc_fence_after();
 
       // ---- online softmax over the 128 scores of this row ----
-      const bool need_mask = (j * 128 + 127 > pq);
+      // blocks strictly below the diagonal of the whole tile need no mask (warp-uniform fast path)
+      const bool fast = (j * 128 + 127 <= off + q0);
+      const int lim = pq - j * 128;        // column c of this block is visible to this row iff c <= lim
       float m_new = m_run;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         uint32_t v[32];
         tmem_ld_x32(t_S + c * 32, v);
         tmem_ld_wait();
+        if (fast) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float s = __uint_as_float(v[i]);
-          if (need_mask && (j * 128 + c * 32 + i > pq)) s = -INFINITY;
-          m_new = fmaxf(m_new, s);
+          for (int i = 0; i < 32; ++i) m_new = fmaxf(m_new, __uint_as_float(v[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) m_new = fmaxf(m_new, (c * 32 + i <= lim) ? __uint_as_float(v[i]) : -INFINITY);
         }
       }
-      const float alpha = exp2f((m_run - m_new) * p.scale_log2);
+      const float alpha = ex2_approx((m_run - m_new) * p.scale_log2);
       const float mb = m_new * p.scale_log2;
       float rowsum = 0.0f;
 #pragma unroll 1
@@ -152,19 +155,28 @@ ot_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tmem_ld_x32(t_S + c * 32, v);
         tmem_ld_wait();
         float pr[32];
+        if (fast) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float e = exp2f(__uint_as_float(v[i]) * p.scale_log2 - mb);
-          if (need_mask && (j * 128 + c * 32 + i > pq)) e = 0.0f;
-          pr[i] = e;
-          rowsum += e;
+          for (int i = 0; i < 32; ++i) {
+            pr[i] = ex2_approx(fmaf(__uint_as_float(v[i]), p.scale_log2, -mb));
+            rowsum += pr[i];
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float e = ex2_approx(fmaf(__uint_as_float(v[i]), p.scale_log2, -mb));
+            pr[i] = (c * 32 + i <= lim) ? e : 0.0f;
+            rowsum += pr[i];
+          }
         }
         ptile_store32(sP, tid, c * 32, pr);
       }
       l_run = l_run * alpha + rowsum;
       m_run = m_new;
+      if (alpha != 1.0f) {   // the running maximum moved: rescale the accumulator
 #pragma unroll
-      for (int i = 0; i < DH; ++i) o_acc[i] *= alpha;
+        for (int i = 0; i < DH; ++i) o_acc[i] *= alpha;
+      }
 
       fence_proxy_async_smem();   // P (generic-proxy stores) -> visible to tcgen05.mma
       tc_fence_before();

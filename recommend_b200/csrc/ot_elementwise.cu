@@ -33,7 +33,7 @@ template <int NCH>
 __global__ void __launch_bounds__(256)
 rmsnorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const float* __restrict__ g,
                    __nv_bfloat16* __restrict__ y, long long ldy, float* __restrict__ rstd, long long rows, int d,
-                   float eps) {
+                   float eps, const float* __restrict__ x_hp, long long hp_row0) {
   const int lane = threadIdx.x & 31;
   const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long n_warps = (long long)gridDim.x * (blockDim.x >> 5);
@@ -46,7 +46,13 @@ rmsnorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const flo
     for (int i = 0; i < NCH; ++i) {
       const int ch = lane + 32 * i;
       if (ch < nch) {
-        unpack8(xr[ch], v[i]);
+        if (x_hp != nullptr && row >= hp_row0) {   // NS-token row: fp32 residual stream
+          const float4* hr = reinterpret_cast<const float4*>(x_hp + (row - hp_row0) * d) + 2 * ch;
+          const float4 a = hr[0], b = hr[1];
+          v[i][0] = a.x; v[i][1] = a.y; v[i][2] = a.z; v[i][3] = a.w; v[i][4] = b.x; v[i][5] = b.y; v[i][6] = b.z; v[i][7] = b.w;
+        } else {
+          unpack8(xr[ch], v[i]);
+        }
 #pragma unroll
         for (int e = 0; e < 8; ++e) ss += v[i][e] * v[i][e];
       }
@@ -155,7 +161,8 @@ static constexpr int MAX_NS_FEAT = 32;
 
 __global__ void __launch_bounds__(256)
 ns_tokenizer_fwd_kernel(const float* __restrict__ x, int n_feat, const float* __restrict__ W, const float* __restrict__ bias,
-                        __nv_bfloat16* __restrict__ out, long long ldo, long long row0, int B, int L_ns, int d) {
+                        __nv_bfloat16* __restrict__ out, long long ldo, long long row0, int B, int L_ns, int d,
+                        float* __restrict__ out_hp) {
   const long long total = (long long)B * L_ns * (d >> 3);
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     const int nch = d >> 3;
@@ -177,6 +184,11 @@ ns_tokenizer_fwd_kernel(const float* __restrict__ x, int n_feat, const float* __
       acc[4] += xv * w1.x; acc[5] += xv * w1.y; acc[6] += xv * w1.z; acc[7] += xv * w1.w;
     }
     *reinterpret_cast<uint4*>(out + (row0 + (long long)j * B + b) * ldo + c * 8) = pack8(acc);
+    if (out_hp != nullptr) {
+      float4* hp = reinterpret_cast<float4*>(out_hp + ((long long)j * B + b) * d + c * 8);
+      hp[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      hp[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    }
   }
 }
 
@@ -284,7 +296,7 @@ int rmsnorm_fwd_impl(const ot_rmsnorm_params* p, cudaStream_t st) {
   const int grid = grid_for_rows(p->rows, 8);
 #define OT_LAUNCH_RMS_FWD(N)                                                                                             \
   rmsnorm_fwd_kernel<N><<<grid, 256, 0, st>>>((const __nv_bfloat16*)p->x, p->ldx, p->gain, (__nv_bfloat16*)p->y, p->ldy, \
-                                              p->rstd, p->rows, p->d, p->eps)
+                                              p->rstd, p->rows, p->d, p->eps, p->x_hp, p->hp_row0)
   if (nch <= 1) OT_LAUNCH_RMS_FWD(1); else if (nch == 2) OT_LAUNCH_RMS_FWD(2); else OT_LAUNCH_RMS_FWD(4);
 #undef OT_LAUNCH_RMS_FWD
   OT_CUDA_CHECK(cudaGetLastError());
@@ -317,7 +329,7 @@ int ns_tokenizer_fwd_impl(const ot_ns_tokenizer_params* p, cudaStream_t st) {
   const long long total = (long long)p->B * p->L_ns * (p->d / 8);
   long long blocks = (total + 255) / 256;
   if (blocks > (long long)num_sms() * 32) blocks = (long long)num_sms() * 32;
-  ns_tokenizer_fwd_kernel<<<(int)blocks, 256, 0, st>>>(p->x, p->n_feat, p->W, p->bias, (__nv_bfloat16*)p->out, p->ldo, p->row0, p->B, p->L_ns, p->d);
+  ns_tokenizer_fwd_kernel<<<(int)blocks, 256, 0, st>>>(p->x, p->n_feat, p->W, p->bias, (__nv_bfloat16*)p->out, p->ldo, p->row0, p->B, p->L_ns, p->d, p->out_hp);
   OT_CUDA_CHECK(cudaGetLastError());
   return OT_OK;
 }

@@ -49,6 +49,7 @@ struct GemmKParams {
   const __nv_bfloat16* aux; long long ldaux;
   const float* bias; long long bias_group_stride;
   const float* row_scale;
+  const float* res_hp; float* out_hp; long long ld_hp; long long hp_row0;
 };
 
 struct TileInfo {
@@ -228,6 +229,24 @@ ot_mixed_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       }
       float rs = 1.0f;
       if (f_rs && r_own < t.valid) rs = p.row_scale[t.row0 + r_own];
+      // NS-token tiles may carry an fp32 residual stream (tile-uniform: NS units start on tile boundaries)
+      const bool hp_tile = f_res && (p.res_hp != nullptr) && (t.row0 >= p.hp_row0);
+      const bool tile_in = has_in && !hp_tile;
+
+      // residual / GELU' input of this set's first chunk: requested before the accumulator wait so that the global
+      // latency hides under the MMAs; the following chunk is requested while the current one is processed
+      uint4 pre_in[BM / 16];
+      auto fetch_in = [&](int c) {
+        const int col0 = n0 + c * CHUNK;
+#pragma unroll
+        for (int i = 0; i < BM / 16; ++i) {
+          const int r = i * 16 + ld_row;
+          pre_in[i] = make_uint4(0, 0, 0, 0);
+          if (r < t.valid)
+            pre_in[i] = *reinterpret_cast<const uint4*>(in_ptr + (long long)(t.row0 + r) * in_ld + col0 + ld_ch * 8);
+        }
+      };
+      if (tile_in && set < BN / CHUNK) fetch_in(set);
 
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
@@ -238,15 +257,13 @@ ot_mixed_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const int col0 = n0 + c * CHUNK;
         uint8_t* buf = stg + sbuf * CH_BYTES;
         uint8_t* buf2 = stg + (sbuf ^ 1) * CH_BYTES;
-        if (has_in) {   // residual / GELU' input chunk: coalesced global -> staging
+        if (tile_in) {   // residual / GELU' input chunk (prefetched registers) -> staging
 #pragma unroll
           for (int i = 0; i < BM / 16; ++i) {
             const int r = i * 16 + ld_row;
-            uint4 q = make_uint4(0, 0, 0, 0);
-            if (r < t.valid)
-              q = *reinterpret_cast<const uint4*>(in_ptr + (long long)(t.row0 + r) * in_ld + col0 + ld_ch * 8);
-            *reinterpret_cast<uint4*>(buf + swz_off<128>(r, ld_ch)) = q;
+            *reinterpret_cast<uint4*>(buf + swz_off<128>(r, ld_ch)) = pre_in[i];
           }
+          if (c + 2 < BN / CHUNK) fetch_in(c + 2);
           named_bar_sync(bar_id, EPI_SET_THREADS);
         }
 #pragma unroll
@@ -262,8 +279,12 @@ ot_mixed_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             for (int j = 0; j < 32; ++j) f[j] *= rs;
           }
           if (f_bias) {
+            const float4* b4 = reinterpret_cast<const float4*>(bias_s + c * CHUNK + half * 32);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] += bias_s[c * CHUNK + half * 32 + j];
+            for (int j = 0; j < 8; ++j) {
+              const float4 bb = b4[j];
+              f[4 * j + 0] += bb.x; f[4 * j + 1] += bb.y; f[4 * j + 2] += bb.z; f[4 * j + 3] += bb.w;
+            }
           }
           if (f_gelu) {
             if (dual) {   // keep the pre-activation for the backward pass
@@ -280,7 +301,20 @@ ot_mixed_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
           }
-          if (has_in) {
+          if (hp_tile) {   // fp32 residual in, fp32 result out: one 128-byte line per thread and half-chunk
+            if (r_own < t.valid) {
+              const long long hr = (long long)(t.row0 + r_own) - p.hp_row0;
+              const float4* rp = reinterpret_cast<const float4*>(p.res_hp + hr * p.ld_hp + col0 + half * 32);
+              float4* op = reinterpret_cast<float4*>(p.out_hp + hr * p.ld_hp + col0 + half * 32);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 rr = rp[j];
+                f[4 * j + 0] += rr.x; f[4 * j + 1] += rr.y; f[4 * j + 2] += rr.z; f[4 * j + 3] += rr.w;
+                op[j] = make_float4(f[4 * j + 0], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+              }
+            }
+          }
+          if (tile_in) {
 #pragma unroll
             for (int ch = 0; ch < 4; ++ch) {
               const uint4 q = *reinterpret_cast<const uint4*>(buf + swz_off<128>(r_own, half * 4 + ch));
@@ -398,6 +432,14 @@ int mixed_gemm_impl(const ot_gemm_params* p, cudaStream_t st) {
   kp.out = (__nv_bfloat16*)p->out; kp.ldo = p->ldo; kp.out2 = (__nv_bfloat16*)p->out2; kp.ldo2 = p->ldo2;
   kp.res = (const __nv_bfloat16*)p->res; kp.ldr = p->ldr; kp.aux = (const __nv_bfloat16*)p->aux; kp.ldaux = p->ldaux;
   kp.bias = p->bias; kp.bias_group_stride = p->bias_group_stride; kp.row_scale = p->row_scale;
+  kp.res_hp = p->res_hp; kp.out_hp = p->out_hp; kp.ld_hp = p->ld_hp; kp.hp_row0 = p->hp_row0;
+  if (p->res_hp || p->out_hp) {
+    if (!(p->flags & OT_EPI_RESIDUAL) || !p->res_hp || !p->out_hp || (p->ld_hp % 4))
+      OT_FAIL(OT_ERR_INVALID_ARG, "ot_mixed_gemm: res_hp/out_hp need OT_EPI_RESIDUAL, both pointers and ld_hp %% 4 == 0");
+    bool ok = false;
+    for (int s2 = 0; s2 < p->n_segs; ++s2) ok = ok || (p->segs[s2].row_start == p->hp_row0);
+    if (!ok) OT_FAIL(OT_ERR_INVALID_ARG, "ot_mixed_gemm: hp_row0=%lld is not the first row of a segment", (long long)p->hp_row0);
+  }
 
   // tensor maps: A always rank 3 (k, c1, c2); W rank 2 (k, group*N + n)
   CUtensorMap tmA, tmB;

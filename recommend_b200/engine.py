@@ -54,8 +54,27 @@ class BlockWeights:
         self.key = key
 
 
+def split_segments(segs: Sequence[ops.Seg], row: int) -> List[ops.Seg]:
+    """Split a segment list at output row ``row`` so that the rows from ``row`` on start a segment of their own
+    (the GEMM epilogue switches to the fp32 residual stream on a segment boundary, which is a tile boundary)."""
+    out: List[ops.Seg] = []
+    for (r0, n_units, rpu, g0, gs) in segs:
+        end = r0 + n_units * rpu
+        if row <= r0 or row >= end:
+            out.append((r0, n_units, rpu, g0, gs))
+        elif n_units == 1:
+            out.append((r0, 1, row - r0, g0, gs))
+            out.append((row, 1, end - row, g0, gs))
+        else:
+            assert (row - r0) % rpu == 0, 'split point must fall on a unit boundary'
+            u = (row - r0) // rpu
+            out.append((r0, u, rpu, g0, gs))
+            out.append((row, n_units - u, rpu, g0 + u * gs, gs))
+    return out
+
+
 def mha_forward(xn: torch.Tensor, res: Optional[torch.Tensor], w: BlockWeights, B: int, cur: int, keep: int, H: int,
-                L_ns: int, alignment: str, kv_prefix: Optional[torch.Tensor] = None):
+                L_ns: int, alignment: str, kv_prefix: Optional[torch.Tensor] = None, res_hp: Optional[torch.Tensor] = None):
     """MixedMHA.call (OT/model.py:76-122) on normalised ``xn [cur*B, d]``; queries for the last ``keep``
     positions.  ``res`` (``[keep*B, d]``) is added to the Wo output (the block's residual, OT/model.py:193).
     ``kv_prefix [Lc*B, 2d]``: cached K|V rows placed in front of the new ones (OT/model.py:95-98).
@@ -77,8 +96,18 @@ def mha_forward(xn: torch.Tensor, res: Optional[torch.Tensor], w: BlockWeights, 
     lse = torch.empty(B * H * keep, dtype=torch.float32, device=dev)
     ops.attn_fwd(q, kv[:, :d], kv[:, d:], o, lse, B, H, keep, Lc + cur, dh)
     z = torch.empty(rows_t, d, dtype=bf16, device=dev)
-    ops.mixed_gemm(o, w.Wo_f, [(0, 1, rows_t, 0, 0)], z, flags=OT_EPI_RESIDUAL if res is not None else 0, res=res)
-    return z, (q, kv, o, lse, segs_all, segs_tail)
+    z_hp = None
+    if res_hp is not None and res is not None:
+        # Wo is shared, but the NS-token rows (the last rows of the tail) keep an fp32 residual stream: split the row
+        # range at that boundary so that they form their own (tile-aligned) segment
+        n_hp = min(res_hp.shape[0], rows_t)
+        hp0 = rows_t - n_hp
+        z_hp = torch.empty(n_hp, d, dtype=torch.float32, device=dev)
+        segs_o = split_segments([(0, 1, rows_t, 0, 0)], hp0)
+        ops.mixed_gemm(o, w.Wo_f, segs_o, z, flags=OT_EPI_RESIDUAL, res=res, res_hp=res_hp[res_hp.shape[0] - n_hp:], out_hp=z_hp, hp_row0=hp0)
+    else:
+        ops.mixed_gemm(o, w.Wo_f, [(0, 1, rows_t, 0, 0)], z, flags=OT_EPI_RESIDUAL if res is not None else 0, res=res)
+    return z, (q, kv, o, lse, segs_all, segs_tail), z_hp
 
 
 def mha_backward(dz: torch.Tensor, xn: torch.Tensor, saved, w: BlockWeights, Wqkv_grad: torch.Tensor, Wo_grad: torch.Tensor,
@@ -110,7 +139,7 @@ def mha_backward(dz: torch.Tensor, xn: torch.Tensor, saved, w: BlockWeights, Wqk
 
 
 def ffn_forward(zn: torch.Tensor, res: Optional[torch.Tensor], w: BlockWeights, b1: torch.Tensor, b2: torch.Tensor,
-                segs: Sequence[ops.Seg], save: bool):
+                segs: Sequence[ops.Seg], save: bool, res_hp: Optional[torch.Tensor] = None):
     """MixedFFN.call (OT/model.py:149-163): ``gelu(zn W1 + b1) W2 + b2`` (+ res)."""
     rows_t, d = zn.shape
     F = w.W1_f.shape[1]
@@ -120,8 +149,14 @@ def ffn_forward(zn: torch.Tensor, res: Optional[torch.Tensor], w: BlockWeights, 
     ops.mixed_gemm(zn, w.W1_f, segs, h, flags=OT_EPI_BIAS | OT_EPI_GELU, bias=b1, out2=pre)
     y = torch.empty(rows_t, d, dtype=bf16, device=dev)
     flags = OT_EPI_BIAS | (OT_EPI_RESIDUAL if res is not None else 0)
-    ops.mixed_gemm(h, w.W2_f, segs, y, flags=flags, bias=b2, res=res)
-    return y, (pre, h)
+    y_hp = None
+    if res_hp is not None and res is not None:
+        hp0 = rows_t - res_hp.shape[0]          # the fp32 stream covers the last rows (the NS tokens)
+        y_hp = torch.empty(res_hp.shape[0], d, dtype=torch.float32, device=dev)
+        ops.mixed_gemm(h, w.W2_f, split_segments(segs, hp0), y, flags=flags, bias=b2, res=res, res_hp=res_hp, out_hp=y_hp, hp_row0=hp0)
+    else:
+        ops.mixed_gemm(h, w.W2_f, segs, y, flags=flags, bias=b2, res=res)
+    return y, (pre, h), y_hp
 
 
 def ffn_backward(dy: torch.Tensor, zn: torch.Tensor, saved, w: BlockWeights, segs: Sequence[ops.Seg], W1_grad, b1_grad,
@@ -143,24 +178,29 @@ def ffn_backward(dy: torch.Tensor, zn: torch.Tensor, saved, w: BlockWeights, seg
 
 
 def block_forward(x: torch.Tensor, P: Dict[str, torch.Tensor], w: BlockWeights, B: int, cur: int, keep: int, H: int,
-                  L_ns: int, alignment: str, eps: float, save: bool, kv_prefix: Optional[torch.Tensor] = None):
-    """OneTransBlock.call (OT/model.py:186-200) + tail keep (:371).  P: norm1, norm2, b1, b2 (fp32)."""
+                  L_ns: int, alignment: str, eps: float, save: bool, kv_prefix: Optional[torch.Tensor] = None,
+                  x_hp: Optional[torch.Tensor] = None):
+    """OneTransBlock.call (OT/model.py:186-200) + tail keep (:371).  P: norm1, norm2, b1, b2 (fp32).
+    ``x_hp``: optional fp32 copy of the NS-token rows of ``x`` (its last ``x_hp.shape[0]`` rows) — the
+    high-precision residual stream of DESIGN.md §5; returns the matching ``y_hp`` as 4th value."""
     rows, d = x.shape
     assert rows == cur * B
     dev = x.device
     rows_t, off = keep * B, (cur - keep) * B
     xn = torch.empty(rows, d, dtype=bf16, device=dev)
     r1 = torch.empty(rows, dtype=torch.float32, device=dev)
-    ops.rmsnorm_fwd(x, P['norm1'], xn, r1, eps)                                           # OT/model.py:191
-    z, mha_saved = mha_forward(xn, x[off:], w, B, cur, keep, H, L_ns, alignment, kv_prefix)  # :192-193
+    if x_hp is not None and x_hp.shape[0] == 0:
+        x_hp = None
+    ops.rmsnorm_fwd(x, P['norm1'], xn, r1, eps, x_hp, rows - (x_hp.shape[0] if x_hp is not None else 0))   # OT/model.py:191
+    z, mha_saved, z_hp = mha_forward(xn, x[off:], w, B, cur, keep, H, L_ns, alignment, kv_prefix, x_hp)   # :192-193
     zn = torch.empty(rows_t, d, dtype=bf16, device=dev)
     r2 = torch.empty(rows_t, dtype=torch.float32, device=dev)
-    ops.rmsnorm_fwd(z, P['norm2'], zn, r2, eps)                                           # :196
+    ops.rmsnorm_fwd(z, P['norm2'], zn, r2, eps, z_hp, rows_t - (z_hp.shape[0] if z_hp is not None else 0))   # :196
     segs_tail = mha_saved[5]
-    y, ffn_saved = ffn_forward(zn, z, w, P['b1'], P['b2'], segs_tail, save)                 # :197-198
+    y, ffn_saved, y_hp = ffn_forward(zn, z, w, P['b1'], P['b2'], segs_tail, save, z_hp)     # :197-198
     kv = mha_saved[1]
     saved = (x, xn, r1, mha_saved, z, zn, r2, ffn_saved) if save else None
-    return y, kv, saved
+    return y, kv, saved, y_hp
 
 
 def block_backward(dy: torch.Tensor, saved, Pm: Dict[str, torch.Tensor], w: BlockWeights, B: int, cur: int, keep: int,
@@ -221,11 +261,13 @@ def tokenizer_forward(ns_x: Optional[torch.Tensor], seq_list: Sequence[Optional[
                            a_transposed_events=True)                # OT/model.py:265
         else:
             ops.fill_rows(sep.reshape(-1), X0, p0 * B, B)           # OT/model.py:270-272
+    X_hp = None
     if ns_x is None:
         X0[L_s * B:].zero_()                                        # OT/model.py:249-251
-    else:
-        ops.ns_tokenizer_fwd(ns_x, Wns, bns, X0, L_s * B, B, L_ns, d)  # OT/model.py:211-214,253-254
-    return X0, L, layout
+    elif L_ns > 0:
+        X_hp = torch.empty(L_ns * B, d, dtype=torch.float32, device=dev)   # fp32 residual stream of the NS rows
+        ops.ns_tokenizer_fwd(ns_x, Wns, bns, X0, L_s * B, B, L_ns, d, X_hp)  # OT/model.py:211-214,253-254
+    return X0, L, layout, X_hp
 
 
 def tokenizer_backward(dX0: torch.Tensor, ns_x, seq_list, layout, B: int, d: int, L_ns: int, Ws, bs, sep, Wns, bns) -> None:
@@ -247,3 +289,81 @@ def tokenizer_backward(dX0: torch.Tensor, ns_x, seq_list, layout, B: int, d: int
             ops.colsum(dX0, [(p0 * B, 1, B, 0, 0)], _grad_buf(sep), 0)
     if ns_x is not None:
         ops.ns_tokenizer_bwd(ns_x, dX0, _grad_buf(Wns), _grad_buf(bns), L_s * B, B, L_ns, d)
+
+
+# ---------------------------------------------------------------------------------------------------
+# inference with a cross-candidate cache of the sequence-side K/V  (north_star item 5, PAPER:144-151)
+# ---------------------------------------------------------------------------------------------------
+
+
+def layer_plan(L0: int, L_ns: int, keep_lens: Sequence[int]):
+    """Per layer: (cur, Tn, cur_S, keep, Tq, keep_S) — current length, NS tokens alive, S tokens alive, kept
+    tail, NS tokens that query, S tokens that query.  The NS tokens are the last rows of the sequence."""
+    plan, cur = [], L0
+    for keep in keep_lens:
+        Tn = min(L_ns, cur)
+        Tq = min(Tn, keep)
+        plan.append((cur, Tn, cur - Tn, keep, Tq, keep - Tq))
+        cur = keep
+    return plan
+
+
+def user_cache_forward(x_s: torch.Tensor, blocks, plan, H: int, eps: float):
+    """Stage 1, once per user (B = 1): run the S tokens alone through the stack and keep every layer's K|V.
+    Valid because S rows never see NS rows (causal mask, S first: OT/model.py:109-110, 235).
+    blocks: list of (P dict with norm1/norm2/b1/b2, BlockWeights).  Returns [kv_l or None]."""
+    cache = []
+    dev = x_s.device
+    d = x_s.shape[1]
+    for (P, w), (cur, Tn, cur_S, keep, Tq, keep_S) in zip(blocks, plan):
+        if cur_S == 0:
+            cache.append(None)
+            x_s = x_s[:0]
+            continue
+        assert x_s.shape[0] == cur_S
+        if keep_S > 0:
+            x_s, kv, _, _ = block_forward(x_s, P, w, 1, cur_S, keep_S, H, 0, 'tail', eps, False)
+        else:
+            xn = torch.empty(cur_S, d, dtype=bf16, device=dev)
+            ops.rmsnorm_fwd(x_s, P['norm1'], xn, None, eps)
+            kv = torch.empty(cur_S, 2 * d, dtype=bf16, device=dev)
+            ops.mixed_gemm(xn, w.Wkv_f, [(0, 1, cur_S, 0, 0)], kv)
+            x_s = x_s[:0]
+        cache.append(kv)
+    return cache
+
+
+def candidates_forward(x_ns: torch.Tensor, C_: int, blocks, plan, cache, H: int, L_ns: int, eps: float,
+                       x_hp: Optional[torch.Tensor] = None):
+    """Stage 2: C candidates of the cached user.  x_ns: token-major [L_ns*C, d] NS tokens.  Per layer only the NS
+    rows are normalised / projected / fed through the FFN; attention reads the shared S-side K|V from the cache."""
+    dev = x_ns.device
+    d = x_ns.shape[1]
+    dh = d // H
+    x = x_ns
+    for (P, w), (cur, Tn, cur_S, keep, Tq, keep_S), kv_s in zip(blocks, plan, cache):
+        assert x.shape[0] == Tn * C_
+        rows, rows_t, off = Tn * C_, Tq * C_, (Tn - Tq) * C_
+        segs_all = ops.position_segments(cur - Tn, cur, cur, L_ns, 'tail', C_)
+        segs_tail = ops.position_segments(cur - Tq, cur, cur, L_ns, 'tail', C_)
+        xn = torch.empty(rows, d, dtype=bf16, device=dev)
+        ops.rmsnorm_fwd(x, P['norm1'], xn, None, eps, x_hp, 0)
+        kv = torch.empty(rows, 2 * d, dtype=bf16, device=dev)
+        ops.mixed_gemm(xn, w.Wkv_f, segs_all, kv)
+        q = torch.empty(rows_t, d, dtype=bf16, device=dev)
+        ops.mixed_gemm(xn[off:], w.Wq_f, segs_tail, q)
+        o = torch.empty(rows_t, d, dtype=bf16, device=dev)
+        Ls = 0 if kv_s is None else kv_s.shape[0]
+        ops.attn_ns_cached(q, kv[:, :d], kv[:, d:], None if kv_s is None else kv_s[:, :d], None if kv_s is None else kv_s[:, d:],
+                           o, C_, H, Tq, Tn, Ls, dh)
+        z = torch.empty(rows_t, d, dtype=bf16, device=dev)
+        z_hp = None
+        if x_hp is not None:   # every candidate row is an NS row: the whole residual stream is fp32
+            z_hp = torch.empty(rows_t, d, dtype=torch.float32, device=dev)
+            ops.mixed_gemm(o, w.Wo_f, [(0, 1, rows_t, 0, 0)], z, flags=OT_EPI_RESIDUAL, res=x[off:], res_hp=x_hp[off:], out_hp=z_hp, hp_row0=0)
+        else:
+            ops.mixed_gemm(o, w.Wo_f, [(0, 1, rows_t, 0, 0)], z, flags=OT_EPI_RESIDUAL, res=x[off:])
+        zn = torch.empty(rows_t, d, dtype=bf16, device=dev)
+        ops.rmsnorm_fwd(z, P['norm2'], zn, None, eps, z_hp, 0)
+        x, _, x_hp = ffn_forward(zn, z, w, P['b1'], P['b2'], segs_tail, False, z_hp)
+    return x, x_hp

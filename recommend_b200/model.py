@@ -157,8 +157,8 @@ class _MHAFn(torch.autograd.Function):
     def forward(ctx, x2, Wqkv, Wo, mod: MixedMHA, B, cur, keep, prefix):
         w = _weights_of(mod, None)
         cfg = mod.config
-        out, saved = engine.mha_forward(x2, None, w, B, cur, keep, cfg.num_heads, cfg.num_ns_tokens,
-                                        cfg.ns_param_alignment, prefix)
+        out, saved, _ = engine.mha_forward(x2, None, w, B, cur, keep, cfg.num_heads, cfg.num_ns_tokens,
+                                           cfg.ns_param_alignment, prefix)
         kv = saved[1]
         ctx.mark_non_differentiable(kv)
         if prefix is not None and any(ctx.needs_input_grad):
@@ -203,7 +203,7 @@ class _FFNFn(torch.autograd.Function):
         w = _weights_of(None, mod)
         cfg = mod.config
         segs = ops.position_segments(0, cur, cur, cfg.num_ns_tokens, cfg.ns_param_alignment, B)
-        y, saved = engine.ffn_forward(x2, None, w, mod.b1.detach(), mod.b2.detach(), segs, save=True)
+        y, saved, _ = engine.ffn_forward(x2, None, w, mod.b1.detach(), mod.b2.detach(), segs, save=True)
         ctx.saved = (x2, saved, w, mod, segs)
         return y
 
@@ -278,13 +278,14 @@ class OneTransBlock(nn.Module):
                 'W1': self.ffn.W1, 'b1': self.ffn.b1, 'W2': self.ffn.W2, 'b2': self.ffn.b2}
 
     def forward_token_major(self, x2: torch.Tensor, B: int, cur: int, keep: int, training: bool = False,
-                            kv_prefix: Optional[torch.Tensor] = None):
-        """Token-major entry used by OneTransModel: ``x2 [cur*B, d]`` -> ``([keep*B, d], kv [Lk*B, 2d])``."""
+                            kv_prefix: Optional[torch.Tensor] = None, x_hp: Optional[torch.Tensor] = None):
+        """Token-major entry used by OneTransModel: ``x2 [cur*B, d]`` -> ``([keep*B, d], kv [Lk*B, 2d], y_hp)``.
+        ``x_hp``: fp32 copy of the NS-token rows (high-precision residual stream) or None."""
         if training and self.dropout_rate > 0.0:
             raise NotImplementedError(
                 'dropout inside the fused block is not built yet; set config.dropout_rate = 0 for training '
                 '(SURVEY.md §8d: parity runs use dropout 0)')
-        return _BlockFn.apply(x2, self.norm1.scale, self, B, cur, keep, kv_prefix)
+        return _BlockFn.apply(x2, self.norm1.scale, self, B, cur, keep, kv_prefix, x_hp)
 
     def forward(self, x: torch.Tensor, training: bool = False,
                 kv_cache: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, query_len: Optional[int] = None):
@@ -298,7 +299,7 @@ class OneTransBlock(nn.Module):
             k2, _, _ = _to_token_major(kv_cache[0])
             v2, _, _ = _to_token_major(kv_cache[1])
             prefix = torch.cat([k2, v2], dim=1)
-        y, kv = self.forward_token_major(x2, B, L, keep, training, prefix)
+        y, kv, _ = self.forward_token_major(x2, B, L, keep, training, prefix)
         d = self.config.hidden_dim
         Lk = kv.shape[0] // B
         return _from_token_major(y, B, keep), (_from_token_major(kv[:, :d], B, Lk), _from_token_major(kv[:, d:], B, Lk))
@@ -306,7 +307,7 @@ class OneTransBlock(nn.Module):
 
 class _BlockFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x2, anchor, blk: OneTransBlock, B, cur, keep, kv_prefix):
+    def forward(ctx, x2, anchor, blk: OneTransBlock, B, cur, keep, kv_prefix, x_hp):
         cfg = blk.config
         need_grad = any(ctx.needs_input_grad)
         if need_grad and kv_prefix is not None:
@@ -314,18 +315,20 @@ class _BlockFn(torch.autograd.Function):
         w = blk._weights()
         P = {'norm1': blk.norm1.scale.detach(), 'norm2': blk.norm2.scale.detach(), 'b1': blk.ffn.b1.detach(),
              'b2': blk.ffn.b2.detach()}
-        y, kv, saved = engine.block_forward(x2, P, w, B, cur, keep, cfg.num_heads, cfg.num_ns_tokens, cfg.ns_param_alignment,
-                                            blk.norm1.eps, need_grad, kv_prefix)
-        ctx.mark_non_differentiable(kv)
+        y, kv, saved, y_hp = engine.block_forward(x2, P, w, B, cur, keep, cfg.num_heads, cfg.num_ns_tokens, cfg.ns_param_alignment,
+                                                  blk.norm1.eps, need_grad, kv_prefix, x_hp)
+        if y_hp is None:
+            y_hp = y.new_zeros(0, dtype=torch.float32)
+        ctx.mark_non_differentiable(kv, y_hp)
         ctx.saved = (saved, w, blk, B, cur, keep)
-        return y, kv
+        return y, kv, y_hp
 
     @staticmethod
-    def backward(ctx, dy, _dkv):
+    def backward(ctx, dy, _dkv, _dhp):
         saved, w, blk, B, cur, keep = ctx.saved
         dx = engine.block_backward(dy, saved, blk._params(), w, B, cur, keep, blk.config.num_heads)
         ctx.saved = None
-        return dx, None, None, None, None, None, None
+        return dx, None, None, None, None, None, None, None
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -381,7 +384,8 @@ class Tokenizer(nn.Module):
 
     def forward_token_major(self, non_seq_features, seq_features):
         ns_x, seq_list, B = self._gather_inputs(non_seq_features, seq_features)
-        X0, L = _TokenizerFn.apply(self.ns_kernel, self, ns_x, seq_list, B)
+        X0, L, X_hp = _TokenizerFn.apply(self.ns_kernel, self, ns_x, seq_list, B)
+        self._last_hp = X_hp if X_hp.numel() else None
         return X0, B, L
 
     def forward(self, non_seq_features: Dict[str, torch.Tensor], seq_features: Dict[str, torch.Tensor]) -> torch.Tensor:
@@ -394,14 +398,17 @@ class _TokenizerFn(torch.autograd.Function):
     def forward(ctx, anchor, tok: Tokenizer, ns_x, seq_list, B):
         cfg = tok.config
         d, L_ns = cfg.hidden_dim, cfg.num_ns_tokens
-        X0, L, layout = engine.tokenizer_forward(ns_x, seq_list, B, d, L_ns, tok._seq_weights(),
-                                                 [b.detach() for b in tok.seq_biases], tok.sep_embedding.detach(),
-                                                 tok.ns_kernel.detach(), tok.ns_bias.detach())
+        X0, L, layout, X_hp = engine.tokenizer_forward(ns_x, seq_list, B, d, L_ns, tok._seq_weights(),
+                                                       [b.detach() for b in tok.seq_biases], tok.sep_embedding.detach(),
+                                                       tok.ns_kernel.detach(), tok.ns_bias.detach())
+        if X_hp is None:
+            X_hp = X0.new_zeros(0, dtype=torch.float32)
+        ctx.mark_non_differentiable(X_hp)
         ctx.saved = (tok, ns_x, seq_list, layout, B)
-        return X0, L
+        return X0, L, X_hp
 
     @staticmethod
-    def backward(ctx, dX0, _dL=None):
+    def backward(ctx, dX0, _dL=None, _dhp=None):
         tok, ns_x, seq_list, layout, B = ctx.saved
         cfg = tok.config
         engine.tokenizer_backward(dX0, ns_x, seq_list, layout, B, cfg.hidden_dim, cfg.num_ns_tokens, list(tok.seq_kernels),
@@ -446,13 +453,29 @@ class OneTransModel(nn.Module):
 
     def forward(self, non_seq_features: Dict[str, torch.Tensor], seq_features: Dict[str, torch.Tensor],
                 training: bool = False, use_kv_cache: bool = False, return_logits: bool = False) -> Dict[str, torch.Tensor]:
+        if use_kv_cache and not training:
+            # OT/model.py:359-363 (as repaired, D6): reuse the cached sequence-side K/V of the current user; the
+            # first call (or a call after reset_kv_cache) builds it from batch-1 sequence features.
+            if self.kv_cache is None:
+                self.build_kv_cache(seq_features)
+            return self.score_candidates(non_seq_features, return_logits=return_logits)
         x2, B, L = self.tokenizer.forward_token_major(non_seq_features, seq_features)       # OT/model.py:342
         keep_lens = resolve_keep_lens(self.config, L)                                      # :349 (+D2, D5)
         cur = L
+        x_hp = self.tokenizer._last_hp if getattr(self.config, 'hp_ns_residual', True) else None
         for block, keep in zip(self.blocks, keep_lens):                                    # :348
-            x2, _ = block.forward_token_major(x2, B, cur, keep, training)                   # :366-371
+            if x_hp is not None:   # the NS rows that survive into this layer's input (suffix of the fp32 stream)
+                x_hp = x_hp[x_hp.shape[0] - min(self.config.num_ns_tokens, cur) * B:]
+            x2, _, x_hp = block.forward_token_major(x2, B, cur, keep, training, None, x_hp)   # :366-371
+            if x_hp.numel() == 0:
+                x_hp = None
             cur = keep
-        return self._heads(x2[(cur - 1) * B:cur * B], return_logits)
+        x_last = x2[(cur - 1) * B:cur * B]
+        if x_hp is not None:
+            # value of the fp32 stream, gradient through the bf16 activations the kernels differentiate
+            xf = x_last.float()
+            x_last = xf + (x_hp[-B:] - xf).detach()
+        return self._heads(x_last, return_logits)
 
     def _heads(self, x_last: torch.Tensor, return_logits: bool) -> Dict[str, torch.Tensor]:
         # output norm (OT/model.py:384) and heads (:388-391) on the last token, in fp32
@@ -463,6 +486,56 @@ class OneTransModel(nn.Module):
             logit = head(xn)
             out[task] = logit if return_logits else torch.sigmoid(logit)
         return out
+
+    # ---- inference with a cross-candidate cache of the sequence-side K/V (PAPER:144-151; repair D6) ----
+    def _block_bundles(self):
+        return [({'norm1': b.norm1.scale.detach(), 'norm2': b.norm2.scale.detach(), 'b1': b.ffn.b1.detach(), 'b2': b.ffn.b2.detach()},
+                 b._weights()) for b in self.blocks]
+
+    @torch.no_grad()
+    def build_kv_cache(self, seq_features: Dict[str, torch.Tensor]):
+        """Stage 1, once per user: ``seq_features`` with batch 1.  Runs the S tokens alone through the stack and
+        returns (and stores in ``self.kv_cache``) every layer's sequence-side K|V."""
+        cfg = self.config
+        if cfg.ns_param_alignment != 'tail':
+            raise NotImplementedError("the KV cache needs ns_param_alignment='tail' (NS weights on the NS tokens)")
+        tok = self.tokenizer
+        seq_list = []
+        for name in cfg.feature_config['sequence_features']:
+            e = seq_features.get(name)
+            if e is not None:
+                _require_cuda(e, 'build_kv_cache')
+                if e.shape[0] != 1:
+                    raise ValueError('build_kv_cache caches ONE user: sequence features must have batch 1')
+                e = e.to(bf16).contiguous()
+            seq_list.append(e)
+        x_s, L_s, _, _ = engine.tokenizer_forward(None, seq_list, 1, cfg.hidden_dim, 0, tok._seq_weights(),
+                                               [b.detach() for b in tok.seq_biases], tok.sep_embedding.detach(),
+                                               tok.ns_kernel.detach(), tok.ns_bias.detach())
+        L0 = L_s + cfg.num_ns_tokens
+        plan = engine.layer_plan(L0, cfg.num_ns_tokens, resolve_keep_lens(cfg, L0))
+        layers = engine.user_cache_forward(x_s, self._block_bundles(), plan, cfg.num_heads, self.blocks[0].norm1.eps)
+        self.kv_cache = {'plan': plan, 'layers': layers, 'L0': L0}
+        return self.kv_cache
+
+    @torch.no_grad()
+    def score_candidates(self, non_seq_features: Dict[str, torch.Tensor], kv_cache=None, return_logits: bool = False):
+        """Stage 2: score C candidates of the cached user; only the NS tokens are computed per candidate."""
+        cache = kv_cache if kv_cache is not None else self.kv_cache
+        if cache is None:
+            raise RuntimeError('score_candidates: no KV cache; call build_kv_cache(seq_features) first')
+        cfg = self.config
+        tok = self.tokenizer
+        ns_x, _, C_ = tok._gather_inputs(non_seq_features, {})
+        if ns_x is None:
+            raise ValueError('score_candidates needs the non-sequence features of the candidates')
+        d, L_ns = cfg.hidden_dim, cfg.num_ns_tokens
+        x_ns = torch.empty(L_ns * C_, d, dtype=bf16, device=ns_x.device)
+        x_hp = torch.empty(L_ns * C_, d, dtype=torch.float32, device=ns_x.device) if getattr(cfg, 'hp_ns_residual', True) else None
+        ops.ns_tokenizer_fwd(ns_x, tok.ns_kernel.detach(), tok.ns_bias.detach(), x_ns, 0, C_, L_ns, d, x_hp)
+        x, x_hp = engine.candidates_forward(x_ns, C_, self._block_bundles(), cache['plan'], cache['layers'], cfg.num_heads, L_ns,
+                                            self.blocks[0].norm1.eps, x_hp)
+        return self._heads(x_hp[-C_:] if x_hp is not None else x[-C_:], return_logits)
 
     def reset_kv_cache(self):
         """OT/model.py:395-397."""

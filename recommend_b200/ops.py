@@ -101,7 +101,8 @@ def mixed_gemm(A: torch.Tensor, W: torch.Tensor, segs: Sequence[Seg], out: torch
                bias: Optional[torch.Tensor] = None, res: Optional[torch.Tensor] = None,
                aux: Optional[torch.Tensor] = None, out2: Optional[torch.Tensor] = None,
                row_scale: Optional[torch.Tensor] = None, a_transposed_events: bool = False,
-               block_n: int = 0, swizzle: int = 0) -> torch.Tensor:
+               block_n: int = 0, swizzle: int = 0, res_hp: Optional[torch.Tensor] = None,
+               out_hp: Optional[torch.Tensor] = None, hp_row0: int = 0) -> torch.Tensor:
     """``out[row] = epilogue(A[row] @ W[group(row)].T)``.  W: ``[G, N, K]`` bf16 (rows may be strided).
     With ``a_transposed_events`` A is ``[B, L_i, K]`` and output rows are ``(l, b)`` token-major."""
     _check_bf16(W, 'W')
@@ -143,6 +144,11 @@ def mixed_gemm(A: torch.Tensor, W: torch.Tensor, segs: Sequence[Seg], out: torch
         assert row_scale.dtype == torch.float32
         p.row_scale = row_scale.data_ptr()
     p.block_n, p.swizzle = block_n, swizzle
+    if res_hp is not None:
+        # fp32 residual stream of the NS-token rows (output rows >= hp_row0)
+        assert out_hp is not None and res_hp.dtype == torch.float32 and out_hp.dtype == torch.float32
+        assert res_hp.stride(-1) == 1 and out_hp.stride(-1) == 1 and res_hp.stride(0) == out_hp.stride(0)
+        p.res_hp, p.out_hp, p.ld_hp, p.hp_row0 = res_hp.data_ptr(), out_hp.data_ptr(), res_hp.stride(0), hp_row0
     rows = sum(s[1] * s[2] for s in segs)
     groups = sum((s[1] if s[4] else 1) for s in segs)
     n_io = 1 + (out2 is not None) + (res is not None) + (aux is not None)
@@ -224,13 +230,37 @@ def attn_bwd(q, k, v, o, lse, d_o, dq, dk, dv, delta, B: int, H: int, Lq: int, L
          (4.0 * Lq + 4.0 * Lk) * B * d * 2.0, n_launch=2)
 
 
-def rmsnorm_fwd(x: torch.Tensor, gain: torch.Tensor, y: torch.Tensor, rstd: Optional[torch.Tensor], eps: float = 1e-6) -> None:
+def attn_ns_cached(q: torch.Tensor, k_own: torch.Tensor, v_own: torch.Tensor, k_shared: Optional[torch.Tensor],
+                   v_shared: Optional[torch.Tensor], o: torch.Tensor, C_: int, H: int, Tq: int, Tn: int, Ls: int, head_dim: int) -> None:
+    """NS-token queries of C candidates against the user's cached S-side K/V plus their own NS K/V."""
+    for t, n in ((q, 'q'), (k_own, 'k_own'), (v_own, 'v_own'), (o, 'o')):
+        _check_bf16(t, n)
+    p = L.AttnCachedParams()
+    p.q, p.ldq, p.k_own, p.ld_own_k, p.v_own, p.ld_own_v = q.data_ptr(), q.stride(0), k_own.data_ptr(), k_own.stride(0), v_own.data_ptr(), v_own.stride(0)
+    if Ls > 0:
+        _check_bf16(k_shared, 'k_shared')
+        _check_bf16(v_shared, 'v_shared')
+        p.k_shared, p.ld_shared_k, p.v_shared, p.ld_shared_v = k_shared.data_ptr(), k_shared.stride(0), v_shared.data_ptr(), v_shared.stride(0)
+    p.o, p.ldo = o.data_ptr(), o.stride(0)
+    p.C, p.H, p.Tq, p.Tn, p.Ls, p.head_dim = C_, H, Tq, Tn, Ls, head_dim
+    pairs = Tq * (Ls + Tn) - Tq * (Tq - 1) / 2.0
+    d = H * head_dim
+    _run('ot_attn_ns_cached_fwd', L.load().ot_attn_ns_cached_fwd, p, f'Tq{Tq}_Ls{Ls}', 4.0 * C_ * H * head_dim * pairs,
+         (2.0 * Tq + 2.0 * Tn) * C_ * d * 2.0 + 2.0 * Ls * d * 2.0)
+
+
+def rmsnorm_fwd(x: torch.Tensor, gain: torch.Tensor, y: torch.Tensor, rstd: Optional[torch.Tensor], eps: float = 1e-6,
+                x_hp: Optional[torch.Tensor] = None, hp_row0: int = 0) -> None:
     _check_bf16(x, 'x')
     _check_bf16(y, 'y')
     assert gain.dtype == torch.float32 and gain.is_cuda and gain.is_contiguous()
     p = L.RmsnormParams()
     p.x, p.ldx, p.y, p.ldy, p.gain, p.rstd = x.data_ptr(), x.stride(0), y.data_ptr(), y.stride(0), gain.data_ptr(), _ptr(rstd)
     p.rows, p.d, p.eps = x.shape[0], x.shape[1], eps
+    if x_hp is not None and x_hp.shape[0] > 0:
+        assert x_hp.dtype == torch.float32 and x_hp.is_contiguous() and x_hp.shape[1] == x.shape[1]
+        assert hp_row0 + x_hp.shape[0] == x.shape[0]
+        p.x_hp, p.hp_row0 = x_hp.data_ptr(), hp_row0
     _run('ot_rmsnorm_fwd', L.load().ot_rmsnorm_fwd, p, f'd{x.shape[1]}', 3.0 * x.numel(), x.numel() * 4.0 + x.shape[0] * 4.0)
 
 
@@ -252,11 +282,14 @@ def rmsnorm_bwd(dy: torch.Tensor, x: torch.Tensor, rstd: torch.Tensor, gain: tor
 
 
 def ns_tokenizer_fwd(x: torch.Tensor, W: torch.Tensor, bias: torch.Tensor, out: torch.Tensor, row0: int, B: int,
-                     L_ns: int, d: int) -> None:
+                     L_ns: int, d: int, out_hp: Optional[torch.Tensor] = None) -> None:
     assert x.dtype == torch.float32 and x.is_contiguous() and W.dtype == torch.float32 and W.is_contiguous()
     p = L.NsTokenizerParams()
     p.x, p.W, p.bias, p.out, p.ldo = x.data_ptr(), W.data_ptr(), bias.data_ptr(), out.data_ptr(), out.stride(0)
     p.row0, p.B, p.L_ns, p.d, p.n_feat = row0, B, L_ns, d, x.shape[1]
+    if out_hp is not None:
+        assert out_hp.dtype == torch.float32 and out_hp.is_contiguous() and out_hp.shape == (L_ns * B, d)
+        p.out_hp = out_hp.data_ptr()
     _run('ot_ns_tokenizer_fwd', L.load().ot_ns_tokenizer_fwd, p, '', 2.0 * B * L_ns * d * x.shape[1], B * L_ns * d * 2.0)
 
 

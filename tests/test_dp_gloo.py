@@ -1,0 +1,80 @@
+"""Data-parallel host logic on CPU: world_size-2 gloo run of FlatGradBuffer.all_reduce (the only exchange on
+the path).  Each rank computes oracle gradients on its half of a global batch; after the
+all-reduce every rank must hold the gradients of the full batch (T10, DP half)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import onetrans_oracle as O
+from recommend_b200.train import FlatGradBuffer, bce_loss
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _cfg():
+    return O.OracleConfig(hidden_dim=32, num_layers=2, num_heads=2, ffn_dim=64, num_ns_tokens=3, dropout_rate=0.0)
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    cfg = _cfg()
+    P = O.init_params(cfg, seed=0)
+    non_seq, seq, labels = O.synthetic_batch(cfg, 8, (5, 4, 3), seed=7)   # the GLOBAL batch, identical on every rank
+    per = 8 // world
+    sl = slice(rank * per, (rank + 1) * per)                               # rank r takes rows [r*B_local, (r+1)*B_local)
+    shard = lambda d: {k: v[sl] for k, v in d.items()}
+    _, grads, _ = O.loss_and_grads(P, cfg, shard(non_seq), shard(seq), shard(labels))
+    names = sorted(P)
+    params = [torch.nn.Parameter(P[n].clone()) for n in names]
+    buf = FlatGradBuffer(params)
+    for p, n in zip(params, names):
+        p.grad.copy_(grads[n])
+    buf.all_reduce(world, bucket_bytes=4096)                               # several buckets
+    torch.save({n: p.grad.clone() for p, n in zip(params, names)}, os.path.join(out_dir, f'rank{rank}.pt'))
+    dist.destroy_process_group()
+
+
+def test_allreduced_shard_grads_equal_full_batch_grads(tmp_path):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    cfg = _cfg()
+    P = O.init_params(cfg, seed=0)
+    non_seq, seq, labels = O.synthetic_batch(cfg, 8, (5, 4, 3), seed=7)
+    _, full, _ = O.loss_and_grads(P, cfg, non_seq, seq, labels)
+    r0 = torch.load(os.path.join(tmp_path, 'rank0.pt'))
+    r1 = torch.load(os.path.join(tmp_path, 'rank1.pt'))
+    for n in full:
+        assert torch.equal(r0[n], r1[n]), n                                # every rank holds the same reduced gradient
+        assert torch.allclose(r0[n], full[n], rtol=1e-4, atol=1e-6), n
+
+
+def test_flat_grad_buffer_views_and_zero():
+    ps = [torch.nn.Parameter(torch.randn(3, 4)), torch.nn.Parameter(torch.randn(5))]
+    buf = FlatGradBuffer(ps)
+    assert buf.flat.numel() == 17
+    ps[0].grad.add_(1.0)
+    ps[1].grad.add_(2.0)
+    assert buf.flat[:12].eq(1).all() and buf.flat[12:].eq(2).all()
+    buf.zero()
+    assert ps[0].grad.abs().sum() == 0 and ps[1].grad.abs().sum() == 0
+    buf.all_reduce(1)   # world 1: no-op, no process group needed
+
+
+def test_bce_matches_oracle():
+    torch.manual_seed(0)
+    p = {'ctr': torch.rand(6, 1), 'cvr': torch.rand(6, 1)}
+    y = {'ctr': (torch.rand(6, 1) < 0.5).float(), 'cvr': (torch.rand(6, 1) < 0.5).float()}
+    assert torch.allclose(bce_loss(p, y, ['ctr', 'cvr']), O.bce_loss(p, y, ['ctr', 'cvr']))

@@ -137,3 +137,32 @@ def test_causality():
         y1, _ = blk(x2)
     assert torch.equal(y0[:, :j, :], y1[:, :j, :])
     assert not torch.equal(y0[:, j:, :], y1[:, j:, :])
+
+
+def test_t9_auc_delta_on_64k_samples():
+    """north_star: AUC delta <= 1e-4 (exact ROC-AUC, sklearn) between the bf16 kernels and the fp32 oracle on >= 64k
+    synthetic samples.  Labels are drawn from the oracle's own probabilities so that the AUC is meaningful."""
+    from sklearn.metrics import roc_auc_score
+    ocfg, cfg = make_configs(num_layers=2, ffn_dim=512, num_ns_tokens=8, schedule='linear_to_ns')
+    P, model = _build(ocfg, cfg, seed=9)
+    N, chunk = 65536, 4096
+    seq_lens = (12, 10, 8)
+    ocfg.pyramid_keep_lens = R.resolve_keep_lens(cfg, sum(seq_lens) + 2 + 8)
+    po, pg = {t: [] for t in cfg.tasks}, {t: [] for t in cfg.tasks}
+    for i in range(N // chunk):
+        non_seq, seq, _ = O.synthetic_batch(ocfg, chunk, seq_lens, seed=100 + i)
+        non_seq, seq = bf16_round_inputs(non_seq, seq)
+        o = O.model_forward(P, ocfg, non_seq, seq)
+        with torch.no_grad():
+            g = model(to_cuda(non_seq), to_cuda(seq))
+        for t in cfg.tasks:
+            po[t].append(o[t].flatten())
+            pg[t].append(g[t].flatten().float().cpu())
+    gen = torch.Generator().manual_seed(0)
+    for t in cfg.tasks:
+        a, b = torch.cat(po[t]), torch.cat(pg[t])
+        logit = torch.logit(a.clamp(1e-6, 1 - 1e-6)) * 3.0          # sharpen: random-init logits are small
+        y = (torch.rand(N, generator=gen) < torch.sigmoid(logit)).numpy()
+        auc_o, auc_g = roc_auc_score(y, a.numpy()), roc_auc_score(y, b.numpy())
+        print(f'AUC[{t}] oracle {auc_o:.6f} kernels {auc_g:.6f} delta {abs(auc_o - auc_g):.2e}')
+        assert abs(auc_o - auc_g) <= 1e-4

@@ -84,7 +84,7 @@ def test_position_segments_match_oracle_rule(alignment):
 
 def test_library_loads_and_exports_every_declared_symbol():
     lib = _lib.load()
-    assert lib.ot_version() == 1
+    assert lib.ot_version() == 2
     declared = set(re.findall(r'^\s*(?:int|const char\*)\s+(ot_\w+)\s*\(', open(HEADER).read(), re.M))
     assert declared == set(_lib.EXPORTED_SYMBOLS)
     for name in declared:
@@ -94,7 +94,7 @@ def test_library_loads_and_exports_every_declared_symbol():
 def test_ctypes_structs_match_header_layout():
     """Compile a C probe that prints sizeof/offsetof for every params struct and compare with ctypes."""
     pairs = [('ot_gemm_seg', _lib.GemmSeg), ('ot_gemm_params', _lib.GemmParams), ('ot_wgrad_seg', _lib.WgradSeg),
-             ('ot_wgrad_params', _lib.WgradParams), ('ot_attn_params', _lib.AttnParams), ('ot_rmsnorm_params', _lib.RmsnormParams),
+             ('ot_wgrad_params', _lib.WgradParams), ('ot_attn_params', _lib.AttnParams), ('ot_attn_cached_params', _lib.AttnCachedParams), ('ot_rmsnorm_params', _lib.RmsnormParams),
              ('ot_ns_tokenizer_params', _lib.NsTokenizerParams), ('ot_colsum_params', _lib.ColsumParams)]
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', 'int main(void){']
     for cname, st in pairs:
@@ -137,3 +137,23 @@ def test_param_name_map_roundtrip_and_counts():
     E = R.export_reference_style_params(m)
     assert set(E) == set(P)
     assert all(torch.equal(E[k], P[k].reshape(E[k].shape)) for k in P)
+
+
+def test_gelu_approximation_constants():
+    """The epilogue GELU evaluates erf(x/sqrt2) as tanh(x*(c1 + c3 x^2 + c5 x^4)) (ot_common.cuh); check the constants'
+    error bounds against the exact erf form the reference uses (Keras activation='gelu')."""
+    import math
+    src = open(os.path.join(ROOT, 'recommend_b200', 'csrc', 'ot_common.cuh')).read()
+    m = re.search(r'kGeluC1 = ([-0-9.e+]+)f, kGeluC3 = ([-0-9.e+]+)f, kGeluC5 = ([-0-9.e+]+)f', src)
+    c1, c3, c5 = (float(v) for v in m.groups())
+    x = torch.linspace(-12, 12, 240001, dtype=torch.float64)
+    xc = x.clamp(-8, 8)
+    t = torch.tanh(xc * (c1 + c3 * xc ** 2 + c5 * xc ** 4))
+    erf = torch.erf(x / math.sqrt(2))
+    assert (t - erf).abs().max() < 4e-5
+    gelu = 0.5 * x * (1 + t)
+    assert (gelu - 0.5 * x * (1 + erf)).abs().max() < 6e-5
+    du = c1 + 3 * c3 * xc ** 2 + 5 * c5 * xc ** 4
+    grad = 0.5 * (1 + t) + xc * 0.5 * (1 - t * t) * du
+    ref = 0.5 * (1 + erf) + x * torch.exp(-x * x / 2) / math.sqrt(2 * math.pi)
+    assert (grad - ref).abs().max() < 1.5e-4
