@@ -34,16 +34,15 @@ struct AttnBwdFusedKParams {
 };
 
 static constexpr float kLog2eF = 1.4426950408889634f;
-static constexpr int FB_THREADS = 320;   // 8 element-wise warps + MMA warp + loader warp
+static constexpr int FB_THREADS = 448;   // 8 element-wise warps + MMA warp + loader warp + 4 output warps
 static constexpr int FB_DH = 64;
 
 struct AttnBwdFusedCfg {
   using T = AttnTile<FB_DH, 128>;
   static constexpr int KV_BUFS = 2;     // K_j/V_j of the next item are fetched while this item runs
-  static constexpr int Q_STAGES = 2;    // Q_i/dO_i are fetched one step ahead
+  static constexpr int Q_STAGES = 3;    // Q_i/dO_i are fetched two steps ahead (TMA latency stays off the MMA chain)
   static constexpr int INFO_SLOTS = 8;
-  static constexpr int STG_BYTES = 128 * 128;   // one [128 x 64] bf16 output tile staged for coalesced stores
-  static constexpr int TILES_BYTES = T::TILE_BYTES * (2 * KV_BUFS + 2 * Q_STAGES) + 2 * PT_BYTES + STG_BYTES;
+  static constexpr int TILES_BYTES = T::TILE_BYTES * (2 * KV_BUFS + 2 * Q_STAGES) + 2 * PT_BYTES;
   static constexpr int SMEM_BYTES = TILES_BYTES + INFO_SLOTS * 32 + 256;
   static constexpr uint32_t T_S = 0, T_DP = 128, T_DV = 256, T_DK = 320, T_DQ = 384;
 };
@@ -109,19 +108,18 @@ ot_attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   uint8_t* sdO = sQ + Cfg::Q_STAGES * T::TILE_BYTES;       // [Q_STAGES]
   uint8_t* sP = sdO + Cfg::Q_STAGES * T::TILE_BYTES;
   uint8_t* sdS = sP + PT_BYTES;
-  uint8_t* sStg = sdS + PT_BYTES;
   StepInfo* info = reinterpret_cast<StepInfo*>(smem + Cfg::TILES_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::TILES_BYTES + Cfg::INFO_SLOTS * 32);
   uint64_t* bar_kv = bars;            // [2] K_j, V_j landed                     (loader -> MMA)
   uint64_t* bar_kvfree = bars + 2;    // [2] MMAs of the item's last step done   (MMA commit -> loader)
   uint64_t* bar_q = bars + 4;         // [Q_STAGES] Q_i, dO_i landed (+ step info) (loader -> MMA)
-  uint64_t* bar_qfree = bars + 7;     // [Q_STAGES] MMAs of the step done          (MMA commit -> loader)
+  uint64_t* bar_qfree = bars + 7;     // [Q_STAGES] stage released                 (4 output-warp arrivals -> loader)
   uint64_t* bar_s = bars + 10;        // S, dP MMAs complete                     (per step)
   uint64_t* bar_sread = bars + 11;    // E warps pulled S, dP out of TMEM        (per step, 8 arrivals)
   uint64_t* bar_pds = bars + 12;      // P, dS tiles written                     (per step, 8 arrivals)
   uint64_t* bar_d = bars + 13;        // dV, dK, dQp MMAs complete               (per step)
-  uint64_t* bar_dqfree = bars + 14;   // E warps pulled dQp out of TMEM          (per step, 8 arrivals)
-  uint64_t* bar_accfree = bars + 15;  // E warps pulled dV, dK out               (per item, 8 arrivals)
+  uint64_t* bar_dqfree = bars + 14;   // output warps pulled dQp out of TMEM     (per step, 4 arrivals)
+  uint64_t* bar_accfree = bars + 15;  // output warps pulled dV, dK out          (per item, 4 arrivals)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
 
   const int tid = threadIdx.x;
@@ -132,13 +130,13 @@ ot_attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     if ((smem_u32(smem) & 1023u) != 0) __trap();
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmdO);
     for (int i = 0; i < 2; ++i) { mbar_init(&bar_kv[i], 1); mbar_init(&bar_kvfree[i], 1); }
-    for (int i = 0; i < Cfg::Q_STAGES; ++i) { mbar_init(&bar_q[i], 1); mbar_init(&bar_qfree[i], 1); }
+    for (int i = 0; i < Cfg::Q_STAGES; ++i) { mbar_init(&bar_q[i], 1); mbar_init(&bar_qfree[i], 4); }
     mbar_init(bar_s, 1);
     mbar_init(bar_sread, 8);
     mbar_init(bar_pds, 8);
     mbar_init(bar_d, 1);
-    mbar_init(bar_dqfree, 8);
-    mbar_init(bar_accfree, 8);
+    mbar_init(bar_dqfree, 4);
+    mbar_init(bar_accfree, 4);
     fence_mbar_init();
   }
   if (warp == 8) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
@@ -250,13 +248,86 @@ ot_attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         for (int kk = 0; kk < 8; ++kk)   // dQp[q, e] = sum_key dS[q, key] K[key, e]
           umma_bf16_ss(tmem_base + Cfg::T_DQ, (kk < 4 ? dS_k0 : dS_k1) + 2 * (kk & 3), mK + 128 * kk, idesc_q, kk != 0);
         umma_commit(bar_d);
-        umma_commit(&bar_qfree[st]);
         if (si.flags & SI_LAST) umma_commit(&bar_kvfree[kb]);
         ++g;
       }
     }
+  } else if (warp >= 10) {
+    // ============================== output warps (10-13) ==============================
+    // Every finished [128 x 64] accumulator tile (dQ partial of each step; dV and dK at the end of an item) leaves
+    // through these four warps: TMEM -> registers -> bf16 -> swizzled smem staging -> global in full 128-byte rows
+    // (row-per-thread stores cost 32 memory transactions per instruction and slowed the whole SM down).  The staging
+    // buffer is the Q tile of the step's own pipeline stage, which is dead once bar_d completes; the stage goes back
+    // to the loader only when these warps are done with it.  The element-wise warps never wait for their own MMAs.
+    const int lgrp = warp & 3;
+    const int row = lgrp * 32 + lane;
+    const int ot = ((warp - 10) << 5) | lane;         // 0..127 among the output warps
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(lgrp * 32) << 16);
+    uint32_t g = 0;
+    bool end = false;
+    while (!end) {
+      mbar_wait(bar_d, g & 1);                        // dV, dK, dQp MMAs of step g complete
+      tc_fence_after();
+      const StepInfo si = info[g & (Cfg::INFO_SLOTS - 1)];
+      // the Q tile of this step's stage is dead now (every MMA that read it has completed): it is the staging buffer
+      uint8_t* sStg = sQ + (g % Cfg::Q_STAGES) * T::TILE_BYTES;
+      end = (si.flags & SI_END) != 0;
+      const bool last_of_item = si.flags & SI_LAST;
+      const int n_pass = last_of_item ? 3 : 1;        // dQp | dV | dK
+#pragma unroll 1
+      for (int pass = 0; pass < n_pass; ++pass) {
+        const uint32_t tcol = pass == 0 ? Cfg::T_DQ : (pass == 1 ? Cfg::T_DV : Cfg::T_DK);
+        uint32_t v0[32], v1[32];
+        tmem_ld_x32(t_row + tcol, v0);
+        tmem_ld_x32(t_row + tcol + 32, v1);
+        tmem_ld_wait();
+        if (pass == 0 || pass == 2) {                 // dQp / (dV, dK) columns are free again
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(pass == 0 ? bar_dqfree : bar_accfree);
+        }
+        named_bar_sync(2, 128);                       // previous readers of the staging tile are done
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          *reinterpret_cast<uint4*>(sStg + swz_off<128>(row, ch)) =
+              make_uint4(pack_bf16x2(__uint_as_float(v0[ch * 8 + 0]), __uint_as_float(v0[ch * 8 + 1])),
+                         pack_bf16x2(__uint_as_float(v0[ch * 8 + 2]), __uint_as_float(v0[ch * 8 + 3])),
+                         pack_bf16x2(__uint_as_float(v0[ch * 8 + 4]), __uint_as_float(v0[ch * 8 + 5])),
+                         pack_bf16x2(__uint_as_float(v0[ch * 8 + 6]), __uint_as_float(v0[ch * 8 + 7])));
+          *reinterpret_cast<uint4*>(sStg + swz_off<128>(row, 4 + ch)) =
+              make_uint4(pack_bf16x2(__uint_as_float(v1[ch * 8 + 0]), __uint_as_float(v1[ch * 8 + 1])),
+                         pack_bf16x2(__uint_as_float(v1[ch * 8 + 2]), __uint_as_float(v1[ch * 8 + 3])),
+                         pack_bf16x2(__uint_as_float(v1[ch * 8 + 4]), __uint_as_float(v1[ch * 8 + 5])),
+                         pack_bf16x2(__uint_as_float(v1[ch * 8 + 6]), __uint_as_float(v1[ch * 8 + 7])));
+        }
+        named_bar_sync(2, 128);
+        // tile row r <-> query (pass 0) or key (pass 1/2) position base+r; 8 lanes x 16 B cover one output row
+        const int base = pass == 0 ? si.q0 : si.k0;
+        const int limit = pass == 0 ? p.Lq : p.Lk;
+        __nv_bfloat16* gptr = pass == 0 ? p.dq : (pass == 1 ? p.dv : p.dk);
+        const long long gld = pass == 0 ? p.lddq : (pass == 1 ? p.lddv : p.lddk);
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int r = it * 16 + (ot >> 3);
+          const int ch = ot & 7;
+          if (base + r < limit) {
+            const uint4 q = *reinterpret_cast<const uint4*>(sStg + swz_off<128>(r, ch));
+            __nv_bfloat16* dst = gptr + ((long long)(base + r) * p.B + si.b) * gld + si.h * DH + ch * 8;
+            if (pass == 0) {
+              if (!(p.dbg & 1)) red_add_bf16x8(dst, q.x, q.y, q.z, q.w);
+            } else {
+              *reinterpret_cast<uint4*>(dst) = q;
+            }
+          }
+        }
+      }
+      // hand the Q/dO stage (whose Q tile served as staging) back to the loader
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_qfree[g % Cfg::Q_STAGES]);
+      ++g;
+    }
   } else {
-    // ============================== element-wise warps ==============================
+    // ============================== element-wise warps (0-7) ==============================
     const int half = warp >> 2;
     const int row = (warp & 3) * 32 + lane;
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
@@ -332,8 +403,8 @@ ot_attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         }
       }
       OT_TICK(1);   // TMEM loads + exp math
-      // P/dS tiles are free once the MMAs of the previous step have read them
-      if (!first_of_item) {
+      // P/dS tiles are free once the MMAs of the previous step (possibly the previous item's last) have read them
+      if (g > 0) {
         mbar_wait(bar_d, (g - 1) & 1);
         tc_fence_after();
       }
@@ -358,64 +429,6 @@ ot_attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       if (lane == 0) mbar_arrive(bar_pds);
       OT_TICK(3);   // P/dS stores
 
-      // ---- outputs: dQ partial of the previous step; on the item's last step also this step's dQ partial, dV, dK.
-      // Each [128 x 64] tile goes TMEM -> registers -> bf16 -> swizzled smem staging -> global in full 128-byte rows
-      // (row-per-thread stores would cost 32 memory transactions per instruction).
-      const int et = tid;                       // 0..255 among the element-wise warps
-#pragma unroll 1
-      for (int pass = 0; pass < 4; ++pass) {
-        // pass 0: dQp of step g-1 | pass 1: dQp of step g | pass 2: dV | pass 3: dK   (1..3 only on the last step)
-        if (pass == 0 && first_of_item) continue;
-        if (pass >= 1 && !last_of_item) break;
-        if (pass == 1) {
-          OT_TICK(4);   // dQ flush of the previous step
-          mbar_wait(bar_d, g & 1);              // MMAs of this (last) step
-          tc_fence_after();
-          OT_TICK(5);   // wait for the last step's MMAs
-        }
-        const uint32_t tcol = pass <= 1 ? Cfg::T_DQ : (pass == 2 ? Cfg::T_DV : Cfg::T_DK);
-        uint32_t v[32];
-        tmem_ld_x32(t_row + tcol + half * 32, v);
-        tmem_ld_wait();
-        if (pass <= 1 || pass == 3) {           // dQp / (dV, dK) columns are free again
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(pass == 3 ? bar_accfree : bar_dqfree);
-        }
-        named_bar_sync(1, 256);                 // previous readers of the staging tile are done
-        {
-          uint32_t row_v = row;
-          asm volatile("" : "+r"(row_v));
-#pragma unroll
-          for (int ch = 0; ch < 4; ++ch)
-            *reinterpret_cast<uint4*>(sStg + swz_off<128>(row_v, half * 4 + ch)) =
-                make_uint4(pack_bf16x2(__uint_as_float(v[ch * 8 + 0]), __uint_as_float(v[ch * 8 + 1])),
-                           pack_bf16x2(__uint_as_float(v[ch * 8 + 2]), __uint_as_float(v[ch * 8 + 3])),
-                           pack_bf16x2(__uint_as_float(v[ch * 8 + 4]), __uint_as_float(v[ch * 8 + 5])),
-                           pack_bf16x2(__uint_as_float(v[ch * 8 + 6]), __uint_as_float(v[ch * 8 + 7])));
-        }
-        named_bar_sync(1, 256);
-        // tile row r <-> query (pass 0/1) or key (pass 2/3) position base+r; 8 lanes x 16 B cover one row
-        const int base = pass == 0 ? q0 - 128 : (pass == 1 ? q0 : k0);
-        const int limit = pass <= 1 ? p.Lq : p.Lk;
-        __nv_bfloat16* gptr = pass <= 1 ? p.dq : (pass == 2 ? p.dv : p.dk);
-        const long long gld = pass <= 1 ? p.lddq : (pass == 2 ? p.lddv : p.lddk);
-#pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          const int r = it * 32 + (et >> 3);
-          const int ch = et & 7;
-          if (base + r < limit) {
-            const uint4 q = *reinterpret_cast<const uint4*>(sStg + swz_off<128>(r, ch));
-            __nv_bfloat16* dst = gptr + ((long long)(base + r) * p.B + b) * gld + h * DH + ch * 8;
-            if (pass <= 1) {
-              if (!(p.dbg & 1)) red_add_bf16x8(dst, q.x, q.y, q.z, q.w);
-            } else {
-              *reinterpret_cast<uint4*>(dst) = q;
-            }
-          }
-        }
-      }
-      OT_TICK(6);   // dQ flush (+ dV/dK epilogue on the last step of an item)
       ++g;
     }
     if ((p.dbg & 2) && p.dbg_buf != nullptr && warp == 0 && lane == 0 && blockIdx.x < 8) {
@@ -509,7 +522,7 @@ int attn_bwd_fused_impl(const ot_attn_params* p, cudaStream_t st) {
     unsigned long long h[64];
     cudaStreamSynchronize(st);
     cudaMemcpy(h, kp.dbg_buf, sizeof(h), cudaMemcpyDeviceToHost);
-    static const char* names[7] = {"wait S/dP", "tmem+exp", "wait prev MMAs", "P/dS stores", "dQ flush(prev)", "wait last MMAs", "flush+epilogue"};
+    static const char* names[7] = {"wait S/dP", "tmem+exp", "wait prev MMAs", "P/dS stores", "-", "-", "-"};
     for (int c = 0; c < 2; ++c) {
       fprintf(stderr, "[attn_bwd cta %d] steps=%llu cycles/step:", c, h[c * 8 + 7]);
       for (int i = 0; i < 7; ++i) fprintf(stderr, " %s=%.0f", names[i], (double)h[c * 8 + i] / (double)(h[c * 8 + 7] ? h[c * 8 + 7] : 1));
