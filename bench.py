@@ -113,11 +113,11 @@ def measured_peaks():
 # CPU arm: the oracle port timed on the host cores (cpu_baseline, and --impl reference)
 # ---------------------------------------------------------------------------------------------------
 
-def cpu_oracle_samples_per_sec(wl, sample_B: int, steps: int, warmup: int):
+def cpu_oracle_samples_per_sec(wl, sample_B: int, steps: int, warmup: int, dropout: float = 0.0):
     from oracle import onetrans_oracle as O
     torch.set_num_threads(os.cpu_count() or 1)
     ocfg = O.small_config(num_ns_tokens=wl['L_ns']) if wl['model'] == 'small' else O.default_config(num_ns_tokens=wl['L_ns'])
-    ocfg.dropout_rate = 0.0
+    ocfg.dropout_rate = dropout
     L0 = sum(wl['seq_lens']) + 2 + wl['L_ns']
     ocfg.pyramid_keep_lens = resolve_schedule(wl, ocfg.num_layers, L0)
     P = O.init_params(ocfg, seed=0)
@@ -125,7 +125,7 @@ def cpu_oracle_samples_per_sec(wl, sample_B: int, steps: int, warmup: int):
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        O.loss_and_grads(P, ocfg, non_seq, seq, labels)
+        O.loss_and_grads(P, ocfg, non_seq, seq, labels, training=dropout > 0, gen=torch.Generator().manual_seed(i))
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
@@ -146,7 +146,7 @@ def run_reference_arm(args, wl, rank):
     if rank != 0:
         return
     sample_B = args.cpu_sample_batch
-    v, ms, cores = cpu_oracle_samples_per_sec(wl, sample_B, max(1, args.steps), max(0, args.warmup))
+    v, ms, cores = cpu_oracle_samples_per_sec(wl, sample_B, max(1, args.steps), max(0, args.warmup), args.dropout)
     line = {
         'impl': 'reference', 'metric': 'OneTrans samples/sec (fwd+bwd)', 'value': v, 'unit': 'samples/s', 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak',
@@ -164,7 +164,8 @@ def config_dict(args, wl, B):
     return {'workload': f"{args.workload}: OneTrans-{'S' if wl['model'] == 'small' else 'L'} fwd+BCE+bwd, batch {B}/GPU, "
                         f"{sum(wl['seq_lens']) + 2} S + {wl['L_ns']} NS tokens, schedule {wl['schedule']}",
             'global_batch': B * args.gpus, 'seq_tokens': sum(wl['seq_lens']) + 2, 'ns_tokens': wl['L_ns'],
-            'parallelism': f'dp{args.gpus}', 'dropout': 0.0, 'optimizer': 'none (metric is fwd+bwd)',
+            'parallelism': f'dp{args.gpus}', 'dropout': args.dropout,
+            'optimizer': 'clip_by_norm 90 + RMSprop inside the timed step' if args.optimizer else 'none (metric is fwd+bwd)',
             'l2_policy': 'activations per step (>20 GB) far exceed the 126 MB L2; no explicit flush'}
 
 
@@ -183,6 +184,8 @@ def main():
     ap.add_argument('--cpu-sample-batch', type=int, default=8)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-kernel-profile', action='store_true')
+    ap.add_argument('--dropout', type=float, default=0.1, help='training dropout rate (OT/config.py:50 default 0.1)')
+    ap.add_argument('--optimizer', action='store_true', help='also run the clip + RMSprop update inside the step (OT/train.py:133-138)')
     args = ap.parse_args()
 
     wl = workload(args.workload)
@@ -199,7 +202,7 @@ def main():
     import torch.distributed as dist
     import recommend_b200 as R
     from recommend_b200 import _lib, ops
-    from recommend_b200.train import FlatGradBuffer, bce_loss, train_step
+    from recommend_b200.train import FlatGradBuffer, ClipRMSprop, bce_loss, train_step
     from oracle import onetrans_oracle as O  # synthetic input generator only (and the cpu_baseline leg below)
 
     if not torch.cuda.is_available():
@@ -212,10 +215,11 @@ def main():
     cfg = R.get_model_config(wl['model'])
     cfg.num_ns_tokens = wl['L_ns']
     cfg.pyramid_schedule = wl['schedule']
-    cfg.dropout_rate = 0.0
+    cfg.dropout_rate = args.dropout
     torch.manual_seed(0)
     model = R.OneTransModel(cfg).to(dev)
     grads = FlatGradBuffer(model.parameters())
+    opt = ClipRMSprop.from_config(grads, cfg) if args.optimizer else None
 
     B = wl['B']
     ocfg = O.small_config(num_ns_tokens=wl['L_ns']) if wl['model'] == 'small' else O.default_config(num_ns_tokens=wl['L_ns'])
@@ -235,13 +239,13 @@ def main():
         torch.cuda.synchronize()
 
     def step_device():
-        return train_step(model, grads, d_ns, d_seq, d_lab, world)
+        return train_step(model, grads, d_ns, d_seq, d_lab, world, opt)
 
     def step_e2e():
         ns = {k: v.to(dev, non_blocking=True) for k, v in h_ns.items()}
         sq = {k: v.to(dev, non_blocking=True) for k, v in h_seq.items()}
         lb = {k: v.to(dev, non_blocking=True) for k, v in h_lab.items()}
-        loss = train_step(model, grads, ns, sq, lb, world)
+        loss = train_step(model, grads, ns, sq, lb, world, opt)
         return float(loss)     # device->host read of the step's result
 
     # ---- device-resident timing ----
@@ -340,7 +344,7 @@ def main():
                          'traffic': load_ncu_traffic(name)})
             line['roofline'] = roof
         if world == 1 and not args.no_cpu_baseline:
-            v, ms, cores = cpu_oracle_samples_per_sec(wl, args.cpu_sample_batch, 2, 1)
+            v, ms, cores = cpu_oracle_samples_per_sec(wl, args.cpu_sample_batch, 2, 1, args.dropout)
             line['cpu_baseline'] = {'value': v, 'unit': 'samples/s', 'cores': cores, 'kind': 'port',
                                     'sample': f'oracle (PyTorch CPU fp32 restatement of OT/model.py) fwd+BCE+bwd, 2 timed steps of '
                                               f'{args.cpu_sample_batch} samples of the same workload'}

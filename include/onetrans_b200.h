@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define OT_ABI_VERSION 2
+#define OT_ABI_VERSION 4
 
 int ot_version(void);
 const char* ot_last_error_string(void);
@@ -56,7 +56,9 @@ enum {
   OT_EPI_GELU = 2,        /* out = gelu_erf(v); if out2 != NULL, out2 = v (pre-activation)          */
   OT_EPI_RESIDUAL = 4,    /* + res[row, n]                                                          */
   OT_EPI_GELU_GRAD = 8,   /* v *= gelu_erf'(aux[row, n])                                            */
-  OT_EPI_ROW_SCALE = 16   /* v *= row_scale[row]   (applied first)                                  */
+  OT_EPI_ROW_SCALE = 16,  /* v *= row_scale[row]   (applied first)                                  */
+  OT_EPI_DROPOUT = 32     /* v = keep(row,n) ? v/(1-rate) : 0, after bias and before the residual add
+                             (Keras inverted dropout on the branch output, OT/model.py:193,198)        */
 };
 
 typedef struct ot_gemm_params {
@@ -89,6 +91,9 @@ typedef struct ot_gemm_params {
   float* out_hp;
   int64_t ld_hp;
   int64_t hp_row0;
+  /* OT_EPI_DROPOUT: counter-based mask hash(seed, row, n); rate in [0, 1). */
+  uint32_t drop_seed;
+  float drop_rate;
 } ot_gemm_params;
 
 int ot_mixed_gemm(const ot_gemm_params* p, void* stream);
@@ -231,6 +236,36 @@ typedef struct ot_colsum_params {
 } ot_colsum_params;
 
 int ot_colsum(const ot_colsum_params* p, void* stream);
+
+/* out[r, c] = keep(r, c) ? in[r, c] / (1 - rate) : 0 with the mask of OT_EPI_DROPOUT (same seed, same [rows, cols]
+ * index space): the backward of the dropout on a branch output.  bf16 in/out, cols % 8 == 0. */
+int ot_dropout_mask(const void* in, int64_t ld_in, void* out, int64_t ld_out, int64_t rows, int32_t cols,
+                    uint32_t seed, float rate, void* stream);
+
+/* ---- parameter update: per-tensor clip_by_norm + RMSprop (OT/train.py:131-138; optimizer OT/train.py:65-70,
+ * hyper-parameters OT/config.py:39-52).  Keras 2.12 RMSprop.update_step semantics:
+ *   g' = grad_scale * g * clip_norm / max(||grad_scale * g||_2, clip_norm)      (tf.clip_by_norm, per tensor; off if clip_norm <= 0)
+ *   rms = rho * rms + (1 - rho) * g'^2 ;  inc = lr * g' * rsqrt(rms + eps)
+ *   momentum > 0:  mom = momentum * mom + inc ; w -= mom        else  w -= inc
+ * grad / rms / mom are flat fp32 buffers of n_flat elements in which tensor s occupies
+ * [seg_off[s], seg_off[s] + seg_numel[s]); every seg_off and n_flat is a multiple of OT_OPT_CHUNK.  The fp32 masters
+ * stay in the caller's own allocations: param_ptrs[s] (16-byte aligned).  All tables are DEVICE arrays.
+ * sqnorm: device workspace of n_seg floats; on return it holds ||grad_scale * g_s||^2 (when clip_norm > 0). */
+#define OT_OPT_CHUNK 1024
+typedef struct ot_rmsprop_params {
+  float* const* param_ptrs;
+  const int64_t* seg_off;      /* [n_seg + 1] */
+  const int64_t* seg_numel;    /* [n_seg] */
+  int32_t n_seg;
+  int64_t n_flat;
+  float* grad;                 /* read; zeroed after use when zero_grad != 0 */
+  float* rms;
+  float* mom;                  /* may be NULL when momentum == 0 */
+  float* sqnorm;
+  float lr, rho, momentum, eps, clip_norm, grad_scale;
+  int32_t zero_grad;
+} ot_rmsprop_params;
+int ot_clip_rmsprop_step(const ot_rmsprop_params* p, void* stream);
 
 #ifdef __cplusplus
 }

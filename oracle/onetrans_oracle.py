@@ -408,6 +408,36 @@ def clip_by_norm(g: torch.Tensor, c: float) -> torch.Tensor:
     return g * (c / torch.maximum(n, torch.tensor(c, dtype=g.dtype)))
 
 
+def rmsprop_step(w: torch.Tensor, g: torch.Tensor, rms: torch.Tensor, mom: Optional[torch.Tensor], lr: float,
+                 rho: float = 0.9, momentum: float = 0.0, eps: float = 1e-7):
+    """One Keras-2.12 ``RMSprop.update_step`` (optimizer built at OT/train.py:65-70, applied at :138; the arithmetic
+    is TensorFlow's): ``rms = rho*rms + (1-rho)*g^2``; ``inc = lr*g*rsqrt(rms + eps)`` (non-centered:
+    epsilon inside the root); with momentum ``mom = momentum*mom + inc; w -= mom`` else ``w -= inc``.
+    Returns the new (w, rms, mom); inputs are not modified."""
+    rms = rho * rms + (1.0 - rho) * g * g
+    inc = lr * g * torch.rsqrt(rms + eps)
+    if momentum > 0.0:
+        mom = momentum * mom + inc
+        return w - mom, rms, mom
+    return w - inc, rms, mom
+
+
+def clip_rmsprop_update(params: Dict[str, torch.Tensor], grads: Dict[str, torch.Tensor], state: Dict[str, Dict[str, torch.Tensor]],
+                        lr: float = 0.005, rho: float = 0.9, momentum: float = 0.99999, eps: float = 1e-7,
+                        clip_norm: float = 90.0) -> None:
+    """OT/train.py:133-138 for every trainable tensor: ``tf.clip_by_norm`` per tensor, then ``apply_gradients``.
+    Defaults are OT/config.py:39-52 (dense_lr, momentum, gradient_clip_norm).  Updates ``params``/``state`` in place."""
+    for name, w in params.items():
+        g = grads[name]
+        if clip_norm > 0:
+            g = clip_by_norm(g, clip_norm)
+        st = state.setdefault(name, {'rms': torch.zeros_like(w), 'mom': torch.zeros_like(w)})
+        nw, st['rms'], nm = rmsprop_step(w, g, st['rms'], st['mom'], lr, rho, momentum, eps)
+        if nm is not None:
+            st['mom'] = nm
+        params[name] = nw
+
+
 # ---------------------------------------------------------------------------------------------------
 # synthetic inputs  (SURVEY.md §8d; OT/data_loader.py:301-329, :146-154)
 # ---------------------------------------------------------------------------------------------------

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, 'lib', 'libonetrans_sm100.so')
 
 i32, i64, vp, fp = C.c_int32, C.c_int64, C.c_void_p, C.c_void_p  # float* passed as raw address
 
-OT_EPI_BIAS, OT_EPI_GELU, OT_EPI_RESIDUAL, OT_EPI_GELU_GRAD, OT_EPI_ROW_SCALE = 1, 2, 4, 8, 16
+OT_EPI_BIAS, OT_EPI_GELU, OT_EPI_RESIDUAL, OT_EPI_GELU_GRAD, OT_EPI_ROW_SCALE, OT_EPI_DROPOUT = 1, 2, 4, 8, 16, 32
 
 
 class GemmSeg(C.Structure):
@@ -27,7 +27,7 @@ class GemmParams(C.Structure):
                 ('n_segs', i32), ('flags', i32), ('segs', GemmSeg * 3),
                 ('out', vp), ('ldo', i64), ('out2', vp), ('ldo2', i64), ('res', vp), ('ldr', i64),
                 ('aux', vp), ('ldaux', i64), ('bias', fp), ('bias_group_stride', i64), ('row_scale', fp),
-                ('block_n', i32), ('swizzle', i32), ('res_hp', fp), ('out_hp', fp), ('ld_hp', i64), ('hp_row0', i64)]
+                ('block_n', i32), ('swizzle', i32), ('res_hp', fp), ('out_hp', fp), ('ld_hp', i64), ('hp_row0', i64), ('drop_seed', C.c_uint32), ('drop_rate', C.c_float)]
 
 
 class WgradSeg(C.Structure):
@@ -71,10 +71,20 @@ class ColsumParams(C.Structure):
                 ('group_start', i32), ('group_stride', i32), ('out', fp), ('out_group_stride', i64), ('N', i32)]
 
 
+class RmspropParams(C.Structure):
+    _fields_ = [('param_ptrs', vp), ('seg_off', vp), ('seg_numel', vp), ('n_seg', i32), ('n_flat', i64),
+                ('grad', fp), ('rms', fp), ('mom', fp), ('sqnorm', fp),
+                ('lr', C.c_float), ('rho', C.c_float), ('momentum', C.c_float), ('eps', C.c_float),
+                ('clip_norm', C.c_float), ('grad_scale', C.c_float), ('zero_grad', i32)]
+
+
+OPT_CHUNK = 1024  # OT_OPT_CHUNK
+
 # every symbol include/onetrans_b200.h declares (tests check that the library exports all of them)
 EXPORTED_SYMBOLS = [
     'ot_version', 'ot_last_error_string', 'ot_num_sms', 'ot_mixed_gemm', 'ot_wgrad', 'ot_attn_fwd', 'ot_attn_bwd', 'ot_attn_ns_cached_fwd',
-    'ot_rmsnorm_fwd', 'ot_rmsnorm_bwd', 'ot_ns_tokenizer_fwd', 'ot_ns_tokenizer_bwd', 'ot_fill_rows', 'ot_colsum',
+    'ot_rmsnorm_fwd', 'ot_rmsnorm_bwd', 'ot_ns_tokenizer_fwd', 'ot_ns_tokenizer_bwd', 'ot_fill_rows', 'ot_colsum', 'ot_dropout_mask',
+    'ot_clip_rmsprop_step',
 ]
 
 _lib = None
@@ -104,12 +114,14 @@ def load() -> C.CDLL:
         for name, st in [('ot_mixed_gemm', GemmParams), ('ot_wgrad', WgradParams), ('ot_attn_fwd', AttnParams),
                          ('ot_attn_bwd', AttnParams), ('ot_attn_ns_cached_fwd', AttnCachedParams), ('ot_rmsnorm_fwd', RmsnormParams), ('ot_rmsnorm_bwd', RmsnormParams),
                          ('ot_ns_tokenizer_fwd', NsTokenizerParams), ('ot_ns_tokenizer_bwd', NsTokenizerParams),
-                         ('ot_colsum', ColsumParams)]:
+                         ('ot_colsum', ColsumParams), ('ot_clip_rmsprop_step', RmspropParams)]:
             fn = getattr(lib, name)
             fn.argtypes = [C.POINTER(st), C.c_void_p]
             fn.restype = C.c_int
         lib.ot_fill_rows.argtypes = [C.c_void_p, C.c_void_p, i64, i64, i64, i32, C.c_void_p]
         lib.ot_fill_rows.restype = C.c_int
+        lib.ot_dropout_mask.argtypes = [C.c_void_p, i64, C.c_void_p, i64, i64, i32, C.c_uint32, C.c_float, C.c_void_p]
+        lib.ot_dropout_mask.restype = C.c_int
         _lib = lib
     return _lib
 

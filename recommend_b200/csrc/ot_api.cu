@@ -49,6 +49,9 @@ int ns_tokenizer_fwd_impl(const ot_ns_tokenizer_params* p, cudaStream_t st);
 int ns_tokenizer_bwd_impl(const ot_ns_tokenizer_params* p, cudaStream_t st);
 int fill_rows_impl(const float* vec, void* out, long long ldo, long long row0, long long n_rows, int d, cudaStream_t st);
 int colsum_impl(const ot_colsum_params* p, cudaStream_t st);
+int dropout_mask_impl(const void* in, long long ld_in, void* out, long long ld_out, long long rows, int cols, uint32_t seed,
+                      float rate, cudaStream_t st);
+int clip_rmsprop_impl(const ot_rmsprop_params* p, cudaStream_t st);
 
 }  // namespace ot
 
@@ -83,5 +86,10 @@ int ot_fill_rows(const float* vec, void* out, int64_t ldo, int64_t row0, int64_t
   return ot::fill_rows_impl(vec, out, ldo, row0, n_rows, d, static_cast<cudaStream_t>(stream));
 }
 int ot_colsum(const ot_colsum_params* p, void* stream) { return ot::colsum_impl(p, static_cast<cudaStream_t>(stream)); }
+int ot_dropout_mask(const void* in, int64_t ld_in, void* out, int64_t ld_out, int64_t rows, int32_t cols, uint32_t seed, float rate,
+                    void* stream) {
+  return ot::dropout_mask_impl(in, ld_in, out, ld_out, rows, cols, seed, rate, static_cast<cudaStream_t>(stream));
+}
+int ot_clip_rmsprop_step(const ot_rmsprop_params* p, void* stream) { return ot::clip_rmsprop_impl(p, static_cast<cudaStream_t>(stream)); }
 
 }  // extern "C"

@@ -262,6 +262,17 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// Counter-based dropout mask (Keras inverted dropout, OT/model.py:184,193,198): one 32-bit hash decides the two
+// elements (row, col) and (row, col+1), col even; an element is kept iff its 16-bit lane >= thr16 = round(rate*65536).
+// The forward epilogue and the backward mask kernel evaluate the same function, so no mask is ever stored.
+__device__ __forceinline__ uint32_t ot_hash32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+  return x;
+}
+__device__ __forceinline__ uint32_t dropout_bits(uint32_t seed, uint32_t row, uint32_t col_even, uint32_t n_cols) {
+  return ot_hash32(((row * n_cols + col_even) >> 1) * 2654435761u + seed);
+}
+
 // Byte offset of 16-byte chunk `chunk` of row `row` inside a SWB-byte-wide swizzled slab.
 template <int SWB>
 __device__ __forceinline__ uint32_t swz_off(uint32_t row, uint32_t chunk) {

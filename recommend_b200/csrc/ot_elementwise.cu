@@ -277,6 +277,29 @@ colsum_kernel(const __nv_bfloat16* __restrict__ in, long long ld, long long row_
 }
 
 // ---------------------------------------------------------------------------------------------
+// dropout backward:  out = keep(row, col) ? in / (1 - rate) : 0   (mask recomputed from the seed)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+dropout_mask_kernel(const __nv_bfloat16* __restrict__ in, long long ld_in, __nv_bfloat16* __restrict__ out, long long ld_out,
+                    long long rows, int cols, uint32_t seed, uint32_t thr16, float scale) {
+  const int nch = cols >> 3;
+  const long long total = rows * nch;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % nch);
+    const long long r = idx / nch;
+    float v[8];
+    unpack8(*reinterpret_cast<const uint4*>(in + r * ld_in + c * 8), v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t hb = dropout_bits(seed, static_cast<uint32_t>(r), static_cast<uint32_t>(c * 8 + 2 * j), static_cast<uint32_t>(cols));
+      v[2 * j] = ((hb & 0xFFFFu) >= thr16) ? v[2 * j] * scale : 0.0f;
+      v[2 * j + 1] = ((hb >> 16) >= thr16) ? v[2 * j + 1] * scale : 0.0f;
+    }
+    *reinterpret_cast<uint4*>(out + r * ld_out + c * 8) = pack8(v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // host wrappers
 // ---------------------------------------------------------------------------------------------
 static int grid_for_rows(long long rows, int warps_per_block) {
@@ -355,6 +378,20 @@ int fill_rows_impl(const float* vec, void* out, long long ldo, long long row0, l
   long long blocks = (n_rows * (d / 8) + 255) / 256;
   if (blocks > (long long)num_sms() * 32) blocks = (long long)num_sms() * 32;
   fill_rows_kernel<<<(int)blocks, 256, 0, st>>>(vec, (__nv_bfloat16*)out, ldo, row0, n_rows, d);
+  OT_CUDA_CHECK(cudaGetLastError());
+  return OT_OK;
+}
+
+int dropout_mask_impl(const void* in, long long ld_in, void* out, long long ld_out, long long rows, int cols, uint32_t seed,
+                      float rate, cudaStream_t st) {
+  if (!in || !out) OT_FAIL(OT_ERR_INVALID_ARG, "ot_dropout_mask: null pointer");
+  if (cols <= 0 || cols % 8 || ld_in % 8 || ld_out % 8) OT_FAIL(OT_ERR_UNSUPPORTED_SHAPE, "ot_dropout_mask: cols=%d", cols);
+  if (!(rate >= 0.0f && rate < 1.0f)) OT_FAIL(OT_ERR_INVALID_ARG, "ot_dropout_mask: rate=%f", (double)rate);
+  if (rows <= 0) return OT_OK;
+  long long blocks = (rows * (cols / 8) + 255) / 256;
+  if (blocks > (long long)num_sms() * 32) blocks = (long long)num_sms() * 32;
+  dropout_mask_kernel<<<(int)blocks, 256, 0, st>>>((const __nv_bfloat16*)in, ld_in, (__nv_bfloat16*)out, ld_out, rows, cols, seed,
+                                                   (uint32_t)(rate * 65536.0f + 0.5f), 1.0f / (1.0f - rate));
   OT_CUDA_CHECK(cudaGetLastError());
   return OT_OK;
 }

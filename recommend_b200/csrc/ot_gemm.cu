@@ -7,12 +7,13 @@
 // which weight set" (OT/model.py:67-74) arrives as data (ot_gemm_seg), so the shared S-token run and
 // the per-token NS runs are tiles of ONE persistent launch.
 //
-// Kernel structure (one CTA per SM, persistent over a static tile list; 10 warps):
+// Kernel structure (one CTA per SM, persistent over a static tile list; 20 warps, registers re-balanced with
+// setmaxnreg: 40 per control thread, 112 per epilogue thread):
 //   warp 0   : TMA producer   — A tile [128 x BK] and W tile [BN x BK] into a STAGES-deep smem ring
 //   warp 1   : MMA issuer     — tcgen05.mma (M=128, N=BN, K=16) into one of two TMEM accumulators
-//   warps 2-9: epilogue       — tcgen05.ld -> fp32 math (row scale, bias, GELU, GELU', residual)
+//   warps 4-19: epilogue      — tcgen05.ld -> fp32 math (row scale, bias, GELU, GELU', residual)
 //                               -> bf16 -> swizzled smem staging -> coalesced 16-byte global stores
-//                               (two sets of four warps split the 64-column chunks of a tile)
+//                               (four sets of four warps split the 64-column chunks of a tile)
 // The two TMEM accumulators (2*BN <= 512 columns) let the epilogue of tile i overlap the MMAs of
 // tile i+1.  Roofline: at d=256 every GEMM of the block is HBM-bound, so the
 // epilogue reads/writes each activation byte exactly once and in full 128-byte lines.
@@ -23,11 +24,14 @@
 namespace ot {
 
 static constexpr int BM = 128;
-static constexpr int GEMM_THREADS = 320;     // producer warp + MMA warp + 8 epilogue warps
-static constexpr int EPI_THREADS = 256;
+static constexpr int EPI_SETS = 4;
 static constexpr int EPI_SET_THREADS = 128;
-static constexpr int EPI_BAR_ID = 1;         // named barriers 1, 2: one per epilogue set
-static constexpr int EPI_BAR_ALL = 3;        // all epilogue warps (bias tile reload)
+static constexpr int EPI_THREADS = EPI_SETS * EPI_SET_THREADS;
+static constexpr int CTRL_THREADS = 128;      // one control warpgroup: warp 0 TMA producer, warp 1 MMA issuer, warps 2-3 idle
+static constexpr int GEMM_THREADS = CTRL_THREADS + EPI_THREADS;   // + 16 epilogue warps (warps 4..19)
+static constexpr int EPI_REGS = 112, CTRL_REGS = 32;   // setmaxnreg: the control warpgroup releases 4*32*(96-32) registers into the CTA pool, exactly what the four epilogue warpgroups take (4*128*(112-96)); asking for more than was released spins forever
+static constexpr int EPI_BAR_ID = 1;         // named barriers 1..4: one per epilogue set
+static constexpr int EPI_BAR_ALL = 5;        // all epilogue warps (bias tile reload)
 static constexpr int CHUNK = 64;             // epilogue column chunk (128 bytes of bf16 per row)
 static constexpr int CH_BYTES = 128 * 64 * 2;   // one staged chunk: 128 rows x 128 bytes
 
@@ -50,6 +54,7 @@ struct GemmKParams {
   const float* bias; long long bias_group_stride;
   const float* row_scale;
   const float* res_hp; float* out_hp; long long ld_hp; long long hp_row0;
+  uint32_t drop_seed, drop_thr16; float drop_scale;
 };
 
 struct TileInfo {
@@ -84,7 +89,7 @@ struct GemmCfg {
   static constexpr int A_BYTES = BM * SWB;
   static constexpr int B_BYTES = BN * SWB;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGING_BYTES = 4 * BM * CHUNK * 2;  // two epilogue sets x two 128x64 bf16 buffers
+  static constexpr int STAGING_BYTES = EPI_SETS * BM * CHUNK * 2;  // one 128x64 bf16 buffer per epilogue set
   static constexpr int BIAS_BYTES = BN * 4;
   static constexpr int BUDGET = 227 * 1024 - STAGING_BYTES - BIAS_BYTES - 256;
   static constexpr int STAGES_RAW = BUDGET / STAGE_BYTES;
@@ -128,7 +133,7 @@ ot_mixed_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 8);
+      mbar_init(&tempty_bar[i], 4 * EPI_SETS);
     }
     fence_mbar_init();
   }
@@ -141,6 +146,7 @@ ot_mixed_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(CTRL_REGS));
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect_one()) {
@@ -193,25 +199,27 @@ ot_mixed_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         umma_commit(&tfull_bar[acc]);
       }
     }
-  } else {
-    // ===================== epilogue (warps 2..9: two sets of four) =====================
-    // Set s handles the 64-column chunks c = s, s+2, ... of every tile with its own pair of staging buffers
-    // and its own named barrier; inside a set, warp w may read TMEM lanes 32*(w%4)..+31 (one row per thread).
-    const int set = (warp - 2) >> 2;
-    const int et = threadIdx.x - 64 - set * EPI_SET_THREADS;   // 0..127 inside the set
+  } else if (warp >= 4) {
+    // ===================== epilogue (warps 4..19: four sets of four) =====================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(EPI_REGS));
+    // Set s handles the 64-column chunks c = s, s+4, ... of every tile with its own staging buffer and named
+    // barrier; inside a set, warp w may read TMEM lanes 32*(w%4)..+31 (one accumulator row per thread).  Sixteen
+    // warps (four per scheduler) are what it takes to hide the TMEM / MUFU / smem latencies of the GELU epilogues:
+    // with eight the FFN GEMMs ran at ~35 % of the HBM roofline, issue slots 60 % idle (profiles/README.md).
+    const int set = (warp - 4) >> 2;
+    const int et = threadIdx.x - CTRL_THREADS - set * EPI_SET_THREADS;   // 0..127 inside the set
     const int lgrp = warp & 3;
     const int r_own = lgrp * 32 + lane;
     const int ld_row = et >> 3;                // cooperative copy: 16 rows per pass, 8 x 16 B per row
     const int ld_ch = et & 7;
     const uint32_t bar_id = EPI_BAR_ID + set;
-    uint8_t* stg = staging + set * (2 * CH_BYTES);
+    uint8_t* buf = staging + set * CH_BYTES;
     const bool f_bias = p.flags & OT_EPI_BIAS, f_gelu = p.flags & OT_EPI_GELU, f_res = p.flags & OT_EPI_RESIDUAL;
-    const bool f_ggrad = p.flags & OT_EPI_GELU_GRAD, f_rs = p.flags & OT_EPI_ROW_SCALE;
+    const bool f_ggrad = p.flags & OT_EPI_GELU_GRAD, f_rs = p.flags & OT_EPI_ROW_SCALE, f_drop = p.flags & OT_EPI_DROPOUT;
     const bool has_in = f_res || f_ggrad;
     const bool dual = f_gelu && (p.out2 != nullptr);
     const __nv_bfloat16* in_ptr = f_res ? p.res : p.aux;
     const long long in_ld = f_res ? p.ldr : p.ldaux;
-    int sbuf = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int mblk = tile / p.n_nblks;
@@ -223,7 +231,7 @@ ot_mixed_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 
       if (f_bias) {
         named_bar_sync(EPI_BAR_ALL, EPI_THREADS);  // previous tile's readers of bias_s are done
-        for (int j = threadIdx.x - 64; j < BN; j += EPI_THREADS)
+        for (int j = threadIdx.x - CTRL_THREADS; j < BN; j += EPI_THREADS)
           bias_s[j] = p.bias[(long long)t.group * p.bias_group_stride + n0 + j];
         named_bar_sync(EPI_BAR_ALL, EPI_THREADS);
       }
@@ -233,131 +241,124 @@ ot_mixed_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       const bool hp_tile = f_res && (p.res_hp != nullptr) && (t.row0 >= p.hp_row0);
       const bool tile_in = has_in && !hp_tile;
 
-      // residual / GELU' input of this set's first chunk: requested before the accumulator wait so that the global
-      // latency hides under the MMAs; the following chunk is requested while the current one is processed
-      uint4 pre_in[BM / 16];
-      auto fetch_in = [&](int c) {
-        const int col0 = n0 + c * CHUNK;
-#pragma unroll
-        for (int i = 0; i < BM / 16; ++i) {
-          const int r = i * 16 + ld_row;
-          pre_in[i] = make_uint4(0, 0, 0, 0);
-          if (r < t.valid)
-            pre_in[i] = *reinterpret_cast<const uint4*>(in_ptr + (long long)(t.row0 + r) * in_ld + col0 + ld_ch * 8);
-        }
-      };
-      if (tile_in && set < BN / CHUNK) fetch_in(set);
-
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(lgrp * 32) << 16) + acc * BN;
 
 #pragma unroll 1
-      for (int c = set; c < BN / CHUNK; c += 2) {
+      for (int c = set; c < BN / CHUNK; c += EPI_SETS) {
         const int col0 = n0 + c * CHUNK;
-        uint8_t* buf = stg + sbuf * CH_BYTES;
-        uint8_t* buf2 = stg + (sbuf ^ 1) * CH_BYTES;
-        if (tile_in) {   // residual / GELU' input chunk (prefetched registers) -> staging
+        // staging-buffer helpers (the buffer is single: every use starts behind a barrier)
+        auto store_rows = [&](__nv_bfloat16* dst, long long ld) {   // staging -> global, full 128-byte rows
 #pragma unroll
           for (int i = 0; i < BM / 16; ++i) {
             const int r = i * 16 + ld_row;
-            *reinterpret_cast<uint4*>(buf + swz_off<128>(r, ld_ch)) = pre_in[i];
+            if (r < t.valid)
+              *reinterpret_cast<uint4*>(dst + (long long)(t.row0 + r) * ld + col0 + ld_ch * 8) =
+                  *reinterpret_cast<const uint4*>(buf + swz_off<128>(r, ld_ch));
           }
-          if (c + 2 < BN / CHUNK) fetch_in(c + 2);
+        };
+        named_bar_sync(bar_id, EPI_SET_THREADS);   // the previous chunk's stores out of `buf` are done
+        if (tile_in) {   // residual / GELU' input chunk: coalesced global -> staging
+#pragma unroll
+          for (int i = 0; i < BM / 16; ++i) {
+            const int r = i * 16 + ld_row;
+            uint4 q = make_uint4(0, 0, 0, 0);
+            if (r < t.valid)
+              q = *reinterpret_cast<const uint4*>(in_ptr + (long long)(t.row0 + r) * in_ld + col0 + ld_ch * 8);
+            *reinterpret_cast<uint4*>(buf + swz_off<128>(r, ld_ch)) = q;
+          }
           named_bar_sync(bar_id, EPI_SET_THREADS);
         }
+        // dual mode (FFN-1 forward keeps the pre-activation for the backward pass): pass 0 stores the pre-activation,
+        // pass 1 re-reads the accumulator (TMEM reads are cheap, registers are not) and stores GELU of it
+        const int n_pass = dual ? 2 : 1;
+#pragma unroll 1
+        for (int pass = 0; pass < n_pass; ++pass) {
+          if (pass == 1) named_bar_sync(bar_id, EPI_SET_THREADS);   // pre-activation rows have left `buf`
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          uint32_t v[32];
-          tmem_ld_x32(t_row + c * CHUNK + half * 32, v);
-          tmem_ld_wait();
-          float f[32];
+          for (int half = 0; half < 2; ++half) {
+            uint32_t v[32];
+            tmem_ld_x32(t_row + c * CHUNK + half * 32, v);
+            tmem_ld_wait();
+            float f[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-          if (f_rs) {
+            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+            if (f_rs) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] *= rs;
-          }
-          if (f_bias) {
-            const float4* b4 = reinterpret_cast<const float4*>(bias_s + c * CHUNK + half * 32);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 bb = b4[j];
-              f[4 * j + 0] += bb.x; f[4 * j + 1] += bb.y; f[4 * j + 2] += bb.z; f[4 * j + 3] += bb.w;
+              for (int j = 0; j < 32; ++j) f[j] *= rs;
             }
-          }
-          if (f_gelu) {
-            if (dual) {   // keep the pre-activation for the backward pass
-#pragma unroll
-              for (int ch = 0; ch < 4; ++ch) {
-                uint4 q;
-                q.x = pack_bf16x2(f[ch * 8 + 0], f[ch * 8 + 1]);
-                q.y = pack_bf16x2(f[ch * 8 + 2], f[ch * 8 + 3]);
-                q.z = pack_bf16x2(f[ch * 8 + 4], f[ch * 8 + 5]);
-                q.w = pack_bf16x2(f[ch * 8 + 6], f[ch * 8 + 7]);
-                *reinterpret_cast<uint4*>(buf2 + swz_off<128>(r_own, half * 4 + ch)) = q;
-              }
-            }
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
-          }
-          if (hp_tile) {   // fp32 residual in, fp32 result out: one 128-byte line per thread and half-chunk
-            if (r_own < t.valid) {
-              const long long hr = (long long)(t.row0 + r_own) - p.hp_row0;
-              const float4* rp = reinterpret_cast<const float4*>(p.res_hp + hr * p.ld_hp + col0 + half * 32);
-              float4* op = reinterpret_cast<float4*>(p.out_hp + hr * p.ld_hp + col0 + half * 32);
+            if (f_bias) {
+              const float4* b4 = reinterpret_cast<const float4*>(bias_s + c * CHUNK + half * 32);
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
-                const float4 rr = rp[j];
-                f[4 * j + 0] += rr.x; f[4 * j + 1] += rr.y; f[4 * j + 2] += rr.z; f[4 * j + 3] += rr.w;
-                op[j] = make_float4(f[4 * j + 0], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                const float4 bb = b4[j];
+                f[4 * j + 0] += bb.x; f[4 * j + 1] += bb.y; f[4 * j + 2] += bb.z; f[4 * j + 3] += bb.w;
               }
             }
-          }
-          if (tile_in) {
+            if (f_drop) {   // inverted dropout on the branch output, before the residual add
+              const uint32_t grow = static_cast<uint32_t>(t.row0 + r_own);
 #pragma unroll
-            for (int ch = 0; ch < 4; ++ch) {
-              const uint4 q = *reinterpret_cast<const uint4*>(buf + swz_off<128>(r_own, half * 4 + ch));
-              const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+              for (int j = 0; j < 16; ++j) {
+                const uint32_t hb = dropout_bits(p.drop_seed, grow, static_cast<uint32_t>(col0 + half * 32 + 2 * j), static_cast<uint32_t>(p.N));
+                f[2 * j] = ((hb & 0xFFFFu) >= p.drop_thr16) ? f[2 * j] * p.drop_scale : 0.0f;
+                f[2 * j + 1] = ((hb >> 16) >= p.drop_thr16) ? f[2 * j + 1] * p.drop_scale : 0.0f;
+              }
+            }
+            if (hp_tile) {   // fp32 residual in, fp32 result out: one 128-byte line per thread and half-chunk
+              if (r_own < t.valid) {
+                const long long hr = (long long)(t.row0 + r_own) - p.hp_row0;
+                const float4* rp = reinterpret_cast<const float4*>(p.res_hp + hr * p.ld_hp + col0 + half * 32);
+                float4* op = reinterpret_cast<float4*>(p.out_hp + hr * p.ld_hp + col0 + half * 32);
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                if (f_ggrad) {
-                  f[ch * 8 + 2 * e] *= gelu_erf_grad(bf16lo(w[e]));
-                  f[ch * 8 + 2 * e + 1] *= gelu_erf_grad(bf16hi(w[e]));
-                } else {
-                  f[ch * 8 + 2 * e] += bf16lo(w[e]);
-                  f[ch * 8 + 2 * e + 1] += bf16hi(w[e]);
+                for (int j = 0; j < 8; ++j) {
+                  const float4 rr = rp[j];
+                  f[4 * j + 0] += rr.x; f[4 * j + 1] += rr.y; f[4 * j + 2] += rr.z; f[4 * j + 3] += rr.w;
+                  op[j] = make_float4(f[4 * j + 0], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
                 }
               }
             }
-          }
-          // each thread (over)writes only its own row of `buf`
+            if (tile_in) {
+              // the mode test stays outside the element loops: a branch per element doubled the instruction count
+              uint32_t w[16];
 #pragma unroll
-          for (int ch = 0; ch < 4; ++ch) {
-            uint4 q;
-            q.x = pack_bf16x2(f[ch * 8 + 0], f[ch * 8 + 1]);
-            q.y = pack_bf16x2(f[ch * 8 + 2], f[ch * 8 + 3]);
-            q.z = pack_bf16x2(f[ch * 8 + 4], f[ch * 8 + 5]);
-            q.w = pack_bf16x2(f[ch * 8 + 6], f[ch * 8 + 7]);
-            *reinterpret_cast<uint4*>(buf + swz_off<128>(r_own, half * 4 + ch)) = q;
-          }
-        }
-        named_bar_sync(bar_id, EPI_SET_THREADS);
-        // the chunk leaves in full 128-byte rows
+              for (int ch = 0; ch < 4; ++ch) {
+                const uint4 q = *reinterpret_cast<const uint4*>(buf + swz_off<128>(r_own, half * 4 + ch));
+                w[ch * 4 + 0] = q.x; w[ch * 4 + 1] = q.y; w[ch * 4 + 2] = q.z; w[ch * 4 + 3] = q.w;
+              }
+              if (f_ggrad) {
 #pragma unroll
-        for (int i = 0; i < BM / 16; ++i) {
-          const int r = i * 16 + ld_row;
-          if (r < t.valid) {
-            const uint4 q = *reinterpret_cast<const uint4*>(buf + swz_off<128>(r, ld_ch));
-            *reinterpret_cast<uint4*>(p.out + (long long)(t.row0 + r) * p.ldo + col0 + ld_ch * 8) = q;
-            if (dual) {
-              const uint4 q2 = *reinterpret_cast<const uint4*>(buf2 + swz_off<128>(r, ld_ch));
-              *reinterpret_cast<uint4*>(p.out2 + (long long)(t.row0 + r) * p.ldo2 + col0 + ld_ch * 8) = q2;
+                for (int e = 0; e < 16; ++e) {
+                  f[2 * e] *= gelu_erf_grad(bf16lo(w[e]));
+                  f[2 * e + 1] *= gelu_erf_grad(bf16hi(w[e]));
+                }
+              } else {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                  f[2 * e] += bf16lo(w[e]);
+                  f[2 * e + 1] += bf16hi(w[e]);
+                }
+              }
+            }
+            if (f_gelu && (pass == 1 || !dual)) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+            }
+            // each thread (over)writes only its own row of `buf`
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) {
+              uint4 q;
+              q.x = pack_bf16x2(f[ch * 8 + 0], f[ch * 8 + 1]);
+              q.y = pack_bf16x2(f[ch * 8 + 2], f[ch * 8 + 3]);
+              q.z = pack_bf16x2(f[ch * 8 + 4], f[ch * 8 + 5]);
+              q.w = pack_bf16x2(f[ch * 8 + 6], f[ch * 8 + 7]);
+              *reinterpret_cast<uint4*>(buf + swz_off<128>(r_own, half * 4 + ch)) = q;
             }
           }
+          named_bar_sync(bar_id, EPI_SET_THREADS);
+          if (dual && pass == 0) store_rows(p.out2, p.ldo2);   // pre-activation
+          else store_rows(p.out, p.ldo);
         }
-        if (dual) named_bar_sync(bar_id, EPI_SET_THREADS);  // both buffers were in use
-        else sbuf ^= 1;
       }
       // all TMEM reads of this accumulator are complete -> hand it back to the MMA warp
       tc_fence_before();
@@ -433,6 +434,10 @@ int mixed_gemm_impl(const ot_gemm_params* p, cudaStream_t st) {
   kp.res = (const __nv_bfloat16*)p->res; kp.ldr = p->ldr; kp.aux = (const __nv_bfloat16*)p->aux; kp.ldaux = p->ldaux;
   kp.bias = p->bias; kp.bias_group_stride = p->bias_group_stride; kp.row_scale = p->row_scale;
   kp.res_hp = p->res_hp; kp.out_hp = p->out_hp; kp.ld_hp = p->ld_hp; kp.hp_row0 = p->hp_row0;
+  if (p->flags & OT_EPI_DROPOUT) {
+    if (!(p->drop_rate >= 0.0f && p->drop_rate < 1.0f)) OT_FAIL(OT_ERR_INVALID_ARG, "ot_mixed_gemm: drop_rate=%f", (double)p->drop_rate);
+    kp.drop_seed = p->drop_seed; kp.drop_thr16 = (uint32_t)(p->drop_rate * 65536.0f + 0.5f); kp.drop_scale = 1.0f / (1.0f - p->drop_rate);
+  }
   if (p->res_hp || p->out_hp) {
     if (!(p->flags & OT_EPI_RESIDUAL) || !p->res_hp || !p->out_hp || (p->ld_hp % 4))
       OT_FAIL(OT_ERR_INVALID_ARG, "ot_mixed_gemm: res_hp/out_hp need OT_EPI_RESIDUAL, both pointers and ld_hp %% 4 == 0");

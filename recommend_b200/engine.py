@@ -74,7 +74,8 @@ def split_segments(segs: Sequence[ops.Seg], row: int) -> List[ops.Seg]:
 
 
 def mha_forward(xn: torch.Tensor, res: Optional[torch.Tensor], w: BlockWeights, B: int, cur: int, keep: int, H: int,
-                L_ns: int, alignment: str, kv_prefix: Optional[torch.Tensor] = None, res_hp: Optional[torch.Tensor] = None):
+                L_ns: int, alignment: str, kv_prefix: Optional[torch.Tensor] = None, res_hp: Optional[torch.Tensor] = None,
+                drop: Optional[Tuple[int, float]] = None):
     """MixedMHA.call (OT/model.py:76-122) on normalised ``xn [cur*B, d]``; queries for the last ``keep``
     positions.  ``res`` (``[keep*B, d]``) is added to the Wo output (the block's residual, OT/model.py:193).
     ``kv_prefix [Lc*B, 2d]``: cached K|V rows placed in front of the new ones (OT/model.py:95-98).
@@ -104,9 +105,10 @@ def mha_forward(xn: torch.Tensor, res: Optional[torch.Tensor], w: BlockWeights, 
         hp0 = rows_t - n_hp
         z_hp = torch.empty(n_hp, d, dtype=torch.float32, device=dev)
         segs_o = split_segments([(0, 1, rows_t, 0, 0)], hp0)
-        ops.mixed_gemm(o, w.Wo_f, segs_o, z, flags=OT_EPI_RESIDUAL, res=res, res_hp=res_hp[res_hp.shape[0] - n_hp:], out_hp=z_hp, hp_row0=hp0)
+        ops.mixed_gemm(o, w.Wo_f, segs_o, z, flags=OT_EPI_RESIDUAL, res=res, res_hp=res_hp[res_hp.shape[0] - n_hp:], out_hp=z_hp, hp_row0=hp0,
+                       dropout=drop)
     else:
-        ops.mixed_gemm(o, w.Wo_f, [(0, 1, rows_t, 0, 0)], z, flags=OT_EPI_RESIDUAL if res is not None else 0, res=res)
+        ops.mixed_gemm(o, w.Wo_f, [(0, 1, rows_t, 0, 0)], z, flags=OT_EPI_RESIDUAL if res is not None else 0, res=res, dropout=drop)
     return z, (q, kv, o, lse, segs_all, segs_tail), z_hp
 
 
@@ -139,7 +141,8 @@ def mha_backward(dz: torch.Tensor, xn: torch.Tensor, saved, w: BlockWeights, Wqk
 
 
 def ffn_forward(zn: torch.Tensor, res: Optional[torch.Tensor], w: BlockWeights, b1: torch.Tensor, b2: torch.Tensor,
-                segs: Sequence[ops.Seg], save: bool, res_hp: Optional[torch.Tensor] = None):
+                segs: Sequence[ops.Seg], save: bool, res_hp: Optional[torch.Tensor] = None,
+                drop: Optional[Tuple[int, float]] = None):
     """MixedFFN.call (OT/model.py:149-163): ``gelu(zn W1 + b1) W2 + b2`` (+ res)."""
     rows_t, d = zn.shape
     F = w.W1_f.shape[1]
@@ -153,9 +156,10 @@ def ffn_forward(zn: torch.Tensor, res: Optional[torch.Tensor], w: BlockWeights, 
     if res_hp is not None and res is not None:
         hp0 = rows_t - res_hp.shape[0]          # the fp32 stream covers the last rows (the NS tokens)
         y_hp = torch.empty(res_hp.shape[0], d, dtype=torch.float32, device=dev)
-        ops.mixed_gemm(h, w.W2_f, split_segments(segs, hp0), y, flags=flags, bias=b2, res=res, res_hp=res_hp, out_hp=y_hp, hp_row0=hp0)
+        ops.mixed_gemm(h, w.W2_f, split_segments(segs, hp0), y, flags=flags, bias=b2, res=res, res_hp=res_hp, out_hp=y_hp, hp_row0=hp0,
+                       dropout=drop)
     else:
-        ops.mixed_gemm(h, w.W2_f, segs, y, flags=flags, bias=b2, res=res)
+        ops.mixed_gemm(h, w.W2_f, segs, y, flags=flags, bias=b2, res=res, dropout=drop)
     return y, (pre, h), y_hp
 
 
@@ -179,10 +183,12 @@ def ffn_backward(dy: torch.Tensor, zn: torch.Tensor, saved, w: BlockWeights, seg
 
 def block_forward(x: torch.Tensor, P: Dict[str, torch.Tensor], w: BlockWeights, B: int, cur: int, keep: int, H: int,
                   L_ns: int, alignment: str, eps: float, save: bool, kv_prefix: Optional[torch.Tensor] = None,
-                  x_hp: Optional[torch.Tensor] = None):
+                  x_hp: Optional[torch.Tensor] = None, drop: Optional[Tuple[int, int, float]] = None):
     """OneTransBlock.call (OT/model.py:186-200) + tail keep (:371).  P: norm1, norm2, b1, b2 (fp32).
     ``x_hp``: optional fp32 copy of the NS-token rows of ``x`` (its last ``x_hp.shape[0]`` rows) — the
-    high-precision residual stream of DESIGN.md §5; returns the matching ``y_hp`` as 4th value."""
+    high-precision residual stream of DESIGN.md §5; returns the matching ``y_hp`` as 4th value.
+    ``drop = (seed_attention, seed_ffn, rate)``: Keras inverted dropout on the two branch outputs (OT/model.py:193,198),
+    fused into the Wo / FFN-2 epilogues; the masks are recomputed from the seeds in the backward pass."""
     rows, d = x.shape
     assert rows == cur * B
     dev = x.device
@@ -192,14 +198,16 @@ def block_forward(x: torch.Tensor, P: Dict[str, torch.Tensor], w: BlockWeights, 
     if x_hp is not None and x_hp.shape[0] == 0:
         x_hp = None
     ops.rmsnorm_fwd(x, P['norm1'], xn, r1, eps, x_hp, rows - (x_hp.shape[0] if x_hp is not None else 0))   # OT/model.py:191
-    z, mha_saved, z_hp = mha_forward(xn, x[off:], w, B, cur, keep, H, L_ns, alignment, kv_prefix, x_hp)   # :192-193
+    d_att = (drop[0], drop[2]) if drop is not None else None
+    d_ffn = (drop[1], drop[2]) if drop is not None else None
+    z, mha_saved, z_hp = mha_forward(xn, x[off:], w, B, cur, keep, H, L_ns, alignment, kv_prefix, x_hp, d_att)   # :192-193
     zn = torch.empty(rows_t, d, dtype=bf16, device=dev)
     r2 = torch.empty(rows_t, dtype=torch.float32, device=dev)
     ops.rmsnorm_fwd(z, P['norm2'], zn, r2, eps, z_hp, rows_t - (z_hp.shape[0] if z_hp is not None else 0))   # :196
     segs_tail = mha_saved[5]
-    y, ffn_saved, y_hp = ffn_forward(zn, z, w, P['b1'], P['b2'], segs_tail, save, z_hp)     # :197-198
+    y, ffn_saved, y_hp = ffn_forward(zn, z, w, P['b1'], P['b2'], segs_tail, save, z_hp, d_ffn)     # :197-198
     kv = mha_saved[1]
-    saved = (x, xn, r1, mha_saved, z, zn, r2, ffn_saved) if save else None
+    saved = (x, xn, r1, mha_saved, z, zn, r2, ffn_saved, drop) if save else None
     return y, kv, saved, y_hp
 
 
@@ -207,20 +215,22 @@ def block_backward(dy: torch.Tensor, saved, Pm: Dict[str, torch.Tensor], w: Bloc
                    H: int) -> torch.Tensor:
     """Backward of block_forward.  Pm maps names to the fp32 master parameters (their .grad buffers
     receive the gradients).  Returns dx ``[cur*B, d]``."""
-    x, xn, r1, mha_saved, z, zn, r2, ffn_saved = saved
+    x, xn, r1, mha_saved, z, zn, r2, ffn_saved, drop = saved
     rows, d = x.shape
     dev = x.device
     rows_t, off = keep * B, (cur - keep) * B
     segs_tail = mha_saved[5]
     if not dy.is_contiguous():
         dy = dy.contiguous()
-    # y = z + FFN(norm2(z))
-    dzn = ffn_backward(dy, zn, ffn_saved, w, segs_tail, _grad_buf(Pm['W1']), _grad_buf(Pm['b1']), _grad_buf(Pm['W2']),
+    # y = z + drop(FFN(norm2(z)))
+    dy_f = ops.dropout_mask(dy, drop[1], drop[2]) if drop is not None else dy
+    dzn = ffn_backward(dy_f, zn, ffn_saved, w, segs_tail, _grad_buf(Pm['W1']), _grad_buf(Pm['b1']), _grad_buf(Pm['W2']),
                        _grad_buf(Pm['b2']))
     dz = torch.empty(rows_t, d, dtype=bf16, device=dev)
     ops.rmsnorm_bwd(dzn, z, r2, Pm['norm2'].detach(), dz, _grad_buf(Pm['norm2']), dres=dy)
-    # z = x_tail + MHA(norm1(x))
-    dxn = mha_backward(dz, xn, mha_saved, w, _grad_buf(Pm['Wqkv']), _grad_buf(Pm['Wo']), B, cur, keep, H)
+    # z = x_tail + drop(MHA(norm1(x)))
+    dz_a = ops.dropout_mask(dz, drop[0], drop[2]) if drop is not None else dz
+    dxn = mha_backward(dz_a, xn, mha_saved, w, _grad_buf(Pm['Wqkv']), _grad_buf(Pm['Wo']), B, cur, keep, H)
     dx = torch.empty(rows, d, dtype=bf16, device=dev)
     g1, dg1 = Pm['norm1'].detach(), _grad_buf(Pm['norm1'])
     if off > 0:

@@ -281,11 +281,12 @@ class OneTransBlock(nn.Module):
                             kv_prefix: Optional[torch.Tensor] = None, x_hp: Optional[torch.Tensor] = None):
         """Token-major entry used by OneTransModel: ``x2 [cur*B, d]`` -> ``([keep*B, d], kv [Lk*B, 2d], y_hp)``.
         ``x_hp``: fp32 copy of the NS-token rows (high-precision residual stream) or None."""
+        drop = None
         if training and self.dropout_rate > 0.0:
-            raise NotImplementedError(
-                'dropout inside the fused block is not built yet; set config.dropout_rate = 0 for training '
-                '(SURVEY.md §8d: parity runs use dropout 0)')
-        return _BlockFn.apply(x2, self.norm1.scale, self, B, cur, keep, kv_prefix, x_hp)
+            # Keras Dropout(rate) on both branch outputs (OT/model.py:184,193,198); seeds come from torch's CPU generator
+            s = torch.randint(0, 2 ** 31 - 1, (2,))
+            drop = (int(s[0]), int(s[1]), float(self.dropout_rate))
+        return _BlockFn.apply(x2, self.norm1.scale, self, B, cur, keep, kv_prefix, x_hp, drop)
 
     def forward(self, x: torch.Tensor, training: bool = False,
                 kv_cache: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, query_len: Optional[int] = None):
@@ -307,7 +308,7 @@ class OneTransBlock(nn.Module):
 
 class _BlockFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x2, anchor, blk: OneTransBlock, B, cur, keep, kv_prefix, x_hp):
+    def forward(ctx, x2, anchor, blk: OneTransBlock, B, cur, keep, kv_prefix, x_hp, drop):
         cfg = blk.config
         need_grad = any(ctx.needs_input_grad)
         if need_grad and kv_prefix is not None:
@@ -316,7 +317,7 @@ class _BlockFn(torch.autograd.Function):
         P = {'norm1': blk.norm1.scale.detach(), 'norm2': blk.norm2.scale.detach(), 'b1': blk.ffn.b1.detach(),
              'b2': blk.ffn.b2.detach()}
         y, kv, saved, y_hp = engine.block_forward(x2, P, w, B, cur, keep, cfg.num_heads, cfg.num_ns_tokens, cfg.ns_param_alignment,
-                                                  blk.norm1.eps, need_grad, kv_prefix, x_hp)
+                                                  blk.norm1.eps, need_grad, kv_prefix, x_hp, drop)
         if y_hp is None:
             y_hp = y.new_zeros(0, dtype=torch.float32)
         ctx.mark_non_differentiable(kv, y_hp)
@@ -328,7 +329,7 @@ class _BlockFn(torch.autograd.Function):
         saved, w, blk, B, cur, keep = ctx.saved
         dx = engine.block_backward(dy, saved, blk._params(), w, B, cur, keep, blk.config.num_heads)
         ctx.saved = None
-        return dx, None, None, None, None, None, None, None
+        return dx, None, None, None, None, None, None, None, None
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -102,7 +102,7 @@ def mixed_gemm(A: torch.Tensor, W: torch.Tensor, segs: Sequence[Seg], out: torch
                aux: Optional[torch.Tensor] = None, out2: Optional[torch.Tensor] = None,
                row_scale: Optional[torch.Tensor] = None, a_transposed_events: bool = False,
                block_n: int = 0, swizzle: int = 0, res_hp: Optional[torch.Tensor] = None,
-               out_hp: Optional[torch.Tensor] = None, hp_row0: int = 0) -> torch.Tensor:
+               out_hp: Optional[torch.Tensor] = None, hp_row0: int = 0, dropout: Optional[Tuple[int, float]] = None) -> torch.Tensor:
     """``out[row] = epilogue(A[row] @ W[group(row)].T)``.  W: ``[G, N, K]`` bf16 (rows may be strided).
     With ``a_transposed_events`` A is ``[B, L_i, K]`` and output rows are ``(l, b)`` token-major."""
     _check_bf16(W, 'W')
@@ -121,6 +121,9 @@ def mixed_gemm(A: torch.Tensor, W: torch.Tensor, segs: Sequence[Seg], out: torch
         p.a_dim1, p.a_dim2, p.a_stride1, p.a_stride2, p.a_transposed = A.shape[0], 1, A.stride(0), 0, 0
     assert W.stride(2) == 1 and W.stride(0) == N * W.stride(1), 'W groups must be evenly strided rows'
     p.n_groups, p.W, p.ldw, p.N, p.K = G, W.data_ptr(), W.stride(1), N, K
+    if dropout is not None and dropout[1] > 0.0:
+        flags |= L.OT_EPI_DROPOUT
+        p.drop_seed, p.drop_rate = dropout[0] & 0xFFFFFFFF, dropout[1]
     p.n_segs, p.flags = len(segs), flags
     for i, s in enumerate(segs):
         sg = p.segs[i]
@@ -309,6 +312,23 @@ def fill_rows(vec: torch.Tensor, out: torch.Tensor, row0: int, n_rows: int) -> N
     L.count_launch()
 
 
+def dropout_mask(inp: torch.Tensor, seed: int, rate: float) -> torch.Tensor:
+    """Backward of the epilogue dropout: ``keep ? inp/(1-rate) : 0`` with the mask the forward GEMM used."""
+    _check_bf16(inp, 'inp')
+    out = torch.empty_like(inp)
+    prof = _PROFILER
+    if prof is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    L.check(L.load().ot_dropout_mask(inp.data_ptr(), inp.stride(0), out.data_ptr(), out.stride(0), inp.shape[0], inp.shape[1],
+                                     seed & 0xFFFFFFFF, rate, _stream()), 'ot_dropout_mask')
+    if prof is not None:
+        e1.record()
+        prof.records.append(('ot_dropout_mask', f'N{inp.shape[1]}', e0, e1, float(inp.numel()), inp.numel() * 4.0))
+    L.count_launch()
+    return out
+
+
 def colsum(inp: torch.Tensor, segs: Sequence[Seg], out: torch.Tensor, out_group_stride: int) -> None:
     """``out[group][n] += sum_rows inp[row, n]`` for each unit of each segment (bias gradients)."""
     _check_bf16(inp, 'inp')
@@ -320,3 +340,25 @@ def colsum(inp: torch.Tensor, segs: Sequence[Seg], out: torch.Tensor, out_group_
         p.out, p.out_group_stride, p.N = out.data_ptr(), out_group_stride, inp.shape[1]
         _run('ot_colsum', L.load().ot_colsum, p, f'N{inp.shape[1]}', float(n_units * rpu * inp.shape[1]),
              n_units * rpu * inp.shape[1] * 2.0)
+
+
+def clip_rmsprop_step(param_ptrs: torch.Tensor, seg_off: torch.Tensor, seg_numel: torch.Tensor, grad: torch.Tensor,
+                      rms: torch.Tensor, mom: Optional[torch.Tensor], sqnorm: torch.Tensor, *, lr: float, rho: float,
+                      momentum: float, eps: float, clip_norm: float, grad_scale: float = 1.0, zero_grad: bool = False) -> None:
+    """Per-tensor ``clip_by_norm`` then Keras RMSprop on flat fp32 buffers (OT/train.py:131-138).  ``param_ptrs`` /
+    ``seg_off`` / ``seg_numel`` are int64 DEVICE tables (see ``ot_rmsprop_params``)."""
+    for t in (param_ptrs, seg_off, seg_numel):
+        if not t.is_cuda or t.dtype != torch.int64:
+            raise RuntimeError('clip_rmsprop_step: tables must be CUDA int64 tensors (no CPU fallback)')
+    for t in (grad, rms, sqnorm) + ((mom,) if mom is not None else ()):
+        if not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+            raise RuntimeError('clip_rmsprop_step: buffers must be contiguous CUDA fp32 tensors (no CPU fallback)')
+    p = L.RmspropParams()
+    p.param_ptrs, p.seg_off, p.seg_numel = param_ptrs.data_ptr(), seg_off.data_ptr(), seg_numel.data_ptr()
+    p.n_seg, p.n_flat = seg_numel.numel(), grad.numel()
+    p.grad, p.rms, p.mom, p.sqnorm = grad.data_ptr(), rms.data_ptr(), _ptr(mom), sqnorm.data_ptr()
+    p.lr, p.rho, p.momentum, p.eps, p.clip_norm, p.grad_scale = lr, rho, momentum, eps, clip_norm, grad_scale
+    p.zero_grad = 1 if zero_grad else 0
+    n = float(grad.numel())
+    _run('ot_clip_rmsprop_step', L.load().ot_clip_rmsprop_step, p, f'n{grad.numel()}', 10.0 * n,
+         n * (4.0 * (clip_norm > 0) + 24.0 + 8.0 * (momentum != 0.0) + 4.0 * bool(zero_grad)), n_launch=2 if clip_norm > 0 else 1)

@@ -30,15 +30,19 @@ class FlatGradBuffer:
     The weight-gradient kernels accumulate into the views directly, ``zero()`` is one memset and the
     data-parallel reduction is one (bucketed) all-reduce of the buffer."""
 
+    ALIGN = 1024  # elements; == OT_OPT_CHUNK so an optimizer chunk never straddles two tensors
+
     def __init__(self, params: Iterable[torch.nn.Parameter]):
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
-        n = sum(p.numel() for p in self.params)
-        dev = self.params[0].device
-        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.offsets: List[int] = []
         off = 0
         for p in self.params:
-            p.grad = self.flat[off:off + p.numel()].view(p.shape)
-            off += p.numel()
+            self.offsets.append(off)
+            off += -(-p.numel() // self.ALIGN) * self.ALIGN
+        dev = self.params[0].device
+        self.flat = torch.zeros(off, dtype=torch.float32, device=dev)
+        for p, o in zip(self.params, self.offsets):
+            p.grad = self.flat[o:o + p.numel()].view(p.shape)
 
     def zero(self) -> None:
         self.flat.zero_()
@@ -53,12 +57,69 @@ class FlatGradBuffer:
         self.flat.mul_(1.0 / world_size)
 
 
-def train_step(model, grads: FlatGradBuffer, non_seq, seq, labels, world_size: int = 1) -> torch.Tensor:
+class ClipRMSprop:
+    """The dense-parameter update of the reference train step (OT/train.py:131-138): per-tensor
+    ``tf.clip_by_norm(g, gradient_clip_norm)`` followed by Keras ``RMSprop(learning_rate, rho=0.9, momentum,
+    epsilon=1e-7)`` (OT/train.py:65-70; lr 0.005, momentum 0.99999, clip 90 from OT/config.py:39-52), as two
+    streaming kernels over the flat gradient buffer (``ot_clip_rmsprop_step``).  fp32 masters are updated in place and
+    their version counters bumped so the bf16 compute copies refresh on the next forward."""
+
+    def __init__(self, grads: FlatGradBuffer, lr: float = 0.005, rho: float = 0.9, momentum: float = 0.0,
+                 eps: float = 1e-7, clip_norm: float = 0.0):
+        from . import ops
+        self._ops = ops
+        self.grads = grads
+        self.lr, self.rho, self.momentum, self.eps, self.clip_norm = float(lr), float(rho), float(momentum), float(eps), float(clip_norm)
+        dev = grads.flat.device
+        if dev.type != 'cuda':
+            raise RuntimeError('ClipRMSprop runs on CUDA tensors only (no CPU fallback)')
+        for p in grads.params:
+            if p.dtype != torch.float32 or not p.is_contiguous() or p.data_ptr() % 16:
+                raise RuntimeError('ClipRMSprop: parameters must be contiguous, 16-byte aligned fp32 CUDA tensors')
+        self.rms = torch.zeros_like(grads.flat)
+        self.mom = torch.zeros_like(grads.flat) if self.momentum != 0.0 else None
+        self.sqnorm = torch.zeros(len(grads.params), dtype=torch.float32, device=dev)
+        self._seg_off = torch.tensor(grads.offsets + [grads.flat.numel()], dtype=torch.int64, device=dev)
+        self._seg_numel = torch.tensor([p.numel() for p in grads.params], dtype=torch.int64, device=dev)
+        self._ptrs = None
+        self._ptr_key = None
+
+    @classmethod
+    def from_config(cls, grads: FlatGradBuffer, config) -> 'ClipRMSprop':
+        oc = config.optimizer_config
+        return cls(grads, lr=oc.get('dense_lr', 0.005), rho=oc.get('rho', 0.9), momentum=oc.get('momentum', 0.0),
+                   eps=oc.get('epsilon', 1e-7), clip_norm=getattr(config, 'gradient_clip_norm', 0.0))
+
+    def _param_table(self) -> torch.Tensor:
+        key = tuple(p.data_ptr() for p in self.grads.params)
+        if key != self._ptr_key:
+            self._ptrs = torch.tensor(key, dtype=torch.int64, device=self.grads.flat.device)
+            self._ptr_key = key
+        return self._ptrs
+
+    @torch.no_grad()
+    def step(self, grad_scale: float = 1.0, zero_grad: bool = False) -> None:
+        self._ops.clip_rmsprop_step(self._param_table(), self._seg_off, self._seg_numel, self.grads.flat, self.rms, self.mom,
+                                    self.sqnorm, lr=self.lr, rho=self.rho, momentum=self.momentum, eps=self.eps,
+                                    clip_norm=self.clip_norm, grad_scale=grad_scale, zero_grad=zero_grad)
+        for p in self.grads.params:
+            torch.autograd.graph.increment_version(p)
+
+    def grad_norms(self) -> torch.Tensor:
+        """Per-tensor gradient L2 norms seen by the last ``step`` (valid when clip_norm > 0)."""
+        return self.sqnorm.sqrt()
+
+
+def train_step(model, grads: FlatGradBuffer, non_seq, seq, labels, world_size: int = 1,
+               optimizer: Optional[ClipRMSprop] = None) -> torch.Tensor:
     """forward + BCE + backward (+ gradient all-reduce): the "fwd+bwd" of the headline metric
-    (OT/train.py:116-131).  Returns the detached loss tensor (no host sync)."""
+    (OT/train.py:116-131); with ``optimizer`` also the clip + RMSprop update (OT/train.py:133-138).
+    Returns the detached loss tensor (no host sync)."""
     grads.zero()
     probs = model(non_seq, seq, training=True)
     loss = bce_loss(probs, labels, model.config.tasks)
     loss.backward()
     grads.all_reduce(world_size)
+    if optimizer is not None:
+        optimizer.step()
     return loss.detach()

@@ -64,10 +64,12 @@ def test_allreduced_shard_grads_equal_full_batch_grads(tmp_path):
 def test_flat_grad_buffer_views_and_zero():
     ps = [torch.nn.Parameter(torch.randn(3, 4)), torch.nn.Parameter(torch.randn(5))]
     buf = FlatGradBuffer(ps)
-    assert buf.flat.numel() == 17
+    A = FlatGradBuffer.ALIGN                      # every tensor starts on an optimizer-chunk boundary
+    assert buf.offsets == [0, A] and buf.flat.numel() == 2 * A
     ps[0].grad.add_(1.0)
     ps[1].grad.add_(2.0)
-    assert buf.flat[:12].eq(1).all() and buf.flat[12:].eq(2).all()
+    assert buf.flat[:12].eq(1).all() and buf.flat[A:A + 5].eq(2).all()
+    assert buf.flat[12:A].eq(0).all() and buf.flat[A + 5:].eq(0).all()
     buf.zero()
     assert ps[0].grad.abs().sum() == 0 and ps[1].grad.abs().sum() == 0
     buf.all_reduce(1)   # world 1: no-op, no process group needed

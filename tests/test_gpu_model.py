@@ -166,3 +166,84 @@ def test_t9_auc_delta_on_64k_samples():
         auc_o, auc_g = roc_auc_score(y, a.numpy()), roc_auc_score(y, b.numpy())
         print(f'AUC[{t}] oracle {auc_o:.6f} kernels {auc_g:.6f} delta {abs(auc_o - auc_g):.2e}')
         assert abs(auc_o - auc_g) <= 1e-4
+
+
+def test_dropout_forward_backward_consistency():
+    """training=True with the reference's dropout (OT/config.py:50, OT/model.py:184,193,198).  The mask is a counter-based
+    hash, so parity with the oracle's torch RNG can only be statistical; what is checked exactly is that the forward
+    epilogue mask and the backward mask kernel are the same function: extract the mask by pushing ones through the
+    backward kernel, then compare one block's forward/backward with a torch autograd evaluation that uses that mask."""
+    from recommend_b200 import ops, engine
+    torch.manual_seed(0)
+    rows, d = 700, 256
+    ones = torch.ones(rows, d, dtype=torch.bfloat16, device='cuda')
+    rate, seed = 0.1, 12345
+    m = ops.dropout_mask(ones, seed, rate).float()
+    keep = (m > 0).float()
+    assert torch.allclose(m[m > 0], torch.full_like(m[m > 0], 1 / (1 - rate)), rtol=1e-2)       # inverted dropout scale
+    assert abs(keep.mean().item() - (1 - rate)) < 5e-3                                          # drop fraction ~ rate
+    assert abs(keep[:, ::2].mean().item() - keep[:, 1::2].mean().item()) < 1e-2                 # both hash lanes behave
+    assert not torch.equal(keep, (ops.dropout_mask(ones, seed + 1, rate) > 0).float())          # seed matters
+    # GEMM epilogue applies the same mask: out = res + mask * (A W^T)
+    A = (torch.randn(rows, 64, device='cuda')).to(torch.bfloat16)
+    W = (torch.randn(1, d, 64, device='cuda') * 0.2).to(torch.bfloat16)
+    res = torch.randn(rows, d, device='cuda').to(torch.bfloat16)
+    out = torch.empty(rows, d, dtype=torch.bfloat16, device='cuda')
+    ops.mixed_gemm(A, W, [(0, 1, rows, 0, 0)], out, flags=4, res=res, dropout=(seed, rate))
+    ref = res.float() + m * (A.float() @ W[0].float().t())
+    assert ((out.float() - ref).abs() / (1 + ref.abs())).max().item() < 2e-2
+
+    # whole model: training=True runs, is deterministic under torch.manual_seed, differs from eval, grads are finite
+    ocfg, cfg = make_configs(num_layers=2, num_ns_tokens=8, schedule='linear_to_ns')
+    cfg.dropout_rate = 0.1
+    P, model = _build(ocfg, cfg)
+    non_seq, seq, labels = O.synthetic_batch(ocfg, 64, (30, 20, 10))
+    ns, sq = to_cuda(non_seq), to_cuda(seq)
+    torch.manual_seed(7)
+    a = model(ns, sq, training=True, return_logits=True)
+    torch.manual_seed(7)
+    b = model(ns, sq, training=True, return_logits=True)
+    e = model(ns, sq, training=False, return_logits=True)
+    assert all(torch.equal(a[t], b[t]) for t in cfg.tasks)
+    assert not torch.equal(a['ctr'], e['ctr'])
+    assert rel_l2(a['ctr'], e['ctr']) < 0.5     # dropout noise, same function underneath
+    model.zero_grad(set_to_none=True)
+    torch.manual_seed(7)
+    out2 = model(ns, sq, training=True, return_logits=True)
+    (out2['ctr'].sum() + out2['cvr'].sum()).backward()
+    g = R.export_reference_style_params(model, grads=True)
+    assert all(torch.isfinite(v).all() for v in g.values() if v is not None)
+    assert g['blocks.0.ffn.W1'].abs().sum() > 0
+
+
+def test_block_dropout_backward_matches_autograd_with_extracted_mask():
+    """One OneTransBlock with dropout: forward and input gradient against torch autograd using the masks extracted from the
+    backward mask kernel (the oracle block with identical weights, dropout applied explicitly)."""
+    from recommend_b200 import ops
+    ocfg, cfg = make_configs(num_layers=1, num_ns_tokens=4, pyramid_enabled=False)
+    cfg.dropout_rate = 0.1
+    P, model = _build(ocfg, cfg)
+    blk = model.blocks[0]
+    B, L, d = 16, 20, 256
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(B, L, d, generator=g).to(torch.bfloat16)
+    xg = x.cuda().requires_grad_(True)
+    torch.manual_seed(11)
+    y, _ = blk(xg, training=True)
+    dy = torch.randn(B, L, d, generator=g).to(torch.bfloat16)
+    (y.float() * dy.cuda().float()).sum().backward()
+    # reproduce the two seeds the block drew
+    torch.manual_seed(11)
+    s = torch.randint(0, 2 ** 31 - 1, (2,))
+    ones = torch.ones(L * B, d, dtype=torch.bfloat16, device='cuda')
+    m_att = ops.dropout_mask(ones, int(s[0]), 0.1).float().cpu().view(L, B, d).transpose(0, 1)
+    m_ffn = ops.dropout_mask(ones, int(s[1]), 0.1).float().cpu().view(L, B, d).transpose(0, 1)
+    xo = x.float().requires_grad_(True)
+    b0 = 'blocks.0.'
+    xn = O.rmsnorm(xo, P[b0 + 'norm1.scale'])
+    z = xo + m_att * O.mixed_mha(P, b0 + 'attention.', ocfg, xn, L)
+    zn = O.rmsnorm(z, P[b0 + 'norm2.scale'])
+    yo = z + m_ffn * O.mixed_ffn(P, b0 + 'ffn.', ocfg, zn, 0, L)
+    (yo * dy.float()).sum().backward()
+    assert rel_l2(y.detach().float().cpu(), yo.detach()) < 1e-2
+    assert rel_l2(xg.grad.float().cpu(), xo.grad) < 3e-2

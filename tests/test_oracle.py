@@ -217,3 +217,26 @@ def test_golden_vectors():
         got = run_case(spec)
         for k, v in want[name].items():
             assert torch.allclose(torch.tensor(got[k]), torch.tensor(v), rtol=1e-5, atol=1e-6), (name, k)
+
+
+def test_T12_clip_and_rmsprop_hand_computed():
+    """OT/train.py:133-138 with Keras-2.12 RMSprop arithmetic, two steps by hand."""
+    g = torch.tensor([3.0, 4.0], dtype=torch.float64)
+    assert torch.equal(O.clip_by_norm(g, 10.0), g)                       # ||g|| = 5 <= 10: untouched
+    assert torch.allclose(O.clip_by_norm(g, 2.5), g * 0.5, atol=0, rtol=1e-15)
+    w, rms, mom = torch.tensor([1.0, -1.0], dtype=torch.float64), torch.zeros(2, dtype=torch.float64), torch.zeros(2, dtype=torch.float64)
+    lr, rho, m, eps = 0.005, 0.9, 0.5, 1e-7
+    w1, rms1, mom1 = O.rmsprop_step(w, g, rms, mom, lr, rho, m, eps)
+    r = [0.1 * 9.0, 0.1 * 16.0]
+    inc = [lr * 3.0 / (r[0] + eps) ** 0.5, lr * 4.0 / (r[1] + eps) ** 0.5]
+    assert torch.allclose(rms1, torch.tensor(r, dtype=torch.float64), rtol=1e-14)
+    assert torch.allclose(mom1, torch.tensor(inc, dtype=torch.float64), rtol=1e-14)
+    assert torch.allclose(w1, torch.tensor([1.0 - inc[0], -1.0 - inc[1]], dtype=torch.float64), rtol=1e-14)
+    w2, rms2, mom2 = O.rmsprop_step(w1, g, rms1, mom1, lr, rho, m, eps)
+    r2 = [0.9 * r[0] + 0.1 * 9.0, 0.9 * r[1] + 0.1 * 16.0]
+    inc2 = [lr * 3.0 / (r2[0] + eps) ** 0.5, lr * 4.0 / (r2[1] + eps) ** 0.5]
+    assert torch.allclose(mom2, torch.tensor([m * inc[0] + inc2[0], m * inc[1] + inc2[1]], dtype=torch.float64), rtol=1e-14)
+    assert torch.allclose(w2, w1 - mom2, rtol=1e-14)
+    # momentum 0: plain step, mom untouched
+    w3, _, mom3 = O.rmsprop_step(w, g, rms, None, lr, rho, 0.0, eps)
+    assert mom3 is None and torch.allclose(w3, w1, rtol=1e-14)
