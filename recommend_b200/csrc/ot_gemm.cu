@@ -8,12 +8,12 @@
 // the per-token NS runs are tiles of ONE persistent launch.
 //
 // Kernel structure (one CTA per SM, persistent over a static tile list; 20 warps, registers re-balanced with
-// setmaxnreg: 40 per control thread, 112 per epilogue thread):
+// setmaxnreg: 32 per control thread, 112 per epilogue thread):
 //   warp 0   : TMA producer   — A tile [128 x BK] and W tile [BN x BK] into a STAGES-deep smem ring
 //   warp 1   : MMA issuer     — tcgen05.mma (M=128, N=BN, K=16) into one of two TMEM accumulators
-//   warps 4-19: epilogue      — tcgen05.ld -> fp32 math (row scale, bias, GELU, GELU', residual)
-//                               -> bf16 -> swizzled smem staging -> coalesced 16-byte global stores
-//                               (four sets of four warps split the 64-column chunks of a tile)
+//   warps 4-19: epilogue      — tcgen05.ld -> packed fp32 math (row scale, bias, GELU, GELU', residual, dropout)
+//                               -> bf16 -> swizzled smem staging tile -> TMA store; residual / GELU' inputs arrive
+//                               by TMA one tile ahead (four sets of four warps, one 64-column chunk each)
 // The two TMEM accumulators (2*BN <= 512 columns) let the epilogue of tile i overlap the MMAs of
 // tile i+1.  Roofline: at d=256 every GEMM of the block is HBM-bound, so the
 // epilogue reads/writes each activation byte exactly once and in full 128-byte lines.
@@ -31,7 +31,6 @@ static constexpr int CTRL_THREADS = 128;      // one control warpgroup: warp 0 T
 static constexpr int GEMM_THREADS = CTRL_THREADS + EPI_THREADS;   // + 16 epilogue warps (warps 4..19)
 static constexpr int EPI_REGS = 112, CTRL_REGS = 32;   // setmaxnreg: the control warpgroup releases 4*32*(96-32) registers into the CTA pool, exactly what the four epilogue warpgroups take (4*128*(112-96)); asking for more than was released spins forever
 static constexpr int EPI_BAR_ID = 1;         // named barriers 1..4: one per epilogue set
-static constexpr int EPI_BAR_ALL = 5;        // all epilogue warps (bias tile reload)
 static constexpr int CHUNK = 64;             // epilogue column chunk (128 bytes of bf16 per row)
 static constexpr int CH_BYTES = 128 * 64 * 2;   // one staged chunk: 128 rows x 128 bytes
 
@@ -90,11 +89,10 @@ struct GemmCfg {
   static constexpr int B_BYTES = BN * SWB;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGING_BYTES = EPI_SETS * BM * CHUNK * 2;  // one 128x64 bf16 buffer per epilogue set
-  static constexpr int BIAS_BYTES = BN * 4;
-  static constexpr int BUDGET = 227 * 1024 - STAGING_BYTES - BIAS_BYTES - 256;
+  static constexpr int BUDGET = 227 * 1024 - STAGING_BYTES - 256;
   static constexpr int STAGES_RAW = BUDGET / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + BIAS_BYTES + 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 256;
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
                                    : (2 * BN <= 256) ? 256 : 512;
 };
@@ -102,7 +100,8 @@ struct GemmCfg {
 template <int BN, int SWB>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 ot_mixed_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                     const __grid_constant__ GemmKParams p) {
+                     const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOut2,
+                     const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ GemmKParams p) {
   using Cfg = GemmCfg<BN, SWB>;
   constexpr int BK = Cfg::BK;
   constexpr int STAGES = Cfg::STAGES;
@@ -110,13 +109,13 @@ ot_mixed_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 
   uint8_t* stage_base = smem;
   uint8_t* staging = smem + STAGES * Cfg::STAGE_BYTES;
-  float* bias_s = reinterpret_cast<float*>(staging + Cfg::STAGING_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + Cfg::STAGING_BYTES + Cfg::BIAS_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + Cfg::STAGING_BYTES);
   uint64_t* full_bar = bars;                 // [STAGES]
   uint64_t* empty_bar = bars + STAGES;       // [STAGES]
   uint64_t* tfull_bar = bars + 2 * STAGES;   // [2]
   uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint64_t* in_bars = bars + 2 * STAGES + 4;     // [EPI_SETS] auxiliary-input tiles
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4 + EPI_SETS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -127,6 +126,7 @@ ot_mixed_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     if ((smem_u32(smem) & 1023u) != 0) __trap();  // swizzled tiles need a 1024-byte aligned base
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmOut);
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
@@ -135,6 +135,7 @@ ot_mixed_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], 4 * EPI_SETS);
     }
+    for (int i = 0; i < EPI_SETS; ++i) mbar_init(&in_bars[i], 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -158,7 +159,7 @@ ot_mixed_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const TileInfo t = decode_tile(p, mblk);
         const int w_row = t.group * p.N + nblk * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_wait_backoff(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = stage_base + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
@@ -178,11 +179,11 @@ ot_mixed_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        mbar_wait_backoff(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
+          mbar_wait_backoff(&full_bar[stage], phase, 32);
           tc_fence_after();
           const uint32_t sa = smem_u32(stage_base + stage * Cfg::STAGE_BYTES);
           const uint32_t sb = sa + Cfg::A_BYTES;
@@ -202,10 +203,13 @@ ot_mixed_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   } else if (warp >= 4) {
     // ===================== epilogue (warps 4..19: four sets of four) =====================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(EPI_REGS));
-    // Set s handles the 64-column chunks c = s, s+4, ... of every tile with its own staging buffer and named
-    // barrier; inside a set, warp w may read TMEM lanes 32*(w%4)..+31 (one accumulator row per thread).  Sixteen
-    // warps (four per scheduler) are what it takes to hide the TMEM / MUFU / smem latencies of the GELU epilogues:
-    // with eight the FFN GEMMs ran at ~35 % of the HBM roofline, issue slots 60 % idle (profiles/README.md).
+    // Set s owns the 64-column chunk s of every tile (BN <= 256 -> at most one chunk per set and tile), one 16 KB
+    // staging tile and one mbarrier.  Inside a set, warp w may read TMEM lanes 32*(w%4)..+31 (one accumulator row
+    // per thread).  Data path of a chunk:
+    //   residual / GELU' input: TMA load into the staging tile, issued one TILE ahead by the set's IO thread
+    //   tcgen05.ld -> packed fp32 math (FFMA2) -> bf16 -> the thread's own row of the staging tile (in place)
+    //   TMA store of the staging tile; the IO thread waits for it to drain before it issues the next prefetch
+    // Tiles with fewer than 128 valid rows (small batches) take the cooperative 16-byte load/store path instead.
     const int set = (warp - 4) >> 2;
     const int et = threadIdx.x - CTRL_THREADS - set * EPI_SET_THREADS;   // 0..127 inside the set
     const int lgrp = warp & 3;
@@ -214,12 +218,30 @@ ot_mixed_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const int ld_ch = et & 7;
     const uint32_t bar_id = EPI_BAR_ID + set;
     uint8_t* buf = staging + set * CH_BYTES;
+    uint64_t* in_bar = &in_bars[set];
+    uint32_t in_phase = 0;
+    const bool has_chunk = set < BN / CHUNK;
+    const bool io_thread = (et == 0);
     const bool f_bias = p.flags & OT_EPI_BIAS, f_gelu = p.flags & OT_EPI_GELU, f_res = p.flags & OT_EPI_RESIDUAL;
     const bool f_ggrad = p.flags & OT_EPI_GELU_GRAD, f_rs = p.flags & OT_EPI_ROW_SCALE, f_drop = p.flags & OT_EPI_DROPOUT;
     const bool has_in = f_res || f_ggrad;
     const bool dual = f_gelu && (p.out2 != nullptr);
     const __nv_bfloat16* in_ptr = f_res ? p.res : p.aux;
     const long long in_ld = f_res ? p.ldr : p.ldaux;
+    // does tile t take its bf16 auxiliary input through TMA?  (tile-uniform; NS tiles with an fp32 residual do not)
+    auto tma_in_tile = [&](const TileInfo& t) {
+      return has_in && t.valid == BM && !(f_res && p.res_hp != nullptr && t.row0 >= p.hp_row0);
+    };
+    auto issue_in = [&](int tile) {            // IO thread only
+      const int mblk = tile / p.n_nblks;
+      const TileInfo t = decode_tile(p, mblk);
+      if (tma_in_tile(t)) {
+        mbar_arrive_expect_tx(in_bar, CH_BYTES);
+        tma_load_2d(buf, &tmIn, in_bar, (tile - mblk * p.n_nblks) * BN + set * CHUNK, t.row0);
+      }
+    };
+    if (has_chunk && io_thread && has_in && (int)blockIdx.x < total_tiles) issue_in(blockIdx.x);
+
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int mblk = tile / p.n_nblks;
@@ -229,26 +251,22 @@ ot_mixed_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
 
-      if (f_bias) {
-        named_bar_sync(EPI_BAR_ALL, EPI_THREADS);  // previous tile's readers of bias_s are done
-        for (int j = threadIdx.x - CTRL_THREADS; j < BN; j += EPI_THREADS)
-          bias_s[j] = p.bias[(long long)t.group * p.bias_group_stride + n0 + j];
-        named_bar_sync(EPI_BAR_ALL, EPI_THREADS);
-      }
       float rs = 1.0f;
       if (f_rs && r_own < t.valid) rs = p.row_scale[t.row0 + r_own];
       // NS-token tiles may carry an fp32 residual stream (tile-uniform: NS units start on tile boundaries)
       const bool hp_tile = f_res && (p.res_hp != nullptr) && (t.row0 >= p.hp_row0);
       const bool tile_in = has_in && !hp_tile;
+      const bool tma_in = tma_in_tile(t);
+      const bool tma_out = (t.valid == BM);
 
-      mbar_wait(&tfull_bar[acc], acc_phase);
+      mbar_wait_backoff(&tfull_bar[acc], acc_phase, 32);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(lgrp * 32) << 16) + acc * BN;
 
-#pragma unroll 1
-      for (int c = set; c < BN / CHUNK; c += EPI_SETS) {
+      if (has_chunk) {
+        const int c = set;
         const int col0 = n0 + c * CHUNK;
-        // staging-buffer helpers (the buffer is single: every use starts behind a barrier)
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(lgrp * 32) << 16) + acc * BN + c * CHUNK;
+        const float* bias_g = f_bias ? p.bias + (long long)t.group * p.bias_group_stride + col0 : nullptr;
         auto store_rows = [&](__nv_bfloat16* dst, long long ld) {   // staging -> global, full 128-byte rows
 #pragma unroll
           for (int i = 0; i < BM / 16; ++i) {
@@ -258,42 +276,53 @@ ot_mixed_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                   *reinterpret_cast<const uint4*>(buf + swz_off<128>(r, ld_ch));
           }
         };
-        named_bar_sync(bar_id, EPI_SET_THREADS);   // the previous chunk's stores out of `buf` are done
-        if (tile_in) {   // residual / GELU' input chunk: coalesced global -> staging
-#pragma unroll
-          for (int i = 0; i < BM / 16; ++i) {
-            const int r = i * 16 + ld_row;
-            uint4 q = make_uint4(0, 0, 0, 0);
-            if (r < t.valid)
-              q = *reinterpret_cast<const uint4*>(in_ptr + (long long)(t.row0 + r) * in_ld + col0 + ld_ch * 8);
-            *reinterpret_cast<uint4*>(buf + swz_off<128>(r, ld_ch)) = q;
-          }
+        if (tma_in) {
+          mbar_wait(in_bar, in_phase);           // prefetched one tile ago, behind the drain of the last store
+          in_phase ^= 1;
+        } else {
+          if (io_thread) bulk_wait_read0();      // the previous TMA store has left the staging tile
           named_bar_sync(bar_id, EPI_SET_THREADS);
+          if (tile_in) {   // partial tile: cooperative global -> staging
+#pragma unroll
+            for (int i = 0; i < BM / 16; ++i) {
+              const int r = i * 16 + ld_row;
+              uint4 q = make_uint4(0, 0, 0, 0);
+              if (r < t.valid)
+                q = *reinterpret_cast<const uint4*>(in_ptr + (long long)(t.row0 + r) * in_ld + col0 + ld_ch * 8);
+              *reinterpret_cast<uint4*>(buf + swz_off<128>(r, ld_ch)) = q;
+            }
+            named_bar_sync(bar_id, EPI_SET_THREADS);
+          }
         }
         // dual mode (FFN-1 forward keeps the pre-activation for the backward pass): pass 0 stores the pre-activation,
         // pass 1 re-reads the accumulator (TMEM reads are cheap, registers are not) and stores GELU of it
         const int n_pass = dual ? 2 : 1;
 #pragma unroll 1
         for (int pass = 0; pass < n_pass; ++pass) {
-          if (pass == 1) named_bar_sync(bar_id, EPI_SET_THREADS);   // pre-activation rows have left `buf`
+          if (pass == 1) {                       // pre-activation rows have left the staging tile
+            if (tma_out && io_thread) bulk_wait_read0();
+            named_bar_sync(bar_id, EPI_SET_THREADS);
+          }
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
             uint32_t v[32];
-            tmem_ld_x32(t_row + c * CHUNK + half * 32, v);
+            tmem_ld_x32(t_row + half * 32, v);
             tmem_ld_wait();
-            float f[32];
+            f32x2 f[16];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+            for (int j = 0; j < 16; ++j) f[j] = pk2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
             if (f_rs) {
+              const f32x2 rs2 = pk2(rs);
 #pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] *= rs;
+              for (int j = 0; j < 16; ++j) f[j] = mul2(f[j], rs2);
             }
-            if (f_bias) {
-              const float4* b4 = reinterpret_cast<const float4*>(bias_s + c * CHUNK + half * 32);
+            if (f_bias) {                        // 32 floats shared by the whole warp: broadcast loads, L1-resident
+              const float4* b4 = reinterpret_cast<const float4*>(bias_g + half * 32);
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
-                const float4 bb = b4[j];
-                f[4 * j + 0] += bb.x; f[4 * j + 1] += bb.y; f[4 * j + 2] += bb.z; f[4 * j + 3] += bb.w;
+                const float4 bb = __ldg(b4 + j);
+                f[2 * j] = add2(f[2 * j], pk2(bb.x, bb.y));
+                f[2 * j + 1] = add2(f[2 * j + 1], pk2(bb.z, bb.w));
               }
             }
             if (f_drop) {   // inverted dropout on the branch output, before the residual add
@@ -301,8 +330,11 @@ ot_mixed_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
                 const uint32_t hb = dropout_bits(p.drop_seed, grow, static_cast<uint32_t>(col0 + half * 32 + 2 * j), static_cast<uint32_t>(p.N));
-                f[2 * j] = ((hb & 0xFFFFu) >= p.drop_thr16) ? f[2 * j] * p.drop_scale : 0.0f;
-                f[2 * j + 1] = ((hb >> 16) >= p.drop_thr16) ? f[2 * j + 1] * p.drop_scale : 0.0f;
+                float a, b;
+                upk2(f[j], a, b);
+                a = ((hb & 0xFFFFu) >= p.drop_thr16) ? a * p.drop_scale : 0.0f;
+                b = ((hb >> 16) >= p.drop_thr16) ? b * p.drop_scale : 0.0f;
+                f[j] = pk2(a, b);
               }
             }
             if (hp_tile) {   // fp32 residual in, fp32 result out: one 128-byte line per thread and half-chunk
@@ -313,8 +345,12 @@ ot_mixed_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                   const float4 rr = rp[j];
-                  f[4 * j + 0] += rr.x; f[4 * j + 1] += rr.y; f[4 * j + 2] += rr.z; f[4 * j + 3] += rr.w;
-                  op[j] = make_float4(f[4 * j + 0], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                  f[2 * j] = add2(f[2 * j], pk2(rr.x, rr.y));
+                  f[2 * j + 1] = add2(f[2 * j + 1], pk2(rr.z, rr.w));
+                  float4 o;
+                  upk2(f[2 * j], o.x, o.y);
+                  upk2(f[2 * j + 1], o.z, o.w);
+                  op[j] = o;
                 }
               }
             }
@@ -328,36 +364,43 @@ ot_mixed_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
               }
               if (f_ggrad) {
 #pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                  f[2 * e] *= gelu_erf_grad(bf16lo(w[e]));
-                  f[2 * e + 1] *= gelu_erf_grad(bf16hi(w[e]));
-                }
+                for (int e = 0; e < 16; ++e) f[e] = mul2(f[e], gelu_erf_grad2(pk2(bf16lo(w[e]), bf16hi(w[e]))));
               } else {
 #pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                  f[2 * e] += bf16lo(w[e]);
-                  f[2 * e + 1] += bf16hi(w[e]);
-                }
+                for (int e = 0; e < 16; ++e) f[e] = add2(f[e], pk2(bf16lo(w[e]), bf16hi(w[e])));
               }
             }
             if (f_gelu && (pass == 1 || !dual)) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+              for (int j = 0; j < 16; ++j) f[j] = gelu_erf2(f[j]);
             }
-            // each thread (over)writes only its own row of `buf`
+            // each thread (over)writes only its own row of the staging tile
 #pragma unroll
             for (int ch = 0; ch < 4; ++ch) {
+              float a0, a1, a2, a3, a4, a5, a6, a7;
+              upk2(f[ch * 4 + 0], a0, a1); upk2(f[ch * 4 + 1], a2, a3); upk2(f[ch * 4 + 2], a4, a5); upk2(f[ch * 4 + 3], a6, a7);
               uint4 q;
-              q.x = pack_bf16x2(f[ch * 8 + 0], f[ch * 8 + 1]);
-              q.y = pack_bf16x2(f[ch * 8 + 2], f[ch * 8 + 3]);
-              q.z = pack_bf16x2(f[ch * 8 + 4], f[ch * 8 + 5]);
-              q.w = pack_bf16x2(f[ch * 8 + 6], f[ch * 8 + 7]);
+              q.x = pack_bf16x2(a0, a1); q.y = pack_bf16x2(a2, a3); q.z = pack_bf16x2(a4, a5); q.w = pack_bf16x2(a6, a7);
               *reinterpret_cast<uint4*>(buf + swz_off<128>(r_own, half * 4 + ch)) = q;
             }
           }
+          if (tma_out) fence_proxy_async_smem();   // my row -> visible to the TMA store
           named_bar_sync(bar_id, EPI_SET_THREADS);
-          if (dual && pass == 0) store_rows(p.out2, p.ldo2);   // pre-activation
-          else store_rows(p.out, p.ldo);
+          const bool to_out2 = dual && pass == 0;
+          if (tma_out) {
+            if (io_thread) {
+              tma_store_2d(to_out2 ? &tmOut2 : &tmOut, buf, col0, t.row0);
+              bulk_commit();
+            }
+          } else {
+            if (to_out2) store_rows(p.out2, p.ldo2); else store_rows(p.out, p.ldo);
+            named_bar_sync(bar_id, EPI_SET_THREADS);   // readers done before anything lands in the tile again
+          }
+        }
+        // prefetch the auxiliary input of this set's chunk in the CTA's next tile
+        if (io_thread && has_in && tile + (int)gridDim.x < total_tiles) {
+          bulk_wait_read0();
+          issue_in(tile + gridDim.x);
         }
       }
       // all TMEM reads of this accumulator are complete -> hand it back to the MMA warp
@@ -365,6 +408,7 @@ ot_mixed_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
     }
+    if (io_thread) bulk_wait_all();
   }
 
   tc_fence_before();
@@ -376,7 +420,8 @@ ot_mixed_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 // host launcher
 // -------------------------------------------------------------------------------------------------
 template <int BN, int SWB>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKParams& kp, cudaStream_t st) {
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const CUtensorMap& tmOut2,
+                       const CUtensorMap& tmIn, const GemmKParams& kp, cudaStream_t st) {
   using Cfg = GemmCfg<BN, SWB>;
   static bool attr_done = false;
   auto kern = ot_mixed_gemm_kernel<BN, SWB>;
@@ -386,7 +431,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   }
   const int total_tiles = kp.total_mblks * kp.n_nblks;
   const int grid = total_tiles < num_sms() ? total_tiles : num_sms();
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, kp);
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, tmOut, tmOut2, tmIn, kp);
   OT_CUDA_CHECK(cudaGetLastError());
   return OT_OK;
 }
@@ -400,6 +445,8 @@ int mixed_gemm_impl(const ot_gemm_params* p, cudaStream_t st) {
   if (p->N <= 0 || p->N % 64 != 0) OT_FAIL(OT_ERR_UNSUPPORTED_SHAPE, "ot_mixed_gemm: N=%d not a multiple of 64", p->N);
   if (p->n_segs < 1 || p->n_segs > 3) OT_FAIL(OT_ERR_INVALID_ARG, "ot_mixed_gemm: n_segs=%d", p->n_segs);
   if ((p->flags & OT_EPI_BIAS) && !p->bias) OT_FAIL(OT_ERR_INVALID_ARG, "ot_mixed_gemm: bias flag without bias");
+  if ((p->flags & OT_EPI_BIAS) && ((reinterpret_cast<uintptr_t>(p->bias) & 15) || (p->bias_group_stride % 4)))
+    OT_FAIL(OT_ERR_INVALID_ARG, "ot_mixed_gemm: bias must be 16-byte aligned with a group stride that is a multiple of 4");
   if ((p->flags & OT_EPI_RESIDUAL) && !p->res) OT_FAIL(OT_ERR_INVALID_ARG, "ot_mixed_gemm: residual flag without res");
   if ((p->flags & OT_EPI_GELU_GRAD) && !p->aux) OT_FAIL(OT_ERR_INVALID_ARG, "ot_mixed_gemm: gelu-grad flag without aux");
   if ((p->flags & OT_EPI_ROW_SCALE) && !p->row_scale) OT_FAIL(OT_ERR_INVALID_ARG, "ot_mixed_gemm: row-scale flag without row_scale");
@@ -464,14 +511,40 @@ int mixed_gemm_impl(const ot_gemm_params* p, cudaStream_t st) {
     int rc = make_tmap_bf16(&tmB, p->W, 2, dims, str, box, swb);
     if (rc) return rc;
   }
+  // epilogue I/O maps: [rows, N] bf16, box 128 rows x 64 columns in the 128-byte swizzle of the staging tiles
+  CUtensorMap tmOut, tmOut2, tmIn;
+  {
+    long long row_extent = 0;
+    for (int s = 0; s < p->n_segs; ++s) {
+      const long long e = (long long)p->segs[s].row_start + (long long)p->segs[s].n_units * p->segs[s].rows_per_unit;
+      if (e > row_extent) row_extent = e;
+    }
+    uint64_t dims[2] = {(uint64_t)p->N, (uint64_t)row_extent};
+    uint32_t box[2] = {(uint32_t)CHUNK, (uint32_t)BM};
+    uint64_t str[1] = {(uint64_t)p->ldo * 2};
+    int rc = make_tmap_bf16(&tmOut, p->out, 2, dims, str, box, 128);
+    if (rc) return rc;
+    tmOut2 = tmOut; tmIn = tmOut;
+    if (p->out2) {
+      str[0] = (uint64_t)p->ldo2 * 2;
+      rc = make_tmap_bf16(&tmOut2, p->out2, 2, dims, str, box, 128);
+      if (rc) return rc;
+    }
+    const void* in_base = (p->flags & OT_EPI_RESIDUAL) ? p->res : (p->flags & OT_EPI_GELU_GRAD) ? p->aux : nullptr;
+    if (in_base) {
+      str[0] = (uint64_t)((p->flags & OT_EPI_RESIDUAL) ? p->ldr : p->ldaux) * 2;
+      rc = make_tmap_bf16(&tmIn, in_base, 2, dims, str, box, 128);
+      if (rc) return rc;
+    }
+  }
   if (swb == 128) {
-    if (bn == 256) return launch_gemm<256, 128>(tmA, tmB, kp, st);
-    if (bn == 128) return launch_gemm<128, 128>(tmA, tmB, kp, st);
-    return launch_gemm<64, 128>(tmA, tmB, kp, st);
+    if (bn == 256) return launch_gemm<256, 128>(tmA, tmB, tmOut, tmOut2, tmIn, kp, st);
+    if (bn == 128) return launch_gemm<128, 128>(tmA, tmB, tmOut, tmOut2, tmIn, kp, st);
+    return launch_gemm<64, 128>(tmA, tmB, tmOut, tmOut2, tmIn, kp, st);
   } else {
-    if (bn == 256) return launch_gemm<256, 64>(tmA, tmB, kp, st);
-    if (bn == 128) return launch_gemm<128, 64>(tmA, tmB, kp, st);
-    return launch_gemm<64, 64>(tmA, tmB, kp, st);
+    if (bn == 256) return launch_gemm<256, 64>(tmA, tmB, tmOut, tmOut2, tmIn, kp, st);
+    if (bn == 128) return launch_gemm<128, 64>(tmA, tmB, tmOut, tmOut2, tmIn, kp, st);
+    return launch_gemm<64, 64>(tmA, tmB, tmOut, tmOut2, tmIn, kp, st);
   }
 }
 
