@@ -289,6 +289,18 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = B * world / (float(t.item()) / args.steps * 1e-3)
 
+    ar_ms = None
+    if world > 1:   # the one collective of the path, timed alone (device events, max over ranks)
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            grads.all_reduce(world)
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ar_ms = float(t.item()) / args.steps
+
     if rank == 0:
         peaks = measured_peaks()
         L0 = sum(wl['seq_lens']) + 2 + wl['L_ns']
@@ -304,6 +316,8 @@ def main():
             'e2e': {'value': e2e_value, 'unit': 'samples/s', 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': 4},
             'gpu_launches': launches,
             'loss': float(loss),
+            'grad_allreduce': None if ar_ms is None else {'ms': ar_ms, 'bytes': grads.flat.numel() * 4,
+                                                          'algbw_gbs': grads.flat.numel() * 4 / (ar_ms * 1e-3) / 1e9},
             'model_flops': {'algorithmic_tflop_per_step_per_gpu': step_tflop, 'achieved_tflops_per_gpu': step_tflop / (ms_step * 1e-3),
                             'frac_of_bf16_sustained_peak': step_tflop / (ms_step * 1e-3) / peaks['tf_sustained'], 'peak_source': peaks['src']},
         }

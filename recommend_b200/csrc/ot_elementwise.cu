@@ -38,8 +38,27 @@ rmsnorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const flo
   const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long n_warps = (long long)gridDim.x * (blockDim.x >> 5);
   const int nch = d >> 3;
+  // one row ahead in registers: with one 16-byte load per lane and row, a warp would otherwise have 512 bytes in
+  // flight, 32 KB per SM at full occupancy - not enough to cover the HBM latency at 6.5 TB/s
+  uint4 nxt[NCH];
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) {
+    const int ch = lane + 32 * i;
+    nxt[i] = make_uint4(0, 0, 0, 0);
+    if (warp_global < rows && ch < nch) nxt[i] = reinterpret_cast<const uint4*>(x + warp_global * ldx)[ch];
+  }
   for (long long row = warp_global; row < rows; row += n_warps) {
-    const uint4* xr = reinterpret_cast<const uint4*>(x + row * ldx);
+    uint4 cur[NCH];
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) cur[i] = nxt[i];
+    const long long nrow = row + n_warps;
+    if (nrow < rows) {
+#pragma unroll
+      for (int i = 0; i < NCH; ++i) {
+        const int ch = lane + 32 * i;
+        if (ch < nch) nxt[i] = reinterpret_cast<const uint4*>(x + nrow * ldx)[ch];
+      }
+    }
     float v[NCH][8];
     float ss = 0.0f;
 #pragma unroll
@@ -51,7 +70,7 @@ rmsnorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const flo
           const float4 a = hr[0], b = hr[1];
           v[i][0] = a.x; v[i][1] = a.y; v[i][2] = a.z; v[i][3] = a.w; v[i][4] = b.x; v[i][5] = b.y; v[i][6] = b.z; v[i][7] = b.w;
         } else {
-          unpack8(xr[ch], v[i]);
+          unpack8(cur[i], v[i]);
         }
 #pragma unroll
         for (int e = 0; e < 8; ++e) ss += v[i][e] * v[i][e];
@@ -98,10 +117,30 @@ rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long lddy, const _
 #pragma unroll
     for (int e = 0; e < 8; ++e) dg_acc[i][e] = 0.0f;
 
+  // one row ahead in registers (x, dy, dres and rstd of the next row are in flight while this one is reduced)
+  uint4 nx[NCH], ndy[NCH], nres[NCH];
+  float nr = 0.0f;
+  auto prefetch = [&](long long row) {
+    nr = rstd[row];
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      const int ch = lane + 32 * i;
+      if (ch < nch) {
+        nx[i] = reinterpret_cast<const uint4*>(x + row * ldx)[ch];
+        ndy[i] = reinterpret_cast<const uint4*>(dy + row * lddy)[ch];
+        if (dres != nullptr) nres[i] = reinterpret_cast<const uint4*>(dres + row * lddres)[ch];
+      }
+    }
+  };
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) { nx[i] = make_uint4(0, 0, 0, 0); ndy[i] = nx[i]; nres[i] = nx[i]; }
+  if (warp_global < rows) prefetch(warp_global);
   for (long long row = warp_global; row < rows; row += n_warps) {
-    const uint4* xr = reinterpret_cast<const uint4*>(x + row * ldx);
-    const uint4* dyr = reinterpret_cast<const uint4*>(dy + row * lddy);
-    const float r = rstd[row];
+    uint4 cx[NCH], cdy[NCH], cres[NCH];
+    const float r = nr;
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) { cx[i] = nx[i]; cdy[i] = ndy[i]; cres[i] = nres[i]; }
+    if (row + n_warps < rows) prefetch(row + n_warps);
     float xh[NCH][8], dxh[NCH][8];
     float dot = 0.0f;
 #pragma unroll
@@ -109,8 +148,8 @@ rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long lddy, const _
       const int ch = lane + 32 * i;
       if (ch < nch) {
         float xv[8], dv[8];
-        unpack8(xr[ch], xv);
-        unpack8(dyr[ch], dv);
+        unpack8(cx[i], xv);
+        unpack8(cdy[i], dv);
         const float4 g0 = reinterpret_cast<const float4*>(g)[2 * ch], g1 = reinterpret_cast<const float4*>(g)[2 * ch + 1];
         const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
@@ -133,7 +172,7 @@ rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long lddy, const _
         for (int e = 0; e < 8; ++e) o[e] = r * (dxh[i][e] - xh[i][e] * dot);
         if (dres != nullptr) {
           float rv[8];
-          unpack8(reinterpret_cast<const uint4*>(dres + row * lddres)[ch], rv);
+          unpack8(cres[i], rv);
 #pragma unroll
           for (int e = 0; e < 8; ++e) o[e] += rv[e];
         }

@@ -47,14 +47,19 @@ class FlatGradBuffer:
     def zero(self) -> None:
         self.flat.zero_()
 
-    def all_reduce(self, world_size: int, bucket_bytes: int = 256 << 20) -> None:
-        """Sum over ranks then average.  Buckets keep each NCCL call in its high-bandwidth regime."""
+    def all_reduce(self, world_size: int, bucket_bytes: int = 0) -> None:
+        """Average over ranks (PAPER:190 data parallelism; the reference code is single-device).  On NCCL the
+        averaging rides in the collective (``ReduceOp.AVG``), so the 4 B/parameter scaling pass disappears; one call
+        over the whole buffer unless ``bucket_bytes`` asks for pieces."""
         if world_size <= 1:
             return
-        n_per = max(1, bucket_bytes // 4)
+        nccl = dist.get_backend() == 'nccl'
+        op = dist.ReduceOp.AVG if nccl else dist.ReduceOp.SUM
+        n_per = self.flat.numel() if bucket_bytes <= 0 else max(1, bucket_bytes // 4)
         for s in range(0, self.flat.numel(), n_per):
-            dist.all_reduce(self.flat[s:s + n_per], op=dist.ReduceOp.SUM)
-        self.flat.mul_(1.0 / world_size)
+            dist.all_reduce(self.flat[s:s + n_per], op=op)
+        if not nccl:
+            self.flat.mul_(1.0 / world_size)
 
 
 class ClipRMSprop:
