@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define OT_ABI_VERSION 4
+#define OT_ABI_VERSION 5
 
 int ot_version(void);
 const char* ot_last_error_string(void);
@@ -125,6 +125,10 @@ typedef struct ot_wgrad_params {
   const float* p_row_scale;  /* optional: P rows scaled... reserved, must be NULL */
   int32_t block_n;           /* 0 = choose */
   int32_t target_ctas;       /* 0 = 2 waves of the device */
+  /* optional bias gradient riding on the same pass (OT/train.py:131 for the Dense biases of OT/model.py:137-145):
+   * q_colsum[g * q_colsum_group_stride + n] += sum_rows Q[row, n], fp32 atomics, caller zeroes; NULL = off */
+  float* q_colsum;
+  int64_t q_colsum_group_stride;
 } ot_wgrad_params;
 
 int ot_wgrad(const ot_wgrad_params* p, void* stream);

@@ -39,7 +39,7 @@ class WgradSeg(C.Structure):
 class WgradParams(C.Structure):
     _fields_ = [('Mdim', i32), ('Ndim', i32), ('n_segs', i32), ('swizzle', i32), ('segs', WgradSeg * 2),
                 ('C', fp), ('c_group_stride', i64), ('c_stride_m', i64), ('c_stride_n', i64),
-                ('p_row_scale', fp), ('block_n', i32), ('target_ctas', i32)]
+                ('p_row_scale', fp), ('block_n', i32), ('target_ctas', i32), ('q_colsum', fp), ('q_colsum_group_stride', i64)]
 
 
 class AttnParams(C.Structure):

@@ -10,6 +10,8 @@
 // into slices so that the launch fills the device about twice; every CTA keeps its accumulator in
 // TMEM for its whole slice and flushes once with fp32 atomics (the caller zeroes C).
 //   warp 0 lane*: TMA producer     warp 1 lane*: MMA issuer     all 4 warps: epilogue
+//   warps 2-3 (CTAs of the first M tile, when asked): column sums of the Q tiles as they pass through shared
+//   memory - the bias gradient of the same Dense layer without a second pass over Q
 #include "ot_common.cuh"
 #include "ot_host.h"
 #include "../../include/onetrans_b200.h"
@@ -34,6 +36,8 @@ struct WgradKParams {
   WgradSegDev segs[2];
   float* C;
   long long c_group_stride, c_stride_m, c_stride_n;
+  float* q_colsum;
+  long long q_colsum_group_stride;
 };
 
 template <int BN, int SWB>
@@ -87,6 +91,10 @@ ot_wgrad_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constant_
   const int group = sg.group_start + out_idx * sg.group_stride;
   const CUtensorMap* tmP = s == 0 ? &tmP0 : &tmP1;
   const CUtensorMap* tmQ = s == 0 ? &tmQ0 : &tmQ1;
+  // the column sums of a 64-row k-block are shared out over the CTAs of up to 8 M tiles (they all stream the same Q tile)
+  int m_split = 1;
+  while (m_split * 2 <= p.m_tiles && m_split < 8) m_split *= 2;
+  const bool do_colsum = (p.q_colsum != nullptr) && (mt < m_split);
 
   if (threadIdx.x == 0) {
     if ((smem_u32(smem) & 1023u) != 0) __trap();
@@ -94,7 +102,7 @@ ot_wgrad_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constant_
     tma_prefetch_desc(tmQ);
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&empty_bar[i], do_colsum ? 3 : 1);   // tcgen05.commit (+ the two column-sum warps)
     }
     mbar_init(done_bar, 1);
     fence_mbar_init();
@@ -153,6 +161,37 @@ ot_wgrad_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constant_
         }
         umma_commit(done_bar);
       }
+    } else if (do_colsum) {
+      // warps 2-3: thread t owns one 16-byte chunk (8 columns) of the Q tile and a group of its 64 rows
+      constexpr int NCHK = BN / 8;                    // 16-byte chunks per tile row (8, 16 or 32)
+      constexpr int RG = 64 / NCHK;                   // row groups: 64 threads = NCHK chunks x RG groups
+      constexpr int CPS = Cfg::SLAB_COLS / 8;         // chunks per slab row
+      const int t = threadIdx.x - 64;
+      const int chk = t % NCHK, rg = t / NCHK;
+      const int slab = chk / CPS, cin = chk % CPS;
+      const int n_r = (WG_KROWS / m_split) / RG;      // rows per thread and k-block (>= 1: m_split <= 8 <= 64 / RG)
+      const int r_begin = mt * (WG_KROWS / m_split) + rg * n_r;
+      float acc[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = 0.0f;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int i = 0; i < num_kb; ++i) {
+        mbar_wait(&full_bar[stage], phase);
+        const uint8_t* sq = smem + stage * Cfg::STAGE_BYTES + Cfg::P_BYTES + slab * Cfg::SLAB_BYTES;
+#pragma unroll 4
+        for (int r = r_begin; r < r_begin + n_r; ++r) {
+          const uint4 q = *reinterpret_cast<const uint4*>(sq + swz_off<SWB>(r, cin));
+          acc[0] += bf16lo(q.x); acc[1] += bf16hi(q.x); acc[2] += bf16lo(q.y); acc[3] += bf16hi(q.y);
+          acc[4] += bf16lo(q.z); acc[5] += bf16hi(q.z); acc[6] += bf16lo(q.w); acc[7] += bf16hi(q.w);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      float* dst = p.q_colsum + (long long)group * p.q_colsum_group_stride + nt * BN + chk * 8;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) atomicAdd(dst + e, acc[e]);
     }
     // ---- epilogue: every warp flushes its 32 accumulator rows ----
     mbar_wait(done_bar, 0);
@@ -205,6 +244,7 @@ int wgrad_impl(const ot_wgrad_params* p, cudaStream_t st) {
   kp.Mdim = p->Mdim; kp.Ndim = p->Ndim; kp.m_tiles = p->Mdim / 128; kp.n_tiles = p->Ndim / bn;
   kp.n_segs = p->n_segs; kp.C = p->C;
   kp.c_group_stride = p->c_group_stride; kp.c_stride_m = p->c_stride_m; kp.c_stride_n = p->c_stride_n;
+  kp.q_colsum = p->q_colsum; kp.q_colsum_group_stride = p->q_colsum_group_stride;
   const int tiles = kp.m_tiles * kp.n_tiles;
   const int target = p->target_ctas > 0 ? p->target_ctas : 2 * num_sms();
 

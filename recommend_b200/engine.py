@@ -170,12 +170,10 @@ def ffn_backward(dy: torch.Tensor, zn: torch.Tensor, saved, w: BlockWeights, seg
     rows_t, d = zn.shape
     F = pre.shape[1]
     dev = zn.device
-    ops.colsum(dy, segs, b2_grad, d)
-    ops.wgrad_rows(h, dy, segs, W2_grad, F * d, d, 1)
+    ops.wgrad_rows(h, dy, segs, W2_grad, F * d, d, 1, q_colsum=b2_grad, q_colsum_group_stride=d)   # dW2 and db2
     dpre = torch.empty(rows_t, F, dtype=bf16, device=dev)
     ops.mixed_gemm(dy, w.W2_b, segs, dpre, flags=OT_EPI_GELU_GRAD, aux=pre)
-    ops.colsum(dpre, segs, b1_grad, F)
-    ops.wgrad_rows(zn, dpre, segs, W1_grad, d * F, F, 1)
+    ops.wgrad_rows(zn, dpre, segs, W1_grad, d * F, F, 1, q_colsum=b1_grad, q_colsum_group_stride=F)  # dW1 and db1
     dzn = torch.empty(rows_t, d, dtype=bf16, device=dev)
     ops.mixed_gemm(dpre, w.W1_b, segs, dzn)
     return dzn

@@ -155,6 +155,7 @@ class MixedMHA(nn.Module):
 class _MHAFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x2, Wqkv, Wo, mod: MixedMHA, B, cur, keep, prefix):
+        ctx.set_materialize_grads(False)   # no zero tensors for the (k, v) output nobody differentiates
         w = _weights_of(mod, None)
         cfg = mod.config
         out, saved, _ = engine.mha_forward(x2, None, w, B, cur, keep, cfg.num_heads, cfg.num_ns_tokens,
@@ -168,6 +169,8 @@ class _MHAFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout, _dkv):
+        if dout is None:
+            return (None,) * 8
         x2, saved, w, mod, B, cur, keep = ctx.saved
         dxn = engine.mha_backward(dout.contiguous(), x2, saved, w, engine._grad_buf(mod.Wqkv), engine._grad_buf(mod.Wo),
                                   B, cur, keep, mod.config.num_heads)
@@ -309,6 +312,9 @@ class OneTransBlock(nn.Module):
 class _BlockFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x2, anchor, blk: OneTransBlock, B, cur, keep, kv_prefix, x_hp, drop):
+        # without this autograd fills a [cur*B, 2d] bf16 and a [L_NS*B, d] fp32 zero tensor per block and step for the
+        # two outputs nobody differentiates (1.3 ms/step at C2, profiles/README.md)
+        ctx.set_materialize_grads(False)
         cfg = blk.config
         need_grad = any(ctx.needs_input_grad)
         if need_grad and kv_prefix is not None:
@@ -326,6 +332,8 @@ class _BlockFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy, _dkv, _dhp):
+        if dy is None:
+            return (None,) * 9
         saved, w, blk, B, cur, keep = ctx.saved
         dx = engine.block_backward(dy, saved, blk._params(), w, B, cur, keep, blk.config.num_heads)
         ctx.saved = None
@@ -397,6 +405,7 @@ class Tokenizer(nn.Module):
 class _TokenizerFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, anchor, tok: Tokenizer, ns_x, seq_list, B):
+        ctx.set_materialize_grads(False)
         cfg = tok.config
         d, L_ns = cfg.hidden_dim, cfg.num_ns_tokens
         X0, L, layout, X_hp = engine.tokenizer_forward(ns_x, seq_list, B, d, L_ns, tok._seq_weights(),
@@ -410,6 +419,8 @@ class _TokenizerFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dX0, _dL=None, _dhp=None):
+        if dX0 is None:
+            return None, None, None, None, None
         tok, ns_x, seq_list, layout, B = ctx.saved
         cfg = tok.config
         engine.tokenizer_backward(dX0, ns_x, seq_list, layout, B, cfg.hidden_dim, cfg.num_ns_tokens, list(tok.seq_kernels),

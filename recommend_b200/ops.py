@@ -164,10 +164,12 @@ WSeg = Tuple[torch.Tensor, int, int, torch.Tensor, int, int, int, int, int, int]
 
 
 def wgrad(segs: Sequence[dict], Cout: torch.Tensor, Mdim: int, Ndim: int, c_group_stride: int, c_stride_m: int,
-          c_stride_n: int, *, block_n: int = 0, swizzle: int = 0, target_ctas: int = 0) -> None:
+          c_stride_n: int, *, block_n: int = 0, swizzle: int = 0, target_ctas: int = 0,
+          q_colsum: Optional[torch.Tensor] = None, q_colsum_group_stride: int = 0) -> None:
     """``Cout[g][m, n] += sum_rows P[row, m] * Q[row, n]``; each seg is a dict with keys
     P, p_stride_row, p_stride_unit, Q, q_stride_row, q_stride_unit, n_units, rows_per_unit, group_start,
-    group_stride.  ``Cout`` is an fp32 tensor (any view); strides in elements."""
+    group_stride.  ``Cout`` is an fp32 tensor (any view); strides in elements.  ``q_colsum`` (fp32, optional) also
+    receives ``sum_rows Q[row, n]`` per group - the bias gradient of the same Dense layer, for free."""
     assert Cout.dtype == torch.float32 and Cout.is_cuda
     p = L.WgradParams()
     p.Mdim, p.Ndim, p.n_segs, p.swizzle = Mdim, Ndim, len(segs), swizzle
@@ -182,6 +184,9 @@ def wgrad(segs: Sequence[dict], Cout: torch.Tensor, Mdim: int, Ndim: int, c_grou
     p.C = Cout.data_ptr()
     p.c_group_stride, p.c_stride_m, p.c_stride_n = c_group_stride, c_stride_m, c_stride_n
     p.block_n, p.target_ctas = block_n, target_ctas
+    if q_colsum is not None:
+        assert q_colsum.dtype == torch.float32 and q_colsum.is_cuda
+        p.q_colsum, p.q_colsum_group_stride = q_colsum.data_ptr(), q_colsum_group_stride
     rows = sum(s['n_units'] * s['rows_per_unit'] for s in segs)
     groups = sum((s['n_units'] if s['group_stride'] else 1) for s in segs)
     _run('ot_wgrad', L.load().ot_wgrad, p, f'M{Mdim}_N{Ndim}', 2.0 * rows * Mdim * Ndim,
@@ -189,7 +194,7 @@ def wgrad(segs: Sequence[dict], Cout: torch.Tensor, Mdim: int, Ndim: int, c_grou
 
 
 def wgrad_rows(P: torch.Tensor, Q: torch.Tensor, segs: Sequence[Seg], Cout: torch.Tensor, c_group_stride: int,
-               c_stride_m: int, c_stride_n: int) -> None:
+               c_stride_m: int, c_stride_n: int, q_colsum: Optional[torch.Tensor] = None, q_colsum_group_stride: int = 0) -> None:
     """Weight gradient for row-aligned 2-D activations ``P [rows, Mdim]`` and ``Q [rows, Ndim]`` whose
     rows are described by the same position segments the forward GEMM used."""
     wsegs = []
@@ -197,7 +202,8 @@ def wgrad_rows(P: torch.Tensor, Q: torch.Tensor, segs: Sequence[Seg], Cout: torc
         wsegs.append(dict(P=P[row_start:], p_stride_row=P.stride(0), p_stride_unit=rpu * P.stride(0),
                           Q=Q[row_start:], q_stride_row=Q.stride(0), q_stride_unit=rpu * Q.stride(0),
                           n_units=n_units, rows_per_unit=rpu, group_start=g0, group_stride=gs))
-    wgrad(wsegs, Cout, P.shape[1], Q.shape[1], c_group_stride, c_stride_m, c_stride_n)
+    wgrad(wsegs, Cout, P.shape[1], Q.shape[1], c_group_stride, c_stride_m, c_stride_n, q_colsum=q_colsum,
+          q_colsum_group_stride=q_colsum_group_stride)
 
 
 def attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, o: torch.Tensor, lse: torch.Tensor, B: int, H: int,

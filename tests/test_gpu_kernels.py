@@ -124,6 +124,29 @@ def test_wgrad_grouped(B, n_s, n_ns):
     assert ((C - 2 * ref).abs().max() / ref.abs().max()).item() < 2e-3
 
 
+@pytest.mark.parametrize('B,n_s,n_ns,M,N,bn', [(32, 9, 4, 256, 512, 0), (200, 7, 3, 128, 1024, 0), (2048, 3, 2, 1024, 256, 0),
+                                                (96, 5, 2, 256, 128, 128), (40, 3, 1, 128, 64, 64)])
+def test_wgrad_with_bias_gradient(B, n_s, n_ns, M, N, bn):
+    """The same pass also delivers the Dense bias gradient: column sums of Q per weight group."""
+    rows = (n_s + n_ns) * B
+    P, Q = rnd(rows, M, seed=21), rnd(rows, N, seed=22)
+    C = torch.zeros(1 + n_ns, M, N, device='cuda')
+    db = torch.zeros(1 + n_ns, N, device='cuda')
+    segs = [(0, 1, n_s * B, 0, 0), (n_s * B, n_ns, B, 1, 1)]
+    wsegs = [dict(P=P[r0:], p_stride_row=M, p_stride_unit=rpu * M, Q=Q[r0:], q_stride_row=N, q_stride_unit=rpu * N,
+                  n_units=nu, rows_per_unit=rpu, group_start=g0, group_stride=gs) for (r0, nu, rpu, g0, gs) in segs]
+    ops.wgrad(wsegs, C, M, N, M * N, N, 1, block_n=bn, q_colsum=db, q_colsum_group_stride=N)
+    ref, dref = torch.zeros_like(C), torch.zeros_like(db)
+    ref[0] = P[:n_s * B].float().t() @ Q[:n_s * B].float()
+    dref[0] = Q[:n_s * B].float().sum(0)
+    for j in range(n_ns):
+        sl = slice((n_s + j) * B, (n_s + j + 1) * B)
+        ref[1 + j] = P[sl].float().t() @ Q[sl].float()
+        dref[1 + j] = Q[sl].float().sum(0)
+    assert ((C - ref).abs().max() / ref.abs().max()).item() < 2e-3
+    assert ((db - dref).abs().max() / dref.abs().max()).item() < 1e-4
+
+
 def attn_ref(q, k, v, B, H, Lq, Lk, dh):
     d = H * dh
     q4 = q.float().view(Lq, B, H, dh).permute(1, 2, 0, 3)
