@@ -73,7 +73,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def window(self, t0: float, t1: float):
+        """Keep only the samples that arrived inside [t0, t1] (host clock around the synchronised timed region)."""
+        self.t0, self.t1 = t0, t1
 
     def stop(self):
         if self.proc is None:
@@ -85,7 +89,11 @@ class ClockSampler:
             self.proc.kill()
         sm, smax, reasons = [], [], set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for r in self.rows:
+        t0, t1 = getattr(self, 't0', None), getattr(self, 't1', None)
+        rows = [r for (t, r) in self.rows if t0 is None or t0 <= t <= t1 + 0.15]
+        if not rows:      # very short timed regions: fall back to every sample taken under load (warm-up included)
+            rows = [r for (_, r) in self.rows]
+        for r in rows:
             parts = [x.strip() for x in r.split(',')]
             if len(parts) < 7:
                 continue
@@ -166,6 +174,7 @@ def config_dict(args, wl, B):
             'global_batch': B * args.gpus, 'seq_tokens': sum(wl['seq_lens']) + 2, 'ns_tokens': wl['L_ns'],
             'parallelism': f'dp{args.gpus}', 'dropout': args.dropout,
             'optimizer': 'clip_by_norm 90 + RMSprop inside the timed step' if args.optimizer else 'none (metric is fwd+bwd)',
+            'inputs': 'pre-embedded events bf16 [B, L_i, 64] x3, 11 fp32 scalars, 2 fp32 labels per sample (pinned host buffers in the e2e arm)',
             'l2_policy': 'activations per step (>20 GB) far exceed the 126 MB L2; no explicit flush'}
 
 
@@ -202,7 +211,7 @@ def main():
     import torch.distributed as dist
     import recommend_b200 as R
     from recommend_b200 import _lib, ops
-    from recommend_b200.train import FlatGradBuffer, ClipRMSprop, bce_loss, train_step
+    from recommend_b200.train import FlatGradBuffer, ClipRMSprop, bce_loss, train_loop, train_step
     from oracle import onetrans_oracle as O  # synthetic input generator only (and the cpu_baseline leg below)
 
     if not torch.cuda.is_available():
@@ -241,30 +250,33 @@ def main():
     def step_device():
         return train_step(model, grads, d_ns, d_seq, d_lab, world, opt)
 
-    def step_e2e():
-        ns = {k: v.to(dev, non_blocking=True) for k, v in h_ns.items()}
-        sq = {k: v.to(dev, non_blocking=True) for k, v in h_seq.items()}
-        lb = {k: v.to(dev, non_blocking=True) for k, v in h_lab.items()}
-        loss = train_step(model, grads, ns, sq, lb, world, opt)
-        return float(loss)     # device->host read of the step's result
+    def run_e2e(n_steps):
+        """The user-facing loop (recommend_b200.train.train_loop): pinned host batches -> device (copies of step i+1
+        overlap step i) -> train_step -> every step's loss read back on the host (one step behind the queue).
+        Every step's inputs cross PCIe and every step's loss reaches the host inside the timed region."""
+        losses = train_loop(model, grads, ((h_ns, h_seq, h_lab) for _ in range(n_steps)), world, opt, dev)
+        assert len(losses) == n_steps
+        return losses[-1]
 
     # ---- device-resident timing ----
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()       # nvidia-smi needs a few hundred ms to start: launch it before the warm-up, window it below
     for _ in range(max(3, args.warmup)):
         step_device()
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     launches0 = _lib.launch_count
     prof = None if args.no_kernel_profile else ops.KernelProfiler()
     ops.set_profiler(prof)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_host0 = time.perf_counter()
     e0.record()
     for _ in range(args.steps):
         loss = step_device()
     e1.record()
     barrier()
+    sampler.window(t_host0, time.perf_counter())
     ops.set_profiler(None)
     ms_total = e0.elapsed_time(e1)
     launches = _lib.launch_count - launches0
@@ -276,12 +288,10 @@ def main():
     value = B * world / (ms_step * 1e-3)
 
     # ---- end-to-end timing (host buffers -> public API -> loss on host) ----
-    for _ in range(2):
-        step_e2e()
+    run_e2e(2)
     barrier()
     e0.record()
-    for _ in range(args.steps):
-        step_e2e()
+    run_e2e(args.steps)
     e1.record()
     barrier()
     t = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -355,7 +365,7 @@ def main():
             roof.update({'kernel': f'{name}[{tag}]', 'launches': dmn['launches'], 'avg_launch_us': dmn['ms'] * 1e3 / dmn['launches'],
                          'algorithmic_bytes_per_launch': dmn['bytes'] / dmn['launches'], 'algorithmic_flops_per_launch': dmn['flops'] / dmn['launches'],
                          'peak_source': peaks['src'] + (' (sustained bf16)' if roof['bound'] == 'tensor' else ' (copy bandwidth)'),
-                         'traffic': load_ncu_traffic(name)})
+                         'traffic': load_ncu_traffic(name, tag, dmn['bytes'] / dmn['launches'])})
             line['roofline'] = roof
         if world == 1 and not args.no_cpu_baseline:
             v, ms, cores = cpu_oracle_samples_per_sec(wl, args.cpu_sample_batch, 2, 1, args.dropout)
@@ -367,15 +377,22 @@ def main():
         dist.destroy_process_group()
 
 
-def load_ncu_traffic(kernel_name):
-    """dram bytes per launch of the dominant kernel from the committed ncu capture (profiles/), or None."""
+def load_ncu_traffic(family, tag=None, algorithmic_bytes_per_launch=None):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/ncu_traffic.json), or None.
+    The capture holds layer-0 shapes; for a (family, shape) bucket averaged over layers the measured
+    traffic / algorithmic ratio of that shape is applied to the bucket's algorithmic bytes per launch."""
     path = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
-    if os.path.exists(path):
-        try:
-            return json.load(open(path)).get(kernel_name)
-        except Exception:
-            return None
-    return None
+    if not os.path.exists(path):
+        return None
+    try:
+        d = json.load(open(path))
+        e = d.get(f'{family}[{tag}]')
+        if isinstance(e, dict) and e.get('traffic_over_algorithmic') and algorithmic_bytes_per_launch:
+            return e['traffic_over_algorithmic'] * algorithmic_bytes_per_launch
+        v = d.get(family)
+        return v if isinstance(v, (int, float)) else None
+    except Exception:
+        return None
 
 
 if __name__ == '__main__':

@@ -1,0 +1,64 @@
+"""Reduce an `ncu --set full` report to the handful of metrics DESIGN.md / README.md quote, one row per launch, and
+write the per-kernel DRAM traffic table bench.py reads for `roofline.traffic`.
+usage: python profiles/ncu_summary.py gpurun_out/prof.ncu-rep profiles/r1_ncu_summary.csv [profiles/ncu_traffic.json
+       gpurun_out/prof_kernels_all.json]   (the last file is prof_kernels.py's launch list: shape tags + algorithmic bytes)"""
+import csv, json, subprocess, sys
+
+METRICS = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
+           'dram__throughput.avg.pct_of_peak_sustained_elapsed', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
+           'sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active',
+           'sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active',
+           'lts__t_sector_hit_rate.pct', 'inst_executed', 'launch__registers_per_thread', 'launch__grid_size', 'launch__block_size',
+           'smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio',
+           'smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio',
+           'smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio',
+           'smsp__average_warps_issue_stalled_wait_per_issue_active.ratio']
+FAMILY = {'ot_mixed_gemm_kernel': 'ot_mixed_gemm', 'ot_wgrad_kernel': 'ot_wgrad', 'ot_attn_fwd_ws_kernel': 'ot_attn_fwd',
+          'ot_attn_fwd_kernel': 'ot_attn_fwd', 'ot_attn_bwd_fused_kernel': 'ot_attn_bwd', 'rmsnorm_fwd_kernel': 'ot_rmsnorm_fwd',
+          'rmsnorm_bwd_kernel': 'ot_rmsnorm_bwd'}
+
+rep, out_csv = sys.argv[1], sys.argv[2]
+raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+rows = list(csv.reader(raw.splitlines()))
+hdr, units, data = rows[0], rows[1], rows[2:]
+cols = [m for m in METRICS if m in hdr]
+traffic = {}
+with open(out_csv, 'w', newline='') as f:
+    w = csv.writer(f)
+    w.writerow(['id', 'kernel'] + [f'{m} [{units[hdr.index(m)]}]' for m in cols])
+    for r in data:
+        name = r[hdr.index('Kernel Name')]
+        short = name.split('(')[0].replace('void ', '').replace('ot::', '')
+        w.writerow([r[0], short] + [r[hdr.index(m)] for m in cols])
+        fam = next((v for k, v in FAMILY.items() if k in name), None)
+        if fam:
+            def gb(m):
+                v, u = float(r[hdr.index(m)].replace(',', '')), units[hdr.index(m)]
+                return v * {'Gbyte': 1e9, 'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1.0, 'Tbyte': 1e12}[u]
+            t = gb('dram__bytes_read.sum') + gb('dram__bytes_write.sum')
+            traffic.setdefault(fam, []).append({'kernel': short, 'dram_bytes': t,
+                                                'time_us': float(r[hdr.index('gpu__time_duration.sum')].replace(',', '')) *
+                                                {'ms': 1e3, 'us': 1.0, 'ns': 1e-3, 's': 1e6}[units[hdr.index('gpu__time_duration.sum')]]})
+print(f'wrote {out_csv}: {len(data)} launches, {len(cols)} metrics')
+if len(sys.argv) > 3:
+    out = {}
+    if len(sys.argv) > 4:
+        # join with prof_kernels.py's own launch list (same order per family): traffic / algorithmic bytes per shape
+        launches = json.load(open(sys.argv[4]))
+        per_fam = {}
+        for l in launches:
+            per_fam.setdefault(l['kernel'], []).append(l)
+        for fam, v in traffic.items():
+            ls = per_fam.get(fam, [])
+            if len(ls) != len(v):
+                continue
+            for l, m in zip(ls, v):
+                m['tag'], m['algorithmic_bytes'] = l['tag'], l['bytes']
+                out[f"{fam}[{l['tag']}]"] = {'dram_bytes': m['dram_bytes'], 'algorithmic_bytes': l['bytes'],
+                                             'traffic_over_algorithmic': m['dram_bytes'] / l['bytes'] if l['bytes'] else None}
+    for fam, v in traffic.items():   # one number per family as well: the launch with the largest traffic
+        out[fam] = max(v, key=lambda d: d['dram_bytes'])['dram_bytes']
+    out['_detail'] = traffic
+    out['_note'] = 'dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, layer-0 shapes of C2 (profiles/prof_kernels.py)'
+    json.dump(out, open(sys.argv[3], 'w'), indent=1)
+    print('wrote', sys.argv[3])

@@ -9,6 +9,8 @@ from recommend_b200 import ops
 from recommend_b200._lib import OT_EPI_BIAS, OT_EPI_GELU, OT_EPI_GELU_GRAD, OT_EPI_RESIDUAL
 
 what = sys.argv[1] if len(sys.argv) > 1 else 'all'
+prof = ops.KernelProfiler()      # records (family, shape tag, algorithmic flops / bytes) of every launch, in order
+ops.set_profiler(prof)
 bf16 = torch.bfloat16
 B, Lq, Lk, d, F, H = 2048, 458, 544, 256, 1024, 4
 rows = Lq * B
@@ -43,4 +45,7 @@ if what in ('attn', 'all'):
     for _ in range(2):
         ops.attn_bwd(q, kv[:, :d], kv[:, d:], o, lse, do, dq, dkv[:, :d], dkv[:, d:], delta, B, H, Lq, Lk, d // H)
 torch.cuda.synchronize()
+import json
+json.dump([{'kernel': n, 'tag': t, 'flops': fl, 'bytes': by} for (n, t, _e0, _e1, fl, by) in prof.records],
+          open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'gpurun_out', f'prof_kernels_{what}.json'), 'w'), indent=1)
 print('done')

@@ -62,6 +62,85 @@ class FlatGradBuffer:
             self.flat.mul_(1.0 / world_size)
 
 
+class DevicePrefetcher:
+    """Host -> device input pipeline for the train loop (the role of ``tf.data`` prefetching in OT/data_loader.py:
+    195-222): iterates ``(non_seq, seq, labels)`` dictionaries of pinned host tensors and hands out device copies,
+    always keeping the NEXT batch's copies in flight on a side stream so that they overlap the current step.
+    Two sets of device buffers are allocated once and reused alternately (no allocator traffic in steady state)."""
+
+    def __init__(self, batches, device: torch.device):
+        self.it = iter(batches)
+        self.device = device
+        self.copy_stream = torch.cuda.Stream(device=device)
+        self.slots = [None, None]
+        self.free_ev = [None, None]      # compute-stream event after the last step that read the slot
+        self.n = 0
+        self._next = None
+        self._preload()
+
+    def _preload(self) -> None:
+        try:
+            host = next(self.it)
+        except StopIteration:
+            self._next = None
+            return
+        k = self.n % 2
+        self.n += 1
+        if self.slots[k] is None or any(d[key].shape != h[key].shape or d[key].dtype != h[key].dtype
+                                        for d, h in zip(self.slots[k], host) for key in h):
+            self.slots[k] = tuple({key: torch.empty(v.shape, dtype=v.dtype, device=self.device) for key, v in h.items()} for h in host)
+        with torch.cuda.stream(self.copy_stream):
+            if self.free_ev[k] is not None:
+                self.copy_stream.wait_event(self.free_ev[k])
+            for d, h in zip(self.slots[k], host):
+                for key, v in h.items():
+                    d[key].copy_(v, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.copy_stream)
+        self._next = (k, ev)
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        if self._next is None:
+            raise StopIteration
+        k, ev = self._next
+        cur = torch.cuda.current_stream(self.device)
+        # everything enqueued so far (the previous step) read the OTHER slot: it may be overwritten once that is done
+        done = torch.cuda.Event()
+        done.record(cur)
+        self.free_ev[1 - k] = done
+        cur.wait_event(ev)
+        self._preload()
+        return self.slots[k]
+
+
+def train_loop(model, grads: FlatGradBuffer, host_batches, world_size: int = 1, optimizer: Optional['ClipRMSprop'] = None,
+               device: Optional[torch.device] = None) -> List[float]:
+    """The epoch loop of OT/train.py:186-232 around ``train_step``: pinned host batches in, per-step losses out.
+    Inputs of step i+1 are copied while step i runs (DevicePrefetcher); the loss of step i travels to pinned host
+    memory asynchronously and is read after step i+1 has been enqueued, so the host never drains the GPU queue
+    between steps.  Returns one Python float per step."""
+    device = device if device is not None else grads.flat.device
+    losses: List[float] = []
+    pending = None      # (pinned host scalar, event)
+    for non_seq, seq, labels in DevicePrefetcher(host_batches, device):
+        loss = train_step(model, grads, non_seq, seq, labels, world_size, optimizer)
+        h = torch.empty((), dtype=torch.float32, pin_memory=True)
+        h.copy_(loss, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        if pending is not None:
+            pending[1].synchronize()
+            losses.append(float(pending[0]))
+        pending = (h, ev)
+    if pending is not None:
+        pending[1].synchronize()
+        losses.append(float(pending[0]))
+    return losses
+
+
 class ClipRMSprop:
     """The dense-parameter update of the reference train step (OT/train.py:131-138): per-tensor
     ``tf.clip_by_norm(g, gradient_clip_norm)`` followed by Keras ``RMSprop(learning_rate, rho=0.9, momentum,
