@@ -38,6 +38,7 @@ struct WgradKParams {
   long long c_group_stride, c_stride_m, c_stride_n;
   float* q_colsum;
   long long q_colsum_group_stride;
+  int vec_flush;   // C rows are contiguous along n and 16-byte aligned: flush with 4-wide vector reductions
 };
 
 template <int BN, int SWB>
@@ -204,8 +205,16 @@ ot_wgrad_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constant_
       uint32_t v[32];
       tmem_ld_x32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + c * 32, v);
       tmem_ld_wait();
+      if (p.vec_flush) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) atomicAdd(crow + (long long)(c * 32 + j) * p.c_stride_n, __uint_as_float(v[j]));
+        for (int j = 0; j < 8; ++j)
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(crow + c * 32 + 4 * j), "f"(__uint_as_float(v[4 * j])),
+                       "f"(__uint_as_float(v[4 * j + 1])), "f"(__uint_as_float(v[4 * j + 2])), "f"(__uint_as_float(v[4 * j + 3]))
+                       : "memory");
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) atomicAdd(crow + (long long)(c * 32 + j) * p.c_stride_n, __uint_as_float(v[j]));
+      }
     }
   }
   tc_fence_before();
@@ -245,6 +254,8 @@ int wgrad_impl(const ot_wgrad_params* p, cudaStream_t st) {
   kp.n_segs = p->n_segs; kp.C = p->C;
   kp.c_group_stride = p->c_group_stride; kp.c_stride_m = p->c_stride_m; kp.c_stride_n = p->c_stride_n;
   kp.q_colsum = p->q_colsum; kp.q_colsum_group_stride = p->q_colsum_group_stride;
+  kp.vec_flush = (p->c_stride_n == 1 && (p->c_stride_m % 4) == 0 && (p->c_group_stride % 4) == 0 &&
+                  (reinterpret_cast<uintptr_t>(p->C) & 15) == 0) ? 1 : 0;
   const int tiles = kp.m_tiles * kp.n_tiles;
   const int target = p->target_ctas > 0 ? p->target_ctas : 2 * num_sms();
 

@@ -17,8 +17,12 @@ class KernelProfiler:
     """Optional per-launch CUDA-event timing on the launching stream (bench.py's roofline numbers).
     Each record: (kernel family, shape tag, start event, end event, algorithmic flops, algorithmic bytes)."""
 
-    def __init__(self):
+    def __init__(self, only: Optional[Tuple[str, str]] = None):
         self.records = []
+        self.only = only          # (family, shape tag): time just these launches (two event records each are not free)
+
+    def wants(self, name: str, tag: str) -> bool:
+        return self.only is None or self.only == (name, tag)
 
     def summary(self):
         """{(family, tag): dict(launches, ms, flops, bytes)} — call after torch.cuda.synchronize()."""
@@ -42,6 +46,8 @@ def set_profiler(p: Optional[KernelProfiler]) -> None:
 
 def _run(name: str, fn, p, tag: str = '', flops: float = 0.0, nbytes: float = 0.0, n_launch: int = 1) -> None:
     prof = _PROFILER
+    if prof is not None and not prof.wants(name, tag):
+        prof = None
     if prof is not None:
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
@@ -323,6 +329,8 @@ def dropout_mask(inp: torch.Tensor, seed: int, rate: float) -> torch.Tensor:
     _check_bf16(inp, 'inp')
     out = torch.empty_like(inp)
     prof = _PROFILER
+    if prof is not None and not prof.wants('ot_dropout_mask', f'N{inp.shape[1]}'):
+        prof = None
     if prof is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
