@@ -12,6 +12,12 @@ def short(n):
     return re.sub(r'<.*', '', n) if n.startswith('at::') or 'cutlass' in n or 'cublas' in n else n
 
 
+# keep whole steps only: every step starts with the memset of the flat fp32 gradient buffer (FillFunctor<float>, > 100k blocks)
+starts = [i for i, r in enumerate(data) if 'FillFunctor<float>' in r[kn] and int(r[g].strip('()').split(',')[0]) > 100000]
+starts = [s0 for j, s0 in enumerate(starts) if j + 1 == len(starts) or starts[j + 1] - s0 > 10]   # (the buffer's own zero-init)
+if len(starts) >= 2:
+    data = data[starts[0]:starts[-1]]
+    print(f'{len(starts) - 1} complete step(s): launches {starts[0]}..{starts[-1] - 1}')
 agg, tot = collections.OrderedDict(), 0.0
 with open(sys.argv[2], 'w', newline='') as f:
     w = csv.writer(f)
