@@ -37,12 +37,14 @@ static constexpr int CH_BYTES = 128 * 64 * 2;   // one staged chunk: 128 rows x 
 struct GemmSegDev {
   int row_start, n_units, rows_per_unit, group_start, group_stride, a_row_start;
   int mblk_start, mblk_per_unit;
+  uint32_t mpu_rcp;        // ceil(2^32 / mblk_per_unit): unit = umulhi(local, mpu_rcp), exact for local < 2^32 / mblk_per_unit
 };
 
 struct GemmKParams {
   int N, K;
   int n_segs;
   int total_mblks, n_nblks;
+  uint32_t nn_rcp;         // ceil(2^32 / n_nblks)
   int a_transposed;
   int flags;
   GemmSegDev segs[3];
@@ -60,25 +62,34 @@ struct TileInfo {
   int row0, valid, group, a_c1, a_c2;
 };
 
+__device__ __forceinline__ int div_rcp(int n, uint32_t rcp, int d) {
+  return d == 1 ? n : static_cast<int>(__umulhi(static_cast<uint32_t>(n), rcp));
+}
+
+// Every epilogue warp decodes every tile, so this runs ~16 x tiles times per CTA: no divisions (host-made reciprocals)
+// and no dynamic indexing of the kernel parameters (that would copy the segment table to local memory).
 __device__ __forceinline__ TileInfo decode_tile(const GemmKParams& p, int mblk) {
-  int s = 0;
-  while (s + 1 < p.n_segs && mblk >= p.segs[s + 1].mblk_start) ++s;
-  const GemmSegDev& sg = p.segs[s];
-  const int local = mblk - sg.mblk_start;
-  const int unit = local / sg.mblk_per_unit;
-  const int sub = local - unit * sg.mblk_per_unit;
+  const bool s2 = p.n_segs > 2 && mblk >= p.segs[2].mblk_start;
+  const bool s1 = !s2 && p.n_segs > 1 && mblk >= p.segs[1].mblk_start;
+#define OT_SEG(f) (s2 ? p.segs[2].f : s1 ? p.segs[1].f : p.segs[0].f)
+  const int mblk_per_unit = OT_SEG(mblk_per_unit);
+  const int rows_per_unit = OT_SEG(rows_per_unit);
+  const int local = mblk - OT_SEG(mblk_start);
+  const int unit = div_rcp(local, OT_SEG(mpu_rcp), mblk_per_unit);
+  const int sub = local - unit * mblk_per_unit;
   const int riu = sub * BM;
   TileInfo t;
-  t.row0 = sg.row_start + unit * sg.rows_per_unit + riu;
-  t.valid = min(BM, sg.rows_per_unit - riu);
-  t.group = sg.group_start + unit * sg.group_stride;
+  t.row0 = OT_SEG(row_start) + unit * rows_per_unit + riu;
+  t.valid = min(BM, rows_per_unit - riu);
+  t.group = OT_SEG(group_start) + unit * OT_SEG(group_stride);
   if (!p.a_transposed) {
-    t.a_c1 = sg.a_row_start + unit * sg.rows_per_unit + riu;
+    t.a_c1 = OT_SEG(a_row_start) + unit * rows_per_unit + riu;
     t.a_c2 = 0;
   } else {
-    t.a_c1 = sg.a_row_start + unit;
+    t.a_c1 = OT_SEG(a_row_start) + unit;
     t.a_c2 = riu;
   }
+#undef OT_SEG
   return t;
 }
 
@@ -154,7 +165,7 @@ ot_mixed_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int mblk = tile / p.n_nblks;
+        const int mblk = div_rcp(tile, p.nn_rcp, p.n_nblks);
         const int nblk = tile - mblk * p.n_nblks;
         const TileInfo t = decode_tile(p, mblk);
         const int w_row = t.group * p.N + nblk * BN;
@@ -233,7 +244,7 @@ ot_mixed_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       return has_in && t.valid == BM && !(f_res && p.res_hp != nullptr && t.row0 >= p.hp_row0);
     };
     auto issue_in = [&](int tile) {            // IO thread only
-      const int mblk = tile / p.n_nblks;
+      const int mblk = div_rcp(tile, p.nn_rcp, p.n_nblks);
       const TileInfo t = decode_tile(p, mblk);
       if (tma_in_tile(t)) {
         mbar_arrive_expect_tx(in_bar, CH_BYTES);
@@ -244,7 +255,7 @@ ot_mixed_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      const int mblk = tile / p.n_nblks;
+      const int mblk = div_rcp(tile, p.nn_rcp, p.n_nblks);
       const int nblk = tile - mblk * p.n_nblks;
       const TileInfo t = decode_tile(p, mblk);
       const int n0 = nblk * BN;
@@ -471,12 +482,15 @@ int mixed_gemm_impl(const ot_gemm_params* p, cudaStream_t st) {
     d.row_start = sg.row_start; d.n_units = sg.n_units; d.rows_per_unit = sg.rows_per_unit;
     d.group_start = sg.group_start; d.group_stride = sg.group_stride; d.a_row_start = sg.a_row_start;
     d.mblk_start = mb; d.mblk_per_unit = (sg.rows_per_unit + BM - 1) / BM;
+    d.mpu_rcp = (uint32_t)(((1ull << 32) + d.mblk_per_unit - 1) / d.mblk_per_unit);
     mb += d.mblk_per_unit * sg.n_units;
     const int last_group = sg.group_start + (sg.n_units - 1) * sg.group_stride;
     if (sg.group_start < 0 || last_group >= p->n_groups)
       OT_FAIL(OT_ERR_INVALID_ARG, "ot_mixed_gemm: segment %d addresses weight group %d of %d", s, last_group, p->n_groups);
   }
   kp.total_mblks = mb; kp.n_nblks = p->N / bn;
+  kp.nn_rcp = (uint32_t)(((1ull << 32) + kp.n_nblks - 1) / kp.n_nblks);
+  if ((long long)mb * kp.n_nblks >= (1ll << 24)) OT_FAIL(OT_ERR_UNSUPPORTED_SHAPE, "ot_mixed_gemm: %lld tiles exceed the tile-index range", (long long)mb * kp.n_nblks);
   kp.out = (__nv_bfloat16*)p->out; kp.ldo = p->ldo; kp.out2 = (__nv_bfloat16*)p->out2; kp.ldo2 = p->ldo2;
   kp.res = (const __nv_bfloat16*)p->res; kp.ldr = p->ldr; kp.aux = (const __nv_bfloat16*)p->aux; kp.ldaux = p->ldaux;
   kp.bias = p->bias; kp.bias_group_stride = p->bias_group_stride; kp.row_scale = p->row_scale;
