@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define OT_ABI_VERSION 5
+#define OT_ABI_VERSION 6
 
 int ot_version(void);
 const char* ot_last_error_string(void);
@@ -57,6 +57,8 @@ enum {
   OT_EPI_RESIDUAL = 4,    /* + res[row, n]                                                          */
   OT_EPI_GELU_GRAD = 8,   /* v *= gelu_erf'(aux[row, n])                                            */
   OT_EPI_ROW_SCALE = 16,  /* v *= row_scale[row]   (applied first)                                  */
+  OT_EPI_NORM = 64,       /* second output norm_out = rmsnorm(out row) * norm_gain (RMSNorm.call, OT/model.py:19-23, fused into
+                             the producing GEMM); needs N == block_n <= 256 so that a tile holds whole rows               */
   OT_EPI_DROPOUT = 32     /* v = keep(row,n) ? v/(1-rate) : 0, after bias and before the residual add
                              (Keras inverted dropout on the branch output, OT/model.py:193,198)        */
 };
@@ -94,6 +96,13 @@ typedef struct ot_gemm_params {
   /* OT_EPI_DROPOUT: counter-based mask hash(seed, row, n); rate in [0, 1). */
   uint32_t drop_seed;
   float drop_rate;
+  /* OT_EPI_NORM: norm_out[row, n] = x[row, n] * rstd[row] * norm_gain[n] with rstd = rsqrt(mean_n(x^2) + norm_eps), where x
+   * is the row just written to `out` (the fp32 value on res_hp rows); rstd is stored to norm_rstd (fp32 [rows], may be
+   * NULL).  Not together with out2. */
+  void* norm_out; int64_t ld_norm;
+  const float* norm_gain;
+  float* norm_rstd;
+  float norm_eps;
 } ot_gemm_params;
 
 int ot_mixed_gemm(const ot_gemm_params* p, void* stream);

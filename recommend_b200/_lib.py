@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, 'lib', 'libonetrans_sm100.so')
 
 i32, i64, vp, fp = C.c_int32, C.c_int64, C.c_void_p, C.c_void_p  # float* passed as raw address
 
-OT_EPI_BIAS, OT_EPI_GELU, OT_EPI_RESIDUAL, OT_EPI_GELU_GRAD, OT_EPI_ROW_SCALE, OT_EPI_DROPOUT = 1, 2, 4, 8, 16, 32
+OT_EPI_BIAS, OT_EPI_GELU, OT_EPI_RESIDUAL, OT_EPI_GELU_GRAD, OT_EPI_ROW_SCALE, OT_EPI_DROPOUT, OT_EPI_NORM = 1, 2, 4, 8, 16, 32, 64
 
 
 class GemmSeg(C.Structure):
@@ -27,7 +27,8 @@ class GemmParams(C.Structure):
                 ('n_segs', i32), ('flags', i32), ('segs', GemmSeg * 3),
                 ('out', vp), ('ldo', i64), ('out2', vp), ('ldo2', i64), ('res', vp), ('ldr', i64),
                 ('aux', vp), ('ldaux', i64), ('bias', fp), ('bias_group_stride', i64), ('row_scale', fp),
-                ('block_n', i32), ('swizzle', i32), ('res_hp', fp), ('out_hp', fp), ('ld_hp', i64), ('hp_row0', i64), ('drop_seed', C.c_uint32), ('drop_rate', C.c_float)]
+                ('block_n', i32), ('swizzle', i32), ('res_hp', fp), ('out_hp', fp), ('ld_hp', i64), ('hp_row0', i64), ('drop_seed', C.c_uint32), ('drop_rate', C.c_float),
+                ('norm_out', vp), ('ld_norm', i64), ('norm_gain', fp), ('norm_rstd', fp), ('norm_eps', C.c_float)]
 
 
 class WgradSeg(C.Structure):

@@ -31,6 +31,7 @@ static constexpr int CTRL_THREADS = 128;      // one control warpgroup: warp 0 T
 static constexpr int GEMM_THREADS = CTRL_THREADS + EPI_THREADS;   // + 16 epilogue warps (warps 4..19)
 static constexpr int EPI_REGS = 112, CTRL_REGS = 32;   // setmaxnreg: the control warpgroup releases 4*32*(96-32) registers into the CTA pool, exactly what the four epilogue warpgroups take (4*128*(112-96)); asking for more than was released spins forever
 static constexpr int EPI_BAR_ID = 1;         // named barriers 1..4: one per epilogue set
+static constexpr int EPI_BAR_NORM = 5;       // all active epilogue sets (row statistics of the fused RMSNorm)
 static constexpr int CHUNK = 64;             // epilogue column chunk (128 bytes of bf16 per row)
 static constexpr int CH_BYTES = 128 * 64 * 2;   // one staged chunk: 128 rows x 128 bytes
 
@@ -56,6 +57,7 @@ struct GemmKParams {
   const float* row_scale;
   const float* res_hp; float* out_hp; long long ld_hp; long long hp_row0;
   uint32_t drop_seed, drop_thr16; float drop_scale;
+  __nv_bfloat16* norm_out; long long ld_norm; const float* norm_gain; float* norm_rstd; float norm_eps;
 };
 
 struct TileInfo {
@@ -100,10 +102,11 @@ struct GemmCfg {
   static constexpr int B_BYTES = BN * SWB;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGING_BYTES = EPI_SETS * BM * CHUNK * 2;  // one 128x64 bf16 buffer per epilogue set
-  static constexpr int BUDGET = 227 * 1024 - STAGING_BYTES - 256;
+  static constexpr int NORM_BYTES = 2 * EPI_SETS * BM * 4;        // fused RMSNorm: per-set partial sums of squares, double-buffered
+  static constexpr int BUDGET = 227 * 1024 - STAGING_BYTES - NORM_BYTES - 256;
   static constexpr int STAGES_RAW = BUDGET / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + NORM_BYTES + 256;
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
                                    : (2 * BN <= 256) ? 256 : 512;
 };
@@ -120,7 +123,8 @@ ot_mixed_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 
   uint8_t* stage_base = smem;
   uint8_t* staging = smem + STAGES * Cfg::STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + Cfg::STAGING_BYTES);
+  float* ss_part = reinterpret_cast<float*>(staging + Cfg::STAGING_BYTES);          // [2][EPI_SETS][BM]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + Cfg::STAGING_BYTES + Cfg::NORM_BYTES);
   uint64_t* full_bar = bars;                 // [STAGES]
   uint64_t* empty_bar = bars + STAGES;       // [STAGES]
   uint64_t* tfull_bar = bars + 2 * STAGES;   // [2]
@@ -235,6 +239,7 @@ ot_mixed_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const bool io_thread = (et == 0);
     const bool f_bias = p.flags & OT_EPI_BIAS, f_gelu = p.flags & OT_EPI_GELU, f_res = p.flags & OT_EPI_RESIDUAL;
     const bool f_ggrad = p.flags & OT_EPI_GELU_GRAD, f_rs = p.flags & OT_EPI_ROW_SCALE, f_drop = p.flags & OT_EPI_DROPOUT;
+    const bool f_norm = p.flags & OT_EPI_NORM;
     const bool has_in = f_res || f_ggrad;
     const bool dual = f_gelu && (p.out2 != nullptr);
     const __nv_bfloat16* in_ptr = f_res ? p.res : p.aux;
@@ -408,6 +413,70 @@ ot_mixed_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             named_bar_sync(bar_id, EPI_SET_THREADS);   // readers done before anything lands in the tile again
           }
         }
+        if (f_norm) {
+          // ---- fused RMSNorm of the rows just produced (OT/model.py:19-23): the tile holds whole rows (N == BN),
+          // each set its 64 columns.  Values come back from the staging tile (bf16, exactly what went to HBM) or,
+          // on fp32-residual rows, from out_hp. ----
+          const long long hr = (long long)(t.row0 + r_own) - p.hp_row0;
+          const bool hp_row = hp_tile && r_own < t.valid;
+          auto load8 = [&](int ch, float (&x)[8]) {
+            if (hp_tile) {
+              if (hp_row) {
+                const float4* rp = reinterpret_cast<const float4*>(p.out_hp + hr * p.ld_hp + col0 + ch * 8);
+                const float4 a = rp[0], b = rp[1];
+                x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+              } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) x[e] = 0.0f;
+              }
+            } else {
+              const uint4 q = *reinterpret_cast<const uint4*>(buf + swz_off<128>(r_own, ch));
+              x[0] = bf16lo(q.x); x[1] = bf16hi(q.x); x[2] = bf16lo(q.y); x[3] = bf16hi(q.y);
+              x[4] = bf16lo(q.z); x[5] = bf16hi(q.z); x[6] = bf16lo(q.w); x[7] = bf16hi(q.w);
+            }
+          };
+          float ss = 0.0f;
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch) {
+            float x[8];
+            load8(ch, x);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) ss = fmaf(x[e], x[e], ss);
+          }
+          float* ssb = ss_part + (it & 1) * (EPI_SETS * BM);
+          ssb[set * BM + r_own] = ss;
+          if (tma_out && io_thread) bulk_wait_read0();          // the `out` rows have left the staging tile
+          named_bar_sync(EPI_BAR_NORM, EPI_SET_THREADS * (BN / CHUNK));
+          float tot = 0.0f;
+#pragma unroll
+          for (int s2 = 0; s2 < BN / CHUNK; ++s2) tot += ssb[s2 * BM + r_own];
+          const float rstd = rsqrtf(tot / (float)p.N + p.norm_eps);
+          if (set == 0 && r_own < t.valid && p.norm_rstd != nullptr) p.norm_rstd[t.row0 + r_own] = rstd;
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch) {
+            float x[8];
+            load8(ch, x);
+            const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.norm_gain + col0 + ch * 8));
+            const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.norm_gain + col0 + ch * 8) + 1);
+            uint4 q;
+            q.x = pack_bf16x2(x[0] * rstd * g0.x, x[1] * rstd * g0.y);
+            q.y = pack_bf16x2(x[2] * rstd * g0.z, x[3] * rstd * g0.w);
+            q.z = pack_bf16x2(x[4] * rstd * g1.x, x[5] * rstd * g1.y);
+            q.w = pack_bf16x2(x[6] * rstd * g1.z, x[7] * rstd * g1.w);
+            *reinterpret_cast<uint4*>(buf + swz_off<128>(r_own, ch)) = q;
+          }
+          if (tma_out) fence_proxy_async_smem();
+          named_bar_sync(bar_id, EPI_SET_THREADS);
+          if (tma_out) {
+            if (io_thread) {
+              tma_store_2d(&tmOut2, buf, col0, t.row0);       // tmOut2 maps norm_out in this mode
+              bulk_commit();
+            }
+          } else {
+            store_rows(p.norm_out, p.ld_norm);
+            named_bar_sync(bar_id, EPI_SET_THREADS);
+          }
+        }
         // prefetch the auxiliary input of this set's chunk in the CTA's next tile
         if (io_thread && has_in && tile + (int)gridDim.x < total_tiles) {
           bulk_wait_read0();
@@ -463,10 +532,17 @@ int mixed_gemm_impl(const ot_gemm_params* p, cudaStream_t st) {
   if ((p->flags & OT_EPI_ROW_SCALE) && !p->row_scale) OT_FAIL(OT_ERR_INVALID_ARG, "ot_mixed_gemm: row-scale flag without row_scale");
   if ((p->flags & OT_EPI_RESIDUAL) && (p->flags & OT_EPI_GELU_GRAD))
     OT_FAIL(OT_ERR_INVALID_ARG, "ot_mixed_gemm: residual and gelu-grad epilogues cannot be combined (one auxiliary input per launch)");
+  if (p->flags & OT_EPI_NORM) {
+    if (!p->norm_out || !p->norm_gain || p->out2 || (p->ld_norm % 8) || (reinterpret_cast<uintptr_t>(p->norm_gain) & 15))
+      OT_FAIL(OT_ERR_INVALID_ARG, "ot_mixed_gemm: OT_EPI_NORM needs norm_out, a 16-byte aligned norm_gain, ld_norm %% 8 == 0 and no out2");
+    if (p->N > 256 || (p->block_n != 0 && p->block_n != p->N))
+      OT_FAIL(OT_ERR_UNSUPPORTED_SHAPE, "ot_mixed_gemm: OT_EPI_NORM needs whole rows in one tile (N=%d <= 256, block_n == N)", p->N);
+  }
   if ((p->ldo % 8) || (p->out2 && (p->ldo2 % 8)) || (p->res && (p->ldr % 8)) || (p->aux && (p->ldaux % 8)))
     OT_FAIL(OT_ERR_UNSUPPORTED_SHAPE, "ot_mixed_gemm: leading dimensions must be multiples of 8 elements");
 
   int bn = p->block_n;
+  if (bn == 0 && (p->flags & OT_EPI_NORM)) bn = p->N;
   if (bn == 0) bn = (p->N % 256 == 0) ? 256 : (p->N % 128 == 0) ? 128 : 64;
   if ((bn != 64 && bn != 128 && bn != 256) || p->N % bn != 0)
     OT_FAIL(OT_ERR_UNSUPPORTED_SHAPE, "ot_mixed_gemm: block_n=%d does not tile N=%d", bn, p->N);
@@ -495,6 +571,8 @@ int mixed_gemm_impl(const ot_gemm_params* p, cudaStream_t st) {
   kp.res = (const __nv_bfloat16*)p->res; kp.ldr = p->ldr; kp.aux = (const __nv_bfloat16*)p->aux; kp.ldaux = p->ldaux;
   kp.bias = p->bias; kp.bias_group_stride = p->bias_group_stride; kp.row_scale = p->row_scale;
   kp.res_hp = p->res_hp; kp.out_hp = p->out_hp; kp.ld_hp = p->ld_hp; kp.hp_row0 = p->hp_row0;
+  kp.norm_out = (__nv_bfloat16*)p->norm_out; kp.ld_norm = p->ld_norm; kp.norm_gain = p->norm_gain; kp.norm_rstd = p->norm_rstd;
+  kp.norm_eps = p->norm_eps;
   if (p->flags & OT_EPI_DROPOUT) {
     if (!(p->drop_rate >= 0.0f && p->drop_rate < 1.0f)) OT_FAIL(OT_ERR_INVALID_ARG, "ot_mixed_gemm: drop_rate=%f", (double)p->drop_rate);
     kp.drop_seed = p->drop_seed; kp.drop_thr16 = (uint32_t)(p->drop_rate * 65536.0f + 0.5f); kp.drop_scale = 1.0f / (1.0f - p->drop_rate);
@@ -542,6 +620,11 @@ int mixed_gemm_impl(const ot_gemm_params* p, cudaStream_t st) {
     if (p->out2) {
       str[0] = (uint64_t)p->ldo2 * 2;
       rc = make_tmap_bf16(&tmOut2, p->out2, 2, dims, str, box, 128);
+      if (rc) return rc;
+    }
+    if (p->flags & OT_EPI_NORM) {
+      str[0] = (uint64_t)p->ld_norm * 2;
+      rc = make_tmap_bf16(&tmOut2, p->norm_out, 2, dims, str, box, 128);
       if (rc) return rc;
     }
     const void* in_base = (p->flags & OT_EPI_RESIDUAL) ? p->res : (p->flags & OT_EPI_GELU_GRAD) ? p->aux : nullptr;

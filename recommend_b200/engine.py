@@ -73,13 +73,25 @@ def split_segments(segs: Sequence[ops.Seg], row: int) -> List[ops.Seg]:
     return out
 
 
+def _fused_norm_args(norm: Optional[dict], rows: int, d: int, dev):
+    """Allocate the outputs of an RMSNorm fused into a GEMM epilogue (north_star item 4) and return the ``norm=`` tuple
+    of ops.mixed_gemm, or None when no norm was asked for / the row does not fit one tile."""
+    if norm is None or not ops.can_fuse_norm(d):
+        return None
+    norm['out'] = torch.empty(rows, d, dtype=bf16, device=dev)
+    norm['rstd'] = torch.empty(rows, dtype=torch.float32, device=dev)
+    return (norm['out'], norm['gain'], norm['rstd'], norm['eps'])
+
+
 def mha_forward(xn: torch.Tensor, res: Optional[torch.Tensor], w: BlockWeights, B: int, cur: int, keep: int, H: int,
                 L_ns: int, alignment: str, kv_prefix: Optional[torch.Tensor] = None, res_hp: Optional[torch.Tensor] = None,
-                drop: Optional[Tuple[int, float]] = None):
+                drop: Optional[Tuple[int, float]] = None, norm: Optional[dict] = None):
     """MixedMHA.call (OT/model.py:76-122) on normalised ``xn [cur*B, d]``; queries for the last ``keep``
     positions.  ``res`` (``[keep*B, d]``) is added to the Wo output (the block's residual, OT/model.py:193).
     ``kv_prefix [Lc*B, 2d]``: cached K|V rows placed in front of the new ones (OT/model.py:95-98).
-    Returns (z, saved) with z = res + attn_out @ Wo."""
+    Returns (z, saved, z_hp) with z = res + attn_out @ Wo.  ``norm={'gain': g, 'eps': e}``: the Wo epilogue also writes
+    ``RMSNorm(z) * g`` (the block's norm2, OT/model.py:196) and its row statistics into ``norm['out']`` / ``norm['rstd']``
+    when the shape allows (``ops.can_fuse_norm``); otherwise the dict comes back without ``'out'``."""
     d = xn.shape[1]
     dh = d // H
     dev = xn.device
@@ -98,6 +110,7 @@ def mha_forward(xn: torch.Tensor, res: Optional[torch.Tensor], w: BlockWeights, 
     ops.attn_fwd(q, kv[:, :d], kv[:, d:], o, lse, B, H, keep, Lc + cur, dh)
     z = torch.empty(rows_t, d, dtype=bf16, device=dev)
     z_hp = None
+    nrm = _fused_norm_args(norm, rows_t, d, dev)
     if res_hp is not None and res is not None:
         # Wo is shared, but the NS-token rows (the last rows of the tail) keep an fp32 residual stream: split the row
         # range at that boundary so that they form their own (tile-aligned) segment
@@ -106,9 +119,10 @@ def mha_forward(xn: torch.Tensor, res: Optional[torch.Tensor], w: BlockWeights, 
         z_hp = torch.empty(n_hp, d, dtype=torch.float32, device=dev)
         segs_o = split_segments([(0, 1, rows_t, 0, 0)], hp0)
         ops.mixed_gemm(o, w.Wo_f, segs_o, z, flags=OT_EPI_RESIDUAL, res=res, res_hp=res_hp[res_hp.shape[0] - n_hp:], out_hp=z_hp, hp_row0=hp0,
-                       dropout=drop)
+                       dropout=drop, norm=nrm)
     else:
-        ops.mixed_gemm(o, w.Wo_f, [(0, 1, rows_t, 0, 0)], z, flags=OT_EPI_RESIDUAL if res is not None else 0, res=res, dropout=drop)
+        ops.mixed_gemm(o, w.Wo_f, [(0, 1, rows_t, 0, 0)], z, flags=OT_EPI_RESIDUAL if res is not None else 0, res=res, dropout=drop,
+                       norm=nrm)
     return z, (q, kv, o, lse, segs_all, segs_tail), z_hp
 
 
@@ -142,8 +156,9 @@ def mha_backward(dz: torch.Tensor, xn: torch.Tensor, saved, w: BlockWeights, Wqk
 
 def ffn_forward(zn: torch.Tensor, res: Optional[torch.Tensor], w: BlockWeights, b1: torch.Tensor, b2: torch.Tensor,
                 segs: Sequence[ops.Seg], save: bool, res_hp: Optional[torch.Tensor] = None,
-                drop: Optional[Tuple[int, float]] = None):
-    """MixedFFN.call (OT/model.py:149-163): ``gelu(zn W1 + b1) W2 + b2`` (+ res)."""
+                drop: Optional[Tuple[int, float]] = None, norm: Optional[dict] = None):
+    """MixedFFN.call (OT/model.py:149-163): ``gelu(zn W1 + b1) W2 + b2`` (+ res).  ``norm`` as in mha_forward: the FFN-2
+    epilogue also writes the NEXT block's ``norm1(y)`` (OT/model.py:191)."""
     rows_t, d = zn.shape
     F = w.W1_f.shape[1]
     dev = zn.device
@@ -153,13 +168,14 @@ def ffn_forward(zn: torch.Tensor, res: Optional[torch.Tensor], w: BlockWeights, 
     y = torch.empty(rows_t, d, dtype=bf16, device=dev)
     flags = OT_EPI_BIAS | (OT_EPI_RESIDUAL if res is not None else 0)
     y_hp = None
+    nrm = _fused_norm_args(norm, rows_t, d, dev)
     if res_hp is not None and res is not None:
         hp0 = rows_t - res_hp.shape[0]          # the fp32 stream covers the last rows (the NS tokens)
         y_hp = torch.empty(res_hp.shape[0], d, dtype=torch.float32, device=dev)
         ops.mixed_gemm(h, w.W2_f, split_segments(segs, hp0), y, flags=flags, bias=b2, res=res, res_hp=res_hp, out_hp=y_hp, hp_row0=hp0,
-                       dropout=drop)
+                       dropout=drop, norm=nrm)
     else:
-        ops.mixed_gemm(h, w.W2_f, segs, y, flags=flags, bias=b2, res=res, dropout=drop)
+        ops.mixed_gemm(h, w.W2_f, segs, y, flags=flags, bias=b2, res=res, dropout=drop, norm=nrm)
     return y, (pre, h), y_hp
 
 
@@ -181,8 +197,12 @@ def ffn_backward(dy: torch.Tensor, zn: torch.Tensor, saved, w: BlockWeights, seg
 
 def block_forward(x: torch.Tensor, P: Dict[str, torch.Tensor], w: BlockWeights, B: int, cur: int, keep: int, H: int,
                   L_ns: int, alignment: str, eps: float, save: bool, kv_prefix: Optional[torch.Tensor] = None,
-                  x_hp: Optional[torch.Tensor] = None, drop: Optional[Tuple[int, int, float]] = None):
+                  x_hp: Optional[torch.Tensor] = None, drop: Optional[Tuple[int, int, float]] = None,
+                  pre_norm: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, next_gain: Optional[torch.Tensor] = None):
     """OneTransBlock.call (OT/model.py:186-200) + tail keep (:371).  P: norm1, norm2, b1, b2 (fp32).
+    RMSNorms ride in the epilogue of the GEMM that produces their input (north_star item 4): norm2 in the Wo GEMM,
+    and - when ``next_gain`` (the next block's norm1 scale) is given - the next block's norm1 in the FFN-2 GEMM; the
+    result comes back as 5th value ``(xn_next, rstd_next)`` and enters the next call as ``pre_norm``.
     ``x_hp``: optional fp32 copy of the NS-token rows of ``x`` (its last ``x_hp.shape[0]`` rows) — the
     high-precision residual stream of DESIGN.md §5; returns the matching ``y_hp`` as 4th value.
     ``drop = (seed_attention, seed_ffn, rate)``: Keras inverted dropout on the two branch outputs (OT/model.py:193,198),
@@ -191,22 +211,31 @@ def block_forward(x: torch.Tensor, P: Dict[str, torch.Tensor], w: BlockWeights, 
     assert rows == cur * B
     dev = x.device
     rows_t, off = keep * B, (cur - keep) * B
-    xn = torch.empty(rows, d, dtype=bf16, device=dev)
-    r1 = torch.empty(rows, dtype=torch.float32, device=dev)
     if x_hp is not None and x_hp.shape[0] == 0:
         x_hp = None
-    ops.rmsnorm_fwd(x, P['norm1'], xn, r1, eps, x_hp, rows - (x_hp.shape[0] if x_hp is not None else 0))   # OT/model.py:191
+    if pre_norm is not None:
+        xn, r1 = pre_norm                                             # written by the previous block's FFN-2 epilogue
+    else:
+        xn = torch.empty(rows, d, dtype=bf16, device=dev)
+        r1 = torch.empty(rows, dtype=torch.float32, device=dev)
+        ops.rmsnorm_fwd(x, P['norm1'], xn, r1, eps, x_hp, rows - (x_hp.shape[0] if x_hp is not None else 0))   # OT/model.py:191
     d_att = (drop[0], drop[2]) if drop is not None else None
     d_ffn = (drop[1], drop[2]) if drop is not None else None
-    z, mha_saved, z_hp = mha_forward(xn, x[off:], w, B, cur, keep, H, L_ns, alignment, kv_prefix, x_hp, d_att)   # :192-193
-    zn = torch.empty(rows_t, d, dtype=bf16, device=dev)
-    r2 = torch.empty(rows_t, dtype=torch.float32, device=dev)
-    ops.rmsnorm_fwd(z, P['norm2'], zn, r2, eps, z_hp, rows_t - (z_hp.shape[0] if z_hp is not None else 0))   # :196
+    n2 = {'gain': P['norm2'], 'eps': eps}
+    z, mha_saved, z_hp = mha_forward(xn, x[off:], w, B, cur, keep, H, L_ns, alignment, kv_prefix, x_hp, d_att, n2)   # :192-193, :196
+    if 'out' in n2:
+        zn, r2 = n2['out'], n2['rstd']
+    else:
+        zn = torch.empty(rows_t, d, dtype=bf16, device=dev)
+        r2 = torch.empty(rows_t, dtype=torch.float32, device=dev)
+        ops.rmsnorm_fwd(z, P['norm2'], zn, r2, eps, z_hp, rows_t - (z_hp.shape[0] if z_hp is not None else 0))   # :196
     segs_tail = mha_saved[5]
-    y, ffn_saved, y_hp = ffn_forward(zn, z, w, P['b1'], P['b2'], segs_tail, save, z_hp, d_ffn)     # :197-198
+    n1 = {'gain': next_gain, 'eps': eps} if next_gain is not None else None
+    y, ffn_saved, y_hp = ffn_forward(zn, z, w, P['b1'], P['b2'], segs_tail, save, z_hp, d_ffn, n1)     # :197-198
+    nxt = (n1['out'], n1['rstd']) if n1 is not None and 'out' in n1 else None
     kv = mha_saved[1]
     saved = (x, xn, r1, mha_saved, z, zn, r2, ffn_saved, drop) if save else None
-    return y, kv, saved, y_hp
+    return y, kv, saved, y_hp, nxt
 
 
 def block_backward(dy: torch.Tensor, saved, Pm: Dict[str, torch.Tensor], w: BlockWeights, B: int, cur: int, keep: int,
@@ -330,7 +359,7 @@ def user_cache_forward(x_s: torch.Tensor, blocks, plan, H: int, eps: float):
             continue
         assert x_s.shape[0] == cur_S
         if keep_S > 0:
-            x_s, kv, _, _ = block_forward(x_s, P, w, 1, cur_S, keep_S, H, 0, 'tail', eps, False)
+            x_s, kv, _, _, _ = block_forward(x_s, P, w, 1, cur_S, keep_S, H, 0, 'tail', eps, False)
         else:
             xn = torch.empty(cur_S, d, dtype=bf16, device=dev)
             ops.rmsnorm_fwd(x_s, P['norm1'], xn, None, eps)

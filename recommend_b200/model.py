@@ -281,15 +281,18 @@ class OneTransBlock(nn.Module):
                 'W1': self.ffn.W1, 'b1': self.ffn.b1, 'W2': self.ffn.W2, 'b2': self.ffn.b2}
 
     def forward_token_major(self, x2: torch.Tensor, B: int, cur: int, keep: int, training: bool = False,
-                            kv_prefix: Optional[torch.Tensor] = None, x_hp: Optional[torch.Tensor] = None):
+                            kv_prefix: Optional[torch.Tensor] = None, x_hp: Optional[torch.Tensor] = None,
+                            pre_norm=None, next_gain: Optional[torch.Tensor] = None):
         """Token-major entry used by OneTransModel: ``x2 [cur*B, d]`` -> ``([keep*B, d], kv [Lk*B, 2d], y_hp)``.
-        ``x_hp``: fp32 copy of the NS-token rows (high-precision residual stream) or None."""
+        ``x_hp``: fp32 copy of the NS-token rows (high-precision residual stream) or None.
+        ``pre_norm`` / ``next_gain``: norm1 of this block already computed by the previous block's FFN-2 epilogue /
+        ask this block's FFN-2 epilogue for the next block's norm1 (left in ``self._next_norm``)."""
         drop = None
         if training and self.dropout_rate > 0.0:
             # Keras Dropout(rate) on both branch outputs (OT/model.py:184,193,198); seeds come from torch's CPU generator
             s = torch.randint(0, 2 ** 31 - 1, (2,))
             drop = (int(s[0]), int(s[1]), float(self.dropout_rate))
-        return _BlockFn.apply(x2, self.norm1.scale, self, B, cur, keep, kv_prefix, x_hp, drop)
+        return _BlockFn.apply(x2, self.norm1.scale, self, B, cur, keep, kv_prefix, x_hp, drop, pre_norm, next_gain)
 
     def forward(self, x: torch.Tensor, training: bool = False,
                 kv_cache: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, query_len: Optional[int] = None):
@@ -311,7 +314,7 @@ class OneTransBlock(nn.Module):
 
 class _BlockFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x2, anchor, blk: OneTransBlock, B, cur, keep, kv_prefix, x_hp, drop):
+    def forward(ctx, x2, anchor, blk: OneTransBlock, B, cur, keep, kv_prefix, x_hp, drop, pre_norm=None, next_gain=None):
         # without this autograd fills a [cur*B, 2d] bf16 and a [L_NS*B, d] fp32 zero tensor per block and step for the
         # two outputs nobody differentiates (1.3 ms/step at C2, profiles/README.md)
         ctx.set_materialize_grads(False)
@@ -322,8 +325,10 @@ class _BlockFn(torch.autograd.Function):
         w = blk._weights()
         P = {'norm1': blk.norm1.scale.detach(), 'norm2': blk.norm2.scale.detach(), 'b1': blk.ffn.b1.detach(),
              'b2': blk.ffn.b2.detach()}
-        y, kv, saved, y_hp = engine.block_forward(x2, P, w, B, cur, keep, cfg.num_heads, cfg.num_ns_tokens, cfg.ns_param_alignment,
-                                                  blk.norm1.eps, need_grad, kv_prefix, x_hp, drop)
+        y, kv, saved, y_hp, nxt = engine.block_forward(x2, P, w, B, cur, keep, cfg.num_heads, cfg.num_ns_tokens, cfg.ns_param_alignment,
+                                                       blk.norm1.eps, need_grad, kv_prefix, x_hp, drop, pre_norm,
+                                                       None if next_gain is None else next_gain.detach())
+        object.__setattr__(blk, '_next_norm', nxt)    # side channel to the next block (plain tensors, no autograd edge)
         if y_hp is None:
             y_hp = y.new_zeros(0, dtype=torch.float32)
         ctx.mark_non_differentiable(kv, y_hp)
@@ -333,11 +338,11 @@ class _BlockFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy, _dkv, _dhp):
         if dy is None:
-            return (None,) * 9
+            return (None,) * 11
         saved, w, blk, B, cur, keep = ctx.saved
         dx = engine.block_backward(dy, saved, blk._params(), w, B, cur, keep, blk.config.num_heads)
         ctx.saved = None
-        return dx, None, None, None, None, None, None, None, None
+        return dx, None, None, None, None, None, None, None, None, None, None
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -475,10 +480,15 @@ class OneTransModel(nn.Module):
         keep_lens = resolve_keep_lens(self.config, L)                                      # :349 (+D2, D5)
         cur = L
         x_hp = self.tokenizer._last_hp if getattr(self.config, 'hp_ns_residual', True) else None
-        for block, keep in zip(self.blocks, keep_lens):                                    # :348
+        pre_norm = None
+        n_blocks = len(self.blocks)
+        for i, (block, keep) in enumerate(zip(self.blocks, keep_lens)):                    # :348
             if x_hp is not None:   # the NS rows that survive into this layer's input (suffix of the fp32 stream)
                 x_hp = x_hp[x_hp.shape[0] - min(self.config.num_ns_tokens, cur) * B:]
-            x2, _, x_hp = block.forward_token_major(x2, B, cur, keep, training, None, x_hp)   # :366-371
+            next_gain = self.blocks[i + 1].norm1.scale if i + 1 < n_blocks else None
+            x2, _, x_hp = block.forward_token_major(x2, B, cur, keep, training, None, x_hp, pre_norm, next_gain)   # :366-371
+            pre_norm = block._next_norm
+            object.__setattr__(block, '_next_norm', None)
             if x_hp.numel() == 0:
                 x_hp = None
             cur = keep

@@ -108,9 +108,12 @@ def mixed_gemm(A: torch.Tensor, W: torch.Tensor, segs: Sequence[Seg], out: torch
                aux: Optional[torch.Tensor] = None, out2: Optional[torch.Tensor] = None,
                row_scale: Optional[torch.Tensor] = None, a_transposed_events: bool = False,
                block_n: int = 0, swizzle: int = 0, res_hp: Optional[torch.Tensor] = None,
-               out_hp: Optional[torch.Tensor] = None, hp_row0: int = 0, dropout: Optional[Tuple[int, float]] = None) -> torch.Tensor:
+               out_hp: Optional[torch.Tensor] = None, hp_row0: int = 0, dropout: Optional[Tuple[int, float]] = None,
+               norm: Optional[Tuple[torch.Tensor, torch.Tensor, Optional[torch.Tensor], float]] = None) -> torch.Tensor:
     """``out[row] = epilogue(A[row] @ W[group(row)].T)``.  W: ``[G, N, K]`` bf16 (rows may be strided).
-    With ``a_transposed_events`` A is ``[B, L_i, K]`` and output rows are ``(l, b)`` token-major."""
+    With ``a_transposed_events`` A is ``[B, L_i, K]`` and output rows are ``(l, b)`` token-major.
+    ``norm=(norm_out, gain, rstd_out, eps)`` also writes ``RMSNorm(out) * gain`` (and the row statistics the backward
+    needs) from the same epilogue; N <= 256 only (``can_fuse_norm``)."""
     _check_bf16(W, 'W')
     _check_bf16(out, 'out')
     G, N, K = W.shape
@@ -158,12 +161,26 @@ def mixed_gemm(A: torch.Tensor, W: torch.Tensor, segs: Sequence[Seg], out: torch
         assert out_hp is not None and res_hp.dtype == torch.float32 and out_hp.dtype == torch.float32
         assert res_hp.stride(-1) == 1 and out_hp.stride(-1) == 1 and res_hp.stride(0) == out_hp.stride(0)
         p.res_hp, p.out_hp, p.ld_hp, p.hp_row0 = res_hp.data_ptr(), out_hp.data_ptr(), res_hp.stride(0), hp_row0
+    if norm is not None:
+        n_out, n_gain, n_rstd, n_eps = norm
+        _check_bf16(n_out, 'norm_out')
+        assert n_gain.dtype == torch.float32 and n_gain.is_cuda and n_gain.numel() == N and out2 is None
+        p.flags = flags = flags | L.OT_EPI_NORM
+        p.norm_out, p.ld_norm, p.norm_gain, p.norm_eps = n_out.data_ptr(), n_out.stride(0), n_gain.data_ptr(), n_eps
+        if n_rstd is not None:
+            assert n_rstd.dtype == torch.float32 and n_rstd.is_contiguous()
+            p.norm_rstd = n_rstd.data_ptr()
     rows = sum(s[1] * s[2] for s in segs)
     groups = sum((s[1] if s[4] else 1) for s in segs)
-    n_io = 1 + (out2 is not None) + (res is not None) + (aux is not None)
+    n_io = 1 + (out2 is not None) + (res is not None) + (aux is not None) + (norm is not None)
     _run('ot_mixed_gemm', L.load().ot_mixed_gemm, p, f'N{N}_K{K}_f{flags}', 2.0 * rows * N * K,
          rows * K * 2.0 + n_io * rows * N * 2.0 + groups * N * K * 2.0)
     return out
+
+
+def can_fuse_norm(N: int) -> bool:
+    """OT_EPI_NORM needs whole rows inside one 128 x N tile."""
+    return N in (64, 128, 256)
 
 
 WSeg = Tuple[torch.Tensor, int, int, torch.Tensor, int, int, int, int, int, int]

@@ -83,6 +83,38 @@ def test_gemm_epilogues():
     close(acc, base + res.float())
 
 
+@pytest.mark.parametrize('rows,N,K,hp_rows', [(1000, 256, 256, 0), (1280, 256, 1024, 256), (300, 128, 64, 0), (77, 64, 128, 0)])
+def test_gemm_fused_rmsnorm_output(rows, N, K, hp_rows):
+    """OT_EPI_NORM: the epilogue that writes z = res + A W^T also writes RMSNorm(z) * gain and rstd (OT/model.py:19-23)."""
+    A, W = rnd(rows, K, seed=31), rnd(1, N, K, seed=32) * 0.1
+    res = rnd(rows, N, seed=33)
+    gain = (1.0 + 0.1 * torch.randn(N, device='cuda'))
+    out = torch.empty(rows, N, dtype=bf16, device='cuda')
+    nout = torch.empty(rows, N, dtype=bf16, device='cuda')
+    rstd = torch.empty(rows, device='cuda')
+    kw = {}
+    segs = [(0, 1, rows, 0, 0)]
+    if hp_rows:
+        res_hp = res[rows - hp_rows:].float() + 1e-3 * torch.randn(hp_rows, N, device='cuda')
+        out_hp = torch.empty_like(res_hp)
+        kw = dict(res_hp=res_hp, out_hp=out_hp, hp_row0=rows - hp_rows)
+        segs = [(0, 1, rows - hp_rows, 0, 0), (rows - hp_rows, 1, hp_rows, 0, 0)]
+    ops.mixed_gemm(A, W, segs, out, flags=OT_EPI_RESIDUAL, res=res, norm=(nout, gain, rstd, 1e-6), **kw)
+    z = A.float() @ W[0].float().t() + res.float()
+    if hp_rows:
+        z[rows - hp_rows:] = A[rows - hp_rows:].float() @ W[0].float().t() + res_hp
+        assert (out_hp - z[rows - hp_rows:]).abs().max().item() < 2e-3 * z.abs().max().item()
+    assert ((out.float() - z).abs().max() / z.abs().max()).item() < 1e-2
+    # the norm is taken of what went to HBM (bf16 rows; fp32 on the high-precision rows)
+    zq = out.float()
+    if hp_rows:
+        zq[rows - hp_rows:] = out_hp
+    r_ref = torch.rsqrt(zq.square().mean(-1) + 1e-6)
+    assert ((rstd - r_ref).abs().max() / r_ref.abs().max()).item() < 1e-5
+    n_ref = zq * r_ref[:, None] * gain
+    assert ((nout.float() - n_ref).abs().max() / n_ref.abs().max()).item() < 6e-3      # one bf16 rounding
+
+
 def test_gemm_transposed_events_tokenizer_layout():
     """[B, L_i, 64] events -> token-major rows (l, b) (OT/model.py:262-265 + DESIGN.md layout)."""
     B, Li, E, d, off = 200, 7, 64, 256, 3
