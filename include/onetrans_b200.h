@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define OT_ABI_VERSION 6
+#define OT_ABI_VERSION 7
 
 int ot_version(void);
 const char* ot_last_error_string(void);
@@ -212,6 +212,13 @@ typedef struct ot_rmsnorm_params {
   /* forward only: rows >= hp_row0 are read from x_hp (fp32 [rows-hp_row0, d]) instead of x.  NULL = off. */
   const float* x_hp;
   int64_t hp_row0;
+  /* backward only: second output dx_drop[r, c] = keep(drop_row0 + r, c) ? dx[r, c] / (1 - rate) : 0 with the mask of
+   * OT_EPI_DROPOUT / ot_dropout_mask (same seed, index space [*, d]): the gradient entering the dropped-out branch that
+   * sits below this norm (OT/model.py:193,198), written in the same pass.  NULL = off. */
+  void* dx_drop; int64_t lddx_drop;
+  int64_t drop_row0;
+  uint32_t drop_seed;
+  float drop_rate;
 } ot_rmsnorm_params;
 
 int ot_rmsnorm_fwd(const ot_rmsnorm_params* p, void* stream);

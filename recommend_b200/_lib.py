@@ -59,7 +59,8 @@ class AttnCachedParams(C.Structure):
 class RmsnormParams(C.Structure):
     _fields_ = [('x', vp), ('ldx', i64), ('y', vp), ('ldy', i64), ('gain', fp), ('rstd', fp),
                 ('dy', vp), ('lddy', i64), ('dres', vp), ('lddres', i64), ('dx', vp), ('lddx', i64),
-                ('dgain', fp), ('rows', i64), ('d', i32), ('eps', C.c_float), ('x_hp', fp), ('hp_row0', i64)]
+                ('dgain', fp), ('rows', i64), ('d', i32), ('eps', C.c_float), ('x_hp', fp), ('hp_row0', i64),
+                ('dx_drop', vp), ('lddx_drop', i64), ('drop_row0', i64), ('drop_seed', C.c_uint32), ('drop_rate', C.c_float)]
 
 
 class NsTokenizerParams(C.Structure):

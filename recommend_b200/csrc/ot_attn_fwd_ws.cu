@@ -209,7 +209,9 @@ ot_attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       }
       float* xm = s_max + (g & 1) * 512;
       xm[quarter * 128 + row] = mx;
-      named_bar_sync(1, 512);
+      // the four warps that share these 32 rows (one per column quarter) exchange their maxima; the other twelve
+      // softmax warps work on other rows and need not wait here
+      named_bar_sync(1 + (warp & 3), 128);
       const float m_new = fmaxf(fmaxf(m_run, fmaxf(xm[row], xm[128 + row])), fmaxf(xm[256 + row], xm[384 + row]));
       // key 0 is visible to every query, so after the first block m_new is finite for every real row
       const float alpha = ex2_approx((m_run - m_new) * p.scale_log2);
@@ -270,7 +272,7 @@ ot_attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         tmem_ld_x16(t_row + Cfg::T_PV + quarter * 16, w);
         tmem_ld_wait();
         s_sum[quarter * 128 + row] = l_part;
-        named_bar_sync(1, 512);
+        named_bar_sync(1 + (warp & 3), 128);
         const float l = (s_sum[row] + s_sum[128 + row]) + (s_sum[256 + row] + s_sum[384 + row]);
         if (q0 + row < p.Lq) {
           const float inv = 1.0f / l;

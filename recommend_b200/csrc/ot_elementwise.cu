@@ -103,7 +103,8 @@ __global__ void __launch_bounds__(256)
 rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long lddy, const __nv_bfloat16* __restrict__ x,
                    long long ldx, const float* __restrict__ rstd, const float* __restrict__ g,
                    const __nv_bfloat16* __restrict__ dres, long long lddres, __nv_bfloat16* __restrict__ dx,
-                   long long lddx, float* __restrict__ dg, long long rows, int d) {
+                   long long lddx, float* __restrict__ dg, long long rows, int d, __nv_bfloat16* __restrict__ dx_drop,
+                   long long lddx_drop, long long drop_row0, uint32_t drop_seed, uint32_t drop_thr16, float drop_scale) {
   extern __shared__ float s_dg[];  // [d]
   const int lane = threadIdx.x & 31;
   const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -177,6 +178,16 @@ rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long lddy, const _
           for (int e = 0; e < 8; ++e) o[e] += rv[e];
         }
         dxr[ch] = pack8(o);
+        if (dx_drop != nullptr) {   // the same gradient behind the dropout of the branch below (mask recomputed from the seed)
+          const uint32_t mrow = static_cast<uint32_t>(drop_row0 + row);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t hb = dropout_bits(drop_seed, mrow, static_cast<uint32_t>(ch * 8 + 2 * j), static_cast<uint32_t>(d));
+            o[2 * j] = ((hb & 0xFFFFu) >= drop_thr16) ? o[2 * j] * drop_scale : 0.0f;
+            o[2 * j + 1] = ((hb >> 16) >= drop_thr16) ? o[2 * j + 1] * drop_scale : 0.0f;
+          }
+          reinterpret_cast<uint4*>(dx_drop + row * lddx_drop)[ch] = pack8(o);
+        }
       }
     }
   }
@@ -370,6 +381,8 @@ int rmsnorm_bwd_impl(const ot_rmsnorm_params* p, cudaStream_t st) {
   if (p->d <= 0 || p->d % 8 || p->d > 8 * 32 * MAX_CHUNKS) OT_FAIL(OT_ERR_UNSUPPORTED_SHAPE, "ot_rmsnorm_bwd: d=%d", p->d);
   if ((p->ldx % 8) || (p->lddy % 8) || (p->lddx % 8) || (p->dres && (p->lddres % 8)))
     OT_FAIL(OT_ERR_UNSUPPORTED_SHAPE, "ot_rmsnorm_bwd: leading dimensions must be multiples of 8");
+  if (p->dx_drop && (!(p->drop_rate >= 0.0f && p->drop_rate < 1.0f) || (p->lddx_drop % 8)))
+    OT_FAIL(OT_ERR_INVALID_ARG, "ot_rmsnorm_bwd: dx_drop needs 0 <= drop_rate < 1 and lddx_drop %% 8 == 0");
   if (p->rows <= 0) return OT_OK;
   int grid = grid_for_rows(p->rows, 8);
   const int cap = num_sms() * 8;  // a few resident blocks per SM; every block flushes dgain once
@@ -378,7 +391,9 @@ int rmsnorm_bwd_impl(const ot_rmsnorm_params* p, cudaStream_t st) {
 #define OT_LAUNCH_RMS_BWD(N)                                                                                                         \
   rmsnorm_bwd_kernel<N><<<grid, 256, p->d * sizeof(float), st>>>((const __nv_bfloat16*)p->dy, p->lddy, (const __nv_bfloat16*)p->x, p->ldx, \
                                                                  p->rstd, p->gain, (const __nv_bfloat16*)p->dres, p->lddres,          \
-                                                                 (__nv_bfloat16*)p->dx, p->lddx, p->dgain, p->rows, p->d)
+                                                                 (__nv_bfloat16*)p->dx, p->lddx, p->dgain, p->rows, p->d,             \
+                                                                 (__nv_bfloat16*)p->dx_drop, p->lddx_drop, p->drop_row0, p->drop_seed, \
+                                                                 (uint32_t)(p->drop_rate * 65536.0f + 0.5f), 1.0f / (1.0f - p->drop_rate))
   if (nch <= 1) OT_LAUNCH_RMS_BWD(1); else if (nch == 2) OT_LAUNCH_RMS_BWD(2); else OT_LAUNCH_RMS_BWD(4);
 #undef OT_LAUNCH_RMS_BWD
   OT_CUDA_CHECK(cudaGetLastError());

@@ -239,9 +239,12 @@ def block_forward(x: torch.Tensor, P: Dict[str, torch.Tensor], w: BlockWeights, 
 
 
 def block_backward(dy: torch.Tensor, saved, Pm: Dict[str, torch.Tensor], w: BlockWeights, B: int, cur: int, keep: int,
-                   H: int) -> torch.Tensor:
+                   H: int, dy_masked: Optional[torch.Tensor] = None, prev_drop: Optional[Tuple[int, float]] = None):
     """Backward of block_forward.  Pm maps names to the fp32 master parameters (their .grad buffers
-    receive the gradients).  Returns dx ``[cur*B, d]``."""
+    receive the gradients).  Returns ``(dx [cur*B, d], dx_masked)``.
+    The dropout masks of the two branches are applied to gradients as they are produced: ``dz`` leaves the norm2
+    backward both plain and masked; with ``prev_drop = (seed_ffn, rate)`` of the block below, ``dx`` leaves the norm1
+    backward also as that block's masked ``dy`` (returned as 2nd value, passed to its call as ``dy_masked``)."""
     x, xn, r1, mha_saved, z, zn, r2, ffn_saved, drop = saved
     rows, d = x.shape
     dev = x.device
@@ -250,20 +253,29 @@ def block_backward(dy: torch.Tensor, saved, Pm: Dict[str, torch.Tensor], w: Bloc
     if not dy.is_contiguous():
         dy = dy.contiguous()
     # y = z + drop(FFN(norm2(z)))
-    dy_f = ops.dropout_mask(dy, drop[1], drop[2]) if drop is not None else dy
+    if drop is None:
+        dy_f = dy
+    elif dy_masked is not None:
+        dy_f = dy_masked
+    else:
+        dy_f = ops.dropout_mask(dy, drop[1], drop[2])
     dzn = ffn_backward(dy_f, zn, ffn_saved, w, segs_tail, _grad_buf(Pm['W1']), _grad_buf(Pm['b1']), _grad_buf(Pm['W2']),
                        _grad_buf(Pm['b2']))
     dz = torch.empty(rows_t, d, dtype=bf16, device=dev)
-    ops.rmsnorm_bwd(dzn, z, r2, Pm['norm2'].detach(), dz, _grad_buf(Pm['norm2']), dres=dy)
     # z = x_tail + drop(MHA(norm1(x)))
-    dz_a = ops.dropout_mask(dz, drop[0], drop[2]) if drop is not None else dz
+    dz_a = torch.empty(rows_t, d, dtype=bf16, device=dev) if drop is not None else dz
+    ops.rmsnorm_bwd(dzn, z, r2, Pm['norm2'].detach(), dz, _grad_buf(Pm['norm2']), dres=dy,
+                    drop_out=(dz_a, drop[0], drop[2], 0) if drop is not None else None)
     dxn = mha_backward(dz_a, xn, mha_saved, w, _grad_buf(Pm['Wqkv']), _grad_buf(Pm['Wo']), B, cur, keep, H)
     dx = torch.empty(rows, d, dtype=bf16, device=dev)
+    dx_m = torch.empty(rows, d, dtype=bf16, device=dev) if prev_drop is not None else None
     g1, dg1 = Pm['norm1'].detach(), _grad_buf(Pm['norm1'])
     if off > 0:
-        ops.rmsnorm_bwd(dxn[:off], x[:off], r1[:off], g1, dx[:off], dg1, dres=None)
-    ops.rmsnorm_bwd(dxn[off:], x[off:], r1[off:], g1, dx[off:], dg1, dres=dz)
-    return dx
+        ops.rmsnorm_bwd(dxn[:off], x[:off], r1[:off], g1, dx[:off], dg1, dres=None,
+                        drop_out=(dx_m[:off], prev_drop[0], prev_drop[1], 0) if prev_drop is not None else None)
+    ops.rmsnorm_bwd(dxn[off:], x[off:], r1[off:], g1, dx[off:], dg1, dres=dz,
+                    drop_out=(dx_m[off:], prev_drop[0], prev_drop[1], off) if prev_drop is not None else None)
+    return dx, dx_m
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -282,7 +282,7 @@ class OneTransBlock(nn.Module):
 
     def forward_token_major(self, x2: torch.Tensor, B: int, cur: int, keep: int, training: bool = False,
                             kv_prefix: Optional[torch.Tensor] = None, x_hp: Optional[torch.Tensor] = None,
-                            pre_norm=None, next_gain: Optional[torch.Tensor] = None):
+                            pre_norm=None, next_gain: Optional[torch.Tensor] = None, prev_block=None):
         """Token-major entry used by OneTransModel: ``x2 [cur*B, d]`` -> ``([keep*B, d], kv [Lk*B, 2d], y_hp)``.
         ``x_hp``: fp32 copy of the NS-token rows (high-precision residual stream) or None.
         ``pre_norm`` / ``next_gain``: norm1 of this block already computed by the previous block's FFN-2 epilogue /
@@ -292,7 +292,12 @@ class OneTransBlock(nn.Module):
             # Keras Dropout(rate) on both branch outputs (OT/model.py:184,193,198); seeds come from torch's CPU generator
             s = torch.randint(0, 2 ** 31 - 1, (2,))
             drop = (int(s[0]), int(s[1]), float(self.dropout_rate))
-        return _BlockFn.apply(x2, self.norm1.scale, self, B, cur, keep, kv_prefix, x_hp, drop, pre_norm, next_gain)
+        object.__setattr__(self, '_last_drop', drop)
+        # the block below (if any) gets its masked output gradient from this block's norm1 backward
+        prev = None
+        if prev_block is not None and getattr(prev_block, '_last_drop', None) is not None:
+            prev = (prev_block, (prev_block._last_drop[1], prev_block._last_drop[2]))
+        return _BlockFn.apply(x2, self.norm1.scale, self, B, cur, keep, kv_prefix, x_hp, drop, pre_norm, next_gain, prev)
 
     def forward(self, x: torch.Tensor, training: bool = False,
                 kv_cache: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, query_len: Optional[int] = None):
@@ -314,7 +319,7 @@ class OneTransBlock(nn.Module):
 
 class _BlockFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x2, anchor, blk: OneTransBlock, B, cur, keep, kv_prefix, x_hp, drop, pre_norm=None, next_gain=None):
+    def forward(ctx, x2, anchor, blk: OneTransBlock, B, cur, keep, kv_prefix, x_hp, drop, pre_norm=None, next_gain=None, prev=None):
         # without this autograd fills a [cur*B, 2d] bf16 and a [L_NS*B, d] fp32 zero tensor per block and step for the
         # two outputs nobody differentiates (1.3 ms/step at C2, profiles/README.md)
         ctx.set_materialize_grads(False)
@@ -332,17 +337,27 @@ class _BlockFn(torch.autograd.Function):
         if y_hp is None:
             y_hp = y.new_zeros(0, dtype=torch.float32)
         ctx.mark_non_differentiable(kv, y_hp)
-        ctx.saved = (saved, w, blk, B, cur, keep)
+        ctx.saved = (saved, w, blk, B, cur, keep, prev)
         return y, kv, y_hp
 
     @staticmethod
     def backward(ctx, dy, _dkv, _dhp):
         if dy is None:
-            return (None,) * 11
-        saved, w, blk, B, cur, keep = ctx.saved
-        dx = engine.block_backward(dy, saved, blk._params(), w, B, cur, keep, blk.config.num_heads)
+            return (None,) * 12
+        saved, w, blk, B, cur, keep, prev = ctx.saved
+        # masked copy of dy left behind by the block above (its norm1 backward wrote it in the same pass as dy itself)
+        dy_masked = None
+        m = getattr(blk, '_dy_masked', None)
+        if m is not None:
+            object.__setattr__(blk, '_dy_masked', None)
+            if m[1].data_ptr() == dy.data_ptr() and m[1].shape == dy.shape:
+                dy_masked = m[0]
+        dx, dx_m = engine.block_backward(dy, saved, blk._params(), w, B, cur, keep, blk.config.num_heads, dy_masked,
+                                         prev[1] if prev is not None else None)
+        if prev is not None:
+            object.__setattr__(prev[0], '_dy_masked', (dx_m, dx))
         ctx.saved = None
-        return dx, None, None, None, None, None, None, None, None, None, None
+        return dx, None, None, None, None, None, None, None, None, None, None, None
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -486,7 +501,8 @@ class OneTransModel(nn.Module):
             if x_hp is not None:   # the NS rows that survive into this layer's input (suffix of the fp32 stream)
                 x_hp = x_hp[x_hp.shape[0] - min(self.config.num_ns_tokens, cur) * B:]
             next_gain = self.blocks[i + 1].norm1.scale if i + 1 < n_blocks else None
-            x2, _, x_hp = block.forward_token_major(x2, B, cur, keep, training, None, x_hp, pre_norm, next_gain)   # :366-371
+            x2, _, x_hp = block.forward_token_major(x2, B, cur, keep, training, None, x_hp, pre_norm, next_gain,
+                                                    self.blocks[i - 1] if i > 0 else None)                      # :366-371
             pre_norm = block._next_norm
             object.__setattr__(block, '_next_norm', None)
             if x_hp.numel() == 0:

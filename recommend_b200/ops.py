@@ -297,7 +297,9 @@ def rmsnorm_fwd(x: torch.Tensor, gain: torch.Tensor, y: torch.Tensor, rstd: Opti
 
 
 def rmsnorm_bwd(dy: torch.Tensor, x: torch.Tensor, rstd: torch.Tensor, gain: torch.Tensor, dx: torch.Tensor,
-                dgain: torch.Tensor, dres: Optional[torch.Tensor] = None) -> None:
+                dgain: torch.Tensor, dres: Optional[torch.Tensor] = None,
+                drop_out: Optional[Tuple[torch.Tensor, int, float, int]] = None) -> None:
+    """``drop_out = (dx_drop, seed, rate, row0)``: also write ``dropout_mask(dx)`` (mask rows ``row0 + r``) in the same pass."""
     for t, n in ((dy, 'dy'), (x, 'x'), (dx, 'dx')):
         _check_bf16(t, n)
     assert dgain.dtype == torch.float32 and rstd.dtype == torch.float32
@@ -308,9 +310,13 @@ def rmsnorm_bwd(dy: torch.Tensor, x: torch.Tensor, rstd: torch.Tensor, gain: tor
         _check_bf16(dres, 'dres')
         p.dres, p.lddres = dres.data_ptr(), dres.stride(0)
     p.rows, p.d, p.eps = x.shape[0], x.shape[1], 0.0
+    if drop_out is not None:
+        dd, seed, rate, row0 = drop_out
+        _check_bf16(dd, 'dx_drop')
+        p.dx_drop, p.lddx_drop, p.drop_row0, p.drop_seed, p.drop_rate = dd.data_ptr(), dd.stride(0), row0, seed & 0xFFFFFFFF, rate
     if p.rows > 0:
         _run('ot_rmsnorm_bwd', L.load().ot_rmsnorm_bwd, p, f'd{x.shape[1]}', 8.0 * x.numel(),
-             x.numel() * 2.0 * (3 + (dres is not None)) + x.shape[0] * 4.0)
+             x.numel() * 2.0 * (3 + (dres is not None) + (drop_out is not None)) + x.shape[0] * 4.0)
 
 
 def ns_tokenizer_fwd(x: torch.Tensor, W: torch.Tensor, bias: torch.Tensor, out: torch.Tensor, row0: int, B: int,

@@ -84,7 +84,7 @@ def test_position_segments_match_oracle_rule(alignment):
 
 def test_library_loads_and_exports_every_declared_symbol():
     lib = _lib.load()
-    assert lib.ot_version() == 6
+    assert lib.ot_version() == 7
     declared = set(re.findall(r'^\s*(?:int|const char\*)\s+(ot_\w+)\s*\(', open(HEADER).read(), re.M))
     assert declared == set(_lib.EXPORTED_SYMBOLS)
     for name in declared:
