@@ -442,25 +442,36 @@ ot_attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   if (warp == 8) tmem_dealloc(tmem_base, 512);
 }
 
-// delta[b,h,q] = sum_e dO[q,b,h,e] * O[q,b,h,e]   (one thread per (row, head))
+// delta[b,h,q] = sum_e dO[q,b,h,e] * O[q,b,h,e].  dh/8 consecutive lanes share one (row, head): every lane reads one 16-byte
+// chunk of O and of dO (fully coalesced rows) and the partial dot products meet in a shuffle reduction.
+template <int LPH>   // lanes per (row, head) = dh / 8: 8 (dh 64), 4 (dh 32), 16 (dh 128)
 __global__ void __launch_bounds__(256)
 attn_delta_kernel(const __nv_bfloat16* __restrict__ o, long long ldo, const __nv_bfloat16* __restrict__ d_o, long long lddo,
-                  float* __restrict__ delta, int B, int H, int Lq, int dh) {
-  const long long total = (long long)Lq * B * H;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const int h = (int)(idx % H);
-    const long long rowi = idx / H;          // = q*B + b
-    const int b = (int)(rowi % B);
-    const int q = (int)(rowi / B);
-    const uint4* po = reinterpret_cast<const uint4*>(o + rowi * ldo + h * dh);
-    const uint4* pd = reinterpret_cast<const uint4*>(d_o + rowi * lddo + h * dh);
+                  float* __restrict__ delta, int B, int H, int Lq) {
+  const long long total = (long long)Lq * B * H * LPH;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long idx0 = (long long)blockIdx.x * blockDim.x; idx0 < total; idx0 += stride) {   // warp-uniform trip count
+    const long long idx = idx0 + threadIdx.x;
     float acc = 0.0f;
-    for (int ch = 0; ch < dh / 8; ++ch) {
-      const uint4 a = po[ch], g = pd[ch];
-      acc += bf16lo(a.x) * bf16lo(g.x) + bf16hi(a.x) * bf16hi(g.x) + bf16lo(a.y) * bf16lo(g.y) + bf16hi(a.y) * bf16hi(g.y) +
-             bf16lo(a.z) * bf16lo(g.z) + bf16hi(a.z) * bf16hi(g.z) + bf16lo(a.w) * bf16lo(g.w) + bf16hi(a.w) * bf16hi(g.w);
+    long long item = idx / LPH;
+    const int ch = (int)(idx % LPH);
+    const bool live = idx < total;
+    if (!live) item = 0;
+    const int h = (int)(item % H);
+    const long long rowi = item / H;          // = q*B + b
+    if (live) {
+      const uint4 a = reinterpret_cast<const uint4*>(o + rowi * ldo + h * (LPH * 8))[ch];
+      const uint4 g = reinterpret_cast<const uint4*>(d_o + rowi * lddo + h * (LPH * 8))[ch];
+      acc = bf16lo(a.x) * bf16lo(g.x) + bf16hi(a.x) * bf16hi(g.x) + bf16lo(a.y) * bf16lo(g.y) + bf16hi(a.y) * bf16hi(g.y) +
+            bf16lo(a.z) * bf16lo(g.z) + bf16hi(a.z) * bf16hi(g.z) + bf16lo(a.w) * bf16lo(g.w) + bf16hi(a.w) * bf16hi(g.w);
     }
-    delta[((long long)b * H + h) * Lq + q] = acc;
+#pragma unroll
+    for (int off = LPH / 2; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (live && ch == 0) {
+      const int b = (int)(rowi % B);
+      const int q = (int)(rowi / B);
+      delta[((long long)b * H + h) * Lq + q] = acc;
+    }
   }
 }
 
@@ -507,11 +518,15 @@ int attn_bwd_fused_impl(const ot_attn_params* p, cudaStream_t st) {
     OT_CUDA_CHECK(cudaMemset2DAsync(p->dq, (size_t)p->lddq * 2, 0, (size_t)cols * 2, (size_t)p->Lq * p->B, st));
   }
   {
-    const long long total = (long long)p->Lq * p->B * p->H;
+    const int lph = p->head_dim / 8;
+    const long long total = (long long)p->Lq * p->B * p->H * lph;
     long long blocks = (total + 255) / 256;
-    if (blocks > (long long)num_sms() * 16) blocks = (long long)num_sms() * 16;
-    attn_delta_kernel<<<(int)blocks, 256, 0, st>>>((const __nv_bfloat16*)p->o, p->ldo, (const __nv_bfloat16*)p->d_o, p->lddo, p->delta,
-                                                   p->B, p->H, p->Lq, p->head_dim);
+    if (blocks > (long long)num_sms() * 32) blocks = (long long)num_sms() * 32;
+#define OT_LAUNCH_DELTA(N) attn_delta_kernel<N><<<(int)blocks, 256, 0, st>>>((const __nv_bfloat16*)p->o, p->ldo, (const __nv_bfloat16*)p->d_o, \
+                                                                             p->lddo, p->delta, p->B, p->H, p->Lq)
+    if (lph == 8) OT_LAUNCH_DELTA(8); else if (lph == 4) OT_LAUNCH_DELTA(4); else if (lph == 16) OT_LAUNCH_DELTA(16);
+    else OT_FAIL(OT_ERR_UNSUPPORTED_SHAPE, "ot_attn_bwd: head_dim=%d", p->head_dim);
+#undef OT_LAUNCH_DELTA
     OT_CUDA_CHECK(cudaGetLastError());
   }
   const int sms = num_sms();
