@@ -31,7 +31,7 @@ static constexpr int CTRL_THREADS = 128;      // one control warpgroup: warp 0 T
 static constexpr int GEMM_THREADS = CTRL_THREADS + EPI_THREADS;   // + 16 epilogue warps (warps 4..19)
 static constexpr int EPI_REGS = 112, CTRL_REGS = 32;   // setmaxnreg: the control warpgroup releases 4*32*(96-32) registers into the CTA pool, exactly what the four epilogue warpgroups take (4*128*(112-96)); asking for more than was released spins forever
 static constexpr int EPI_BAR_ID = 1;         // named barriers 1..4: one per epilogue set
-static constexpr int EPI_BAR_NORM = 5;       // all active epilogue sets (row statistics of the fused RMSNorm)
+static constexpr int EPI_BAR_NORM = 5;       // 5..8: the sets working on one tile (row statistics of the fused RMSNorm)
 static constexpr int CHUNK = 64;             // epilogue column chunk (128 bytes of bf16 per row)
 static constexpr int CH_BYTES = 128 * 64 * 2;   // one staged chunk: 128 rows x 128 bytes
 
@@ -235,7 +235,12 @@ ot_mixed_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     uint8_t* buf = staging + set * CH_BYTES;
     uint64_t* in_bar = &in_bars[set];
     uint32_t in_phase = 0;
-    const bool has_chunk = set < BN / CHUNK;
+    // A tile has BN/64 chunks; with BN < 256 the sets form 4/(BN/64) groups that take the CTA's tiles in turn (group g
+    // owns tiles it % n_grp == g, i.e. always the same TMEM accumulator when n_grp == 2), so no set idles and every set
+    // has n_grp tile periods between two of its chunks - room to prefetch its auxiliary input.
+    constexpr int SPT = BN / CHUNK;                 // sets per tile
+    constexpr int N_GRP = EPI_SETS / SPT;           // set groups
+    const int my_grp = set / SPT;
     const bool io_thread = (et == 0);
     const bool f_bias = p.flags & OT_EPI_BIAS, f_gelu = p.flags & OT_EPI_GELU, f_res = p.flags & OT_EPI_RESIDUAL;
     const bool f_ggrad = p.flags & OT_EPI_GELU_GRAD, f_rs = p.flags & OT_EPI_ROW_SCALE, f_drop = p.flags & OT_EPI_DROPOUT;
@@ -253,10 +258,10 @@ ot_mixed_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       const TileInfo t = decode_tile(p, mblk);
       if (tma_in_tile(t)) {
         mbar_arrive_expect_tx(in_bar, CH_BYTES);
-        tma_load_2d(buf, &tmIn, in_bar, (tile - mblk * p.n_nblks) * BN + set * CHUNK, t.row0);
+        tma_load_2d(buf, &tmIn, in_bar, (tile - mblk * p.n_nblks) * BN + (set % SPT) * CHUNK, t.row0);
       }
     };
-    if (has_chunk && io_thread && has_in && (int)blockIdx.x < total_tiles) issue_in(blockIdx.x);
+    if (io_thread && has_in && (int)(blockIdx.x + my_grp * gridDim.x) < total_tiles) issue_in(blockIdx.x + my_grp * gridDim.x);
 
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -278,8 +283,8 @@ ot_mixed_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       mbar_wait_backoff(&tfull_bar[acc], acc_phase, 32);
       tc_fence_after();
 
-      if (has_chunk) {
-        const int c = set;
+      if ((it % N_GRP) == my_grp) {
+        const int c = set % SPT;
         const int col0 = n0 + c * CHUNK;
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(lgrp * 32) << 16) + acc * BN + c * CHUNK;
         const float* bias_g = f_bias ? p.bias + (long long)t.group * p.bias_group_stride + col0 : nullptr;
@@ -443,15 +448,15 @@ ot_mixed_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 #pragma unroll
             for (int e = 0; e < 8; ++e) ss = fmaf(x[e], x[e], ss);
           }
-          float* ssb = ss_part + (it & 1) * (EPI_SETS * BM);
+          float* ssb = ss_part + ((it / N_GRP) & 1) * (EPI_SETS * BM);   // alternates between two consecutive tiles of a set
           ssb[set * BM + r_own] = ss;
           if (tma_out && io_thread) bulk_wait_read0();          // the `out` rows have left the staging tile
-          named_bar_sync(EPI_BAR_NORM, EPI_SET_THREADS * (BN / CHUNK));
+          named_bar_sync(EPI_BAR_NORM + my_grp, EPI_SET_THREADS * SPT);
           float tot = 0.0f;
 #pragma unroll
-          for (int s2 = 0; s2 < BN / CHUNK; ++s2) tot += ssb[s2 * BM + r_own];
+          for (int s2 = 0; s2 < SPT; ++s2) tot += ssb[(my_grp * SPT + s2) * BM + r_own];
           const float rstd = rsqrtf(tot / (float)p.N + p.norm_eps);
-          if (set == 0 && r_own < t.valid && p.norm_rstd != nullptr) p.norm_rstd[t.row0 + r_own] = rstd;
+          if (c == 0 && r_own < t.valid && p.norm_rstd != nullptr) p.norm_rstd[t.row0 + r_own] = rstd;
 #pragma unroll
           for (int ch = 0; ch < 8; ++ch) {
             float x[8];
@@ -478,9 +483,9 @@ ot_mixed_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           }
         }
         // prefetch the auxiliary input of this set's chunk in the CTA's next tile
-        if (io_thread && has_in && tile + (int)gridDim.x < total_tiles) {
+        if (io_thread && has_in && tile + N_GRP * (int)gridDim.x < total_tiles) {
           bulk_wait_read0();
-          issue_in(tile + gridDim.x);
+          issue_in(tile + N_GRP * gridDim.x);
         }
       }
       // all TMEM reads of this accumulator are complete -> hand it back to the MMA warp

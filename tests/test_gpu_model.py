@@ -116,6 +116,23 @@ def test_onetrans_l_shapes():
     _check(_run_pair(ocfg, cfg, B=24, seq_lens=(60, 50, 40)))
 
 
+def test_c4_long_sequence_halving():
+    """BASELINE config 4 shapes: three behaviour sequences concatenated to 2048 tokens (2016 S + 32 NS), query set
+    halved per block (1024, 512, ... 32); batch cut to 8 so that the fp32 oracle finishes in seconds."""
+    ocfg, cfg = make_configs(num_ns_tokens=32, schedule='halving')
+    out = _run_pair(ocfg, cfg, B=8, seq_lens=(672, 671, 671))
+    assert R.resolve_keep_lens(cfg, 2048) == [1024, 512, 256, 128, 64, 32]
+    _check(out)
+
+
+def test_c2_sequence_length_linear_to_ns():
+    """BASELINE config 2 token counts (512 S + 32 NS, linear_to_ns = [458, 373, 288, 202, 117, 32]) at batch 32."""
+    ocfg, cfg = make_configs(num_ns_tokens=32, schedule='linear_to_ns')
+    out = _run_pair(ocfg, cfg, B=32, seq_lens=(170, 170, 170))
+    assert R.resolve_keep_lens(cfg, 544) == [458, 373, 288, 202, 117, 32]
+    _check(out)
+
+
 def test_pyramid_disabled_and_missing_sequence():
     ocfg, cfg = make_configs(num_layers=2, num_ns_tokens=4, pyramid_enabled=False)
     _check(_run_pair(ocfg, cfg, B=8, seq_lens=(20, 10, 5), present=('click_seq', 'purchase_seq')))
