@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define OT_ABI_VERSION 7
+#define OT_ABI_VERSION 8
 
 int ot_version(void);
 const char* ot_last_error_string(void);
@@ -286,6 +286,35 @@ typedef struct ot_rmsprop_params {
   int32_t zero_grad;
 } ot_rmsprop_params;
 int ot_clip_rmsprop_step(const ot_rmsprop_params* p, void* stream);
+
+/* ---- ID front end of the sequence tokenizer (north_star item 1; extension of OT/model.py:217-219 along PAPER:89-109 and
+ * the lookup-and-concat idiom of recall/bert_like/kuaiformer/practice/model.py:58-94).  One fp32 table holds the rows of
+ * all fields back to back: field f owns rows [field_off[f], field_off[f] + field_rows[f]), every row has `ef` floats.
+ *   ot_embed_gather_fwd  : events[e, f*ef + j] = bf16(table[(field_off[f] + ids[e, f]) * ef + j])      (bit-exact copy)
+ *   ot_embed_scatter_bwd : grad[(field_off[f] + ids[e, f]) * ef + j] += events[e, f*ef + j]   (events = d loss / d events)
+ *   ot_embed_adagrad_step: once per row present in ids:  acc += g*g ; table -= lr * g / (sqrt(acc) + eps) ; g = 0
+ *                          (Keras Adagrad on the summed sparse gradient; OT/config.py:39-47 sparse_optimizer / sparse_lr)
+ * ids: int32 [n_events, n_fields]; ids outside [0, field_rows[f]) give a zero row and are counted in *bad_ids (may be NULL).
+ * stamp: int32 [total rows], zero-initialised by the caller, step_id != 0 and different from the previous step's.
+ * field_off / field_rows are int64 DEVICE arrays. */
+typedef struct ot_embed_params {
+  const float* table;
+  const int64_t* field_off;
+  const int64_t* field_rows;
+  const int32_t* ids;
+  void* events; int64_t ld_events;   /* bf16 [n_events, n_fields*ef] */
+  int64_t n_events;
+  int32_t n_fields, ef;              /* ef % 8 == 0 */
+  int32_t* bad_ids;
+  float* grad;                       /* fp32, same shape as table */
+  float* acc;                        /* Adagrad accumulator, same shape */
+  int32_t* stamp;
+  int32_t step_id;
+  float lr, eps;
+} ot_embed_params;
+int ot_embed_gather_fwd(const ot_embed_params* p, void* stream);
+int ot_embed_scatter_bwd(const ot_embed_params* p, void* stream);
+int ot_embed_adagrad_step(const ot_embed_params* p, void* stream);
 
 #ifdef __cplusplus
 }

@@ -438,6 +438,37 @@ def clip_rmsprop_update(params: Dict[str, torch.Tensor], grads: Dict[str, torch.
         params[name] = nw
 
 
+def embed_events(table: torch.Tensor, vocab_sizes: Sequence[int], ids: torch.Tensor, out_dtype=torch.bfloat16) -> torch.Tensor:
+    """ID front end of the sequence tokenizer (extension along PAPER:89-109; lookup-and-concat idiom of
+    recall/bert_like/kuaiformer/practice/model.py:58-94): ``ids [..., n_fields]`` -> concat over fields of
+    ``table[field_off[f] + ids[..., f]]``, rounded to the dtype the tokenizer reads its events in."""
+    off, cols = 0, []
+    for f, v in enumerate(vocab_sizes):
+        cols.append(table[off + ids[..., f].long()])
+        off += v
+    return torch.cat(cols, dim=-1).to(out_dtype)
+
+
+def embed_grad_table(table: torch.Tensor, vocab_sizes: Sequence[int], ids: torch.Tensor, d_events: torch.Tensor) -> torch.Tensor:
+    """Dense view of the sparse gradient ``tape.gradient`` gives an Embedding (IndexedSlices summed per row)."""
+    g = torch.zeros_like(table, dtype=torch.float64)
+    ef = table.shape[1]
+    off = 0
+    flat_ids = ids.reshape(-1, len(vocab_sizes))
+    d2 = d_events.reshape(-1, len(vocab_sizes) * ef).double()
+    for f, v in enumerate(vocab_sizes):
+        g.index_add_(0, off + flat_ids[:, f].long(), d2[:, f * ef:(f + 1) * ef])
+        off += v
+    return g
+
+
+def adagrad_step(w: torch.Tensor, g: torch.Tensor, acc: torch.Tensor, lr: float = 0.1, eps: float = 1e-7):
+    """Keras-2.12 ``Adagrad.update_step`` (sparse_optimizer of OT/config.py:39-47; initial accumulator 0.1):
+    ``acc += g^2; w -= lr * g / (sqrt(acc) + eps)``.  Returns the new (w, acc)."""
+    acc = acc + g * g
+    return w - lr * g / (torch.sqrt(acc) + eps), acc
+
+
 # ---------------------------------------------------------------------------------------------------
 # synthetic inputs  (SURVEY.md §8d; OT/data_loader.py:301-329, :146-154)
 # ---------------------------------------------------------------------------------------------------

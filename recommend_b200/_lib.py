@@ -80,13 +80,19 @@ class RmspropParams(C.Structure):
                 ('clip_norm', C.c_float), ('grad_scale', C.c_float), ('zero_grad', i32)]
 
 
+class EmbedParams(C.Structure):
+    _fields_ = [('table', fp), ('field_off', vp), ('field_rows', vp), ('ids', vp), ('events', vp), ('ld_events', i64),
+                ('n_events', i64), ('n_fields', i32), ('ef', i32), ('bad_ids', vp), ('grad', fp), ('acc', fp), ('stamp', vp),
+                ('step_id', i32), ('lr', C.c_float), ('eps', C.c_float)]
+
+
 OPT_CHUNK = 1024  # OT_OPT_CHUNK
 
 # every symbol include/onetrans_b200.h declares (tests check that the library exports all of them)
 EXPORTED_SYMBOLS = [
     'ot_version', 'ot_last_error_string', 'ot_num_sms', 'ot_mixed_gemm', 'ot_wgrad', 'ot_attn_fwd', 'ot_attn_bwd', 'ot_attn_ns_cached_fwd',
     'ot_rmsnorm_fwd', 'ot_rmsnorm_bwd', 'ot_ns_tokenizer_fwd', 'ot_ns_tokenizer_bwd', 'ot_fill_rows', 'ot_colsum', 'ot_dropout_mask',
-    'ot_clip_rmsprop_step',
+    'ot_clip_rmsprop_step', 'ot_embed_gather_fwd', 'ot_embed_scatter_bwd', 'ot_embed_adagrad_step',
 ]
 
 _lib = None
@@ -116,7 +122,8 @@ def load() -> C.CDLL:
         for name, st in [('ot_mixed_gemm', GemmParams), ('ot_wgrad', WgradParams), ('ot_attn_fwd', AttnParams),
                          ('ot_attn_bwd', AttnParams), ('ot_attn_ns_cached_fwd', AttnCachedParams), ('ot_rmsnorm_fwd', RmsnormParams), ('ot_rmsnorm_bwd', RmsnormParams),
                          ('ot_ns_tokenizer_fwd', NsTokenizerParams), ('ot_ns_tokenizer_bwd', NsTokenizerParams),
-                         ('ot_colsum', ColsumParams), ('ot_clip_rmsprop_step', RmspropParams)]:
+                         ('ot_colsum', ColsumParams), ('ot_clip_rmsprop_step', RmspropParams), ('ot_embed_gather_fwd', EmbedParams),
+                         ('ot_embed_scatter_bwd', EmbedParams), ('ot_embed_adagrad_step', EmbedParams)]:
             fn = getattr(lib, name)
             fn.argtypes = [C.POINTER(st), C.c_void_p]
             fn.restype = C.c_int

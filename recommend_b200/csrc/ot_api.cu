@@ -52,6 +52,9 @@ int colsum_impl(const ot_colsum_params* p, cudaStream_t st);
 int dropout_mask_impl(const void* in, long long ld_in, void* out, long long ld_out, long long rows, int cols, uint32_t seed,
                       float rate, cudaStream_t st);
 int clip_rmsprop_impl(const ot_rmsprop_params* p, cudaStream_t st);
+int embed_gather_impl(const ot_embed_params* p, cudaStream_t st);
+int embed_scatter_impl(const ot_embed_params* p, cudaStream_t st);
+int embed_adagrad_impl(const ot_embed_params* p, cudaStream_t st);
 
 }  // namespace ot
 
@@ -91,5 +94,8 @@ int ot_dropout_mask(const void* in, int64_t ld_in, void* out, int64_t ld_out, in
   return ot::dropout_mask_impl(in, ld_in, out, ld_out, rows, cols, seed, rate, static_cast<cudaStream_t>(stream));
 }
 int ot_clip_rmsprop_step(const ot_rmsprop_params* p, void* stream) { return ot::clip_rmsprop_impl(p, static_cast<cudaStream_t>(stream)); }
+int ot_embed_gather_fwd(const ot_embed_params* p, void* stream) { return ot::embed_gather_impl(p, static_cast<cudaStream_t>(stream)); }
+int ot_embed_scatter_bwd(const ot_embed_params* p, void* stream) { return ot::embed_scatter_impl(p, static_cast<cudaStream_t>(stream)); }
+int ot_embed_adagrad_step(const ot_embed_params* p, void* stream) { return ot::embed_adagrad_impl(p, static_cast<cudaStream_t>(stream)); }
 
 }  // extern "C"

@@ -319,11 +319,15 @@ def tokenizer_forward(ns_x: Optional[torch.Tensor], seq_list: Sequence[Optional[
     return X0, L, layout, X_hp
 
 
-def tokenizer_backward(dX0: torch.Tensor, ns_x, seq_list, layout, B: int, d: int, L_ns: int, Ws, bs, sep, Wns, bns) -> None:
-    """Accumulate the tokenizer's parameter gradients from dX0 (no input gradients: inputs are data)."""
+def tokenizer_backward(dX0: torch.Tensor, ns_x, seq_list, layout, B: int, d: int, L_ns: int, Ws, bs, sep, Wns, bns,
+                       want_event_grads: Sequence[int] = ()) -> Dict[int, torch.Tensor]:
+    """Accumulate the tokenizer's parameter gradients from dX0.  The scalar inputs are data; for the sequences listed
+    in ``want_event_grads`` (events that came out of an ``EventEmbedding``) the event gradients
+    ``dX0_rows @ Ws[i]^T`` are returned as ``{i: [B, L_i, E]}`` (a transposed view of a token-major buffer)."""
     if not dX0.is_contiguous():
         dX0 = dX0.contiguous()
     L_s = sum(n for _, _, _, n in layout)
+    d_events: Dict[int, torch.Tensor] = {}
     for kind, i, p0, n in layout:
         rows = dX0[p0 * B:(p0 + n) * B]
         if kind == 'seq':
@@ -334,10 +338,15 @@ def tokenizer_backward(dX0: torch.Tensor, ns_x, seq_list, layout, B: int, d: int
                             q_stride_unit=E, n_units=n, rows_per_unit=B, group_start=0, group_stride=0)],
                       _grad_buf(Ws[i]), d, E, 0, 1, d)
             ops.colsum(dX0, [(p0 * B, 1, n * B, 0, 0)], _grad_buf(bs[i]), 0)
+            if i in want_event_grads:
+                de = torch.empty(n * B, E, dtype=bf16, device=dX0.device)                  # rows (l, b), token-major
+                ops.mixed_gemm(rows, Ws[i].detach().to(bf16).unsqueeze(0), [(0, 1, n * B, 0, 0)], de)   # [E, d] is W[N, K] as stored
+                d_events[i] = de.view(n, B, E).transpose(0, 1)
         else:
             ops.colsum(dX0, [(p0 * B, 1, B, 0, 0)], _grad_buf(sep), 0)
     if ns_x is not None:
         ops.ns_tokenizer_bwd(ns_x, dX0, _grad_buf(Wns), _grad_buf(bns), L_s * B, B, L_ns, d)
+    return d_events
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -413,7 +413,7 @@ class Tokenizer(nn.Module):
 
     def forward_token_major(self, non_seq_features, seq_features):
         ns_x, seq_list, B = self._gather_inputs(non_seq_features, seq_features)
-        X0, L, X_hp = _TokenizerFn.apply(self.ns_kernel, self, ns_x, seq_list, B)
+        X0, L, X_hp = _TokenizerFn.apply(self.ns_kernel, self, ns_x, seq_list, B, *[e for e in seq_list if e is not None])
         self._last_hp = X_hp if X_hp.numel() else None
         return X0, B, L
 
@@ -424,7 +424,9 @@ class Tokenizer(nn.Module):
 
 class _TokenizerFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, anchor, tok: Tokenizer, ns_x, seq_list, B):
+    def forward(ctx, anchor, tok: Tokenizer, ns_x, seq_list, B, *events):
+        # ``events`` repeats the present entries of seq_list as explicit tensor arguments so that autograd can hand a
+        # gradient back to an EventEmbedding in front of the tokenizer
         ctx.set_materialize_grads(False)
         cfg = tok.config
         d, L_ns = cfg.hidden_dim, cfg.num_ns_tokens
@@ -435,17 +437,20 @@ class _TokenizerFn(torch.autograd.Function):
             X_hp = X0.new_zeros(0, dtype=torch.float32)
         ctx.mark_non_differentiable(X_hp)
         ctx.saved = (tok, ns_x, seq_list, layout, B)
+        ctx.present = [i for i, e in enumerate(seq_list) if e is not None]
         return X0, L, X_hp
 
     @staticmethod
     def backward(ctx, dX0, _dL=None, _dhp=None):
+        n_ev = len(ctx.present)
         if dX0 is None:
-            return None, None, None, None, None
+            return (None,) * (5 + n_ev)
         tok, ns_x, seq_list, layout, B = ctx.saved
         cfg = tok.config
-        engine.tokenizer_backward(dX0, ns_x, seq_list, layout, B, cfg.hidden_dim, cfg.num_ns_tokens, list(tok.seq_kernels),
-                                  list(tok.seq_biases), tok.sep_embedding, tok.ns_kernel, tok.ns_bias)
-        return None, None, None, None, None
+        want = [i for j, i in enumerate(ctx.present) if ctx.needs_input_grad[5 + j]]
+        d_ev = engine.tokenizer_backward(dX0, ns_x, seq_list, layout, B, cfg.hidden_dim, cfg.num_ns_tokens, list(tok.seq_kernels),
+                                         list(tok.seq_biases), tok.sep_embedding, tok.ns_kernel, tok.ns_bias, want)
+        return (None, None, None, None, None) + tuple(d_ev.get(i) for i in ctx.present)
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -240,3 +240,19 @@ def test_T12_clip_and_rmsprop_hand_computed():
     # momentum 0: plain step, mom untouched
     w3, _, mom3 = O.rmsprop_step(w, g, rms, None, lr, rho, 0.0, eps)
     assert mom3 is None and torch.allclose(w3, w1, rtol=1e-14)
+
+
+def test_T13_event_embedding_lookup_concat_and_adagrad():
+    """ID front end (extension, SURVEY §8f rank 2): lookup-and-concat is a copy; sparse gradient == summed IndexedSlices;
+    Keras Adagrad by hand."""
+    table = torch.arange(5 * 2, dtype=torch.float32).reshape(5, 2)          # field 0: rows 0-2, field 1: rows 3-4
+    ids = torch.tensor([[[2, 1], [0, 0]], [[2, 0], [1, 1]]])                # [B=2, L=2, 2 fields]
+    ev = O.embed_events(table, [3, 2], ids, out_dtype=torch.float32)
+    assert ev.shape == (2, 2, 4)
+    assert torch.equal(ev[0, 0], torch.tensor([4., 5., 8., 9.]))            # row 2 | row 3+1
+    assert torch.equal(ev[1, 1], torch.tensor([2., 3., 8., 9.]))
+    d = torch.ones(2, 2, 4)
+    g = O.embed_grad_table(table, [3, 2], ids, d)
+    assert torch.equal(g[:, 0], torch.tensor([1., 1., 2., 2., 2.], dtype=torch.float64))   # row 2 twice, rows 3 and 4 twice each
+    w, acc = O.adagrad_step(torch.tensor([1.0]), torch.tensor([2.0]), torch.tensor([0.1]), lr=0.1, eps=1e-7)
+    assert abs(float(acc) - 4.1) < 1e-6 and abs(float(w) - (1.0 - 0.1 * 2.0 / (4.1 ** 0.5 + 1e-7))) < 1e-6
