@@ -1,6 +1,10 @@
 // ot_api.cu — the C-ABI surface of libonetrans_sm100.so (include/onetrans_b200.h): thin extern "C"
 // wrappers that validate, build tensor maps and enqueue the sm_100a kernels on the caller's stream.
 // No C++ exception crosses this boundary, nothing here allocates device memory or synchronises.
+#include <atomic>
+#include <cstdlib>
+#include <mutex>
+
 #include "ot_host.h"
 #include "../../include/onetrans_b200.h"
 
@@ -24,6 +28,30 @@ PFN_cuTensorMapEncodeTiled get_encode_fn() {
     }
   }
   return fn;
+}
+
+// Work counters of the persistent kernels (dynamic tile / item scheduling): a per-device ring of 1024 ints, allocated once
+// on first use (the only device allocation the library ever makes, 4 KB); every launch takes the next slot and zeroes it
+// on its stream.  OT_STATIC_SCHED=1 (or a failed allocation) returns NULL = static round-robin schedule.
+int* sched_slot(cudaStream_t st) {
+  static int* base[64] = {nullptr};
+  static std::atomic<unsigned> next[64];
+  static std::mutex mu;
+  static const bool disabled = [] { const char* e = getenv("OT_STATIC_SCHED"); return e && e[0] && e[0] != '0'; }();
+  if (disabled) return nullptr;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (base[dev] == nullptr) {
+    std::lock_guard<std::mutex> lk(mu);
+    if (base[dev] == nullptr) {
+      int* ptr = nullptr;
+      if (cudaMalloc(&ptr, 1024 * sizeof(int)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+      base[dev] = ptr;
+    }
+  }
+  int* slot = base[dev] + (next[dev].fetch_add(1) % 1024u);
+  if (cudaMemsetAsync(slot, 0, sizeof(int), st) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return slot;
 }
 
 int num_sms() {

@@ -34,6 +34,7 @@ static constexpr int EPI_BAR_ID = 1;         // named barriers 1..4: one per epi
 static constexpr int EPI_BAR_NORM = 5;       // 5..8: the sets working on one tile (row statistics of the fused RMSNorm)
 static constexpr int CHUNK = 64;             // epilogue column chunk (128 bytes of bf16 per row)
 static constexpr int CH_BYTES = 128 * 64 * 2;   // one staged chunk: 128 rows x 128 bytes
+static constexpr int TILE_SLOTS = 8;         // tile-index ring: producer -> MMA issuer and epilogue warps
 
 struct GemmSegDev {
   int row_start, n_units, rows_per_unit, group_start, group_stride, a_row_start;
@@ -58,6 +59,7 @@ struct GemmKParams {
   const float* res_hp; float* out_hp; long long ld_hp; long long hp_row0;
   uint32_t drop_seed, drop_thr16; float drop_scale;
   __nv_bfloat16* norm_out; long long ld_norm; const float* norm_gain; float* norm_rstd; float norm_eps;
+  int* sched;              // dynamic tile counter (zeroed by the launcher) or NULL = static round-robin
 };
 
 struct TileInfo {
@@ -103,10 +105,10 @@ struct GemmCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGING_BYTES = EPI_SETS * BM * CHUNK * 2;  // one 128x64 bf16 buffer per epilogue set
   static constexpr int NORM_BYTES = 2 * EPI_SETS * BM * 4;        // fused RMSNorm: per-set partial sums of squares, double-buffered
-  static constexpr int BUDGET = 227 * 1024 - STAGING_BYTES - NORM_BYTES - 256;
+  static constexpr int BUDGET = 227 * 1024 - STAGING_BYTES - NORM_BYTES - 512;
   static constexpr int STAGES_RAW = BUDGET / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + NORM_BYTES + 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + NORM_BYTES + 512;
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
                                    : (2 * BN <= 256) ? 256 : 512;
 };
@@ -130,7 +132,10 @@ ot_mixed_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   uint64_t* tfull_bar = bars + 2 * STAGES;   // [2]
   uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]
   uint64_t* in_bars = bars + 2 * STAGES + 4;     // [EPI_SETS] auxiliary-input tiles
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4 + EPI_SETS);
+  uint64_t* tile_full = bars + 2 * STAGES + 4 + EPI_SETS;                 // [TILE_SLOTS] tile index published
+  uint64_t* tile_empty = tile_full + TILE_SLOTS;                          // [TILE_SLOTS] read by the MMA issuer + 16 epilogue warps
+  int* tile_ring = reinterpret_cast<int*>(tile_empty + TILE_SLOTS);       // [TILE_SLOTS] tile index or -1 (no more work)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tile_ring + TILE_SLOTS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -151,6 +156,7 @@ ot_mixed_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       mbar_init(&tempty_bar[i], 4 * EPI_SETS);
     }
     for (int i = 0; i < EPI_SETS; ++i) mbar_init(&in_bars[i], 1);
+    for (int i = 0; i < TILE_SLOTS; ++i) { mbar_init(&tile_full[i], 1); mbar_init(&tile_empty[i], 1 + 4 * EPI_SETS); }
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -166,9 +172,24 @@ ot_mixed_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect_one()) {
+      // Tile schedule: every CTA starts with tile blockIdx.x; afterwards tiles come from a device-wide counter
+      // (p.sched) so that CTAs which start late - e.g. because a collective holds their SM - simply take fewer tiles
+      // instead of becoming stragglers.  The index travels to the MMA issuer and the epilogue warps through a small
+      // ring; -1 ends the kernel.  The next index is fetched while this tile's loads are issued.
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int n = 0;
+      int tile = blockIdx.x;
+      while (true) {
+        const int slot = n & (TILE_SLOTS - 1);
+        mbar_wait_backoff(&tile_empty[slot], ((n / TILE_SLOTS) & 1) ^ 1);
+        tile_ring[slot] = tile;
+        mbar_arrive(&tile_full[slot]);
+        if (tile < 0) break;
+        int nxt;
+        if (p.sched != nullptr) nxt = (int)gridDim.x + atomicAdd(p.sched, 1);
+        else nxt = tile + (int)gridDim.x;
+        if (nxt >= total_tiles) nxt = -1;
         const int mblk = div_rcp(tile, p.nn_rcp, p.n_nblks);
         const int nblk = tile - mblk * p.n_nblks;
         const TileInfo t = decode_tile(p, mblk);
@@ -182,6 +203,8 @@ ot_mixed_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, w_row);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        tile = nxt;
+        ++n;
       }
     }
   } else if (warp == 1) {
@@ -190,8 +213,12 @@ ot_mixed_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      for (int it = 0;; ++it) {
+        const int slot = it & (TILE_SLOTS - 1);
+        mbar_wait_backoff(&tile_full[slot], (it / TILE_SLOTS) & 1, 32);
+        const int tile = tile_ring[slot];
+        mbar_arrive(&tile_empty[slot]);
+        if (tile < 0) break;
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait_backoff(&tempty_bar[acc], acc_phase ^ 1);
@@ -261,10 +288,36 @@ ot_mixed_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         tma_load_2d(buf, &tmIn, in_bar, (tile - mblk * p.n_nblks) * BN + (set % SPT) * CHUNK, t.row0);
       }
     };
-    if (io_thread && has_in && (int)(blockIdx.x + my_grp * gridDim.x) < total_tiles) issue_in(blockIdx.x + my_grp * gridDim.x);
+    // tile index of ring entry n without consuming it (the entry is released when this warp reaches iteration n)
+    auto peek = [&](int n) {
+      const int slot = n & (TILE_SLOTS - 1);
+      mbar_wait_backoff(&tile_full[slot], (n / TILE_SLOTS) & 1, 32);
+      return tile_ring[slot];
+    };
+    // the tile `ahead` entries after entry n, or -1 when the schedule ends before it
+    auto tile_after = [&](int n, int ahead) {
+      int tl = -1;
+      for (int j = 1; j <= ahead; ++j) {
+        tl = peek(n + j);
+        if (tl < 0) break;
+      }
+      return tl;
+    };
+    if (io_thread && has_in) {               // this set's first tile is ring entry my_grp
+      const int first = my_grp == 0 ? (int)blockIdx.x : tile_after(0, my_grp);
+      if (first >= 0) issue_in(first);
+    }
 
-    int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int it = 0;; ++it) {
+      int tile;
+      {
+        const int slot = it & (TILE_SLOTS - 1);
+        mbar_wait_backoff(&tile_full[slot], (it / TILE_SLOTS) & 1, 32);
+        tile = tile_ring[slot];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tile_empty[slot]);
+      }
+      if (tile < 0) break;
       const int mblk = div_rcp(tile, p.nn_rcp, p.n_nblks);
       const int nblk = tile - mblk * p.n_nblks;
       const TileInfo t = decode_tile(p, mblk);
@@ -483,9 +536,12 @@ ot_mixed_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           }
         }
         // prefetch the auxiliary input of this set's chunk in the CTA's next tile
-        if (io_thread && has_in && tile + N_GRP * (int)gridDim.x < total_tiles) {
-          bulk_wait_read0();
-          issue_in(tile + N_GRP * gridDim.x);
+        if (io_thread && has_in) {
+          const int nxt = tile_after(it, N_GRP);
+          if (nxt >= 0) {
+            bulk_wait_read0();
+            issue_in(nxt);
+          }
         }
       }
       // all TMEM reads of this accumulator are complete -> hand it back to the MMA warp
@@ -578,6 +634,7 @@ int mixed_gemm_impl(const ot_gemm_params* p, cudaStream_t st) {
   kp.res_hp = p->res_hp; kp.out_hp = p->out_hp; kp.ld_hp = p->ld_hp; kp.hp_row0 = p->hp_row0;
   kp.norm_out = (__nv_bfloat16*)p->norm_out; kp.ld_norm = p->ld_norm; kp.norm_gain = p->norm_gain; kp.norm_rstd = p->norm_rstd;
   kp.norm_eps = p->norm_eps;
+  kp.sched = sched_slot(st);
   if (p->flags & OT_EPI_DROPOUT) {
     if (!(p->drop_rate >= 0.0f && p->drop_rate < 1.0f)) OT_FAIL(OT_ERR_INVALID_ARG, "ot_mixed_gemm: drop_rate=%f", (double)p->drop_rate);
     kp.drop_seed = p->drop_seed; kp.drop_thr16 = (uint32_t)(p->drop_rate * 65536.0f + 0.5f); kp.drop_scale = 1.0f / (1.0f - p->drop_rate);

@@ -69,5 +69,6 @@ inline int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const ui
 }
 
 int num_sms();  // cached SM count of the current device (ot_api.cu)
+int* sched_slot(cudaStream_t st);  // zeroed work counter for one persistent-kernel launch, or NULL (static schedule)
 
 }  // namespace ot
