@@ -31,6 +31,7 @@ struct AttnBwdFusedKParams {
   __nv_bfloat16* dv; long long lddv;
   int dbg;   // profiling experiments only (env OT_DEBUG_ATTN_BWD): bit0 = skip the dQ reductions, bit1 = phase timers
   unsigned long long* dbg_buf;
+  int* sched;   // dynamic work counter (zeroed by the launcher) or NULL = static round-robin
 };
 
 static constexpr float kLog2eF = 1.4426950408889634f;
@@ -63,8 +64,13 @@ enum { SI_FIRST = 1, SI_LAST = 2, SI_END = 4, SI_KVBUF = 8 };
 
 // Walks the (item, query tile) steps of one CTA in launch order (loader warp only).
 struct StepCursor {
-  int item, ii, n_i, i_min, h, b, k0, item_idx;
+  int item, next_item, ii, n_i, i_min, h, b, k0, item_idx;
   bool valid;
+  // After its first item (blockIdx.x) a CTA draws items from a device-wide counter (p.sched): a CTA that starts late
+  // takes fewer items instead of finishing last.  The following item is fetched when the current one is set up.
+  __device__ __forceinline__ void fetch_next(const AttnBwdFusedKParams& p) {
+    next_item = p.sched != nullptr ? (int)gridDim.x + atomicAdd(p.sched, 1) : item + (int)gridDim.x;
+  }
   __device__ __forceinline__ void load_item(const AttnBwdFusedKParams& p) {
     valid = item < p.total_items;
     if (!valid) return;
@@ -78,16 +84,21 @@ struct StepCursor {
     n_i = p.n_qt - i_min;
     ii = 0;
   }
-  __device__ __forceinline__ void init(const AttnBwdFusedKParams& p) {
+  // `walker`: the loader's cursor, which goes on to later items (and therefore draws from the counter); everybody else
+  // only looks at the CTA's first item
+  __device__ __forceinline__ void init(const AttnBwdFusedKParams& p, bool walker) {
     item = blockIdx.x;
+    next_item = p.total_items;
     item_idx = 0;
     load_item(p);
+    if (walker && valid) fetch_next(p);
   }
   __device__ __forceinline__ void next(const AttnBwdFusedKParams& p) {
     if (++ii == n_i) {
-      item += gridDim.x;
+      item = next_item;
       ++item_idx;
       load_item(p);
+      if (valid) fetch_next(p);
     }
   }
   __device__ __forceinline__ int q0() const { return (i_min + ii) * 128; }
@@ -150,7 +161,7 @@ ot_attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     // ============================== loader warp: step ring + TMA ==============================
     if (elect_one()) {
       StepCursor c;
-      c.init(p);
+      c.init(p, true);
       uint32_t t = 0;
       while (c.valid) {
         const int st = t % Cfg::Q_STAGES;
@@ -336,7 +347,7 @@ ot_attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     float lse_raw = 0.0f, delta = 0.0f;
     {
       StepCursor c0;
-      c0.init(p);
+      c0.init(p, false);
       if (c0.q0() + row < p.Lq) {
         const long long si0 = ((long long)c0.b * p.H + c0.h) * p.Lq + c0.q0() + row;
         lse_raw = p.lse[si0];
@@ -490,6 +501,7 @@ int attn_bwd_fused_impl(const ot_attn_params* p, cudaStream_t st) {
   kp.B = p->B; kp.H = p->H; kp.Lq = p->Lq; kp.Lk = p->Lk;
   kp.n_qt = (p->Lq + 127) / 128; kp.n_kt = (p->Lk + 127) / 128;
   kp.total_items = kp.n_kt * kp.H * kp.B;
+  kp.sched = sched_slot(st);
   kp.scale = 1.0f / sqrtf((float)p->head_dim);
   kp.scale_log2 = kp.scale * kLog2eF;
   kp.lse = p->lse; kp.delta = p->delta;

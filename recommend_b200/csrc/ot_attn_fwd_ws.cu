@@ -20,6 +20,7 @@ struct AttnFwdWsKParams {
   float scale, scale_log2;
   __nv_bfloat16* o; long long ldo;
   float* lse;  // [B, H, Lq]
+  int* sched;  // dynamic work counter (zeroed by the launcher) or NULL = static round-robin
 };
 
 static constexpr int FW_THREADS = 576;   // 16 softmax warps + MMA warp + loader warp
@@ -95,8 +96,13 @@ ot_attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       uint32_t t = 0, item_idx = 0;
       // A CTA takes whole (sample, head) pairs and walks their query tiles back to back: the K/V blocks a pair's
       // tiles share are then re-read by the same SM within microseconds and come from L2, not DRAM (profiles/README.md).
+      // After its first pair (blockIdx.x) a CTA draws pairs from a device-wide counter (p.sched), so a CTA that starts
+      // late takes fewer pairs instead of finishing last; the next pair is fetched while this one is being loaded.
       const int n_bh = p.B * p.H;
-      for (int bh = blockIdx.x; bh < n_bh; bh += gridDim.x)
+      int bh = blockIdx.x;
+      while (bh >= 0) {
+      int next_bh = p.sched != nullptr ? (int)gridDim.x + atomicAdd(p.sched, 1) : bh + (int)gridDim.x;
+      if (next_bh >= n_bh) next_bh = -1;
       for (int qt = p.n_qt - 1; qt >= 0; --qt, ++item_idx) {   // long tiles first
         const int h = bh % p.H;
         const int b = bh / p.H;
@@ -104,7 +110,7 @@ ot_attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         const int q_last = min(q0 + 127, p.Lq - 1);
         const int nkv = min((p.Lk + 127) / 128, (off + q_last) / 128 + 1);
         const int qb = item_idx & 1;
-        const bool last_item = (bh + (int)gridDim.x >= n_bh) && qt == 0;
+        const bool last_item = (next_bh < 0) && qt == 0;
         if (item_idx >= 2) mbar_wait(&bar_qfree[qb], ((item_idx >> 1) - 1) & 1);
         mbar_arrive_expect_tx(&bar_q[qb], T::TILE_BYTES);
         load_head_tile<DH, SWB>(sQ + qb * T::TILE_BYTES, &tmQ, &bar_q[qb], h, b, q0);
@@ -120,6 +126,8 @@ ot_attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           load_head_tile<DH, SWB>(sK + st * T::TILE_BYTES, &tmK, &bar_kv[st], h, b, j * 128);
           load_head_tile<DH, SWB>(sV + st * T::TILE_BYTES, &tmV, &bar_kv[st], h, b, j * 128);
         }
+      }
+      bh = next_bh;
       }
     }
   } else if (warp == 16) {
@@ -316,6 +324,7 @@ int attn_fwd_ws_impl(const ot_attn_params* p, cudaStream_t st) {
   kp.scale = 1.0f / sqrtf((float)p->head_dim);
   kp.scale_log2 = kp.scale * 1.4426950408889634f;
   kp.o = (__nv_bfloat16*)p->o; kp.ldo = p->ldo; kp.lse = p->lse;
+  kp.sched = sched_slot(st);
   static bool attr_done = false;
   if (!attr_done) {
     OT_CUDA_CHECK(cudaFuncSetAttribute(ot_attn_fwd_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnFwdWsCfg::SMEM_BYTES));
