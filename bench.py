@@ -174,6 +174,7 @@ def config_dict(args, wl, B):
             'global_batch': B * args.gpus, 'seq_tokens': sum(wl['seq_lens']) + 2, 'ns_tokens': wl['L_ns'],
             'parallelism': f'dp{args.gpus}', 'dropout': args.dropout,
             'optimizer': 'clip_by_norm 90 + RMSprop inside the timed step' if args.optimizer else 'none (metric is fwd+bwd)',
+            'grad_allreduce': 'none (1 GPU)' if args.gpus == 1 else ('after the backward' if args.no_overlap else 'per block, under the backward of the blocks below'),
             'inputs': 'pre-embedded events bf16 [B, L_i, 64] x3, 11 fp32 scalars, 2 fp32 labels per sample (pinned host buffers in the e2e arm)',
             'l2_policy': 'activations per step (>20 GB) far exceed the 126 MB L2; no explicit flush'}
 
@@ -194,6 +195,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-kernel-profile', action='store_true')
     ap.add_argument('--dropout', type=float, default=0.1, help='training dropout rate (OT/config.py:50 default 0.1)')
+    ap.add_argument('--no-overlap', action='store_true', help='N > 1: all-reduce the whole gradient buffer after the backward instead of per block under it')
     ap.add_argument('--optimizer', action='store_true', help='also run the clip + RMSprop update inside the step (OT/train.py:133-138)')
     args = ap.parse_args()
 
@@ -218,7 +220,9 @@ def main():
         raise SystemExit('bench.py: no CUDA device; the product path has no CPU fallback')
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+        opts = dist.ProcessGroupNCCL.Options()
+        opts.is_high_priority_stream = True       # the per-block gradient all-reduces slip in between the backward's kernels
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank), pg_options=opts)
     dev = torch.device('cuda', local_rank)
 
     cfg = R.get_model_config(wl['model'])
@@ -248,7 +252,7 @@ def main():
         torch.cuda.synchronize()
 
     def step_device():
-        return train_step(model, grads, d_ns, d_seq, d_lab, world, opt)
+        return train_step(model, grads, d_ns, d_seq, d_lab, world, opt, not args.no_overlap)
 
     def run_e2e(n_steps):
         """The user-facing loop (recommend_b200.train.train_loop): pinned host batches -> device (copies of step i+1

@@ -73,6 +73,10 @@ def split_segments(segs: Sequence[ops.Seg], row: int) -> List[ops.Seg]:
     return out
 
 
+# set by train.train_step while a data-parallel backward runs: called with the block whose gradients are complete (enqueued)
+after_block_backward = None
+
+
 def _fused_norm_args(norm: Optional[dict], rows: int, d: int, dev):
     """Allocate the outputs of an RMSNorm fused into a GEMM epilogue (north_star item 4) and return the ``norm=`` tuple
     of ops.mixed_gemm, or None when no norm was asked for / the row does not fit one tile."""

@@ -356,6 +356,8 @@ class _BlockFn(torch.autograd.Function):
                                          prev[1] if prev is not None else None)
         if prev is not None:
             object.__setattr__(prev[0], '_dy_masked', (dx_m, dx))
+        if engine.after_block_backward is not None:
+            engine.after_block_backward(blk)      # data parallel: this block's gradients may start their all-reduce now
         ctx.saved = None
         return dx, None, None, None, None, None, None, None, None, None, None, None
 

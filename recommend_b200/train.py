@@ -61,6 +61,45 @@ class FlatGradBuffer:
         if not nccl:
             self.flat.mul_(1.0 / world_size)
 
+    # ---- overlapped reduction: one asynchronous all-reduce per block, issued as soon as the block's backward is enqueued ----
+    def range_of(self, params: Iterable[torch.nn.Parameter]):
+        """[start, end) of the flat buffer covering ``params`` (which must be consecutive in the buffer)."""
+        index = {id(p): i for i, p in enumerate(self.params)}
+        idx = sorted(index[id(p)] for p in params if id(p) in index)
+        if not idx:
+            return None
+        assert idx == list(range(idx[0], idx[-1] + 1)), 'parameters of one bucket must be consecutive in the flat buffer'
+        last = self.params[idx[-1]]
+        end = self.offsets[idx[-1]] + -(-last.numel() // self.ALIGN) * self.ALIGN
+        return self.offsets[idx[0]], end
+
+    def begin_overlapped_reduce(self, world_size: int) -> None:
+        self._works, self._done, self._world = [], [], world_size
+
+    def reduce_range_async(self, rng) -> None:
+        """Enqueue the all-reduce of flat[start:end] behind everything already on the current stream; later kernels of
+        the current stream run concurrently with it (the persistent kernels schedule their tiles dynamically, so SMs
+        that the collective occupies cost throughput, not stragglers)."""
+        if rng is None or self._world <= 1:
+            return
+        nccl = dist.get_backend() == 'nccl'
+        self._works.append(dist.all_reduce(self.flat[rng[0]:rng[1]], op=dist.ReduceOp.AVG if nccl else dist.ReduceOp.SUM, async_op=True))
+        self._done.append(rng)
+
+    def finish_overlapped_reduce(self) -> None:
+        """Reduce whatever no bucket covered, then make the current stream wait for every outstanding collective."""
+        if self._world > 1:
+            covered, pos = sorted(self._done), 0
+            for s, e in covered + [(self.flat.numel(), self.flat.numel())]:
+                if s > pos:
+                    self.reduce_range_async((pos, s))
+                pos = max(pos, e)
+            for w in self._works:
+                w.wait()
+            if dist.get_backend() != 'nccl':
+                self.flat.mul_(1.0 / self._world)
+        self._works, self._done = [], []
+
 
 class DevicePrefetcher:
     """Host -> device input pipeline for the train loop (the role of ``tf.data`` prefetching in OT/data_loader.py:
@@ -195,15 +234,28 @@ class ClipRMSprop:
 
 
 def train_step(model, grads: FlatGradBuffer, non_seq, seq, labels, world_size: int = 1,
-               optimizer: Optional[ClipRMSprop] = None) -> torch.Tensor:
+               optimizer: Optional[ClipRMSprop] = None, overlap_reduce: bool = True) -> torch.Tensor:
     """forward + BCE + backward (+ gradient all-reduce): the "fwd+bwd" of the headline metric
     (OT/train.py:116-131); with ``optimizer`` also the clip + RMSprop update (OT/train.py:133-138).
-    Returns the detached loss tensor (no host sync)."""
+    With more than one rank the gradients of block l are all-reduced while the backward of blocks l-1 ... 0 runs
+    (``overlap_reduce``; PAPER:190 data parallelism).  Returns the detached loss tensor (no host sync)."""
+    from . import engine
     grads.zero()
     probs = model(non_seq, seq, training=True)
     loss = bce_loss(probs, labels, model.config.tasks)
-    loss.backward()
-    grads.all_reduce(world_size)
+    if world_size > 1 and overlap_reduce and hasattr(model, 'blocks'):
+        if getattr(grads, '_block_ranges', None) is None:
+            grads._block_ranges = {id(b): grads.range_of(list(b.parameters())) for b in model.blocks}
+        grads.begin_overlapped_reduce(world_size)
+        engine.after_block_backward = lambda blk: grads.reduce_range_async(grads._block_ranges.get(id(blk)))
+        try:
+            loss.backward()
+        finally:
+            engine.after_block_backward = None
+        grads.finish_overlapped_reduce()
+    else:
+        loss.backward()
+        grads.all_reduce(world_size)
     if optimizer is not None:
         optimizer.step()
     return loss.detach()

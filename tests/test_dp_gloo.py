@@ -47,6 +47,35 @@ def _worker(rank, world, port, out_dir):
     dist.destroy_process_group()
 
 
+def _worker_ranges(rank, world, port, out_dir):
+    """Overlapped reduction API: two 'blocks' reduced early by range, the rest swept up by finish_overlapped_reduce."""
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(100 + rank)
+    params = [torch.nn.Parameter(torch.zeros(n)) for n in (5, 1500, 7, 2048, 3)]
+    buf = FlatGradBuffer(params)
+    for p in params:
+        p.grad.copy_(torch.randn(p.shape, generator=g))
+    local = [p.grad.clone() for p in params]
+    buf.begin_overlapped_reduce(world)
+    buf.reduce_range_async(buf.range_of(params[3:4]))          # "block 1" finishes its backward first
+    buf.reduce_range_async(buf.range_of(params[1:3]))          # then "block 0"
+    buf.finish_overlapped_reduce()                             # params 0 and 4 were in no bucket
+    torch.save({'local': local, 'reduced': [p.grad.clone() for p in params]}, os.path.join(out_dir, f'ranges{rank}.pt'))
+    dist.destroy_process_group()
+
+
+def test_overlapped_range_reduce_covers_every_parameter_once(tmp_path):
+    world = 2
+    mp.spawn(_worker_ranges, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    r = [torch.load(os.path.join(tmp_path, f'ranges{i}.pt')) for i in range(world)]
+    for i in range(5):
+        want = (r[0]['local'][i] + r[1]['local'][i]) / world
+        assert torch.allclose(r[0]['reduced'][i], want, rtol=1e-6, atol=1e-7), i
+        assert torch.equal(r[0]['reduced'][i], r[1]['reduced'][i]), i
+
+
 def test_allreduced_shard_grads_equal_full_batch_grads(tmp_path):
     world = 2
     mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
