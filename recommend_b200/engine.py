@@ -73,7 +73,9 @@ def split_segments(segs: Sequence[ops.Seg], row: int) -> List[ops.Seg]:
     return out
 
 
-# set by train.train_step while a data-parallel backward runs: called with the block whose gradients are complete (enqueued)
+# set by train.train_step while a data-parallel backward runs: called with the block whose FFN gradients / whose remaining
+# gradients are complete (enqueued on the current stream), so that their all-reduce can start under the rest of the backward
+after_ffn_backward = None
 after_block_backward = None
 
 
@@ -243,7 +245,8 @@ def block_forward(x: torch.Tensor, P: Dict[str, torch.Tensor], w: BlockWeights, 
 
 
 def block_backward(dy: torch.Tensor, saved, Pm: Dict[str, torch.Tensor], w: BlockWeights, B: int, cur: int, keep: int,
-                   H: int, dy_masked: Optional[torch.Tensor] = None, prev_drop: Optional[Tuple[int, float]] = None):
+                   H: int, dy_masked: Optional[torch.Tensor] = None, prev_drop: Optional[Tuple[int, float]] = None,
+                   on_ffn_done=None):
     """Backward of block_forward.  Pm maps names to the fp32 master parameters (their .grad buffers
     receive the gradients).  Returns ``(dx [cur*B, d], dx_masked)``.
     The dropout masks of the two branches are applied to gradients as they are produced: ``dz`` leaves the norm2
@@ -265,6 +268,8 @@ def block_backward(dy: torch.Tensor, saved, Pm: Dict[str, torch.Tensor], w: Bloc
         dy_f = ops.dropout_mask(dy, drop[1], drop[2])
     dzn = ffn_backward(dy_f, zn, ffn_saved, w, segs_tail, _grad_buf(Pm['W1']), _grad_buf(Pm['b1']), _grad_buf(Pm['W2']),
                        _grad_buf(Pm['b2']))
+    if on_ffn_done is not None:
+        on_ffn_done()                  # W1, b1, W2, b2 gradients are final: data parallel starts reducing them now
     dz = torch.empty(rows_t, d, dtype=bf16, device=dev)
     # z = x_tail + drop(MHA(norm1(x)))
     dz_a = torch.empty(rows_t, d, dtype=bf16, device=dev) if drop is not None else dz

@@ -352,8 +352,10 @@ class _BlockFn(torch.autograd.Function):
             object.__setattr__(blk, '_dy_masked', None)
             if m[1].data_ptr() == dy.data_ptr() and m[1].shape == dy.shape:
                 dy_masked = m[0]
+        hook = engine.after_ffn_backward
         dx, dx_m = engine.block_backward(dy, saved, blk._params(), w, B, cur, keep, blk.config.num_heads, dy_masked,
-                                         prev[1] if prev is not None else None)
+                                         prev[1] if prev is not None else None,
+                                         (lambda: hook(blk)) if hook is not None else None)
         if prev is not None:
             object.__setattr__(prev[0], '_dy_masked', (dx_m, dx))
         if engine.after_block_backward is not None:

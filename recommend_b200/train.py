@@ -245,13 +245,18 @@ def train_step(model, grads: FlatGradBuffer, non_seq, seq, labels, world_size: i
     loss = bce_loss(probs, labels, model.config.tasks)
     if world_size > 1 and overlap_reduce and hasattr(model, 'blocks'):
         if getattr(grads, '_block_ranges', None) is None:
-            grads._block_ranges = {id(b): grads.range_of(list(b.parameters())) for b in model.blocks}
+            # two slices per block, in the order their gradients become final: the FFN weights (about 3/4 of a block),
+            # then the norms and the attention weights
+            grads._ffn_ranges = {id(b): grads.range_of(list(b.ffn.parameters())) for b in model.blocks}
+            grads._block_ranges = {id(b): grads.range_of([p for p in b.parameters() if all(p is not q for q in b.ffn.parameters())])
+                                   for b in model.blocks}
         grads.begin_overlapped_reduce(world_size)
+        engine.after_ffn_backward = lambda blk: grads.reduce_range_async(grads._ffn_ranges.get(id(blk)))
         engine.after_block_backward = lambda blk: grads.reduce_range_async(grads._block_ranges.get(id(blk)))
         try:
             loss.backward()
         finally:
-            engine.after_block_backward = None
+            engine.after_ffn_backward = engine.after_block_backward = None
         grads.finish_overlapped_reduce()
     else:
         loss.backward()
