@@ -7,15 +7,19 @@
 // which weight set" (OT/model.py:67-74) arrives as data (ot_gemm_seg), so the shared S-token run and
 // the per-token NS runs are tiles of ONE persistent launch.
 //
-// Kernel structure (one CTA per SM, persistent over a static tile list; 20 warps, registers re-balanced with
-// setmaxnreg: 32 per control thread, 112 per epilogue thread):
-//   warp 0   : TMA producer   — A tile [128 x BK] and W tile [BN x BK] into a STAGES-deep smem ring
+// Kernel structure (one CTA per SM, persistent; 20 warps, registers re-balanced with setmaxnreg: 32 per control
+// thread, 112 per epilogue thread).  Tiles are scheduled dynamically: every CTA starts with tile blockIdx.x and then
+// draws from a device-wide counter, so CTAs that start late (an SM held by a collective) take fewer tiles.
+//   warp 0   : TMA producer   — tile index -> ring (to warps 1, 4-19); A tile [128 x BK] and W tile [BN x BK] into a
+//                               STAGES-deep smem ring
 //   warp 1   : MMA issuer     — tcgen05.mma (M=128, N=BN, K=16) into one of two TMEM accumulators
 //   warps 4-19: epilogue      — tcgen05.ld -> packed fp32 math (row scale, bias, GELU, GELU', residual, dropout)
 //                               -> bf16 -> swizzled smem staging tile -> TMA store; residual / GELU' inputs arrive
-//                               by TMA one tile ahead (four sets of four warps, one 64-column chunk each)
+//                               by TMA one tile ahead (four sets of four warps, one 64-column chunk each; with
+//                               BN < 256 the sets split into groups that take tiles in turn); OT_EPI_NORM adds the
+//                               RMSNorm of the finished rows as a second output (row statistics exchanged in smem)
 // The two TMEM accumulators (2*BN <= 512 columns) let the epilogue of tile i overlap the MMAs of
-// tile i+1.  Roofline: at d=256 every GEMM of the block is HBM-bound (DESIGN.md §5), so the
+// tile i+1.  Roofline: at d=256 every GEMM of the block is HBM-bound (DESIGN.md §4), so the
 // epilogue reads/writes each activation byte exactly once and in full 128-byte lines.
 #include "ot_common.cuh"
 #include "ot_host.h"
