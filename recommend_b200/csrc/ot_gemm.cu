@@ -374,6 +374,7 @@ ot_mixed_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         }
         // dual mode (FFN-1 forward keeps the pre-activation for the backward pass): pass 0 stores the pre-activation,
         // pass 1 re-reads the accumulator (TMEM reads are cheap, registers are not) and stores GELU of it
+        f32x2 ss2 = pk2(0.0f);                 // OT_EPI_NORM: sum of squares of my 64 result columns (fp32, before rounding)
         const int n_pass = dual ? 2 : 1;
 #pragma unroll 1
         for (int pass = 0; pass < n_pass; ++pass) {
@@ -452,6 +453,10 @@ ot_mixed_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 #pragma unroll
               for (int j = 0; j < 16; ++j) f[j] = gelu_erf2(f[j]);
             }
+            if (f_norm) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) ss2 = fma2(f[j], f[j], ss2);
+            }
             // each thread (over)writes only its own row of the staging tile
 #pragma unroll
             for (int ch = 0; ch < 4; ++ch) {
@@ -477,8 +482,8 @@ ot_mixed_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         }
         if (f_norm) {
           // ---- fused RMSNorm of the rows just produced (OT/model.py:19-23): the tile holds whole rows (N == BN),
-          // each set its 64 columns.  Values come back from the staging tile (bf16, exactly what went to HBM) or,
-          // on fp32-residual rows, from out_hp. ----
+          // each set its 64 columns.  The row statistics use the fp32 results of the main pass; the values to scale come
+          // back from the staging tile (bf16, exactly what went to HBM) or, on fp32-residual rows, from out_hp. ----
           const long long hr = (long long)(t.row0 + r_own) - p.hp_row0;
           const bool hp_row = hp_tile && r_own < t.valid;
           auto load8 = [&](int ch, float (&x)[8]) {
@@ -497,14 +502,9 @@ ot_mixed_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
               x[4] = bf16lo(q.z); x[5] = bf16hi(q.z); x[6] = bf16lo(q.w); x[7] = bf16hi(q.w);
             }
           };
-          float ss = 0.0f;
-#pragma unroll
-          for (int ch = 0; ch < 8; ++ch) {
-            float x[8];
-            load8(ch, x);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) ss = fmaf(x[e], x[e], ss);
-          }
+          float ss, ss_hi;
+          upk2(ss2, ss, ss_hi);
+          ss += ss_hi;                            // accumulated in the main pass: no extra trip through the staging tile
           float* ssb = ss_part + ((it / N_GRP) & 1) * (EPI_SETS * BM);   // alternates between two consecutive tiles of a set
           ssb[set * BM + r_own] = ss;
           if (tma_out && io_thread) bulk_wait_read0();          // the `out` rows have left the staging tile

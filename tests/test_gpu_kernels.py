@@ -105,13 +105,13 @@ def test_gemm_fused_rmsnorm_output(rows, N, K, hp_rows):
         z[rows - hp_rows:] = A[rows - hp_rows:].float() @ W[0].float().t() + res_hp
         assert (out_hp - z[rows - hp_rows:]).abs().max().item() < 2e-3 * z.abs().max().item()
     assert ((out.float() - z).abs().max() / z.abs().max()).item() < 1e-2
-    # the norm is taken of what went to HBM (bf16 rows; fp32 on the high-precision rows)
+    # row statistics come from the fp32 results (before the bf16 rounding of `out`), the scaled values from what went to HBM
     zq = out.float()
     if hp_rows:
         zq[rows - hp_rows:] = out_hp
-    r_ref = torch.rsqrt(zq.square().mean(-1) + 1e-6)
-    assert ((rstd - r_ref).abs().max() / r_ref.abs().max()).item() < 1e-5
-    n_ref = zq * r_ref[:, None] * gain
+    r_ref = torch.rsqrt(z.square().mean(-1) + 1e-6)
+    assert ((rstd - r_ref).abs().max() / r_ref.abs().max()).item() < 2e-4      # z itself is a bf16-input matmul: fp32 accumulation order
+    n_ref = zq * rstd[:, None] * gain
     assert ((nout.float() - n_ref).abs().max() / n_ref.abs().max()).item() < 6e-3      # one bf16 rounding
 
 

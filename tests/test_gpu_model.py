@@ -81,9 +81,10 @@ def _check(out, logit_tol=LOGIT_TOL, grad_tol=GRAD_L2_TOL):
 
 def test_smoke_shape_of_reference_main():
     """The reference's own __main__ smoke shapes (OT/model.py:420-442): d=128 -> here d=256 H=4 (head_dim 64),
-    2 layers, 4 NS tokens, click 10 + cart 5 events."""
+    2 layers, 4 NS tokens, click 10 + cart 5 events.  Batch 64 instead of the script's 2: with four logits the relative
+    L2 error is a coin toss around the bf16 floor (0.8-1.1e-2 depending on the rounding of a single row statistic)."""
     ocfg, cfg = make_configs(hidden_dim=256, num_layers=2, ffn_dim=512, num_ns_tokens=4)
-    _check(_run_pair(ocfg, cfg, B=2, seq_lens=(10, 5, 7), present=('click_seq', 'cart_seq')))
+    _check(_run_pair(ocfg, cfg, B=64, seq_lens=(10, 5, 7), present=('click_seq', 'cart_seq')))
 
 
 def test_c1_small_reference_ratio():
