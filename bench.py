@@ -214,7 +214,7 @@ def main():
     import recommend_b200 as R
     from recommend_b200 import _lib, ops
     from recommend_b200.train import FlatGradBuffer, ClipRMSprop, bce_loss, train_loop, train_step
-    from oracle import onetrans_oracle as O  # synthetic input generator only (and the cpu_baseline leg below)
+    from recommend_b200.data import create_sample_batch
 
     if not torch.cuda.is_available():
         raise SystemExit('bench.py: no CUDA device; the product path has no CPU fallback')
@@ -235,8 +235,7 @@ def main():
     opt = ClipRMSprop.from_config(grads, cfg) if args.optimizer else None
 
     B = wl['B']
-    ocfg = O.small_config(num_ns_tokens=wl['L_ns']) if wl['model'] == 'small' else O.default_config(num_ns_tokens=wl['L_ns'])
-    non_seq, seq, labels = O.synthetic_batch(ocfg, B, wl['seq_lens'], seed=1234 + rank)
+    non_seq, seq, labels = create_sample_batch(cfg, B, wl['seq_lens'], seed=1234 + rank)
     # host (pinned) copies for the e2e arm; device copies for the device-resident arm
     h_ns = {k: v.pin_memory() for k, v in non_seq.items()}
     h_seq = {k: v.to(torch.bfloat16).pin_memory() for k, v in seq.items()}

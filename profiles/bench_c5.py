@@ -7,15 +7,14 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import recommend_b200 as R
 from recommend_b200 import _lib
-from oracle import onetrans_oracle as O      # synthetic input generator only
+from recommend_b200.data import create_sample_batch
 
 C = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
 K = int(sys.argv[2]) if len(sys.argv) > 2 else 10
 cfg = R.get_model_config('small'); cfg.num_ns_tokens = 32; cfg.pyramid_schedule = 'linear_to_ns'; cfg.dropout_rate = 0.0
 torch.manual_seed(0)
 model = R.OneTransModel(cfg).cuda().eval()
-ocfg = O.small_config(num_ns_tokens=32)
-ns, sq, _ = O.synthetic_batch(ocfg, C, (170, 170, 170), seed=5)
+ns, sq, _ = create_sample_batch(cfg, C, (170, 170, 170), seed=5)
 ns = {k: v.cuda() for k, v in ns.items()}
 user_seq = {k: v[:1].cuda().bfloat16() for k, v in sq.items()}                 # ONE user's behaviour sequences
 

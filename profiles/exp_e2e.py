@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import recommend_b200 as R
 from recommend_b200.train import FlatGradBuffer, DevicePrefetcher, train_loop, train_step
-from oracle import onetrans_oracle as O
+from recommend_b200.data import create_sample_batch
 
 B, K = 2048, 8
 dev = torch.device('cuda', 0)
@@ -13,7 +13,7 @@ cfg = R.get_model_config('small'); cfg.num_ns_tokens = 32; cfg.pyramid_schedule 
 torch.manual_seed(0)
 model = R.OneTransModel(cfg).to(dev)
 grads = FlatGradBuffer(model.parameters())
-ns, sq, lb = O.synthetic_batch(O.small_config(num_ns_tokens=32), B, (170, 170, 170))
+ns, sq, lb = create_sample_batch(cfg, B, (170, 170, 170))
 h = ({k: v.pin_memory() for k, v in ns.items()}, {k: v.to(torch.bfloat16).pin_memory() for k, v in sq.items()}, {k: v.pin_memory() for k, v in lb.items()})
 d = tuple({k: v.to(dev) for k, v in x.items()} for x in h)
 

@@ -5,15 +5,14 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import recommend_b200 as R
 from recommend_b200.train import FlatGradBuffer, train_step
-from oracle import onetrans_oracle as O
+from recommend_b200.data import create_sample_batch
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 cfg = R.get_model_config('small'); cfg.num_ns_tokens = 32; cfg.pyramid_schedule = 'linear_to_ns'; cfg.dropout_rate = 0.1
 torch.manual_seed(0)
 model = R.OneTransModel(cfg).cuda()
 grads = FlatGradBuffer(model.parameters())
-ocfg = O.small_config(num_ns_tokens=32)
-ns, sq, lb = O.synthetic_batch(ocfg, B, (170, 170, 170))
+ns, sq, lb = create_sample_batch(cfg, B, (170, 170, 170))
 ns = {k: v.cuda() for k, v in ns.items()}; sq = {k: v.cuda().bfloat16() for k, v in sq.items()}; lb = {k: v.cuda() for k, v in lb.items()}
 for _ in range(3):
     train_step(model, grads, ns, sq, lb)

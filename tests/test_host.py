@@ -158,3 +158,32 @@ def test_gelu_approximation_constants():
     grad = 0.5 * (1 + t) + xc * 0.5 * (1 - t * t) * du
     ref = 0.5 * (1 + erf) + x * torch.exp(-x * x / 2) / math.sqrt(2 * math.pi)
     assert (grad - ref).abs().max() < 1.5e-4
+
+
+def test_product_package_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under recommend_b200/ may import it, and bench.py only in its CPU legs."""
+    import glob
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for path in glob.glob(os.path.join(root, 'recommend_b200', '**', '*.py'), recursive=True):
+        src = open(path).read()
+        assert not re.search(r'^\s*(from|import)\s+oracle\b', src, re.M), path
+    bench = open(os.path.join(root, 'bench.py')).read()
+    imports = [m.start() for m in re.finditer(r'^\s*from oracle import', bench, re.M)]
+    assert len(imports) == 1 and bench.rfind('def cpu_oracle_samples_per_sec', 0, imports[0]) != -1, \
+        'bench.py may touch the oracle only inside cpu_oracle_samples_per_sec (cpu_baseline / --impl reference)'
+
+
+def test_sample_batch_generator_matches_the_oracles():
+    """Both bench arms must see the same synthetic inputs: the product generator (recommend_b200.data, after
+    OT/data_loader.py:301-329) and the oracle's draw the same stream."""
+    from recommend_b200.data import create_sample_batch
+    cfg = R.get_model_config('small')
+    cfg.num_ns_tokens = 16
+    for mode in ('normal', 'ids'):
+        a = create_sample_batch(cfg, 5, (4, 3, 2), seed=77, ns_mode=mode)
+        b = O.synthetic_batch(O.small_config(num_ns_tokens=16), 5, (4, 3, 2), seed=77, ns_mode=mode)
+        for da, db in zip(a, b):
+            assert da.keys() == db.keys()
+            for k in da:
+                assert torch.equal(da[k], db[k]), (mode, k)
