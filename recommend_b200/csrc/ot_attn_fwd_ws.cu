@@ -204,14 +204,19 @@ ot_attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_sfree[g & 1]);
 
-      // blocks strictly below the diagonal of the whole tile need no mask
-      const bool fast = (si.j * 128 + 127 <= off + q0);
-      const int lim = (off + q0 + row) - si.j * 128 - quarter * 32;   // column i of this thread is visible iff i <= lim
+      // The causal mask is decided per warp: its 32 rows x 32 columns of the tile are either entirely visible (no mask
+      // code at all - every block strictly below the diagonal, and most blocks of a diagonal tile), entirely hidden
+      // (nothing to compute) or cut by the diagonal (per-element selects).  Column i of this thread is visible iff
+      // i <= lim; lim grows by one per row, so the warp's extremes sit in lanes 0 and 31.
+      const int lim = (off + q0 + row) - si.j * 128 - quarter * 32;
+      const int lim_first = lim - lane, lim_last = lim_first + 31;
+      const bool fast = lim_first >= 31;
+      const bool none = lim_last < 0;
       float mx = -INFINITY;
       if (fast) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
-      } else {
+      } else if (!none) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (i <= lim) ? __uint_as_float(v[i]) : -INFINITY);
       }
@@ -234,6 +239,9 @@ ot_attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           rowsum += e0 + e1;
           pk[i] = pack_bf16x2(e0, e1);
         }
+      } else if (none) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) pk[i] = 0u;
       } else {
 #pragma unroll
         for (int i = 0; i < 16; ++i) {

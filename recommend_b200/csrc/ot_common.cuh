@@ -46,6 +46,12 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
+// Same packing on the integer pipe (round half away from zero instead of half to even; finite inputs only): two adds
+// and one byte permute instead of one F2FP.  For inner loops whose conversion pipe is the busy one.
+__device__ __forceinline__ uint32_t pack_bf16x2_alu(float lo, float hi) {
+  const uint32_t a = __float_as_uint(lo) + 0x8000u, b = __float_as_uint(hi) + 0x8000u;
+  return __byte_perm(a, b, 0x7632);
+}
 __device__ __forceinline__ float bf16lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 
