@@ -376,41 +376,52 @@ ot_attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         delta = p.delta[sn];
       }
       uint32_t pk[32], dsk[32];   // packed bf16 P and dS of this thread's 64 columns
-      // Tiles strictly below the diagonal with only valid rows need no mask (the common case).  Otherwise column
-      // j of the tile is visible to this row iff j <= lim.
-      const bool fast = (q0 + 127 < p.Lq) && (k0 + 127 <= off + q0);
+      // The mask is decided per warp (32 rows x 64 columns of the tile): entirely visible with only valid rows -> no
+      // mask code; entirely hidden -> P = dS = 0 without touching TMEM; cut by the diagonal (or the last query rows)
+      // -> per-element selects.  Column j of the tile is visible to this row iff j <= lim.
       const int lim = row_valid ? (pq - k0) : -1;
+      const int lim_first = off + q0 + (row - lane) - k0;                     // lim of the warp's first row (if it exists)
+      const bool fast = (q0 + (row - lane) + 31 < p.Lq) && (lim_first >= half * 64 + 63);
+      const bool none = (lim_first + 31 < half * 64) || (q0 + (row - lane) >= p.Lq);
       const float dlt_s = dlt * p.scale;
-      uint32_t vs[2][16], vd[2][16];   // double-buffered TMEM reads: chunk c+1 is in flight while chunk c is processed
-      tmem_ld_x16(t_row + Cfg::T_S + half * 64, vs[0]);
-      tmem_ld_x16(t_row + Cfg::T_DP + half * 64, vd[0]);
-      tmem_ld_wait();
+      if (none) {
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const int cb = c & 1;
-        if (c < 3) {
-          tmem_ld_x16(t_row + Cfg::T_S + half * 64 + (c + 1) * 16, vs[cb ^ 1]);
-          tmem_ld_x16(t_row + Cfg::T_DP + half * 64 + (c + 1) * 16, vd[cb ^ 1]);
-        }
-        const int j0 = half * 64 + c * 16;
+        for (int i = 0; i < 32; ++i) { pk[i] = 0u; dsk[i] = 0u; }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_sread);      // nothing to read: as far as this warp goes S / dP may be reused
+      } else {
+        uint32_t vs[2][8], vd[2][8];   // double-buffered TMEM reads: chunk c+1 is in flight while chunk c is processed
+        tmem_ld_x8(t_row + Cfg::T_S + half * 64, vs[0]);
+        tmem_ld_x8(t_row + Cfg::T_DP + half * 64, vd[0]);
+        tmem_ld_wait();
 #pragma unroll
-        for (int i2 = 0; i2 < 8; ++i2) {
-          float pv0 = ex2_approx(fmaf(__uint_as_float(vs[cb][2 * i2]), p.scale_log2, -lse2));
-          float pv1 = ex2_approx(fmaf(__uint_as_float(vs[cb][2 * i2 + 1]), p.scale_log2, -lse2));
-          if (!fast) {
-            pv0 = (j0 + 2 * i2 <= lim) ? pv0 : 0.0f;
-            pv1 = (j0 + 2 * i2 + 1 <= lim) ? pv1 : 0.0f;
+        for (int c = 0; c < 8; ++c) {
+          const int cb = c & 1;
+          if (c < 7) {
+            tmem_ld_x8(t_row + Cfg::T_S + half * 64 + (c + 1) * 8, vs[cb ^ 1]);
+            tmem_ld_x8(t_row + Cfg::T_DP + half * 64 + (c + 1) * 8, vd[cb ^ 1]);
           }
-          const float ds0 = pv0 * fmaf(__uint_as_float(vd[cb][2 * i2]), p.scale, -dlt_s);
-          const float ds1 = pv1 * fmaf(__uint_as_float(vd[cb][2 * i2 + 1]), p.scale, -dlt_s);
-          pk[c * 8 + i2] = pack_bf16x2(pv0, pv1);
-          dsk[c * 8 + i2] = pack_bf16x2(ds0, ds1);
-        }
-        if (c < 3) tmem_ld_wait();
-        if (c == 2) {   // every S/dP column of this thread is in registers: the MMA warp may issue the next S/dP
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_sread);
+          const int j0 = half * 64 + c * 8;
+#pragma unroll
+          for (int i2 = 0; i2 < 4; ++i2) {
+            float pv0 = ex2_approx(fmaf(__uint_as_float(vs[cb][2 * i2]), p.scale_log2, -lse2));
+            float pv1 = ex2_approx(fmaf(__uint_as_float(vs[cb][2 * i2 + 1]), p.scale_log2, -lse2));
+            if (!fast) {
+              pv0 = (j0 + 2 * i2 <= lim) ? pv0 : 0.0f;
+              pv1 = (j0 + 2 * i2 + 1 <= lim) ? pv1 : 0.0f;
+            }
+            const float ds0 = pv0 * fmaf(__uint_as_float(vd[cb][2 * i2]), p.scale, -dlt_s);
+            const float ds1 = pv1 * fmaf(__uint_as_float(vd[cb][2 * i2 + 1]), p.scale, -dlt_s);
+            pk[c * 4 + i2] = pack_bf16x2(pv0, pv1);
+            dsk[c * 4 + i2] = pack_bf16x2(ds0, ds1);
+          }
+          if (c < 7) tmem_ld_wait();
+          if (c == 6) {   // every S/dP column of this thread is in registers: the MMA warp may issue the next S/dP
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_sread);
+          }
         }
       }
       OT_TICK(1);   // TMEM loads + exp math
