@@ -156,10 +156,10 @@ def run_reference_arm(args, wl, rank):
     sample_B = args.cpu_sample_batch
     v, ms, cores = cpu_oracle_samples_per_sec(wl, sample_B, max(1, args.steps), max(0, args.warmup), args.dropout)
     line = {
-        'impl': 'reference', 'metric': 'OneTrans samples/sec (fwd+bwd)', 'value': v, 'unit': 'samples/s', 'n_gpus': args.gpus,
+        'impl': 'reference', 'metric': 'OneTrans samples/sec (fwd+bwd bf16)', 'value': v, 'unit': 'samples/s', 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': config_dict(args, wl, sample_B),
+        'config': config_dict(args, wl, wl['B']),      # the GPU arm's workload; each CPU step is a bounded sample of it (cpu_baseline.sample)
         'cpu_baseline': {'value': v, 'unit': 'samples/s', 'cores': cores, 'kind': 'port',
                          'sample': f'oracle (PyTorch CPU fp32 restatement of OT/model.py; TensorFlow reference not installable) fwd+BCE+bwd on {sample_B} '
                                    f'samples of the same workload per step'},
