@@ -88,6 +88,14 @@ ot_attn_cached_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   const uint32_t q_bytes = (uint32_t)(BC * p.Tq) * SWB * T::NSLAB;
   const uint32_t own_bytes = (uint32_t)(BC * p.Tn) * SWB * T::NSLAB;
 
+  // visibility of the 128 columns of the candidates' own key block for this thread's row, one bit per column (the row
+  // and therefore the pattern is the same for every item): column c holds key token c / BC of candidate slot c % BC
+  uint32_t own_mask[4] = {0u, 0u, 0u, 0u};
+  for (int c = 0; c < 128; ++c) {
+    const int lk = c / BC;
+    const int cck = c - lk * BC;
+    if ((cck == cc_row) && (lk <= pq) && (lk < p.Tn)) own_mask[c >> 5] |= 1u << (c & 31);
+  }
   uint32_t n_items_done = 0, kv_count = 0, blk_count = 0;
   const int nblk = p.n_sblk + 1;
 
@@ -133,23 +141,29 @@ ot_attn_cached_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 
       auto allowed = [&](int c) -> bool {
         if (shared_blk) return (j * 128 + c) < p.Ls;                // every NS query follows every S key
-        const int lk = c / BC;
-        const int cck = c - lk * BC;
-        return (cck == cc_row) && (lk <= pq) && (lk < p.Tn);        // same candidate, causal among its NS tokens
+        return (own_mask[c >> 5] >> (c & 31)) & 1u;                 // same candidate, causal among its NS tokens
       };
+      // full blocks of cached sequence keys are visible to every query: no mask code (the common case: all but the last
+      // shared block and the block of the candidates' own keys)
+      const bool fast = shared_blk && (j * 128 + 127 < p.Ls);
       float m_new = m_run;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         uint32_t v[32];
         tmem_ld_x32(t_S + c * 32, v);
         tmem_ld_wait();
+        if (fast) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (allowed(c * 32 + i)) m_new = fmaxf(m_new, __uint_as_float(v[i]));
+          for (int i = 0; i < 32; ++i) m_new = fmaxf(m_new, __uint_as_float(v[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (allowed(c * 32 + i)) m_new = fmaxf(m_new, __uint_as_float(v[i]));
+        }
       }
       // a row may have no allowed key in a block (e.g. an invalid padding row): keep the running state finite
       const float m_use = (m_new == -INFINITY) ? 0.0f : m_new;
-      const float alpha = (m_run == -INFINITY) ? 0.0f : exp2f((m_run - m_use) * p.scale_log2);
+      const float alpha = (m_run == -INFINITY) ? 0.0f : ex2_approx((m_run - m_use) * p.scale_log2);
       const float mb = m_use * p.scale_log2;
       float rowsum = 0.0f;
 #pragma unroll 1
@@ -158,11 +172,20 @@ ot_attn_cached_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         tmem_ld_x32(t_S + c * 32, v);
         tmem_ld_wait();
         float pr[32];
+        if (fast) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float e = allowed(c * 32 + i) ? exp2f(__uint_as_float(v[i]) * p.scale_log2 - mb) : 0.0f;
-          pr[i] = e;
-          rowsum += e;
+          for (int i = 0; i < 32; ++i) {
+            const float e = ex2_approx(fmaf(__uint_as_float(v[i]), p.scale_log2, -mb));
+            pr[i] = e;
+            rowsum += e;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float e = allowed(c * 32 + i) ? ex2_approx(fmaf(__uint_as_float(v[i]), p.scale_log2, -mb)) : 0.0f;
+            pr[i] = e;
+            rowsum += e;
+          }
         }
         ptile_store32(sP, tid, c * 32, pr);
       }
