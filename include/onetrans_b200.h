@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define OT_ABI_VERSION 8
+#define OT_ABI_VERSION 9
 
 int ot_version(void);
 const char* ot_last_error_string(void);
@@ -315,6 +315,30 @@ typedef struct ot_embed_params {
 int ot_embed_gather_fwd(const ot_embed_params* p, void* stream);
 int ot_embed_scatter_bwd(const ot_embed_params* p, void* stream);
 int ot_embed_adagrad_step(const ot_embed_params* p, void* stream);
+
+/* ---- output norm + task heads (+ BCE) on the last token, fp32 (OT/model.py:322-330 heads, :384-391 output norm and
+ * last-token slice; loss OT/train.py:84-87, 124-128).  Per task t: pre = RMSNorm(x) W0[t] + b0[t], h = gelu_erf(pre),
+ * logit = h . W1[t] + b1[t], prob = sigmoid(logit).  With labels: *loss += sum_t mean_b BCE(prob, y) (Keras semantics: clip
+ * to [1e-7, 1-1e-7], log(p + 1e-7)) and g_bce[t, b] = d loss / d logit[t, b].
+ * ot_heads_bwd takes dlogit [T, B] (any mix of g_bce * upstream and gradients w.r.t. probs / logits) and ACCUMULATES
+ * dW0, db0, dW1, db1, dgain (caller zeroes), and writes dx.  All tensors fp32; W0[t] is [d, hidden] (Keras [in, out]). */
+#define OT_MAX_TASKS 4
+typedef struct ot_heads_params {
+  const float* x; int64_t ldx;          /* [B, d] last-token rows of the residual stream */
+  const float* gain; float eps;         /* output_norm.scale */
+  int32_t B, d, hidden, n_tasks;        /* hidden = d/2 in the reference */
+  const float* W0[OT_MAX_TASKS]; const float* b0[OT_MAX_TASKS]; const float* W1[OT_MAX_TASKS]; const float* b1[OT_MAX_TASKS];
+  float* xn; float* rstd; float* pre;   /* saved for the backward: [B, d], [B], [n_tasks, B, hidden] */
+  float* logits; float* probs;          /* [n_tasks, B] */
+  const float* labels; float* loss; float* g_bce;   /* optional (all three or none): [n_tasks, B], scalar, [n_tasks, B] */
+  const float* dlogit;                  /* backward input [n_tasks, B] */
+  float* dpre;                          /* backward workspace [n_tasks, B, hidden] */
+  float* dW0[OT_MAX_TASKS]; float* db0[OT_MAX_TASKS]; float* dW1[OT_MAX_TASKS]; float* db1[OT_MAX_TASKS];
+  float* dgain;
+  float* dx; int64_t lddx;
+} ot_heads_params;
+int ot_heads_fwd(const ot_heads_params* p, void* stream);
+int ot_heads_bwd(const ot_heads_params* p, void* stream);
 
 #ifdef __cplusplus
 }

@@ -86,6 +86,18 @@ class EmbedParams(C.Structure):
                 ('step_id', i32), ('lr', C.c_float), ('eps', C.c_float)]
 
 
+MAX_TASKS = 4  # OT_MAX_TASKS
+
+
+class HeadsParams(C.Structure):
+    _fields_ = [('x', fp), ('ldx', i64), ('gain', fp), ('eps', C.c_float), ('B', i32), ('d', i32), ('hidden', i32), ('n_tasks', i32),
+                ('W0', fp * MAX_TASKS), ('b0', fp * MAX_TASKS), ('W1', fp * MAX_TASKS), ('b1', fp * MAX_TASKS),
+                ('xn', fp), ('rstd', fp), ('pre', fp), ('logits', fp), ('probs', fp), ('labels', fp), ('loss', fp), ('g_bce', fp),
+                ('dlogit', fp), ('dpre', fp),
+                ('dW0', fp * MAX_TASKS), ('db0', fp * MAX_TASKS), ('dW1', fp * MAX_TASKS), ('db1', fp * MAX_TASKS),
+                ('dgain', fp), ('dx', fp), ('lddx', i64)]
+
+
 OPT_CHUNK = 1024  # OT_OPT_CHUNK
 
 # every symbol include/onetrans_b200.h declares (tests check that the library exports all of them)
@@ -93,6 +105,7 @@ EXPORTED_SYMBOLS = [
     'ot_version', 'ot_last_error_string', 'ot_num_sms', 'ot_mixed_gemm', 'ot_wgrad', 'ot_attn_fwd', 'ot_attn_bwd', 'ot_attn_ns_cached_fwd',
     'ot_rmsnorm_fwd', 'ot_rmsnorm_bwd', 'ot_ns_tokenizer_fwd', 'ot_ns_tokenizer_bwd', 'ot_fill_rows', 'ot_colsum', 'ot_dropout_mask',
     'ot_clip_rmsprop_step', 'ot_embed_gather_fwd', 'ot_embed_scatter_bwd', 'ot_embed_adagrad_step',
+    'ot_heads_fwd', 'ot_heads_bwd',
 ]
 
 _lib = None
@@ -123,7 +136,8 @@ def load() -> C.CDLL:
                          ('ot_attn_bwd', AttnParams), ('ot_attn_ns_cached_fwd', AttnCachedParams), ('ot_rmsnorm_fwd', RmsnormParams), ('ot_rmsnorm_bwd', RmsnormParams),
                          ('ot_ns_tokenizer_fwd', NsTokenizerParams), ('ot_ns_tokenizer_bwd', NsTokenizerParams),
                          ('ot_colsum', ColsumParams), ('ot_clip_rmsprop_step', RmspropParams), ('ot_embed_gather_fwd', EmbedParams),
-                         ('ot_embed_scatter_bwd', EmbedParams), ('ot_embed_adagrad_step', EmbedParams)]:
+                         ('ot_embed_scatter_bwd', EmbedParams), ('ot_embed_adagrad_step', EmbedParams),
+                         ('ot_heads_fwd', HeadsParams), ('ot_heads_bwd', HeadsParams)]:
             fn = getattr(lib, name)
             fn.argtypes = [C.POINTER(st), C.c_void_p]
             fn.restype = C.c_int

@@ -83,6 +83,8 @@ int clip_rmsprop_impl(const ot_rmsprop_params* p, cudaStream_t st);
 int embed_gather_impl(const ot_embed_params* p, cudaStream_t st);
 int embed_scatter_impl(const ot_embed_params* p, cudaStream_t st);
 int embed_adagrad_impl(const ot_embed_params* p, cudaStream_t st);
+int heads_fwd_impl(const ot_heads_params* p, cudaStream_t st);
+int heads_bwd_impl(const ot_heads_params* p, cudaStream_t st);
 
 }  // namespace ot
 
@@ -125,5 +127,7 @@ int ot_clip_rmsprop_step(const ot_rmsprop_params* p, void* stream) { return ot::
 int ot_embed_gather_fwd(const ot_embed_params* p, void* stream) { return ot::embed_gather_impl(p, static_cast<cudaStream_t>(stream)); }
 int ot_embed_scatter_bwd(const ot_embed_params* p, void* stream) { return ot::embed_scatter_impl(p, static_cast<cudaStream_t>(stream)); }
 int ot_embed_adagrad_step(const ot_embed_params* p, void* stream) { return ot::embed_adagrad_impl(p, static_cast<cudaStream_t>(stream)); }
+int ot_heads_fwd(const ot_heads_params* p, void* stream) { return ot::heads_fwd_impl(p, static_cast<cudaStream_t>(stream)); }
+int ot_heads_bwd(const ot_heads_params* p, void* stream) { return ot::heads_bwd_impl(p, static_cast<cudaStream_t>(stream)); }
 
 }  // extern "C"

@@ -477,6 +477,40 @@ class TaskHead(nn.Module):
         return h @ self.kernel1 + self.bias1
 
 
+class _HeadsFn(torch.autograd.Function):
+    """Output norm + task heads (+ BCE) as two library calls (``ot_heads_fwd`` / ``ot_heads_bwd``).  ``x_last`` carries the
+    autograd edge into the blocks (bf16 rows of the residual stream); ``x_val`` are the fp32 values actually used (the
+    fp32 NS stream when the model keeps one).  Returns (probs [T, B], logits [T, B], loss: scalar, or empty without labels)."""
+
+    @staticmethod
+    def forward(ctx, x_last, anchor, model, x_val, labels):
+        ctx.set_materialize_grads(False)
+        heads = [(h.kernel0.detach(), h.bias0.detach(), h.kernel1.detach(), h.bias1.detach()) for h in model.task_heads.values()]
+        probs, logits, loss, saved = ops.heads_fwd(x_val, model.output_norm.scale.detach(), model.output_norm.eps, heads, labels)
+        ctx.saved = (model, x_val, heads, saved, probs, x_last.dtype)
+        return probs, logits, (loss if loss is not None else probs.new_zeros(0))
+
+    @staticmethod
+    def backward(ctx, d_probs, d_logits, d_loss):
+        model, x_val, heads, saved, probs, x_dtype = ctx.saved
+        dlogit = None
+        if d_loss is not None and d_loss.numel() and saved[3] is not None:
+            dlogit = saved[3] * d_loss                              # fused BCE: d loss / d logit was written by the forward kernel
+        if d_logits is not None:
+            dlogit = d_logits if dlogit is None else dlogit + d_logits
+        if d_probs is not None:
+            dl = d_probs * probs * (1.0 - probs)                    # sigmoid'
+            dlogit = dl if dlogit is None else dlogit + dl
+        if dlogit is None:
+            return None, None, None, None, None
+        g = engine._grad_buf
+        grads = [(g(h.kernel0), g(h.bias0), g(h.kernel1), g(h.bias1)) for h in model.task_heads.values()]
+        dx = ops.heads_bwd(x_val, model.output_norm.scale.detach(), model.output_norm.eps, heads, saved, dlogit.contiguous().float(),
+                           grads, g(model.output_norm.scale))
+        ctx.saved = None
+        return dx.to(x_dtype), None, None, None, None
+
+
 class OneTransModel(nn.Module):
     """OneTrans unified ranking model (OT/model.py:305-408): tokenizer -> pyramid-stacked blocks -> output
     RMSNorm -> task heads on the last token.  Returns ``{task: probabilities [B, 1]}`` like the reference
@@ -493,7 +527,8 @@ class OneTransModel(nn.Module):
         self.kv_cache = None
 
     def forward(self, non_seq_features: Dict[str, torch.Tensor], seq_features: Dict[str, torch.Tensor],
-                training: bool = False, use_kv_cache: bool = False, return_logits: bool = False) -> Dict[str, torch.Tensor]:
+                training: bool = False, use_kv_cache: bool = False, return_logits: bool = False,
+                _labels: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
         if use_kv_cache and not training:
             # OT/model.py:359-363 (as repaired, D6): reuse the cached sequence-side K/V of the current user; the
             # first call (or a call after reset_kv_cache) builds it from batch-1 sequence features.
@@ -518,20 +553,28 @@ class OneTransModel(nn.Module):
                 x_hp = None
             cur = keep
         x_last = x2[(cur - 1) * B:cur * B]
-        if x_hp is not None:
-            # value of the fp32 stream, gradient through the bf16 activations the kernels differentiate
-            xf = x_last.float()
-            x_last = xf + (x_hp[-B:] - xf).detach()
-        return self._heads(x_last, return_logits)
+        return self._heads(x_last, return_logits, x_hp[-B:] if x_hp is not None else None, _labels)
 
-    def _heads(self, x_last: torch.Tensor, return_logits: bool) -> Dict[str, torch.Tensor]:
-        # output norm (OT/model.py:384) and heads (:388-391) on the last token, in fp32
-        xf = x_last.float()
-        xn = xf * torch.rsqrt(xf.square().mean(dim=-1, keepdim=True) + self.output_norm.eps) * self.output_norm.scale
-        out = {}
-        for task, head in self.task_heads.items():
-            logit = head(xn)
-            out[task] = logit if return_logits else torch.sigmoid(logit)
+    def forward_with_loss(self, non_seq_features: Dict[str, torch.Tensor], seq_features: Dict[str, torch.Tensor],
+                          labels: Dict[str, torch.Tensor], training: bool = True):
+        """``(loss, probabilities)`` of one training step's forward: the model call of OT/train.py:118 and the loss of
+        :124-128 (sum over tasks of Keras BinaryCrossentropy) in one pass - the BCE is evaluated inside the head kernel."""
+        tasks = list(self.task_heads.keys())
+        y = torch.stack([labels[t].reshape(-1).to(torch.float32) for t in tasks]).contiguous()
+        out = self.forward(non_seq_features, seq_features, training=training, _labels=y)
+        return out.pop('_loss'), out
+
+    def _heads(self, x_last: torch.Tensor, return_logits: bool, x_val: Optional[torch.Tensor] = None,
+               labels: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+        """Output norm (OT/model.py:384) and heads (:388-391) on the last token, in fp32 (``ot_heads_fwd``).  ``x_val``: fp32
+        values of the rows (the fp32 NS stream) when they differ from ``x_last``, which then only carries the gradient."""
+        if x_val is None:
+            x_val = x_last.detach().float()
+        probs, logits, loss = _HeadsFn.apply(x_last, self.output_norm.scale, self, x_val.contiguous(), labels)
+        src = logits if return_logits else probs
+        out = {task: src[t].unsqueeze(1) for t, task in enumerate(self.task_heads.keys())}
+        if labels is not None:
+            out['_loss'] = loss
         return out
 
     # ---- inference with a cross-candidate cache of the sequence-side K/V (PAPER:144-151; repair D6) ----

@@ -399,3 +399,55 @@ def clip_rmsprop_step(param_ptrs: torch.Tensor, seg_off: torch.Tensor, seg_numel
     n = float(grad.numel())
     _run('ot_clip_rmsprop_step', L.load().ot_clip_rmsprop_step, p, f'n{grad.numel()}', 10.0 * n,
          n * (4.0 * (clip_norm > 0) + 24.0 + 8.0 * (momentum != 0.0) + 4.0 * bool(zero_grad)), n_launch=2 if clip_norm > 0 else 1)
+
+
+def heads_fwd(x: torch.Tensor, gain: torch.Tensor, eps: float, heads: Sequence[Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]],
+              labels: Optional[torch.Tensor] = None):
+    """Output norm + task heads (+ BCE) on the last-token rows ``x [B, d]`` (fp32).  ``heads``: per task
+    ``(kernel0 [d, h], bias0 [h], kernel1 [h, 1], bias1 [1])``.  Returns ``(probs [T, B], logits [T, B], loss | None, saved)``."""
+    if not x.is_cuda or x.dtype != torch.float32 or x.stride(-1) != 1:
+        raise RuntimeError('heads_fwd: x must be a CUDA fp32 tensor with contiguous rows (no CPU fallback)')
+    B, d = x.shape
+    T, Hd = len(heads), heads[0][0].shape[1]
+    dev = x.device
+    xn = torch.empty(B, d, dtype=torch.float32, device=dev)
+    rstd = torch.empty(B, dtype=torch.float32, device=dev)
+    pre = torch.empty(T, B, Hd, dtype=torch.float32, device=dev)
+    out = torch.empty(2, T, B, dtype=torch.float32, device=dev)          # probs, logits
+    p = L.HeadsParams()
+    p.x, p.ldx, p.gain, p.eps, p.B, p.d, p.hidden, p.n_tasks = x.data_ptr(), x.stride(0), gain.data_ptr(), eps, B, d, Hd, T
+    for t, (k0, b0, k1, b1) in enumerate(heads):
+        for w in (k0, b0, k1, b1):
+            assert w.dtype == torch.float32 and w.is_cuda and w.is_contiguous()
+        p.W0[t], p.b0[t], p.W1[t], p.b1[t] = k0.data_ptr(), b0.data_ptr(), k1.data_ptr(), b1.data_ptr()
+    p.xn, p.rstd, p.pre, p.probs, p.logits = xn.data_ptr(), rstd.data_ptr(), pre.data_ptr(), out[0].data_ptr(), out[1].data_ptr()
+    loss = g_bce = None
+    if labels is not None:
+        assert labels.shape == (T, B) and labels.dtype == torch.float32 and labels.is_contiguous()
+        lg = torch.zeros(1 + T * B, dtype=torch.float32, device=dev)   # [loss | g_bce]
+        loss, g_bce = lg[0], lg[1:].view(T, B)
+        p.labels, p.loss, p.g_bce = labels.data_ptr(), loss.data_ptr(), g_bce.data_ptr()
+    _run('ot_heads_fwd', L.load().ot_heads_fwd, p, f'd{d}_h{Hd}_T{T}', 2.0 * T * B * d * Hd, 4.0 * B * d * 2 + 4.0 * T * B * Hd)
+    return out[0], out[1], loss, (xn, rstd, pre, g_bce)
+
+
+def heads_bwd(x: torch.Tensor, gain: torch.Tensor, eps: float, heads, saved, dlogit: torch.Tensor, grads, dgain: torch.Tensor) -> torch.Tensor:
+    """Backward of ``heads_fwd``: ``dlogit [T, B]`` -> accumulates into ``grads`` (per task ``(dW0, db0, dW1, db1)`` fp32 buffers) and
+    ``dgain``; returns ``dx [B, d]`` (fp32)."""
+    xn, rstd, pre, _ = saved
+    B, d = x.shape
+    T, Hd = len(heads), heads[0][0].shape[1]
+    dx = torch.empty(B, d, dtype=torch.float32, device=x.device)
+    dpre = torch.empty(T, B, Hd, dtype=torch.float32, device=x.device)
+    assert dlogit.shape == (T, B) and dlogit.dtype == torch.float32 and dlogit.is_contiguous()
+    p = L.HeadsParams()
+    p.x, p.ldx, p.gain, p.eps, p.B, p.d, p.hidden, p.n_tasks = x.data_ptr(), x.stride(0), gain.data_ptr(), eps, B, d, Hd, T
+    for t, ((k0, b0, k1, b1), (g0, gb0, g1, gb1)) in enumerate(zip(heads, grads)):
+        p.W0[t], p.b0[t], p.W1[t], p.b1[t] = k0.data_ptr(), b0.data_ptr(), k1.data_ptr(), b1.data_ptr()
+        for gq in (g0, gb0, g1, gb1):
+            assert gq.dtype == torch.float32 and gq.is_contiguous()
+        p.dW0[t], p.db0[t], p.dW1[t], p.db1[t] = g0.data_ptr(), gb0.data_ptr(), g1.data_ptr(), gb1.data_ptr()
+    p.xn, p.rstd, p.pre = xn.data_ptr(), rstd.data_ptr(), pre.data_ptr()
+    p.dlogit, p.dpre, p.dgain, p.dx, p.lddx = dlogit.data_ptr(), dpre.data_ptr(), dgain.data_ptr(), dx.data_ptr(), dx.stride(0)
+    _run('ot_heads_bwd', L.load().ot_heads_bwd, p, f'd{d}_h{Hd}_T{T}', 6.0 * T * B * d * Hd, 4.0 * B * d * 3 + 8.0 * T * B * Hd, n_launch=2)
+    return dx

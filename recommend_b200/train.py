@@ -241,8 +241,10 @@ def train_step(model, grads: FlatGradBuffer, non_seq, seq, labels, world_size: i
     (``overlap_reduce``; PAPER:190 data parallelism).  Returns the detached loss tensor (no host sync)."""
     from . import engine
     grads.zero()
-    probs = model(non_seq, seq, training=True)
-    loss = bce_loss(probs, labels, model.config.tasks)
+    if hasattr(model, 'forward_with_loss'):
+        loss, _ = model.forward_with_loss(non_seq, seq, labels, training=True)      # BCE inside the head kernel
+    else:
+        loss = bce_loss(model(non_seq, seq, training=True), labels, model.config.tasks)
     if world_size > 1 and overlap_reduce and hasattr(model, 'blocks'):
         if getattr(grads, '_block_ranges', None) is None:
             # two slices per block, in the order their gradients become final: the FFN weights (about 3/4 of a block),

@@ -84,7 +84,7 @@ def test_position_segments_match_oracle_rule(alignment):
 
 def test_library_loads_and_exports_every_declared_symbol():
     lib = _lib.load()
-    assert lib.ot_version() == 8
+    assert lib.ot_version() == 9
     declared = set(re.findall(r'^\s*(?:int|const char\*)\s+(ot_\w+)\s*\(', open(HEADER).read(), re.M))
     assert declared == set(_lib.EXPORTED_SYMBOLS)
     for name in declared:
@@ -96,7 +96,7 @@ def test_ctypes_structs_match_header_layout():
     pairs = [('ot_gemm_seg', _lib.GemmSeg), ('ot_gemm_params', _lib.GemmParams), ('ot_wgrad_seg', _lib.WgradSeg),
              ('ot_wgrad_params', _lib.WgradParams), ('ot_attn_params', _lib.AttnParams), ('ot_attn_cached_params', _lib.AttnCachedParams), ('ot_rmsnorm_params', _lib.RmsnormParams),
              ('ot_ns_tokenizer_params', _lib.NsTokenizerParams), ('ot_colsum_params', _lib.ColsumParams),
-             ('ot_rmsprop_params', _lib.RmspropParams), ('ot_embed_params', _lib.EmbedParams)]
+             ('ot_rmsprop_params', _lib.RmspropParams), ('ot_embed_params', _lib.EmbedParams), ('ot_heads_params', _lib.HeadsParams)]
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', 'int main(void){']
     for cname, st in pairs:
         lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
