@@ -8,7 +8,7 @@
 //   ot_heads_fwd : x -> xn = RMSNorm(x) -> per task  pre = xn W0 + b0, h = gelu(pre), logit = h.w1 + b1, prob = sigmoid
 //                  (+ with labels: loss += sum_t mean_b BCE, and g_bce = d loss / d logit)
 //   ot_heads_bwd : dlogit -> dW1, db1, db0, dpre (kept for the dW0 pass), dxn -> norm backward -> dx, dgain
-//   (second launch inside ot_heads_bwd) dW0[k, j] += sum_b xn[b, k] dpre[b, j], one CTA per 8 rows of W0, no atomics
+//   (second launch inside ot_heads_bwd) dW0[k, j] += sum_b xn[b, k] dpre[b, j], one CTA per 8 rows of W0 and task
 #include "ot_common.cuh"
 #include "ot_host.h"
 #include "../../include/onetrans_b200.h"
@@ -79,7 +79,8 @@ heads_fwd_kernel(const __grid_constant__ HeadsKParams p) {
 #pragma unroll
       for (int s = 0; s < HD_SPB; ++s) acc[s] = 0.0f;
       const float* w = p.W0[t] + j;
-      for (int k = 0; k < p.d; ++k) {
+#pragma unroll 8
+      for (int k = 0; k < p.d; ++k) {        // d % 8 == 0: eight independent loads in flight per thread
         const float wk = __ldg(w + (long long)k * p.Hd);
 #pragma unroll
         for (int s = 0; s < HD_SPB; ++s)
@@ -178,6 +179,7 @@ heads_bwd_kernel(const __grid_constant__ HeadsKParams p) {
 #pragma unroll
       for (int s = 0; s < HD_SPB; ++s) acc[s] = 0.0f;
       const float4* wrow = reinterpret_cast<const float4*>(p.W0[t] + (long long)k * p.Hd);
+#pragma unroll 4
       for (int j4 = 0; j4 < p.Hd / 4; ++j4) {
         const float4 w = __ldg(wrow + j4);
 #pragma unroll
@@ -209,17 +211,19 @@ heads_bwd_kernel(const __grid_constant__ HeadsKParams p) {
   }
 }
 
-// dW0[t][k, j] += sum_b xn[b, k] * dpre[t][b, j]: CTA (kb, t) owns rows 8 kb .. 8 kb + 7 of W0[t] and walks the batch.
+// dW0[t][k, j] += sum_b xn[b, k] * dpre[t][b, j]: CTA (kb, t, z) owns rows 8 kb .. 8 kb + 7 of W0[t] and walks its slice of the batch.
 __global__ void __launch_bounds__(HD_THREADS)
 heads_dw0_kernel(const __grid_constant__ HeadsKParams p) {
   const int t = blockIdx.y, k0 = blockIdx.x * 8;
   const int ng = HD_THREADS / p.Hd;
   const int g = threadIdx.x / p.Hd, j = threadIdx.x - g * p.Hd;
   if (g >= ng) return;
-  const int per = (p.B + ng - 1) / ng;
-  const int bb = g * per, be = min(p.B, bb + per);
+  const int n_slices = ng * gridDim.z;          // the batch is cut over the thread groups and over blockIdx.z
+  const int per = (p.B + n_slices - 1) / n_slices;
+  const int bb = (blockIdx.z * ng + g) * per, be = min(p.B, bb + per);
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   const float* dp = p.dpre + (long long)t * p.B * p.Hd + j;
+#pragma unroll 4
   for (int b = bb; b < be; ++b) {
     const float d = dp[(long long)b * p.Hd];
     const float4 a = __ldg(reinterpret_cast<const float4*>(p.xn + (long long)b * p.d + k0));
@@ -282,7 +286,8 @@ int heads_bwd_impl(const ot_heads_params* p, cudaStream_t st) {
   }
   heads_bwd_kernel<<<(p->B + HD_SPB - 1) / HD_SPB, HD_THREADS, smem, st>>>(kp);
   OT_CUDA_CHECK(cudaGetLastError());
-  heads_dw0_kernel<<<dim3(p->d / 8, p->n_tasks), HD_THREADS, 0, st>>>(kp);
+  const int bsplit = p->B >= 1024 ? 8 : (p->B >= 128 ? 2 : 1);   // enough CTAs to fill the device; each adds its partial with atomics
+  heads_dw0_kernel<<<dim3(p->d / 8, p->n_tasks, bsplit), HD_THREADS, 0, st>>>(kp);
   OT_CUDA_CHECK(cudaGetLastError());
   return OT_OK;
 }
