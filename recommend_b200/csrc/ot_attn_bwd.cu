@@ -32,21 +32,32 @@ struct AttnBwdKParams {
 
 static constexpr float kLog2e = 1.4426950408889634f;
 
-// p and dS for 32 score columns of one row; writes bf16 into the P / dS tiles.
+// p and dS for 32 score columns of one row; writes bf16 into the P / dS tiles.  `fast`: the warp's 32 rows all exist and
+// see all 32 columns (every block below the diagonal) - no mask code.  exp2 is the one-instruction MUFU form.
 __device__ __forceinline__ void bwd_chunk(uint32_t t_s, uint32_t t_dp, int col0, int key0, int pq, bool row_valid,
                                           float lse2, float delta, float scale, float scale_log2, int row,
-                                          uint8_t* sP, uint8_t* sdS) {
+                                          uint8_t* sP, uint8_t* sdS, bool fast) {
   uint32_t vs[32], vd[32];
   tmem_ld_x32(t_s + col0, vs);
   tmem_ld_x32(t_dp + col0, vd);
   tmem_ld_wait();
   float pr[32], ds[32];
+  const float dlt_s = delta * scale;
+  if (fast) {
 #pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    float pv = exp2f(__uint_as_float(vs[i]) * scale_log2 - lse2);
-    if (!row_valid || (key0 + col0 + i > pq)) pv = 0.0f;
-    pr[i] = pv;
-    ds[i] = pv * (__uint_as_float(vd[i]) - delta) * scale;
+    for (int i = 0; i < 32; ++i) {
+      const float pv = ex2_approx(fmaf(__uint_as_float(vs[i]), scale_log2, -lse2));
+      pr[i] = pv;
+      ds[i] = pv * fmaf(__uint_as_float(vd[i]), scale, -dlt_s);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      float pv = ex2_approx(fmaf(__uint_as_float(vs[i]), scale_log2, -lse2));
+      if (!row_valid || (key0 + col0 + i > pq)) pv = 0.0f;
+      pr[i] = pv;
+      ds[i] = pv * fmaf(__uint_as_float(vd[i]), scale, -dlt_s);
+    }
   }
   if (sP != nullptr) ptile_store32(sP, row, col0, pr);
   ptile_store32(sdS, row, col0, ds);
@@ -179,7 +190,8 @@ ot_attn_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       tc_fence_after();
 #pragma unroll 1
       for (int c = 0; c < 2; ++c)
-        bwd_chunk(t_row, t_row + 128, half * 64 + c * 32, j * 128, pq, row_valid, lse2, delta, p.scale, p.scale_log2, row, nullptr, sdS);
+        bwd_chunk(t_row, t_row + 128, half * 64 + c * 32, j * 128, pq, row_valid, lse2, delta, p.scale, p.scale_log2, row, nullptr, sdS,
+                  /*fast=*/(q0 + (row - lane) + 31 < p.Lq) && (j * 128 + half * 64 + c * 32 + 31 <= off + q0 + (row - lane)));
       fence_proxy_async_smem();
       tc_fence_before();
       __syncthreads();
@@ -340,7 +352,8 @@ ot_attn_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tc_fence_after();
 #pragma unroll 1
       for (int c = 0; c < 2; ++c)
-        bwd_chunk(t_row, t_row + 128, half * 64 + c * 32, k0, pq, row_valid, lse2, delta, p.scale, p.scale_log2, row, sP, sdS);
+        bwd_chunk(t_row, t_row + 128, half * 64 + c * 32, k0, pq, row_valid, lse2, delta, p.scale, p.scale_log2, row, sP, sdS,
+                  /*fast=*/(q0 + (row - lane) + 31 < p.Lq) && (k0 + half * 64 + c * 32 + 31 <= off + q0 + (row - lane)));
       fence_proxy_async_smem();
       tc_fence_before();
       __syncthreads();
