@@ -187,3 +187,29 @@ def test_sample_batch_generator_matches_the_oracles():
             assert da.keys() == db.keys()
             for k in da:
                 assert torch.equal(da[k], db[k]), (mode, k)
+
+
+def test_public_surface_matches_the_reference_module():
+    """Names, call signatures and return shapes a user of OT/model.py relies on (OT/__init__.py:9-26,
+    OT/model.py:280-302, 395-416)."""
+    import inspect
+    for name in ('OneTransModel', 'OneTransConfig', 'get_model_config', 'RMSNorm', 'MixedMHA', 'MixedFFN', 'OneTransBlock', 'Tokenizer',
+                 'PyramidScheduler', 'create_onetrans_model'):
+        assert hasattr(R, name), name
+    cfg = R.get_model_config('small')
+    sched = R.PyramidScheduler(cfg).get_layer_config(0, 272)
+    assert set(sched) == {'keep_ratio', 'query_indices', 'keep_len'} and sched['keep_len'] == 136
+    assert list(sched['query_indices']) == list(range(136, 272))
+    cfg.num_layers, cfg.num_ns_tokens = 1, 2
+    m = R.create_onetrans_model('small')
+    assert isinstance(m, R.OneTransModel)
+    sig = inspect.signature(R.OneTransModel.forward)
+    assert list(sig.parameters)[:5] == ['self', 'non_seq_features', 'seq_features', 'training', 'use_kv_cache']
+    small = R.OneTransModel(cfg)
+    info = small.get_model_info()
+    assert set(info) >= {'total_parameters', 'num_layers', 'hidden_dim', 'num_heads'}
+    assert info['total_parameters'] == sum(p.numel() for p in small.parameters()) and info['num_layers'] == 1
+    small.reset_kv_cache()
+    assert small.kv_cache is None
+    for meth in ('build_kv_cache', 'score_candidates', 'forward_with_loss'):
+        assert callable(getattr(small, meth))
