@@ -191,7 +191,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='c2')
     ap.add_argument('--batch', type=int, default=0, help='override per-GPU batch')
-    ap.add_argument('--cpu-sample-batch', type=int, default=8)
+    ap.add_argument('--cpu-sample-batch', type=int, default=32, help='samples per CPU-oracle step (cpu_baseline and --impl reference)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-kernel-profile', action='store_true')
     ap.add_argument('--dropout', type=float, default=0.1, help='training dropout rate (OT/config.py:50 default 0.1)')
@@ -390,9 +390,9 @@ def main():
                          'timed': 'CUDA events around every launch of this bucket inside the timed region; the kernels[] table comes from a second, fully instrumented pass of the same steps'})
             line['roofline'] = roof
         if world == 1 and not args.no_cpu_baseline:
-            v, ms, cores = cpu_oracle_samples_per_sec(wl, args.cpu_sample_batch, 2, 1, args.dropout)
+            v, ms, cores = cpu_oracle_samples_per_sec(wl, args.cpu_sample_batch, 6, 1, args.dropout)
             line['cpu_baseline'] = {'value': v, 'unit': 'samples/s', 'cores': cores, 'kind': 'port',
-                                    'sample': f'oracle (PyTorch CPU fp32 restatement of OT/model.py) fwd+BCE+bwd, 2 timed steps of '
+                                    'sample': f'oracle (PyTorch CPU fp32 restatement of OT/model.py) fwd+BCE+bwd, 6 timed steps (1 warm-up) of '
                                               f'{args.cpu_sample_batch} samples of the same workload'}
         print(json.dumps(line), flush=True)
     if world > 1:
