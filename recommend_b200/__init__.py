@@ -9,10 +9,11 @@ from .model import (RMSNorm, MixedMHA, MixedFFN, OneTransBlock, Tokenizer, OneTr
                     create_onetrans_model)
 from .state import load_reference_style_params, export_reference_style_params
 from .embedding import EventEmbedding, SparseAdagrad
+from .inference import OneTransInferenceEngine
 
 __all__ = [
     'OneTransModel', 'OneTransConfig', 'OneTransSmallConfig', 'OneTransLargeConfig', 'get_model_config',
     'RMSNorm', 'MixedMHA', 'MixedFFN', 'OneTransBlock', 'Tokenizer', 'PyramidScheduler', 'TaskHead',
     'create_onetrans_model', 'resolve_keep_lens', 'load_reference_style_params', 'export_reference_style_params',
-    'EventEmbedding', 'SparseAdagrad',
+    'EventEmbedding', 'SparseAdagrad', 'OneTransInferenceEngine',
 ]
