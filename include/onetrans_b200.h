@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define OT_ABI_VERSION 9
+#define OT_ABI_VERSION 10
 
 int ot_version(void);
 const char* ot_last_error_string(void);
@@ -339,6 +339,53 @@ typedef struct ot_heads_params {
 } ot_heads_params;
 int ot_heads_fwd(const ot_heads_params* p, void* stream);
 int ot_heads_bwd(const ot_heads_params* p, void* stream);
+
+/* ---- streaming evaluation metrics (OT/train.py:95-109, 141-150, 178-187, 248-249; OT/evaluate.py:39-56, 91-99, 109-111):
+ * per binary task the reference keeps Keras AUC() / BinaryAccuracy() / Precision() / Recall() (+ F1Score, absent from the
+ * pinned TF 2.12 - SURVEY.md D11 - and the BinaryCrossentropy metric).  One pass over the predictions feeds all of them:
+ *   state[task] (int64 words): pos_hist[NT] | neg_hist[NT] | tp fp tn fn count rejected bce_sum(double bits) reserved
+ *   bucket  b = max(ceil(clip(p, 0, 1) * (NT - 1)) - 1, 0) in fp32   (Keras' update for evenly spaced thresholds)
+ *   tp/fp/tn/fn at p > threshold;  bce as Keras (clip to [1e-7, 1 - 1e-7], log(. + 1e-7))
+ *   samples with a NaN prediction or a label outside {0, 1} are skipped and counted in `rejected`
+ * ot_metrics_update ACCUMULATES into state (caller zeroes to reset); ot_metrics_result writes, per task,
+ *   result[task] (double words): auc accuracy precision recall f1 logloss count rejected
+ * with fp32 element-wise arithmetic for auc / precision / recall / f1 as Keras' result() (ROC, trapezoid summation).
+ * probs / labels: fp32, task t at base + t * ld, B samples each (the [n_tasks, B] layout ot_heads_fwd writes). */
+#define OT_METRICS_MAX_THRESHOLDS 512
+#define OT_METRICS_TAIL_WORDS 8
+#define OT_METRICS_RESULT_WORDS 8
+typedef struct ot_metrics_params {
+  const float* probs; const float* labels; int64_t ld;
+  int64_t B;
+  int32_t n_tasks;
+  int32_t num_thresholds;       /* NT; Keras default 200 */
+  float threshold;              /* 0.5 */
+  int64_t* state; int64_t state_stride;   /* >= 2 * NT + OT_METRICS_TAIL_WORDS words per task */
+  double* result;               /* ot_metrics_result only: [n_tasks, OT_METRICS_RESULT_WORDS] */
+} ot_metrics_params;
+int ot_metrics_update(const ot_metrics_params* p, void* stream);
+int ot_metrics_result(const ot_metrics_params* p, void* stream);
+
+/* ---- exact (tie-aware) ROC-AUC, overall or per segment (per-user AUC), for the north_star's "AUC delta <= 1e-4" check
+ * (Keras AUC() is a 200-threshold approximation).  Three steps:
+ *   ot_auc_pack_keys : keys[i] = segment_ids[i] << 33 | ordered_bits(probs[i]) << 1 | label   (segment 0 if segment_ids NULL;
+ *                      NaN / non-binary label / segment outside [0, n_segments) -> INT64_MAX key, counted in *rejected)
+ *   caller sorts keys ascending (any int64 sort)
+ *   ot_auc_ranksum   : per segment s:  seg_count[s] += #samples, seg_pos[s] += #positives,
+ *                      seg_sum2[s] += sum over positives of (first + last + 1) of their tie group in the sorted order
+ *                      = twice the 1-based mid-rank (ACCUMULATES; caller zeroes).
+ * With start[s] the exclusive prefix sum of seg_count:  U_s = (seg_sum2[s] - 2*seg_pos[s]*start[s])/2 - P_s(P_s+1)/2,
+ * AUC_s = U_s / (P_s * (count_s - P_s)).  n_segments < 2^30 - 1. */
+typedef struct ot_auc_params {
+  const float* probs; const float* labels; const int32_t* segment_ids;
+  int64_t n;
+  int32_t n_segments;
+  int64_t* keys;
+  int32_t* rejected;            /* may be NULL */
+  int64_t* seg_count; int64_t* seg_pos; int64_t* seg_sum2;
+} ot_auc_params;
+int ot_auc_pack_keys(const ot_auc_params* p, void* stream);
+int ot_auc_ranksum(const ot_auc_params* p, void* stream);
 
 #ifdef __cplusplus
 }

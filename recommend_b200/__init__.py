@@ -10,10 +10,16 @@ from .model import (RMSNorm, MixedMHA, MixedFFN, OneTransBlock, Tokenizer, OneTr
 from .state import load_reference_style_params, export_reference_style_params
 from .embedding import EventEmbedding, SparseAdagrad
 from .inference import OneTransInferenceEngine
+from .metrics import BinaryTaskMetrics, exact_auc, user_auc
+from .evaluate import OneTransEvaluator, load_model_for_evaluation, evaluate_model
+from .train import OneTransTrainer, train_one_trans_model
+from .data import DataLoader, OneTransDataset, SequenceProcessor, create_sample_batch
 
 __all__ = [
     'OneTransModel', 'OneTransConfig', 'OneTransSmallConfig', 'OneTransLargeConfig', 'get_model_config',
     'RMSNorm', 'MixedMHA', 'MixedFFN', 'OneTransBlock', 'Tokenizer', 'PyramidScheduler', 'TaskHead',
     'create_onetrans_model', 'resolve_keep_lens', 'load_reference_style_params', 'export_reference_style_params',
-    'EventEmbedding', 'SparseAdagrad', 'OneTransInferenceEngine',
+    'EventEmbedding', 'SparseAdagrad', 'OneTransInferenceEngine', 'BinaryTaskMetrics', 'exact_auc', 'user_auc', 'OneTransEvaluator',
+    'load_model_for_evaluation', 'evaluate_model', 'OneTransTrainer', 'train_one_trans_model', 'DataLoader', 'OneTransDataset',
+    'SequenceProcessor', 'create_sample_batch',
 ]

@@ -98,6 +98,17 @@ class HeadsParams(C.Structure):
                 ('dgain', fp), ('dx', fp), ('lddx', i64)]
 
 
+class MetricsParams(C.Structure):
+    _fields_ = [('probs', fp), ('labels', fp), ('ld', i64), ('B', i64), ('n_tasks', i32), ('num_thresholds', i32),
+                ('threshold', C.c_float), ('state', vp), ('state_stride', i64), ('result', vp)]
+
+
+class AucParams(C.Structure):
+    _fields_ = [('probs', fp), ('labels', fp), ('segment_ids', vp), ('n', i64), ('n_segments', i32), ('keys', vp),
+                ('rejected', vp), ('seg_count', vp), ('seg_pos', vp), ('seg_sum2', vp)]
+
+
+METRICS_MAX_THRESHOLDS, METRICS_TAIL_WORDS, METRICS_RESULT_WORDS = 512, 8, 8  # OT_METRICS_*
 OPT_CHUNK = 1024  # OT_OPT_CHUNK
 
 # every symbol include/onetrans_b200.h declares (tests check that the library exports all of them)
@@ -105,7 +116,7 @@ EXPORTED_SYMBOLS = [
     'ot_version', 'ot_last_error_string', 'ot_num_sms', 'ot_mixed_gemm', 'ot_wgrad', 'ot_attn_fwd', 'ot_attn_bwd', 'ot_attn_ns_cached_fwd',
     'ot_rmsnorm_fwd', 'ot_rmsnorm_bwd', 'ot_ns_tokenizer_fwd', 'ot_ns_tokenizer_bwd', 'ot_fill_rows', 'ot_colsum', 'ot_dropout_mask',
     'ot_clip_rmsprop_step', 'ot_embed_gather_fwd', 'ot_embed_scatter_bwd', 'ot_embed_adagrad_step',
-    'ot_heads_fwd', 'ot_heads_bwd',
+    'ot_heads_fwd', 'ot_heads_bwd', 'ot_metrics_update', 'ot_metrics_result', 'ot_auc_pack_keys', 'ot_auc_ranksum',
 ]
 
 _lib = None
@@ -137,7 +148,9 @@ def load() -> C.CDLL:
                          ('ot_ns_tokenizer_fwd', NsTokenizerParams), ('ot_ns_tokenizer_bwd', NsTokenizerParams),
                          ('ot_colsum', ColsumParams), ('ot_clip_rmsprop_step', RmspropParams), ('ot_embed_gather_fwd', EmbedParams),
                          ('ot_embed_scatter_bwd', EmbedParams), ('ot_embed_adagrad_step', EmbedParams),
-                         ('ot_heads_fwd', HeadsParams), ('ot_heads_bwd', HeadsParams)]:
+                         ('ot_heads_fwd', HeadsParams), ('ot_heads_bwd', HeadsParams),
+                         ('ot_metrics_update', MetricsParams), ('ot_metrics_result', MetricsParams),
+                         ('ot_auc_pack_keys', AucParams), ('ot_auc_ranksum', AucParams)]:
             fn = getattr(lib, name)
             fn.argtypes = [C.POINTER(st), C.c_void_p]
             fn.restype = C.c_int

@@ -85,6 +85,10 @@ int embed_scatter_impl(const ot_embed_params* p, cudaStream_t st);
 int embed_adagrad_impl(const ot_embed_params* p, cudaStream_t st);
 int heads_fwd_impl(const ot_heads_params* p, cudaStream_t st);
 int heads_bwd_impl(const ot_heads_params* p, cudaStream_t st);
+int metrics_update_impl(const ot_metrics_params* p, cudaStream_t st);
+int metrics_result_impl(const ot_metrics_params* p, cudaStream_t st);
+int auc_pack_impl(const ot_auc_params* p, cudaStream_t st);
+int auc_ranksum_impl(const ot_auc_params* p, cudaStream_t st);
 
 }  // namespace ot
 
@@ -129,5 +133,9 @@ int ot_embed_scatter_bwd(const ot_embed_params* p, void* stream) { return ot::em
 int ot_embed_adagrad_step(const ot_embed_params* p, void* stream) { return ot::embed_adagrad_impl(p, static_cast<cudaStream_t>(stream)); }
 int ot_heads_fwd(const ot_heads_params* p, void* stream) { return ot::heads_fwd_impl(p, static_cast<cudaStream_t>(stream)); }
 int ot_heads_bwd(const ot_heads_params* p, void* stream) { return ot::heads_bwd_impl(p, static_cast<cudaStream_t>(stream)); }
+int ot_metrics_update(const ot_metrics_params* p, void* stream) { return ot::metrics_update_impl(p, static_cast<cudaStream_t>(stream)); }
+int ot_metrics_result(const ot_metrics_params* p, void* stream) { return ot::metrics_result_impl(p, static_cast<cudaStream_t>(stream)); }
+int ot_auc_pack_keys(const ot_auc_params* p, void* stream) { return ot::auc_pack_impl(p, static_cast<cudaStream_t>(stream)); }
+int ot_auc_ranksum(const ot_auc_params* p, void* stream) { return ot::auc_ranksum_impl(p, static_cast<cudaStream_t>(stream)); }
 
 }  // extern "C"

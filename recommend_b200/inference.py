@@ -4,8 +4,9 @@
 north_star item 5 (PAPER:144-151): the user's sequence-side K/V are computed once and every candidate only runs its
 NS tokens (``OneTransModel.build_kv_cache`` / ``score_candidates``).
 
-Differences from the reference, all forced: weights come from a torch ``state_dict`` file (``model_weights.pt``; the
-reference's ``.h5`` needs h5py / Keras) next to the same ``config.json``; the model is called with two arguments (the
+Differences from the reference, all forced: weights come from ``model_weights.npz`` (Keras weight order, what
+``OneTransTrainer.save_model`` writes) or a torch ``state_dict`` file ``model_weights.pt`` (the reference's ``.h5`` needs h5py /
+Keras) next to the same ``config.json``; the model is called with two arguments (the
 reference passes one tuple, which its own ``call`` signature rejects - SURVEY.md D7)."""
 from __future__ import annotations
 
@@ -42,11 +43,15 @@ class OneTransInferenceEngine:
             raise FileNotFoundError(f'config file not found: {config_path}')
         with open(config_path, 'r') as f:
             self.config = OneTransConfig.from_dict(json.load(f))
-        weights_path = self.model_path / 'model_weights.pt'
-        if not weights_path.exists():
-            raise FileNotFoundError(f'model weights not found: {weights_path}')
+        from . import state
+        npz_path, weights_path = self.model_path / state.WEIGHTS_FILE, self.model_path / 'model_weights.pt'
+        if not npz_path.exists() and not weights_path.exists():
+            raise FileNotFoundError(f'model weights not found: {npz_path} (written by OneTransTrainer.save_model) or {weights_path}')
         self.model = OneTransModel(self.config)
-        self.model.load_state_dict(torch.load(weights_path, map_location='cpu'))
+        if npz_path.exists():
+            state.load_weights(self.model, npz_path)
+        else:
+            self.model.load_state_dict(torch.load(weights_path, map_location='cpu'))
         self.model = self.model.to(self.device).eval()
 
     # OT/examples/inference_example.py:62-92

@@ -266,3 +266,159 @@ def train_step(model, grads: FlatGradBuffer, non_seq, seq, labels, world_size: i
     if optimizer is not None:
         optimizer.step()
     return loss.detach()
+
+
+class OneTransTrainer:
+    """The reference's trainer object (OT/train.py:19-338) on the sm_100a path: same constructor and method names
+    (``train_step`` / ``val_step`` / ``train`` / ``save_model`` / ``load_model``), same history dictionary, same early-stopping and
+    checkpoint cadence.  What differs, and why:
+
+    * batches are ``(non_seq_features, seq_features, labels)`` triples of host or device tensors; the model is called with two
+      arguments (the reference passes one tuple, which its own ``call`` rejects - SURVEY.md D7);
+    * the per-tensor clip reads ``config.gradient_clip_norm`` (the reference reads a non-existent ``gradient_clip``, D8);
+    * dense optimizer: RMSprop only (``ot_clip_rmsprop_step``); the reference's ``'adam'`` branch (:56-62) is not on the path that
+      OT/config.py:39-47 selects and raises here rather than silently running something else;
+    * metrics are the streaming kernels of ``recommend_b200.metrics`` (all tasks in one pass);
+    * weights go to ``model_weights.npz`` in Keras weight order (``state.save_weights``; ``.h5`` needs h5py)."""
+
+    def __init__(self, config, model_dir: str = './models', device: str = 'cuda', world_size: int = 1):
+        from pathlib import Path
+        from .model import OneTransModel
+        from .metrics import BinaryTaskMetrics
+        self.config = config
+        self.model_dir = Path(model_dir)
+        self.model_dir.mkdir(parents=True, exist_ok=True)
+        self.device = torch.device(device)
+        self.world_size = world_size
+        self.model = OneTransModel(config).to(self.device)                       # OT/train.py:28
+        self.grads = FlatGradBuffer(self.model.parameters())
+        self.optimizer = self._create_optimizer()                                # :31
+        self.train_metrics = BinaryTaskMetrics(config.tasks, self.device)        # :37-38
+        self.val_metrics = BinaryTaskMetrics(config.tasks, self.device)
+        self.history = {'train_loss': [], 'val_loss': [], 'train_metrics': {}, 'val_metrics': {}}      # :41-46
+
+    def _create_optimizer(self) -> ClipRMSprop:
+        kind = self.config.optimizer_config.get('dense_optimizer', 'rmsprop')
+        if kind != 'rmsprop':
+            raise NotImplementedError(f"dense_optimizer={kind!r}: only 'rmsprop' (OT/config.py:40) has a kernel")
+        oc = dict(self.config.optimizer_config)
+        oc.setdefault('dense_lr', oc.get('learning_rate', self.config.learning_rate))
+        opt = ClipRMSprop(self.grads, lr=oc['dense_lr'], rho=oc.get('rho', 0.9), momentum=oc.get('momentum', 0.0),
+                          eps=oc.get('epsilon', 1e-7), clip_norm=getattr(self.config, 'gradient_clip_norm', 0.0))
+        return opt
+
+    def _to_device(self, batch):
+        return tuple({k: v.to(self.device, non_blocking=True) for k, v in part.items()} for part in batch)
+
+    def train_step(self, batch_data) -> Dict[str, torch.Tensor]:
+        """OT/train.py:111-155: forward, summed BCE, backward, clip, RMSprop, metric update.  Returns device tensors."""
+        non_seq, seq, labels = self._to_device(batch_data)
+        self.grads.zero()
+        loss, probs = self.model.forward_with_loss(non_seq, seq, labels, training=True)
+        loss.backward()
+        self.grads.all_reduce(self.world_size)
+        self.optimizer.step()
+        with torch.no_grad():
+            self.train_metrics.update_state(labels, {t: probs[t].detach() for t in self.config.tasks})
+            task_losses = {t: bce_loss({t: probs[t].detach()}, labels, [t]) for t in self.config.tasks}
+        return {'total_loss': loss.detach(), 'task_losses': task_losses}
+
+    @torch.no_grad()
+    def val_step(self, batch_data) -> Dict[str, torch.Tensor]:
+        """OT/train.py:157-184."""
+        non_seq, seq, labels = self._to_device(batch_data)
+        loss, probs = self.model.forward_with_loss(non_seq, seq, labels, training=False)
+        self.val_metrics.update_state(labels, probs)
+        return {'total_loss': loss, 'task_losses': {t: bce_loss({t: probs[t]}, labels, [t]) for t in self.config.tasks}}
+
+    def train(self, train_loader, val_loader=None, epochs: int = 10, save_freq: int = 1, early_stopping_patience: int = 5,
+              log_every: int = 100) -> Dict:
+        """OT/train.py:186-279.  Losses stay on the device during an epoch (one read-back per epoch, not per step)."""
+        import time
+        best_val_loss, patience_counter = float('inf'), 0
+        train_dataset = train_loader.get_train_dataset()
+        val_dataset = val_loader.get_val_dataset() if val_loader else None
+        for epoch in range(epochs):
+            start = time.time()
+            self.model.train()
+            train_losses = []
+            for step, batch in enumerate(train_dataset):
+                info = self.train_step(batch)
+                train_losses.append(info['total_loss'])
+                if log_every and step % log_every == 0:
+                    print(f"Epoch {epoch + 1}, Step {step}, Loss: {float(info['total_loss']):.4f}")
+            avg_train_loss = float(torch.stack(train_losses).mean())
+            if val_dataset is not None:
+                self.model.eval()
+                avg_val_loss = float(torch.stack([self.val_step(b)['total_loss'] for b in val_dataset]).mean())
+            else:
+                avg_val_loss = avg_train_loss                                    # :222-223
+            self.history['train_loss'].append(avg_train_loss)
+            self.history['val_loss'].append(avg_val_loss)
+            self.history['train_metrics'][epoch] = self.train_metrics.result()   # :233-237
+            self.history['val_metrics'][epoch] = self.val_metrics.result() if val_dataset is not None else {}
+            print(f'Epoch {epoch + 1}/{epochs} - Train Loss: {avg_train_loss:.4f}, Val Loss: {avg_val_loss:.4f}, Time: {time.time() - start:.2f}s')
+            if avg_val_loss < best_val_loss:                                     # :245-252
+                best_val_loss, patience_counter = avg_val_loss, 0
+                self.save_model('best_model')
+            else:
+                patience_counter += 1
+            if (epoch + 1) % save_freq == 0:                                     # :254-256
+                self.save_model(f'model_epoch_{epoch + 1}')
+            if patience_counter >= early_stopping_patience:                      # :258-261
+                print(f'early stopping at epoch {epoch + 1}')
+                break
+            self.train_metrics.reset_states()                                    # :263-267
+            self.val_metrics.reset_states()
+        self.save_model('final_model')                                           # :269-270
+        return self.history
+
+    def save_model(self, model_name: str) -> None:
+        """OT/train.py:281-314: weights, ``config.json`` and ``training_history.json`` under ``model_dir / model_name``."""
+        import json
+        from . import state
+        path = self.model_dir / model_name
+        path.mkdir(parents=True, exist_ok=True)
+        state.save_weights(self.model, path / state.WEIGHTS_FILE)
+        with open(path / 'config.json', 'w') as f:
+            json.dump(self.config.to_dict(), f, indent=2)
+        with open(path / 'training_history.json', 'w') as f:
+            json.dump(self.history, f, indent=2)
+
+    def load_model(self, model_path) -> None:
+        """OT/train.py:316-338: config, fresh model, weights, history - each only if its file is there."""
+        import json
+        from pathlib import Path
+        from . import state
+        from .config import OneTransConfig
+        from .model import OneTransModel
+        model_path = Path(model_path)
+        if (model_path / 'config.json').exists():
+            with open(model_path / 'config.json') as f:
+                self.config = OneTransConfig.from_dict(json.load(f))
+        self.model = OneTransModel(self.config).to(self.device)
+        if (model_path / state.WEIGHTS_FILE).exists():
+            state.load_weights(self.model, model_path / state.WEIGHTS_FILE)
+        self.grads = FlatGradBuffer(self.model.parameters())
+        self.optimizer = self._create_optimizer()
+        if (model_path / 'training_history.json').exists():
+            with open(model_path / 'training_history.json') as f:
+                self.history = json.load(f)
+
+
+def train_one_trans_model(config_name: str = 'small', data_paths: Optional[Dict[str, str]] = None, epochs: int = 10,
+                          model_dir: str = './models', config=None) -> OneTransTrainer:
+    """OT/train.py:341-375: config -> loader (sample data when no paths are given) -> trainer -> ``train`` with the same loader
+    for training and validation; returns the trainer."""
+    from .config import get_model_config
+    from .data import DataLoader
+    config = config if config is not None else get_model_config(config_name)
+    data_loader = DataLoader(config)
+    if data_paths:
+        data_loader.load_datasets(data_paths.get('train'), data_paths.get('val'), data_paths.get('test'))
+    else:
+        data_loader.train_dataset = data_loader.create_sample_data(seed=1)
+        data_loader.val_dataset = data_loader.create_sample_data(seed=2)
+    trainer = OneTransTrainer(config, model_dir)
+    trainer.train(train_loader=data_loader, val_loader=data_loader, epochs=epochs)
+    return trainer

@@ -7,6 +7,7 @@ import re
 import subprocess
 import tempfile
 
+import numpy as np
 import pytest
 import torch
 
@@ -84,7 +85,7 @@ def test_position_segments_match_oracle_rule(alignment):
 
 def test_library_loads_and_exports_every_declared_symbol():
     lib = _lib.load()
-    assert lib.ot_version() == 9
+    assert lib.ot_version() == 10
     declared = set(re.findall(r'^\s*(?:int|const char\*)\s+(ot_\w+)\s*\(', open(HEADER).read(), re.M))
     assert declared == set(_lib.EXPORTED_SYMBOLS)
     for name in declared:
@@ -213,3 +214,78 @@ def test_public_surface_matches_the_reference_module():
     assert small.kv_cache is None
     for meth in ('build_kv_cache', 'score_candidates', 'forward_with_loss'):
         assert callable(getattr(small, meth))
+
+
+# ---- rank-4 widening: datasets, Keras weight order, checkpoint files (host logic, CPU) ----------------------------------
+def test_dataset_and_loader_surface():
+    import recommend_b200 as R
+    cfg = R.get_model_config('small')
+    cfg.max_seq_len, cfg.batch_size = 8, 16
+    dl = R.DataLoader(cfg)
+    with pytest.raises(ValueError):
+        dl.get_train_dataset()                                    # OT/data_loader.py:246-247
+    dl.load_datasets(num_samples=(40, 20, 10))
+    assert dl.get_data_info() == {'train_samples': 40, 'val_samples': 20, 'test_samples': 10}
+    train = dl.get_train_dataset()
+    assert len(train) == 3
+    b1, b2 = [next(iter(train)) for _ in range(2)]               # re-iterable, reshuffled every epoch
+    assert b1[0]['price'].shape == (16, 1) and b1[1]['click_seq'].shape == (16, 8, 64) and b1[2]['ctr'].shape == (16, 1)
+    assert not torch.equal(b1[0]['price'], b2[0]['price'])
+    t1, t2 = [next(iter(dl.get_test_dataset(4))) for _ in range(2)]
+    assert torch.equal(t1[0]['price'], t2[0]['price']) and t1[0]['price'].shape == (4, 1)
+    assert sum(b[2]['ctr'].shape[0] for b in dl.get_val_dataset(16)) == 20          # ragged last batch kept
+    ns, seq, lab = dl.train_dataset[5]
+    n = int(dl.train_dataset.seq_lens['cart_seq'][5])
+    assert seq['cart_seq'].shape == (8, 64) and (seq['cart_seq'][:8 - n] == 0).all() and (seq['cart_seq'][8 - n:].abs().sum(1) > 0).all()
+    sp = R.SequenceProcessor(cfg)                                                   # OT/data_loader.py:68-101
+    assert sp.process_sequence(torch.zeros(0, 64)).shape == (8, 64)
+    long = torch.arange(20.0).reshape(20, 1).expand(20, 64)
+    assert torch.equal(sp.process_sequence(long)[:, 0], torch.arange(12.0, 20.0))   # the most recent events
+    short = sp.process_sequence(torch.ones(3, 64))
+    assert short[:5].abs().sum() == 0 and short[5:].eq(1).all()                     # padded in front
+    assert set(sp.process_multi_sequences({'a': long, 'b': short})) == {'a', 'b'}
+
+
+def test_keras_weight_order_and_checkpoint_roundtrip(tmp_path):
+    import recommend_b200 as R
+    from recommend_b200 import state
+    cfg = R.get_model_config('small')
+    cfg.num_layers, cfg.num_ns_tokens = 2, 3
+    torch.manual_seed(0)
+    m = R.OneTransModel(cfg)
+    wl = state.keras_weight_list(m)
+    names = [n for n, _ in wl]
+    # OT/model.py:308-333 / :206-222 / :169-184 / :29-57 / :128-147 attribute order
+    assert names[:2] == ['tokenizer/ns_tokenizer/dense/kernel', 'tokenizer/ns_tokenizer/dense/bias']
+    assert names[8] == 'tokenizer/sep_embedding/embeddings' and wl[8][1].shape == (1, 256)
+    blk = [n for n in names if n.startswith('blocks/0/')]
+    assert blk[:5] == ['blocks/0/norm1/scale', 'blocks/0/norm2/scale', 'blocks/0/attention/Wq_shared/kernel',
+                       'blocks/0/attention/Wk_shared/kernel', 'blocks/0/attention/Wv_shared/kernel']
+    assert blk[5:8] == [f'blocks/0/attention/Wq_dedicated/{j}/kernel' for j in range(3)] and blk[14] == 'blocks/0/attention/Wo/kernel'
+    assert blk[15:19] == ['blocks/0/ffn/ffn_shared/dense/kernel', 'blocks/0/ffn/ffn_shared/dense/bias',
+                          'blocks/0/ffn/ffn_shared/dense_1/kernel', 'blocks/0/ffn/ffn_shared/dense_1/bias']
+    assert names[-4:] == ['task_heads/cvr/dense/kernel', 'task_heads/cvr/dense/bias', 'task_heads/cvr/dense_1/kernel', 'task_heads/cvr/dense_1/bias']
+    assert dict(wl)['blocks/1/ffn/ffn_dedicated/2/dense/kernel'].shape == (256, 1024)            # Keras [in, out]
+    assert sum(a.size for _, a in wl) == m.get_model_info()['total_parameters']                  # every parameter exactly once
+    d = 256
+    assert np.array_equal(dict(wl)['blocks/1/attention/Wk_dedicated/1/kernel'], m.blocks[1].attention.Wqkv[2, :, d:2 * d].detach().numpy())
+    state.save_weights(m, tmp_path / 'w.npz')
+    m2 = R.OneTransModel(cfg)
+    with torch.no_grad():
+        for p in m2.parameters():
+            p.normal_()
+    state.load_weights(m2, tmp_path / 'w.npz')
+    assert all(torch.equal(a, b) for a, b in zip(m.parameters(), m2.parameters()))
+    with pytest.raises(ValueError):
+        state.load_keras_weight_list(m2, [a for _, a in wl][:-1])
+    cfg3 = R.get_model_config('small')
+    cfg3.num_layers, cfg3.num_ns_tokens = 2, 4
+    with pytest.raises(ValueError):
+        state.load_weights(R.OneTransModel(cfg3), tmp_path / 'w.npz')
+
+
+def test_evaluator_percentile_is_numpy_linear():
+    from recommend_b200.evaluate import _percentile
+    xs = [0.3, 0.1, 0.9, 0.5, 0.7, 0.2]
+    for q in (0, 50, 95, 99, 100):
+        assert _percentile(xs, q) == pytest.approx(float(np.percentile(xs, q)))
