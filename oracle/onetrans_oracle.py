@@ -495,3 +495,103 @@ def synthetic_batch(cfg: OracleConfig, B: int, seq_lens: Sequence[int], seed: in
         seq[name] = torch.randn(B, L, cfg.seq_feature_dim, generator=g, dtype=torch.float64).to(dtype)  # OT/data_loader.py:146
     labels = {t: (torch.rand(B, 1, generator=g) < 0.5).to(dtype) for t in cfg.tasks}  # OT/data_loader.py:151-154
     return non_seq, seq, labels
+
+
+# ---------------------------------------------------------------------------------------------------
+# two-stage inference with a per-layer cache of the sequence-side K/V  (PAPER:144-151; the reference's own
+# branch OT/model.py:95-98,120 cannot run).  Pinned in tests/test_oracle.py: stage 1 + stage 2 equal
+# ``model_forward`` on the same rows (S rows never see NS rows: causal mask, S first, OT/model.py:109-110, 235), and
+# with the pyramid off ``two_stage_extend`` equals a fresh stage 1 on the longer sequence.
+# ---------------------------------------------------------------------------------------------------
+def _layer_plan(L0: int, L_ns: int, keep_lens: Sequence[int]):
+    """Per layer (cur, Tn, cur_S, keep, Tq, keep_S): length, NS tokens alive, S tokens alive, kept tail, NS / S tokens that query."""
+    plan, cur = [], L0
+    for keep in keep_lens:
+        Tn = min(L_ns, cur)
+        Tq = min(Tn, keep)
+        plan.append((cur, Tn, cur - Tn, keep, Tq, keep - Tq))
+        cur = keep
+    return plan
+
+
+def _attend_tail(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, H: int) -> torch.Tensor:
+    """q [B, Tq, d] are the LAST Tq positions of the key sequence k/v [B, Lk, d]: query i sees keys 0 .. (Lk - Tq) + i
+    (OT/model.py:101-114 with the tail-aligned mask of ``mixed_mha``)."""
+    B, Tq, d = q.shape
+    Lk, dh = k.shape[1], d // H
+    s = torch.einsum('bqhd,bkhd->bhqk', q.reshape(B, Tq, H, dh), k.reshape(B, Lk, H, dh)) / math.sqrt(float(dh))
+    allowed = torch.arange(Lk).unsqueeze(0) <= torch.arange(Tq).unsqueeze(1) + (Lk - Tq)
+    s = torch.where(allowed, s, torch.full_like(s, -1e9))
+    return torch.einsum('bhqk,bkhd->bqhd', torch.softmax(s, dim=-1), v.reshape(B, Lk, H, dh)).reshape(B, Tq, d)
+
+
+def _s_rows_through_block(P, l: int, cfg: OracleConfig, x: torch.Tensor, n_q: int, kv_old=None):
+    """Sequence tokens (shared weights, group 0) through block ``l``: K/V for every row of ``x`` (behind ``kv_old`` if given),
+    queries for the last ``n_q`` rows.  Returns ``(y [1, n_q, d], (k, v))``."""
+    b = f'blocks.{l}.'
+    xn = rmsnorm(x, P[b + 'norm1.scale'])
+    k, v = xn @ P[b + 'attention.Wk'][0], xn @ P[b + 'attention.Wv'][0]
+    if kv_old is not None:
+        k, v = torch.cat([kv_old[0], k], 1), torch.cat([kv_old[1], v], 1)
+    if n_q == 0:
+        return x[:, :0], (k, v)
+    q = xn[:, xn.shape[1] - n_q:] @ P[b + 'attention.Wq'][0]
+    z = x[:, x.shape[1] - n_q:] + _attend_tail(q, k, v, cfg.num_heads) @ P[b + 'attention.Wo']
+    zn = rmsnorm(z, P[b + 'norm2.scale'])
+    f = gelu_erf(zn @ P[b + 'ffn.W1'][0] + P[b + 'ffn.b1'][0]) @ P[b + 'ffn.W2'][0] + P[b + 'ffn.b2'][0]
+    return z + f, (k, v)
+
+
+def two_stage_user_cache(P, cfg: OracleConfig, seq: Dict[str, torch.Tensor]):
+    """Stage 1, one user (batch 1): every layer's sequence-side (K, V)."""
+    assert cfg.ns_param_alignment == 'tail'
+    x = tokenizer_forward(P, cfg, {}, seq)
+    x = x[:, :x.shape[1] - cfg.num_ns_tokens]
+    L0 = x.shape[1] + cfg.num_ns_tokens
+    plan = _layer_plan(L0, cfg.num_ns_tokens, resolve_keep_lens(cfg, L0))
+    layers = []
+    for l, (cur, Tn, cur_S, keep, Tq, keep_S) in enumerate(plan):
+        if cur_S == 0:
+            layers.append(None)
+            x = x[:, :0]
+            continue
+        assert x.shape[1] == cur_S
+        x, kv = _s_rows_through_block(P, l, cfg, x, keep_S)
+        layers.append(kv)
+    return {'plan': plan, 'layers': layers, 'L0': L0}
+
+
+def two_stage_extend(P, cfg: OracleConfig, cache, new_events: torch.Tensor):
+    """Cross-request incremental update (PAPER:151): ``new_events [1, n, 64]`` are new behaviours of the LAST sequence, i.e. new
+    tokens at the tail of the S block.  Streaming rule: layer l gains the K/V of the new tokens alive at l; a new token sees
+    every key the layer already holds plus the new ones up to itself; ``n_{l+1} = min(n_l, keep_S(l))`` of them move on (the
+    key sets of a built cache only grow - which old tokens a layer keeps was decided when the cache was built)."""
+    i = len(cfg.sequence_features) - 1
+    x = new_events.to(P['tokenizer.sep_embedding'].dtype) @ P[f'tokenizer.seq_projections.{i}.kernel'] + P[f'tokenizer.seq_projections.{i}.bias']
+    layers = list(cache['layers'])
+    for l, (cur, Tn, cur_S, keep, Tq, keep_S) in enumerate(cache['plan']):
+        if layers[l] is None or x.shape[1] == 0:
+            break
+        x, layers[l] = _s_rows_through_block(P, l, cfg, x, min(x.shape[1], keep_S), layers[l])
+    return {'plan': cache['plan'], 'layers': layers, 'L0': cache['L0']}
+
+
+def two_stage_score(P, cfg: OracleConfig, cache, non_seq: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """Stage 2: logits of C candidates of the cached user; only their NS tokens are computed."""
+    L_ns, H = cfg.num_ns_tokens, cfg.num_heads
+    x = tokenizer_forward(P, cfg, non_seq, {})                       # [C, L_ns, d]: no sequence -> NS tokens only
+    for l, ((cur, Tn, cur_S, keep, Tq, keep_S), kv_s) in enumerate(zip(cache['plan'], cache['layers'])):
+        b = f'blocks.{l}.'
+        C = x.shape[0]
+        assert x.shape[1] == Tn
+        xn = rmsnorm(x, P[b + 'norm1.scale'])
+        lin = lambda t, W, bias, first: _mixed_linear(t, P[b + W], None if bias is None else P[b + bias], first, cur, L_ns, 'tail', False)
+        k, v = lin(xn, 'attention.Wk', None, cur - Tn), lin(xn, 'attention.Wv', None, cur - Tn)
+        if kv_s is not None:
+            k = torch.cat([kv_s[0].expand(C, -1, -1), k], 1)
+            v = torch.cat([kv_s[1].expand(C, -1, -1), v], 1)
+        q = lin(xn[:, Tn - Tq:], 'attention.Wq', None, cur - Tq)
+        z = x[:, Tn - Tq:] + _attend_tail(q, k, v, H) @ P[b + 'attention.Wo']
+        zn = rmsnorm(z, P[b + 'norm2.scale'])
+        x = z + lin(gelu_erf(lin(zn, 'ffn.W1', 'ffn.b1', cur - Tq)), 'ffn.W2', 'ffn.b2', cur - Tq)
+    return heads_forward(P, cfg, rmsnorm(x, P['output_norm.scale'])[:, -1, :])

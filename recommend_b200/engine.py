@@ -400,6 +400,32 @@ def user_cache_forward(x_s: torch.Tensor, blocks, plan, H: int, eps: float):
     return cache
 
 
+def extend_user_cache(x_new: torch.Tensor, blocks, plan, cache, H: int, eps: float):
+    """Cross-request incremental update of a user's cache (PAPER:151): ``x_new [n, d]`` are the tokens of
+    n new behaviours at the tail of the S block.  Streaming rule (restated in oracle ``two_stage_extend``): layer l gains the
+    K|V of the new tokens alive at l; a new token attends every key the layer already holds plus the new ones up to itself -
+    this is the pyramid kernel's own shape, a query tail over a longer key sequence, with the old keys supplied as
+    ``kv_prefix`` instead of being recomputed; ``n_{l+1} = min(n_l, keep_S(l))`` tokens move on.  Returns the new layer list."""
+    out = list(cache)
+    dev, d = x_new.device, x_new.shape[1]
+    for l, ((P, w), (cur, Tn, cur_S, keep, Tq, keep_S)) in enumerate(zip(blocks, plan)):
+        n = x_new.shape[0]
+        if out[l] is None or n == 0:
+            break
+        n_q = min(n, keep_S)
+        if n_q > 0:
+            x_new, out[l], _, _, _ = block_forward(x_new, P, w, 1, n, n_q, H, 0, 'tail', eps, False, kv_prefix=out[l])
+        else:
+            xn = torch.empty(n, d, dtype=bf16, device=dev)
+            ops.rmsnorm_fwd(x_new, P['norm1'], xn, None, eps)
+            kv = torch.empty(out[l].shape[0] + n, 2 * d, dtype=bf16, device=dev)
+            kv[:out[l].shape[0]].copy_(out[l])
+            ops.mixed_gemm(xn, w.Wkv_f, [(0, 1, n, 0, 0)], kv[out[l].shape[0]:])
+            out[l] = kv
+            x_new = x_new[:0]
+    return out
+
+
 def candidates_forward(x_ns: torch.Tensor, C_: int, blocks, plan, cache, H: int, L_ns: int, eps: float,
                        x_hp: Optional[torch.Tensor] = None):
     """Stage 2: C candidates of the cached user.  x_ns: token-major [L_ns*C, d] NS tokens.  Per layer only the NS

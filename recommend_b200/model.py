@@ -605,8 +605,36 @@ class OneTransModel(nn.Module):
         L0 = L_s + cfg.num_ns_tokens
         plan = engine.layer_plan(L0, cfg.num_ns_tokens, resolve_keep_lens(cfg, L0))
         layers = engine.user_cache_forward(x_s, self._block_bundles(), plan, cfg.num_heads, self.blocks[0].norm1.eps)
-        self.kv_cache = {'plan': plan, 'layers': layers, 'L0': L0}
+        self.kv_cache = {'plan': plan, 'layers': layers, 'L0': L0, 'has_last_sequence': seq_list[-1] is not None, 'appended': 0}
         return self.kv_cache
+
+    @torch.no_grad()
+    def extend_kv_cache(self, new_events: torch.Tensor, kv_cache=None):
+        """Cross-request incremental update (PAPER:151): ``new_events [1, n, 64]`` are n new behaviours of the cached user in the
+        LAST configured sequence (the only place where new tokens land at the tail of the S block; a new event in an earlier
+        sequence shifts every token behind it and needs ``build_kv_cache``).  Only the n new tokens are computed; each layer's
+        key set grows by the new tokens alive there (``engine.extend_user_cache``).  With the pyramid off this equals a fresh
+        build on the longer sequence; with it on, which OLD tokens a layer holds stays as decided at build time."""
+        cache = kv_cache if kv_cache is not None else self.kv_cache
+        if cache is None:
+            raise RuntimeError('extend_kv_cache: no KV cache; call build_kv_cache(seq_features) first')
+        if not cache.get('has_last_sequence', False):
+            raise ValueError('extend_kv_cache: the cache was built without the last sequence; new events would not be at the tail')
+        cfg, tok = self.config, self.tokenizer
+        _require_cuda(new_events, 'extend_kv_cache')
+        if new_events.dim() != 3 or new_events.shape[0] != 1 or new_events.shape[2] != cfg.seq_feature_dim:
+            raise ValueError(f'extend_kv_cache: new_events must be [1, n, {cfg.seq_feature_dim}], got {tuple(new_events.shape)}')
+        if new_events.shape[1] == 0:
+            return cache
+        n_seq = len(cfg.feature_config['sequence_features'])
+        seq_list = [None] * (n_seq - 1) + [new_events.to(bf16).contiguous()]
+        x_new, _, _, _ = engine.tokenizer_forward(None, seq_list, 1, cfg.hidden_dim, 0, tok._seq_weights(),
+                                                 [b.detach() for b in tok.seq_biases], tok.sep_embedding.detach(),
+                                                 tok.ns_kernel.detach(), tok.ns_bias.detach())
+        cache['layers'] = engine.extend_user_cache(x_new, self._block_bundles(), cache['plan'], cache['layers'], cfg.num_heads,
+                                                   self.blocks[0].norm1.eps)
+        cache['appended'] = cache.get('appended', 0) + new_events.shape[1]
+        return cache
 
     @torch.no_grad()
     def score_candidates(self, non_seq_features: Dict[str, torch.Tensor], kv_cache=None, return_logits: bool = False):

@@ -76,3 +76,75 @@ def test_t8_cached_scoring_equals_uncached_forward(schedule, L_ns, layers):
     lg = torch.cat([cached[t].flatten().float().cpu() for t in cfg.tasks])
     print('cached vs fp32 oracle rel-L2', rel_l2(lg, lo))
     assert rel_l2(lg, lo) < 1.5e-2, rel_l2(lg, lo)
+
+
+def _cache_fp(cache):
+    return [None if kv is None else kv.float().cpu() for kv in cache['layers']]
+
+
+@pytest.mark.parametrize('schedule,pyramid,L_ns,layers,n_new', [('linear_to_ns', True, 16, 4, 5), ('reference_ratio', True, 16, 6, 40),
+                                                              ('halving', True, 8, 3, 1), ('linear_to_ns', False, 8, 3, 7)])
+def test_extend_kv_cache_matches_the_oracle_streaming_rule(schedule, pyramid, L_ns, layers, n_new):
+    """append n new behaviours to a built cache == oracle ``two_stage_extend`` (fp32) on the same weights."""
+    ocfg, cfg = make_configs(num_layers=layers, num_ns_tokens=L_ns, schedule=schedule, pyramid_enabled=pyramid)
+    P = O.init_params(ocfg, seed=5)
+    O.randomize_small_params(P, seed=6)
+    # bf16-representable GEMM weights (as in T8 above): the comparison measures the kernels, not the weight cast
+    P = {k: (v.to(bf16).float() if (v.dim() >= 2 and 'ns_tokenizer' not in k and 'task_heads' not in k and 'sep_embedding' not in k) else v)
+         for k, v in P.items()}
+    model = R.OneTransModel(cfg).cuda()
+    R.load_reference_style_params(model, P)
+    C = 30
+    non_seq, seq, _ = O.synthetic_batch(ocfg, C, (60, 50, 40 + n_new), seed=11)
+    seq = {k: v[:1].to(bf16).float() for k, v in seq.items()}                       # one user; bf16-representable events
+    last = ocfg.sequence_features[-1]
+    head = dict(seq)
+    head[last], new = seq[last][:, :40], seq[last][:, 40:]
+    L0 = 60 + 50 + 40 + 2 + L_ns
+    ocfg.pyramid_keep_lens = R.resolve_keep_lens(cfg, L0) if pyramid else None
+    want_cache = O.two_stage_extend(P, ocfg, O.two_stage_user_cache(P, ocfg, head), new)
+    want = O.two_stage_score(P, ocfg, want_cache, non_seq)
+    with torch.no_grad():
+        model.build_kv_cache(to_cuda(head))
+        before = _cache_fp(model.kv_cache)
+        model.extend_kv_cache(new.cuda())
+        got = model.score_candidates(to_cuda(non_seq), return_logits=True)
+    d = cfg.hidden_dim
+    for l, (kv, want_kv, old) in enumerate(zip(_cache_fp(model.kv_cache), want_cache['layers'], before)):
+        if want_kv is None:
+            assert kv is None
+            continue
+        wk, wv = want_kv
+        assert kv.shape[0] == wk.shape[1], (l, kv.shape, wk.shape)                  # same key-set sizes per layer
+        assert torch.equal(kv[:old.shape[0]], old)                                  # old rows are copied, not recomputed
+        assert rel_l2(kv[:, :d], wk[0]) < 1.5e-2 and rel_l2(kv[:, d:], wv[0]) < 1.5e-2
+    err = rel_l2(torch.cat([got[t].flatten().float().cpu() for t in cfg.tasks]), torch.cat([want[t].flatten() for t in cfg.tasks]))
+    print(f'extend[{schedule}, pyramid={pyramid}] logits rel-L2 vs fp32 oracle: {err:.3e}')
+    assert err < 1.5e-2                                                              # the bar T8 holds the cached path to
+    if not pyramid:     # size-independent property: append == fresh build on the longer sequence
+        with torch.no_grad():
+            fresh = _cache_fp(model.build_kv_cache(to_cuda(seq)))
+        model.build_kv_cache(to_cuda(head))
+        model.extend_kv_cache(new.cuda())
+        for a, b in zip(_cache_fp(model.kv_cache), fresh):
+            assert a.shape == b.shape and rel_l2(a, b) < 1.5e-2
+
+
+def test_extend_kv_cache_argument_checks():
+    ocfg, cfg = make_configs(num_layers=2, num_ns_tokens=4, schedule='linear_to_ns')
+    model = R.OneTransModel(cfg).cuda()
+    ev = torch.randn(1, 3, 64, device='cuda')
+    with pytest.raises(RuntimeError):
+        model.extend_kv_cache(ev)                                                   # no cache yet
+    _, seq, _ = O.synthetic_batch(ocfg, 1, (6, 5, 4), seed=1)
+    model.build_kv_cache(to_cuda({k: v for k, v in seq.items() if k != 'purchase_seq'}))
+    with pytest.raises(ValueError):
+        model.extend_kv_cache(ev)                                                   # built without the last sequence
+    model.build_kv_cache(to_cuda(seq))
+    with pytest.raises(ValueError):
+        model.extend_kv_cache(torch.randn(2, 3, 64, device='cuda'))                 # one user only
+    sizes = [kv.shape[0] for kv in model.kv_cache['layers'] if kv is not None]
+    model.extend_kv_cache(ev[:, :0])                                                # nothing new: unchanged
+    assert sizes == [kv.shape[0] for kv in model.kv_cache['layers'] if kv is not None] and model.kv_cache['appended'] == 0
+    model.extend_kv_cache(ev)
+    assert model.kv_cache['layers'][0].shape[0] == sizes[0] + 3 and model.kv_cache['appended'] == 3

@@ -256,3 +256,56 @@ def test_T13_event_embedding_lookup_concat_and_adagrad():
     assert torch.equal(g[:, 0], torch.tensor([1., 1., 2., 2., 2.], dtype=torch.float64))   # row 2 twice, rows 3 and 4 twice each
     w, acc = O.adagrad_step(torch.tensor([1.0]), torch.tensor([2.0]), torch.tensor([0.1]), lr=0.1, eps=1e-7)
     assert abs(float(acc) - 4.1) < 1e-6 and abs(float(w) - (1.0 - 0.1 * 2.0 / (4.1 ** 0.5 + 1e-7))) < 1e-6
+
+
+# ---- two-stage inference restatement (oracle-internal pins, fp64) --------------------------------------------------------
+def _two_stage_setup(schedule, pyramid=True, layers=3, L_ns=4):
+    cfg = O.OracleConfig(hidden_dim=64, num_layers=layers, num_heads=4, ffn_dim=128, num_ns_tokens=L_ns, pyramid_enabled=pyramid)
+    L0 = 9 + 7 + 11 + 2 + L_ns
+    cfg.pyramid_keep_lens = {'linear_to_ns': O.keep_lens_linear_to_ns(L0, layers, L_ns), 'halving': O.keep_lens_halving(L0, layers, L_ns),
+                             'reference_ratio': None}[schedule]
+    P = O.init_params(cfg, seed=3, dtype=torch.float64)
+    O.randomize_small_params(P, seed=4)
+    non_seq, seq, _ = O.synthetic_batch(cfg, 5, (9, 7, 11), seed=8)
+    to64 = lambda d: {k: v.double() for k, v in d.items()}
+    return cfg, P, to64(non_seq), to64({k: v[:1] for k, v in seq.items()})
+
+
+@pytest.mark.parametrize('schedule', ['linear_to_ns', 'reference_ratio', 'halving'])
+def test_two_stage_equals_full_forward(schedule):
+    cfg, P, non_seq, seq1 = _two_stage_setup(schedule)
+    full = O.model_forward(P, cfg, non_seq, {k: v.expand(5, -1, -1) for k, v in seq1.items()}, return_logits=True)
+    cache = O.two_stage_user_cache(P, cfg, seq1)
+    got = O.two_stage_score(P, cfg, cache, non_seq)
+    for t in cfg.tasks:
+        assert torch.allclose(got[t], full[t], rtol=0, atol=1e-10)
+
+
+def test_two_stage_extend_without_pyramid_is_a_fresh_build():
+    cfg, P, non_seq, seq1 = _two_stage_setup('linear_to_ns', pyramid=False)
+    last = cfg.sequence_features[-1]
+    head = dict(seq1)
+    head[last] = seq1[last][:, :6]
+    cache = O.two_stage_extend(P, cfg, O.two_stage_user_cache(P, cfg, head), seq1[last][:, 6:])
+    fresh = O.two_stage_user_cache(P, cfg, seq1)
+    for a, b in zip(cache['layers'], fresh['layers']):
+        assert torch.allclose(a[0], b[0], rtol=0, atol=1e-10) and torch.allclose(a[1], b[1], rtol=0, atol=1e-10)
+    # the NS-side plan of a cache is the one it was built with: score both with the fresh plan
+    got = O.two_stage_score(P, cfg, {**cache, 'plan': fresh['plan']}, non_seq)
+    want = O.two_stage_score(P, cfg, fresh, non_seq)
+    for t in cfg.tasks:
+        assert torch.allclose(got[t], want[t], rtol=0, atol=1e-10)
+
+
+def test_two_stage_extend_with_pyramid_only_grows_key_sets():
+    cfg, P, non_seq, seq1 = _two_stage_setup('linear_to_ns')
+    base = O.two_stage_user_cache(P, cfg, seq1)
+    ext = O.two_stage_extend(P, cfg, base, torch.randn(1, 3, 64, dtype=torch.float64, generator=torch.Generator().manual_seed(2)))
+    n = 3
+    for (cur, Tn, cur_S, keep, Tq, keep_S), a, b in zip(base['plan'], base['layers'], ext['layers']):
+        if a is None or n == 0:
+            assert (a is None and b is None) or a[0].shape == b[0].shape
+            continue
+        assert b[0].shape[1] == a[0].shape[1] + n and torch.equal(b[0][:, :a[0].shape[1]], a[0])    # old keys untouched
+        n = min(n, keep_S)
+    assert not torch.allclose(O.two_stage_score(P, cfg, ext, non_seq)['ctr'], O.two_stage_score(P, cfg, base, non_seq)['ctr'])
