@@ -9,7 +9,7 @@ from .model import (RMSNorm, MixedMHA, MixedFFN, OneTransBlock, Tokenizer, OneTr
                     create_onetrans_model)
 from .state import load_reference_style_params, export_reference_style_params
 from .embedding import EventEmbedding, SparseAdagrad
-from .inference import OneTransInferenceEngine
+from .inference import OneTransInferenceEngine, score_candidates_sharded, shard_bounds, gather_shards
 from .metrics import BinaryTaskMetrics, exact_auc, user_auc
 from .evaluate import OneTransEvaluator, load_model_for_evaluation, evaluate_model
 from .train import OneTransTrainer, train_one_trans_model
@@ -21,5 +21,5 @@ __all__ = [
     'create_onetrans_model', 'resolve_keep_lens', 'load_reference_style_params', 'export_reference_style_params',
     'EventEmbedding', 'SparseAdagrad', 'OneTransInferenceEngine', 'BinaryTaskMetrics', 'exact_auc', 'user_auc', 'OneTransEvaluator',
     'load_model_for_evaluation', 'evaluate_model', 'OneTransTrainer', 'train_one_trans_model', 'DataLoader', 'OneTransDataset',
-    'SequenceProcessor', 'create_sample_batch',
+    'SequenceProcessor', 'create_sample_batch', 'score_candidates_sharded', 'shard_bounds', 'gather_shards',
 ]

@@ -21,6 +21,53 @@ from .config import OneTransConfig
 from .model import OneTransModel
 
 
+def shard_bounds(n: int, world_size: int, rank: int) -> Tuple[int, int]:
+    """Rows ``[start, end)`` of rank ``rank`` when ``n`` candidates are split into ``world_size`` contiguous shards whose sizes
+    differ by at most one (the first ``n % world_size`` ranks take the extra row)."""
+    base, extra = divmod(n, world_size)
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
+def gather_shards(local: torch.Tensor, n: int, world_size: int, rank: int, group=None) -> torch.Tensor:
+    """All-gather of per-rank score shards ``local [T, n_rank]`` (shard layout of ``shard_bounds``) into ``[T, n]`` on every rank:
+    the one collective of sharded candidate scoring ("scores AllGather [8192]").  Shards are padded to the largest
+    shard so that one ``all_gather`` moves them (NCCL over NVLink on GPUs; gloo in the CPU tests)."""
+    import torch.distributed as dist
+    if world_size == 1 or n == 0:
+        return local
+    T = local.shape[0]
+    width = -(-n // world_size)
+    send = local.new_zeros(T, width)
+    send[:, :local.shape[1]] = local
+    recv = local.new_empty(world_size, T, width)
+    dist.all_gather(list(recv.unbind(0)), send, group=group)      # contiguous views of one buffer; works on NCCL and gloo alike
+    parts = []
+    for r in range(world_size):
+        s, e = shard_bounds(n, world_size, r)
+        parts.append(recv[r, :, :e - s])
+    return torch.cat(parts, dim=1)
+
+
+@torch.no_grad()
+def score_candidates_sharded(model: OneTransModel, user_sequence_features: Dict[str, torch.Tensor], candidate_non_seq: Dict[str, torch.Tensor],
+                             world_size: int = 1, rank: int = 0, group=None, return_logits: bool = False) -> Dict[str, torch.Tensor]:
+    """BASELINE config 5 on several GPUs: candidates are the shard axis.  Every rank builds the user's per-layer
+    K/V cache itself (1-2 MB of state, cheaper to recompute than to broadcast), scores rows ``shard_bounds(C, world, rank)`` of
+    the candidate features and the probabilities are all-gathered, so every rank returns ``{task: [C, 1]}`` for all C."""
+    C = next(iter(candidate_non_seq.values())).shape[0]
+    s, e = shard_bounds(C, world_size, rank)
+    model.build_kv_cache(user_sequence_features)
+    tasks = list(model.config.tasks)
+    if e > s:
+        out = model.score_candidates({k: v[s:e] for k, v in candidate_non_seq.items()}, return_logits=return_logits)
+        local = torch.stack([out[t].reshape(-1).float() for t in tasks])
+    else:
+        local = torch.zeros(len(tasks), 0, dtype=torch.float32, device=next(iter(candidate_non_seq.values())).device)
+    full = gather_shards(local, C, world_size, rank, group)
+    return {t: full[i].unsqueeze(1) for i, t in enumerate(tasks)}
+
+
 class OneTransInferenceEngine:
     def __init__(self, model_or_path: Union[OneTransModel, str, Path], device: str = 'cuda', pad_sequences: bool = True):
         self.device = torch.device(device)

@@ -109,3 +109,32 @@ def test_bce_matches_oracle():
     p = {'ctr': torch.rand(6, 1), 'cvr': torch.rand(6, 1)}
     y = {'ctr': (torch.rand(6, 1) < 0.5).float(), 'cvr': (torch.rand(6, 1) < 0.5).float()}
     assert torch.allclose(bce_loss(p, y, ['ctr', 'cvr']), O.bce_loss(p, y, ['ctr', 'cvr']))
+
+
+# ---- sharded candidate scoring (BASELINE config 5 on several GPUs): the host side of the one all-gather ----------
+def _worker_gather(rank, world, port, out_dir):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from recommend_b200.inference import shard_bounds, gather_shards
+    res = {}
+    for n in (7, 8, 1, 2):                                    # ragged shards, even shards, an empty shard on the last rank
+        scores = torch.arange(2 * n, dtype=torch.float32).reshape(2, n) * 0.5 + 1.0      # the [T, n] table every rank should end with
+        s, e = shard_bounds(n, world, rank)
+        res[n] = gather_shards(scores[:, s:e].contiguous(), n, world, rank)
+    torch.save(res, os.path.join(out_dir, f'gather{rank}.pt'))
+    dist.destroy_process_group()
+
+
+def test_sharded_candidate_scores_gather_in_order(tmp_path):
+    from recommend_b200.inference import shard_bounds
+    for n, w in ((8192, 8), (7, 2), (5, 8), (0, 4)):
+        b = [shard_bounds(n, w, r) for r in range(w)]
+        assert b[0][0] == 0 and b[-1][1] == n and all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+        assert max(e - s for s, e in b) - min(e - s for s, e in b) <= 1
+    world = 2
+    mp.spawn(_worker_gather, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    r = [torch.load(os.path.join(tmp_path, f'gather{i}.pt')) for i in range(world)]
+    for n in (7, 8, 1, 2):
+        want = torch.arange(2 * n, dtype=torch.float32).reshape(2, n) * 0.5 + 1.0
+        assert torch.equal(r[0][n], want) and torch.equal(r[1][n], want), n
