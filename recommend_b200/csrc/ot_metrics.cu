@@ -49,8 +49,25 @@ __device__ __forceinline__ void block_sum_u32(unsigned (&v)[NV], unsigned* red /
     }
 }
 
+// one sample into the per-warp histogram and the per-thread counters
+__device__ __forceinline__ void metrics_sample(float pi, float yi, unsigned* __restrict__ my, int NT, float scale, float threshold,
+                                               unsigned (&c)[6], float& bce) {
+  if (!(pi == pi) || !(yi == 0.0f || yi == 1.0f)) { c[5]++; return; }       // NaN prediction or non-binary label
+  const bool pos = yi != 0.0f;
+  const float pc = fminf(fmaxf(pi, 0.0f), 1.0f);
+  int b = (int)ceilf(pc * scale) - 1;
+  b = b < 0 ? 0 : b;
+  atomicAdd(&my[(pos ? 0 : NT) + b], 1u);
+  const bool pp = pi > threshold;
+  c[0] += (pos && pp); c[1] += (!pos && pp); c[2] += (!pos && !pp); c[3] += (pos && !pp); c[4]++;
+  const float q = fminf(fmaxf(pi, 1e-7f), 1.0f - 1e-7f);
+  bce -= logf((pos ? q : 1.0f - q) + 1e-7f);      // == -(y log(q + eps) + (1 - y) log(1 - q + eps)) for y in {0, 1}
+}
+
 // grid (x = sample chunks, y = task).  Per-warp private histograms in shared memory (predictions of a trained model pile up
 // in a few buckets; eight copies keep the shared atomics apart), one int64 atomic per non-empty bucket and CTA at the end.
+// Loads are 16-byte and two deep per thread (32 B of predictions + 32 B of labels in flight per thread): with one 4-byte
+// load per thread the kernel sat at 23 % of the HBM peak, stalled on the long scoreboard (profiles/README.md).
 __global__ void __launch_bounds__(MET_THREADS)
 metrics_update_kernel(const float* __restrict__ probs, const float* __restrict__ labels, long long ld, long long B, int NT,
                       float threshold, long long* __restrict__ state, long long state_stride) {
@@ -67,23 +84,35 @@ metrics_update_kernel(const float* __restrict__ probs, const float* __restrict__
   const float scale = (float)(NT - 1);
   unsigned c[6] = {0u, 0u, 0u, 0u, 0u, 0u};           // tp, fp, tn, fn, count, rejected
   float bce = 0.0f;
-  // each CTA walks a contiguous run of samples so that at most ~2^24 land in one fp32 partial sum / u32 counter
-  const long long per = (B + gridDim.x - 1) / gridDim.x;
+  // each CTA walks a contiguous run of samples (a multiple of 4, so that runs start 16-byte aligned when the rows do)
+  const long long per = (((B + gridDim.x - 1) / gridDim.x) + 3) & ~3ll;
   const long long i0 = (long long)blockIdx.x * per;
   const long long i1 = (i0 + per < B) ? i0 + per : B;
-  for (long long i = i0 + threadIdx.x; i < i1; i += MET_THREADS) {
-    const float pi = __ldg(p + i), yi = __ldg(y + i);
-    if (!(pi == pi) || !(yi == 0.0f || yi == 1.0f)) { c[5]++; continue; }     // NaN prediction or non-binary label
-    const bool pos = yi != 0.0f;
-    const float pc = fminf(fmaxf(pi, 0.0f), 1.0f);
-    int b = (int)ceilf(pc * scale) - 1;
-    b = b < 0 ? 0 : b;
-    atomicAdd(&my[(pos ? 0 : NT) + b], 1u);
-    const bool pp = pi > threshold;
-    c[0] += (pos && pp); c[1] += (!pos && pp); c[2] += (!pos && !pp); c[3] += (pos && !pp); c[4]++;
-    const float q = fminf(fmaxf(pi, 1e-7f), 1.0f - 1e-7f);
-    bce -= yi * logf(q + 1e-7f) + (1.0f - yi) * logf(1.0f - q + 1e-7f);
+  long long done = i0;
+  if (i0 < i1 && ((reinterpret_cast<uintptr_t>(p + i0) | reinterpret_cast<uintptr_t>(y + i0)) & 15) == 0) {
+    const float4* p4 = reinterpret_cast<const float4*>(p + i0);
+    const float4* y4 = reinterpret_cast<const float4*>(y + i0);
+    const long long n4 = (i1 - i0) >> 2;
+    for (long long j = threadIdx.x; j < n4; j += 2 * MET_THREADS) {
+      const bool two = j + MET_THREADS < n4;
+      const float4 pa = __ldg(p4 + j), ya = __ldg(y4 + j);
+      float4 pb = make_float4(0.f, 0.f, 0.f, 0.f), yb = pb;
+      if (two) { pb = __ldg(p4 + j + MET_THREADS); yb = __ldg(y4 + j + MET_THREADS); }
+      metrics_sample(pa.x, ya.x, my, NT, scale, threshold, c, bce);
+      metrics_sample(pa.y, ya.y, my, NT, scale, threshold, c, bce);
+      metrics_sample(pa.z, ya.z, my, NT, scale, threshold, c, bce);
+      metrics_sample(pa.w, ya.w, my, NT, scale, threshold, c, bce);
+      if (two) {
+        metrics_sample(pb.x, yb.x, my, NT, scale, threshold, c, bce);
+        metrics_sample(pb.y, yb.y, my, NT, scale, threshold, c, bce);
+        metrics_sample(pb.z, yb.z, my, NT, scale, threshold, c, bce);
+        metrics_sample(pb.w, yb.w, my, NT, scale, threshold, c, bce);
+      }
+    }
+    done = i0 + (n4 << 2);
   }
+  for (long long i = done + threadIdx.x; i < i1; i += MET_THREADS)
+    metrics_sample(__ldg(p + i), __ldg(y + i), my, NT, scale, threshold, c, bce);
   __syncthreads();
   for (int b = threadIdx.x; b < 2 * NT; b += MET_THREADS) {
     unsigned t = 0;
@@ -128,7 +157,7 @@ metrics_result_kernel(const long long* __restrict__ state, long long state_strid
     auc += (x_prev - x) * ((y_prev + y) / 2.0f);
     x_prev = x; y_prev = y;
   }
-  const float ctp = (float)tail[0], cfp = (float)tail[1], ctn = (float)tail[2], cfn = (float)tail[3];
+  const float ctp = (float)tail[0], cfp = (float)tail[1], cfn = (float)tail[3];
   const double cnt = (double)tail[4];
   const float prec = div_no_nan(ctp, ctp + cfp), rec = div_no_nan(ctp, ctp + cfn);
   o[0] = auc;
@@ -148,8 +177,8 @@ int metrics_update_impl(const ot_metrics_params* p, cudaStream_t st) {
   if (p->n_tasks <= 0 || p->n_tasks > 65535 || p->B < 0) OT_FAIL(OT_ERR_INVALID_ARG, "ot_metrics_update: n_tasks=%d B=%lld", p->n_tasks, (long long)p->B);
   if (p->state_stride < 2 * p->num_thresholds + OT_METRICS_TAIL_WORDS) OT_FAIL(OT_ERR_INVALID_ARG, "ot_metrics_update: state_stride=%lld too small", (long long)p->state_stride);
   if (p->B == 0) return OT_OK;
-  const long long want = (p->B + MET_THREADS * 8 - 1) / (MET_THREADS * 8);
-  long long cap = (long long)num_sms() * 4 / p->n_tasks;
+  const long long want = (p->B + MET_THREADS * 16 - 1) / (MET_THREADS * 16);
+  long long cap = (long long)num_sms() * 8 / p->n_tasks;
   if (cap < 1) cap = 1;
   long long gx = want < cap ? want : cap;
   const long long min_gx = (p->B + (1ll << 30) - 1) >> 30;          // u32 per-CTA counters
@@ -191,40 +220,62 @@ auc_pack_kernel(const float* __restrict__ probs, const float* __restrict__ label
 }
 
 // sorted keys -> per segment: cnt, pos, sum2 = sum over positives of (first + last + 1) of their tie group, i.e. twice the
-// 1-based mid-rank in the GLOBAL order (the host subtracts the segment start).
+// 1-based mid-rank in the GLOBAL order (the host subtracts the segment start).  A CTA covers AUC_ITEMS * 256 consecutive keys
+// and, when they all belong to one segment (the common case), leaves with one atomic triple: with one triple per 256 keys the
+// same-address atomics of the single-segment case serialised the kernel at 185 GB/s (profiles/README.md).
+static constexpr int AUC_ITEMS = 8;
 __global__ void __launch_bounds__(256)
 auc_ranksum_kernel(const long long* __restrict__ keys, long long n, long long* __restrict__ seg_cnt, long long* __restrict__ seg_pos,
                    long long* __restrict__ seg_sum2) {
   __shared__ long long red[3][8];
-  const long long base = (long long)blockIdx.x * blockDim.x;
-  const long long i = base + threadIdx.x;
+  const long long base = (long long)blockIdx.x * (256 * AUC_ITEMS);
+  const long long last = (base + 256 * AUC_ITEMS <= n ? base + 256 * AUC_ITEMS : n) - 1;
+  const bool uniform = (keys[base] >> 33) == (keys[last] >> 33);      // base < n by the grid size
   long long cnt = 0, pos = 0, sum2 = 0;
-  int seg = -1;
-  if (i < n && keys[i] != AUC_REJECTED_KEY) {
+#pragma unroll 2
+  for (int it = 0; it < AUC_ITEMS; ++it) {
+    const long long i = base + it * 256 + threadIdx.x;
+    if (i >= n) break;
     const long long k = keys[i];
+    if (k == AUC_REJECTED_KEY) continue;
     const long long v = k >> 1;                     // (segment, value): the tie class
-    seg = (int)(k >> 33);
-    cnt = 1;
+    long long s2 = 0;
     if (k & 1) {
-      pos = 1;
       long long s = i, e = i + 1;                   // tie group [s, e)
-      if (i > 0 && (keys[i - 1] >> 1) == v) {       // lower bound of v in [0, i)
-        long long lo = 0, hi = i - 1;               // keys[hi] == v
+      // tie groups are short: gallop outwards from i (1, 2, 4 ... keys), then bisect the last bracket
+      if (i > 0 && (keys[i - 1] >> 1) == v) {
+        long long hi = i - 1, step = 1, below = -1;                 // keys[hi] == v; keys[below] < v (or below == -1)
+        for (;;) {
+          const long long probe = hi - step;
+          if (probe < 0) break;
+          if ((keys[probe] >> 1) == v) { hi = probe; step <<= 1; } else { below = probe; break; }
+        }
+        long long lo = below + 1;
         while (lo < hi) { const long long mid = (lo + hi) >> 1; if ((keys[mid] >> 1) < v) lo = mid + 1; else hi = mid; }
         s = lo;
       }
-      if (i + 1 < n && (keys[i + 1] >> 1) == v) {   // upper bound of v in (i, n)
-        long long lo = i + 1, hi = n;               // first index with value > v in [lo, hi]
-        while (lo < hi) { const long long mid = (lo + hi) >> 1; if ((keys[mid] >> 1) <= v) lo = mid + 1; else hi = mid; }
-        e = lo;
+      if (i + 1 < n && (keys[i + 1] >> 1) == v) {
+        long long lo = i + 1, step = 1, above = n;                  // keys[lo] == v; keys[above] > v (or above == n)
+        for (;;) {
+          const long long probe = lo + step;
+          if (probe >= n) break;
+          if ((keys[probe] >> 1) == v) { lo = probe; step <<= 1; } else { above = probe; break; }
+        }
+        long long a = lo + 1, b = above;                            // first index with a larger value lies in [a, b]
+        while (a < b) { const long long mid = (a + b) >> 1; if ((keys[mid] >> 1) <= v) a = mid + 1; else b = mid; }
+        e = a;
       }
-      sum2 = s + e + 1;
+      s2 = s + e + 1;
+    }
+    if (uniform) {
+      cnt += 1; pos += (k & 1); sum2 += s2;
+    } else {
+      const int seg = (int)(k >> 33);
+      atomic_add_i64(seg_cnt + seg, 1);
+      if (k & 1) { atomic_add_i64(seg_pos + seg, 1); atomic_add_i64(seg_sum2 + seg, s2); }
     }
   }
-  // CTA-uniform segment (the common case: segments are much longer than 256) -> one atomic triple per CTA
-  const long long last = (base + blockDim.x <= n ? base + blockDim.x : n) - 1;
-  const bool uniform = last >= base && (keys[base] >> 33) == (keys[last] >> 33);
-  if (uniform) {
+  if (uniform) {                                     // CTA-uniform branch
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       cnt += __shfl_xor_sync(0xffffffffu, cnt, o); pos += __shfl_xor_sync(0xffffffffu, pos, o); sum2 += __shfl_xor_sync(0xffffffffu, sum2, o);
@@ -238,9 +289,6 @@ auc_ranksum_kernel(const long long* __restrict__ keys, long long n, long long* _
       if (a) atomic_add_i64(seg_cnt + sg, a);        // a == 0: a CTA of rejected keys only
       if (b) { atomic_add_i64(seg_pos + sg, b); atomic_add_i64(seg_sum2 + sg, c); }
     }
-  } else if (seg >= 0) {
-    atomic_add_i64(seg_cnt + seg, 1);
-    if (pos) { atomic_add_i64(seg_pos + seg, 1); atomic_add_i64(seg_sum2 + seg, sum2); }
   }
 }
 
@@ -259,7 +307,7 @@ int auc_ranksum_impl(const ot_auc_params* p, cudaStream_t st) {
   if (!p || !p->keys || !p->seg_count || !p->seg_pos || !p->seg_sum2) OT_FAIL(OT_ERR_INVALID_ARG, "ot_auc_ranksum: null pointer");
   if (p->n < 0 || p->n > (1ll << 38)) OT_FAIL(OT_ERR_INVALID_ARG, "ot_auc_ranksum: n=%lld", (long long)p->n);
   if (p->n == 0) return OT_OK;
-  auc_ranksum_kernel<<<(unsigned)((p->n + 255) / 256), 256, 0, st>>>((const long long*)p->keys, p->n, (long long*)p->seg_count,
+  auc_ranksum_kernel<<<(unsigned)((p->n + 256 * AUC_ITEMS - 1) / (256 * AUC_ITEMS)), 256, 0, st>>>((const long long*)p->keys, p->n, (long long*)p->seg_count,
                                                                     (long long*)p->seg_pos, (long long*)p->seg_sum2);
   OT_CUDA_CHECK(cudaGetLastError());
   return OT_OK;
