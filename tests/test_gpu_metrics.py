@@ -102,3 +102,31 @@ def test_user_auc_matches_the_oracle():
     assert got == pytest.approx(M.user_auc(y[0], p[0], u, n_users), abs=1e-12)
     with pytest.raises(ValueError):
         GM.grouped_auc(torch.from_numpy(y[0]).cuda(), torch.from_numpy(p[0]).cuda(), torch.from_numpy(u).cuda(), 10)   # ids outside the range
+
+
+def test_kernels_reproduce_the_committed_golden_vectors():
+    """tests/golden/metrics_golden.json: integer targets (bucket histograms, confusion counts, twice the U statistic) bit-exact."""
+    import json, os
+    G = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'metrics_golden.json')))
+    for name, g in G.items():
+        p = torch.tensor(g['p'], dtype=torch.float32, device='cuda')
+        y = torch.tensor(g['y'], dtype=torch.float32, device='cuda')
+        u = torch.tensor(g['user'], dtype=torch.int32, device='cuda')
+        for nt in (200, 17):
+            m = GM.BinaryTaskMetrics(['t'], num_thresholds=nt)
+            m.update_state(y.reshape(1, -1), p.reshape(1, -1))
+            st = m.state.cpu().numpy()[0]
+            assert st[:nt].tolist() == g[f'pos_hist_{nt}'] and st[nt:2 * nt].tolist() == g[f'neg_hist_{nt}'], (name, nt)
+            res = m.result()
+            assert res['t_auc'] == pytest.approx(g[f'keras_auc_{nt}'], abs=2e-6)
+            c = m.counts()['t']
+            assert {k: c[k] for k in g['confusion']} == g['confusion']
+        assert res['t_accuracy'] == pytest.approx(g['accuracy'], abs=1e-12) and res['t_f1'] == pytest.approx(g['f1'], abs=5e-7)
+        assert res['t_logloss'] == pytest.approx(g['logloss'], rel=2e-6)
+        auc, cnt, pos = GM.grouped_auc(y, p)
+        P, n = int(pos[0]), int(cnt[0])
+        assert 2 * P * (n - P) == g['exact_auc_den'] and float(auc[0]) == g['exact_auc']
+        assert GM.user_auc(y, p, u, g['n_users']) == pytest.approx(g['user_auc'], abs=1e-12)
+        per = GM.grouped_auc(y, p, u, g['n_users'])[0].cpu().tolist()
+        for a, b in zip(per, g['per_user_auc']):
+            assert (b is None and a != a) or a == pytest.approx(b, abs=1e-12)

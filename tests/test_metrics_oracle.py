@@ -57,3 +57,25 @@ def test_user_auc_weights_by_impressions():
     # user 0: 1.0 (2 rows); user 1: 0.0 (2 rows); user 2: one class only, skipped; user 3: pos 0.3 vs neg .3 .2 .1 -> (0.5+1+1)/3 (4 rows)
     want = (1.0 * 2 + 0.0 * 2 + (2.5 / 3) * 4) / 8
     assert M.user_auc(y, p, u, 4) == pytest.approx(want, abs=1e-12)
+
+
+def test_oracle_reproduces_the_committed_golden_vectors():
+    """tests/golden/metrics_golden.json (script: tests/golden/make_metrics_golden.py) - a regression pin of the restatement."""
+    import json, os
+    G = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'metrics_golden.json')))
+    assert set(G) == {'smooth', 'ties', 'edges'}
+    for name, g in G.items():
+        p, y, u = np.array(g['p'], np.float32), np.array(g['y'], np.float32), np.array(g['user'])
+        assert [float(v) for v in p] == g['p']                                         # float32 values survive the JSON round trip
+        for nt in (200, 17):
+            pos, neg = M.keras_auc_state(y, p, nt)
+            assert pos.tolist() == g[f'pos_hist_{nt}'] and neg.tolist() == g[f'neg_hist_{nt}']
+            assert M.keras_auc_result(pos, neg) == g[f'keras_auc_{nt}']
+        assert M.confusion_counts(y, p) == g['confusion']
+        assert M.exact_auc(y, p) == g['exact_auc'] == g['exact_auc_u2'] / g['exact_auc_den']
+        assert M.user_auc(y, p, u, g['n_users']) == pytest.approx(g['user_auc'], abs=1e-15)
+        assert M.binary_crossentropy(y, p) == pytest.approx(g['logloss'], rel=1e-12)
+    e = G['edges']                                                                     # hand-checked entries of the edge case (NT = 17)
+    p = np.array(e['p'], np.float32)
+    b = np.maximum(np.ceil(p[:12] * np.float32(16)) - 1, 0).astype(int).tolist()
+    assert b == [0, 15, 7, 8, 0, 1, 0, 15, 14, 0, 3, 11]
