@@ -96,6 +96,27 @@ class BinaryTaskMetrics:
 
     reset_state = reset_states      # Keras >= 2.5 spelling
 
+    def all_reduce(self, group=None) -> None:
+        """Data-parallel evaluation: every rank streams its shard of the samples, then the states are summed over the ranks
+        (``merge_states_``) and every rank's ``result()`` is the metric of the whole dataset - exact, because the state is
+        counts (the reference evaluates on one device, OT/evaluate.py:58-129)."""
+        merge_states_(self.state, self.num_thresholds, group)
+
+
+def merge_states_(state: torch.Tensor, num_thresholds: int, group=None) -> torch.Tensor:
+    """Sum metric states ``[n_tasks, 2 * NT + 8]`` (int64) over the ranks of ``group``, in place.  Every word is an integer count
+    except word ``2 * NT + 6``, the BCE sum, whose int64 slot holds the bits of a double: it is reduced as float64."""
+    import torch.distributed as dist
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return state
+    k = 2 * num_thresholds + 6
+    bce = state[:, k].clone().view(torch.float64)
+    state[:, k] = 0
+    dist.all_reduce(state, op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(bce, op=dist.ReduceOp.SUM, group=group)
+    state[:, k] = bce.view(torch.int64)
+    return state
+
 
 class _SingleMetric:
     """Keras-style single metric over ``y_true`` / ``y_pred`` of any (equal) shape: a one-task ``BinaryTaskMetrics``."""

@@ -138,3 +138,51 @@ def test_sharded_candidate_scores_gather_in_order(tmp_path):
     for n in (7, 8, 1, 2):
         want = torch.arange(2 * n, dtype=torch.float32).reshape(2, n) * 0.5 + 1.0
         assert torch.equal(r[0][n], want) and torch.equal(r[1][n], want), n
+
+
+# ---- data-parallel evaluation: metric states are counts, so the sum over ranks is the state of the whole dataset ---------------
+def _metric_state(y, p, nt):
+    """What ot_metrics_update leaves in the state, written with the oracle (layout of include/onetrans_b200.h)."""
+    import numpy as np
+    from oracle import metrics_oracle as M
+    st = torch.zeros(2, 2 * nt + 8, dtype=torch.int64)
+    for t in range(2):
+        pos, neg = M.keras_auc_state(y[t], p[t], nt)
+        c = M.confusion_counts(y[t], p[t])
+        st[t, :nt], st[t, nt:2 * nt] = torch.from_numpy(pos), torch.from_numpy(neg)
+        st[t, 2 * nt:2 * nt + 5] = torch.tensor([c['tp'], c['fp'], c['tn'], c['fn'], c['count']])
+        st[t, 2 * nt + 6] = torch.tensor([M.binary_crossentropy(y[t], p[t]) * c['count']], dtype=torch.float64).view(torch.int64)[0]
+    return st
+
+
+def _worker_metrics(rank, world, port, out_dir):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    import numpy as np
+    from recommend_b200.metrics import merge_states_
+    rng = np.random.default_rng(0)                                   # the GLOBAL evaluation set, identical on every rank
+    p = rng.random((2, 1001)).astype(np.float32)
+    y = (rng.random((2, 1001)) < p).astype(np.float32)
+    s, e = (0, 400) if rank == 0 else (400, 1001)                    # uneven shards
+    st = _metric_state(y[:, s:e], p[:, s:e], 200)
+    merge_states_(st, 200)
+    torch.save(st, os.path.join(out_dir, f'metrics{rank}.pt'))
+    dist.destroy_process_group()
+
+
+def test_metric_states_sum_over_ranks_to_the_whole_dataset(tmp_path):
+    import numpy as np
+    world = 2
+    mp.spawn(_worker_metrics, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    rng = np.random.default_rng(0)
+    p = rng.random((2, 1001)).astype(np.float32)
+    y = (rng.random((2, 1001)) < p).astype(np.float32)
+    want = _metric_state(y, p, 200)
+    got = [torch.load(os.path.join(tmp_path, f'metrics{i}.pt')) for i in range(world)]
+    k = 2 * 200 + 6
+    for g in got:
+        ints = [c for c in range(g.shape[1]) if c != k]
+        assert torch.equal(g[:, ints], want[:, ints])                                     # every count exact
+        assert torch.allclose(g[:, k].clone().view(torch.float64), want[:, k].clone().view(torch.float64), rtol=1e-12)
+    assert torch.equal(got[0], got[1])
