@@ -121,7 +121,14 @@ def measured_peaks():
 # CPU arm: the oracle port timed on the host cores (cpu_baseline, and --impl reference)
 # ---------------------------------------------------------------------------------------------------
 
-def cpu_oracle_samples_per_sec(wl, sample_B: int, steps: int, warmup: int, dropout: float = 0.0):
+CPU_VARIANTS = {   # SURVEY.md §8d "CPU baseline beside it": the three structures of the same arithmetic
+    'tail_only': dict(query_mode='tail_only', literal_loop=False),            # fair: same algorithmic FLOPs as the GPU path (D3)
+    'literal_gather': dict(query_mode='literal_gather', literal_loop=False),  # reference FLOP structure: every query, then gather (OT/model.py:366-371)
+    'literal_loop': dict(query_mode='literal_gather', literal_loop=True),     # reference dispatch structure: one tiny matmul per position (:84-88, 154-161)
+}
+
+
+def cpu_oracle_samples_per_sec(wl, sample_B: int, steps: int, warmup: int, dropout: float = 0.0, variant: str = 'tail_only'):
     from oracle import onetrans_oracle as O
     torch.set_num_threads(os.cpu_count() or 1)
     ocfg = O.small_config(num_ns_tokens=wl['L_ns']) if wl['model'] == 'small' else O.default_config(num_ns_tokens=wl['L_ns'])
@@ -133,7 +140,7 @@ def cpu_oracle_samples_per_sec(wl, sample_B: int, steps: int, warmup: int, dropo
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        O.loss_and_grads(P, ocfg, non_seq, seq, labels, training=dropout > 0, gen=torch.Generator().manual_seed(i))
+        O.loss_and_grads(P, ocfg, non_seq, seq, labels, training=dropout > 0, gen=torch.Generator().manual_seed(i), **CPU_VARIANTS[variant])
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
@@ -154,7 +161,7 @@ def run_reference_arm(args, wl, rank):
     if rank != 0:
         return
     sample_B = args.cpu_sample_batch
-    v, ms, cores = cpu_oracle_samples_per_sec(wl, sample_B, max(1, args.steps), max(0, args.warmup), args.dropout)
+    v, ms, cores = cpu_oracle_samples_per_sec(wl, sample_B, max(1, args.steps), max(0, args.warmup), args.dropout, args.cpu_variant)
     line = {
         'impl': 'reference', 'metric': 'OneTrans samples/sec (fwd+bwd bf16)', 'value': v, 'unit': 'samples/s', 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak',
@@ -162,7 +169,7 @@ def run_reference_arm(args, wl, rank):
         'config': config_dict(args, wl, wl['B']),      # the GPU arm's workload; each CPU step is a bounded sample of it (cpu_baseline.sample)
         'cpu_baseline': {'value': v, 'unit': 'samples/s', 'cores': cores, 'kind': 'port',
                          'sample': f'oracle (PyTorch CPU fp32 restatement of OT/model.py; TensorFlow reference not installable) fwd+BCE+bwd on {sample_B} '
-                                   f'samples of the same workload per step'},
+                                   f'samples of the same workload per step; structure: {args.cpu_variant}'},
         'e2e': {'value': v, 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
     print(json.dumps(line), flush=True)
@@ -192,6 +199,8 @@ def main():
     ap.add_argument('--workload', default='c2')
     ap.add_argument('--batch', type=int, default=0, help='override per-GPU batch')
     ap.add_argument('--cpu-sample-batch', type=int, default=32, help='samples per CPU-oracle step (cpu_baseline and --impl reference)')
+    ap.add_argument('--cpu-variant', default='tail_only', choices=sorted(CPU_VARIANTS), help='--impl reference: tail_only (same FLOPs as the GPU path), '
+                    'literal_gather (every query, then gather: the reference FLOP structure) or literal_loop (one matmul per position: its dispatch structure)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-kernel-profile', action='store_true')
     ap.add_argument('--dropout', type=float, default=0.1, help='training dropout rate (OT/config.py:50 default 0.1)')
