@@ -289,3 +289,21 @@ def test_evaluator_percentile_is_numpy_linear():
     xs = [0.3, 0.1, 0.9, 0.5, 0.7, 0.2]
     for q in (0, 50, 95, 99, 100):
         assert _percentile(xs, q) == pytest.approx(float(np.percentile(xs, q)))
+
+
+def test_unsupported_head_dims_are_errors_before_any_device_work():
+    """Argument validation of the attention entry points returns before the first CUDA call, so it runs without a GPU: head_dim 32
+    is built but unverified on hardware and stays an unsupported-shape error unless OT_ENABLE_HEAD_DIM_32=1."""
+    if os.environ.get('OT_ENABLE_HEAD_DIM_32') == '1':
+        pytest.skip('head_dim 32 enabled in this environment')
+    lib = _lib.load()
+    p = _lib.AttnParams()
+    for f in ('q', 'k', 'v', 'o', 'lse', 'd_o', 'dq', 'dk', 'dv', 'delta'):
+        setattr(p, f, 4096)                                  # never dereferenced: the shape check comes first
+    p.ldq = p.ldk = p.ldv = p.ldo = p.lddo = p.lddq = p.lddk = p.lddv = 128
+    p.B, p.H, p.Lq, p.Lk = 2, 4, 4, 4
+    for hd in (32, 48, 128):
+        p.head_dim = hd
+        for fn in (lib.ot_attn_fwd, lib.ot_attn_bwd):
+            assert fn(ctypes.byref(p), None) == -2           # OT_ERR_UNSUPPORTED_SHAPE, never a fallback
+            assert f'head_dim={hd}' in lib.ot_last_error_string().decode()
