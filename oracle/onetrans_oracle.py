@@ -11,11 +11,19 @@ repairs of SURVEY.md §A.3 where the reference as written cannot run (D2 pyramid
 alignment, D5 python ints, D6 KV cache, D9 float cast).  Every function cites the reference lines it
 follows.
 
-PARITY UNPINNED: the reference ships no tests, golden vectors or seeds and cannot be
-imported here (TensorFlow 2.12 is absent, F2), so this oracle is pinned only by (i) the line-by-line
-citations below, (ii) the algebraic invariants in tests/ (tail-only == compute-all-then-gather,
-grouped == per-token loop, causality, hand-computed RMSNorm/BCE vectors), and (iii) golden vectors that
-this file itself generated (tests/golden/, script tests/golden/make_golden.py).
+PARITY PIN: the reference ships no tests, golden vectors or seeds and its arithmetic lives in TensorFlow 2.12,
+which is absent here (F2).  The oracle is pinned by golden vectors produced by the reference's OWN code: tests/golden/
+make_reference_golden.py imports OT/config.py, OT/model.py and OT/data_loader.py UNMODIFIED from /root/reference, with
+oracle/tf_shim.py standing in for the ~30 TensorFlow ops they call, runs ``OneTransModel.call`` (pyramid off, 2 blocks; pyramid on,
+1 block; a missing sequence), ``OneTransBlock.call`` with its returned (k, v), ``PyramidScheduler.get_layer_config``,
+``SequenceProcessor.process_sequence`` and the config classes, and commits inputs, every weight and the outputs
+(tests/golden/reference_golden.{npz,json}).  tests/test_reference_golden.py holds this oracle to them at 1e-12 (fp64) in its literal
+modes (``ns_param_alignment='head_literal'``, ``query_mode='literal_gather'``, per-token loop) - so the control flow that decides
+results is the reference's, executed; only what each TensorFlow op computes is restated (in the shim, from the documented TF 2.12
+semantics of SURVEY.md §A.2).  The same run reproduces defects D2 and D9 as the exceptions the reference raises.  The repaired
+modes the product uses are tied to the literal ones by the algebraic invariants in tests/test_oracle.py (T4 tail-only ==
+compute-all-then-gather, T5 grouped == per-token loop, T6 causality, hand-computed RMSNorm / BCE vectors) and by the golden vectors
+this file generated itself (tests/golden/oracle_golden.json, script tests/golden/make_golden.py).
 """
 from __future__ import annotations
 

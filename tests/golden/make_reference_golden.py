@@ -1,0 +1,232 @@
+"""Golden vectors from the REFERENCE ITSELF: imports /root/reference/rank/scaling_up/oneTrans/practice/{config,model}.py unmodified,
+with ``oracle/tf_shim.py`` standing in for the TensorFlow ops they call, runs the reference's own classes and writes
+``tests/golden/reference_golden.npz`` (+ ``reference_golden.json`` for the integer / configuration facts).
+
+    python -m tests.golden.make_reference_golden          # in the build container, where /root/reference exists
+
+What runs as written (and is recorded):
+  * ``OneTransConfig`` / ``OneTransSmallConfig`` / ``OneTransLargeConfig`` / ``get_model_config`` defaults (pure Python);
+  * ``PyramidScheduler.get_layer_config`` for a sweep of lengths (pure Python, OT/model.py:287-302);
+  * case A - ``OneTransModel.call`` with the pyramid off, 2 blocks: tokenizer -> blocks -> output norm -> heads (OT/model.py:335-393);
+  * case B - ``OneTransModel.call`` with the pyramid ON and ONE block: the literal compute-every-query-then-gather path (:356-371);
+  * case C - ``OneTransBlock`` alone on a random input, training=False, and its returned (k, v);
+  * ``SequenceProcessor.process_sequence`` of OT/data_loader.py:68-101 (numpy: keep the newest events, pad in front) on an empty, a
+    short and a long sequence;
+  * the per-position weight rule as the code applies it (``_get_projection_weights``: position < num_ns_tokens -> dedicated), i.e. the
+    literal 'head' alignment of SURVEY.md D4 - the oracle's ``ns_param_alignment='head_literal'`` mode is what these vectors pin.
+What does NOT run as written (recorded as the exception the reference raises - SURVEY.md §A.3):
+  * D2 - pyramid on with two blocks: layer 1 gathers indices of the ORIGINAL length from the already shortened sequence;
+  * D9 - integer ids next to float features in ``tf.concat``.
+Every parameter of the reference model is exported under the oracle's names so that the oracle can be run on identical weights."""
+import importlib
+import json
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+from oracle import tf_shim
+
+REF = '/root/reference/rank/scaling_up/oneTrans/practice'
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def import_reference():
+    tf_shim.install()
+    pkg = types.ModuleType('ot_ref')
+    pkg.__path__ = [REF]                      # a package without running the reference's __init__ (it imports pandas / matplotlib users)
+    sys.modules['ot_ref'] = pkg
+    return importlib.import_module('ot_ref.config'), importlib.import_module('ot_ref.model')
+
+
+def export_params(model, cfg):
+    """Reference model -> the oracle's parameter names (packed: index 0 shared, 1 + j dedicated j)."""
+    P = {}
+    tok = model.tokenizer
+    P['tokenizer.ns_tokenizer.kernel'] = tok.ns_tokenizer.layers[0].kernel
+    P['tokenizer.ns_tokenizer.bias'] = tok.ns_tokenizer.layers[0].bias
+    for i, dense in enumerate(tok.seq_projections):
+        if dense.kernel is not None:          # a projection whose sequence never appeared is never built (lazy Keras build)
+            P[f'tokenizer.seq_projections.{i}.kernel'], P[f'tokenizer.seq_projections.{i}.bias'] = dense.kernel, dense.bias
+    P['tokenizer.sep_embedding'] = tok.sep_embedding.embeddings
+    for l, blk in enumerate(model.blocks):
+        P.update(export_block(blk, f'blocks.{l}.'))
+    P['output_norm.scale'] = model.output_norm.scale
+    for t, head in model.task_heads.items():
+        for i, dense in enumerate(head.layers):
+            P[f'task_heads.{t}.{i}.kernel'], P[f'task_heads.{t}.{i}.bias'] = dense.kernel, dense.bias
+    return P
+
+
+def export_block(blk, b):
+    att, ffn = blk.attention, blk.ffn
+    d = att.hidden_dim
+
+    def stack(shared, dedicated, attr, shape):
+        # positions the run never reached leave their Dense unbuilt: zeros there (the oracle never reads them either)
+        return torch.stack([getattr(m, attr) if getattr(m, attr) is not None else torch.zeros(shape, dtype=tf_shim.FLOAT) for m in [shared] + list(dedicated)])
+    P = {b + 'norm1.scale': blk.norm1.scale, b + 'norm2.scale': blk.norm2.scale, b + 'attention.Wo': att.Wo.kernel}
+    P[b + 'attention.Wq'] = stack(att.Wq_shared, att.Wq_dedicated, 'kernel', (d, d))
+    P[b + 'attention.Wk'] = stack(att.Wk_shared, att.Wk_dedicated, 'kernel', (d, d))
+    P[b + 'attention.Wv'] = stack(att.Wv_shared, att.Wv_dedicated, 'kernel', (d, d))
+    F = ffn.ffn_dim
+    first = lambda seq: seq.layers[0]
+    second = lambda seq: seq.layers[1]
+    P[b + 'ffn.W1'] = stack(first(ffn.ffn_shared), [first(s) for s in ffn.ffn_dedicated], 'kernel', (d, F))
+    P[b + 'ffn.b1'] = stack(first(ffn.ffn_shared), [first(s) for s in ffn.ffn_dedicated], 'bias', (F,))
+    P[b + 'ffn.W2'] = stack(second(ffn.ffn_shared), [second(s) for s in ffn.ffn_dedicated], 'kernel', (F, d))
+    P[b + 'ffn.b2'] = stack(second(ffn.ffn_shared), [second(s) for s in ffn.ffn_dedicated], 'bias', (d,))
+    return P
+
+
+def perturb(root, seed):
+    """Biases and norm gains of the LIVE reference layers away from their zero / one initial values (in place, before the export), so
+    that the vectors exercise them.  Walks the layer tree the way it was built: attributes, lists, dicts."""
+    g = torch.Generator().manual_seed(seed)
+    seen = set()
+
+    def visit(obj):
+        if id(obj) in seen:
+            return
+        seen.add(id(obj))
+        if isinstance(obj, tf_shim.Dense):
+            if obj.bias is not None:
+                obj.bias.copy_((torch.rand(obj.bias.shape, generator=g, dtype=obj.bias.dtype) * 2 - 1) * 0.1)
+        elif isinstance(obj, tf_shim.Layer):
+            if isinstance(getattr(obj, 'scale', None), torch.Tensor):           # RMSNorm (OT/model.py:14-17)
+                obj.scale.copy_(1.0 + (torch.rand(obj.scale.shape, generator=g, dtype=obj.scale.dtype) * 2 - 1) * 0.1)
+            for v in vars(obj).values():
+                visit(v)
+        elif isinstance(obj, (list, tuple)):
+            for v in obj:
+                visit(v)
+        elif isinstance(obj, dict):
+            for v in obj.values():
+                visit(v)
+    visit(root)
+
+
+def small_config(C, num_layers, pyramid):
+    cfg = C.OneTransConfig()
+    cfg.hidden_dim, cfg.num_heads, cfg.ffn_dim, cfg.num_layers, cfg.num_ns_tokens = 16, 4, 24, num_layers, 3
+    cfg.pyramid_enabled, cfg.dropout_rate = pyramid, 0.1
+    return cfg
+
+
+def inputs(cfg, B, seq_lens, seed, present=None):
+    g = torch.Generator().manual_seed(seed)
+    fc = cfg.feature_config
+    names = fc['user_features'] + fc['item_features'] + fc['context_features']
+    non_seq = {n: torch.randn(B, 1, generator=g, dtype=tf_shim.FLOAT) for n in names}
+    seq = {n: torch.randn(B, L, 64, generator=g, dtype=tf_shim.FLOAT) for n, L in zip(fc['sequence_features'], seq_lens)
+           if present is None or n in present}
+    return non_seq, seq
+
+
+def run_model_case(C, M, name, num_layers, pyramid, seq_lens, seed, present=None):
+    cfg = small_config(C, num_layers, pyramid)
+    tf_shim.set_seed(seed)
+    model = M.OneTransModel(cfg)
+    non_seq, seq = inputs(cfg, 3, seq_lens, seed + 100, present)
+    model(non_seq, seq, training=False)                       # builds every weight the run touches
+    perturb(model, seed + 200)
+    P = export_params(model, cfg)
+    model.reset_kv_cache()
+    tokens = model.tokenizer(non_seq, seq)
+    out = model(non_seq, seq, training=False, use_kv_cache=False)
+    arrays = {f'{name}/in/non_seq/{k}': v for k, v in non_seq.items()}
+    arrays.update({f'{name}/in/seq/{k}': v for k, v in seq.items()})
+    arrays.update({f'{name}/param/{k}': v for k, v in P.items()})
+    arrays[f'{name}/out/tokens'] = tokens
+    for t, v in out.items():
+        arrays[f'{name}/out/prob/{t}'] = v
+    meta = {'hidden_dim': cfg.hidden_dim, 'num_heads': cfg.num_heads, 'ffn_dim': cfg.ffn_dim, 'num_layers': cfg.num_layers,
+            'num_ns_tokens': cfg.num_ns_tokens, 'pyramid_enabled': cfg.pyramid_enabled, 'pyramid_ratios': list(cfg.pyramid_ratios),
+            'seq_lens': list(seq_lens), 'present': sorted(seq), 'total_len': int(tokens.shape[1]),
+            'total_parameters': int(model.get_model_info()['total_parameters']),
+            'kv_cache_len_after_call': int(model.kv_cache[0].shape[1])}
+    return arrays, meta
+
+
+def run_block_case(C, M, seed):
+    cfg = small_config(C, 1, False)
+    tf_shim.set_seed(seed)
+    blk = M.OneTransBlock(cfg)
+    g = torch.Generator().manual_seed(seed + 1)
+    x = torch.randn(2, 9, cfg.hidden_dim, generator=g, dtype=tf_shim.FLOAT)
+    blk(x, training=False)
+    perturb(blk, seed + 2)
+    P = export_block(blk, 'blocks.0.')
+    y, (k, v) = blk(x, training=False)
+    arrays = {'block/in/x': x, 'block/out/y': y, 'block/out/k': k, 'block/out/v': v}
+    arrays.update({f'block/param/{n}': t for n, t in P.items()})
+    return arrays, {'seq_len': 9, 'num_ns_tokens': cfg.num_ns_tokens}
+
+
+def expected_failure(fn):
+    try:
+        fn()
+    except Exception as e:            # noqa: BLE001 - the point is to record what the reference raises
+        return f'{type(e).__name__}: {e}'
+    return None
+
+
+def main():
+    C, M = import_reference()
+    facts = {'config': {}, 'scheduler': {}, 'cases': {}, 'defects': {}}
+    for name in ('small', 'default', 'large'):
+        cfg = C.get_model_config(name)
+        facts['config'][name] = {k: v for k, v in cfg.to_dict().items() if isinstance(v, (int, float, str, bool, list, dict))}
+    sched = M.PyramidScheduler(C.OneTransConfig())
+    for L0 in (1, 2, 7, 21, 100, 272, 544, 1202, 2048):
+        facts['scheduler'][str(L0)] = [sched.get_layer_config(l, L0).get('keep_len') for l in range(9)]
+    lc = sched.get_layer_config(0, 21)
+    facts['scheduler']['query_indices_layer0_len21'] = lc['query_indices']
+    arrays = {}
+    for name, kw in {'A_pyramid_off_2_blocks': dict(num_layers=2, pyramid=False, seq_lens=(5, 4, 3), seed=1),
+                     'B_pyramid_on_1_block': dict(num_layers=1, pyramid=True, seq_lens=(6, 3, 4), seed=2),
+                     'D_missing_sequence': dict(num_layers=1, pyramid=False, seq_lens=(4, 5, 3), seed=4, present=('click_seq', 'purchase_seq'))}.items():
+        a, meta = run_model_case(C, M, name, **kw)
+        arrays.update(a)
+        facts['cases'][name] = meta
+    a, meta = run_block_case(C, M, 3)
+    arrays.update(a)
+    facts['cases']['block'] = meta
+
+    # OT/data_loader.py:68-101, the reference's numpy code
+    DL = importlib.import_module('ot_ref.data_loader')
+    dcfg = C.OneTransConfig()
+    dcfg.max_seq_len = 6
+    sp = DL.SequenceProcessor(dcfg)
+    g = torch.Generator().manual_seed(7)
+    for tag, n in (('empty', 0), ('short', 4), ('exact', 6), ('long', 11)):
+        raw = torch.randn(n, 64, generator=g, dtype=torch.float64).numpy()
+        arrays[f'seqproc/{tag}/in'] = torch.from_numpy(raw)
+        arrays[f'seqproc/{tag}/out'] = torch.from_numpy(np.asarray(sp.process_sequence(raw, 'click_seq'), dtype=np.float64))
+    facts['cases']['seqproc'] = {'max_seq_len': 6}
+
+    # the defects of SURVEY.md §A.3 that the shimmed reference reproduces
+    def d2():
+        cfg = small_config(C, 2, True)
+        non_seq, seq = inputs(cfg, 2, (6, 3, 4), 9)
+        M.OneTransModel(cfg)(non_seq, seq, training=False)
+    facts['defects']['D2_pyramid_on_two_blocks'] = expected_failure(d2)
+
+    def d9():
+        cfg = small_config(C, 1, False)
+        non_seq, seq = inputs(cfg, 2, (6, 3, 4), 9)
+        non_seq['user_id'] = torch.randint(0, 100, (2, 1))
+        M.OneTransModel(cfg)(non_seq, seq, training=False)
+    facts['defects']['D9_integer_ids_in_concat'] = expected_failure(d9)
+
+    np.savez_compressed(os.path.join(HERE, 'reference_golden.npz'), **{k: v.detach().numpy() for k, v in arrays.items()})
+    with open(os.path.join(HERE, 'reference_golden.json'), 'w') as f:
+        json.dump(facts, f, indent=1, sort_keys=True)
+    print('wrote reference_golden.npz', os.path.getsize(os.path.join(HERE, 'reference_golden.npz')), 'bytes;', len(arrays), 'arrays')
+    print('defects reproduced:', json.dumps(facts['defects'], indent=1))
+
+
+if __name__ == '__main__':
+    main()

@@ -1,5 +1,6 @@
 """CPU tests of the oracle (oracle/onetrans_oracle.py): the KATs of SURVEY.md §4.3 that pin it, since the
-reference ships no tests or golden vectors of its own (parity unpinned)."""
+reference ships no tests or golden vectors of its own; tests/test_reference_golden.py adds vectors produced by executing
+the reference's own model code over a TensorFlow-op shim."""
 import json
 import math
 import os

@@ -1,0 +1,108 @@
+"""The oracle against vectors produced by the REFERENCE'S OWN CODE: tests/golden/reference_golden.{npz,json} come from
+/root/reference/rank/scaling_up/oneTrans/practice/{config,model}.py, imported unmodified and executed over a shim of the TensorFlow
+ops they call (oracle/tf_shim.py; generator tests/golden/make_reference_golden.py).  The control flow that decides results - weight
+selection per position, concat orders, mask, [SEP] placement, pyramid indices and gathers, last-token heads - is the reference's.
+
+The reference applies dedicated weights to positions < num_ns_tokens (OT/model.py:69-74, 155-157): the oracle's literal mode
+``ns_param_alignment='head_literal'`` + ``query_mode='literal_gather'`` is the one compared; the repaired modes the product uses are
+tied to it by T4 / T5 in tests/test_oracle.py (tail-only == compute-all-then-gather, grouped == per-token loop)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import onetrans_oracle as O
+import recommend_b200 as R
+
+HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+Z = np.load(os.path.join(HERE, 'reference_golden.npz'))
+FACTS = json.load(open(os.path.join(HERE, 'reference_golden.json')))
+
+
+def _group(prefix):
+    return {k[len(prefix):]: torch.from_numpy(Z[k]) for k in Z.files if k.startswith(prefix)}
+
+
+def _oracle_cfg(meta, literal=True):
+    cfg = O.OracleConfig(hidden_dim=meta['hidden_dim'], num_layers=meta['num_layers'], num_heads=meta['num_heads'], ffn_dim=meta['ffn_dim'],
+                         num_ns_tokens=meta['num_ns_tokens'], pyramid_enabled=meta['pyramid_enabled'], pyramid_ratios=meta['pyramid_ratios'],
+                         ns_param_alignment='head_literal', dropout_rate=0.1)
+    return cfg
+
+
+@pytest.mark.parametrize('case', ['A_pyramid_off_2_blocks', 'B_pyramid_on_1_block', 'D_missing_sequence'])
+def test_oracle_equals_the_reference_model_call(case):
+    meta = FACTS['cases'][case]
+    cfg = _oracle_cfg(meta)
+    P, non_seq, seq = _group(f'{case}/param/'), _group(f'{case}/in/non_seq/'), _group(f'{case}/in/seq/')
+    assert sorted(seq) == meta['present']
+    tokens = O.tokenizer_forward(P, cfg, non_seq, seq)
+    want_tokens = torch.from_numpy(Z[f'{case}/out/tokens'])
+    assert tokens.shape == want_tokens.shape and tokens.shape[1] == meta['total_len']
+    assert torch.allclose(tokens, want_tokens, rtol=0, atol=1e-13)                        # layout + projections: S first, [SEP]s, NS last
+    for mode, loop in (('literal_gather', True), ('literal_gather', False), ('tail_only', False)):
+        out = O.model_forward(P, cfg, non_seq, seq, training=False, query_mode=mode, literal_loop=loop)
+        for t in cfg.tasks:
+            want = torch.from_numpy(Z[f'{case}/out/prob/{t}'])
+            assert out[t].shape == want.shape == (3, 1)
+            assert torch.allclose(out[t], want, rtol=0, atol=1e-12), (case, mode, loop, float((out[t] - want).abs().max()))
+    # every parameter the run touched, counted the way get_model_info does (OT/model.py:399-408)
+    touched = sum(int(np.count_nonzero(Z[k]) > 0) * Z[k].size for k in Z.files if k.startswith(f'{case}/param/'))
+    assert touched <= meta['total_parameters']
+
+
+def test_oracle_equals_the_reference_block_and_its_kv():
+    meta = FACTS['cases']['block']
+    cfg = O.OracleConfig(hidden_dim=16, num_layers=1, num_heads=4, ffn_dim=24, num_ns_tokens=meta['num_ns_tokens'], ns_param_alignment='head_literal')
+    P = _group('block/param/')
+    x = torch.from_numpy(Z['block/in/x'])
+    y = O.block_forward(P, 0, cfg, x, keep=meta['seq_len'], query_mode='literal_gather', literal_loop=True)
+    assert torch.allclose(y, torch.from_numpy(Z['block/out/y']), rtol=0, atol=1e-13)
+    xn = O.rmsnorm(x, P['blocks.0.norm1.scale'])
+    _, (k, v) = O.mixed_mha(P, 'blocks.0.attention.', cfg, xn, meta['seq_len'], return_kv=True)
+    B, L = x.shape[:2]
+    assert torch.allclose(k.reshape(B, L, -1), torch.from_numpy(Z['block/out/k']).reshape(B, L, -1), rtol=0, atol=1e-13)   # (k, v) as MixedMHA returns them
+    assert torch.allclose(v.reshape(B, L, -1), torch.from_numpy(Z['block/out/v']).reshape(B, L, -1), rtol=0, atol=1e-13)
+
+
+def test_scheduler_and_config_facts_of_the_reference():
+    ratios = FACTS['config']['default']['pyramid_ratios']
+    for L0, keeps in FACTS['scheduler'].items():
+        if not L0.isdigit():
+            continue
+        for l, k in enumerate(keeps):                                # None past the ratio list (OT/model.py:289-290)
+            assert O.reference_keep_len(l, int(L0), ratios) == k
+            got = R.PyramidScheduler(R.OneTransConfig()).get_layer_config(l, int(L0))
+            assert got.get('keep_len') == k
+    assert FACTS['scheduler']['query_indices_layer0_len21'] == O.reference_query_indices(0, 21, ratios) == list(range(11, 21))
+    for name, ref in FACTS['config'].items():                        # the attribute bag of OT/config.py, value by value
+        mine = R.get_model_config(name).to_dict()
+        for key, value in ref.items():
+            assert key in mine and mine[key] == value, (name, key, mine.get(key), value)
+
+
+def test_defects_the_reference_shows_when_executed():
+    """SURVEY.md §A.3 D2 and D9, observed by running the reference (the repairs the oracle and the product adopt start here)."""
+    assert 'is not in [0,' in FACTS['defects']['D2_pyramid_on_two_blocks']          # layer 1 gathers original-length indices
+    assert 'different dtypes' in FACTS['defects']['D9_integer_ids_in_concat']       # int ids next to float features
+    # after a call the model holds the LAST block's (k, v) as its "cache" (OT/model.py:366-368) - per-layer caching needs D6
+    assert FACTS['cases']['A_pyramid_off_2_blocks']['kv_cache_len_after_call'] == FACTS['cases']['A_pyramid_off_2_blocks']['total_len']
+
+
+def test_sequence_processor_equals_the_reference_numpy_code():
+    """OT/data_loader.py:68-101 executed (numpy): newest ``max_seq_len`` events kept, shorter sequences padded IN FRONT, an empty one
+    becomes all zeros - against ``recommend_b200.data.SequenceProcessor`` and the serving wrapper's ``preprocess_input``."""
+    cfg = R.OneTransConfig()
+    cfg.max_seq_len = FACTS['cases']['seqproc']['max_seq_len']
+    sp = R.SequenceProcessor(cfg)
+    eng = R.OneTransInferenceEngine.__new__(R.OneTransInferenceEngine)       # preprocess_input only needs the config
+    eng.config, eng.pad_sequences = cfg, True
+    for tag in ('empty', 'short', 'exact', 'long'):
+        raw, want = torch.from_numpy(Z[f'seqproc/{tag}/in']), torch.from_numpy(Z[f'seqproc/{tag}/out'])
+        got = sp.process_sequence(raw)
+        assert got.shape == want.shape == (cfg.max_seq_len, 64) and torch.equal(got.double(), want.float().double()), tag
+        if raw.shape[0]:
+            _, seq = eng.preprocess_input({}, {}, {}, {'click_seq': raw})
+            assert torch.equal(seq['click_seq'].double(), want.float().double()), tag
