@@ -81,6 +81,61 @@ def export_block(blk, b):
     return P
 
 
+def assign_params(model, P):
+    """The inverse of ``export_params``: copy an oracle-named parameter dict into the LIVE tensors of a built reference model."""
+    def put(dst, src):
+        if dst is not None:
+            dst.copy_(src.to(dst.dtype).reshape(dst.shape))
+    tok = model.tokenizer
+    put(tok.ns_tokenizer.layers[0].kernel, P['tokenizer.ns_tokenizer.kernel'])
+    put(tok.ns_tokenizer.layers[0].bias, P['tokenizer.ns_tokenizer.bias'])
+    for i, dense in enumerate(tok.seq_projections):
+        put(dense.kernel, P[f'tokenizer.seq_projections.{i}.kernel'])
+        put(dense.bias, P[f'tokenizer.seq_projections.{i}.bias'])
+    put(tok.sep_embedding.embeddings, P['tokenizer.sep_embedding'])
+    for l, blk in enumerate(model.blocks):
+        b = f'blocks.{l}.'
+        att, ffn = blk.attention, blk.ffn
+        put(blk.norm1.scale, P[b + 'norm1.scale'])
+        put(blk.norm2.scale, P[b + 'norm2.scale'])
+        put(att.Wo.kernel, P[b + 'attention.Wo'])
+        for name, shared, dedicated in (('Wq', att.Wq_shared, att.Wq_dedicated), ('Wk', att.Wk_shared, att.Wk_dedicated), ('Wv', att.Wv_shared, att.Wv_dedicated)):
+            for g, dense in enumerate([shared] + list(dedicated)):
+                put(dense.kernel, P[b + 'attention.' + name][g])
+        for g, seq in enumerate([ffn.ffn_shared] + list(ffn.ffn_dedicated)):
+            put(seq.layers[0].kernel, P[b + 'ffn.W1'][g])
+            put(seq.layers[0].bias, P[b + 'ffn.b1'][g])
+            put(seq.layers[1].kernel, P[b + 'ffn.W2'][g])
+            put(seq.layers[1].bias, P[b + 'ffn.b2'][g])
+    put(model.output_norm.scale, P['output_norm.scale'])
+    for t, head in model.task_heads.items():
+        for i, dense in enumerate(head.layers):
+            put(dense.kernel, P[f'task_heads.{t}.{i}.kernel'])
+            put(dense.bias, P[f'task_heads.{t}.{i}.bias'])
+
+
+def run_kernel_shape_case(C, M, name, spec):
+    """A case at a shape the sm_100a kernels support (d 256, head_dim 64), for the DIRECT product-vs-reference test on the GPU
+    (tests/test_gpu_model.py::test_product_equals_the_reference_outputs).  Weights and inputs are not stored: both sides rebuild them
+    with the recipe of tests/helpers.reference_case_inputs (oracle init_params seed + bf16 rounding, synthetic_batch seed); only the
+    reference's outputs and a checksum of what went in are committed."""
+    from tests.helpers import reference_case_inputs
+    ocfg, P, non_seq, seq = reference_case_inputs(spec)
+    cfg = C.OneTransConfig()
+    cfg.hidden_dim, cfg.num_heads, cfg.ffn_dim, cfg.num_layers, cfg.num_ns_tokens = spec['hidden_dim'], spec['num_heads'], spec['ffn_dim'], spec['num_layers'], spec['num_ns_tokens']
+    cfg.pyramid_enabled = spec['pyramid_enabled']
+    tf_shim.set_seed(0)
+    model = M.OneTransModel(cfg)
+    f64 = lambda d: {k: v.to(tf_shim.FLOAT) for k, v in d.items()}
+    model(f64(non_seq), f64(seq), training=False)            # builds the weights
+    assign_params(model, P)
+    model.reset_kv_cache()
+    out = model(f64(non_seq), f64(seq), training=False)
+    arrays = {f'{name}/out/prob/{t}': v for t, v in out.items()}
+    checksum = float(sum(v.double().sum() for v in P.values()) + sum(v.double().sum() for v in non_seq.values()) + sum(v.double().sum() for v in seq.values()))
+    return arrays, dict(spec, checksum=checksum, total_len=int(model.tokenizer(f64(non_seq), f64(seq)).shape[1]))
+
+
 def perturb(root, seed):
     """Biases and norm gains of the LIVE reference layers away from their zero / one initial values (in place, before the export), so
     that the vectors exercise them.  Walks the layer tree the way it was built: attributes, lists, dicts."""
@@ -194,6 +249,12 @@ def main():
     a, meta = run_block_case(C, M, 3)
     arrays.update(a)
     facts['cases']['block'] = meta
+
+    from tests.helpers import REFERENCE_KERNEL_CASES
+    for name, spec in REFERENCE_KERNEL_CASES.items():
+        a, meta = run_kernel_shape_case(C, M, name, spec)
+        arrays.update(a)
+        facts['cases'][name] = meta
 
     # OT/data_loader.py:68-101, the reference's numpy code
     DL = importlib.import_module('ot_ref.data_loader')

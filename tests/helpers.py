@@ -45,3 +45,33 @@ def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
 def rel_l2(a: torch.Tensor, b: torch.Tensor) -> float:
     a, b = a.double().cpu().flatten(), b.double().cpu().flatten()
     return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+# ---- cases at kernel-supported shapes whose EXPECTED outputs come from the reference's own code (tests/golden/make_reference_golden.py) ----
+REFERENCE_KERNEL_CASES = {
+    'G_d256_pyramid_on_1_block': dict(hidden_dim=256, num_heads=4, ffn_dim=256, num_layers=1, num_ns_tokens=2, pyramid_enabled=True,
+                                      B=64, seq_lens=(10, 5, 7), seed=21),
+    'H_d256_pyramid_off_2_blocks': dict(hidden_dim=256, num_heads=4, ffn_dim=256, num_layers=2, num_ns_tokens=2, pyramid_enabled=False,
+                                        B=64, seq_lens=(9, 6, 4), seed=22),
+}
+
+
+def reference_case_inputs(spec):
+    """Weights and inputs of a REFERENCE_KERNEL_CASES entry, rebuilt from seeds (nothing but the reference's outputs is stored):
+    oracle ``init_params`` + ``randomize_small_params`` with the GEMM weights rounded to bf16-representable values, ``synthetic_batch``
+    with bf16-representable events.  ``head_literal`` alignment: the reference gives dedicated weights to positions < num_ns_tokens."""
+    ocfg = O.OracleConfig(hidden_dim=spec['hidden_dim'], num_layers=spec['num_layers'], num_heads=spec['num_heads'], ffn_dim=spec['ffn_dim'],
+                          num_ns_tokens=spec['num_ns_tokens'], ns_param_alignment='head_literal', pyramid_enabled=spec['pyramid_enabled'],
+                          dropout_rate=0.0)
+    P = O.init_params(ocfg, seed=spec['seed'])
+    O.randomize_small_params(P, seed=spec['seed'] + 1)
+    for k in P:
+        if P[k].dim() >= 2 and 'ns_tokenizer' not in k and 'task_heads' not in k and 'sep_embedding' not in k:
+            P[k] = P[k].to(torch.bfloat16).to(torch.float32)
+    non_seq, seq, _ = O.synthetic_batch(ocfg, spec['B'], spec['seq_lens'], seed=1234 + spec['seed'])
+    non_seq, seq = bf16_round_inputs(non_seq, seq)
+    return ocfg, P, non_seq, seq
+
+
+def reference_case_checksum(P, non_seq, seq) -> float:
+    return float(sum(v.double().sum() for v in P.values()) + sum(v.double().sum() for v in non_seq.values()) + sum(v.double().sum() for v in seq.values()))

@@ -87,6 +87,37 @@ def test_smoke_shape_of_reference_main():
     _check(_run_pair(ocfg, cfg, B=64, seq_lens=(10, 5, 7), present=('click_seq', 'cart_seq')))
 
 
+@pytest.mark.parametrize('case', ['G_d256_pyramid_on_1_block', 'H_d256_pyramid_off_2_blocks'])
+def test_product_equals_the_reference_outputs(case):
+    """DIRECT product-vs-reference parity: the expected probabilities were produced by the reference's own, unmodified
+    ``OneTransModel.call`` (OT/model.py:335-393) executed over oracle/tf_shim.py on these weights and inputs
+    (tests/golden/make_reference_golden.py; the CPU twin in tests/test_reference_golden.py shows that the seeds rebuild what the
+    reference saw).  The reference gives dedicated weights to positions < num_ns_tokens: ``ns_param_alignment='head_literal'``."""
+    import json, os
+    import numpy as np
+    from tests.helpers import REFERENCE_KERNEL_CASES, reference_case_inputs, reference_case_checksum
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+    Z = np.load(os.path.join(here, 'reference_golden.npz'))
+    spec = json.load(open(os.path.join(here, 'reference_golden.json')))['cases'][case]
+    assert {k: (tuple(v) if isinstance(v, list) else v) for k, v in spec.items() if k in REFERENCE_KERNEL_CASES[case]} == REFERENCE_KERNEL_CASES[case]
+    ocfg, P, non_seq, seq = reference_case_inputs(spec)
+    assert reference_case_checksum(P, non_seq, seq) == pytest.approx(spec['checksum'], rel=1e-13)
+    _, cfg = make_configs(hidden_dim=spec['hidden_dim'], num_layers=spec['num_layers'], num_heads=spec['num_heads'], ffn_dim=spec['ffn_dim'],
+                          num_ns_tokens=spec['num_ns_tokens'], schedule='reference_ratio', alignment='head_literal',
+                          pyramid_enabled=spec['pyramid_enabled'])
+    model = R.OneTransModel(cfg).cuda()
+    R.load_reference_style_params(model, P)
+    with torch.no_grad():
+        got = model(to_cuda(non_seq), to_cuda(seq), training=False, return_logits=True)
+    ref_prob = torch.cat([torch.from_numpy(Z[f'{case}/out/prob/{t}']).flatten() for t in cfg.tasks])
+    lo = torch.log(ref_prob) - torch.log1p(-ref_prob)                     # the reference returns probabilities (sigmoid heads, OT/model.py:329)
+    lg = torch.cat([got[t].flatten().double().cpu() for t in cfg.tasks])
+    e = rel_l2(lg, lo)
+    print(f'product vs REFERENCE [{case}] logits rel-L2 err {e:.3e}')
+    assert e <= LOGIT_TOL, f'logits rel err {e:.3e}'
+    assert (torch.sigmoid(lg) - ref_prob).abs().max() < 1e-2
+
+
 def test_c1_small_reference_ratio():
     """BASELINE config 1 shapes: OneTrans-S, B=32, 256 S + 16 NS tokens, reference ratio schedule."""
     ocfg, cfg = make_configs(num_ns_tokens=16, schedule='reference_ratio')

@@ -106,3 +106,18 @@ def test_sequence_processor_equals_the_reference_numpy_code():
         if raw.shape[0]:
             _, seq = eng.preprocess_input({}, {}, {}, {'click_seq': raw})
             assert torch.equal(seq['click_seq'].double(), want.float().double()), tag
+
+
+@pytest.mark.parametrize('case', ['G_d256_pyramid_on_1_block', 'H_d256_pyramid_off_2_blocks'])
+def test_kernel_shape_cases_rebuild_from_seeds_and_match_the_reference(case):
+    """The CPU twin of tests/test_gpu_model.py::test_product_equals_the_reference_outputs: same rebuilt weights / inputs, the oracle
+    in place of the CUDA model, against the probabilities the reference's own code produced (fp64: 1e-12)."""
+    from tests.helpers import reference_case_inputs, reference_case_checksum
+    spec = FACTS['cases'][case]
+    ocfg, P, non_seq, seq = reference_case_inputs(spec)
+    assert reference_case_checksum(P, non_seq, seq) == pytest.approx(spec['checksum'], rel=1e-13)     # the seeds rebuild what the reference saw
+    f64 = lambda d: {k: v.double() for k, v in d.items()}
+    out = O.model_forward(f64(P), ocfg, f64(non_seq), f64(seq), query_mode='literal_gather')
+    for t in ocfg.tasks:
+        want = torch.from_numpy(Z[f'{case}/out/prob/{t}'])
+        assert torch.allclose(out[t], want, rtol=0, atol=1e-12), float((out[t] - want).abs().max())
