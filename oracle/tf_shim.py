@@ -70,6 +70,9 @@ def concat(values: Sequence[torch.Tensor], axis: int):
     kinds = {v.dtype for v in values}
     if len(kinds) > 1:
         raise InvalidArgumentError(f'ConcatOp: inputs of different dtypes {sorted(map(str, kinds))}')
+    ranks = {v.dim() for v in values}
+    if len(ranks) > 1:
+        raise InvalidArgumentError(f'ConcatOp: ranks of all input tensors should match, got shapes {[tuple(v.shape) for v in values]}')
     return torch.cat(list(values), dim=axis)
 
 

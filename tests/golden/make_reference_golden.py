@@ -16,7 +16,11 @@ What runs as written (and is recorded):
     literal 'head' alignment of SURVEY.md D4 - the oracle's ``ns_param_alignment='head_literal'`` mode is what these vectors pin.
 What does NOT run as written (recorded as the exception the reference raises - SURVEY.md §A.3):
   * D2 - pyramid on with two blocks: layer 1 gathers indices of the ORIGINAL length from the already shortened sequence;
-  * D9 - integer ids next to float features in ``tf.concat``.
+  * D9 - integer ids next to float features in ``tf.concat``;
+  * D6 - the KV-cache branch: a second call with ``use_kv_cache=True`` puts the cached keys in front of the new ones while the mask
+    keeps its built ``[L, L]`` shape;
+  * D7 - the one-tuple call form of OT/train.py:118 / OT/evaluate.py:87 against ``call(non_seq_features, seq_features, ...)``;
+  * D8 - ``config.gradient_clip`` (OT/train.py:134) does not exist, ``gradient_clip_norm`` does.
 Every parameter of the reference model is exported under the oracle's names so that the oracle can be run on identical weights."""
 import importlib
 import json
@@ -281,6 +285,22 @@ def main():
         non_seq['user_id'] = torch.randint(0, 100, (2, 1))
         M.OneTransModel(cfg)(non_seq, seq, training=False)
     facts['defects']['D9_integer_ids_in_concat'] = expected_failure(d9)
+
+    def d6():      # second call with use_kv_cache=True: cached keys in front, mask still [L, L] (OT/model.py:95-98, 109-110)
+        cfg = small_config(C, 1, False)
+        non_seq, seq = inputs(cfg, 2, (6, 3, 4), 9)
+        m = M.OneTransModel(cfg)
+        m(non_seq, seq, training=False, use_kv_cache=True)
+        m(non_seq, seq, training=False, use_kv_cache=True)
+    facts['defects']['D6_kv_cache_second_call'] = expected_failure(d6)
+
+    def d7():      # how OT/train.py:118,163, OT/evaluate.py:87 and the example scripts call the model: ONE tuple argument
+        cfg = small_config(C, 1, False)
+        non_seq, seq = inputs(cfg, 2, (6, 3, 4), 9)
+        M.OneTransModel(cfg)((non_seq, seq), training=True)
+    facts['defects']['D7_tuple_call'] = expected_failure(d7)
+    facts['defects']['D8_config_has_gradient_clip'] = hasattr(C.OneTransConfig(), 'gradient_clip')      # read by OT/train.py:134
+    facts['defects']['D8_config_has_gradient_clip_norm'] = hasattr(C.OneTransConfig(), 'gradient_clip_norm')
 
     np.savez_compressed(os.path.join(HERE, 'reference_golden.npz'), **{k: v.detach().numpy() for k, v in arrays.items()})
     with open(os.path.join(HERE, 'reference_golden.json'), 'w') as f:

@@ -87,6 +87,10 @@ def test_defects_the_reference_shows_when_executed():
     """SURVEY.md §A.3 D2 and D9, observed by running the reference (the repairs the oracle and the product adopt start here)."""
     assert 'is not in [0,' in FACTS['defects']['D2_pyramid_on_two_blocks']          # layer 1 gathers original-length indices
     assert 'different dtypes' in FACTS['defects']['D9_integer_ids_in_concat']       # int ids next to float features
+    assert 'ranks of all input tensors should match' in FACTS['defects']['D6_kv_cache_second_call']   # the cache holds the 4-D reshaped k / v
+    assert FACTS['defects']['D7_tuple_call'].startswith('TypeError')                 # model((non_seq, seq)) as train.py / evaluate.py call it
+    assert FACTS['defects']['D8_config_has_gradient_clip'] is False and FACTS['defects']['D8_config_has_gradient_clip_norm'] is True
+    assert R.OneTransConfig().gradient_clip_norm == 90.0 and not hasattr(R.OneTransConfig(), 'gradient_clip')
     # after a call the model holds the LAST block's (k, v) as its "cache" (OT/model.py:366-368) - per-layer caching needs D6
     assert FACTS['cases']['A_pyramid_off_2_blocks']['kv_cache_len_after_call'] == FACTS['cases']['A_pyramid_off_2_blocks']['total_len']
 
