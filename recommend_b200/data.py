@@ -4,22 +4,29 @@ per-sample generators :126-154): 11 scalar non-sequence features ``[B, 1]``, beh
 every rank, with ``seed = 1234 + rank``) sees reproducible inputs."""
 from __future__ import annotations
 
-from typing import Dict, Sequence, Tuple
+from typing import Dict, Optional, Sequence, Tuple
 
 import torch
 
 from .config import OneTransConfig
 
 
-def create_sample_batch(config: OneTransConfig, batch_size: int, seq_lens: Sequence[int], seed: int = 1234,
+def create_sample_batch(config=None, batch_size=None, seq_lens: Optional[Sequence[int]] = None, seed: int = 1234,
                         ns_mode: str = 'normal', dtype=torch.float32) -> Tuple[Dict[str, torch.Tensor], Dict[str, torch.Tensor], Dict[str, torch.Tensor]]:
     """``(non_seq_features, seq_features, labels)`` on the CPU.  ``ns_mode='ids'`` follows the reference literally (ids
     ``randint(0, 100)`` / ``randint(0, 1000)`` cast to float, context ``U[0, 1)``, OT/data_loader.py:309-316);
     ``'normal'`` draws N(0, 1) scalars (raw id magnitudes up to 1000 through a Dense make bf16 tolerances meaningless,
     SURVEY.md §8d).  Events are N(0, 1) (OT/data_loader.py:146)."""
+    if config is None or isinstance(config, int):
+        # the reference's call form ``create_sample_batch(batch_size=2, config=None)`` (OT/data_loader.py:301-329): ids as the
+        # reference draws them (cast to float, SURVEY.md D9), one random length in [1, max_seq_len] per sequence (:320-321)
+        config, batch_size = (batch_size if batch_size is not None else OneTransConfig()), (2 if config is None else config)
+        ns_mode = 'ids'
     g = torch.Generator().manual_seed(seed)
     fc = config.feature_config
     B = batch_size
+    if seq_lens is None:
+        seq_lens = [int(torch.randint(1, config.max_seq_len + 1, (), generator=g)) for _ in fc['sequence_features']]
     non_seq: Dict[str, torch.Tensor] = {}
     if ns_mode == 'ids':
         for n in fc['user_features']:

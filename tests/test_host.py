@@ -307,3 +307,17 @@ def test_unsupported_head_dims_are_errors_before_any_device_work():
         for fn in (lib.ot_attn_fwd, lib.ot_attn_bwd):
             assert fn(ctypes.byref(p), None) == -2           # OT_ERR_UNSUPPORTED_SHAPE, never a fallback
             assert f'head_dim={hd}' in lib.ot_last_error_string().decode()
+
+
+def test_create_sample_batch_accepts_the_reference_call_form():
+    """OT/data_loader.py:301-329: ``create_sample_batch(batch_size=2, config=None)`` - ids, one random length per sequence."""
+    cfg = R.get_model_config('small')
+    cfg.max_seq_len = 9
+    for args, kw in (((4, cfg), {}), ((), dict(batch_size=4, config=cfg))):
+        non_seq, seq, labels = R.create_sample_batch(*args, **kw)
+        assert set(non_seq) == set(cfg.ns_features) and all(v.shape == (4, 1) for v in non_seq.values())
+        assert all(v.shape[0] == 4 and 1 <= v.shape[1] <= 9 and v.shape[2] == 64 for v in seq.values())
+        assert float(non_seq['user_id'].max()) < 100 and float(non_seq['item_id'].max()) < 1000 and (non_seq['user_id'] == non_seq['user_id'].round()).all()
+        assert set(labels) == set(cfg.tasks)
+    a, b = R.create_sample_batch(cfg, 5, (3, 2, 1)), R.create_sample_batch(config=cfg, batch_size=5, seq_lens=(3, 2, 1))
+    assert all(torch.equal(a[1][k], b[1][k]) for k in a[1]) and a[1]['cart_seq'].shape == (5, 2, 64)
