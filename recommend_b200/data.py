@@ -21,6 +21,8 @@ def create_sample_batch(config=None, batch_size=None, seq_lens: Optional[Sequenc
         # the reference's call form ``create_sample_batch(batch_size=2, config=None)`` (OT/data_loader.py:301-329): ids as the
         # reference draws them (cast to float), one random length in [1, max_seq_len] per sequence (:320-321)
         config, batch_size = (batch_size if batch_size is not None else OneTransConfig()), (2 if config is None else config)
+    if seq_lens is None:        # no explicit lengths = the reference's form, whichever way the two arguments were passed
+        batch_size = 2 if batch_size is None else batch_size
         ns_mode = 'ids'
     g = torch.Generator().manual_seed(seed)
     fc = config.feature_config
