@@ -194,3 +194,37 @@ def evaluate_model(model_path: str, data_loader, output_dir: str = './evaluation
     model, config = load_model_for_evaluation(model_path)
     evaluator = OneTransEvaluator(model, config)
     return {'model_path': model_path, 'report_path': evaluator.generate_evaluation_report(data_loader, output_dir), 'evaluator': evaluator}
+
+
+def _cli(argv=None) -> int:
+    """``python -m recommend_b200.evaluate`` - the command line of OT/evaluate.py:419-465 (``--model_path``, ``--data_dir``,
+    ``--output_dir``, ``--eval_type full|offline|performance|ab_test``); data is generated sample data as in the reference (:445-448)."""
+    import argparse
+    ap = argparse.ArgumentParser(description='Evaluate a OneTrans model on the sm_100a path')
+    ap.add_argument('--model_path', type=str, required=True)
+    ap.add_argument('--data_dir', type=str, default=None)
+    ap.add_argument('--output_dir', type=str, default='./evaluation_reports')
+    ap.add_argument('--eval_type', type=str, default='full', choices=['full', 'offline', 'performance', 'ab_test'])
+    args = ap.parse_args(argv)
+    if not torch.cuda.is_available():
+        print('recommend_b200.evaluate needs a CUDA device (sm_100a); there is no CPU fallback')
+        return 2
+    from .data import DataLoader
+    model, config = load_model_for_evaluation(args.model_path)
+    data_loader = DataLoader(config)
+    data_loader.train_dataset = data_loader.create_sample_data(seed=1)
+    data_loader.test_dataset = data_loader.create_sample_data(seed=3)
+    evaluator = OneTransEvaluator(model, config)
+    if args.eval_type == 'full':
+        print('report:', evaluator.generate_evaluation_report(data_loader, args.output_dir))
+    elif args.eval_type == 'offline':
+        print(json.dumps(evaluator.evaluate_offline(data_loader), indent=2))
+    elif args.eval_type == 'performance':
+        print(json.dumps(evaluator.benchmark_performance(data_loader), indent=2))
+    else:
+        print('ab_test needs a control and a treatment dataset (OT/evaluate.py:464-465); call OneTransEvaluator.evaluate_ab_test')
+    return 0
+
+
+if __name__ == '__main__':
+    raise SystemExit(_cli())

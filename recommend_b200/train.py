@@ -422,3 +422,29 @@ def train_one_trans_model(config_name: str = 'small', data_paths: Optional[Dict[
     trainer = OneTransTrainer(config, model_dir)
     trainer.train(train_loader=data_loader, val_loader=data_loader, epochs=epochs)
     return trainer
+
+
+def _cli(argv=None) -> int:
+    """``python -m recommend_b200.train`` - the command line of OT/train.py:378-419 (same flags; ``--data_dir`` files are a stub in
+    the reference too, so both paths train on generated sample data)."""
+    import argparse
+    ap = argparse.ArgumentParser(description='Train a OneTrans model on the sm_100a path')
+    ap.add_argument('--config', type=str, default='small', help='model preset: small, base, large')
+    ap.add_argument('--epochs', type=int, default=10)
+    ap.add_argument('--batch_size', type=int, default=32)
+    ap.add_argument('--model_dir', type=str, default='./models')
+    ap.add_argument('--data_dir', type=str, default=None)
+    args = ap.parse_args(argv)
+    if not torch.cuda.is_available():
+        print('recommend_b200.train needs a CUDA device (sm_100a); there is no CPU fallback')
+        return 2
+    from .config import get_model_config
+    config = get_model_config(args.config)
+    config.batch_size = args.batch_size                                                   # OT/train.py:404-405
+    trainer = train_one_trans_model(args.config, None, args.epochs, args.model_dir, config=config)
+    print(f'training finished; models under {args.model_dir}; final loss {trainer.history["train_loss"][-1]:.4f}')
+    return 0
+
+
+if __name__ == '__main__':
+    raise SystemExit(_cli())

@@ -321,3 +321,17 @@ def test_create_sample_batch_accepts_the_reference_call_form():
         assert set(labels) == set(cfg.tasks)
     a, b = R.create_sample_batch(cfg, 5, (3, 2, 1)), R.create_sample_batch(config=cfg, batch_size=5, seq_lens=(3, 2, 1))
     assert all(torch.equal(a[1][k], b[1][k]) for k in a[1]) and a[1]['cart_seq'].shape == (5, 2, 64)
+
+
+def test_command_lines_keep_the_reference_flags():
+    """OT/train.py:378-419 and OT/evaluate.py:419-465: same flags; without a CUDA device they stop with exit code 2 (no CPU fallback)."""
+    from recommend_b200 import train as T, evaluate as E
+    for cli, argv in ((T._cli, ['--config', 'small', '--epochs', '1', '--batch_size', '8', '--model_dir', '/tmp/x', '--data_dir', '/tmp/d']),
+                      (E._cli, ['--model_path', '/tmp/x', '--data_dir', '/tmp/d', '--output_dir', '/tmp/o', '--eval_type', 'offline'])):
+        if not torch.cuda.is_available():
+            assert cli(argv) == 2
+        with pytest.raises(SystemExit) as e:
+            cli(['--no-such-flag'])
+        assert e.value.code == 2
+    with pytest.raises(SystemExit):
+        E._cli([])                                   # --model_path is required
