@@ -49,12 +49,14 @@ def export_params(model, cfg):
     """Reference model -> the oracle's parameter names (packed: index 0 shared, 1 + j dedicated j)."""
     P = {}
     tok = model.tokenizer
-    P['tokenizer.ns_tokenizer.kernel'] = tok.ns_tokenizer.layers[0].kernel
-    P['tokenizer.ns_tokenizer.bias'] = tok.ns_tokenizer.layers[0].bias
+    if tok.ns_tokenizer.layers[0].kernel is not None:      # never built when no configured feature was present
+        P['tokenizer.ns_tokenizer.kernel'] = tok.ns_tokenizer.layers[0].kernel
+        P['tokenizer.ns_tokenizer.bias'] = tok.ns_tokenizer.layers[0].bias
     for i, dense in enumerate(tok.seq_projections):
         if dense.kernel is not None:          # a projection whose sequence never appeared is never built (lazy Keras build)
             P[f'tokenizer.seq_projections.{i}.kernel'], P[f'tokenizer.seq_projections.{i}.bias'] = dense.kernel, dense.bias
-    P['tokenizer.sep_embedding'] = tok.sep_embedding.embeddings
+    if tok.sep_embedding.embeddings is not None:           # never built when no [SEP] was placed (only the last sequence present)
+        P['tokenizer.sep_embedding'] = tok.sep_embedding.embeddings
     for l, blk in enumerate(model.blocks):
         P.update(export_block(blk, f'blocks.{l}.'))
     P['output_norm.scale'] = model.output_norm.scale
@@ -184,11 +186,15 @@ def inputs(cfg, B, seq_lens, seed, present=None):
     return non_seq, seq
 
 
-def run_model_case(C, M, name, num_layers, pyramid, seq_lens, seed, present=None):
+def run_model_case(C, M, name, num_layers, pyramid, seq_lens, seed, present=None, drop_non_seq=False, ratios=None):
     cfg = small_config(C, num_layers, pyramid)
+    if ratios is not None:
+        cfg.pyramid_ratios = list(ratios)
     tf_shim.set_seed(seed)
     model = M.OneTransModel(cfg)
     non_seq, seq = inputs(cfg, 3, seq_lens, seed + 100, present)
+    if drop_non_seq:      # no CONFIGURED feature present -> the zeros branch of OT/model.py:249-251 (an empty dict raises instead, see defects)
+        non_seq = {'not_a_configured_feature': non_seq['price']}
     model(non_seq, seq, training=False)                       # builds every weight the run touches
     perturb(model, seed + 200)
     P = export_params(model, cfg)
@@ -246,7 +252,10 @@ def main():
     arrays = {}
     for name, kw in {'A_pyramid_off_2_blocks': dict(num_layers=2, pyramid=False, seq_lens=(5, 4, 3), seed=1),
                      'B_pyramid_on_1_block': dict(num_layers=1, pyramid=True, seq_lens=(6, 3, 4), seed=2),
-                     'D_missing_sequence': dict(num_layers=1, pyramid=False, seq_lens=(4, 5, 3), seed=4, present=('click_seq', 'purchase_seq'))}.items():
+                     'D_missing_sequence': dict(num_layers=1, pyramid=False, seq_lens=(4, 5, 3), seed=4, present=('click_seq', 'purchase_seq')),
+                     'F_no_non_seq_features': dict(num_layers=1, pyramid=False, seq_lens=(3, 2, 4), seed=6, drop_non_seq=True),
+                     'I_pyramid_keeps_one_token': dict(num_layers=1, pyramid=True, seq_lens=(2, 1, 1), seed=7, ratios=(0.05,)),
+                     'J_only_last_sequence': dict(num_layers=1, pyramid=True, seq_lens=(2, 2, 6), seed=8, present=('purchase_seq',))}.items():
         a, meta = run_model_case(C, M, name, **kw)
         arrays.update(a)
         facts['cases'][name] = meta
@@ -293,6 +302,18 @@ def main():
         m(non_seq, seq, training=False, use_kv_cache=True)
         m(non_seq, seq, training=False, use_kv_cache=True)
     facts['defects']['D6_kv_cache_second_call'] = expected_failure(d6)
+
+    def no_seq():  # OT/model.py:274-275: the empty-sequence fallback indexes list(features.values())[0] of an EMPTY dict
+        cfg = small_config(C, 1, False)
+        non_seq, _ = inputs(cfg, 2, (6, 3, 4), 9)
+        M.OneTransModel(cfg)(non_seq, {}, training=False)
+    facts['defects']['no_sequences_at_all'] = expected_failure(no_seq)
+
+    def no_ns():   # OT/model.py:249-251 likewise for an empty non-sequence dict
+        cfg = small_config(C, 1, False)
+        _, seq = inputs(cfg, 2, (6, 3, 4), 9)
+        M.OneTransModel(cfg)({}, seq, training=False)
+    facts['defects']['no_non_seq_features_at_all'] = expected_failure(no_ns)
 
     def d7():      # how OT/train.py:118,163, OT/evaluate.py:87 and the example scripts call the model: ONE tuple argument
         cfg = small_config(C, 1, False)

@@ -32,12 +32,14 @@ def _oracle_cfg(meta, literal=True):
     return cfg
 
 
-@pytest.mark.parametrize('case', ['A_pyramid_off_2_blocks', 'B_pyramid_on_1_block', 'D_missing_sequence'])
+@pytest.mark.parametrize('case', ['A_pyramid_off_2_blocks', 'B_pyramid_on_1_block', 'D_missing_sequence', 'F_no_non_seq_features',
+                                  'I_pyramid_keeps_one_token', 'J_only_last_sequence'])
 def test_oracle_equals_the_reference_model_call(case):
     meta = FACTS['cases'][case]
     cfg = _oracle_cfg(meta)
     P, non_seq, seq = _group(f'{case}/param/'), _group(f'{case}/in/non_seq/'), _group(f'{case}/in/seq/')
     assert sorted(seq) == meta['present']
+    P.setdefault('tokenizer.sep_embedding', torch.zeros(1, meta['hidden_dim'], dtype=torch.float64))   # unbuilt in the reference when no [SEP] is placed
     tokens = O.tokenizer_forward(P, cfg, non_seq, seq)
     want_tokens = torch.from_numpy(Z[f'{case}/out/tokens'])
     assert tokens.shape == want_tokens.shape and tokens.shape[1] == meta['total_len']
@@ -88,6 +90,8 @@ def test_defects_the_reference_shows_when_executed():
     assert 'is not in [0,' in FACTS['defects']['D2_pyramid_on_two_blocks']          # layer 1 gathers original-length indices
     assert 'different dtypes' in FACTS['defects']['D9_integer_ids_in_concat']       # int ids next to float features
     assert 'ranks of all input tensors should match' in FACTS['defects']['D6_kv_cache_second_call']   # the cache holds the 4-D reshaped k / v
+    assert FACTS['defects']['no_sequences_at_all'].startswith('IndexError')          # OT/model.py:274-275 indexes an empty dict's values
+    assert FACTS['defects']['no_non_seq_features_at_all'].startswith('IndexError')   # OT/model.py:249-251 likewise
     assert FACTS['defects']['D7_tuple_call'].startswith('TypeError')                 # model((non_seq, seq)) as train.py / evaluate.py call it
     assert FACTS['defects']['D8_config_has_gradient_clip'] is False and FACTS['defects']['D8_config_has_gradient_clip_norm'] is True
     assert R.OneTransConfig().gradient_clip_norm == 90.0 and not hasattr(R.OneTransConfig(), 'gradient_clip')
