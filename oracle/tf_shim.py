@@ -243,6 +243,10 @@ class Sequential(Layer):
         return x
 
 
+def one_hot(indices, depth):
+    return torch.nn.functional.one_hot(torch.as_tensor(indices).long(), int(depth)).to(FLOAT)
+
+
 def count_params(w) -> int:
     return int(w.numel())
 
@@ -252,7 +256,7 @@ def install() -> types.ModuleType:
     me = sys.modules[__name__]
     tf = types.ModuleType('tensorflow')
     for name in ('float32', 'int32', 'Tensor', 'Variable', 'ones', 'zeros', 'cast', 'shape', 'concat', 'reshape', 'einsum', 'where', 'gather',
-                 'linalg', 'nn', 'random'):
+                 'linalg', 'nn', 'random', 'one_hot'):
         setattr(tf, name, getattr(me, name))
     tf.math = math_ns
     tf.errors = types.SimpleNamespace(InvalidArgumentError=InvalidArgumentError)

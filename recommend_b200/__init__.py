@@ -13,7 +13,7 @@ from .inference import OneTransInferenceEngine, score_candidates_sharded, shard_
 from .metrics import BinaryTaskMetrics, exact_auc, user_auc
 from .evaluate import OneTransEvaluator, load_model_for_evaluation, evaluate_model
 from .train import OneTransTrainer, train_one_trans_model
-from .data import DataLoader, OneTransDataset, SequenceProcessor, create_sample_batch
+from .data import DataLoader, OneTransDataset, FeatureProcessor, SequenceProcessor, create_sample_batch
 
 __all__ = [
     'OneTransModel', 'OneTransConfig', 'OneTransSmallConfig', 'OneTransLargeConfig', 'get_model_config',
@@ -21,5 +21,5 @@ __all__ = [
     'create_onetrans_model', 'resolve_keep_lens', 'load_reference_style_params', 'export_reference_style_params',
     'EventEmbedding', 'SparseAdagrad', 'OneTransInferenceEngine', 'BinaryTaskMetrics', 'exact_auc', 'user_auc', 'OneTransEvaluator',
     'load_model_for_evaluation', 'evaluate_model', 'OneTransTrainer', 'train_one_trans_model', 'DataLoader', 'OneTransDataset',
-    'SequenceProcessor', 'create_sample_batch', 'score_candidates_sharded', 'shard_bounds', 'gather_shards',
+    'FeatureProcessor', 'SequenceProcessor', 'create_sample_batch', 'score_candidates_sharded', 'shard_bounds', 'gather_shards',
 ]

@@ -47,6 +47,50 @@ def create_sample_batch(config=None, batch_size=None, seq_lens: Optional[Sequenc
     return non_seq, seq, labels
 
 
+class FeatureProcessor:
+    """OT/data_loader.py:13-65: per-feature statistics from a table (``fit``), z-score + clip to [-3, 3] for numerical features
+    (:47-57), one-hot for categorical ones (:59-65).  Host-side preparation (numpy / pandas in the reference); ``data`` is anything
+    with ``columns`` / ``__getitem__`` returning array-likes (a pandas DataFrame, or a dict of arrays)."""
+
+    NUMERICAL = ('price', 'age', 'ctr')                                                    # :39-41
+    CATEGORICAL = ('user_id', 'item_id', 'category', 'brand', 'location', 'device')         # :43-45
+
+    def __init__(self, config: OneTransConfig):
+        self.config = config
+        self.feature_stats: Dict[str, Dict[str, float]] = {}
+        self.vocab_sizes: Dict[str, int] = {}
+
+    def _get_numerical_features(self):
+        return list(self.NUMERICAL)
+
+    def _get_categorical_features(self):
+        return list(self.CATEGORICAL)
+
+    def fit(self, data) -> None:
+        columns = list(data.columns) if hasattr(data, 'columns') else list(data.keys())
+        for f in self.NUMERICAL:
+            if f in columns:
+                col = torch.as_tensor(list(data[f]), dtype=torch.float64)
+                self.feature_stats[f] = {'mean': float(col.mean()), 'std': float(col.std(unbiased=True)) if col.numel() > 1 else float('nan'),
+                                         'min': float(col.min()), 'max': float(col.max())}      # pandas .std() is the sample (n - 1) deviation
+        for f in self.CATEGORICAL:
+            if f in columns:
+                self.vocab_sizes[f] = int(torch.as_tensor(list(data[f])).max() + 1)
+
+    def process_numerical_feature(self, feature_name: str, values):
+        v = torch.as_tensor(values, dtype=torch.float64)
+        if feature_name not in self.feature_stats:
+            return v                                                                           # :49-50
+        st = self.feature_stats[feature_name]
+        return ((v - st['mean']) / (st['std'] + 1e-8)).clamp(-3, 3)                          # :53-56
+
+    def process_categorical_feature(self, feature_name: str, values):
+        v = torch.as_tensor(values)
+        if feature_name not in self.vocab_sizes:
+            return v                                                                           # :61-62
+        return torch.nn.functional.one_hot(v.long(), self.vocab_sizes[feature_name]).to(torch.float32)   # :64-65
+
+
 class SequenceProcessor:
     """OT/data_loader.py:68-101: keep the most recent ``max_seq_len`` events, left-pad shorter sequences with zero events."""
 

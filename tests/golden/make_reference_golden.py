@@ -281,6 +281,21 @@ def main():
         arrays[f'seqproc/{tag}/out'] = torch.from_numpy(np.asarray(sp.process_sequence(raw, 'click_seq'), dtype=np.float64))
     facts['cases']['seqproc'] = {'max_seq_len': 6}
 
+    # OT/data_loader.py:13-65 FeatureProcessor: pandas statistics, numpy standardisation, tf.one_hot
+    import pandas as pd
+    rng = np.random.default_rng(3)
+    table = {'price': rng.uniform(0, 1000, 50).tolist(), 'age': rng.integers(18, 70, 50).astype(float).tolist(),
+             'user_id': rng.integers(0, 40, 50).tolist(), 'category': rng.integers(0, 7, 50).tolist()}
+    fp = DL.FeatureProcessor(dcfg)
+    fp.fit(pd.DataFrame(table))
+    probe = {'price': [0.0, 250.0, 999.0, 5000.0, -4000.0], 'age': [18.0, 44.0, 69.0], 'ctr': [0.1, 0.2]}
+    facts['cases']['featproc'] = {
+        'table': table, 'feature_stats': {k: {kk: float(vv) for kk, vv in v.items()} for k, v in fp.feature_stats.items()},
+        'vocab_sizes': {k: int(v) for k, v in fp.vocab_sizes.items()}, 'probe': probe,
+        'numerical': {k: np.asarray(fp.process_numerical_feature(k, np.array(v))).tolist() for k, v in probe.items()},
+        'one_hot_category': np.asarray(fp.process_categorical_feature('category', np.array([0, 3, 6]))).tolist(),
+        'unknown_categorical_passthrough': np.asarray(fp.process_categorical_feature('brand', np.array([5, 9]))).tolist()}
+
     # the defects of SURVEY.md §A.3 that the shimmed reference reproduces
     def d2():
         cfg = small_config(C, 2, True)

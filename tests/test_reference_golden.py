@@ -129,3 +129,19 @@ def test_kernel_shape_cases_rebuild_from_seeds_and_match_the_reference(case):
     for t in ocfg.tasks:
         want = torch.from_numpy(Z[f'{case}/out/prob/{t}'])
         assert torch.allclose(out[t], want, rtol=0, atol=1e-12), float((out[t] - want).abs().max())
+
+
+def test_feature_processor_equals_the_reference_pandas_numpy_code():
+    """OT/data_loader.py:13-65 executed (pandas statistics, numpy z-score + clip, one-hot) against ``recommend_b200.FeatureProcessor``."""
+    f = FACTS['cases']['featproc']
+    fp = R.FeatureProcessor(R.OneTransConfig())
+    fp.fit(f['table'])
+    assert fp.vocab_sizes == f['vocab_sizes'] and set(fp.feature_stats) == set(f['feature_stats'])
+    for name, st in f['feature_stats'].items():
+        for key, value in st.items():
+            assert fp.feature_stats[name][key] == pytest.approx(value, rel=1e-12), (name, key)
+    for name, values in f['probe'].items():
+        got = fp.process_numerical_feature(name, values)
+        assert torch.allclose(got, torch.tensor(f['numerical'][name], dtype=torch.float64), rtol=1e-12, atol=1e-12), name
+    assert fp.process_categorical_feature('category', [0, 3, 6]).tolist() == f['one_hot_category']
+    assert fp.process_categorical_feature('brand', [5, 9]).tolist() == f['unknown_categorical_passthrough']     # unfitted feature: unchanged
