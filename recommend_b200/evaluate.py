@@ -63,14 +63,19 @@ class OneTransEvaluator:
         return preds, e0, e1
 
     @torch.no_grad()
-    def evaluate_offline(self, data_loader, dataset_type: str = 'test', ablate: Optional[str] = None) -> Dict[str, Any]:
+    def evaluate_offline(self, data_loader, dataset_type: str = 'test', ablate: Optional[str] = None, rank: int = 0,
+                         world_size: int = 1) -> Dict[str, Any]:
         """OT/evaluate.py:58-129: one pass over the dataset; every ``{task}_{auc,accuracy,precision,recall,f1,logloss}`` plus the
         ``'performance'`` block (``total_samples``, ``avg_inference_time_per_batch``, ``throughput_samples_per_second``,
-        ``avg_inference_time_per_sample``)."""
+        ``avg_inference_time_per_sample``).  ``world_size > 1`` (one process per GPU, ``torch.distributed`` initialised): rank r takes
+        batches ``r, r + world_size, ...`` and the metric states - counts - are summed over the ranks, so every rank returns the
+        metrics of the whole dataset; ``{task}_auc_exact`` and the performance block then describe the rank's own shard."""
         self.metrics.reset_states()                                                             # :71-73
         total_samples, events = 0, []
         kept = {t: ([], []) for t in self.config.tasks}
-        for batch in self._dataset(data_loader, dataset_type):
+        for i_batch, batch in enumerate(self._dataset(data_loader, dataset_type)):
+            if i_batch % world_size != rank:
+                continue
             non_seq, seq, labels = self._to_device(batch)
             if ablate is not None:
                 for d in (non_seq, seq):
@@ -88,6 +93,8 @@ class OneTransEvaluator:
                 kept[t][1].append(preds[t].reshape(-1).float())
         if not events:
             raise ValueError('evaluate_offline: empty dataset')
+        if world_size > 1:
+            self.metrics.all_reduce()
         results: Dict[str, Any] = dict(self.metrics.result())                                   # :108-111
         for t in self.config.tasks:
             results[f'{t}_auc_exact'] = exact_auc(torch.cat(kept[t][0]), torch.cat(kept[t][1]))
