@@ -46,8 +46,16 @@ def _t(x, dtype=None):
     return x if isinstance(x, torch.Tensor) else torch.as_tensor(x, dtype=dtype or (FLOAT if isinstance(x, float) else None))
 
 
+_VARIABLES = set()           # ids of tensors that are tf.Variables (weights); plain tensors such as a cached (k, v) are not
+
+
+def _variable(t: torch.Tensor) -> torch.Tensor:
+    _VARIABLES.add(id(t))
+    return t
+
+
 def Variable(initial_value, **_):
-    return _t(initial_value).clone()
+    return _variable(_t(initial_value).clone())
 
 
 def ones(shape, dtype=None):
@@ -146,7 +154,7 @@ class Layer:
 
         def visit(obj):
             if isinstance(obj, torch.Tensor):
-                if obj.dtype == FLOAT:
+                if id(obj) in _VARIABLES:
                     out.append(obj)
             elif isinstance(obj, Layer):
                 for k, v in vars(obj).items():
@@ -185,9 +193,9 @@ class Dense(Layer):
     def build(self, input_shape):
         fan_in, fan_out = int(input_shape[-1]), self.units
         limit = math.sqrt(6.0 / (fan_in + fan_out))                  # glorot_uniform
-        self.kernel = (torch.rand(fan_in, fan_out, generator=_GEN, dtype=FLOAT) * 2.0 - 1.0) * limit
+        self.kernel = _variable((torch.rand(fan_in, fan_out, generator=_GEN, dtype=FLOAT) * 2.0 - 1.0) * limit)
         if self.use_bias:
-            self.bias = torch.zeros(fan_out, dtype=FLOAT)
+            self.bias = _variable(torch.zeros(fan_out, dtype=FLOAT))
 
     def call(self, x):
         if x.dtype != FLOAT:
@@ -214,7 +222,7 @@ class Embedding(Layer):
         self.embeddings: Optional[torch.Tensor] = None
 
     def build(self, input_shape):
-        self.embeddings = torch.rand(self.input_dim, self.output_dim, generator=_GEN, dtype=FLOAT) * 0.1 - 0.05   # 'uniform'
+        self.embeddings = _variable(torch.rand(self.input_dim, self.output_dim, generator=_GEN, dtype=FLOAT) * 0.1 - 0.05)   # 'uniform'
 
     def call(self, ids):
         return self.embeddings[ids.long()]

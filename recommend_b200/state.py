@@ -77,7 +77,8 @@ def _keras_entries(model):
     sep_embedding; ``OneTransBlock`` (:169-184): norm1, norm2, attention, ffn; ``MixedMHA`` (:29-57): Wq/Wk/Wv shared, then the
     Wq / Wk / Wv dedicated lists, Wo; ``MixedFFN`` (:128-147): ffn_shared, ffn_dedicated[j]; every Dense is kernel then bias.
     ``index`` selects a slice of a packed parameter: ``(group, part)`` for Wqkv (part 0/1/2 = q/k/v), ``(group,)`` for W1/b1/W2/b2.
-    Dedicated weights j belong to NS token j (group 1 + j; SURVEY.md D4 'tail' alignment)."""
+    Dedicated weights j belong to NS token j (group 1 + j; SURVEY.md D4 'tail' alignment).  The order (names and shapes) is checked
+    against the attribute order of a live reference model in tests/test_reference_golden.py."""
     tok = model.tokenizer
     yield 'tokenizer/ns_tokenizer/dense/kernel', tok.ns_kernel, None
     yield 'tokenizer/ns_tokenizer/dense/bias', tok.ns_bias, None

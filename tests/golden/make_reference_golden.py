@@ -207,7 +207,8 @@ def run_model_case(C, M, name, num_layers, pyramid, seq_lens, seed, present=None
     arrays[f'{name}/out/tokens'] = tokens
     for t, v in out.items():
         arrays[f'{name}/out/prob/{t}'] = v
-    meta = {'hidden_dim': cfg.hidden_dim, 'num_heads': cfg.num_heads, 'ffn_dim': cfg.ffn_dim, 'num_layers': cfg.num_layers,
+    paths = weight_paths(model)
+    meta = {'weight_paths': paths, 'hidden_dim': cfg.hidden_dim, 'num_heads': cfg.num_heads, 'ffn_dim': cfg.ffn_dim, 'num_layers': cfg.num_layers,
             'num_ns_tokens': cfg.num_ns_tokens, 'pyramid_enabled': cfg.pyramid_enabled, 'pyramid_ratios': list(cfg.pyramid_ratios),
             'seq_lens': list(seq_lens), 'present': sorted(seq), 'total_len': int(tokens.shape[1]),
             'total_parameters': int(model.get_model_info()['total_parameters']),
@@ -228,6 +229,36 @@ def run_block_case(C, M, seed):
     arrays = {'block/in/x': x, 'block/out/y': y, 'block/out/k': k, 'block/out/v': v}
     arrays.update({f'block/param/{n}': t for n, t in P.items()})
     return arrays, {'seq_len': 9, 'num_ns_tokens': cfg.num_ns_tokens}
+
+
+def weight_paths(root):
+    """``(path, shape)`` of every built float weight of a reference layer tree in ATTRIBUTE-ASSIGNMENT order - the order Keras tracks
+    sub-layers and therefore the order of ``model.weights`` / ``get_weights()`` / an ``.h5`` weight file (a layer's own variables come
+    before its sub-layers; none of the reference's layers has both).  ``layers/i`` of a Sequential is spelled ``dense`` / ``dense_1``."""
+    out = []
+
+    def visit(obj, path):
+        if isinstance(obj, torch.Tensor):
+            if id(obj) in tf_shim._VARIABLES:
+                out.append(('/'.join(path), list(obj.shape)))
+        elif isinstance(obj, tf_shim.Sequential):
+            dense_i = 0
+            for layer in obj.layers:
+                if isinstance(layer, tf_shim.Dense):
+                    visit(layer, path + ['dense' if dense_i == 0 else f'dense_{dense_i}'])
+                    dense_i += 1
+        elif isinstance(obj, tf_shim.Layer):
+            for k, v in vars(obj).items():
+                if k not in ('_built', 'config'):
+                    visit(v, path + [k])
+        elif isinstance(obj, (list, tuple)):
+            for i, v in enumerate(obj):
+                visit(v, path + [str(i)])
+        elif isinstance(obj, dict):
+            for k, v in obj.items():
+                visit(v, path + [str(k)])
+    visit(root, [])
+    return out
 
 
 def expected_failure(fn):

@@ -145,3 +145,18 @@ def test_feature_processor_equals_the_reference_pandas_numpy_code():
         assert torch.allclose(got, torch.tensor(f['numerical'][name], dtype=torch.float64), rtol=1e-12, atol=1e-12), name
     assert fp.process_categorical_feature('category', [0, 3, 6]).tolist() == f['one_hot_category']
     assert fp.process_categorical_feature('brand', [5, 9]).tolist() == f['unknown_categorical_passthrough']     # unfitted feature: unchanged
+
+
+def test_keras_weight_order_follows_the_reference_object_graph():
+    """``state.keras_weight_list`` (what ``OneTransTrainer.save_model`` writes and ``load_keras_weight_list`` reads) lists the weights in
+    the attribute-assignment order of the reference's constructors - recorded from the LIVE reference model (case A), names and shapes."""
+    from recommend_b200 import state
+    meta = FACTS['cases']['A_pyramid_off_2_blocks']
+    cfg = R.OneTransConfig()
+    cfg.hidden_dim, cfg.num_heads, cfg.ffn_dim, cfg.num_layers, cfg.num_ns_tokens = (meta['hidden_dim'], meta['num_heads'], meta['ffn_dim'],
+                                                                                     meta['num_layers'], meta['num_ns_tokens'])
+    mine = [(name, list(a.shape)) for name, a in state.keras_weight_list(R.OneTransModel(cfg))]
+    want = [(name, shape) for name, shape in meta['weight_paths']]
+    assert len(mine) == len(want) == 80
+    assert mine == want
+    assert sum(int(np.prod(s)) for _, s in want) == meta['total_parameters']
