@@ -300,6 +300,20 @@ def main():
         arrays.update(a)
         facts['cases'][name] = meta
 
+    # parameter counts of the BASELINE configurations as the reference's own get_model_info reports them after one forward pass
+    # (Keras builds weights lazily; pyramid off so that every block sees every position and builds every dedicated weight)
+    facts['param_counts'] = {}
+    for tag, preset, L_ns, lens in (('small_ns32_512', 'small', 32, (170, 170, 170)), ('small_ns16_256', 'small', 16, (86, 84, 84))):
+        cfg = C.get_model_config(preset)
+        cfg.num_ns_tokens, cfg.pyramid_enabled = L_ns, False
+        tf_shim.set_seed(0)
+        big = M.OneTransModel(cfg)
+        non_seq, seq = inputs(cfg, 1, lens, 0)
+        with torch.no_grad():
+            big(non_seq, seq, training=False)
+        facts['param_counts'][tag] = {'preset': preset, 'num_ns_tokens': L_ns, 'total_parameters': int(big.get_model_info()['total_parameters'])}
+        del big
+
     # OT/data_loader.py:68-101, the reference's numpy code
     DL = importlib.import_module('ot_ref.data_loader')
     dcfg = C.OneTransConfig()

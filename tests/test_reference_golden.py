@@ -160,3 +160,15 @@ def test_keras_weight_order_follows_the_reference_object_graph():
     assert len(mine) == len(want) == 80
     assert mine == want
     assert sum(int(np.prod(s)) for _, s in want) == meta['total_parameters']
+
+
+def test_parameter_counts_of_the_baseline_configurations():
+    """The reference's own ``get_model_info`` after one forward pass at the BASELINE shapes (SURVEY.md §8d "Params / allreduce payload":
+    OneTrans-S with 32 NS tokens = 143.6 M) against the product model's count."""
+    assert FACTS['param_counts']['small_ns32_512']['total_parameters'] == 143601922
+    for tag, ref in FACTS['param_counts'].items():
+        cfg = R.get_model_config(ref['preset'])
+        cfg.num_ns_tokens = ref['num_ns_tokens']
+        with torch.device('meta'):
+            model = R.OneTransModel(cfg)
+        assert model.get_model_info()['total_parameters'] == ref['total_parameters'], tag
