@@ -294,8 +294,8 @@ def main():
     arrays.update(a)
     facts['cases']['block'] = meta
 
-    from tests.helpers import REFERENCE_KERNEL_CASES
-    for name, spec in REFERENCE_KERNEL_CASES.items():
+    from tests.helpers import REFERENCE_KERNEL_CASES, REFERENCE_CPU_CASES
+    for name, spec in {**REFERENCE_KERNEL_CASES, **REFERENCE_CPU_CASES}.items():
         a, meta = run_kernel_shape_case(C, M, name, spec)
         arrays.update(a)
         facts['cases'][name] = meta

@@ -56,6 +56,13 @@ REFERENCE_KERNEL_CASES = {
 }
 
 
+# BASELINE config 1 (the reference's own CPU-runnable case) at full size; pyramid off because the reference cannot prune past one block (D2)
+REFERENCE_CPU_CASES = {
+    'C1_small_ns16_pyramid_off': dict(hidden_dim=256, num_heads=4, ffn_dim=1024, num_layers=6, num_ns_tokens=16, pyramid_enabled=False,
+                                      B=32, seq_lens=(86, 84, 84), seed=31),
+}
+
+
 def reference_case_inputs(spec):
     """Weights and inputs of a REFERENCE_KERNEL_CASES entry, rebuilt from seeds (nothing but the reference's outputs is stored):
     oracle ``init_params`` + ``randomize_small_params`` with the GEMM weights rounded to bf16-representable values, ``synthetic_batch``

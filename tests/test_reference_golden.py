@@ -172,3 +172,23 @@ def test_parameter_counts_of_the_baseline_configurations():
         with torch.device('meta'):
             model = R.OneTransModel(cfg)
         assert model.get_model_info()['total_parameters'] == ref['total_parameters'], tag
+
+
+def test_baseline_config_1_forward_and_loss_match_the_reference_at_full_size():
+    """BASELINE config 1 - OneTrans-S, CPU fp32, batch 32, 6 blocks, 256 sequence + 16 NS tokens - run by the reference's own code
+    (pyramid off: it cannot prune past one block, D2).  The oracle in fp32 (the arithmetic type config 1 names) against the reference's
+    fp64 probabilities, and the summed BCE of OT/train.py:84-87, 124-128 from both."""
+    from tests.helpers import reference_case_inputs, reference_case_checksum
+    case = 'C1_small_ns16_pyramid_off'
+    spec = FACTS['cases'][case]
+    ocfg, P, non_seq, seq = reference_case_inputs(spec)
+    assert reference_case_checksum(P, non_seq, seq) == pytest.approx(spec['checksum'], rel=1e-12)
+    assert spec['total_len'] == 272
+    out = O.model_forward(P, ocfg, non_seq, seq)                               # fp32, vectorised, tail-only == everything (pyramid off)
+    g = torch.Generator().manual_seed(5)
+    for t in ocfg.tasks:
+        want = torch.from_numpy(Z[f'{case}/out/prob/{t}'])
+        assert out[t].dtype == torch.float32 and out[t].shape == want.shape == (32, 1)
+        assert float((out[t].double() - want).abs().max()) < 5e-6
+        y = (torch.rand(32, 1, generator=g) < 0.5).float()
+        assert float(O.bce_loss({t: out[t]}, {t: y}, [t])) == pytest.approx(float(O.bce_loss({t: want}, {t: y.double()}, [t])), rel=1e-5)
