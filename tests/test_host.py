@@ -97,7 +97,8 @@ def test_ctypes_structs_match_header_layout():
     pairs = [('ot_gemm_seg', _lib.GemmSeg), ('ot_gemm_params', _lib.GemmParams), ('ot_wgrad_seg', _lib.WgradSeg),
              ('ot_wgrad_params', _lib.WgradParams), ('ot_attn_params', _lib.AttnParams), ('ot_attn_cached_params', _lib.AttnCachedParams), ('ot_rmsnorm_params', _lib.RmsnormParams),
              ('ot_ns_tokenizer_params', _lib.NsTokenizerParams), ('ot_colsum_params', _lib.ColsumParams),
-             ('ot_rmsprop_params', _lib.RmspropParams), ('ot_embed_params', _lib.EmbedParams), ('ot_heads_params', _lib.HeadsParams)]
+             ('ot_rmsprop_params', _lib.RmspropParams), ('ot_embed_params', _lib.EmbedParams), ('ot_heads_params', _lib.HeadsParams),
+             ('ot_metrics_params', _lib.MetricsParams), ('ot_auc_params', _lib.AucParams)]
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', 'int main(void){']
     for cname, st in pairs:
         lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
@@ -107,7 +108,7 @@ def test_ctypes_structs_match_header_layout():
     with tempfile.TemporaryDirectory() as td:
         src, exe = os.path.join(td, 'p.c'), os.path.join(td, 'p')
         open(src, 'w').write('\n'.join(lines))
-        subprocess.check_call(['gcc', '-o', exe, src])
+        subprocess.check_call(['gcc', '-std=c99', '-pedantic', '-Werror', '-o', exe, src])      # the header is plain C
         out = dict(l.split() for l in subprocess.check_output([exe]).decode().splitlines())
     for cname, st in pairs:
         assert int(out[cname]) == ctypes.sizeof(st), cname
