@@ -327,6 +327,26 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// 2^x on the FMA / ALU pipes (no MUFU): round-to-nearest split x = n + f with the 1.5 * 2^23 magic add, degree-3 minimax polynomial
+// for 2^f on [-0.5, 0.5] (max relative error 7.5e-5, i.e. 1/50 of a bf16 half-ulp; same bf16 value as the exact exp2 for 99.1 % of
+// inputs), exponent injected by an integer add.  8 FMA/ALU-pipe instructions against one instruction on the 16-lane XU pipe: meant
+// for a FRACTION of the elements of the attention softmax loops, whose element-wise phases are XU-bound (profiles/README.md, known
+// gap 1).  Arguments below -126 give 2^-126 (~1e-38, zero for a softmax).  NOT WIRED INTO ANY KERNEL YET: the constants and the
+// arithmetic are pinned by a bit-level fp32 emulation in tests/test_host.py::test_polynomial_exp2_building_block.
+#define OT_EX2_POLY_C0 0.9999280571937561f
+#define OT_EX2_POLY_C1 0.6932609677314758f
+#define OT_EX2_POLY_C2 0.2426111251115799f
+#define OT_EX2_POLY_C3 0.0551716648042202f
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -126.0f);
+  const float t = x + 12582912.0f;                 // low mantissa bits of t now hold round(x) in two's complement
+  const float f = x - (t - 12582912.0f);           // in [-0.5, 0.5]
+  float p = fmaf(f, OT_EX2_POLY_C3, OT_EX2_POLY_C2);
+  p = fmaf(p, f, OT_EX2_POLY_C1);
+  p = fmaf(p, f, OT_EX2_POLY_C0);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));   // p * 2^round(x)
+}
+
 // Counter-based dropout mask (Keras inverted dropout, OT/model.py:184,193,198): one 32-bit hash decides the two
 // elements (row, col) and (row, col+1), col even; an element is kept iff its 16-bit lane >= thr16 = round(rate*65536).
 // The forward epilogue and the backward mask kernel evaluate the same function, so no mask is ever stored.

@@ -336,3 +336,33 @@ def test_command_lines_keep_the_reference_flags():
         assert e.value.code == 2
     with pytest.raises(SystemExit):
         E._cli([])                                   # --model_path is required
+
+
+def test_polynomial_exp2_building_block():
+    """``ex2_poly`` of ot_common.cuh (FMA-pipe 2^x for the attention softmax loops; not wired into a kernel yet): its constants and
+    its exact fp32 instruction sequence, emulated bit by bit, stay within 8e-5 of exp2 on the range a softmax uses."""
+    src = open(os.path.join(os.path.dirname(_lib.LIB_PATH), '..', 'csrc', 'ot_common.cuh')).read()
+    C = [np.float32(re.search(rf'#define OT_EX2_POLY_C{i} ([0-9.]+)f', src).group(1)) for i in range(4)]
+    assert '12582912.0f' in src and '<< 23' in src
+
+    def fma(a, b, c):
+        return (a.astype(np.float64) * b.astype(np.float64) + c.astype(np.float64)).astype(np.float32)
+
+    def ex2_poly(x):
+        x = np.maximum(x.astype(np.float32), np.float32(-126.0))
+        M = np.float32(12582912.0)
+        t = (x + M).astype(np.float32)
+        f = (x - (t - M).astype(np.float32)).astype(np.float32)
+        p = fma(f, np.full_like(f, C[3]), np.full_like(f, C[2]))
+        p = fma(p, f, np.full_like(f, C[1]))
+        p = fma(p, f, np.full_like(f, C[0]))
+        bits = (p.view(np.int32).astype(np.int64) + ((t.view(np.int32).astype(np.int64) << 23) & 0xFFFFFFFF)) & 0xFFFFFFFF
+        return bits.astype(np.uint32).view(np.float32), f
+
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.uniform(-125, 0, 400000), rng.uniform(-20, 0, 400000), -np.arange(0, 126, 0.5)]).astype(np.float32)
+    y, f = ex2_poly(x)
+    ref = np.exp2(x.astype(np.float64))
+    assert np.abs(f).max() <= 0.5
+    assert (np.abs(y.astype(np.float64) - ref) / ref).max() < 8e-5
+    assert ex2_poly(np.array([-1000.0], np.float32))[0][0] < 2e-38          # far below the running maximum: as good as zero
