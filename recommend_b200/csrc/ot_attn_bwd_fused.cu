@@ -405,8 +405,8 @@ ot_attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
           const int j0 = half * 64 + c * 8;
 #pragma unroll
           for (int i2 = 0; i2 < 4; ++i2) {
-            float pv0 = ex2_approx(fmaf(__uint_as_float(vs[cb][2 * i2]), p.scale_log2, -lse2));
-            float pv1 = ex2_approx(fmaf(__uint_as_float(vs[cb][2 * i2 + 1]), p.scale_log2, -lse2));
+            float pv0 = ex2_mixed(fmaf(__uint_as_float(vs[cb][2 * i2]), p.scale_log2, -lse2), 2 * i2);
+            float pv1 = ex2_mixed(fmaf(__uint_as_float(vs[cb][2 * i2 + 1]), p.scale_log2, -lse2), 2 * i2 + 1);
             if (!fast) {
               pv0 = (j0 + 2 * i2 <= lim) ? pv0 : 0.0f;
               pv1 = (j0 + 2 * i2 + 1 <= lim) ? pv1 : 0.0f;

@@ -234,8 +234,8 @@ ot_attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       if (fast) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const float e0 = ex2_approx(fmaf(__uint_as_float(v[2 * i]), p.scale_log2, -mb));
-          const float e1 = ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), p.scale_log2, -mb));
+          const float e0 = ex2_mixed(fmaf(__uint_as_float(v[2 * i]), p.scale_log2, -mb), 2 * i);
+          const float e1 = ex2_mixed(fmaf(__uint_as_float(v[2 * i + 1]), p.scale_log2, -mb), 2 * i + 1);
           rowsum += e0 + e1;
           pk[i] = pack_bf16x2(e0, e1);
         }
@@ -245,8 +245,8 @@ ot_attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       } else {
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          float e0 = ex2_approx(fmaf(__uint_as_float(v[2 * i]), p.scale_log2, -mb));
-          float e1 = ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), p.scale_log2, -mb));
+          float e0 = ex2_mixed(fmaf(__uint_as_float(v[2 * i]), p.scale_log2, -mb), 2 * i);
+          float e1 = ex2_mixed(fmaf(__uint_as_float(v[2 * i + 1]), p.scale_log2, -mb), 2 * i + 1);
           e0 = (2 * i <= lim) ? e0 : 0.0f;
           e1 = (2 * i + 1 <= lim) ? e1 : 0.0f;
           rowsum += e0 + e1;

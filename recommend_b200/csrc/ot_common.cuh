@@ -347,6 +347,23 @@ __device__ __forceinline__ float ex2_poly(float x) {
   return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));   // p * 2^round(x)
 }
 
+// The i-th exponential of an unrolled softmax loop.  OT_EX2_POLY_MODE (compile time, default 0 = every exponential on the MUFU pipe,
+// the verified build): 1 sends every second one to ex2_poly, 2 every fourth.  An experiment switch for round 2
+// (OT_NVCC_EXTRA="-DOT_EX2_POLY_MODE=1" recommend_b200/csrc/build.sh); `i` is a compile-time constant after unrolling.
+#ifndef OT_EX2_POLY_MODE
+#define OT_EX2_POLY_MODE 0
+#endif
+__device__ __forceinline__ float ex2_mixed(float x, int i) {
+#if OT_EX2_POLY_MODE == 1
+  return (i & 1) ? ex2_poly(x) : ex2_approx(x);
+#elif OT_EX2_POLY_MODE == 2
+  return ((i & 3) == 3) ? ex2_poly(x) : ex2_approx(x);
+#else
+  (void)i;
+  return ex2_approx(x);
+#endif
+}
+
 // Counter-based dropout mask (Keras inverted dropout, OT/model.py:184,193,198): one 32-bit hash decides the two
 // elements (row, col) and (row, col+1), col even; an element is kept iff its 16-bit lane >= thr16 = round(rate*65536).
 // The forward epilogue and the backward mask kernel evaluate the same function, so no mask is ever stored.
