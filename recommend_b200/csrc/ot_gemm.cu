@@ -38,6 +38,9 @@ static constexpr int EPI_BAR_ID = 1;         // named barriers 1..4: one per epi
 static constexpr int EPI_BAR_NORM = 5;       // 5..8: the sets working on one tile (row statistics of the fused RMSNorm)
 static constexpr int CHUNK = 64;             // epilogue column chunk (128 bytes of bf16 per row)
 static constexpr int CH_BYTES = 128 * 64 * 2;   // one staged chunk: 128 rows x 128 bytes
+#ifndef OT_DUAL_LATE_WAIT
+#define OT_DUAL_LATE_WAIT 0     // experiment switch, see the dual-output pass of the epilogue; 0 = the verified build
+#endif
 static constexpr int TILE_SLOTS = 8;         // tile-index ring: producer -> MMA issuer and epilogue warps
 
 struct GemmSegDev {
@@ -378,10 +381,20 @@ ot_mixed_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const int n_pass = dual ? 2 : 1;
 #pragma unroll 1
         for (int pass = 0; pass < n_pass; ++pass) {
+#if OT_DUAL_LATE_WAIT
+          // experiment switch (round 2): when nothing is read from the staging tile, wait for the drain of the pre-activation
+          // store only right before pass 1 first WRITES the tile, so its TMEM load and GELU arithmetic overlap the drain
+          const bool late_wait = !tile_in;
+          if (pass == 1 && !late_wait) {
+            if (tma_out && io_thread) bulk_wait_read0();
+            named_bar_sync(bar_id, EPI_SET_THREADS);
+          }
+#else
           if (pass == 1) {                       // pre-activation rows have left the staging tile
             if (tma_out && io_thread) bulk_wait_read0();
             named_bar_sync(bar_id, EPI_SET_THREADS);
           }
+#endif
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
             uint32_t v[32];
@@ -457,6 +470,12 @@ ot_mixed_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 #pragma unroll
               for (int j = 0; j < 16; ++j) ss2 = fma2(f[j], f[j], ss2);
             }
+#if OT_DUAL_LATE_WAIT
+            if (pass == 1 && late_wait && half == 0) {
+              if (tma_out && io_thread) bulk_wait_read0();
+              named_bar_sync(bar_id, EPI_SET_THREADS);
+            }
+#endif
             // each thread (over)writes only its own row of the staging tile
 #pragma unroll
             for (int ch = 0; ch < 4; ++ch) {
