@@ -261,6 +261,46 @@ def weight_paths(root):
     return out
 
 
+def run_gradient_case(C, M, name, seed):
+    """Gradients of the summed BCE (OT/train.py:124-128; the loss expression is the oracle's restatement of Keras BinaryCrossentropy)
+    through the REFERENCE's forward graph, by torch autograd on the shim's tensors - what ``tape.gradient`` (OT/train.py:131) returns."""
+    from oracle import onetrans_oracle as O
+    cfg = small_config(C, 2, False)
+    tf_shim.set_seed(seed)
+    model = M.OneTransModel(cfg)
+    non_seq, seq = inputs(cfg, 3, (5, 4, 3), seed + 100)
+    with torch.no_grad():
+        model(non_seq, seq, training=False)
+        perturb(model, seed + 200)
+    live = [w for w in model.trainable_weights]
+    for w in live:
+        w.requires_grad_(True)
+    g = torch.Generator().manual_seed(seed + 300)
+    labels = {t: (torch.rand(3, 1, generator=g) < 0.5).to(tf_shim.FLOAT) for t in cfg.tasks}
+    out = model(non_seq, seq, training=False)
+    loss = O.bce_loss(out, labels, cfg.tasks)
+    loss.backward()
+    P = export_params(model, cfg)
+    saved = {id(w): (w.grad if w.grad is not None else torch.zeros_like(w)) for w in live}
+    for w in live:
+        w.requires_grad_(False)
+    swap = {id(w): w.detach().clone() for w in live}
+    with torch.no_grad():
+        for w in live:
+            w.copy_(saved[id(w)])          # export the gradients with the parameter exporter, then put the weights back
+        G = {k: v.detach().clone() for k, v in export_params(model, cfg).items()}
+        for w in live:
+            w.copy_(swap[id(w)])
+    arrays = {f'{name}/in/non_seq/{k}': v for k, v in non_seq.items()}
+    arrays.update({f'{name}/in/seq/{k}': v for k, v in seq.items()})
+    arrays.update({f'{name}/in/label/{k}': v for k, v in labels.items()})
+    arrays.update({f'{name}/param/{k}': v.detach() for k, v in P.items()})
+    arrays.update({f'{name}/grad/{k}': v for k, v in G.items()})
+    arrays[f'{name}/out/loss'] = loss.detach().reshape(1)
+    return arrays, {'hidden_dim': cfg.hidden_dim, 'num_heads': cfg.num_heads, 'ffn_dim': cfg.ffn_dim, 'num_layers': cfg.num_layers,
+                    'num_ns_tokens': cfg.num_ns_tokens, 'pyramid_enabled': cfg.pyramid_enabled, 'pyramid_ratios': list(cfg.pyramid_ratios)}
+
+
 def expected_failure(fn):
     try:
         fn()
@@ -293,6 +333,9 @@ def main():
     a, meta = run_block_case(C, M, 3)
     arrays.update(a)
     facts['cases']['block'] = meta
+    a, meta = run_gradient_case(C, M, 'K_gradients', 11)
+    arrays.update(a)
+    facts['cases']['K_gradients'] = meta
 
     from tests.helpers import REFERENCE_KERNEL_CASES, REFERENCE_CPU_CASES
     for name, spec in {**REFERENCE_KERNEL_CASES, **REFERENCE_CPU_CASES}.items():

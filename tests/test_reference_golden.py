@@ -192,3 +192,22 @@ def test_baseline_config_1_forward_and_loss_match_the_reference_at_full_size():
         assert float((out[t].double() - want).abs().max()) < 5e-6
         y = (torch.rand(32, 1, generator=g) < 0.5).float()
         assert float(O.bce_loss({t: out[t]}, {t: y}, [t])) == pytest.approx(float(O.bce_loss({t: want}, {t: y.double()}, [t])), rel=1e-5)
+
+
+def test_oracle_gradients_equal_autograd_through_the_reference_forward():
+    """``tape.gradient`` of OT/train.py:131: the summed BCE differentiated through the reference's own forward graph (torch autograd on
+    the shim's tensors) against the oracle's ``loss_and_grads`` in its literal mode - every parameter tensor, packed as the GPU parity
+    tests compare them."""
+    meta = FACTS['cases']['K_gradients']
+    cfg = _oracle_cfg(meta)
+    cfg.dropout_rate = 0.0
+    P, G = _group('K_gradients/param/'), _group('K_gradients/grad/')
+    non_seq, seq, labels = _group('K_gradients/in/non_seq/'), _group('K_gradients/in/seq/'), _group('K_gradients/in/label/')
+    loss, grads, _ = O.loss_and_grads(P, cfg, non_seq, seq, labels, query_mode='literal_gather', literal_loop=True)
+    assert float(loss) == pytest.approx(float(Z['K_gradients/out/loss'][0]), rel=1e-13)
+    assert set(G) == set(P) and len(G) > 20
+    for name, want in G.items():
+        got = grads[name]
+        assert got.shape == want.shape, name
+        assert torch.allclose(got, want, rtol=0, atol=1e-12 + 1e-10 * float(want.abs().max())), (name, float((got - want).abs().max()))
+    assert float(G['blocks.0.attention.Wq'][0].abs().max()) > 0 and float(G['tokenizer.sep_embedding'].abs().max()) > 0
