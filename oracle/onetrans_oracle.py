@@ -20,7 +20,9 @@ oracle/tf_shim.py standing in for the ~30 TensorFlow ops they call, runs ``OneTr
 (tests/golden/reference_golden.{npz,json}).  tests/test_reference_golden.py holds this oracle to them at 1e-12 (fp64) in its literal
 modes (``ns_param_alignment='head_literal'``, ``query_mode='literal_gather'``, per-token loop) - so the control flow that decides
 results is the reference's, executed; only what each TensorFlow op computes is restated (in the shim, from the documented TF 2.12
-semantics of SURVEY.md §A.2).  The same run reproduces defects D2 and D9 as the exceptions the reference raises.  The repaired
+semantics of SURVEY.md §A.2).  Also from the reference's code: BASELINE config 1 at full size (fp32 oracle within 5e-6 of its
+probabilities), gradients of the summed BCE through its forward graph (every parameter tensor, 1e-12), parameter counts, the Keras
+weight order.  The same run reproduces defects D2, D6, D7, D8 and D9 as the exceptions the reference raises.  The repaired
 modes the product uses are tied to the literal ones by the algebraic invariants in tests/test_oracle.py (T4 tail-only ==
 compute-all-then-gather, T5 grouped == per-token loop, T6 causality, hand-computed RMSNorm / BCE vectors) and by the golden vectors
 this file generated itself (tests/golden/oracle_golden.json, script tests/golden/make_golden.py).
