@@ -236,7 +236,7 @@ class Dropout(Layer):
     def call(self, x, training=False):
         if not training or self.rate <= 0.0:
             return x
-        keep = (torch.rand(x.shape, generator=_GEN, dtype=FLOAT) >= self.rate).to(x.dtype)
+        keep = (torch.rand(x.shape, generator=_GEN, dtype=torch.float32) >= self.rate).to(x.dtype)    # fp32 draws, as the oracle's _dropout
         return x * keep / (1.0 - self.rate)
 
 

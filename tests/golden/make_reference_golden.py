@@ -333,6 +333,24 @@ def main():
     a, meta = run_block_case(C, M, 3)
     arrays.update(a)
     facts['cases']['block'] = meta
+    # training=True: where the reference places its two dropouts per block (OT/model.py:193,198) - the shim's Dropout draws
+    # torch.rand(shape, fp32) >= rate from a generator reseeded right before the call, the stream the oracle's _dropout consumes
+    cfg = small_config(C, 2, False)
+    tf_shim.set_seed(12)
+    drop_model = M.OneTransModel(cfg)
+    non_seq, seq = inputs(cfg, 3, (5, 4, 3), 112)
+    with torch.no_grad():
+        drop_model(non_seq, seq, training=False)
+        perturb(drop_model, 212)
+        tf_shim.set_seed(777)
+        out = drop_model(non_seq, seq, training=True)
+    arrays.update({f'L_dropout/in/non_seq/{k}': v for k, v in non_seq.items()})
+    arrays.update({f'L_dropout/in/seq/{k}': v for k, v in seq.items()})
+    arrays.update({f'L_dropout/param/{k}': v for k, v in export_params(drop_model, cfg).items()})
+    arrays.update({f'L_dropout/out/prob/{t}': v for t, v in out.items()})
+    facts['cases']['L_dropout'] = {'hidden_dim': cfg.hidden_dim, 'num_heads': cfg.num_heads, 'ffn_dim': cfg.ffn_dim, 'num_layers': cfg.num_layers,
+                                   'num_ns_tokens': cfg.num_ns_tokens, 'pyramid_enabled': False, 'pyramid_ratios': list(cfg.pyramid_ratios),
+                                   'dropout_rate': cfg.dropout_rate, 'dropout_seed': 777}
     a, meta = run_gradient_case(C, M, 'K_gradients', 11)
     arrays.update(a)
     facts['cases']['K_gradients'] = meta

@@ -211,3 +211,19 @@ def test_oracle_gradients_equal_autograd_through_the_reference_forward():
         assert got.shape == want.shape, name
         assert torch.allclose(got, want, rtol=0, atol=1e-12 + 1e-10 * float(want.abs().max())), (name, float((got - want).abs().max()))
     assert float(G['blocks.0.attention.Wq'][0].abs().max()) > 0 and float(G['tokenizer.sep_embedding'].abs().max()) > 0
+
+
+def test_dropout_placement_equals_the_reference_in_training_mode():
+    """training=True through the reference (OT/model.py:193,198: one Dropout layer applied to the attention branch, then to the FFN
+    branch, per block, on the full-length tensors) with the mask stream seeded identically on both sides."""
+    meta = FACTS['cases']['L_dropout']
+    cfg = _oracle_cfg(meta)
+    cfg.dropout_rate = meta['dropout_rate']
+    P, non_seq, seq = _group('L_dropout/param/'), _group('L_dropout/in/non_seq/'), _group('L_dropout/in/seq/')
+    out = O.model_forward(P, cfg, non_seq, seq, training=True, query_mode='literal_gather', literal_loop=True,
+                          gen=torch.Generator().manual_seed(meta['dropout_seed']))
+    plain = O.model_forward(P, cfg, non_seq, seq, training=False, query_mode='literal_gather')
+    for t in cfg.tasks:
+        want = torch.from_numpy(Z[f'L_dropout/out/prob/{t}'])
+        assert torch.allclose(out[t], want, rtol=0, atol=1e-12), float((out[t] - want).abs().max())
+        assert float((plain[t] - want).abs().max()) > 1e-4                      # the masks did something
