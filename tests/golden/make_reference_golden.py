@@ -387,6 +387,33 @@ def main():
         arrays[f'seqproc/{tag}/out'] = torch.from_numpy(np.asarray(sp.process_sequence(raw, 'click_seq'), dtype=np.float64))
     facts['cases']['seqproc'] = {'max_seq_len': 6}
 
+    # OT/examples/inference_example.py cannot be imported (its annotations use Dict / Tuple without importing them, D11), but its method
+    # bodies are plain Python: compile the reference's own function definitions out of the file and run them on a bare object
+    import ast
+    import typing
+    tree = ast.parse(open(os.path.join(REF, 'examples', 'inference_example.py')).read())
+    klass = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == 'OneTransInferenceEngine')
+    wanted = [n for n in klass.body if isinstance(n, ast.FunctionDef) and n.name in ('_update_stats', 'get_stats', 'reset_stats', 'preprocess_input')]
+    ns = {'Dict': typing.Dict, 'Tuple': typing.Tuple, 'List': typing.List, 'np': np}
+    exec(compile(ast.Module(body=wanted, type_ignores=[]), 'inference_example.py', 'exec'), ns)
+    Eng = type('Eng', (), {k: ns[k] for k in ('_update_stats', 'get_stats', 'reset_stats', 'preprocess_input')})
+    eng = Eng()
+    eng.config = dcfg                                   # max_seq_len = 6
+    eng.reset_stats()
+    trace = []
+    for success, latency, n in ((True, 12.0, 1), (True, 30.0, 4), (False, 0.0, 2), (True, 5.5, 3)):
+        eng._update_stats(success, latency, n)
+        trace.append(dict(eng.get_stats()))
+    eng.reset_stats()
+    rng2 = np.random.default_rng(5)
+    seqs = {'click_seq': rng2.standard_normal((4, 64)), 'cart_seq': rng2.standard_normal((9, 64)).tolist(), 'purchase_seq': rng2.standard_normal((6, 64))}
+    ns_out, seq_out = eng.preprocess_input({'user_id': 1.0}, {'item_id': 2.0, 'price': 3.5}, {'time': 0.25}, seqs)
+    facts['cases']['inference_engine'] = {'stats_trace': trace, 'stats_after_reset': dict(eng.get_stats()), 'merged_non_seq': ns_out,
+                                          'calls': [[True, 12.0, 1], [True, 30.0, 4], [False, 0.0, 2], [True, 5.5, 3]]}
+    for k, v in seqs.items():
+        arrays[f'engine/in/{k}'] = torch.from_numpy(np.asarray(v, dtype=np.float64))
+        arrays[f'engine/out/{k}'] = torch.from_numpy(np.asarray(seq_out[k], dtype=np.float64))
+
     # OT/data_loader.py:13-65 FeatureProcessor: pandas statistics, numpy standardisation, tf.one_hot
     import pandas as pd
     rng = np.random.default_rng(3)

@@ -227,3 +227,27 @@ def test_dropout_placement_equals_the_reference_in_training_mode():
         want = torch.from_numpy(Z[f'L_dropout/out/prob/{t}'])
         assert torch.allclose(out[t], want, rtol=0, atol=1e-12), float((out[t] - want).abs().max())
         assert float((plain[t] - want).abs().max()) > 1e-4                      # the masks did something
+
+
+def test_inference_engine_bookkeeping_equals_the_reference_method_bodies():
+    """``_update_stats`` / ``get_stats`` / ``reset_stats`` / ``preprocess_input`` of OT/examples/inference_example.py:62-92, 186-219,
+    compiled from the reference file (the module itself cannot be imported, D11) and run; against ``OneTransInferenceEngine``."""
+    f = FACTS['cases']['inference_engine']
+    cfg = R.OneTransConfig()
+    cfg.max_seq_len = FACTS['cases']['seqproc']['max_seq_len']
+    eng = R.OneTransInferenceEngine.__new__(R.OneTransInferenceEngine)
+    eng.config, eng.pad_sequences = cfg, True
+    eng.reset_stats()
+    for (success, latency, n), want in zip(f['calls'], f['stats_trace']):
+        eng._update_stats(success, latency, n)
+        got = eng.get_stats()
+        assert set(got) == set(want)
+        for k in want:
+            assert got[k] == pytest.approx(want[k], rel=1e-12), (k, got, want)
+    eng.reset_stats()
+    assert eng.get_stats() == f['stats_after_reset']
+    seqs = {k[len('engine/in/'):]: torch.from_numpy(Z[k]) for k in Z.files if k.startswith('engine/in/')}
+    non_seq, seq = eng.preprocess_input({'user_id': 1.0}, {'item_id': 2.0, 'price': 3.5}, {'time': 0.25}, seqs)
+    assert non_seq == f['merged_non_seq']
+    for k, v in seq.items():
+        assert torch.equal(v.double(), torch.from_numpy(Z[f'engine/out/{k}']).float().double()), k
