@@ -414,6 +414,54 @@ def main():
         arrays[f'engine/in/{k}'] = torch.from_numpy(np.asarray(v, dtype=np.float64))
         arrays[f'engine/out/{k}'] = torch.from_numpy(np.asarray(seq_out[k], dtype=np.float64))
 
+    # OT/train.py:186-279 - the epoch loop (best-model / periodic / final checkpoints, early stopping, history, metric resets) is plain
+    # Python around train_step / val_step / save_model: compile the reference's own `train` method and drive it with scripted losses
+    ttree = ast.parse(open(os.path.join(REF, 'train.py')).read())
+    tklass = next(n for n in ttree.body if isinstance(n, ast.ClassDef) and n.name == 'OneTransTrainer')
+    train_def = next(n for n in tklass.body if isinstance(n, ast.FunctionDef) and n.name == 'train')
+    import time as _time
+    tns = {'Dict': typing.Dict, 'Optional': typing.Optional, 'DataLoader': object, 'np': np, 'time': _time, 'print': lambda *a, **k: None}
+    exec(compile(ast.Module(body=[train_def], type_ignores=[]), 'train.py', 'exec'), tns)
+
+    class _Num:
+        def __init__(self, v): self.v = v
+        def numpy(self): return self.v
+
+    class _Metric:
+        def __init__(self, log, name): self.log, self.name, self.n = log, name, 0
+        def result(self): return _Num(float(self.n))
+        def reset_states(self): self.log.append('reset:' + self.name); self.n += 1
+
+    class _Loader:
+        def __init__(self, n): self.n = n
+        def get_train_dataset(self): return list(range(self.n))
+        def get_val_dataset(self): return list(range(2))
+
+    def drive(val_script, epochs, save_freq, patience, with_val=True):
+        log = []
+        T = type('T', (), {'train': tns['train']})
+        t = T()
+        t.config = 'cfg'
+        t.history = {'train_loss': [], 'val_loss': [], 'train_metrics': {}, 'val_metrics': {}}
+        t.train_metrics = {'ctr_auc': _Metric(log, 'train')}
+        t.val_metrics = {'ctr_auc': _Metric(log, 'val')}
+        state = {'epoch': -1, 'step': 0}
+        def train_step(batch):
+            if batch == 0:
+                state['epoch'] += 1
+            return {'total_loss': _Num(1.0 / (1 + state['epoch']) + 0.01 * batch)}
+        def val_step(batch):
+            return {'total_loss': _Num(val_script[state['epoch']] + 0.001 * batch)}
+        t.train_step, t.val_step = train_step, val_step
+        t.save_model = lambda name: log.append('save:' + name)
+        hist = t.train(_Loader(3), _Loader(3) if with_val else None, epochs=epochs, save_freq=save_freq, early_stopping_patience=patience)
+        return {'log': log, 'train_loss': [float(v) for v in hist['train_loss']], 'val_loss': [float(v) for v in hist['val_loss']],
+                'epochs_run': len(hist['train_loss']), 'metric_epochs': sorted(int(k) for k in hist['val_metrics'])}
+    facts['cases']['trainer_loop'] = {
+        'early_stop': dict(args=dict(val_script=[1.0, 0.8, 0.9, 0.85, 0.95, 0.7, 0.6], epochs=7, save_freq=2, patience=3), **drive([1.0, 0.8, 0.9, 0.85, 0.95, 0.7, 0.6], 7, 2, 3)),
+        'runs_out': dict(args=dict(val_script=[1.0, 0.9, 0.8, 0.7], epochs=4, save_freq=1, patience=5), **drive([1.0, 0.9, 0.8, 0.7], 4, 1, 5)),
+        'no_val': dict(args=dict(val_script=[0, 0, 0], epochs=3, save_freq=3, patience=5, with_val=False), **drive([0, 0, 0], 3, 3, 5, with_val=False))}
+
     # OT/data_loader.py:13-65 FeatureProcessor: pandas statistics, numpy standardisation, tf.one_hot
     import pandas as pd
     rng = np.random.default_rng(3)

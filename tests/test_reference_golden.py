@@ -251,3 +251,47 @@ def test_inference_engine_bookkeeping_equals_the_reference_method_bodies():
     assert non_seq == f['merged_non_seq']
     for k, v in seq.items():
         assert torch.equal(v.double(), torch.from_numpy(Z[f'engine/out/{k}']).float().double()), k
+
+
+@pytest.mark.parametrize('script', ['early_stop', 'runs_out', 'no_val'])
+def test_trainer_epoch_loop_equals_the_reference_train_method(script, capsys):
+    """OT/train.py:186-279 compiled from the reference file and driven with scripted losses: which checkpoints are written when
+    (``best_model`` on improvement, ``model_epoch_k`` every ``save_freq``, ``final_model``), when early stopping ends the run, when the
+    metrics are reset, and the loss history - against ``OneTransTrainer.train`` driven by the same script (no GPU involved)."""
+    from recommend_b200.train import OneTransTrainer
+    want = FACTS['cases']['trainer_loop'][script]
+    a = want['args']
+    log = []
+
+    class Metrics:
+        def __init__(self, name): self.name = name
+        def result(self): return {}
+        def reset_states(self): log.append('reset:' + self.name)
+
+    class Loader:
+        def get_train_dataset(self): return list(range(3))
+        def get_val_dataset(self): return list(range(2))
+
+    class Model:
+        def train(self): pass
+        def eval(self): pass
+
+    t = OneTransTrainer.__new__(OneTransTrainer)
+    t.config, t.model = None, Model()
+    t.history = {'train_loss': [], 'val_loss': [], 'train_metrics': {}, 'val_metrics': {}}
+    t.train_metrics, t.val_metrics = Metrics('train'), Metrics('val')
+    state = {'epoch': -1}
+
+    def train_step(batch):
+        if batch == 0:
+            state['epoch'] += 1
+        return {'total_loss': torch.tensor(1.0 / (1 + state['epoch']) + 0.01 * batch, dtype=torch.float64)}
+    t.train_step = train_step
+    t.val_step = lambda batch: {'total_loss': torch.tensor(a['val_script'][state['epoch']] + 0.001 * batch, dtype=torch.float64)}
+    t.save_model = lambda name: log.append('save:' + name)
+    hist = t.train(Loader(), Loader() if a.get('with_val', True) else None, epochs=a['epochs'], save_freq=a['save_freq'],
+                   early_stopping_patience=a['patience'], log_every=0)
+    assert log == want['log']
+    assert len(hist['train_loss']) == want['epochs_run']
+    assert hist['train_loss'] == pytest.approx(want['train_loss'], rel=1e-12) and hist['val_loss'] == pytest.approx(want['val_loss'], rel=1e-12)
+    assert sorted(hist['val_metrics']) == want['metric_epochs']
