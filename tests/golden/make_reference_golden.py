@@ -462,6 +462,27 @@ def main():
         'runs_out': dict(args=dict(val_script=[1.0, 0.9, 0.8, 0.7], epochs=4, save_freq=1, patience=5), **drive([1.0, 0.9, 0.8, 0.7], 4, 1, 5)),
         'no_val': dict(args=dict(val_script=[0, 0, 0], epochs=3, save_freq=3, patience=5, with_val=False), **drive([0, 0, 0], 3, 3, 5, with_val=False))}
 
+    # OT/evaluate.py:131-169 (A/B arithmetic) and :231-282 (placeholder feature importance): plain Python around evaluate_offline
+    etree = ast.parse(open(os.path.join(REF, 'evaluate.py')).read())
+    eklass = next(n for n in etree.body if isinstance(n, ast.ClassDef) and n.name == 'OneTransEvaluator')
+    edefs = [n for n in eklass.body if isinstance(n, ast.FunctionDef) and n.name in ('evaluate_ab_test', 'analyze_feature_importance')]
+    ens = {'Dict': typing.Dict, 'Any': typing.Any, 'DataLoader': object, 'tf': tf_shim, 'print': lambda *a, **k: None}
+    exec(compile(ast.Module(body=edefs, type_ignores=[]), 'evaluate.py', 'exec'), ens)
+    EV = type('EV', (), {k: ens[k] for k in ('evaluate_ab_test', 'analyze_feature_importance')})
+    ab_cases = {}
+    for tag, (c, t) in {'gain': (0.70, 0.721), 'small': (0.70, 0.703), 'loss': (0.8, 0.75), 'zero_control': (0.0, 0.5)}.items():
+        ev = EV()
+        ev.evaluate_offline = lambda loader, kind, _v={'control': c, 'treatment': t}: {'ctr_auc': _v[loader]}
+        r = ev.evaluate_ab_test('control', 'treatment')
+        ab_cases[tag] = {'control': c, 'treatment': t, 'result': {k: (bool(v) if isinstance(v, (bool, np.bool_)) else v) for k, v in r.items()}}
+    ev = EV()
+    ev.config = C.OneTransConfig()
+    ev.model = lambda *a, **k: {}
+    ev.evaluate_offline = lambda loader, kind: {'ctr_auc': 0.7}
+    class _DS:
+        def get_test_dataset(self): return []
+    facts['cases']['evaluator_logic'] = {'ab': ab_cases, 'feature_importance': ev.analyze_feature_importance(_DS())}
+
     # OT/data_loader.py:13-65 FeatureProcessor: pandas statistics, numpy standardisation, tf.one_hot
     import pandas as pd
     rng = np.random.default_rng(3)

@@ -295,3 +295,22 @@ def test_trainer_epoch_loop_equals_the_reference_train_method(script, capsys):
     assert len(hist['train_loss']) == want['epochs_run']
     assert hist['train_loss'] == pytest.approx(want['train_loss'], rel=1e-12) and hist['val_loss'] == pytest.approx(want['val_loss'], rel=1e-12)
     assert sorted(hist['val_metrics']) == want['metric_epochs']
+
+
+def test_evaluator_ab_arithmetic_and_placeholder_importance_equal_the_reference_methods():
+    """OT/evaluate.py:131-169 and :231-282 compiled from the reference file and driven with stubbed ``evaluate_offline`` results."""
+    from recommend_b200.evaluate import OneTransEvaluator
+    f = FACTS['cases']['evaluator_logic']
+    for tag, case in f['ab'].items():
+        ev = OneTransEvaluator.__new__(OneTransEvaluator)
+        ev.evaluate_offline = lambda loader, kind, _v={'control': case['control'], 'treatment': case['treatment']}: {'ctr_auc': _v[loader]}
+        got = ev.evaluate_ab_test('control', 'treatment')
+        assert set(got) == set(case['result']), tag
+        for k, want in case['result'].items():
+            assert (got[k] == pytest.approx(want, rel=1e-12)) if isinstance(want, float) else (got[k] == want), (tag, k, got[k], want)
+    ev = OneTransEvaluator.__new__(OneTransEvaluator)
+    ev.config = R.OneTransConfig()
+    got = ev.analyze_feature_importance(None)
+    assert set(got) == set(f['feature_importance'])
+    for k, want in f['feature_importance'].items():
+        assert got[k] == pytest.approx(want, rel=1e-12), k
