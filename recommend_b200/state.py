@@ -156,8 +156,13 @@ def save_weights(model, path) -> None:
 
 
 def load_weights(model, path) -> None:
+    """Reads a file written by ``save_weights`` (names are checked against this model), or a TensorFlow-side
+    ``np.savez(path, *reference_model.get_weights())`` (keys ``arr_0, arr_1, ...``: positional, shapes are checked one by one)."""
     import numpy as np
     with np.load(path) as z:
+        if z.files and all(k.startswith('arr_') for k in z.files):
+            load_keras_weight_list(model, [z[f'arr_{i}'] for i in range(len(z.files))])
+            return
         keys = sorted(z.files)
         want = [name for name, _, _ in _keras_entries(model)]
         got = [k.split(':', 1)[1] for k in keys]

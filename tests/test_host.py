@@ -277,6 +277,14 @@ def test_keras_weight_order_and_checkpoint_roundtrip(tmp_path):
             p.normal_()
     state.load_weights(m2, tmp_path / 'w.npz')
     assert all(torch.equal(a, b) for a, b in zip(m.parameters(), m2.parameters()))
+    # the TensorFlow-side export: np.savez(path, *model.get_weights()) -> positional arr_i keys
+    np.savez(tmp_path / 'tf_side.npz', *[a for _, a in wl])
+    m3 = R.OneTransModel(cfg)
+    with torch.no_grad():
+        for p in m3.parameters():
+            p.normal_()
+    state.load_weights(m3, tmp_path / 'tf_side.npz')
+    assert all(torch.equal(a, b) for a, b in zip(m.parameters(), m3.parameters()))
     with pytest.raises(ValueError):
         state.load_keras_weight_list(m2, [a for _, a in wl][:-1])
     cfg3 = R.get_model_config('small')
