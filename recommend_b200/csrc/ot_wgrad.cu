@@ -12,6 +12,7 @@
 //   warp 0 lane*: TMA producer     warp 1 lane*: MMA issuer     all 4 warps: epilogue
 //   warps 2-3 (CTAs of the first M tile, when asked): column sums of the Q tiles as they pass through shared
 //   memory - the bias gradient of the same Dense layer without a second pass over Q
+#include <stdlib.h>
 #include "ot_common.cuh"
 #include "ot_host.h"
 #include "../../include/onetrans_b200.h"
@@ -257,7 +258,10 @@ int wgrad_impl(const ot_wgrad_params* p, cudaStream_t st) {
   kp.vec_flush = (p->c_stride_n == 1 && (p->c_stride_m % 4) == 0 && (p->c_group_stride % 4) == 0 &&
                   (reinterpret_cast<uintptr_t>(p->C) & 15) == 0) ? 1 : 0;
   const int tiles = kp.m_tiles * kp.n_tiles;
-  const int target = p->target_ctas > 0 ? p->target_ctas : 2 * num_sms();
+  // default: two CTAs' worth of row slices per SM.  OT_WGRAD_WAVES (read once) is an experiment switch for round 2: more, shorter
+  // slices trade accumulator flushes (fp32 reductions) for a shorter tail; unset = the verified behaviour
+  static const int waves = [] { const char* e = getenv("OT_WGRAD_WAVES"); const int w = e ? atoi(e) : 0; return (w >= 1 && w <= 16) ? w : 2; }();
+  const int target = p->target_ctas > 0 ? p->target_ctas : waves * num_sms();
 
   // total k-blocks over all outputs, to size the slices evenly
   long long total_kb = 0;

@@ -22,3 +22,13 @@ print('ms/step %.2f  gemm %.2f  attn_fwd %.2f  attn_bwd %.2f' % (d['ms_per_step'
 done
 rm -f $OBJS
 bash recommend_b200/csrc/build.sh > /dev/null 2>&1 && echo "default build restored"
+# run-time switches of the default build (no rebuild): row slices per SM in the weight-gradient kernel
+for waves in 3 4; do
+  echo "== default build, OT_WGRAD_WAVES=$waves"
+  OT_WGRAD_WAVES=$waves timeout 200 python -m pytest tests/test_gpu_kernels.py -q -m gpu -x -k "wgrad" 2>&1 | tail -1
+  OT_WGRAD_WAVES=$waves timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline 2>/dev/null | tail -1 | python -c "
+import json,sys
+d=json.loads(sys.stdin.read())
+k={x['kernel']:x['ms_per_step'] for x in d.get('kernels',[])}
+print('ms/step %.2f  wgrad %.2f' % (d['ms_per_step'], k.get('ot_wgrad',0)))" | tee gpurun_out/ab_bench_wgrad_$waves.log
+done
