@@ -168,7 +168,7 @@ def run_reference_arm(args, wl, rank):
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': config_dict(args, wl, wl['B']),      # the GPU arm's workload; each CPU step is a bounded sample of it (cpu_baseline.sample)
         'cpu_baseline': {'value': v, 'unit': 'samples/s', 'cores': cores, 'kind': 'port',
-                         'sample': f'oracle (PyTorch CPU fp32 restatement of OT/model.py; TensorFlow reference not installable) fwd+BCE+bwd on {sample_B} '
+                         'sample': f'oracle (PyTorch CPU fp32 restatement of OT/model.py, held at 1e-12 to vectors produced by the reference code itself over a TensorFlow-op shim; TensorFlow itself is not installable) fwd+BCE+bwd on {sample_B} '
                                    f'samples of the same workload per step; structure: {args.cpu_variant}'},
         'e2e': {'value': v, 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
@@ -401,7 +401,7 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             v, ms, cores = cpu_oracle_samples_per_sec(wl, args.cpu_sample_batch, 6, 1, args.dropout)
             line['cpu_baseline'] = {'value': v, 'unit': 'samples/s', 'cores': cores, 'kind': 'port',
-                                    'sample': f'oracle (PyTorch CPU fp32 restatement of OT/model.py) fwd+BCE+bwd, 6 timed steps (1 warm-up) of '
+                                    'sample': f'oracle (PyTorch CPU fp32 restatement of OT/model.py, held at 1e-12 to vectors produced by the reference code itself over a TensorFlow-op shim) fwd+BCE+bwd, 6 timed steps (1 warm-up) of '
                                               f'{args.cpu_sample_batch} samples of the same workload'}
         print(json.dumps(line), flush=True)
     if world > 1:

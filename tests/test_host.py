@@ -374,3 +374,14 @@ def test_polynomial_exp2_building_block():
     assert np.abs(f).max() <= 0.5
     assert (np.abs(y.astype(np.float64) - ref) / ref).max() < 8e-5
     assert ex2_poly(np.array([-1000.0], np.float32))[0][0] < 2e-38          # far below the running maximum: as good as zero
+
+
+def test_driver_facing_scripts_compile():
+    """bench.py, __graft_entry__.py, the profiling scripts and the examples must at least be valid Python (the GPU arm cannot run here)."""
+    import glob, py_compile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    files = [os.path.join(root, 'bench.py'), os.path.join(root, '__graft_entry__.py')] + glob.glob(os.path.join(root, 'profiles', '*.py')) + \
+        glob.glob(os.path.join(root, 'examples', '*.py')) + glob.glob(os.path.join(root, 'recommend_b200', '*.py'))
+    assert len(files) > 20
+    for f in files:
+        py_compile.compile(f, doraise=True)
