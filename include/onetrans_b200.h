@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define OT_ABI_VERSION 10
+#define OT_ABI_VERSION 11
 
 int ot_version(void);
 const char* ot_last_error_string(void);
@@ -284,6 +284,15 @@ typedef struct ot_rmsprop_params {
   float* sqnorm;
   float lr, rho, momentum, eps, clip_norm, grad_scale;
   int32_t zero_grad;
+  /* Clip granularity (ABI 11).  tf.clip_by_norm runs per KERAS VARIABLE (OT/train.py:135), while a flat-buffer tensor
+   * may pack several of them: Wqkv [G, d, 3d] holds 3*G Dense kernels (q|k|v column blocks of every weight group),
+   * W1 / b1 / W2 / b2 [G, ...] hold G each.  Element `local` of tensor s belongs to clip slot
+   *     slot_base[s] + (local / slot_outer[s]) * (slot_row[s] / slot_part[s]) + (local % slot_row[s]) / slot_part[s]
+   * (slot_outer = elements per weight group, slot_row = row length, slot_part = columns per variable inside a row).
+   * seg_slot == NULL: one slot per tensor (slot == s).  seg_slot: int64 DEVICE table [n_seg][4] =
+   * {slot_base, slot_outer, slot_row, slot_part}; slot_part % 4 == 0.  sqnorm then has n_slots entries. */
+  const int64_t* seg_slot;
+  int32_t n_slots;
 } ot_rmsprop_params;
 int ot_clip_rmsprop_step(const ot_rmsprop_params* p, void* stream);
 
@@ -292,7 +301,7 @@ int ot_clip_rmsprop_step(const ot_rmsprop_params* p, void* stream);
  * all fields back to back: field f owns rows [field_off[f], field_off[f] + field_rows[f]), every row has `ef` floats.
  *   ot_embed_gather_fwd  : events[e, f*ef + j] = bf16(table[(field_off[f] + ids[e, f]) * ef + j])      (bit-exact copy)
  *   ot_embed_scatter_bwd : grad[(field_off[f] + ids[e, f]) * ef + j] += events[e, f*ef + j]   (events = d loss / d events)
- *   ot_embed_adagrad_step: once per row present in ids:  acc += g*g ; table -= lr * g / (sqrt(acc) + eps) ; g = 0
+ *   ot_embed_adagrad_step: once per row present in ids:  acc += g*g ; table -= lr * g / sqrt(acc + eps) ; g = 0
  *                          (Keras Adagrad on the summed sparse gradient; OT/config.py:39-47 sparse_optimizer / sparse_lr)
  * ids: int32 [n_events, n_fields]; ids outside [0, field_rows[f]) give a zero row and are counted in *bad_ids (may be NULL).
  * stamp: int32 [total rows], zero-initialised by the caller, step_id != 0 and different from the previous step's.

@@ -432,15 +432,28 @@ def rmsprop_step(w: torch.Tensor, g: torch.Tensor, rms: torch.Tensor, mom: Optio
     return w - inc, rms, mom
 
 
+PACKED_OVER_GROUPS = ('.attention.Wq', '.attention.Wk', '.attention.Wv', '.ffn.W1', '.ffn.b1', '.ffn.W2', '.ffn.b2')
+
+
+def clip_per_keras_variable(name, g: torch.Tensor, c: float) -> torch.Tensor:
+    """``[tf.clip_by_norm(g, c) for g in gradients]`` (OT/train.py:133-135) runs over ``model.trainable_variables``, i.e. per
+    KERAS variable.  The oracle packs the per-position Dense layers of OT/model.py:38-54 / 136-147 over a leading weight-group
+    index (0 = shared, 1+j = dedicated j): each index of those tensors is a Keras variable of its own and is clipped on its own."""
+    if isinstance(name, str) and name.endswith(PACKED_OVER_GROUPS):
+        return torch.stack([clip_by_norm(g[i], c) for i in range(g.shape[0])])
+    return clip_by_norm(g, c)
+
+
 def clip_rmsprop_update(params: Dict[str, torch.Tensor], grads: Dict[str, torch.Tensor], state: Dict[str, Dict[str, torch.Tensor]],
                         lr: float = 0.005, rho: float = 0.9, momentum: float = 0.99999, eps: float = 1e-7,
                         clip_norm: float = 90.0) -> None:
-    """OT/train.py:133-138 for every trainable tensor: ``tf.clip_by_norm`` per tensor, then ``apply_gradients``.
+    """OT/train.py:133-138 for every trainable variable: ``tf.clip_by_norm`` per Keras variable (see
+    ``clip_per_keras_variable``), then ``apply_gradients``.
     Defaults are OT/config.py:39-52 (dense_lr, momentum, gradient_clip_norm).  Updates ``params``/``state`` in place."""
     for name, w in params.items():
         g = grads[name]
         if clip_norm > 0:
-            g = clip_by_norm(g, clip_norm)
+            g = clip_per_keras_variable(name, g, clip_norm)
         st = state.setdefault(name, {'rms': torch.zeros_like(w), 'mom': torch.zeros_like(w)})
         nw, st['rms'], nm = rmsprop_step(w, g, st['rms'], st['mom'], lr, rho, momentum, eps)
         if nm is not None:
@@ -474,9 +487,10 @@ def embed_grad_table(table: torch.Tensor, vocab_sizes: Sequence[int], ids: torch
 
 def adagrad_step(w: torch.Tensor, g: torch.Tensor, acc: torch.Tensor, lr: float = 0.1, eps: float = 1e-7):
     """Keras-2.12 ``Adagrad.update_step`` (sparse_optimizer of OT/config.py:39-47; initial accumulator 0.1):
-    ``acc += g^2; w -= lr * g / (sqrt(acc) + eps)``.  Returns the new (w, acc)."""
+    ``acc += g^2; w -= lr * g / sqrt(acc + eps)`` - epsilon inside the root (the legacy TF1 op put it outside).
+    Returns the new (w, acc)."""
     acc = acc + g * g
-    return w - lr * g / (torch.sqrt(acc) + eps), acc
+    return w - lr * g / torch.sqrt(acc + eps), acc
 
 
 # ---------------------------------------------------------------------------------------------------

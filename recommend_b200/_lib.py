@@ -77,7 +77,7 @@ class RmspropParams(C.Structure):
     _fields_ = [('param_ptrs', vp), ('seg_off', vp), ('seg_numel', vp), ('n_seg', i32), ('n_flat', i64),
                 ('grad', fp), ('rms', fp), ('mom', fp), ('sqnorm', fp),
                 ('lr', C.c_float), ('rho', C.c_float), ('momentum', C.c_float), ('eps', C.c_float),
-                ('clip_norm', C.c_float), ('grad_scale', C.c_float), ('zero_grad', i32)]
+                ('clip_norm', C.c_float), ('grad_scale', C.c_float), ('zero_grad', i32), ('seg_slot', vp), ('n_slots', i32)]
 
 
 class EmbedParams(C.Structure):
@@ -110,6 +110,7 @@ class AucParams(C.Structure):
 
 METRICS_MAX_THRESHOLDS, METRICS_TAIL_WORDS, METRICS_RESULT_WORDS = 512, 8, 8  # OT_METRICS_*
 OPT_CHUNK = 1024  # OT_OPT_CHUNK
+ABI_VERSION = 11  # OT_ABI_VERSION of include/onetrans_b200.h this binding was written against
 
 # every symbol include/onetrans_b200.h declares (tests check that the library exports all of them)
 EXPORTED_SYMBOLS = [
@@ -141,6 +142,9 @@ def load() -> C.CDLL:
                 f'or recommend_b200/csrc/build.sh — there is no CPU fallback')
         lib = C.CDLL(LIB_PATH)
         lib.ot_version.restype = C.c_int
+        if lib.ot_version() != ABI_VERSION:
+            raise OneTransLibraryError(f'{LIB_PATH} has ABI version {lib.ot_version()}, this binding needs {ABI_VERSION}: rebuild it '
+                                       f'(recommend_b200/csrc/build.sh)')
         lib.ot_last_error_string.restype = C.c_char_p
         lib.ot_num_sms.restype = C.c_int
         for name, st in [('ot_mixed_gemm', GemmParams), ('ot_wgrad', WgradParams), ('ot_attn_fwd', AttnParams),

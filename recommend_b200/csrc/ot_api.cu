@@ -66,11 +66,6 @@ int num_sms() {
   return cached[dev];
 }
 
-bool head_dim_32_enabled() {
-  static const bool on = [] { const char* e = getenv("OT_ENABLE_HEAD_DIM_32"); return e && e[0] == '1'; }();
-  return on;
-}
-
 int mixed_gemm_impl(const ot_gemm_params* p, cudaStream_t st);
 int wgrad_impl(const ot_wgrad_params* p, cudaStream_t st);
 int attn_fwd_impl(const ot_attn_params* p, cudaStream_t st);

@@ -443,8 +443,8 @@ int attn_bwd_impl(const ot_attn_params* p, cudaStream_t st) {
   if (!p || !p->q || !p->k || !p->v || !p->o || !p->lse || !p->d_o || !p->dq || !p->dk || !p->dv || !p->delta)
     OT_FAIL(OT_ERR_INVALID_ARG, "ot_attn_bwd: null pointer");
   if (p->Lq <= 0 || p->Lk < p->Lq || p->B <= 0 || p->H <= 0) OT_FAIL(OT_ERR_INVALID_ARG, "ot_attn_bwd: bad sizes");
-  if ((p->head_dim != 32 || !head_dim_32_enabled()) && p->head_dim != 64 && p->head_dim != 96)
-    OT_FAIL(OT_ERR_UNSUPPORTED_SHAPE, "ot_attn_bwd: head_dim=%d (64 and 96 are supported; 32 is built but unverified: OT_ENABLE_HEAD_DIM_32=1)", p->head_dim);
+  if (p->head_dim != 32 && p->head_dim != 64 && p->head_dim != 96)
+    OT_FAIL(OT_ERR_UNSUPPORTED_SHAPE, "ot_attn_bwd: head_dim=%d (32, 64 and 96 are supported)", p->head_dim);
   if ((p->ldq % 8) || (p->ldk % 8) || (p->ldv % 8) || (p->ldo % 8) || (p->lddo % 8) || (p->lddq % 8) || (p->lddk % 8) || (p->lddv % 8))
     OT_FAIL(OT_ERR_UNSUPPORTED_SHAPE, "ot_attn_bwd: leading dimensions must be multiples of 8");
   const int swb = (p->head_dim == 64 && p->swizzle != 64) ? 128 : 64;

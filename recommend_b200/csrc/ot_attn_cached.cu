@@ -269,8 +269,8 @@ int attn_cached_impl(const ot_attn_cached_params* p, cudaStream_t st) {
   if (p->Ls > 0 && (!p->k_shared || !p->v_shared)) OT_FAIL(OT_ERR_INVALID_ARG, "ot_attn_ns_cached_fwd: shared K/V missing");
   if (p->C <= 0 || p->H <= 0 || p->Tq <= 0 || p->Tn < p->Tq || p->Tn > 128 || p->Ls < 0)
     OT_FAIL(OT_ERR_UNSUPPORTED_SHAPE, "ot_attn_ns_cached_fwd: C=%d H=%d Tq=%d Tn=%d Ls=%d (need 1 <= Tq <= Tn <= 128)", p->C, p->H, p->Tq, p->Tn, p->Ls);
-  if ((p->head_dim != 32 || !head_dim_32_enabled()) && p->head_dim != 64 && p->head_dim != 96)
-    OT_FAIL(OT_ERR_UNSUPPORTED_SHAPE, "ot_attn_ns_cached_fwd: head_dim=%d (64 and 96 are supported; 32 is built but unverified: OT_ENABLE_HEAD_DIM_32=1)", p->head_dim);
+  if (p->head_dim != 32 && p->head_dim != 64 && p->head_dim != 96)
+    OT_FAIL(OT_ERR_UNSUPPORTED_SHAPE, "ot_attn_ns_cached_fwd: head_dim=%d (32, 64 and 96 are supported)", p->head_dim);
   if ((p->ldq % 8) || (p->ld_own_k % 8) || (p->ld_own_v % 8) || (p->ldo % 8) || (p->Ls > 0 && ((p->ld_shared_k % 8) || (p->ld_shared_v % 8))))
     OT_FAIL(OT_ERR_UNSUPPORTED_SHAPE, "ot_attn_ns_cached_fwd: leading dimensions must be multiples of 8");
   const int swb = p->head_dim == 64 ? 128 : 64;

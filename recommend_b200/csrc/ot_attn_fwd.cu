@@ -263,8 +263,8 @@ int attn_fwd_ws_impl(const ot_attn_params* p, cudaStream_t st);   // ot_attn_fwd
 int attn_fwd_impl(const ot_attn_params* p, cudaStream_t st) {
   if (!p || !p->q || !p->k || !p->v || !p->o || !p->lse) OT_FAIL(OT_ERR_INVALID_ARG, "ot_attn_fwd: null pointer");
   if (p->Lq <= 0 || p->Lk < p->Lq || p->B <= 0 || p->H <= 0) OT_FAIL(OT_ERR_INVALID_ARG, "ot_attn_fwd: bad sizes B=%d H=%d Lq=%d Lk=%d", p->B, p->H, p->Lq, p->Lk);
-  if ((p->head_dim != 32 || !head_dim_32_enabled()) && p->head_dim != 64 && p->head_dim != 96)
-    OT_FAIL(OT_ERR_UNSUPPORTED_SHAPE, "ot_attn_fwd: head_dim=%d (64 and 96 are supported; 32 is built but unverified: OT_ENABLE_HEAD_DIM_32=1)", p->head_dim);
+  if (p->head_dim != 32 && p->head_dim != 64 && p->head_dim != 96)
+    OT_FAIL(OT_ERR_UNSUPPORTED_SHAPE, "ot_attn_fwd: head_dim=%d (32, 64 and 96 are supported)", p->head_dim);
   if ((p->ldq % 8) || (p->ldk % 8) || (p->ldv % 8) || (p->ldo % 8)) OT_FAIL(OT_ERR_UNSUPPORTED_SHAPE, "ot_attn_fwd: leading dimensions must be multiples of 8");
   const int swb = (p->head_dim == 64 && p->swizzle != 64) ? 128 : 64;
   if (p->head_dim == 64 && swb == 128 && p->swizzle != 128) return attn_fwd_ws_impl(p, st);   // swizzle=128 forces the simple kernel

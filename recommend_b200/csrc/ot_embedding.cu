@@ -6,7 +6,7 @@
 // idiom as three HBM-streaming kernels:
 //   gather   event[e, f*EF .. (f+1)*EF) = bf16(table[field_off[f] + id[e, f]])       (a copy: bit-exact by construction)
 //   scatter  grad[field_off[f] + id[e, f]] += d_event[e, f*EF ..]                     (fp32 vector reductions)
-//   adagrad  every touched row once: acc += g^2 ; w -= lr * g / (sqrt(acc) + eps) ; g = 0   (Keras Adagrad on the
+//   adagrad  every touched row once: acc += g^2 ; w -= lr * g * rsqrt(acc + eps) ; g = 0   (Keras Adagrad on the
 //            summed IndexedSlices gradient; sparse_optimizer 'adagrad', sparse_lr 0.1 in OT/config.py:39-47)
 // One thread moves one 16-byte output chunk (8 bf16): consecutive threads write consecutive chunks of an event row
 // (full 128-byte lines) and read consecutive 32-byte sectors of one fp32 table row.
@@ -81,8 +81,9 @@ embed_adagrad_kernel(float* __restrict__ table, float* __restrict__ acc, float* 
       const float4 g = g4[j];
       float4 a = a4[j], w = w4[j];
       a.x += g.x * g.x; a.y += g.y * g.y; a.z += g.z * g.z; a.w += g.w * g.w;
-      w.x -= lr * g.x / (sqrtf(a.x) + eps); w.y -= lr * g.y / (sqrtf(a.y) + eps);
-      w.z -= lr * g.z / (sqrtf(a.z) + eps); w.w -= lr * g.w / (sqrtf(a.w) + eps);
+      // Keras 2.12 Adagrad.update_step: variable -= lr * grad / sqrt(accumulator + epsilon)   (epsilon INSIDE the root)
+      w.x -= lr * g.x * rsqrtf(a.x + eps); w.y -= lr * g.y * rsqrtf(a.y + eps);
+      w.z -= lr * g.z * rsqrtf(a.z + eps); w.w -= lr * g.w * rsqrtf(a.w + eps);
       a4[j] = a; w4[j] = w;
       g4[j] = make_float4(0.f, 0.f, 0.f, 0.f);                        // the gradient table is all-zero again after the step
     }

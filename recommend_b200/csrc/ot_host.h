@@ -69,9 +69,6 @@ inline int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const ui
 }
 
 int num_sms();  // cached SM count of the current device (ot_api.cu)
-// head_dim 32 instantiations of the attention kernels are built but not yet verified on hardware: they stay behind
-// OT_ENABLE_HEAD_DIM_32=1 (tests/test_gpu_kernels.py::test_attention_head_dim_32) and are an unsupported-shape error otherwise
-bool head_dim_32_enabled();
 int* sched_slot(cudaStream_t st);  // zeroed work counter for one persistent-kernel launch, or NULL (static schedule)
 
 }  // namespace ot

@@ -5,7 +5,7 @@
 // Layout: gradients and optimizer state live in flat fp32 buffers in which every tensor starts on a
 // 1024-element boundary (OT_OPT_CHUNK), so a 1024-element chunk never straddles two tensors; the fp32
 // masters stay where the framework allocated them and are reached through a pointer table.
-//   pass 1  sqnorm[s] = sum(g_s^2)                                     4 B / parameter
+//   pass 1  sqnorm[v] = sum(g_v^2) per Keras variable v (clip slot)      4 B / parameter
 //   pass 2  g' = g * clip/max(||g||, clip);  rms = rho rms + (1-rho) g'^2;
 //           inc = lr g' rsqrt(rms + eps);  mom = momentum mom + inc;  w -= mom      28-32 B / parameter
 #include "ot_common.cuh"
@@ -24,6 +24,13 @@ __device__ __forceinline__ int seg_of(const long long* __restrict__ seg_off, int
     if (seg_off[mid] <= idx) lo = mid; else hi = mid - 1;
   }
   return lo;
+}
+
+// Clip slot of element `local` of tensor `seg` (see ot_rmsprop_params.seg_slot): which Keras variable the element belongs to.
+__device__ __forceinline__ int slot_of(const long long* __restrict__ seg_slot, int seg, long long local) {
+  if (seg_slot == nullptr) return seg;
+  const long long base = seg_slot[4 * seg], outer = seg_slot[4 * seg + 1], row = seg_slot[4 * seg + 2], part = seg_slot[4 * seg + 3];
+  return (int)(base + (local / outer) * (row / part) + (local % row) / part);
 }
 
 __device__ __forceinline__ float block_sum_256(float v, float* red) {
@@ -70,12 +77,59 @@ opt_sqnorm_kernel(const float* __restrict__ grad, const long long* __restrict__ 
   if (threadIdx.x == 0) atomicAdd(&sqnorm[seg], t);
 }
 
+// Same pass with clip slots finer than tensors (one per Keras variable): a warp covers 128 consecutive elements, which lie
+// in one slot whenever slot_part % 128 == 0 (every production shape: d, F multiples of 128) - then the warp keeps a running
+// (slot, sum) pair over the CTA's chunks and flushes one atomic when the slot changes; otherwise every lane adds its own.
+// Alignment padding holds zeros (the flat buffer is zero-initialised and kernels only write real elements).
+__global__ void __launch_bounds__(256)
+opt_sqnorm_slots_kernel(const float* __restrict__ grad, const long long* __restrict__ seg_off, const long long* __restrict__ seg_numel,
+                        const long long* __restrict__ seg_slot, int n_seg, long long n_chunks, float grad_scale,
+                        float* __restrict__ sqnorm) {
+  const long long per = (n_chunks + gridDim.x - 1) / gridDim.x;
+  const long long c0 = (long long)blockIdx.x * per;
+  const long long c1 = (c0 + per < n_chunks) ? c0 + per : n_chunks;
+  if (c0 >= c1) return;
+  int seg = seg_of(seg_off, n_seg, c0 * OPT_CHUNK);
+  long long seg_end = seg_off[seg + 1];
+  int run_slot = -1;
+  float run = 0.0f;
+  for (long long c = c0; c < c1; ++c) {
+    const long long base = c * OPT_CHUNK;
+    if (base >= seg_end) { seg = seg_of(seg_off, n_seg, base); seg_end = seg_off[seg + 1]; }
+    const long long local = base - seg_off[seg] + threadIdx.x * 4;
+    const bool real = local < seg_numel[seg];
+    float v = 0.0f;
+    int slot = -1;
+    if (real) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(grad + base) + threadIdx.x);
+      const float a = g.x * grad_scale, b = g.y * grad_scale, cc = g.z * grad_scale, d = g.w * grad_scale;
+      v = a * a + b * b + cc * cc + d * d;
+      slot = slot_of(seg_slot, seg, local);
+    }
+    const int slot0 = __shfl_sync(0xffffffffu, slot, 0);
+    if (__all_sync(0xffffffffu, slot == slot0)) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (slot0 != run_slot) {
+        if ((threadIdx.x & 31) == 0 && run_slot >= 0) atomicAdd(&sqnorm[run_slot], run);
+        run_slot = slot0;
+        run = 0.0f;
+      }
+      run += v;
+    } else if (real) {
+      atomicAdd(&sqnorm[slot], v);
+    }
+  }
+  if ((threadIdx.x & 31) == 0 && run_slot >= 0) atomicAdd(&sqnorm[run_slot], run);
+}
+
 template <bool MOMENTUM>
 __global__ void __launch_bounds__(256)
 opt_rmsprop_kernel(float* const* __restrict__ param_ptrs, const long long* __restrict__ seg_off,
                    const long long* __restrict__ seg_numel, int n_seg, long long n_chunks, float* __restrict__ grad,
                    float* __restrict__ rms, float* __restrict__ mom, const float* __restrict__ sqnorm, float lr, float rho,
-                   float momentum, float eps, float clip_norm, float grad_scale, int zero_grad) {
+                   float momentum, float eps, float clip_norm, float grad_scale, int zero_grad,
+                   const long long* __restrict__ seg_slot) {
   for (long long c = blockIdx.x; c < n_chunks; c += gridDim.x) {
     const long long base = c * OPT_CHUNK;
     const int seg = seg_of(seg_off, n_seg, base);
@@ -83,7 +137,8 @@ opt_rmsprop_kernel(float* const* __restrict__ param_ptrs, const long long* __res
     const long long numel = seg_numel[seg];
     if (local >= numel) continue;                                        // alignment padding
     float scale = grad_scale;
-    if (clip_norm > 0.0f) scale *= clip_norm / fmaxf(sqrtf(sqnorm[seg]), clip_norm);   // tf.clip_by_norm
+    // tf.clip_by_norm per Keras variable; the four elements of a thread share a slot (slot_part % 4 == 0)
+    if (clip_norm > 0.0f) scale *= clip_norm / fmaxf(sqrtf(sqnorm[slot_of(seg_slot, seg, local)]), clip_norm);
     float* w = param_ptrs[seg] + local;
     const long long fi = base + threadIdx.x * 4;
     const int n = (numel - local >= 4) ? 4 : (int)(numel - local);
@@ -127,19 +182,25 @@ int clip_rmsprop_impl(const ot_rmsprop_params* p, cudaStream_t st) {
   const long long n_chunks = p->n_flat / OPT_CHUNK;
   const long long cap = (long long)num_sms() * 8;
   const int grid = (int)(n_chunks < cap ? n_chunks : cap);
+  const long long* seg_slot = (const long long*)p->seg_slot;
+  if (seg_slot != nullptr && p->n_slots <= 0) OT_FAIL(OT_ERR_INVALID_ARG, "ot_clip_rmsprop_step: seg_slot without n_slots");
   if (p->clip_norm > 0.0f) {
-    OT_CUDA_CHECK(cudaMemsetAsync(p->sqnorm, 0, sizeof(float) * p->n_seg, st));
-    opt_sqnorm_kernel<<<grid, 256, 0, st>>>(p->grad, (const long long*)p->seg_off, p->n_seg, n_chunks, p->grad_scale, p->sqnorm);
+    OT_CUDA_CHECK(cudaMemsetAsync(p->sqnorm, 0, sizeof(float) * (seg_slot ? p->n_slots : p->n_seg), st));
+    if (seg_slot)
+      opt_sqnorm_slots_kernel<<<grid, 256, 0, st>>>(p->grad, (const long long*)p->seg_off, (const long long*)p->seg_numel, seg_slot, p->n_seg,
+                                                    n_chunks, p->grad_scale, p->sqnorm);
+    else
+      opt_sqnorm_kernel<<<grid, 256, 0, st>>>(p->grad, (const long long*)p->seg_off, p->n_seg, n_chunks, p->grad_scale, p->sqnorm);
     OT_CUDA_CHECK(cudaGetLastError());
   }
   if (p->momentum != 0.0f)
     opt_rmsprop_kernel<true><<<grid, 256, 0, st>>>(p->param_ptrs, (const long long*)p->seg_off, (const long long*)p->seg_numel, p->n_seg, n_chunks,
                                                     p->grad, p->rms, p->mom, p->sqnorm, p->lr, p->rho, p->momentum, p->eps, p->clip_norm,
-                                                    p->grad_scale, p->zero_grad);
+                                                    p->grad_scale, p->zero_grad, seg_slot);
   else
     opt_rmsprop_kernel<false><<<grid, 256, 0, st>>>(p->param_ptrs, (const long long*)p->seg_off, (const long long*)p->seg_numel, p->n_seg, n_chunks,
                                                      p->grad, p->rms, nullptr, p->sqnorm, p->lr, p->rho, 0.0f, p->eps, p->clip_norm,
-                                                     p->grad_scale, p->zero_grad);
+                                                     p->grad_scale, p->zero_grad, seg_slot);
   OT_CUDA_CHECK(cudaGetLastError());
   return OT_OK;
 }

@@ -118,6 +118,9 @@ class MixedMHA(nn.Module):
         for part in range(3):
             _glorot_(self.Wqkv.data[:, :, part * d:(part + 1) * d], d, d)
         _glorot_(self.Wo.data, d, d)
+        # 3*G Keras Dense kernels live in this tensor (q | k | v column blocks per weight group): tf.clip_by_norm treats each
+        # one separately (OT/train.py:135); (elements per group, row length, columns per variable) for train.ClipRMSprop
+        self.Wqkv._ot_clip_layout = (d * 3 * d, 3 * d, d)
 
     # reference-style accessors (OT/model.py:38-54)
     def _slice(self, part: int, j: Optional[int]) -> torch.Tensor:
@@ -144,7 +147,7 @@ class MixedMHA(nn.Module):
             k2, _, Lc = _to_token_major(kv_cache[0])
             v2, _, _ = _to_token_major(kv_cache[1])
             prefix = torch.cat([k2, v2], dim=1)
-        out, kv = _MHAFn.apply(x2, self.Wqkv, self.Wo, self, B, L, keep, prefix)
+        out, kv = _MHAFn.apply(x2, self.Wqkv, self.Wo, self, B, L, keep, prefix, torch.is_grad_enabled())
         d = self.hidden_dim
         Lk = kv.shape[0] // B
         k = _from_token_major(kv[:, :d], B, Lk)
@@ -154,7 +157,7 @@ class MixedMHA(nn.Module):
 
 class _MHAFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x2, Wqkv, Wo, mod: MixedMHA, B, cur, keep, prefix):
+    def forward(ctx, x2, Wqkv, Wo, mod: MixedMHA, B, cur, keep, prefix, grad_on=True):
         ctx.set_materialize_grads(False)   # no zero tensors for the (k, v) output nobody differentiates
         w = _weights_of(mod, None)
         cfg = mod.config
@@ -162,7 +165,9 @@ class _MHAFn(torch.autograd.Function):
                                            cfg.ns_param_alignment, prefix)
         kv = saved[1]
         ctx.mark_non_differentiable(kv)
-        if prefix is not None and any(ctx.needs_input_grad):
+        # ctx.needs_input_grad is True for a Parameter input even under torch.no_grad(), and grad mode is always off inside
+        # Function.forward: the caller's grad mode (``grad_on``) decides
+        if prefix is not None and grad_on and any(ctx.needs_input_grad):
             raise RuntimeError('MixedMHA: kv_cache is an inference feature; call it under torch.no_grad()')
         ctx.saved = (x2, saved, w, mod, B, cur, keep)
         return out, kv
@@ -170,11 +175,11 @@ class _MHAFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout, _dkv):
         if dout is None:
-            return (None,) * 8
+            return (None,) * 9
         x2, saved, w, mod, B, cur, keep = ctx.saved
         dxn = engine.mha_backward(dout.contiguous(), x2, saved, w, engine._grad_buf(mod.Wqkv), engine._grad_buf(mod.Wo),
                                   B, cur, keep, mod.config.num_heads)
-        return dxn, None, None, None, None, None, None, None
+        return dxn, None, None, None, None, None, None, None, None
 
 
 class MixedFFN(nn.Module):
@@ -192,22 +197,26 @@ class MixedFFN(nn.Module):
         self.b1 = nn.Parameter(torch.zeros(G, Fd))
         self.W2 = nn.Parameter(_glorot_(torch.empty(G, Fd, d), Fd, d))
         self.b2 = nn.Parameter(torch.zeros(G, d))
+        for t in (self.W1, self.b1, self.W2, self.b2):      # G Keras variables each (one per weight group), see MixedMHA
+            n = t[0].numel()
+            t._ot_clip_layout = (n, n, n)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         _require_cuda(x, 'MixedFFN')
         x2, B, L = _to_token_major(x)
-        y = _FFNFn.apply(x2, self.W1, self, B, L)
+        y = _FFNFn.apply(x2, self.W1, self, B, L, torch.is_grad_enabled())
         return _from_token_major(y, B, L)
 
 
 class _FFNFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x2, W1, mod: MixedFFN, B, cur):
+    def forward(ctx, x2, W1, mod: MixedFFN, B, cur, grad_on=True):
         w = _weights_of(None, mod)
         cfg = mod.config
         segs = ops.position_segments(0, cur, cur, cfg.num_ns_tokens, cfg.ns_param_alignment, B)
-        y, saved, _ = engine.ffn_forward(x2, None, w, mod.b1.detach(), mod.b2.detach(), segs, save=True)
-        ctx.saved = (x2, saved, w, mod, segs)
+        need_grad = grad_on and any(ctx.needs_input_grad)   # grad mode is always off inside Function.forward
+        y, saved, _ = engine.ffn_forward(x2, None, w, mod.b1.detach(), mod.b2.detach(), segs, save=need_grad)
+        ctx.saved = (x2, saved, w, mod, segs) if need_grad else None
         return y
 
     @staticmethod
@@ -215,7 +224,7 @@ class _FFNFn(torch.autograd.Function):
         x2, saved, w, mod, segs = ctx.saved
         g = engine._grad_buf
         dx = engine.ffn_backward(dy.contiguous(), x2, saved, w, segs, g(mod.W1), g(mod.b1), g(mod.W2), g(mod.b2))
-        return dx, None, None, None, None
+        return dx, None, None, None, None, None
 
 
 class _PartialWeights:
@@ -297,7 +306,8 @@ class OneTransBlock(nn.Module):
         prev = None
         if prev_block is not None and getattr(prev_block, '_last_drop', None) is not None:
             prev = (prev_block, (prev_block._last_drop[1], prev_block._last_drop[2]))
-        return _BlockFn.apply(x2, self.norm1.scale, self, B, cur, keep, kv_prefix, x_hp, drop, pre_norm, next_gain, prev)
+        return _BlockFn.apply(x2, self.norm1.scale, self, B, cur, keep, kv_prefix, x_hp, drop, pre_norm, next_gain, prev,
+                              torch.is_grad_enabled())
 
     def forward(self, x: torch.Tensor, training: bool = False,
                 kv_cache: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, query_len: Optional[int] = None):
@@ -319,12 +329,16 @@ class OneTransBlock(nn.Module):
 
 class _BlockFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x2, anchor, blk: OneTransBlock, B, cur, keep, kv_prefix, x_hp, drop, pre_norm=None, next_gain=None, prev=None):
+    def forward(ctx, x2, anchor, blk: OneTransBlock, B, cur, keep, kv_prefix, x_hp, drop, pre_norm=None, next_gain=None, prev=None,
+                grad_on=True):
         # without this autograd fills a [cur*B, 2d] bf16 and a [L_NS*B, d] fp32 zero tensor per block and step for the
         # two outputs nobody differentiates (1.3 ms/step at C2, profiles/README.md)
         ctx.set_materialize_grads(False)
         cfg = blk.config
-        need_grad = any(ctx.needs_input_grad)
+        # ctx.needs_input_grad is True for the Parameter anchor even under torch.no_grad(), and grad mode is always off inside
+        # Function.forward: the caller's grad mode (``grad_on``) decides whether anything is saved (eval / inference forwards
+        # keep no activations and skip the GELU pre-activation output)
+        need_grad = grad_on and any(ctx.needs_input_grad)
         if need_grad and kv_prefix is not None:
             raise RuntimeError('OneTransBlock: kv_cache is an inference feature; call it under torch.no_grad()')
         w = blk._weights()
@@ -343,7 +357,7 @@ class _BlockFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy, _dkv, _dhp):
         if dy is None:
-            return (None,) * 12
+            return (None,) * 13
         saved, w, blk, B, cur, keep, prev = ctx.saved
         # masked copy of dy left behind by the block above (its norm1 backward wrote it in the same pass as dy itself)
         dy_masked = None
@@ -361,7 +375,7 @@ class _BlockFn(torch.autograd.Function):
         if engine.after_block_backward is not None:
             engine.after_block_backward(blk)      # data parallel: this block's gradients may start their all-reduce now
         ctx.saved = None
-        return dx, None, None, None, None, None, None, None, None, None, None, None
+        return dx, None, None, None, None, None, None, None, None, None, None, None, None
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -381,7 +381,8 @@ def colsum(inp: torch.Tensor, segs: Sequence[Seg], out: torch.Tensor, out_group_
 
 def clip_rmsprop_step(param_ptrs: torch.Tensor, seg_off: torch.Tensor, seg_numel: torch.Tensor, grad: torch.Tensor,
                       rms: torch.Tensor, mom: Optional[torch.Tensor], sqnorm: torch.Tensor, *, lr: float, rho: float,
-                      momentum: float, eps: float, clip_norm: float, grad_scale: float = 1.0, zero_grad: bool = False) -> None:
+                      momentum: float, eps: float, clip_norm: float, grad_scale: float = 1.0, zero_grad: bool = False,
+                      seg_slot: Optional[torch.Tensor] = None, n_slots: int = 0) -> None:
     """Per-tensor ``clip_by_norm`` then Keras RMSprop on flat fp32 buffers (OT/train.py:131-138).  ``param_ptrs`` /
     ``seg_off`` / ``seg_numel`` are int64 DEVICE tables (see ``ot_rmsprop_params``)."""
     for t in (param_ptrs, seg_off, seg_numel):
@@ -396,6 +397,12 @@ def clip_rmsprop_step(param_ptrs: torch.Tensor, seg_off: torch.Tensor, seg_numel
     p.grad, p.rms, p.mom, p.sqnorm = grad.data_ptr(), rms.data_ptr(), _ptr(mom), sqnorm.data_ptr()
     p.lr, p.rho, p.momentum, p.eps, p.clip_norm, p.grad_scale = lr, rho, momentum, eps, clip_norm, grad_scale
     p.zero_grad = 1 if zero_grad else 0
+    if seg_slot is not None:      # clip slots finer than tensors (one per Keras variable), see ot_rmsprop_params.seg_slot
+        if not seg_slot.is_cuda or seg_slot.dtype != torch.int64 or seg_slot.shape != (seg_numel.numel(), 4) or not seg_slot.is_contiguous():
+            raise RuntimeError('clip_rmsprop_step: seg_slot must be a contiguous CUDA int64 [n_seg, 4] table')
+        if sqnorm.numel() < n_slots:
+            raise RuntimeError('clip_rmsprop_step: sqnorm needs one entry per clip slot')
+        p.seg_slot, p.n_slots = seg_slot.data_ptr(), n_slots
     n = float(grad.numel())
     _run('ot_clip_rmsprop_step', L.load().ot_clip_rmsprop_step, p, f'n{grad.numel()}', 10.0 * n,
          n * (4.0 * (clip_norm > 0) + 24.0 + 8.0 * (momentum != 0.0) + 4.0 * bool(zero_grad)), n_launch=2 if clip_norm > 0 else 1)

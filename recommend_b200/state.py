@@ -105,7 +105,10 @@ def _keras_entries(model):
             yield b + f'ffn/{name}/dense_1/kernel', ffn.W2, (g,)
             yield b + f'ffn/{name}/dense_1/bias', ffn.b2, (g,)
     yield 'output_norm/scale', model.output_norm.scale, None
-    for t, head in model.task_heads.items():
+    # the reference keeps its heads in a plain dict attribute (OT/model.py:325-330); Keras' trackable dict wrapper flattens tracked
+    # layers in sorted-key order, which for the default ['ctr', 'cvr'] coincides with insertion order
+    for t in sorted(model.task_heads.keys()):
+        head = model.task_heads[t]
         yield f'task_heads/{t}/dense/kernel', head.kernel0, None
         yield f'task_heads/{t}/dense/bias', head.bias0, None
         yield f'task_heads/{t}/dense_1/kernel', head.kernel1, None
@@ -163,7 +166,7 @@ def load_weights(model, path) -> None:
         if z.files and all(k.startswith('arr_') for k in z.files):
             load_keras_weight_list(model, [z[f'arr_{i}'] for i in range(len(z.files))])
             return
-        keys = sorted(z.files)
+        keys = sorted(z.files, key=lambda k: int(k.split(':', 1)[0]))      # '<position>:<name>'; numeric, not lexicographic
         want = [name for name, _, _ in _keras_entries(model)]
         got = [k.split(':', 1)[1] for k in keys]
         if got != want:

@@ -5,7 +5,7 @@ data-parallel gradient all-reduce (PAPER:190; the reference code has no distribu
 One process per GPU; ``torch.distributed`` (NCCL over NVLink/NVSwitch) is the plumbing."""
 from __future__ import annotations
 
-from typing import Dict, Iterable, List, Optional
+from typing import Dict, Iterable, List, Optional, Tuple
 
 import torch
 import torch.distributed as dist
@@ -180,6 +180,17 @@ def train_loop(model, grads: FlatGradBuffer, host_batches, world_size: int = 1, 
     return losses
 
 
+def broadcast_parameters(model, world_size: int, src: int = 0) -> None:
+    """Data parallel keeps replicas identical only if they start identical: copy rank ``src``'s parameters to every rank (one
+    broadcast per tensor, once after construction / loading).  No-op for one rank or without an initialised process group."""
+    if world_size <= 1 or not dist.is_available() or not dist.is_initialized():
+        return
+    with torch.no_grad():
+        for p in model.parameters():
+            dist.broadcast(p.data, src=src)
+            torch.autograd.graph.increment_version(p)     # bf16 compute copies refresh on the next forward
+
+
 class ClipRMSprop:
     """The dense-parameter update of the reference train step (OT/train.py:131-138): per-tensor
     ``tf.clip_by_norm(g, gradient_clip_norm)`` followed by Keras ``RMSprop(learning_rate, rho=0.9, momentum,
@@ -188,7 +199,7 @@ class ClipRMSprop:
     their version counters bumped so the bf16 compute copies refresh on the next forward."""
 
     def __init__(self, grads: FlatGradBuffer, lr: float = 0.005, rho: float = 0.9, momentum: float = 0.0,
-                 eps: float = 1e-7, clip_norm: float = 0.0):
+                 eps: float = 1e-7, clip_norm: float = 0.0, per_variable: bool = True):
         from . import ops
         self._ops = ops
         self.grads = grads
@@ -201,7 +212,22 @@ class ClipRMSprop:
                 raise RuntimeError('ClipRMSprop: parameters must be contiguous, 16-byte aligned fp32 CUDA tensors')
         self.rms = torch.zeros_like(grads.flat)
         self.mom = torch.zeros_like(grads.flat) if self.momentum != 0.0 else None
-        self.sqnorm = torch.zeros(len(grads.params), dtype=torch.float32, device=dev)
+        # Clip granularity = the reference's Keras variables (OT/train.py:135 clips each entry of model.trainable_variables):
+        # the packed tensors (Wqkv [G, d, 3d], W1 / b1 / W2 / b2 [G, ...]) carry ``_ot_clip_layout`` and split into one clip
+        # slot per (weight group, q | k | v part); ``per_variable=False`` clips each packed tensor as a whole instead.
+        slots, base = [], 0
+        self.slot_names: List[Tuple[int, int]] = []     # (parameter index, first slot) for grad_norms()
+        for i, p in enumerate(grads.params):
+            n = max(p.numel(), 1)
+            outer, row, part = getattr(p, '_ot_clip_layout', (n, n, n)) if per_variable else (n, n, n)
+            if (outer, row, part) != (n, n, n) and (part % 4 or row % part or outer % row or n % outer):
+                raise RuntimeError(f'ClipRMSprop: unsupported clip layout {(outer, row, part)} for a tensor of {n} elements')
+            slots.append((base, outer, row, part))
+            self.slot_names.append((i, base))
+            base += (n // outer) * (row // part)
+        self.n_slots = base
+        self._seg_slot = torch.tensor(slots, dtype=torch.int64, device=dev).contiguous() if base != len(grads.params) else None
+        self.sqnorm = torch.zeros(self.n_slots, dtype=torch.float32, device=dev)
         self._seg_off = torch.tensor(grads.offsets + [grads.flat.numel()], dtype=torch.int64, device=dev)
         self._seg_numel = torch.tensor([p.numel() for p in grads.params], dtype=torch.int64, device=dev)
         self._ptrs = None
@@ -224,12 +250,14 @@ class ClipRMSprop:
     def step(self, grad_scale: float = 1.0, zero_grad: bool = False) -> None:
         self._ops.clip_rmsprop_step(self._param_table(), self._seg_off, self._seg_numel, self.grads.flat, self.rms, self.mom,
                                     self.sqnorm, lr=self.lr, rho=self.rho, momentum=self.momentum, eps=self.eps,
-                                    clip_norm=self.clip_norm, grad_scale=grad_scale, zero_grad=zero_grad)
+                                    clip_norm=self.clip_norm, grad_scale=grad_scale, zero_grad=zero_grad,
+                                    seg_slot=self._seg_slot, n_slots=self.n_slots)
         for p in self.grads.params:
             torch.autograd.graph.increment_version(p)
 
     def grad_norms(self) -> torch.Tensor:
-        """Per-tensor gradient L2 norms seen by the last ``step`` (valid when clip_norm > 0)."""
+        """Gradient L2 norms per clip slot (Keras variable; ``slot_names`` maps parameters to their first slot) seen by the last
+        ``step`` (valid when clip_norm > 0)."""
         return self.sqnorm.sqrt()
 
 
@@ -291,6 +319,7 @@ class OneTransTrainer:
         self.device = torch.device(device)
         self.world_size = world_size
         self.model = OneTransModel(config).to(self.device)                       # OT/train.py:28
+        broadcast_parameters(self.model, world_size)                             # replicas start from rank 0's initialisation
         self.grads = FlatGradBuffer(self.model.parameters())
         self.optimizer = self._create_optimizer()                                # :31
         self.train_metrics = BinaryTaskMetrics(config.tasks, self.device)        # :37-38
@@ -377,6 +406,8 @@ class OneTransTrainer:
         """OT/train.py:281-314: weights, ``config.json`` and ``training_history.json`` under ``model_dir / model_name``."""
         import json
         from . import state
+        if self.world_size > 1 and dist.is_initialized() and dist.get_rank() != 0:
+            return                                                               # data parallel: replicas are identical, rank 0 writes
         path = self.model_dir / model_name
         path.mkdir(parents=True, exist_ok=True)
         state.save_weights(self.model, path / state.WEIGHTS_FILE)
@@ -399,6 +430,7 @@ class OneTransTrainer:
         self.model = OneTransModel(self.config).to(self.device)
         if (model_path / state.WEIGHTS_FILE).exists():
             state.load_weights(self.model, model_path / state.WEIGHTS_FILE)
+        broadcast_parameters(self.model, self.world_size)
         self.grads = FlatGradBuffer(self.model.parameters())
         self.optimizer = self._create_optimizer()
         if (model_path / 'training_history.json').exists():

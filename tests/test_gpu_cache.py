@@ -12,6 +12,7 @@ from tests.helpers import make_configs, to_cuda, rel_l2
 
 pytestmark = pytest.mark.gpu
 bf16 = torch.bfloat16
+LOGIT_TOL = 1e-2      # north_star: logits rel err <= 1e-2 for the bf16 kernels against the fp32 oracle - cached path included
 
 
 @pytest.mark.parametrize('C,H,dh,Tq,Tn,Ls', [(40, 4, 64, 32, 32, 300), (7, 4, 64, 16, 16, 100), (33, 4, 64, 12, 12, 0),
@@ -57,10 +58,10 @@ def test_t8_cached_scoring_equals_uncached_forward(schedule, L_ns, layers):
         again = model(to_cuda(non_seq), to_cuda(seq1), use_kv_cache=True, return_logits=True)    # reuses it
     for t in cfg.tasks:
         assert cached[t].shape == (C, 1)
-        # two bf16 evaluations of the same function (different tile packing / softmax block order): each is ~1e-2 from
-        # the fp32 truth, so they sit within ~2e-2 of each other
+        # two bf16 evaluations of the same function (different tile packing / softmax block order); held to the same bar as
+        # either of them against the fp32 oracle (measured 0.24-0.66e-2)
         print('cached vs uncached rel-L2', t, rel_l2(cached[t], full[t]))
-        assert rel_l2(cached[t], full[t]) < 2.5e-2, (t, rel_l2(cached[t], full[t]))
+        assert rel_l2(cached[t], full[t]) <= LOGIT_TOL, (t, rel_l2(cached[t], full[t]))
         assert torch.equal(cached[t], again[t])
     # and against the fp32 oracle on the same C rows (uncached by construction)
     seq_o = {k: v.to(bf16).float() for k, v in seqC.items()}
@@ -75,7 +76,7 @@ def test_t8_cached_scoring_equals_uncached_forward(schedule, L_ns, layers):
     lo = torch.cat([ref[t].flatten() for t in cfg.tasks])
     lg = torch.cat([cached[t].flatten().float().cpu() for t in cfg.tasks])
     print('cached vs fp32 oracle rel-L2', rel_l2(lg, lo))
-    assert rel_l2(lg, lo) < 1.5e-2, rel_l2(lg, lo)
+    assert rel_l2(lg, lo) <= LOGIT_TOL, rel_l2(lg, lo)                # north_star: logits rel err <= 1e-2 (measured 0.39-0.87e-2)
 
 
 def _cache_fp(cache):
@@ -117,17 +118,19 @@ def test_extend_kv_cache_matches_the_oracle_streaming_rule(schedule, pyramid, L_
         wk, wv = want_kv
         assert kv.shape[0] == wk.shape[1], (l, kv.shape, wk.shape)                  # same key-set sizes per layer
         assert torch.equal(kv[:old.shape[0]], old)                                  # old rows are copied, not recomputed
-        assert rel_l2(kv[:, :d], wk[0]) < 1.5e-2 and rel_l2(kv[:, d:], wv[0]) < 1.5e-2
+        ek, ev = rel_l2(kv[:, :d], wk[0]), rel_l2(kv[:, d:], wv[0])
+        print(f'layer {l} cached K / V rel-L2 vs fp32 oracle: {ek:.2e} / {ev:.2e}')
+        assert ek <= LOGIT_TOL and ev <= LOGIT_TOL
     err = rel_l2(torch.cat([got[t].flatten().float().cpu() for t in cfg.tasks]), torch.cat([want[t].flatten() for t in cfg.tasks]))
     print(f'extend[{schedule}, pyramid={pyramid}] logits rel-L2 vs fp32 oracle: {err:.3e}')
-    assert err < 1.5e-2                                                              # the bar T8 holds the cached path to
+    assert err <= LOGIT_TOL                                                          # north_star: logits rel err <= 1e-2
     if not pyramid:     # size-independent property: append == fresh build on the longer sequence
         with torch.no_grad():
             fresh = _cache_fp(model.build_kv_cache(to_cuda(seq)))
         model.build_kv_cache(to_cuda(head))
         model.extend_kv_cache(new.cuda())
         for a, b in zip(_cache_fp(model.kv_cache), fresh):
-            assert a.shape == b.shape and rel_l2(a, b) < 1.5e-2
+            assert a.shape == b.shape and rel_l2(a, b) <= LOGIT_TOL
 
 
 def test_extend_kv_cache_argument_checks():

@@ -10,8 +10,14 @@ from tests.helpers import make_configs, oracle_keep_lens, bf16_round_inputs, to_
 
 pytestmark = pytest.mark.gpu
 
-LOGIT_TOL = float(__import__('os').environ.get('OT_LOGIT_TOL', 1e-2))      # north_star: logits rel err <= 1e-2 (bf16 kernels vs fp32 oracle)
-GRAD_L2_TOL = float(__import__('os').environ.get('OT_GRAD_TOL', 3e-2))    # per-tensor relative L2 error of parameter gradients (bf16 activations/gradients)
+# north_star: logits rel err <= 1e-2 (bf16 kernels vs fp32 oracle); per-tensor relative L2 error of parameter gradients <= 3e-2
+# (bf16 activations / gradients).  The environment can only TIGHTEN them (experiments with a stricter bar), never loosen them.
+LOGIT_TOL = min(1e-2, float(__import__('os').environ.get('OT_LOGIT_TOL', 1e-2)))
+GRAD_L2_TOL = min(3e-2, float(__import__('os').environ.get('OT_GRAD_TOL', 3e-2)))
+# element-wise companion of the aggregate bar: worst single logit error relative to the largest logit.  The aggregate is an
+# average over the batch, the worst of n logits sits ~sqrt(2 ln n) standard deviations out (2.9x at n = 64, 3.7x at n = 4096),
+# so it is held to 2.5x the aggregate bar; profiles/exp_rounding_ablation.py shows where the bf16 floor (0.7e-2 aggregate) comes from.
+LOGIT_MAX_TOL = 2.5e-2
 
 
 def _build(ocfg, cfg, seed=0):
@@ -62,8 +68,10 @@ def _check(out, logit_tol=LOGIT_TOL, grad_tol=GRAD_L2_TOL):
     lo = torch.cat([out['logits_o'][t].flatten() for t in out['logits_o']])
     lg = torch.cat([out['logits_g'][t].flatten() for t in out['logits_o']])
     e = rel_l2(lg, lo)   # "logits rel err": ||gpu - oracle||_2 / ||oracle||_2 over the batch and tasks
-    print(f'logits rel-L2 err {e:.3e} (max-abs/max {rel_err(lg, lo):.3e})')
+    em = rel_err(lg, lo)
+    print(f'logits rel-L2 err {e:.3e} (max-abs/max {em:.3e})')
     assert e <= logit_tol, f'logits rel err {e:.3e}'
+    assert em <= LOGIT_MAX_TOL, f'worst logit error / largest logit {em:.3e}'
     if 'grads_o' in out:
         assert abs(out['loss_g'] - out['loss_o']) <= 1e-2 * max(1.0, abs(out['loss_o']))
         worst = {}
@@ -118,6 +126,13 @@ def test_product_equals_the_reference_outputs(case):
     assert (torch.sigmoid(lg) - ref_prob).abs().max() < 1e-2
 
 
+def test_reference_example_shape_d128_head_dim_32():
+    """The shape of the reference's own smoke block and example scripts (OT/model.py:420-442, OT/examples/train_example.py:22-27):
+    hidden_dim 128 with 4 heads = head_dim 32, 2 layers, 4 NS tokens, click 10 + cart 5 events (batch 64 for a stable statistic)."""
+    ocfg, cfg = make_configs(hidden_dim=128, num_layers=2, num_heads=4, ffn_dim=512, num_ns_tokens=4)
+    _check(_run_pair(ocfg, cfg, B=64, seq_lens=(10, 5, 7), present=('click_seq', 'cart_seq')))
+
+
 def test_c1_small_reference_ratio():
     """BASELINE config 1 shapes: OneTrans-S, B=32, 256 S + 16 NS tokens, reference ratio schedule."""
     ocfg, cfg = make_configs(num_ns_tokens=16, schedule='reference_ratio')
@@ -146,6 +161,25 @@ def test_onetrans_l_shapes():
     """OneTrans-L (d=384, H=4 -> head_dim 96, F=1536), shortened to 3 blocks."""
     ocfg, cfg = make_configs(hidden_dim=384, num_layers=3, ffn_dim=1536, num_ns_tokens=8, schedule='linear_to_ns')
     _check(_run_pair(ocfg, cfg, B=24, seq_lens=(60, 50, 40)))
+
+
+def test_c3_onetrans_l_full_depth():
+    """BASELINE config 3 at full depth: OneTrans-L = ``get_model_config('default')`` (OT/config.py:14-17: d 384, 8 blocks, 4 heads ->
+    head_dim 96, F 1536), 512 S + 32 NS tokens, linear_to_ns = [480, 416, 352, 288, 224, 160, 96, 32]; batch 128 instead of 2048
+    per GPU so that the fp32 oracle (forward + gradients) finishes in about a minute on the host cores."""
+    ocfg, cfg = make_configs(hidden_dim=384, num_layers=8, ffn_dim=1536, num_ns_tokens=32, schedule='linear_to_ns')
+    out = _run_pair(ocfg, cfg, B=128, seq_lens=(170, 170, 170))
+    assert R.resolve_keep_lens(cfg, 544) == [480, 416, 352, 288, 224, 160, 96, 32]
+    _check(out)
+
+
+def test_onetrans_large_config():
+    """``OneTransLargeConfig`` (OT/config.py:95-103: d 512, 12 blocks, 8 heads, F 2048 - not a paper configuration):
+    N = 512 rows do not fit one epilogue tile, so the RMSNorms run as stand-alone kernels here."""
+    c = R.get_model_config('large')
+    assert (c.hidden_dim, c.num_layers, c.num_heads, c.ffn_dim) == (512, 12, 8, 2048)
+    ocfg, cfg = make_configs(hidden_dim=512, num_layers=12, num_heads=8, ffn_dim=2048, num_ns_tokens=16, schedule='linear_to_ns')
+    _check(_run_pair(ocfg, cfg, B=32, seq_lens=(60, 50, 40)))
 
 
 def test_c4_long_sequence_halving():
@@ -215,6 +249,87 @@ def test_t9_auc_delta_on_64k_samples():
         auc_o, auc_g = roc_auc_score(y, a.numpy()), roc_auc_score(y, b.numpy())
         print(f'AUC[{t}] oracle {auc_o:.6f} kernels {auc_g:.6f} delta {abs(auc_o - auc_g):.2e}')
         assert abs(auc_o - auc_g) <= 1e-4
+
+
+def test_t9_auc_delta_on_c1_shapes():
+    """T9 on a BASELINE configuration: OneTrans-S at config 1's token counts (256 S + 16 NS, 6 blocks, reference ratio schedule),
+    65536 samples in chunks of 2048; AUC delta <= 1e-4 (exact ROC-AUC)."""
+    from sklearn.metrics import roc_auc_score
+    ocfg, cfg = make_configs(num_ns_tokens=16, schedule='reference_ratio')
+    P, model = _build(ocfg, cfg, seed=4)
+    N, chunk = 65536, 2048
+    seq_lens = (86, 84, 84)
+    ocfg.pyramid_keep_lens = R.resolve_keep_lens(cfg, 272)
+    po, pg = {t: [] for t in cfg.tasks}, {t: [] for t in cfg.tasks}
+    for i in range(N // chunk):
+        non_seq, seq, _ = O.synthetic_batch(ocfg, chunk, seq_lens, seed=500 + i)
+        non_seq, seq = bf16_round_inputs(non_seq, seq)
+        o = O.model_forward(P, ocfg, non_seq, seq)
+        with torch.no_grad():
+            g = model(to_cuda(non_seq), to_cuda(seq))
+        for t in cfg.tasks:
+            po[t].append(o[t].flatten())
+            pg[t].append(g[t].flatten().float().cpu())
+    gen = torch.Generator().manual_seed(1)
+    for t in cfg.tasks:
+        a, b = torch.cat(po[t]), torch.cat(pg[t])
+        logit = torch.logit(a.clamp(1e-6, 1 - 1e-6)) * 3.0          # sharpen: random-init logits are small
+        y = (torch.rand(N, generator=gen) < torch.sigmoid(logit)).numpy()
+        auc_o, auc_g = roc_auc_score(y, a.numpy()), roc_auc_score(y, b.numpy())
+        print(f'C1 AUC[{t}] oracle {auc_o:.6f} kernels {auc_g:.6f} delta {abs(auc_o - auc_g):.2e}')
+        assert abs(auc_o - auc_g) <= 1e-4
+
+
+def test_block_and_mha_accept_a_kv_cache_under_no_grad():
+    """The reference's block-level ``kv_cache`` argument (OT/model.py:76,95-98,186): under ``torch.no_grad()`` the cached keys /
+    values are placed in front; the result equals the same block on the concatenated sequence (queries = the new rows).  With
+    gradients enabled it is refused (an inference feature)."""
+    ocfg, cfg = make_configs(num_layers=1, num_ns_tokens=4, pyramid_enabled=False)
+    P, model = _build(ocfg, cfg)
+    blk = model.blocks[0]
+    with torch.no_grad():     # every weight group = the shared one, so that a position's weights do not depend on the split point
+        for w in (blk.attention.Wqkv, blk.ffn.W1, blk.ffn.b1, blk.ffn.W2, blk.ffn.b2):
+            w.copy_(w[0:1].expand_as(w).clone())
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(4, 24, 256, generator=g).to(torch.bfloat16).cuda()
+    with torch.no_grad():
+        y_full, (k_full, v_full) = blk(x)
+        _, (k_old, v_old) = blk(x[:, :16])
+        y_new, (k_cat, v_cat) = blk(x[:, 16:], kv_cache=(k_old, v_old))
+        assert k_cat.shape == k_full.shape and rel_l2(k_cat, k_full) < 1e-2 and rel_l2(v_cat, v_full) < 1e-2
+        assert rel_l2(y_new, y_full[:, 16:]) < 1e-2
+        xn = x.clone()
+        o_new, _ = blk.attention(xn[:, 16:], kv_cache=(k_old, v_old))
+        assert o_new.shape == (4, 8, 256) and torch.isfinite(o_new.float()).all()
+    with pytest.raises(RuntimeError, match='no_grad'):
+        blk(x[:, 16:].requires_grad_(True), kv_cache=(k_old, v_old))
+    with pytest.raises(RuntimeError, match='no_grad'):
+        blk.attention(x[:, 16:].requires_grad_(True), kv_cache=(k_old, v_old))
+
+
+def test_eval_forward_saves_no_activations():
+    """an evaluation forward (``torch.no_grad()``) must not run in save mode - no GELU pre-activation output, no ctx."""
+    from recommend_b200 import ops
+    ocfg, cfg = make_configs(num_layers=1, num_ns_tokens=4, pyramid_enabled=False)
+    P, model = _build(ocfg, cfg)
+    non_seq, seq, _ = O.synthetic_batch(ocfg, 8, (20, 10, 5))
+    seen = []
+    real = ops.mixed_gemm
+
+    def spy(*a, **kw):
+        seen.append(kw.get('out2') is not None)
+        return real(*a, **kw)
+    from recommend_b200 import engine
+    engine.ops.mixed_gemm = spy
+    try:
+        with torch.no_grad():
+            model(to_cuda(non_seq), to_cuda(seq))
+        assert not any(seen)
+        seen.clear()
+        model(to_cuda(non_seq), to_cuda(seq), training=True)
+        assert any(seen)
+    finally:
+        engine.ops.mixed_gemm = real
 
 
 def test_dropout_forward_backward_consistency():

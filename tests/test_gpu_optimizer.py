@@ -85,3 +85,59 @@ def test_train_step_with_optimizer_reduces_loss():
     opt = ClipRMSprop(buf, lr=1e-3, rho=0.9, momentum=0.0, clip_norm=cfg.gradient_clip_norm)
     losses = [float(train_step(model, buf, non_seq, seq, labels, optimizer=opt)) for _ in range(8)]
     assert losses[-1] < losses[0], losses
+
+
+@pytest.mark.parametrize('d', [128, 64])
+def test_clip_granularity_is_the_keras_variable(d):
+    """OT/train.py:135 clips every entry of ``model.trainable_variables``: each (weight group, q | k | v) Dense kernel and each
+    per-group FFN kernel / bias on its own, not the packed ``[G, ...]`` tensors as wholes.  d = 64 makes the
+    q | k | v column blocks narrower than a warp's 128 elements (the kernel's per-lane path)."""
+    from recommend_b200.train import FlatGradBuffer, ClipRMSprop
+    G, Fd = 3, 2 * d
+    g = torch.Generator().manual_seed(11)
+    mk = lambda *s: torch.nn.Parameter(torch.randn(*s, generator=g).cuda())
+    Wqkv, W1, b1, plain = mk(G, d, 3 * d), mk(G, d, Fd), mk(G, Fd), mk(d, d)
+    Wqkv._ot_clip_layout = (d * 3 * d, 3 * d, d)
+    W1._ot_clip_layout = (d * Fd,) * 3
+    b1._ot_clip_layout = (Fd,) * 3
+    params = [Wqkv, W1, b1, plain]
+    buf = FlatGradBuffer(params)
+    clip = 2.0
+    opt = ClipRMSprop(buf, lr=0.01, momentum=0.0, clip_norm=clip)
+    assert opt.n_slots == 3 * G + G + G + 1
+    w0 = [p.detach().cpu().double() for p in params]
+    # gradients whose per-variable norms straddle the clip: some variables are clipped, some are not
+    grads = [torch.randn(p.shape, generator=g, dtype=torch.float64) * sc for p, sc in zip(params, (0.02, 0.005, 0.3, 0.01))]
+    grads[0][1, :, d:2 * d] *= 20.0            # only the k kernel of group 1 is far above the clip
+    grads[1][2] *= 30.0
+    for p, gr in zip(params, grads):
+        p.grad.copy_(gr.float())
+    opt.step()
+    torch.cuda.synchronize()
+
+    def clipped(i, gr):
+        gr = gr.float().double()
+        if i == 0:
+            out = gr.clone()
+            for gi in range(G):
+                for part in range(3):
+                    sl = (gi, slice(None), slice(part * d, (part + 1) * d))
+                    out[sl] = O.clip_by_norm(gr[sl], clip)
+            return out
+        if i in (1, 2):
+            return torch.stack([O.clip_by_norm(gr[gi], clip) for gi in range(G)])
+        return O.clip_by_norm(gr, clip)
+
+    n_clipped = 0
+    for i, (p, gr, w) in enumerate(zip(params, grads, w0)):
+        gc = clipped(i, gr)
+        n_clipped += int(not torch.equal(gc, gr.float().double()))
+        want, _, _ = O.rmsprop_step(w, gc, torch.zeros_like(gc), None, 0.01, 0.9, 0.0, 1e-7)
+        err = (p.detach().cpu().double() - want).abs().max().item() / want.abs().max().item()
+        assert err < 2e-6, (i, err)
+    assert n_clipped >= 2
+    # the packed-tensor granularity of round 1 gives a different update: the test can tell the two apart
+    whole = O.clip_by_norm(grads[0].float().double(), clip)
+    assert not torch.allclose(whole, clipped(0, grads[0]), rtol=1e-3)
+    norms = opt.grad_norms().cpu().double()
+    assert torch.allclose(norms[1 * 3 + 1], grads[0][1, :, d:2 * d].float().double().norm(), rtol=1e-5)

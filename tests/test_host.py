@@ -85,7 +85,7 @@ def test_position_segments_match_oracle_rule(alignment):
 
 def test_library_loads_and_exports_every_declared_symbol():
     lib = _lib.load()
-    assert lib.ot_version() == 10
+    assert lib.ot_version() == _lib.ABI_VERSION == int(re.search(r'#define OT_ABI_VERSION (\d+)', open(HEADER).read()).group(1))
     declared = set(re.findall(r'^\s*(?:int|const char\*)\s+(ot_\w+)\s*\(', open(HEADER).read(), re.M))
     assert declared == set(_lib.EXPORTED_SYMBOLS)
     for name in declared:
@@ -301,17 +301,15 @@ def test_evaluator_percentile_is_numpy_linear():
 
 
 def test_unsupported_head_dims_are_errors_before_any_device_work():
-    """Argument validation of the attention entry points returns before the first CUDA call, so it runs without a GPU: head_dim 32
-    is built but unverified on hardware and stays an unsupported-shape error unless OT_ENABLE_HEAD_DIM_32=1."""
-    if os.environ.get('OT_ENABLE_HEAD_DIM_32') == '1':
-        pytest.skip('head_dim 32 enabled in this environment')
+    """Argument validation of the attention entry points returns before the first CUDA call, so it runs without a GPU: head dims
+    other than 32 / 64 / 96 are an unsupported-shape error, never a fallback."""
     lib = _lib.load()
     p = _lib.AttnParams()
     for f in ('q', 'k', 'v', 'o', 'lse', 'd_o', 'dq', 'dk', 'dv', 'delta'):
         setattr(p, f, 4096)                                  # never dereferenced: the shape check comes first
     p.ldq = p.ldk = p.ldv = p.ldo = p.lddo = p.lddq = p.lddk = p.lddv = 128
     p.B, p.H, p.Lq, p.Lk = 2, 4, 4, 4
-    for hd in (32, 48, 128):
+    for hd in (16, 48, 128):
         p.head_dim = hd
         for fn in (lib.ot_attn_fwd, lib.ot_attn_bwd):
             assert fn(ctypes.byref(p), None) == -2           # OT_ERR_UNSUPPORTED_SHAPE, never a fallback

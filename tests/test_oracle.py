@@ -310,3 +310,21 @@ def test_two_stage_extend_with_pyramid_only_grows_key_sets():
         assert b[0].shape[1] == a[0].shape[1] + n and torch.equal(b[0][:, :a[0].shape[1]], a[0])    # old keys untouched
         n = min(n, keep_S)
     assert not torch.allclose(O.two_stage_score(P, cfg, ext, non_seq)['ctr'], O.two_stage_score(P, cfg, base, non_seq)['ctr'])
+
+
+def test_clip_is_per_keras_variable():
+    """OT/train.py:133-135 clips per Keras variable: every weight-group index of the packed per-position Dense tensors is one."""
+    g = torch.zeros(3, 2, 2, dtype=torch.float64)
+    g[0] = 3.0          # ||.|| = 6
+    g[1] = 0.5          # ||.|| = 1
+    g[2, 0, 0] = 10.0   # ||.|| = 10
+    out = O.clip_per_keras_variable('blocks.0.ffn.W1', g, 2.0)
+    assert torch.allclose(out[0], g[0] * (2.0 / 6.0)) and torch.equal(out[1], g[1]) and torch.allclose(out[2], g[2] * 0.2)
+    whole = O.clip_per_keras_variable('blocks.0.attention.Wo', g, 2.0)     # not packed: one variable
+    assert torch.allclose(whole, g * (2.0 / float(g.norm())))
+    P = {'blocks.0.ffn.b1': torch.zeros(2, 4, dtype=torch.float64), 'output_norm.scale': torch.ones(4, dtype=torch.float64)}
+    G = {'blocks.0.ffn.b1': torch.tensor([[3.0, 4.0, 0, 0], [0.3, 0.4, 0, 0]], dtype=torch.float64), 'output_norm.scale': torch.full((4,), 5.0, dtype=torch.float64)}
+    st = {}
+    O.clip_rmsprop_update(P, G, st, lr=1.0, rho=0.0, momentum=0.0, eps=1e-7, clip_norm=1.0)     # rho = 0: rms == clipped g^2
+    assert torch.allclose(st['blocks.0.ffn.b1']['rms'][0], torch.tensor([0.36, 0.64, 0, 0], dtype=torch.float64))   # (3,4)/5 clipped to norm 1
+    assert torch.allclose(st['blocks.0.ffn.b1']['rms'][1], torch.tensor([0.09, 0.16, 0, 0], dtype=torch.float64))   # below the clip: untouched
