@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define OT_ABI_VERSION 11
+#define OT_ABI_VERSION 12
 
 int ot_version(void);
 const char* ot_last_error_string(void);
@@ -108,6 +108,37 @@ typedef struct ot_gemm_params {
 int ot_mixed_gemm(const ot_gemm_params* p, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Fused MixedFFN forward  (one kernel for OT/model.py:149-163 + the residual / dropout of :198 + the next RMSNorm)
+ *   y[row, :] = res[row, :] + drop( gelu_erf(zn[row, :] . W1[g] + b1[g]) . W2[g] + b2[g] ),   g = group(row)
+ * The hidden activation [rows, F] stays on chip; `pre` (optional, bf16 [rows, F]) receives zn.W1 + b1 for the backward pass.
+ * W1: [n_groups, F, d] (N = F, K = d), W2: [n_groups, d, F] (N = d, K = F), both bf16 with K contiguous (the same transposed
+ * compute copies ot_mixed_gemm takes).  Segments as in ot_gemm_params (a_row_start must equal row_start).
+ * flags: OT_EPI_RESIDUAL | OT_EPI_DROPOUT | OT_EPI_NORM (bias is always applied); res_hp / out_hp / hp_row0, drop_*, norm_* as
+ * in ot_gemm_params.  Built for d == 256 and F % 128 == 0; any other shape is OT_ERR_UNSUPPORTED_SHAPE (callers use two
+ * ot_mixed_gemm launches there). */
+typedef struct ot_ffn_params {
+  const void* zn; int64_t ldzn;
+  const void* W1; int64_t ldw1;
+  const void* W2; int64_t ldw2;
+  const float* b1; int64_t b1_group_stride;
+  const float* b2; int64_t b2_group_stride;
+  int32_t n_groups, d, F;
+  int32_t n_segs;
+  int32_t flags;
+  ot_gemm_seg segs[3];
+  void* out; int64_t ldo;
+  void* pre; int64_t ldpre;          /* may be NULL (evaluation) */
+  const void* res; int64_t ldr;
+  const float* res_hp; float* out_hp; int64_t ld_hp; int64_t hp_row0;
+  uint32_t drop_seed; float drop_rate;
+  void* norm_out; int64_t ld_norm;
+  const float* norm_gain;
+  float* norm_rstd;
+  float norm_eps;
+} ot_ffn_params;
+int ot_ffn_fwd(const ot_ffn_params* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Weight gradient  (tcgen05, both operands MN-major, split over rows, fp32 atomic accumulate)
  *   C[group][m, n] += sum_rows P[row, m] * Q[row, n]
  * Replaces tape.gradient (OT/train.py:131) for every Dense kernel on the path.
@@ -138,6 +169,9 @@ typedef struct ot_wgrad_params {
    * q_colsum[g * q_colsum_group_stride + n] += sum_rows Q[row, n], fp32 atomics, caller zeroes; NULL = off */
   float* q_colsum;
   int64_t q_colsum_group_stride;
+  /* p_gelu != 0: the kernel contracts gelu_erf(P) instead of P (P = the saved FFN pre-activation: dW2 = gelu(pre)^T dy after
+   * ot_ffn_fwd, which keeps the hidden activation on chip).  block_n 256 / 128-byte swizzle only. */
+  int32_t p_gelu;
 } ot_wgrad_params;
 
 int ot_wgrad(const ot_wgrad_params* p, void* stream);

@@ -34,6 +34,26 @@ if what in ('gemm', 'all'):
     dW = torch.zeros(33, d, F, device='cuda')
     for _ in range(2):
         ops.wgrad_rows(zn, dpre, segs, dW, d * F, F, 1)                                               # dW1
+if what in ('ffn', 'all'):
+    # round 2: fused FFN forward (h stays on chip) and dW2 with the GELU rebuilt inside the weight-gradient kernel
+    zn, W1, W2 = rnd(rows, d), rnd(33, F, d) * 0.06, rnd(33, d, F) * 0.03
+    b1, b2 = 0.1 * torch.randn(33, F, device='cuda'), 0.1 * torch.randn(33, d, device='cuda')
+    res, gain = rnd(rows, d), torch.ones(d, device='cuda')
+    y, nout = torch.empty(rows, d, dtype=bf16, device='cuda'), torch.empty(rows, d, dtype=bf16, device='cuda')
+    rstd, pre = torch.empty(rows, device='cuda'), torch.empty(rows, F, dtype=bf16, device='cuda')
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(8)]
+    for i in range(3):
+        ev[2 * i].record()
+        ops.ffn_fused(zn, W1, b1, W2, b2, segs, y, pre=pre, res=res, dropout=(7, 0.1), norm=(nout, gain, rstd, 1e-6))
+        ev[2 * i + 1].record()
+    ops.ffn_fused(zn, W1, b1, W2, b2, segs, y, res=res)                                                  # evaluation form: no pre, no norm
+    dy = rnd(rows, d)
+    dW2, db2 = torch.zeros(33, F, d, device='cuda'), torch.zeros(33, d, device='cuda')
+    ev[6].record()
+    ops.wgrad_rows(pre, dy, segs, dW2, F * d, d, 1, q_colsum=db2, q_colsum_group_stride=d, p_gelu=True)
+    ev[7].record()
+    torch.cuda.synchronize()
+    print('ffn_fused layer-0 size (ms):', [round(ev[2 * i].elapsed_time(ev[2 * i + 1]), 3) for i in range(3)], 'wgrad gelu:', round(ev[6].elapsed_time(ev[7]), 3))
 if what in ('attn', 'all'):
     q, kv, do = rnd(rows, d), rnd(Lk * B, 2 * d), rnd(rows, d)
     o = torch.empty(rows, d, dtype=bf16, device='cuda')

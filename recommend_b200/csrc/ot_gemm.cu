@@ -21,13 +21,11 @@
 // The two TMEM accumulators (2*BN <= 512 columns) let the epilogue of tile i overlap the MMAs of
 // tile i+1.  Roofline: at d=256 every GEMM of the block is HBM-bound, so the
 // epilogue reads/writes each activation byte exactly once and in full 128-byte lines.
-#include "ot_common.cuh"
+#include "ot_gemm_common.cuh"
 #include "ot_host.h"
-#include "../../include/onetrans_b200.h"
 
 namespace ot {
 
-static constexpr int BM = 128;
 static constexpr int EPI_SETS = 4;
 static constexpr int EPI_SET_THREADS = 128;
 static constexpr int EPI_THREADS = EPI_SETS * EPI_SET_THREADS;
@@ -42,12 +40,6 @@ static constexpr int CH_BYTES = 128 * 64 * 2;   // one staged chunk: 128 rows x 
 #define OT_DUAL_LATE_WAIT 0     // experiment switch, see the dual-output pass of the epilogue; 0 = the verified build
 #endif
 static constexpr int TILE_SLOTS = 8;         // tile-index ring: producer -> MMA issuer and epilogue warps
-
-struct GemmSegDev {
-  int row_start, n_units, rows_per_unit, group_start, group_stride, a_row_start;
-  int mblk_start, mblk_per_unit;
-  uint32_t mpu_rcp;        // ceil(2^32 / mblk_per_unit): unit = umulhi(local, mpu_rcp), exact for local < 2^32 / mblk_per_unit
-};
 
 struct GemmKParams {
   int N, K;
@@ -68,41 +60,6 @@ struct GemmKParams {
   __nv_bfloat16* norm_out; long long ld_norm; const float* norm_gain; float* norm_rstd; float norm_eps;
   int* sched;              // dynamic tile counter (zeroed by the launcher) or NULL = static round-robin
 };
-
-struct TileInfo {
-  int row0, valid, group, a_c1, a_c2;
-};
-
-__device__ __forceinline__ int div_rcp(int n, uint32_t rcp, int d) {
-  return d == 1 ? n : static_cast<int>(__umulhi(static_cast<uint32_t>(n), rcp));
-}
-
-// Every epilogue warp decodes every tile, so this runs ~16 x tiles times per CTA: no divisions (host-made reciprocals)
-// and no dynamic indexing of the kernel parameters (that would copy the segment table to local memory).
-__device__ __forceinline__ TileInfo decode_tile(const GemmKParams& p, int mblk) {
-  const bool s2 = p.n_segs > 2 && mblk >= p.segs[2].mblk_start;
-  const bool s1 = !s2 && p.n_segs > 1 && mblk >= p.segs[1].mblk_start;
-#define OT_SEG(f) (s2 ? p.segs[2].f : s1 ? p.segs[1].f : p.segs[0].f)
-  const int mblk_per_unit = OT_SEG(mblk_per_unit);
-  const int rows_per_unit = OT_SEG(rows_per_unit);
-  const int local = mblk - OT_SEG(mblk_start);
-  const int unit = div_rcp(local, OT_SEG(mpu_rcp), mblk_per_unit);
-  const int sub = local - unit * mblk_per_unit;
-  const int riu = sub * BM;
-  TileInfo t;
-  t.row0 = OT_SEG(row_start) + unit * rows_per_unit + riu;
-  t.valid = min(BM, rows_per_unit - riu);
-  t.group = OT_SEG(group_start) + unit * OT_SEG(group_stride);
-  if (!p.a_transposed) {
-    t.a_c1 = OT_SEG(a_row_start) + unit * rows_per_unit + riu;
-    t.a_c2 = 0;
-  } else {
-    t.a_c1 = OT_SEG(a_row_start) + unit;
-    t.a_c2 = riu;
-  }
-#undef OT_SEG
-  return t;
-}
 
 template <int BN, int SWB>
 struct GemmCfg {

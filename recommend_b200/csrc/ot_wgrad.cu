@@ -12,6 +12,9 @@
 //   warp 0 lane*: TMA producer     warp 1 lane*: MMA issuer     all 4 warps: epilogue
 //   warps 2-3 (CTAs of the first M tile, when asked): column sums of the Q tiles as they pass through shared
 //   memory - the bias gradient of the same Dense layer without a second pass over Q
+//   warps 4-7 (PGELU instantiation only): apply GELU to the P tile in shared memory before the MMA reads it.  The fused FFN
+//   forward (ot_ffn_fused.cu) keeps h = gelu(pre) on chip and stores only the pre-activation; dW2 = h^T dy (OT/train.py:131 for
+//   the second Dense of OT/model.py:138,145) then takes P = pre and rebuilds h tile by tile instead of reading a stored copy
 #include <stdlib.h>
 #include "ot_common.cuh"
 #include "ot_host.h"
@@ -20,6 +23,7 @@
 namespace ot {
 
 static constexpr int WG_THREADS = 128;
+static constexpr int WG_XFORM_THREADS = 128;   // warps 4-7 of the PGELU instantiation
 static constexpr int WG_KROWS = 64;  // rows (contraction) per pipeline stage
 
 struct WgradSegDev {
@@ -42,6 +46,18 @@ struct WgradKParams {
   int vec_flush;   // C rows are contiguous along n and 16-byte aligned: flush with 4-wide vector reductions
 };
 
+// gelu of eight bf16 values (one 16-byte chunk), same arithmetic as the forward epilogue (ot_common.cuh gelu_erf2)
+__device__ __forceinline__ uint4 gelu_chunk(uint4 q) {
+  uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float a, b;
+    upk2(gelu_erf2(pk2(bf16lo(w[i]), bf16hi(w[i]))), a, b);
+    w[i] = pack_bf16x2(a, b);
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
 template <int BN, int SWB>
 struct WgradCfg {
   static constexpr int SLAB_COLS = SWB / 2;                  // columns per MN-major slab
@@ -53,12 +69,12 @@ struct WgradCfg {
   static constexpr int STAGE_BYTES = P_BYTES + Q_BYTES;
   static constexpr int STAGES_RAW = (227 * 1024 - 256) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256;   // barriers: (3 * STAGES + 1) * 8 + 4 bytes <= 256
   static constexpr int TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
 };
 
-template <int BN, int SWB>
-__global__ void __launch_bounds__(WG_THREADS, 1)
+template <int BN, int SWB, bool PGELU>
+__global__ void __launch_bounds__(WG_THREADS + (PGELU ? WG_XFORM_THREADS : 0), 1)
 ot_wgrad_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constant__ CUtensorMap tmQ0,
                 const __grid_constant__ CUtensorMap tmP1, const __grid_constant__ CUtensorMap tmQ1,
                 const __grid_constant__ WgradKParams p) {
@@ -69,7 +85,8 @@ ot_wgrad_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constant_
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES;
   uint64_t* done_bar = bars + 2 * STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+  uint64_t* xform_bar = bars + 2 * STAGES + 1;    // [STAGES] P tile transformed (PGELU only; 4 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -107,6 +124,7 @@ ot_wgrad_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constant_
       mbar_init(&empty_bar[i], do_colsum ? 3 : 1);   // tcgen05.commit (+ the two column-sum warps)
     }
     mbar_init(done_bar, 1);
+    if (PGELU) for (int i = 0; i < STAGES; ++i) mbar_init(&xform_bar[i], WG_XFORM_THREADS / 32);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -146,7 +164,7 @@ ot_wgrad_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constant_
         int stage = 0;
         uint32_t phase = 0;
         for (int i = 0; i < num_kb; ++i) {
-          mbar_wait(&full_bar[stage], phase);
+          mbar_wait(PGELU ? &xform_bar[stage] : &full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sp = smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint32_t sq = sp + Cfg::P_BYTES;
@@ -163,7 +181,38 @@ ot_wgrad_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constant_
         }
         umma_commit(done_bar);
       }
-    } else if (do_colsum) {
+    } else if (PGELU && warp >= 4) {
+      // warps 4-7: GELU of the P tile (64 rows x 128 columns = 1024 chunks of 16 bytes, 8 per thread), in place, then hand the
+      // stage to the MMA warp.  Rows past the end of a unit arrive zero-filled and stay zero (gelu(0) == 0).
+      const int t = threadIdx.x - WG_THREADS;
+      constexpr int CPR = 128 / 8;                   // chunks per tile row (all slabs)
+      constexpr int CPS = Cfg::SLAB_COLS / 8;        // chunks per slab row
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int i = 0; i < num_kb; ++i) {
+        mbar_wait(&full_bar[stage], phase);
+        uint8_t* sp = smem + stage * Cfg::STAGE_BYTES;
+        // all loads, then the arithmetic, then all stores: an in-place loop would serialise on possible aliasing (LDS after STS)
+        constexpr int NCH = (WG_KROWS * CPR) / WG_XFORM_THREADS;      // 8 chunks per thread
+        uint4 q[NCH];
+        uint4* ptr[NCH];
+#pragma unroll
+        for (int j = 0; j < NCH; ++j) {
+          const int idx = j * WG_XFORM_THREADS + t;
+          const int r = idx / CPR, ch = idx % CPR;
+          ptr[j] = reinterpret_cast<uint4*>(sp + (ch / CPS) * Cfg::SLAB_BYTES + swz_off<SWB>(r, ch % CPS));
+          q[j] = *ptr[j];
+        }
+#pragma unroll
+        for (int j = 0; j < NCH; ++j) q[j] = gelu_chunk(q[j]);
+#pragma unroll
+        for (int j = 0; j < NCH; ++j) *ptr[j] = q[j];
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&xform_bar[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    } else if (do_colsum && warp < 4) {
       // warps 2-3: thread t owns one 16-byte chunk (8 columns) of the Q tile and a group of its 64 rows
       constexpr int NCHK = BN / 8;                    // 16-byte chunks per tile row (8, 16 or 32)
       constexpr int RG = 64 / NCHK;                   // row groups: 64 threads = NCHK chunks x RG groups
@@ -195,7 +244,8 @@ ot_wgrad_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constant_
 #pragma unroll
       for (int e = 0; e < 8; ++e) atomicAdd(dst + e, acc[e]);
     }
-    // ---- epilogue: every warp flushes its 32 accumulator rows ----
+    // ---- epilogue: warps 0-3 flush their 32 accumulator rows each ----
+    if (warp < 4) {
     mbar_wait(done_bar, 0);
     tc_fence_after();
     const int m = mt * 128 + warp * 32 + lane;
@@ -217,22 +267,23 @@ ot_wgrad_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constant_
         for (int j = 0; j < 32; ++j) atomicAdd(crow + (long long)(c * 32 + j) * p.c_stride_n, __uint_as_float(v[j]));
       }
     }
+    }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
-template <int BN, int SWB>
+template <int BN, int SWB, bool PGELU = false>
 static int launch_wgrad(const CUtensorMap* tm, const WgradKParams& kp, int items, cudaStream_t st) {
   using Cfg = WgradCfg<BN, SWB>;
   static bool attr_done = false;
-  auto kern = ot_wgrad_kernel<BN, SWB>;
+  auto kern = ot_wgrad_kernel<BN, SWB, PGELU>;
   if (!attr_done) {
     OT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_done = true;
   }
-  kern<<<items, WG_THREADS, Cfg::SMEM_BYTES, st>>>(tm[0], tm[1], tm[2], tm[3], kp);
+  kern<<<items, WG_THREADS + (PGELU ? WG_XFORM_THREADS : 0), Cfg::SMEM_BYTES, st>>>(tm[0], tm[1], tm[2], tm[3], kp);
   OT_CUDA_CHECK(cudaGetLastError());
   return OT_OK;
 }
@@ -307,6 +358,10 @@ int wgrad_impl(const ot_wgrad_params* p, cudaStream_t st) {
   }
   if (p->n_segs == 1) { tm[2] = tm[0]; tm[3] = tm[1]; }
 
+  if (p->p_gelu) {
+    if (swb != 128 || bn != 256) OT_FAIL(OT_ERR_UNSUPPORTED_SHAPE, "ot_wgrad: p_gelu is built for block_n 256 with the 128-byte swizzle (Ndim=%d)", p->Ndim);
+    return launch_wgrad<256, 128, true>(tm, kp, items, st);
+  }
   if (swb == 128) {
     if (bn == 256) return launch_wgrad<256, 128>(tm, kp, items, st);
     if (bn == 128) return launch_wgrad<128, 128>(tm, kp, items, st);

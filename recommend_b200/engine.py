@@ -168,16 +168,24 @@ def ffn_forward(zn: torch.Tensor, res: Optional[torch.Tensor], w: BlockWeights, 
     rows_t, d = zn.shape
     F = w.W1_f.shape[1]
     dev = zn.device
+    y = torch.empty(rows_t, d, dtype=bf16, device=dev)
+    y_hp = None
+    hp = res_hp is not None and res is not None
+    if hp:
+        hp0 = rows_t - res_hp.shape[0]          # the fp32 stream covers the last rows (the NS tokens)
+        y_hp = torch.empty(res_hp.shape[0], d, dtype=torch.float32, device=dev)
+    nrm = _fused_norm_args(norm, rows_t, d, dev)
+    if ops.can_fuse_ffn(d, F):
+        # one kernel: h = gelu(zn W1 + b1) stays on chip, only the pre-activation (the backward's GELU' input) is stored
+        pre = torch.empty(rows_t, F, dtype=bf16, device=dev) if save else None
+        ops.ffn_fused(zn, w.W1_f, b1, w.W2_f, b2, split_segments(segs, hp0) if hp else segs, y, pre=pre, res=res,
+                      res_hp=res_hp if hp else None, out_hp=y_hp, hp_row0=hp0 if hp else 0, dropout=drop, norm=nrm)
+        return y, (pre, None), y_hp
     h = torch.empty(rows_t, F, dtype=bf16, device=dev)
     pre = torch.empty(rows_t, F, dtype=bf16, device=dev) if save else None
     ops.mixed_gemm(zn, w.W1_f, segs, h, flags=OT_EPI_BIAS | OT_EPI_GELU, bias=b1, out2=pre)
-    y = torch.empty(rows_t, d, dtype=bf16, device=dev)
     flags = OT_EPI_BIAS | (OT_EPI_RESIDUAL if res is not None else 0)
-    y_hp = None
-    nrm = _fused_norm_args(norm, rows_t, d, dev)
-    if res_hp is not None and res is not None:
-        hp0 = rows_t - res_hp.shape[0]          # the fp32 stream covers the last rows (the NS tokens)
-        y_hp = torch.empty(res_hp.shape[0], d, dtype=torch.float32, device=dev)
+    if hp:
         ops.mixed_gemm(h, w.W2_f, split_segments(segs, hp0), y, flags=flags, bias=b2, res=res, res_hp=res_hp, out_hp=y_hp, hp_row0=hp0,
                        dropout=drop, norm=nrm)
     else:
@@ -192,7 +200,9 @@ def ffn_backward(dy: torch.Tensor, zn: torch.Tensor, saved, w: BlockWeights, seg
     rows_t, d = zn.shape
     F = pre.shape[1]
     dev = zn.device
-    ops.wgrad_rows(h, dy, segs, W2_grad, F * d, d, 1, q_colsum=b2_grad, q_colsum_group_stride=d)   # dW2 and db2
+    # dW2 and db2.  After the fused forward (h kept on chip) the weight-gradient kernel rebuilds h = gelu(pre) tile by tile
+    ops.wgrad_rows(h if h is not None else pre, dy, segs, W2_grad, F * d, d, 1, q_colsum=b2_grad, q_colsum_group_stride=d,
+                   p_gelu=h is None)
     dpre = torch.empty(rows_t, F, dtype=bf16, device=dev)
     ops.mixed_gemm(dy, w.W2_b, segs, dpre, flags=OT_EPI_GELU_GRAD, aux=pre)
     ops.wgrad_rows(zn, dpre, segs, W1_grad, d * F, F, 1, q_colsum=b1_grad, q_colsum_group_stride=F)  # dW1 and db1

@@ -178,6 +178,71 @@ def mixed_gemm(A: torch.Tensor, W: torch.Tensor, segs: Sequence[Seg], out: torch
     return out
 
 
+def can_fuse_ffn(d: int, F: int) -> bool:
+    """``ot_ffn_fwd`` is built for d == 256 (its [128 x d] output accumulator and two [128 x 128] FFN-1 accumulators fill the
+    512 TMEM columns) and F a multiple of its 128-column chunk.  ``OT_FFN_FUSED=0`` selects the two-GEMM path for A/B runs."""
+    import os
+    return d == 256 and F % 128 == 0 and os.environ.get('OT_FFN_FUSED', '1') != '0'
+
+
+def ffn_fused(zn: torch.Tensor, W1_f: torch.Tensor, b1: torch.Tensor, W2_f: torch.Tensor, b2: torch.Tensor, segs: Sequence[Seg],
+              out: torch.Tensor, *, pre: Optional[torch.Tensor] = None, res: Optional[torch.Tensor] = None,
+              res_hp: Optional[torch.Tensor] = None, out_hp: Optional[torch.Tensor] = None, hp_row0: int = 0,
+              dropout: Optional[Tuple[int, float]] = None,
+              norm: Optional[Tuple[torch.Tensor, torch.Tensor, Optional[torch.Tensor], float]] = None) -> torch.Tensor:
+    """``out = res + drop(gelu(zn @ W1[g].T + b1[g]) @ W2[g].T + b2[g])`` in one kernel (MixedFFN.call, OT/model.py:149-163, with
+    the residual / dropout of :198); the hidden activation never reaches HBM.  ``W1_f [G, F, d]``, ``W2_f [G, d, F]`` bf16;
+    ``pre [rows, F]`` receives the pre-activation for the backward pass; ``norm`` as in ``mixed_gemm``."""
+    for t, n in ((zn, 'zn'), (W1_f, 'W1'), (W2_f, 'W2'), (out, 'out')):
+        _check_bf16(t, n)
+    G, F, d = W1_f.shape
+    assert W2_f.shape == (G, d, F) and zn.dim() == 2 and zn.shape[1] == d
+    assert W1_f.stride(2) == 1 and W1_f.stride(0) == F * W1_f.stride(1) and W2_f.stride(2) == 1 and W2_f.stride(0) == d * W2_f.stride(1)
+    assert b1.dtype == torch.float32 and b2.dtype == torch.float32 and b1.is_cuda and b2.is_cuda
+    p = L.FfnParams()
+    p.zn, p.ldzn, p.W1, p.ldw1, p.W2, p.ldw2 = zn.data_ptr(), zn.stride(0), W1_f.data_ptr(), W1_f.stride(1), W2_f.data_ptr(), W2_f.stride(1)
+    p.b1, p.b1_group_stride = b1.data_ptr(), (b1.stride(0) if b1.dim() == 2 else 0)
+    p.b2, p.b2_group_stride = b2.data_ptr(), (b2.stride(0) if b2.dim() == 2 else 0)
+    p.n_groups, p.d, p.F, p.n_segs = G, d, F, len(segs)
+    flags = 0
+    for i, s in enumerate(segs):
+        sg = p.segs[i]
+        sg.row_start, sg.n_units, sg.rows_per_unit, sg.group_start, sg.group_stride = s[:5]
+        sg.a_row_start = s[0]
+    p.out, p.ldo = out.data_ptr(), out.stride(0)
+    if pre is not None:
+        _check_bf16(pre, 'pre')
+        p.pre, p.ldpre = pre.data_ptr(), pre.stride(0)
+    if res is not None:
+        _check_bf16(res, 'res')
+        flags |= L.OT_EPI_RESIDUAL
+        p.res, p.ldr = res.data_ptr(), res.stride(0)
+    if dropout is not None and dropout[1] > 0.0:
+        flags |= L.OT_EPI_DROPOUT
+        p.drop_seed, p.drop_rate = dropout[0] & 0xFFFFFFFF, dropout[1]
+    if res_hp is not None:
+        assert res is not None and out_hp is not None and res_hp.dtype == torch.float32 and out_hp.dtype == torch.float32
+        assert res_hp.stride(-1) == 1 and out_hp.stride(-1) == 1 and res_hp.stride(0) == out_hp.stride(0)
+        p.res_hp, p.out_hp, p.ld_hp, p.hp_row0 = res_hp.data_ptr(), out_hp.data_ptr(), res_hp.stride(0), hp_row0
+    if norm is not None:
+        n_out, n_gain, n_rstd, n_eps = norm
+        _check_bf16(n_out, 'norm_out')
+        assert n_gain.dtype == torch.float32 and n_gain.is_cuda and n_gain.numel() == d
+        flags |= L.OT_EPI_NORM
+        p.norm_out, p.ld_norm, p.norm_gain, p.norm_eps = n_out.data_ptr(), n_out.stride(0), n_gain.data_ptr(), n_eps
+        if n_rstd is not None:
+            assert n_rstd.dtype == torch.float32 and n_rstd.is_contiguous()
+            p.norm_rstd = n_rstd.data_ptr()
+    p.flags = flags
+    rows = sum(s[1] * s[2] for s in segs)
+    groups = sum((s[1] if s[4] else 1) for s in segs)
+    # algorithmic bytes: zn in, y out (+ residual in, norm out), the saved pre-activation, the weights once per group
+    n_io = 2 + (res is not None) + (norm is not None)
+    _run('ot_ffn_fwd', L.load().ot_ffn_fwd, p, f'd{d}_F{F}_f{flags}{"_pre" if pre is not None else ""}', 4.0 * rows * d * F,
+         n_io * rows * d * 2.0 + (rows * F * 2.0 if pre is not None else 0.0) + groups * 2.0 * d * F * 2.0)
+    return out
+
+
 def can_fuse_norm(N: int) -> bool:
     """OT_EPI_NORM needs whole rows inside one 128 x N tile."""
     return N in (64, 128, 256)
@@ -188,8 +253,8 @@ WSeg = Tuple[torch.Tensor, int, int, torch.Tensor, int, int, int, int, int, int]
 
 def wgrad(segs: Sequence[dict], Cout: torch.Tensor, Mdim: int, Ndim: int, c_group_stride: int, c_stride_m: int,
           c_stride_n: int, *, block_n: int = 0, swizzle: int = 0, target_ctas: int = 0,
-          q_colsum: Optional[torch.Tensor] = None, q_colsum_group_stride: int = 0) -> None:
-    """``Cout[g][m, n] += sum_rows P[row, m] * Q[row, n]``; each seg is a dict with keys
+          q_colsum: Optional[torch.Tensor] = None, q_colsum_group_stride: int = 0, p_gelu: bool = False) -> None:
+    """``Cout[g][m, n] += sum_rows P[row, m] * Q[row, n]`` (``p_gelu``: ``gelu(P[row, m])``, rebuilt tile by tile); each seg is a dict with keys
     P, p_stride_row, p_stride_unit, Q, q_stride_row, q_stride_unit, n_units, rows_per_unit, group_start,
     group_stride.  ``Cout`` is an fp32 tensor (any view); strides in elements.  ``q_colsum`` (fp32, optional) also
     receives ``sum_rows Q[row, n]`` per group - the bias gradient of the same Dense layer, for free."""
@@ -210,14 +275,16 @@ def wgrad(segs: Sequence[dict], Cout: torch.Tensor, Mdim: int, Ndim: int, c_grou
     if q_colsum is not None:
         assert q_colsum.dtype == torch.float32 and q_colsum.is_cuda
         p.q_colsum, p.q_colsum_group_stride = q_colsum.data_ptr(), q_colsum_group_stride
+    p.p_gelu = 1 if p_gelu else 0
     rows = sum(s['n_units'] * s['rows_per_unit'] for s in segs)
     groups = sum((s['n_units'] if s['group_stride'] else 1) for s in segs)
-    _run('ot_wgrad', L.load().ot_wgrad, p, f'M{Mdim}_N{Ndim}', 2.0 * rows * Mdim * Ndim,
+    _run('ot_wgrad', L.load().ot_wgrad, p, f'M{Mdim}_N{Ndim}' + ('_gelu' if p_gelu else ''), 2.0 * rows * Mdim * Ndim,
          rows * (Mdim + Ndim) * 2.0 + groups * Mdim * Ndim * 4.0)
 
 
 def wgrad_rows(P: torch.Tensor, Q: torch.Tensor, segs: Sequence[Seg], Cout: torch.Tensor, c_group_stride: int,
-               c_stride_m: int, c_stride_n: int, q_colsum: Optional[torch.Tensor] = None, q_colsum_group_stride: int = 0) -> None:
+               c_stride_m: int, c_stride_n: int, q_colsum: Optional[torch.Tensor] = None, q_colsum_group_stride: int = 0,
+               p_gelu: bool = False) -> None:
     """Weight gradient for row-aligned 2-D activations ``P [rows, Mdim]`` and ``Q [rows, Ndim]`` whose
     rows are described by the same position segments the forward GEMM used."""
     wsegs = []
@@ -226,7 +293,7 @@ def wgrad_rows(P: torch.Tensor, Q: torch.Tensor, segs: Sequence[Seg], Cout: torc
                           Q=Q[row_start:], q_stride_row=Q.stride(0), q_stride_unit=rpu * Q.stride(0),
                           n_units=n_units, rows_per_unit=rpu, group_start=g0, group_stride=gs))
     wgrad(wsegs, Cout, P.shape[1], Q.shape[1], c_group_stride, c_stride_m, c_stride_n, q_colsum=q_colsum,
-          q_colsum_group_stride=q_colsum_group_stride)
+          q_colsum_group_stride=q_colsum_group_stride, p_gelu=p_gelu)
 
 
 def attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, o: torch.Tensor, lse: torch.Tensor, B: int, H: int,

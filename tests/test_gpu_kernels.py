@@ -310,3 +310,124 @@ def test_full_size_gemm_c2_ffn():
     for r0, g in [(0, 0), (n_s * B - 300, 0), (n_s * B, 1), ((n_s + 31) * B + 1000, 32), (rows - 128, 32), (500000, 0)]:
         sl = slice(r0, r0 + 128)
         close(out[sl], A[sl].float() @ W[g].float().t() + bias[g])
+
+
+def _ffn_ref(zn, W1, b1, W2, b2, segs, res=None, mask=None, res_hp=None, hp_row0=0):
+    """fp32 reference of the fused FFN with the kernel's storage points: h rounded to bf16 before the second product."""
+    rows = zn.shape[0]
+    pre = torch.zeros(rows, W1.shape[1], device='cuda')
+    y = torch.zeros(rows, W2.shape[1], device='cuda')
+    for (r0, n_units, rpu, g0, gs) in segs:
+        for u in range(n_units):
+            sl, g = slice(r0 + u * rpu, r0 + (u + 1) * rpu), g0 + u * gs
+            pre[sl] = zn[sl].float() @ W1[g].float().t() + b1[g]
+            h = torch.nn.functional.gelu(pre[sl]).to(bf16).float()
+            y[sl] = h @ W2[g].float().t() + b2[g]
+    if mask is not None:
+        y = y * mask
+    if res is not None:
+        r = res.float().clone()
+        if res_hp is not None:
+            r[hp_row0:] = res_hp
+        y = y + r
+    return pre, y
+
+
+@pytest.mark.parametrize('B,n_s,n_ns,F,opts', [(256, 3, 2, 1024, 'res,norm,pre'), (128, 1, 0, 256, ''), (40, 5, 3, 512, 'res,norm,pre,hp'),
+                                                 (200, 2, 2, 1024, 'res,drop,norm,pre,hp'), (384, 4, 0, 1024, 'res,pre'), (64, 0, 4, 256, 'norm')])
+def test_ffn_fused_forward(B, n_s, n_ns, F, opts):
+    """ot_ffn_fwd (MixedFFN.call + residual + dropout + next RMSNorm in one kernel, OT/model.py:149-163,196-198) against an fp32
+    reference and against the two-GEMM path it replaces: shared run + per-token NS runs, full and partial tiles."""
+    d, G = 256, 1 + 5
+    rows = (n_s + n_ns) * B
+    zn = rnd(rows, d, seed=41)
+    W1, W2 = rnd(G, F, d, scale=0.06, seed=42), rnd(G, d, F, scale=0.03, seed=43)
+    b1, b2 = 0.1 * torch.randn(G, F, device='cuda'), 0.1 * torch.randn(G, d, device='cuda')
+    segs = ([(0, 1, n_s * B, 0, 0)] if n_s else []) + ([(n_s * B, n_ns, B, 2, 1)] if n_ns else [])
+    res = rnd(rows, d, seed=44) if 'res' in opts else None
+    hp = 'hp' in opts and n_ns > 0
+    hp0 = n_s * B
+    res_hp = (res[hp0:].float() + 1e-3 * torch.randn(rows - hp0, d, device='cuda')) if hp else None
+    out_hp = torch.empty_like(res_hp) if hp else None
+    pre = torch.full((rows, F), float('nan'), dtype=bf16, device='cuda') if 'pre' in opts else None
+    y = torch.full((rows, d), float('nan'), dtype=bf16, device='cuda')
+    gain = 1.0 + 0.1 * torch.randn(d, device='cuda')
+    nout = torch.full((rows, d), float('nan'), dtype=bf16, device='cuda') if 'norm' in opts else None
+    rstd = torch.empty(rows, device='cuda') if 'norm' in opts else None
+    drop = (1234, 0.1) if 'drop' in opts else None
+    mask = None
+    if drop:
+        mask = ops.dropout_mask(torch.ones(rows, d, dtype=bf16, device='cuda'), drop[0], drop[1]).float()
+    ops.ffn_fused(zn, W1, b1, W2, b2, segs, y, pre=pre, res=res, res_hp=res_hp, out_hp=out_hp, hp_row0=hp0 if hp else 0,
+                  dropout=drop, norm=(nout, gain, rstd, 1e-6) if nout is not None else None)
+    pre_ref, y_ref = _ffn_ref(zn, W1, b1, W2, b2, segs, res, mask, res_hp, hp0)
+    if pre is not None:
+        close(pre, pre_ref)
+    assert not torch.isnan(y.float()).any()
+    assert ((y.float() - y_ref).abs().max() / y_ref.abs().max()).item() < 1e-2
+    if hp:
+        assert ((out_hp - y_ref[hp0:]).abs().max() / y_ref.abs().max()).item() < 3e-3
+    if nout is not None:
+        r_ref = torch.rsqrt(y_ref.square().mean(-1) + 1e-6)
+        assert ((rstd - r_ref).abs().max() / r_ref.abs().max()).item() < 2e-3
+        n_ref = y_ref * r_ref[:, None] * gain
+        assert ((nout.float() - n_ref).abs().max() / n_ref.abs().max()).item() < 1.5e-2
+    # the two-GEMM path on the same inputs (same storage points except that it normalises the bf16-rounded y)
+    h2 = torch.empty(rows, F, dtype=bf16, device='cuda')
+    y2 = torch.empty(rows, d, dtype=bf16, device='cuda')
+    ops.mixed_gemm(zn, W1, segs, h2, flags=OT_EPI_BIAS | OT_EPI_GELU, bias=b1)
+    from recommend_b200.engine import split_segments
+    kw = dict(res_hp=res_hp, out_hp=torch.empty_like(res_hp), hp_row0=hp0) if hp else {}
+    ops.mixed_gemm(h2, W2, split_segments(segs, hp0) if hp else segs, y2, flags=OT_EPI_BIAS | (OT_EPI_RESIDUAL if res is not None else 0), bias=b2, res=res,
+                   dropout=drop, **kw)
+    assert ((y.float() - y2.float()).abs().max() / y_ref.abs().max()).item() < 1e-2
+
+
+def test_ffn_fused_full_size_and_repeatable():
+    """BASELINE config 2 layer-5 size (32 NS tokens x 2048 rows, one weight group each) and a layer-0-like shared run: the kernel is
+    deterministic (same bits twice) and equals the two-GEMM path at full size."""
+    d, F, B, n_ns = 256, 1024, 2048, 32
+    rows = (8 + n_ns) * B
+    zn = rnd(rows, d, seed=51)
+    W1, W2 = rnd(1 + n_ns, F, d, scale=0.06, seed=52), rnd(1 + n_ns, d, F, scale=0.03, seed=53)
+    b1, b2 = 0.1 * torch.randn(1 + n_ns, F, device='cuda'), 0.1 * torch.randn(1 + n_ns, d, device='cuda')
+    res = rnd(rows, d, seed=54)
+    segs = [(0, 1, 8 * B, 0, 0), (8 * B, n_ns, B, 1, 1)]
+    outs = []
+    for _ in range(2):
+        y = torch.empty(rows, d, dtype=bf16, device='cuda')
+        pre = torch.empty(rows, F, dtype=bf16, device='cuda')
+        ops.ffn_fused(zn, W1, b1, W2, b2, segs, y, pre=pre, res=res)
+        outs.append((y, pre))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    h2 = torch.empty(rows, F, dtype=bf16, device='cuda')
+    pre2 = torch.empty(rows, F, dtype=bf16, device='cuda')
+    y2 = torch.empty(rows, d, dtype=bf16, device='cuda')
+    ops.mixed_gemm(zn, W1, segs, h2, flags=OT_EPI_BIAS | OT_EPI_GELU, bias=b1, out2=pre2)
+    ops.mixed_gemm(h2, W2, segs, y2, flags=OT_EPI_BIAS | OT_EPI_RESIDUAL, bias=b2, res=res)
+    close(outs[0][1], pre2, 1e-2)                                           # same products, at most a bf16 rounding apart
+    assert ((outs[0][0].float() - y2.float()).abs().max() / y2.float().abs().max()).item() < 1e-2
+
+
+@pytest.mark.parametrize('B,n_s,n_ns', [(256, 3, 2), (40, 5, 3), (100, 0, 4)])
+def test_wgrad_with_gelu_of_p(B, n_s, n_ns):
+    """dW2 = gelu(pre)^T dy with the GELU applied to the P tiles inside the weight-gradient kernel (p_gelu) equals the plain
+    weight gradient of a stored h = gelu(pre)."""
+    F, d, G = 512, 256, 1 + 5
+    rows = (n_s + n_ns) * B
+    pre, dy = rnd(rows, F, seed=61), rnd(rows, d, seed=62)
+    segs = ([(0, 1, n_s * B, 0, 0)] if n_s else []) + ([(n_s * B, n_ns, B, 2, 1)] if n_ns else [])
+    h = torch.nn.functional.gelu(pre.float()).to(bf16)
+    C1 = torch.zeros(G, F, d, device='cuda')
+    C2 = torch.zeros(G, F, d, device='cuda')
+    cs1, cs2 = torch.zeros(G, d, device='cuda'), torch.zeros(G, d, device='cuda')
+    ops.wgrad_rows(h, dy, segs, C1, F * d, d, 1, q_colsum=cs1, q_colsum_group_stride=d)
+    ops.wgrad_rows(pre, dy, segs, C2, F * d, d, 1, q_colsum=cs2, q_colsum_group_stride=d, p_gelu=True)
+    ref = torch.zeros(G, F, d, device='cuda')
+    for (r0, n_units, rpu, g0, gs) in segs:
+        for u in range(n_units):
+            sl = slice(r0 + u * rpu, r0 + (u + 1) * rpu)
+            ref[g0 + u * gs] += h[sl].float().t() @ dy[sl].float()
+    assert ((C1 - ref).abs().max() / ref.abs().max()).item() < 2e-3
+    assert ((C2 - ref).abs().max() / ref.abs().max()).item() < 1e-2           # tanh-form GELU + bf16 rounding of h inside the kernel
+    assert torch.allclose(cs1, cs2, rtol=1e-4, atol=1e-3)

@@ -314,22 +314,26 @@ def test_eval_forward_saves_no_activations():
     P, model = _build(ocfg, cfg)
     non_seq, seq, _ = O.synthetic_batch(ocfg, 8, (20, 10, 5))
     seen = []
-    real = ops.mixed_gemm
+    real_gemm, real_ffn = ops.mixed_gemm, ops.ffn_fused
 
-    def spy(*a, **kw):
+    def spy_gemm(*a, **kw):
         seen.append(kw.get('out2') is not None)
-        return real(*a, **kw)
+        return real_gemm(*a, **kw)
+
+    def spy_ffn(*a, **kw):
+        seen.append(kw.get('pre') is not None)
+        return real_ffn(*a, **kw)
     from recommend_b200 import engine
-    engine.ops.mixed_gemm = spy
+    engine.ops.mixed_gemm, engine.ops.ffn_fused = spy_gemm, spy_ffn
     try:
         with torch.no_grad():
             model(to_cuda(non_seq), to_cuda(seq))
-        assert not any(seen)
+        assert seen and not any(seen)
         seen.clear()
         model(to_cuda(non_seq), to_cuda(seq), training=True)
         assert any(seen)
     finally:
-        engine.ops.mixed_gemm = real
+        engine.ops.mixed_gemm, engine.ops.ffn_fused = real_gemm, real_ffn
 
 
 def test_dropout_forward_backward_consistency():

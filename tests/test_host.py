@@ -94,7 +94,7 @@ def test_library_loads_and_exports_every_declared_symbol():
 
 def test_ctypes_structs_match_header_layout():
     """Compile a C probe that prints sizeof/offsetof for every params struct and compare with ctypes."""
-    pairs = [('ot_gemm_seg', _lib.GemmSeg), ('ot_gemm_params', _lib.GemmParams), ('ot_wgrad_seg', _lib.WgradSeg),
+    pairs = [('ot_gemm_seg', _lib.GemmSeg), ('ot_gemm_params', _lib.GemmParams), ('ot_ffn_params', _lib.FfnParams), ('ot_wgrad_seg', _lib.WgradSeg),
              ('ot_wgrad_params', _lib.WgradParams), ('ot_attn_params', _lib.AttnParams), ('ot_attn_cached_params', _lib.AttnCachedParams), ('ot_rmsnorm_params', _lib.RmsnormParams),
              ('ot_ns_tokenizer_params', _lib.NsTokenizerParams), ('ot_colsum_params', _lib.ColsumParams),
              ('ot_rmsprop_params', _lib.RmspropParams), ('ot_embed_params', _lib.EmbedParams), ('ot_heads_params', _lib.HeadsParams),
