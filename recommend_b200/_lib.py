@@ -9,7 +9,8 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'lib', 'libonetrans_sm100.so')
+# OT_LIB_PATH: an alternative build of the same library (A/B experiments with compile-time switches); never another implementation
+LIB_PATH = os.environ.get('OT_LIB_PATH') or os.path.join(_HERE, 'lib', 'libonetrans_sm100.so')
 
 i32, i64, vp, fp = C.c_int32, C.c_int64, C.c_void_p, C.c_void_p  # float* passed as raw address
 

@@ -12,6 +12,7 @@
 //     O += PV (registers, rescaled by the running max)
 // K/V blocks are TMA-prefetched one block ahead.  256 TMEM columns and <=113 KB smem per CTA let two
 // CTAs share an SM, so one CTA's softmax overlaps the other's MMAs.
+#include <stdlib.h>
 #include "ot_attn.cuh"
 #include "ot_host.h"
 #include "../../include/onetrans_b200.h"
@@ -258,7 +259,8 @@ int make_head_tmap(CUtensorMap* tm, const void* base, int cols, int B, int L, lo
   return make_tmap_bf16(tm, base, 3, dims, str, box, swb);
 }
 
-int attn_fwd_ws_impl(const ot_attn_params* p, cudaStream_t st);   // ot_attn_fwd_ws.cu (head_dim 64)
+int attn_fwd_ws_impl(const ot_attn_params* p, cudaStream_t st);   // ot_attn_fwd_ws.cu (head_dim 64, round-1 structure)
+int attn_fwd_v2_impl(const ot_attn_params* p, cudaStream_t st);   // ot_attn_fwd_v2.cu (head_dim 64, round-2 structure)
 
 int attn_fwd_impl(const ot_attn_params* p, cudaStream_t st) {
   if (!p || !p->q || !p->k || !p->v || !p->o || !p->lse) OT_FAIL(OT_ERR_INVALID_ARG, "ot_attn_fwd: null pointer");
@@ -267,7 +269,11 @@ int attn_fwd_impl(const ot_attn_params* p, cudaStream_t st) {
     OT_FAIL(OT_ERR_UNSUPPORTED_SHAPE, "ot_attn_fwd: head_dim=%d (32, 64 and 96 are supported)", p->head_dim);
   if ((p->ldq % 8) || (p->ldk % 8) || (p->ldv % 8) || (p->ldo % 8)) OT_FAIL(OT_ERR_UNSUPPORTED_SHAPE, "ot_attn_fwd: leading dimensions must be multiples of 8");
   const int swb = (p->head_dim == 64 && p->swizzle != 64) ? 128 : 64;
-  if (p->head_dim == 64 && swb == 128 && p->swizzle != 128) return attn_fwd_ws_impl(p, st);   // swizzle=128 forces the simple kernel
+  if (p->head_dim == 64 && swb == 128 && p->swizzle != 128) {   // swizzle=128 forces the simple kernel
+    // OT_ATTN_FWD_V2=0 keeps the round-1 warp-specialised kernel for A/B runs (read once)
+    static const bool v2 = [] { const char* e = getenv("OT_ATTN_FWD_V2"); return !(e && e[0] == '0'); }();
+    return v2 ? attn_fwd_v2_impl(p, st) : attn_fwd_ws_impl(p, st);
+  }
   const int cols = p->H * p->head_dim;
   CUtensorMap tq, tk, tv;
   int rc;

@@ -82,10 +82,35 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// try_wait with a suspend-time hint: the hardware may park the thread for up to `ns` nanoseconds and wakes it when the phase
+// completes, so a waiting warp issues (almost) no instructions.  Round-2 finding (profiles/README.md): spin / nanosleep poll
+// loops of waiting warps were 22 % of all issued instructions of the fused FFN kernel.
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
+#ifndef OT_WAIT_HINT_NS
+#define OT_WAIT_HINT_NS 20000     // 0 = plain try_wait spin (and nanosleep back-off where asked), the round-1 behaviour
+#endif
 // Blocking wait.  With OT_HANG_GUARD a wait that never completes traps (the launch fails loudly)
 // instead of hanging the GPU box.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+#if OT_WAIT_HINT_NS > 0
+  if (mbar_try_wait(bar, parity)) return;       // the common fast path: already complete
+  uint32_t spins = 0;
+  while (!mbar_try_wait_hint(bar, parity, OT_WAIT_HINT_NS)) {
 #if OT_HANG_GUARD
+    if (++spins > (1u << 17)) { __trap(); }      // ~2.6 s of full-length suspensions: a hang, not a wait
+#endif
+  }
+#elif OT_HANG_GUARD
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if (++spins > (1u << 26)) { __trap(); }
@@ -96,10 +121,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 // Same wait for roles that are far off the critical path (GEMM producer / MMA issuer / epilogue waiting for an
-// accumulator): sleep between polls so that the spinning warp stops competing for issue slots with the math
-// warps on its scheduler (profiles/README.md: 10 % of all issued instructions were poll loops).
+// accumulator).  Round 1 slept between polls (__nanosleep) so that the spinning warp stopped competing for issue slots with the
+// math warps on its scheduler; with the suspend-time hint the hardware does the parking and wakes the warp on completion.
+#ifndef OT_BACKOFF
+#define OT_BACKOFF 1      // 0: experiment build, every back-off wait becomes a plain try_wait spin (profiles/README.md, round 2)
+#endif
 __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, uint32_t ns = 64) {
-#if OT_HANG_GUARD
+#if OT_WAIT_HINT_NS > 0 || !OT_BACKOFF
+  (void)ns;
+  mbar_wait(bar, parity);
+#elif OT_HANG_GUARD
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     __nanosleep(ns);

@@ -12,7 +12,7 @@
 //   warp 0 lane*: TMA producer     warp 1 lane*: MMA issuer     all 4 warps: epilogue
 //   warps 2-3 (CTAs of the first M tile, when asked): column sums of the Q tiles as they pass through shared
 //   memory - the bias gradient of the same Dense layer without a second pass over Q
-//   warps 4-7 (PGELU instantiation only): apply GELU to the P tile in shared memory before the MMA reads it.  The fused FFN
+//   warps 4-11 (PGELU instantiation only): apply GELU to the P tile in shared memory before the MMA reads it.  The fused FFN
 //   forward (ot_ffn_fused.cu) keeps h = gelu(pre) on chip and stores only the pre-activation; dW2 = h^T dy (OT/train.py:131 for
 //   the second Dense of OT/model.py:138,145) then takes P = pre and rebuilds h tile by tile instead of reading a stored copy
 #include <stdlib.h>
@@ -23,7 +23,7 @@
 namespace ot {
 
 static constexpr int WG_THREADS = 128;
-static constexpr int WG_XFORM_THREADS = 128;   // warps 4-7 of the PGELU instantiation
+static constexpr int WG_XFORM_THREADS = 256;   // warps 4-11 of the PGELU instantiation (two per scheduler: one warp could not keep up)
 static constexpr int WG_KROWS = 64;  // rows (contraction) per pipeline stage
 
 struct WgradSegDev {
@@ -182,7 +182,7 @@ ot_wgrad_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constant_
         umma_commit(done_bar);
       }
     } else if (PGELU && warp >= 4) {
-      // warps 4-7: GELU of the P tile (64 rows x 128 columns = 1024 chunks of 16 bytes, 8 per thread), in place, then hand the
+      // warps 4-11: GELU of the P tile (64 rows x 128 columns = 1024 chunks of 16 bytes, 4 per thread), in place, then hand the
       // stage to the MMA warp.  Rows past the end of a unit arrive zero-filled and stay zero (gelu(0) == 0).
       const int t = threadIdx.x - WG_THREADS;
       constexpr int CPR = 128 / 8;                   // chunks per tile row (all slabs)
@@ -193,7 +193,7 @@ ot_wgrad_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constant_
         mbar_wait(&full_bar[stage], phase);
         uint8_t* sp = smem + stage * Cfg::STAGE_BYTES;
         // all loads, then the arithmetic, then all stores: an in-place loop would serialise on possible aliasing (LDS after STS)
-        constexpr int NCH = (WG_KROWS * CPR) / WG_XFORM_THREADS;      // 8 chunks per thread
+        constexpr int NCH = (WG_KROWS * CPR) / WG_XFORM_THREADS;      // 4 chunks per thread
         uint4 q[NCH];
         uint4* ptr[NCH];
 #pragma unroll
