@@ -271,8 +271,11 @@ int attn_fwd_impl(const ot_attn_params* p, cudaStream_t st) {
   const int swb = (p->head_dim == 64 && p->swizzle != 64) ? 128 : 64;
   if (p->head_dim == 64 && swb == 128 && p->swizzle != 128) {   // swizzle=128 forces the simple kernel
     // OT_ATTN_FWD_V2=0 keeps the round-1 warp-specialised kernel for A/B runs (read once)
-    static const bool v2 = [] { const char* e = getenv("OT_ATTN_FWD_V2"); return !(e && e[0] == '0'); }();
-    return v2 ? attn_fwd_v2_impl(p, st) : attn_fwd_ws_impl(p, st);
+    // Measured on B200 (profiles/README.md, round 2): the two structures are within 10 % of each other; v2 (one thread per row,
+    // two tiles in lockstep) wins when a (sample, head) has at least two query tiles, the 16-warp round-1 kernel on short tails.
+    static const int v2 = [] { const char* e = getenv("OT_ATTN_FWD_V2"); return e ? atoi(e) : -1; }();     // 0 / 1 force, unset = by shape
+    const bool use_v2 = v2 < 0 ? (p->Lq > 128) : (v2 != 0);
+    return use_v2 ? attn_fwd_v2_impl(p, st) : attn_fwd_ws_impl(p, st);
   }
   const int cols = p->H * p->head_dim;
   CUtensorMap tq, tk, tv;

@@ -2,7 +2,9 @@
 // tail; same arithmetic as ot_attn_fwd_ws.cu, different machine mapping).  What changed and why (profiles/README.md, round 2):
 //   * ONE THREAD PER QUERY ROW.  The round-1 kernel spread a row over four warps and exchanged row maxima through shared memory
 //     behind a named barrier in every key block; ncu showed it latency-bound (XU pipe 31 %, issue 48 %, tensor 18 %).  Here a
-//     softmax thread walks the 128 scores of its row in TMEM twice (max, then exp) - TMEM reads are cheap, no exchange, no barrier.
+//     softmax thread walks the 128 scores of its row in TMEM twice (maximum, then exponentials; TMEM reads run at > 400 B/clk/SM,
+//     profiles/exp_tmem_ld_rate.cu; keeping all 128 in registers spilled) with the next chunk's load under the current chunk's
+//     arithmetic and four-way split maximum / sum accumulators - no exchange, no barrier, no 128-deep dependent chain.
 //   * TWO QUERY TILES PER CTA IN LOCKSTEP.  Tiles 2p and 2p+1 of one (sample, head) share every K/V block they both need: the
 //     block is loaded once, two softmax warpgroups (one per tile) work out of phase, the MMA warp interleaves S = Q K^T of the
 //     next block with P V of the current one, so the tensor pipe and the two warpgroups cover each other's latencies.
@@ -36,7 +38,7 @@ static constexpr int F2_OFF_V = F2_OFF_K + F2_KV_STAGES * F2_TILE;
 static constexpr int F2_OFF_P = F2_OFF_V + F2_KV_STAGES * F2_TILE;
 static constexpr int F2_OFF_INFO = F2_OFF_P + 2 * PT_BYTES;
 static constexpr int F2_OFF_BARS = F2_OFF_INFO + F2_INFO_SLOTS * 32;
-static constexpr int F2_SMEM_BYTES = F2_OFF_BARS + 256;
+static constexpr int F2_SMEM_BYTES = F2_OFF_BARS + 512;
 static_assert(F2_SMEM_BYTES <= 227 * 1024, "shared memory budget");
 static constexpr uint32_t F2_T_S = 0, F2_T_O = 256;      // + tile * 128 / + tile * 64
 static constexpr float F2_TAU = 8.0f;                    // lazy rescale threshold, log2 units
@@ -69,7 +71,9 @@ ot_attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   uint64_t* bar_p = bars + 12;        // [2] P written, S read out, O rescaled                (4 arrivals -> MMA)
   uint64_t* bar_o = bars + 14;        // [2] P V of the tile complete                         (MMA commit -> softmax)
   uint64_t* bar_ofree = bars + 16;    // [2] O of a finished tile has been read out           (4 arrivals -> MMA)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+  uint64_t* bar_ifull = bars + 18;    // [8] step info published                              (loader -> MMA, softmax)
+  uint64_t* bar_ifree = bars + 26;    // [8] step info read by the MMA issuer and the 8 softmax warps (9 arrivals -> loader)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 34);
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -83,6 +87,7 @@ ot_attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       mbar_init(&bar_o[i], 1); mbar_init(&bar_ofree[i], 4);
     }
     for (int i = 0; i < F2_KV_STAGES; ++i) { mbar_init(&bar_kv[i], 1); mbar_init(&bar_kvfree[i], 1); }
+    for (int i = 0; i < F2_INFO_SLOTS; ++i) { mbar_init(&bar_ifull[i], 1); mbar_init(&bar_ifree[i], 9); }
     fence_mbar_init();
   }
   if (warp == 8) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
@@ -119,13 +124,18 @@ ot_attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           if (hasB) load_head_tile<DH, SWB>(sQ + (qb * 2 + 1) * F2_TILE, &tmQ, &bar_q[qb], h, b, q0 + 128);
           for (int j = 0; j < nkv; ++j, ++t) {
             const int st = t % F2_KV_STAGES;
-            if (t >= F2_KV_STAGES) mbar_wait(&bar_kvfree[st], ((t / F2_KV_STAGES) - 1) & 1);
+            // The step ring has its own full / free barriers: a warpgroup that is idle in a step (an item whose second tile does
+            // not exist) takes no part in the K/V hand-shake of that step and could otherwise be lapped on the K/V barrier.
+            const int is = t & (F2_INFO_SLOTS - 1);
+            if (t >= F2_INFO_SLOTS) mbar_wait(&bar_ifree[is], ((t / F2_INFO_SLOTS) - 1) & 1);
             F2StepInfo si;
             si.q0 = q0; si.j = j; si.b = b; si.h = h;
             si.flags = (j == 0 ? F2_FIRST : 0) | (j < nkvA ? F2_A : 0) | (j < nkvB ? F2_B : 0) | (j == nkvA - 1 ? F2_LAST_A : 0) |
                        ((hasB && j == nkvB - 1) ? F2_LAST_B : 0) | ((last_item && j == nkv - 1) ? F2_END : 0) | (qb ? F2_QBUF : 0);
             si.pad0 = si.pad1 = si.pad2 = 0;
-            info[t & (F2_INFO_SLOTS - 1)] = si;        // published by the release-arrive on bar_kv below
+            info[is] = si;
+            mbar_arrive(&bar_ifull[is]);               // release: publishes the slot
+            if (t >= F2_KV_STAGES) mbar_wait(&bar_kvfree[st], ((t / F2_KV_STAGES) - 1) & 1);
             mbar_arrive_expect_tx(&bar_kv[st], 2 * F2_TILE);
             load_head_tile<DH, SWB>(sK + st * F2_TILE, &tmK, &bar_kv[st], h, b, j * 128);
             load_head_tile<DH, SWB>(sV + st * F2_TILE, &tmV, &bar_kv[st], h, b, j * 128);
@@ -148,8 +158,11 @@ ot_attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       // S of step t for tile x: waits for the K/V stage (and, on an item's first step, for its Q tiles)
       auto wait_step = [&](uint32_t t) -> F2StepInfo {
         const int st = t % F2_KV_STAGES;
+        const int is = t & (F2_INFO_SLOTS - 1);
+        mbar_wait(&bar_ifull[is], (t / F2_INFO_SLOTS) & 1);
+        const F2StepInfo si = info[is];
+        mbar_arrive(&bar_ifree[is]);
         mbar_wait(&bar_kv[st], (t / F2_KV_STAGES) & 1);
-        const F2StepInfo si = info[t & (F2_INFO_SLOTS - 1)];
         if (si.flags & F2_FIRST) {
           mbar_wait(&bar_q[(si.flags & F2_QBUF) ? 1 : 0], (n_items >> 1) & 1);
           ++n_items;
@@ -220,9 +233,11 @@ ot_attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     float m_ref = -INFINITY, l_run = 0.0f;
 
     while (!end) {
-      // every step's info is published through the K/V barrier of its stage
-      mbar_wait(&bar_kv[g % F2_KV_STAGES], (g / F2_KV_STAGES) & 1);
-      const F2StepInfo si = info[g & (F2_INFO_SLOTS - 1)];
+      const int is = g & (F2_INFO_SLOTS - 1);
+      mbar_wait(&bar_ifull[is], (g / F2_INFO_SLOTS) & 1);
+      const F2StepInfo si = info[is];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_ifree[is]);
       end = (si.flags & F2_END) != 0;
       ++g;
       if (!(si.flags & act_flag)) continue;
@@ -235,22 +250,43 @@ ot_attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       const int lim = (off + q0 + row) - si.j * 128;
       const int lim_lo = (off + q0 + wrow) - si.j * 128;           // lane 0; lane 31 has lim_lo + 31
       if (warp_valid) {
-        // ---- pass 1: row maximum ----
-        float mx = -INFINITY;
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          if (lim_lo + 31 < c * 32) break;                         // chunk hidden from every row of the warp (and so are the later ones)
-          uint32_t v[32];
-          tmem_ld_x32(t_s + c * 32, v);
+        // ---- pass 1: row maximum (four independent partial maxima: a single running maximum is a 128-deep dependent chain).
+        // Chunk c (32 columns) is, for the whole warp, hidden (vis == 0), cut by the diagonal (1) or fully visible (2). ----
+        int vis[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) vis[c] = (lim_lo + 31 < c * 32) ? 0 : (lim_lo >= c * 32 + 31) ? 2 : 1;
+        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        {
+          uint32_t va[32], vb[32];
+          tmem_ld_x32(t_s, va);                                     // chunk 0 always holds key 0 .. visible to someone
+          if (vis[1]) tmem_ld_x32(t_s + 32, vb);
           tmem_ld_wait();
-          if (lim_lo >= c * 32 + 31) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
-          } else {
+          for (int half = 0; half < 2; ++half) {
+            // chunks (0, 1) on the first trip, (2, 3) on the second; the loads of the second pair fly under the first pair's math
+            const int c0 = half * 2, c1 = half * 2 + 1;
+            if (vis[c0] == 2) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (c * 32 + i <= lim) ? __uint_as_float(v[i]) : -INFINITY);
+              for (int i = 0; i < 32; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(va[i]));
+            } else if (vis[c0] == 1) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], (c0 * 32 + i <= lim) ? __uint_as_float(va[i]) : -INFINITY);
+            }
+            if (half == 0 && vis[2]) tmem_ld_x32(t_s + 64, va);
+            if (vis[c1] == 2) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(vb[i]));
+            } else if (vis[c1] == 1) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], (c1 * 32 + i <= lim) ? __uint_as_float(vb[i]) : -INFINITY);
+            }
+            if (half == 0) {
+              if (vis[3]) tmem_ld_x32(t_s + 96, vb);
+              tmem_ld_wait();
+            }
           }
         }
+        const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
         // ---- lazy rescale: keep the old reference maximum unless the new maximum exceeds it by more than 2^TAU ----
         // (key 0 is visible to every query, so mx is finite in the first block of a tile)
         bool need = false;
@@ -262,21 +298,15 @@ ot_attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           tc_fence_after();
           const float alpha = need ? ex2_approx((m_ref - m_new) * p.scale_log2) : 1.0f;
 #pragma unroll 1
-          for (int c = 0; c < 2; ++c) {
-            uint32_t w[32];
-            tmem_ld_x32(t_o + c * 32, w);
+          for (int c = 0; c < 8; ++c) {        // 8 columns at a time: the 128 scores of the row are live in registers here
+            uint32_t w[8];
+            tmem_ld_x8(t_o + c * 8, w);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) w[i] = __float_as_uint(__uint_as_float(w[i]) * alpha);
-            asm volatile(
-                "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-                "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-                "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(t_o + c * 32),
-                "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]), "r"(w[8]), "r"(w[9]),
-                "r"(w[10]), "r"(w[11]), "r"(w[12]), "r"(w[13]), "r"(w[14]), "r"(w[15]), "r"(w[16]), "r"(w[17]), "r"(w[18]),
-                "r"(w[19]), "r"(w[20]), "r"(w[21]), "r"(w[22]), "r"(w[23]), "r"(w[24]), "r"(w[25]), "r"(w[26]), "r"(w[27]),
-                "r"(w[28]), "r"(w[29]), "r"(w[30]), "r"(w[31])
-                : "memory");
+            for (int i = 0; i < 8; ++i) w[i] = __float_as_uint(__uint_as_float(w[i]) * alpha);
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(t_o + c * 8), "r"(w[0]),
+                         "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+                         : "memory");
           }
           asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
           l_run *= alpha;
@@ -284,23 +314,25 @@ ot_attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         m_ref = m_new;
         // ---- pass 2: p = 2^((s - m_ref) * scale * log2 e), row sum, bf16 P tile ----
         const float mb = m_ref * p.scale_log2;
-        float rowsum = 0.0f;
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          uint32_t pk[16];
-          if (lim_lo + 31 < c * 32) {
+        float rs4[4] = {0.0f, 0.0f, 0.0f, 0.0f};                    // independent partial row sums (no 128-deep add chain)
+        {
+          uint32_t vv[2][32];
+          tmem_ld_x32(t_s, vv[0]);
+          tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 16; ++i) pk[i] = 0u;
-          } else {
-            uint32_t v[32];
-            tmem_ld_x32(t_s + c * 32, v);
-            tmem_ld_wait();
-            if (lim_lo >= c * 32 + 31) {
+          for (int c = 0; c < 4; ++c) {
+            uint32_t (&v)[32] = vv[c & 1];
+            if (c < 3 && vis[c + 1]) tmem_ld_x32(t_s + (c + 1) * 32, vv[(c + 1) & 1]);    // next chunk's load under this chunk's math
+            uint32_t pk[16];
+            if (vis[c] == 0) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) pk[i] = 0u;
+            } else if (vis[c] == 2) {
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
                 const float e0 = ex2_mixed(fmaf(__uint_as_float(v[2 * i]), p.scale_log2, -mb), 2 * i);
                 const float e1 = ex2_mixed(fmaf(__uint_as_float(v[2 * i + 1]), p.scale_log2, -mb), 2 * i + 1);
-                rowsum += e0 + e1;
+                rs4[i & 3] += e0 + e1;
                 pk[i] = pack_bf16x2(e0, e1);
               }
             } else {
@@ -310,17 +342,19 @@ ot_attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                 float e1 = ex2_mixed(fmaf(__uint_as_float(v[2 * i + 1]), p.scale_log2, -mb), 2 * i + 1);
                 e0 = (c * 32 + 2 * i <= lim) ? e0 : 0.0f;
                 e1 = (c * 32 + 2 * i + 1 <= lim) ? e1 : 0.0f;
-                rowsum += e0 + e1;
+                rs4[i & 3] += e0 + e1;
                 pk[i] = pack_bf16x2(e0, e1);
               }
             }
-          }
-          uint8_t* slab = myP + (c >> 1) * PT_SLAB_BYTES;
+            uint8_t* slab = myP + (c >> 1) * PT_SLAB_BYTES;
 #pragma unroll
-          for (int ch = 0; ch < 4; ++ch)
-            *reinterpret_cast<uint4*>(slab + swz_off<128>(row, (c & 1) * 4 + ch)) =
-                make_uint4(pk[ch * 4 + 0], pk[ch * 4 + 1], pk[ch * 4 + 2], pk[ch * 4 + 3]);
+            for (int ch = 0; ch < 4; ++ch)
+              *reinterpret_cast<uint4*>(slab + swz_off<128>(row, (c & 1) * 4 + ch)) =
+                  make_uint4(pk[ch * 4 + 0], pk[ch * 4 + 1], pk[ch * 4 + 2], pk[ch * 4 + 3]);
+            if (c < 3) tmem_ld_wait();
+          }
         }
+        const float rowsum = (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
         l_run += rowsum;
       }
       fence_proxy_async_smem();

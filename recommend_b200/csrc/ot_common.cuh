@@ -334,8 +334,17 @@ __device__ __forceinline__ void upk2(f32x2 r, float& a, float& b) { asm("mov.b64
 __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
 __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 __device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
-__device__ __forceinline__ f32x2 tanh2(f32x2 u) { float a, b; upk2(u, a, b); return pk2(tanh_approx(a), tanh_approx(b)); }
-__device__ __forceinline__ f32x2 min2(f32x2 v, float m) { float a, b; upk2(v, a, b); return pk2(fminf(a, m), fminf(b, m)); }
+// The two scalar steps of the packed GELU (there is no packed tanh / min): one asm block that works on the halves of the 64-bit
+// register pair in place, so that ptxas does not shuffle the halves through IMAD.MOV to re-form an aligned pair (12 % of the
+// instructions of the fused FFN kernel were such moves, profiles/README.md round 2).
+__device__ __forceinline__ f32x2 tanh2(f32x2 u) {
+  asm("{\n\t.reg .f32 a, b;\n\tmov.b64 {a, b}, %0;\n\ttanh.approx.f32 a, a;\n\ttanh.approx.f32 b, b;\n\tmov.b64 %0, {a, b};\n\t}" : "+l"(u));
+  return u;
+}
+__device__ __forceinline__ f32x2 min2(f32x2 v, float m) {
+  asm("{\n\t.reg .f32 a, b;\n\tmov.b64 {a, b}, %0;\n\tmin.f32 a, a, %1;\n\tmin.f32 b, b, %1;\n\tmov.b64 %0, {a, b};\n\t}" : "+l"(v) : "f"(m));
+  return v;
+}
 // the two functions above on a pair: 5 / 8 issue slots per element instead of 9 / 14
 __device__ __forceinline__ f32x2 gelu_erf2(f32x2 x) {
   const f32x2 x2 = min2(mul2(x, x), 64.0f);

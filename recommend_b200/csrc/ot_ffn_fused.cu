@@ -18,7 +18,7 @@
 //   warp 1    MMA issuer   : FFN1(c) -> acc1[c&1] (M128 N128 K256), FFN2(c-1) -> acc2 (M128 N256 K128); FFN1(c+1) is issued
 //                            before FFN2(c) so that the tensor pipe has work while chunk c sits in the epilogue
 //   warps 4-19 epilogue    : four sets of four warps; in a chunk, set s owns 32 of the 128 columns: tcgen05.ld -> +b1 ->
-//                            (bf16 pre-activation -> staging -> TMA store) -> GELU -> bf16 h -> swizzled A-operand tile;
+//                            (bf16 pre-activation -> per-warp staging patch -> TMA store) -> GELU -> bf16 h -> swizzled A-operand tile;
 //                            at the end of a tile, set s owns 64 of the d columns of the output: +b2, dropout, residual
 //                            (TMA-loaded into the staging tile, or the fp32 stream of the NS rows), y -> staging -> TMA store,
 //                            y kept in TMEM (tcgen05.st) for the fused RMSNorm pass once the row statistics are exchanged
@@ -265,15 +265,13 @@ ot_ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int set = (warp - 4) >> 2;
     const int grp = set >> 1;                                              // pair of sets sharing a 64-column box in a chunk
     const int et = threadIdx.x - FF_CTRL_THREADS - set * FF_SET_THREADS;   // 0..127 inside the set
-    const int gt = threadIdx.x - FF_CTRL_THREADS - grp * 2 * FF_SET_THREADS;   // 0..255 inside the pair
     const int lgrp = warp & 3;
     const int r_own = lgrp * 32 + lane;
     const bool set_io = (et == 0);                     // issues this set's TMA traffic of the final epilogue
-    const bool grp_io = (gt == 0);                     // issues the pair's pre-activation stores
     const bool f_res = p.flags & OT_EPI_RESIDUAL, f_drop = p.flags & OT_EPI_DROPOUT, f_norm = p.flags & OT_EPI_NORM;
     const bool save_pre = p.pre != nullptr;
     uint8_t* box_h = sH + grp * FF_BOX_BYTES;          // chunk phase: h columns [64 grp, +64)
-    uint8_t* box_p = sP + grp * FF_BOX_BYTES;
+    uint8_t* patch = sP + (warp - 4) * 2048;           // chunk phase: this warp's pre-activation patch, [32 rows x 64 bytes]
     uint8_t* box_y = stage + set * FF_BOX_BYTES;       // final phase: output columns [64 set, +64)
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(lgrp * 32) << 16);
     uint32_t res_phase = 0;
@@ -293,7 +291,7 @@ ot_ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const bool hp_tile = f_res && (p.res_hp != nullptr) && (t.row0 >= p.hp_row0);
       // the staging boxes still hold the previous tile's output until its TMA stores have read them
       if (it > 0) {
-        if (set_io) bulk_wait_read0();
+        if (lane == 0) bulk_wait_read0();
         named_bar_sync(FF_BAR_ALL, FF_EPI_THREADS);
       }
 
@@ -320,30 +318,27 @@ ot_ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
         }
         if (save_pre) {
-          // pre-activation -> staging box of the pair -> HBM (the only [rows, F] tensor this kernel writes)
-          if (grp_io) bulk_wait_read0();                       // the previous chunk's store has read the box
-          named_bar_sync(FF_BAR_GRP + grp, 2 * FF_SET_THREADS);
+          // pre-activation -> this warp's private [32 rows x 32 columns] staging patch (64-byte swizzle) -> HBM by one TMA store
+          // per warp and chunk: no barrier between warps on this path (the first build staged per pair of sets behind two
+          // 256-thread barriers and a store-drain wait: + 1700 cycles per chunk, profiles/README.md).  It is the only
+          // [rows, F] tensor this kernel writes.
+          uint32_t pk[16];
 #pragma unroll
-          for (int ch = 0; ch < 4; ++ch) {
-            float a0, a1, a2, a3, a4, a5, a6, a7;
-            upk2(f[ch * 4 + 0], a0, a1); upk2(f[ch * 4 + 1], a2, a3); upk2(f[ch * 4 + 2], a4, a5); upk2(f[ch * 4 + 3], a6, a7);
-            uint4 q;
-            q.x = pack_bf16x2(a0, a1); q.y = pack_bf16x2(a2, a3); q.z = pack_bf16x2(a4, a5); q.w = pack_bf16x2(a6, a7);
-            *reinterpret_cast<uint4*>(box_p + swz_off<128>(r_own, (set & 1) * 4 + ch)) = q;
-          }
-          if (full) fence_proxy_async_smem();
-          named_bar_sync(FF_BAR_GRP + grp, 2 * FF_SET_THREADS);
+          for (int j = 0; j < 16; ++j) { float a, bq; upk2(f[j], a, bq); pk[j] = pack_bf16x2(a, bq); }
           if (full) {
-            if (grp_io) { tma_store_2d(&tmPre, box_p, c * FF_FC + grp * 64, t.row0); bulk_commit(); }
-          } else {
-            // partial tile (small batches): cooperative 16-byte stores of the valid rows
+            if (lane == 0) bulk_wait_read0();                    // this warp's previous store has read the patch
+            __syncwarp();
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int idx = i * 256 + gt, rr = idx >> 3, ch = idx & 7;
-              if (rr < t.valid)
-                *reinterpret_cast<uint4*>(p.pre + (long long)(t.row0 + rr) * p.ldpre + c * FF_FC + grp * 64 + ch * 8) =
-                    *reinterpret_cast<const uint4*>(box_p + swz_off<128>(rr, ch));
-            }
+            for (int ch = 0; ch < 4; ++ch)
+              *reinterpret_cast<uint4*>(patch + swz_off<64>(lane, ch)) = make_uint4(pk[ch * 4], pk[ch * 4 + 1], pk[ch * 4 + 2], pk[ch * 4 + 3]);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) { tma_store_2d(&tmPre, patch, c * FF_FC + set * 32, t.row0 + lgrp * 32); bulk_commit(); }
+          } else if (r_own < t.valid) {
+            // partial tile (small batches): the row's 64 bytes straight from registers
+            uint4* dst = reinterpret_cast<uint4*>(p.pre + (long long)(t.row0 + r_own) * p.ldpre + c * FF_FC + set * 32);
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) dst[ch] = make_uint4(pk[ch * 4], pk[ch * 4 + 1], pk[ch * 4 + 2], pk[ch * 4 + 3]);
           }
         }
 #pragma unroll
@@ -366,7 +361,7 @@ ot_ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       // -------------------------------- output tile --------------------------------
       mbar_wait_backoff(acc2_full, it & 1, 32);
       tc_fence_after();
-      if (save_pre && grp_io) bulk_wait_read0();               // the last pre-activation store has read its box
+      if (save_pre && lane == 0) bulk_wait_read0();            // this warp's last pre-activation store has read its patch
       named_bar_sync(FF_BAR_ALL, FF_EPI_THREADS);              // h tile free (acc2_full), pre staging free: 4 boxes of staging
       const int col0 = set * 64;
       const bool tile_res = f_res && !hp_tile;
@@ -514,7 +509,7 @@ ot_ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       __syncwarp();
       if (lane == 0) mbar_arrive(acc2_empty);
     }
-    if (set_io || grp_io) bulk_wait_all();
+    if (lane == 0) bulk_wait_all();
   }
 
   tc_fence_before();
@@ -588,7 +583,12 @@ int ffn_fwd_impl(const ot_ffn_params* p, cudaStream_t st) {
   if ((rc = make_2d(&tmW2, p->W2, (uint64_t)p->F, (uint64_t)p->n_groups * FF_D, p->ldw2, FF_D))) return rc;
   if ((rc = make_2d(&tmOut, p->out, FF_D, (uint64_t)row_extent, p->ldo, BM))) return rc;
   tmPre = tmOut; tmNorm = tmOut; tmRes = tmOut;
-  if (p->pre && (rc = make_2d(&tmPre, p->pre, (uint64_t)p->F, (uint64_t)row_extent, p->ldpre, BM))) return rc;
+  if (p->pre) {   // per-warp patches: 32 columns x 32 rows, 64-byte swizzle
+    uint64_t dims[2] = {(uint64_t)p->F, (uint64_t)row_extent};
+    uint64_t str[1] = {(uint64_t)p->ldpre * 2};
+    uint32_t box[2] = {32u, 32u};
+    if ((rc = make_tmap_bf16(&tmPre, p->pre, 2, dims, str, box, 64))) return rc;
+  }
   if ((p->flags & OT_EPI_NORM) && (rc = make_2d(&tmNorm, p->norm_out, FF_D, (uint64_t)row_extent, p->ld_norm, BM))) return rc;
   if ((p->flags & OT_EPI_RESIDUAL) && (rc = make_2d(&tmRes, p->res, FF_D, (uint64_t)row_extent, p->ldr, BM))) return rc;
 

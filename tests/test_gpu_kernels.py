@@ -196,7 +196,8 @@ def attn_ref(q, k, v, B, H, Lq, Lk, dh):
 
 
 @pytest.mark.parametrize('B,H,dh,Lq,Lk', [(3, 4, 64, 202, 288), (2, 4, 64, 458, 544), (5, 4, 64, 13, 27), (1, 4, 64, 8, 13),
-                                           (2, 4, 96, 224, 288), (2, 2, 64, 1, 1), (1, 4, 64, 1024, 2048)])
+                                           (2, 4, 96, 224, 288), (2, 2, 64, 1, 1), (1, 4, 64, 1024, 2048), (3, 4, 64, 373, 458),
+                                           (40, 4, 64, 300, 300), (2, 4, 64, 640, 700)])
 def test_attention_forward_backward(B, H, dh, Lq, Lk):
     d = H * dh
     q = rnd(Lq * B, d, seed=13)
