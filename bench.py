@@ -35,6 +35,8 @@ def workload(name: str):
         return dict(model='default', B=2048, seq_lens=(170, 170, 170), L_ns=32, schedule='linear_to_ns')
     if name == 'c4':   # long sequence, halving schedule
         return dict(model='small', B=256, seq_lens=(672, 672, 672), L_ns=32, schedule='halving')
+    if name == 'c5':   # cached inference: 1 user x 8192 candidates, NS-token-only queries (handled by run_c5)
+        return dict(model='small', B=8192, seq_lens=(170, 170, 170), L_ns=32, schedule='linear_to_ns')
     if name == 'c1':   # the reference's CPU-runnable case
         return dict(model='small', B=32, seq_lens=(86, 84, 84), L_ns=16, schedule='reference_ratio')
     raise ValueError(name)
@@ -166,7 +168,10 @@ def run_reference_arm(args, wl, rank):
         'impl': 'reference', 'metric': 'OneTrans samples/sec (fwd+bwd bf16)', 'value': v, 'unit': 'samples/s', 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': config_dict(args, wl, wl['B']),      # the GPU arm's workload; each CPU step is a bounded sample of it (cpu_baseline.sample)
+        # the GPU arm's workload; each CPU step is a bounded sample of it: `cpu_step_batch` samples per step, not `global_batch`
+        'config': dict(config_dict(args, wl, wl['B']), cpu_step_batch=sample_B,
+                       note=f'reference arm: every timed step is {sample_B} samples of this workload on the host cores (a samples/s metric; '
+                            f'the batch of {wl["B"]} per GPU is the GPU arm\'s)'),
         'cpu_baseline': {'value': v, 'unit': 'samples/s', 'cores': cores, 'kind': 'port',
                          'sample': f'oracle (PyTorch CPU fp32 restatement of OT/model.py, held at 1e-12 to vectors produced by the reference code itself over a TensorFlow-op shim; TensorFlow itself is not installable) fwd+BCE+bwd on {sample_B} '
                                    f'samples of the same workload per step; structure: {args.cpu_variant}'},
@@ -184,6 +189,143 @@ def config_dict(args, wl, B):
             'grad_allreduce': 'none (1 GPU)' if args.gpus == 1 else ('after the backward' if args.no_overlap else 'per block, under the backward of the blocks below'),
             'inputs': 'pre-embedded events bf16 [B, L_i, 64] x3, 11 fp32 scalars, 2 fp32 labels per sample (pinned host buffers in the e2e arm)',
             'l2_policy': 'activations per step (>20 GB) far exceed the 126 MB L2; no explicit flush'}
+
+
+# ---------------------------------------------------------------------------------------------------
+# BASELINE config 5: scoring with the cross-candidate K/V cache (north_star item 5; OT/model.py:95-98,120 repaired per D6)
+# ---------------------------------------------------------------------------------------------------
+
+def c5_cpu_candidates_per_sec(wl, n_cand: int, steps: int):
+    """oracle two-stage scoring (user cache once, then ``n_cand`` candidates per step) on the host cores."""
+    from oracle import onetrans_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    ocfg = O.small_config(num_ns_tokens=wl['L_ns'])
+    ocfg.dropout_rate = 0.0
+    L0 = sum(wl['seq_lens']) + 2 + wl['L_ns']
+    ocfg.pyramid_keep_lens = resolve_schedule(wl, ocfg.num_layers, L0)
+    P = O.init_params(ocfg, seed=0)
+    non_seq, seq, _ = O.synthetic_batch(ocfg, n_cand, wl['seq_lens'], seed=1234)
+    seq1 = {k: v[:1] for k, v in seq.items()}
+    with torch.no_grad():
+        cache = O.two_stage_user_cache(P, ocfg, seq1)
+        O.two_stage_score(P, ocfg, cache, non_seq)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            O.two_stage_score(P, ocfg, cache, non_seq)
+        dt = (time.perf_counter() - t0) / steps
+    return n_cand / dt, dt * 1e3, torch.get_num_threads()
+
+
+def run_c5(args, wl, rank, local_rank, world):
+    """`python bench.py --workload c5`: one user, 8192 candidates (sharded over the ranks when N > 1: strong scaling), the user's
+    per-layer sequence-side K|V cached (stage 1) and every candidate's NS tokens scored against it (stage 2).  value = stage-2
+    candidates/s with the cache and the candidate features resident; e2e = the request as a caller sees it: user sequences and
+    candidate features from pinned host buffers, stage 1 + stage 2, probabilities back on the host."""
+    C_total = wl['B']
+    sample = min(args.cpu_sample_batch * 8, 256)
+    if args.impl == 'reference':
+        if rank != 0:
+            return
+        v, ms, cores = c5_cpu_candidates_per_sec(wl, sample, max(1, args.steps))
+        print(json.dumps({'impl': 'reference', 'metric': 'OneTrans candidates/sec (cached inference)', 'value': v, 'unit': 'candidates/s',
+                          'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True,
+                          'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+                          'config': {'workload': 'c5: OneTrans-S, 1 user x 8192 candidates, 512 S + 32 NS tokens, NS-token-only queries against the cached K|V',
+                                     'cpu_step_candidates': sample},
+                          'cpu_baseline': {'value': v, 'unit': 'candidates/s', 'cores': cores, 'kind': 'port',
+                                           'sample': f'oracle two_stage_score (fp32) on {sample} candidates per step, user cache built once'},
+                          'e2e': {'value': v, 'unit': 'candidates/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}), flush=True)
+        return
+    import torch.distributed as dist
+    import recommend_b200 as R
+    from recommend_b200 import _lib, ops
+    from recommend_b200.data import create_sample_batch
+    from recommend_b200.inference import score_candidates_sharded, shard_bounds
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    dev = torch.device('cuda', local_rank)
+    cfg = R.get_model_config('small')
+    cfg.num_ns_tokens, cfg.pyramid_schedule, cfg.dropout_rate = wl['L_ns'], wl['schedule'], 0.0
+    torch.manual_seed(0)
+    model = R.OneTransModel(cfg).to(dev).eval()
+    non_seq, seq, _ = create_sample_batch(cfg, C_total, wl['seq_lens'], seed=1234)
+    lo, hi = shard_bounds(C_total, world, rank)
+    h_ns = {k: v[lo:hi].contiguous().pin_memory() for k, v in non_seq.items()}
+    h_seq = {k: v[:1].to(torch.bfloat16).contiguous().pin_memory() for k, v in seq.items()}
+    d_ns = {k: v.to(dev) for k, v in h_ns.items()}
+    d_seq = {k: v.to(dev) for k, v in h_seq.items()}
+    h2d = sum(v.numel() * v.element_size() for d_ in (h_ns, h_seq) for v in d_.values())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        for _ in range(max(3, args.warmup)):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            out = fn()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / n, out
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    with torch.no_grad():
+        model.build_kv_cache(d_seq)
+        l0 = _lib.launch_count
+        t0 = time.perf_counter()
+        ms2, _ = timed(lambda: model.score_candidates(d_ns), args.steps)
+        sampler.window(t0, time.perf_counter())
+        launches = (_lib.launch_count - l0) * args.steps // (args.steps + max(3, args.warmup))
+
+        def request():
+            seq_d = {k: v.to(dev, non_blocking=True) for k, v in h_seq.items()}
+            ns_d = {k: v.to(dev, non_blocking=True) for k, v in h_ns.items()}
+            model.build_kv_cache(seq_d)
+            probs = model.score_candidates(ns_d)
+            return {t: p.float().cpu() for t, p in probs.items()}        # device -> host read of the step's result
+        ms_e2e, out = timed(request, args.steps)
+        prof = ops.KernelProfiler()
+        ops.set_profiler(prof)
+        for _ in range(args.steps):
+            model.score_candidates(d_ns)
+        barrier()
+        ops.set_profiler(None)
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        peaks = measured_peaks()
+        summ = prof.summary()
+        (name, tag), dmn = max(summ.items(), key=lambda kv: kv[1]['ms'])
+        d2h = sum(v.numel() * 4 for v in out.values())
+        line = {'metric': 'OneTrans candidates/sec (cached inference)', 'value': C_total / (ms2 * 1e-3), 'unit': 'candidates/s', 'n_gpus': world,
+                'steps': args.steps, 'warmup': max(3, args.warmup), 'ms_per_step': ms2, 'higher_is_better': True, 'scaling': 'strong',
+                'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
+                'config': {'workload': 'c5: OneTrans-S, 1 user x 8192 candidates, 512 S + 32 NS tokens, NS-token-only queries against the cached per-layer K|V',
+                           'candidates': C_total, 'parallelism': f'candidates sharded over {world} rank(s)', 'l2_policy': 'candidate activations per step (> 1 GB) exceed the 126 MB L2'},
+                'clocks': clocks,
+                'e2e': {'value': C_total / (ms_e2e * 1e-3), 'unit': 'candidates/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                        'step': 'host user sequences + candidate features -> stage 1 (cache) + stage 2 (scores) -> probabilities on the host'},
+                'gpu_launches': launches,
+                'roofline': roofline_of(name, tag, dmn, peaks),
+                'kernels': [{'kernel': f'{n}[{tg}]', 'launches_per_step': d_['launches'] / args.steps, 'ms_per_step': d_['ms'] / args.steps}
+                            for (n, tg), d_ in sorted(summ.items(), key=lambda kv: -kv[1]['ms'])[:10]]}
+        if world == 1 and not args.no_cpu_baseline:
+            v, ms, cores = c5_cpu_candidates_per_sec(wl, sample, 3)
+            line['cpu_baseline'] = {'value': v, 'unit': 'candidates/s', 'cores': cores, 'kind': 'port',
+                                    'sample': f'oracle two_stage_score (fp32) on {sample} candidates per step, 3 timed steps, user cache built once'}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -215,6 +357,9 @@ def main():
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
 
+    if args.workload == 'c5':
+        run_c5(args, wl, rank, local_rank, world)
+        return
     if args.impl == 'reference':
         run_reference_arm(args, wl, rank)
         return
@@ -384,20 +529,15 @@ def main():
                 pass
             # dominant kernel: the (family, shape) bucket with the largest total time, timed inside the headline loop
             (name, tag), dmn = next(iter(dom_prof.summary().items()))
-            secs = dmn['ms'] * 1e-3
-            t_flops = dmn['flops'] / (peaks['tf_sustained'] * 1e12)
-            t_bytes = dmn['bytes'] / (peaks['hbm'] * 1e9)
-            if t_bytes >= t_flops:
-                roof = {'bound': 'hbm', 'achieved': dmn['bytes'] / secs / 1e9, 'peak': peaks['hbm'], 'unit': 'GB/s'}
-            else:
-                roof = {'bound': 'tensor', 'achieved': dmn['flops'] / secs / 1e12, 'peak': peaks['tf_sustained'], 'unit': 'TFLOP/s'}
-            roof['frac'] = roof['achieved'] / roof['peak']
-            roof.update({'kernel': f'{name}[{tag}]', 'launches': dmn['launches'], 'avg_launch_us': dmn['ms'] * 1e3 / dmn['launches'],
-                         'algorithmic_bytes_per_launch': dmn['bytes'] / dmn['launches'], 'algorithmic_flops_per_launch': dmn['flops'] / dmn['launches'],
-                         'peak_source': peaks['src'] + (' (sustained bf16)' if roof['bound'] == 'tensor' else ' (copy bandwidth)'),
-                         'traffic': load_ncu_traffic(name, tag, dmn['bytes'] / dmn['launches']),
-                         'timed': 'CUDA events around every launch of this bucket inside the timed region; the kernels[] table comes from a second, fully instrumented pass of the same steps'})
-            line['roofline'] = roof
+            line['roofline'] = roofline_of(name, tag, dmn, peaks)
+            # the contraction kernels are judged on the tensor pipe, gather / norm kernels on HBM - one entry per family
+            line['rooflines'] = [roofline_of(n, tg, d_, peaks, brief=True) for (n, tg), d_ in sorted(summ.items(), key=lambda kv: -kv[1]['ms'])[:12]]
+            att = [(n, d_) for (n, tg), d_ in summ.items() if n in ('ot_attn_fwd', 'ot_attn_bwd')]
+            if att:
+                fl, ms_ = sum(d_['flops'] for _, d_ in att), sum(d_['ms'] for _, d_ in att)
+                line['attn'] = {'ms_per_step': ms_ / args.steps, 'achieved_tflops': fl / (ms_ * 1e-3) / 1e12,
+                                'frac_of_bf16_sustained_peak': fl / (ms_ * 1e-3) / 1e12 / peaks['tf_sustained'],
+                                'tensor_pipe_util_pct': load_ncu_metric('attn_tensor_pipe_util_pct')}
         if world == 1 and not args.no_cpu_baseline:
             v, ms, cores = cpu_oracle_samples_per_sec(wl, args.cpu_sample_batch, 6, 1, args.dropout)
             line['cpu_baseline'] = {'value': v, 'unit': 'samples/s', 'cores': cores, 'kind': 'port',
@@ -408,22 +548,64 @@ def main():
         dist.destroy_process_group()
 
 
+TENSOR_FAMILIES = ('ot_mixed_gemm', 'ot_ffn_fwd', 'ot_wgrad', 'ot_attn_fwd', 'ot_attn_bwd', 'ot_attn_ns_cached_fwd')
+
+
+def roofline_of(name, tag, d, peaks, brief=False):
+    """Roofline entry of one (kernel family, shape) bucket from CUDA-event time and algorithmic work.  SURVEY.md 8(d): the
+    dense contractions (grouped GEMMs, fused FFN, weight gradients, attention) are bound by the TENSOR pipe and reported against the
+    measured sustained bf16 peak; tokenizer / norm / optimizer / head kernels by HBM against the measured copy bandwidth.  The other
+    side is always given too (`hbm` with the op-minimal bytes, see ops.KernelProfiler), so that a reader can see which wall is closer."""
+    secs = d['ms'] * 1e-3
+    tf = d['flops'] / secs / 1e12
+    gbs_min = d.get('min_bytes', d['bytes']) / secs / 1e9
+    if name in TENSOR_FAMILIES:
+        roof = {'bound': 'tensor', 'achieved': tf, 'peak': peaks['tf_sustained'], 'unit': 'TFLOP/s', 'frac': tf / peaks['tf_sustained'],
+                'hbm': {'achieved': gbs_min, 'peak': peaks['hbm'], 'unit': 'GB/s', 'frac': gbs_min / peaks['hbm'],
+                        'bytes': 'op-minimal: operands and one output, no second outputs'}}
+    else:
+        gbs = d['bytes'] / secs / 1e9
+        roof = {'bound': 'hbm', 'achieved': gbs, 'peak': peaks['hbm'], 'unit': 'GB/s', 'frac': gbs / peaks['hbm']}
+    roof['kernel'] = f'{name}[{tag}]'
+    roof['ms_per_launch'] = d['ms'] / d['launches']
+    if brief:
+        return roof
+    tr, tr_src = load_ncu_traffic(name, tag, d['bytes'] / d['launches'])
+    roof.update({'launches': d['launches'], 'avg_launch_us': d['ms'] * 1e3 / d['launches'],
+                 'algorithmic_bytes_per_launch': d['bytes'] / d['launches'], 'algorithmic_flops_per_launch': d['flops'] / d['launches'],
+                 'peak_source': peaks['src'] + (' (sustained bf16, MEASURED_PEAKS.json)' if roof['bound'] == 'tensor' else ' (copy bandwidth, MEASURED_PEAKS.json)'),
+                 'traffic': tr, 'traffic_source': tr_src,
+                 'timed': 'CUDA events around every launch of this bucket inside the timed region; kernels[] / rooflines[] come from a second, fully instrumented pass of the same steps'})
+    return roof
+
+
+def load_ncu_metric(key):
+    """A number copied from a committed ncu capture of this build (profiles/r2_ncu_metrics.json), with its provenance; None if absent."""
+    path = os.path.join(ROOT, 'profiles', 'r2_ncu_metrics.json')
+    try:
+        return json.load(open(path)).get(key)
+    except Exception:
+        return None
+
+
 def load_ncu_traffic(family, tag=None, algorithmic_bytes_per_launch=None):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/ncu_traffic.json), or None.
-    The capture holds layer-0 shapes; for a (family, shape) bucket averaged over layers the measured
-    traffic / algorithmic ratio of that shape is applied to the bucket's algorithmic bytes per launch."""
+    """(DRAM bytes per launch, provenance) of the dominant kernel from the committed ncu capture (profiles/ncu_traffic.json), or
+    (None, why).  The capture holds layer-0 shapes; the bench bucket averages one shape family over the layers, so the measured
+    traffic / algorithmic ratio of the captured launch is applied to the bucket's algorithmic bytes per launch and labelled so."""
     path = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
     if not os.path.exists(path):
-        return None
+        return None, 'no committed capture'
     try:
         d = json.load(open(path))
         e = d.get(f'{family}[{tag}]')
         if isinstance(e, dict) and e.get('traffic_over_algorithmic') and algorithmic_bytes_per_launch:
-            return e['traffic_over_algorithmic'] * algorithmic_bytes_per_launch
-        v = d.get(family)
-        return v if isinstance(v, (int, float)) else None
-    except Exception:
-        return None
+            return (e['traffic_over_algorithmic'] * algorithmic_bytes_per_launch,
+                    f"extrapolated: dram__bytes_read.sum + dram__bytes_write.sum of the layer-0 launch of this bucket in {e.get('capture', 'profiles/')} "
+                    f"({e['dram_bytes'] / 1e9:.3f} GB measured / {e['algorithmic_bytes'] / 1e9:.3f} GB algorithmic = {e['traffic_over_algorithmic']:.3f}) "
+                    f"x this bucket's algorithmic bytes per launch")
+        return None, f'no capture of {family}[{tag}]'
+    except Exception as ex:
+        return None, f'unreadable capture: {ex}'
 
 
 if __name__ == '__main__':

@@ -15,7 +15,9 @@ Seg = Tuple[int, int, int, int, int]  # (row_start, n_units, rows_per_unit, grou
 
 class KernelProfiler:
     """Optional per-launch CUDA-event timing on the launching stream (bench.py's roofline numbers).
-    Each record: (kernel family, shape tag, start event, end event, algorithmic flops, algorithmic bytes)."""
+    Each record: (kernel family, shape tag, start event, end event, algorithmic flops, algorithmic bytes, op-minimal bytes).
+    ``bytes`` counts every tensor the launch reads or writes once; ``min_bytes`` leaves out second outputs that exist only because
+    of how the work is cut into kernels (a saved pre-activation next to the activation, a fused norm's second output)."""
 
     def __init__(self, only: Optional[Tuple[str, str]] = None):
         self.records = []
@@ -27,12 +29,14 @@ class KernelProfiler:
     def summary(self):
         """{(family, tag): dict(launches, ms, flops, bytes)} — call after torch.cuda.synchronize()."""
         out = {}
-        for fam, tag, e0, e1, fl, by in self.records:
-            d = out.setdefault((fam, tag), dict(launches=0, ms=0.0, flops=0.0, bytes=0.0))
+        for rec in self.records:
+            fam, tag, e0, e1, fl, by = rec[:6]
+            d = out.setdefault((fam, tag), dict(launches=0, ms=0.0, flops=0.0, bytes=0.0, min_bytes=0.0))
             d['launches'] += 1
             d['ms'] += e0.elapsed_time(e1)
             d['flops'] += fl
             d['bytes'] += by
+            d['min_bytes'] += rec[6] if len(rec) > 6 and rec[6] else by
         return out
 
 
@@ -44,7 +48,7 @@ def set_profiler(p: Optional[KernelProfiler]) -> None:
     _PROFILER = p
 
 
-def _run(name: str, fn, p, tag: str = '', flops: float = 0.0, nbytes: float = 0.0, n_launch: int = 1) -> None:
+def _run(name: str, fn, p, tag: str = '', flops: float = 0.0, nbytes: float = 0.0, n_launch: int = 1, min_bytes: float = 0.0) -> None:
     prof = _PROFILER
     if prof is not None and not prof.wants(name, tag):
         prof = None
@@ -55,7 +59,7 @@ def _run(name: str, fn, p, tag: str = '', flops: float = 0.0, nbytes: float = 0.
     L.check(fn(C.byref(p), _stream()), name)
     if prof is not None:
         e1.record()
-        prof.records.append((name, tag, e0, e1, flops, nbytes))
+        prof.records.append((name, tag, e0, e1, flops, nbytes, min_bytes or nbytes))
     L.count_launch(n_launch)
 
 
@@ -173,8 +177,10 @@ def mixed_gemm(A: torch.Tensor, W: torch.Tensor, segs: Sequence[Seg], out: torch
     rows = sum(s[1] * s[2] for s in segs)
     groups = sum((s[1] if s[4] else 1) for s in segs)
     n_io = 1 + (out2 is not None) + (res is not None) + (aux is not None) + (norm is not None)
+    n_min = 1 + (res is not None) + (aux is not None)       # one output (+ the operands the epilogue semantically needs)
     _run('ot_mixed_gemm', L.load().ot_mixed_gemm, p, f'N{N}_K{K}_f{flags}', 2.0 * rows * N * K,
-         rows * K * 2.0 + n_io * rows * N * 2.0 + groups * N * K * 2.0)
+         rows * K * 2.0 + n_io * rows * N * 2.0 + groups * N * K * 2.0,
+         min_bytes=rows * K * 2.0 + n_min * rows * N * 2.0 + groups * N * K * 2.0)
     return out
 
 
@@ -239,7 +245,8 @@ def ffn_fused(zn: torch.Tensor, W1_f: torch.Tensor, b1: torch.Tensor, W2_f: torc
     # algorithmic bytes: zn in, y out (+ residual in, norm out), the saved pre-activation, the weights once per group
     n_io = 2 + (res is not None) + (norm is not None)
     _run('ot_ffn_fwd', L.load().ot_ffn_fwd, p, f'd{d}_F{F}_f{flags}{"_pre" if pre is not None else ""}', 4.0 * rows * d * F,
-         n_io * rows * d * 2.0 + (rows * F * 2.0 if pre is not None else 0.0) + groups * 2.0 * d * F * 2.0)
+         n_io * rows * d * 2.0 + (rows * F * 2.0 if pre is not None else 0.0) + groups * 2.0 * d * F * 2.0,
+         min_bytes=(2 + (res is not None)) * rows * d * 2.0 + (rows * F * 2.0 if pre is not None else 0.0) + groups * 2.0 * d * F * 2.0)
     return out
 
 
