@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define OT_ABI_VERSION 12
+#define OT_ABI_VERSION 14
 
 int ot_version(void);
 const char* ot_last_error_string(void);
@@ -128,6 +128,7 @@ typedef struct ot_ffn_params {
   ot_gemm_seg segs[3];
   void* out; int64_t ldo;
   void* pre; int64_t ldpre;          /* may be NULL (evaluation) */
+  void* h; int64_t ldh;              /* optional (NULL = not stored): bf16 [rows, F] copy of gelu_erf(pre) for the dW2 weight gradient */
   const void* res; int64_t ldr;
   const float* res_hp; float* out_hp; int64_t ld_hp; int64_t hp_row0;
   uint32_t drop_seed; float drop_rate;
@@ -137,6 +138,13 @@ typedef struct ot_ffn_params {
   float norm_eps;
 } ot_ffn_params;
 int ot_ffn_fwd(const ot_ffn_params* p, void* stream);
+/* Input-gradient chain of the same layer in one kernel (tape.gradient of OT/model.py:149-163 w.r.t. the FFN input, OT/train.py:131):
+ *   dpre = (dy . W2[g]^T) o gelu_erf'(pre)        dzn = dpre . W1[g]^T
+ * with the SAME struct read as:  zn = dy [rows, d] (input),  W1 = the second Dense's kernel as [n_groups, F, d] (N = F, K = d: the
+ * master layout of W2),  W2 = the first Dense's kernel as [n_groups, d, F] (the master layout of W1),  pre = saved pre-activation
+ * (INPUT),  h = dpre [rows, F] (OUTPUT, required: the dW1 weight gradient reads it),  out = dzn [rows, d].  b1 / b2 are ignored,
+ * flags must be 0.  dpre lives on chip between the two products and is stored from the kernel's own operand tile. */
+int ot_ffn_bwd(const ot_ffn_params* p, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Weight gradient  (tcgen05, both operands MN-major, split over rows, fp32 atomic accumulate)

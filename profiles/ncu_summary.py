@@ -8,12 +8,15 @@ METRICS = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.
            'dram__throughput.avg.pct_of_peak_sustained_elapsed', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
            'sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active',
            'sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active',
-           'lts__t_sector_hit_rate.pct', 'inst_executed', 'launch__registers_per_thread', 'launch__grid_size', 'launch__block_size',
+           'lts__t_sector_hit_rate.pct', 'lts__t_bytes.sum', 'lts__throughput.avg.pct_of_peak_sustained_elapsed', 'l1tex__m_xbar2l1tex_read_bytes.sum',
+           'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active',
+           'sm__issue_active.avg.pct_of_peak_sustained_elapsed', 'inst_executed', 'launch__registers_per_thread', 'launch__grid_size', 'launch__block_size',
            'smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio',
            'smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio',
            'smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio',
            'smsp__average_warps_issue_stalled_wait_per_issue_active.ratio']
-FAMILY = {'ot_mixed_gemm_kernel': 'ot_mixed_gemm', 'ot_wgrad_kernel': 'ot_wgrad', 'ot_attn_fwd_ws_kernel': 'ot_attn_fwd',
+FAMILY = {'ot_mixed_gemm_kernel': 'ot_mixed_gemm', 'ot_ffn_fused_kernel': 'ot_ffn_fwd', 'ot_wgrad_kernel': 'ot_wgrad', 'ot_attn_fwd_ws_kernel': 'ot_attn_fwd',
+          'ot_attn_fwd_v2_kernel': 'ot_attn_fwd', 'ot_attn_cached_kernel': 'ot_attn_ns_cached_fwd', 'ot_attn_dkv_kernel': 'ot_attn_bwd', 'ot_attn_dq_kernel': 'ot_attn_bwd',
           'ot_attn_fwd_kernel': 'ot_attn_fwd', 'ot_attn_bwd_fused_kernel': 'ot_attn_bwd', 'rmsnorm_fwd_kernel': 'ot_rmsnorm_fwd',
           'rmsnorm_bwd_kernel': 'ot_rmsnorm_bwd'}
 

@@ -36,7 +36,7 @@ class FfnParams(C.Structure):
     _fields_ = [('zn', vp), ('ldzn', i64), ('W1', vp), ('ldw1', i64), ('W2', vp), ('ldw2', i64),
                 ('b1', fp), ('b1_group_stride', i64), ('b2', fp), ('b2_group_stride', i64),
                 ('n_groups', i32), ('d', i32), ('F', i32), ('n_segs', i32), ('flags', i32), ('segs', GemmSeg * 3),
-                ('out', vp), ('ldo', i64), ('pre', vp), ('ldpre', i64), ('res', vp), ('ldr', i64),
+                ('out', vp), ('ldo', i64), ('pre', vp), ('ldpre', i64), ('h', vp), ('ldh', i64), ('res', vp), ('ldr', i64),
                 ('res_hp', fp), ('out_hp', fp), ('ld_hp', i64), ('hp_row0', i64), ('drop_seed', C.c_uint32), ('drop_rate', C.c_float),
                 ('norm_out', vp), ('ld_norm', i64), ('norm_gain', fp), ('norm_rstd', fp), ('norm_eps', C.c_float)]
 
@@ -121,11 +121,11 @@ class AucParams(C.Structure):
 
 METRICS_MAX_THRESHOLDS, METRICS_TAIL_WORDS, METRICS_RESULT_WORDS = 512, 8, 8  # OT_METRICS_*
 OPT_CHUNK = 1024  # OT_OPT_CHUNK
-ABI_VERSION = 12  # OT_ABI_VERSION of include/onetrans_b200.h this binding was written against
+ABI_VERSION = 14  # OT_ABI_VERSION of include/onetrans_b200.h this binding was written against
 
 # every symbol include/onetrans_b200.h declares (tests check that the library exports all of them)
 EXPORTED_SYMBOLS = [
-    'ot_version', 'ot_last_error_string', 'ot_num_sms', 'ot_mixed_gemm', 'ot_ffn_fwd', 'ot_wgrad', 'ot_attn_fwd', 'ot_attn_bwd', 'ot_attn_ns_cached_fwd',
+    'ot_version', 'ot_last_error_string', 'ot_num_sms', 'ot_mixed_gemm', 'ot_ffn_fwd', 'ot_ffn_bwd', 'ot_wgrad', 'ot_attn_fwd', 'ot_attn_bwd', 'ot_attn_ns_cached_fwd',
     'ot_rmsnorm_fwd', 'ot_rmsnorm_bwd', 'ot_ns_tokenizer_fwd', 'ot_ns_tokenizer_bwd', 'ot_fill_rows', 'ot_colsum', 'ot_dropout_mask',
     'ot_clip_rmsprop_step', 'ot_embed_gather_fwd', 'ot_embed_scatter_bwd', 'ot_embed_adagrad_step',
     'ot_heads_fwd', 'ot_heads_bwd', 'ot_metrics_update', 'ot_metrics_result', 'ot_auc_pack_keys', 'ot_auc_ranksum',
@@ -158,7 +158,7 @@ def load() -> C.CDLL:
                                        f'(recommend_b200/csrc/build.sh)')
         lib.ot_last_error_string.restype = C.c_char_p
         lib.ot_num_sms.restype = C.c_int
-        for name, st in [('ot_mixed_gemm', GemmParams), ('ot_ffn_fwd', FfnParams), ('ot_wgrad', WgradParams), ('ot_attn_fwd', AttnParams),
+        for name, st in [('ot_mixed_gemm', GemmParams), ('ot_ffn_fwd', FfnParams), ('ot_ffn_bwd', FfnParams), ('ot_wgrad', WgradParams), ('ot_attn_fwd', AttnParams),
                          ('ot_attn_bwd', AttnParams), ('ot_attn_ns_cached_fwd', AttnCachedParams), ('ot_rmsnorm_fwd', RmsnormParams), ('ot_rmsnorm_bwd', RmsnormParams),
                          ('ot_ns_tokenizer_fwd', NsTokenizerParams), ('ot_ns_tokenizer_bwd', NsTokenizerParams),
                          ('ot_colsum', ColsumParams), ('ot_clip_rmsprop_step', RmspropParams), ('ot_embed_gather_fwd', EmbedParams),

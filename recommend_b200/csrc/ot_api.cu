@@ -69,6 +69,7 @@ int num_sms() {
 int mixed_gemm_impl(const ot_gemm_params* p, cudaStream_t st);
 int wgrad_impl(const ot_wgrad_params* p, cudaStream_t st);
 int ffn_fwd_impl(const ot_ffn_params* p, cudaStream_t st);
+int ffn_bwd_impl(const ot_ffn_params* p, cudaStream_t st);
 int attn_fwd_impl(const ot_attn_params* p, cudaStream_t st);
 int attn_bwd_impl(const ot_attn_params* p, cudaStream_t st);
 int attn_cached_impl(const ot_attn_cached_params* p, cudaStream_t st);
@@ -103,6 +104,7 @@ int ot_mixed_gemm(const ot_gemm_params* p, void* stream) {
   return ot::mixed_gemm_impl(p, static_cast<cudaStream_t>(stream));
 }
 int ot_ffn_fwd(const ot_ffn_params* p, void* stream) { return ot::ffn_fwd_impl(p, static_cast<cudaStream_t>(stream)); }
+int ot_ffn_bwd(const ot_ffn_params* p, void* stream) { return ot::ffn_bwd_impl(p, static_cast<cudaStream_t>(stream)); }
 int ot_wgrad(const ot_wgrad_params* p, void* stream) {
   return ot::wgrad_impl(p, static_cast<cudaStream_t>(stream));
 }

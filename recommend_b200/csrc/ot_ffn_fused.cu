@@ -57,11 +57,13 @@ struct FfnKParams {
   int n_segs, total_mblks;
   int a_transposed;        // always 0; read by decode_tile
   int flags;               // OT_EPI_RESIDUAL | OT_EPI_DROPOUT | OT_EPI_NORM
+  int bwd;                 // 1: input-gradient form (ot_ffn_bwd): no biases, chunk epilogue multiplies by gelu'(pre) instead of applying gelu
   GemmSegDev segs[3];
   const float* b1; long long b1_gs;
   const float* b2; long long b2_gs;
   __nv_bfloat16* out; long long ldo;
   __nv_bfloat16* pre; long long ldpre;
+  __nv_bfloat16* hout; long long ldh;     // optional copy of h = gelu(pre) for the dW2 weight gradient, stored from the h tile itself
   const __nv_bfloat16* res; long long ldr;
   const float* res_hp; float* out_hp; long long ld_hp; long long hp_row0;
   uint32_t drop_seed, drop_thr16; float drop_scale;
@@ -86,7 +88,8 @@ __global__ void __launch_bounds__(FF_THREADS, 1)
 ot_ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW1,
                     const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmPre,
                     const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmNorm,
-                    const __grid_constant__ CUtensorMap tmRes, const __grid_constant__ FfnKParams p) {
+                    const __grid_constant__ CUtensorMap tmRes, const __grid_constant__ CUtensorMap tmH,
+                    const __grid_constant__ FfnKParams p) {
   constexpr int D = FF_D;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA = smem;
@@ -108,8 +111,12 @@ ot_ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* acc2_empty = bars + 15;          // 16 arrivals: output tile pulled out             (epilogue -> MMA)
   uint64_t* res_full = bars + 16;            // [4] residual box landed (one per set)
   uint64_t* tile_full = bars + 20;           // [8]
-  uint64_t* tile_empty = bars + 28;          // [8] read by the MMA issuer + 16 epilogue warps
-  int* tile_ring = reinterpret_cast<int*>(bars + 36);
+  uint64_t* tile_empty = bars + 28;          // [8] read by the MMA issuer, the h-store thread, the pre loader and 16 epilogue warps
+  uint64_t* h_stored = bars + 36;            // the TMA store of the h chunk has read the h tile  (store thread -> epilogue)
+  uint64_t* p_full = bars + 37;              // bwd: pre-activation chunk landed                   (TMA -> epilogue)
+  uint64_t* p_free = bars + 38;              // bwd: 16 arrivals: chunk read out                   (epilogue -> pre loader)
+  uint64_t* stage_free = bars + 39;          // bwd: 16 arrivals: the previous tile's output stores have read the staging boxes
+  int* tile_ring = reinterpret_cast<int*>(bars + 40);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tile_ring + FF_TILE_SLOTS);
 
   const int warp = threadIdx.x >> 5;
@@ -126,7 +133,8 @@ ot_ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     mbar_init(h_full, 4 * FF_SETS); mbar_init(h_empty, 1);
     mbar_init(acc2_full, 1); mbar_init(acc2_empty, 4 * FF_SETS);
     for (int i = 0; i < FF_SETS; ++i) mbar_init(&res_full[i], 1);
-    for (int i = 0; i < FF_TILE_SLOTS; ++i) { mbar_init(&tile_full[i], 1); mbar_init(&tile_empty[i], 1 + 4 * FF_SETS); }
+    for (int i = 0; i < FF_TILE_SLOTS; ++i) { mbar_init(&tile_full[i], 1); mbar_init(&tile_empty[i], 3 + 4 * FF_SETS); }
+    mbar_init(h_stored, 1); mbar_init(p_full, 1); mbar_init(p_free, 4 * FF_SETS); mbar_init(stage_free, 4 * FF_SETS);
     fence_mbar_init();
   }
   if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
@@ -259,6 +267,59 @@ ot_ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
       }
     }
+  } else if (warp == 2) {
+    // ===================== h store (optional second output) =====================
+    // The bf16 h chunk in shared memory is already laid out as two TMA boxes ([128 rows x 64 columns], 128-byte swizzle): when
+    // the caller wants h = gelu(pre) for the dW2 weight gradient (OT/train.py:131), one thread stores the tile as it is - no
+    // epilogue instruction is spent on it.  The epilogue waits for the store to have READ the tile before it writes the next chunk.
+    if (elect_one()) {
+      const bool save_h = p.hout != nullptr;
+      for (int it = 0;; ++it) {
+        const int slot = it & (FF_TILE_SLOTS - 1);
+        mbar_wait_backoff(&tile_full[slot], (it / FF_TILE_SLOTS) & 1, 32);
+        const int tile = tile_ring[slot];
+        mbar_arrive(&tile_empty[slot]);
+        if (tile < 0) break;
+        if (!save_h) continue;
+        const TileInfo t = decode_tile(p, tile);
+        for (int c = 0; c < NC; ++c) {
+          const uint32_t g = (uint32_t)it * NC + c;
+          mbar_wait_backoff(h_full, g & 1, 32);
+          if (t.valid == BM) {                       // partial tiles are written by the epilogue threads themselves (row masks)
+            tma_store_2d(&tmH, sH, c * FF_FC, t.row0);
+            tma_store_2d(&tmH, sH + FF_BOX_BYTES, c * FF_FC + 64, t.row0);
+            bulk_commit();
+            bulk_wait_read0();
+          }
+          mbar_arrive(h_stored);
+        }
+      }
+      bulk_wait_all();
+    }
+  } else if (warp == 3) {
+    // ===================== pre-activation loader (input-gradient form only) =====================
+    // dpre = (dy W2^T) o gelu'(pre): the saved pre-activation chunk [128 x 128] arrives by TMA in the 32 KB that the forward form
+    // uses for its per-warp store patches, one chunk ahead of the epilogue.  The same 32 KB are half of the output staging tile
+    // of the final epilogue, so a tile's first chunk waits until the previous tile's output stores have read them.
+    if (elect_one()) {
+      for (int it = 0;; ++it) {
+        const int slot = it & (FF_TILE_SLOTS - 1);
+        mbar_wait_backoff(&tile_full[slot], (it / FF_TILE_SLOTS) & 1, 32);
+        const int tile = tile_ring[slot];
+        mbar_arrive(&tile_empty[slot]);
+        if (tile < 0) break;
+        if (!p.bwd) continue;
+        const TileInfo t = decode_tile(p, tile);
+        for (int c = 0; c < NC; ++c) {
+          const uint32_t g = (uint32_t)it * NC + c;
+          if (g > 0) mbar_wait_backoff(p_free, (g - 1) & 1, 32);
+          if (c == 0 && it > 0) mbar_wait_backoff(stage_free, (it - 1) & 1, 32);
+          mbar_arrive_expect_tx(p_full, 2 * FF_BOX_BYTES);
+          tma_load_2d(sP, &tmRes, p_full, c * FF_FC, t.row0);                       // tmRes maps the pre-activation in this form
+          tma_load_2d(sP + FF_BOX_BYTES, &tmRes, p_full, c * FF_FC + 64, t.row0);
+        }
+      }
+    }
   } else if (warp >= 4) {
     // ===================== epilogue (warps 4..19: four sets of four) =====================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(FF_EPI_REGS));
@@ -269,7 +330,8 @@ ot_ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int r_own = lgrp * 32 + lane;
     const bool set_io = (et == 0);                     // issues this set's TMA traffic of the final epilogue
     const bool f_res = p.flags & OT_EPI_RESIDUAL, f_drop = p.flags & OT_EPI_DROPOUT, f_norm = p.flags & OT_EPI_NORM;
-    const bool save_pre = p.pre != nullptr;
+    const bool bwd = p.bwd != 0;
+    const bool save_pre = !bwd && p.pre != nullptr, save_h = p.hout != nullptr;
     uint8_t* box_h = sH + grp * FF_BOX_BYTES;          // chunk phase: h columns [64 grp, +64)
     uint8_t* patch = sP + (warp - 4) * 2048;           // chunk phase: this warp's pre-activation patch, [32 rows x 64 bytes]
     uint8_t* box_y = stage + set * FF_BOX_BYTES;       // final phase: output columns [64 set, +64)
@@ -293,6 +355,7 @@ ot_ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (it > 0) {
         if (lane == 0) bulk_wait_read0();
         named_bar_sync(FF_BAR_ALL, FF_EPI_THREADS);
+        if (bwd && lane == 0) mbar_arrive(stage_free);       // the pre loader may refill its half of the staging tile
       }
 
       // -------------------------------- F chunks --------------------------------
@@ -308,7 +371,7 @@ ot_ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc1_empty[b]);
         f32x2 f[16];
-        {
+        if (!bwd) {
           const float4* b4 = reinterpret_cast<const float4*>(p.b1 + (long long)t.group * p.b1_gs + c * FF_FC + set * 32);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -316,6 +379,20 @@ ot_ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             f[2 * j] = add2(pk2(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1])), pk2(bb.x, bb.y));
             f[2 * j + 1] = add2(pk2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])), pk2(bb.z, bb.w));
           }
+        } else {
+          // input-gradient form: dpre = (dy W2^T) o gelu'(pre), pre from the TMA-loaded chunk (own row, own 32 columns)
+          mbar_wait(p_full, g & 1);
+          uint32_t w[16];
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch) {
+            const uint4 q = *reinterpret_cast<const uint4*>(sP + grp * FF_BOX_BYTES + swz_off<128>(r_own, (set & 1) * 4 + ch));
+            w[ch * 4 + 0] = q.x; w[ch * 4 + 1] = q.y; w[ch * 4 + 2] = q.z; w[ch * 4 + 3] = q.w;
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(p_free);
+#pragma unroll
+          for (int e = 0; e < 16; ++e)
+            f[e] = mul2(pk2(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1])), gelu_erf_grad2(pk2(bf16lo(w[e]), bf16hi(w[e]))));
         }
         if (save_pre) {
           // pre-activation -> this warp's private [32 rows x 32 columns] staging patch (64-byte swizzle) -> HBM by one TMA store
@@ -341,9 +418,14 @@ ot_ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int ch = 0; ch < 4; ++ch) dst[ch] = make_uint4(pk[ch * 4], pk[ch * 4 + 1], pk[ch * 4 + 2], pk[ch * 4 + 3]);
           }
         }
+        if (!bwd) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) f[j] = gelu_erf2(f[j]);
-        if (g > 0) mbar_wait(h_empty, (g - 1) & 1);            // FFN2 of the previous chunk has read the h tile
+          for (int j = 0; j < 16; ++j) f[j] = gelu_erf2(f[j]);
+        }
+        if (g > 0) {
+          mbar_wait(h_empty, (g - 1) & 1);                     // FFN2 of the previous chunk has read the h tile
+          if (save_h) mbar_wait(h_stored, (g - 1) & 1);        // ... and so has its TMA store
+        }
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
           float a0, a1, a2, a3, a4, a5, a6, a7;
@@ -351,6 +433,8 @@ ot_ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           uint4 q;
           q.x = pack_bf16x2(a0, a1); q.y = pack_bf16x2(a2, a3); q.z = pack_bf16x2(a4, a5); q.w = pack_bf16x2(a6, a7);
           *reinterpret_cast<uint4*>(box_h + swz_off<128>(r_own, (set & 1) * 4 + ch)) = q;
+          if (save_h && !full && r_own < t.valid)
+            *reinterpret_cast<uint4*>(p.hout + (long long)(t.row0 + r_own) * p.ldh + c * FF_FC + set * 32 + ch * 8) = q;
         }
         fence_proxy_async_smem();
         tc_fence_before();
@@ -360,6 +444,7 @@ ot_ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
       // -------------------------------- output tile --------------------------------
       mbar_wait_backoff(acc2_full, it & 1, 32);
+      if (save_h) mbar_wait(h_stored, ((uint32_t)it * NC + NC - 1) & 1);   // the last chunk's h store has read the h tile too
       tc_fence_after();
       if (save_pre && lane == 0) bulk_wait_read0();            // this warp's last pre-activation store has read its patch
       named_bar_sync(FF_BAR_ALL, FF_EPI_THREADS);              // h tile free (acc2_full), pre staging free: 4 boxes of staging
@@ -382,14 +467,14 @@ ot_ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
       }
       f32x2 ss2 = pk2(0.0f);
-      const float* bias2 = p.b2 + (long long)t.group * p.b2_gs + col0;
+      const float* bias2 = bwd ? nullptr : p.b2 + (long long)t.group * p.b2_gs + col0;
 #pragma unroll 1
       for (int half = 0; half < 2; ++half) {
         uint32_t v[32];
         tmem_ld_x32(t_lane + FF_T_ACC2 + col0 + half * 32, v);
         tmem_ld_wait();
         f32x2 f[16];
-        {
+        if (!bwd) {
           const float4* b4 = reinterpret_cast<const float4*>(bias2 + half * 32);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -397,6 +482,9 @@ ot_ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             f[2 * j] = add2(pk2(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1])), pk2(bb.x, bb.y));
             f[2 * j + 1] = add2(pk2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])), pk2(bb.z, bb.w));
           }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = pk2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
         }
         if (f_drop) {   // inverted dropout on the branch output, before the residual add (OT/model.py:198)
           const uint32_t grow = static_cast<uint32_t>(t.row0 + r_own);
@@ -527,14 +615,18 @@ static int make_2d(CUtensorMap* tm, const void* base, uint64_t cols, uint64_t ro
   return make_tmap_bf16(tm, base, 2, dims, str, box, 128);
 }
 
-int ffn_fwd_impl(const ot_ffn_params* p, cudaStream_t st) {
-  if (!p || !p->zn || !p->W1 || !p->W2 || !p->b1 || !p->b2 || !p->out) OT_FAIL(OT_ERR_INVALID_ARG, "ot_ffn_fwd: null pointer");
+static int ffn_launch(const ot_ffn_params* p, cudaStream_t st, bool bwd) {
+  const char* who = bwd ? "ot_ffn_bwd" : "ot_ffn_fwd";
+  if (!p || !p->zn || !p->W1 || !p->W2 || !p->out) OT_FAIL(OT_ERR_INVALID_ARG, "%s: null pointer", who);
+  if (!bwd && (!p->b1 || !p->b2)) OT_FAIL(OT_ERR_INVALID_ARG, "ot_ffn_fwd: null bias");
+  if (bwd && (!p->pre || !p->h || p->flags != 0 || p->res || p->res_hp))
+    OT_FAIL(OT_ERR_INVALID_ARG, "ot_ffn_bwd: needs pre (saved pre-activation, input) and h (dpre, output); no flags / residual");
   if (p->d != FF_D) OT_FAIL(OT_ERR_UNSUPPORTED_SHAPE, "ot_ffn_fwd: d=%d (this kernel is built for d=%d; use the two-GEMM path)", p->d, FF_D);
   if (p->F <= 0 || p->F % FF_FC != 0) OT_FAIL(OT_ERR_UNSUPPORTED_SHAPE, "ot_ffn_fwd: F=%d not a multiple of %d", p->F, FF_FC);
   if (p->n_segs < 1 || p->n_segs > 3) OT_FAIL(OT_ERR_INVALID_ARG, "ot_ffn_fwd: n_segs=%d", p->n_segs);
-  if ((reinterpret_cast<uintptr_t>(p->b1) & 15) || (reinterpret_cast<uintptr_t>(p->b2) & 15) || (p->b1_group_stride % 4) || (p->b2_group_stride % 4))
+  if (!bwd && ((reinterpret_cast<uintptr_t>(p->b1) & 15) || (reinterpret_cast<uintptr_t>(p->b2) & 15) || (p->b1_group_stride % 4) || (p->b2_group_stride % 4)))
     OT_FAIL(OT_ERR_INVALID_ARG, "ot_ffn_fwd: biases must be 16-byte aligned with group strides that are multiples of 4");
-  if ((p->ldzn % 8) || (p->ldo % 8) || (p->pre && (p->ldpre % 8)) || (p->res && (p->ldr % 8)) || (p->ldw1 % 8) || (p->ldw2 % 8))
+  if ((p->ldzn % 8) || (p->ldo % 8) || (p->pre && (p->ldpre % 8)) || (p->h && (p->ldh % 8)) || (p->res && (p->ldr % 8)) || (p->ldw1 % 8) || (p->ldw2 % 8))
     OT_FAIL(OT_ERR_UNSUPPORTED_SHAPE, "ot_ffn_fwd: leading dimensions must be multiples of 8 elements");
   if ((p->flags & OT_EPI_RESIDUAL) && !p->res) OT_FAIL(OT_ERR_INVALID_ARG, "ot_ffn_fwd: residual flag without res");
   if (p->flags & ~(OT_EPI_RESIDUAL | OT_EPI_DROPOUT | OT_EPI_NORM)) OT_FAIL(OT_ERR_INVALID_ARG, "ot_ffn_fwd: unsupported flags %d", p->flags);
@@ -543,7 +635,7 @@ int ffn_fwd_impl(const ot_ffn_params* p, cudaStream_t st) {
 
   FfnKParams kp;
   memset(&kp, 0, sizeof(kp));
-  kp.F = p->F; kp.NC = p->F / FF_FC; kp.n_segs = p->n_segs; kp.flags = p->flags;
+  kp.F = p->F; kp.NC = p->F / FF_FC; kp.n_segs = p->n_segs; kp.flags = p->flags; kp.bwd = bwd ? 1 : 0;
   long long row_extent = 0;
   for (int s = 0; s < p->n_segs; ++s) {
     const ot_gemm_seg& sg = p->segs[s];
@@ -559,6 +651,7 @@ int ffn_fwd_impl(const ot_ffn_params* p, cudaStream_t st) {
   if (kp.total_mblks >= (1 << 24)) OT_FAIL(OT_ERR_UNSUPPORTED_SHAPE, "ot_ffn_fwd: %d tiles exceed the tile-index range", kp.total_mblks);
   kp.b1 = p->b1; kp.b1_gs = p->b1_group_stride; kp.b2 = p->b2; kp.b2_gs = p->b2_group_stride;
   kp.out = (__nv_bfloat16*)p->out; kp.ldo = p->ldo; kp.pre = (__nv_bfloat16*)p->pre; kp.ldpre = p->ldpre;
+  kp.hout = (__nv_bfloat16*)p->h; kp.ldh = p->ldh;
   kp.res = (const __nv_bfloat16*)p->res; kp.ldr = p->ldr;
   kp.res_hp = p->res_hp; kp.out_hp = p->out_hp; kp.ld_hp = p->ld_hp; kp.hp_row0 = p->hp_row0;
   kp.norm_out = (__nv_bfloat16*)p->norm_out; kp.ld_norm = p->ld_norm; kp.norm_gain = p->norm_gain; kp.norm_rstd = p->norm_rstd;
@@ -576,14 +669,17 @@ int ffn_fwd_impl(const ot_ffn_params* p, cudaStream_t st) {
   }
   kp.sched = sched_slot(st);
 
-  CUtensorMap tmA, tmW1, tmW2, tmPre, tmOut, tmNorm, tmRes;
+  CUtensorMap tmA, tmW1, tmW2, tmPre, tmOut, tmNorm, tmRes, tmH;
   int rc;
   if ((rc = make_2d(&tmA, p->zn, FF_D, (uint64_t)row_extent, p->ldzn, BM))) return rc;
   if ((rc = make_2d(&tmW1, p->W1, FF_D, (uint64_t)p->n_groups * p->F, p->ldw1, FF_FC))) return rc;
   if ((rc = make_2d(&tmW2, p->W2, (uint64_t)p->F, (uint64_t)p->n_groups * FF_D, p->ldw2, FF_D))) return rc;
   if ((rc = make_2d(&tmOut, p->out, FF_D, (uint64_t)row_extent, p->ldo, BM))) return rc;
-  tmPre = tmOut; tmNorm = tmOut; tmRes = tmOut;
-  if (p->pre) {   // per-warp patches: 32 columns x 32 rows, 64-byte swizzle
+  tmPre = tmOut; tmNorm = tmOut; tmRes = tmOut; tmH = tmOut;
+  if (p->h && (rc = make_2d(&tmH, p->h, (uint64_t)p->F, (uint64_t)row_extent, p->ldh, BM))) return rc;
+  if (bwd) {      // the saved pre-activation is an INPUT here: [128 x 64] boxes like a residual tile
+    if ((rc = make_2d(&tmRes, p->pre, (uint64_t)p->F, (uint64_t)row_extent, p->ldpre, BM))) return rc;
+  } else if (p->pre) {   // per-warp patches: 32 columns x 32 rows, 64-byte swizzle
     uint64_t dims[2] = {(uint64_t)p->F, (uint64_t)row_extent};
     uint64_t str[1] = {(uint64_t)p->ldpre * 2};
     uint32_t box[2] = {32u, 32u};
@@ -598,9 +694,12 @@ int ffn_fwd_impl(const ot_ffn_params* p, cudaStream_t st) {
     attr_done = true;
   }
   const int grid = kp.total_mblks < num_sms() ? kp.total_mblks : num_sms();
-  ot_ffn_fused_kernel<<<grid, FF_THREADS, FF_SMEM_BYTES, st>>>(tmA, tmW1, tmW2, tmPre, tmOut, tmNorm, tmRes, kp);
+  ot_ffn_fused_kernel<<<grid, FF_THREADS, FF_SMEM_BYTES, st>>>(tmA, tmW1, tmW2, tmPre, tmOut, tmNorm, tmRes, tmH, kp);
   OT_CUDA_CHECK(cudaGetLastError());
   return OT_OK;
 }
+
+int ffn_fwd_impl(const ot_ffn_params* p, cudaStream_t st) { return ffn_launch(p, st, false); }
+int ffn_bwd_impl(const ot_ffn_params* p, cudaStream_t st) { return ffn_launch(p, st, true); }
 
 }  // namespace ot

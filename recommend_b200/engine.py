@@ -16,6 +16,8 @@ from . import ops
 from ._lib import OT_EPI_BIAS, OT_EPI_GELU, OT_EPI_GELU_GRAD, OT_EPI_RESIDUAL
 
 bf16 = torch.bfloat16
+_SAVE_H = __import__('os').environ.get('OT_FFN_SAVE_H', '0') != '0'      # A/B switch: also store h in the fused forward (see ffn_forward)
+_FUSED_BWD = __import__('os').environ.get('OT_FFN_FUSED_BWD', '1') != '0'  # A/B switch: one-kernel input-gradient chain
 
 
 def _grad_buf(p: torch.Tensor) -> torch.Tensor:
@@ -178,9 +180,13 @@ def ffn_forward(zn: torch.Tensor, res: Optional[torch.Tensor], w: BlockWeights, 
     if ops.can_fuse_ffn(d, F):
         # one kernel: h = gelu(zn W1 + b1) stays on chip, only the pre-activation (the backward's GELU' input) is stored
         pre = torch.empty(rows_t, F, dtype=bf16, device=dev) if save else None
-        ops.ffn_fused(zn, w.W1_f, b1, w.W2_f, b2, split_segments(segs, hp0) if hp else segs, y, pre=pre, res=res,
+        # OT_FFN_SAVE_H=1 also stores h (straight from the kernel's h tile by TMA) so that dW2 reads it instead of rebuilding
+        # gelu(pre) inside the weight-gradient kernel; measured a wash on B200 (forward + 0.8 ms, dW2 - 0.8 ms) for 6 GB more
+        # saved activations, so it is off by default
+        h = torch.empty(rows_t, F, dtype=bf16, device=dev) if (save and _SAVE_H) else None
+        ops.ffn_fused(zn, w.W1_f, b1, w.W2_f, b2, split_segments(segs, hp0) if hp else segs, y, pre=pre, h=h, res=res,
                       res_hp=res_hp if hp else None, out_hp=y_hp, hp_row0=hp0 if hp else 0, dropout=drop, norm=nrm)
-        return y, (pre, None), y_hp
+        return y, (pre, h), y_hp
     h = torch.empty(rows_t, F, dtype=bf16, device=dev)
     pre = torch.empty(rows_t, F, dtype=bf16, device=dev) if save else None
     ops.mixed_gemm(zn, w.W1_f, segs, h, flags=OT_EPI_BIAS | OT_EPI_GELU, bias=b1, out2=pre)
@@ -204,10 +210,14 @@ def ffn_backward(dy: torch.Tensor, zn: torch.Tensor, saved, w: BlockWeights, seg
     ops.wgrad_rows(h if h is not None else pre, dy, segs, W2_grad, F * d, d, 1, q_colsum=b2_grad, q_colsum_group_stride=d,
                    p_gelu=h is None)
     dpre = torch.empty(rows_t, F, dtype=bf16, device=dev)
-    ops.mixed_gemm(dy, w.W2_b, segs, dpre, flags=OT_EPI_GELU_GRAD, aux=pre)
-    ops.wgrad_rows(zn, dpre, segs, W1_grad, d * F, F, 1, q_colsum=b1_grad, q_colsum_group_stride=F)  # dW1 and db1
     dzn = torch.empty(rows_t, d, dtype=bf16, device=dev)
-    ops.mixed_gemm(dpre, w.W1_b, segs, dzn)
+    if ops.can_fuse_ffn(d, F) and _FUSED_BWD:
+        # one kernel: dpre = (dy W2^T) o gelu'(pre) stays on chip as the operand of dzn = dpre W1^T and is stored once for dW1
+        ops.ffn_fused_bwd(dy, w.W2_b, w.W1_b, pre, segs, dpre, dzn)
+    else:
+        ops.mixed_gemm(dy, w.W2_b, segs, dpre, flags=OT_EPI_GELU_GRAD, aux=pre)
+        ops.mixed_gemm(dpre, w.W1_b, segs, dzn)
+    ops.wgrad_rows(zn, dpre, segs, W1_grad, d * F, F, 1, q_colsum=b1_grad, q_colsum_group_stride=F)  # dW1 and db1
     return dzn
 
 
@@ -444,13 +454,18 @@ def candidates_forward(x_ns: torch.Tensor, C_: int, blocks, plan, cache, H: int,
     d = x_ns.shape[1]
     dh = d // H
     x = x_ns
-    for (P, w), (cur, Tn, cur_S, keep, Tq, keep_S), kv_s in zip(blocks, plan, cache):
+    pre_norm = None                      # norm1 of this layer, written by the previous layer's FFN epilogue when it could be fused
+    n_layers = len(blocks)
+    for l, ((P, w), (cur, Tn, cur_S, keep, Tq, keep_S), kv_s) in enumerate(zip(blocks, plan, cache)):
         assert x.shape[0] == Tn * C_
         rows, rows_t, off = Tn * C_, Tq * C_, (Tn - Tq) * C_
         segs_all = ops.position_segments(cur - Tn, cur, cur, L_ns, 'tail', C_)
         segs_tail = ops.position_segments(cur - Tq, cur, cur, L_ns, 'tail', C_)
-        xn = torch.empty(rows, d, dtype=bf16, device=dev)
-        ops.rmsnorm_fwd(x, P['norm1'], xn, None, eps, x_hp, 0)
+        if pre_norm is not None:
+            xn = pre_norm
+        else:
+            xn = torch.empty(rows, d, dtype=bf16, device=dev)
+            ops.rmsnorm_fwd(x, P['norm1'], xn, None, eps, x_hp, 0)
         kv = torch.empty(rows, 2 * d, dtype=bf16, device=dev)
         ops.mixed_gemm(xn, w.Wkv_f, segs_all, kv)
         q = torch.empty(rows_t, d, dtype=bf16, device=dev)
@@ -468,5 +483,11 @@ def candidates_forward(x_ns: torch.Tensor, C_: int, blocks, plan, cache, H: int,
             ops.mixed_gemm(o, w.Wo_f, [(0, 1, rows_t, 0, 0)], z, flags=OT_EPI_RESIDUAL, res=x[off:])
         zn = torch.empty(rows_t, d, dtype=bf16, device=dev)
         ops.rmsnorm_fwd(z, P['norm2'], zn, None, eps, z_hp, 0)
-        x, _, x_hp = ffn_forward(zn, z, w, P['b1'], P['b2'], segs_tail, False, z_hp)
+        # the fused FFN kernel keeps the finished row in TMEM, so the NEXT layer's norm1 (OT/model.py:191) costs it one more pass
+        # over TMEM instead of a kernel of its own; the two-GEMM path (d != 256) keeps the stand-alone norm
+        n1 = None
+        if l + 1 < n_layers and ops.can_fuse_ffn(d, w.W1_f.shape[1]):
+            n1 = {'gain': blocks[l + 1][0]['norm1'], 'eps': eps}
+        x, _, x_hp = ffn_forward(zn, z, w, P['b1'], P['b2'], segs_tail, False, z_hp, norm=n1)
+        pre_norm = n1['out'] if n1 is not None and 'out' in n1 else None
     return x, x_hp

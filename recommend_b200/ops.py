@@ -192,13 +192,14 @@ def can_fuse_ffn(d: int, F: int) -> bool:
 
 
 def ffn_fused(zn: torch.Tensor, W1_f: torch.Tensor, b1: torch.Tensor, W2_f: torch.Tensor, b2: torch.Tensor, segs: Sequence[Seg],
-              out: torch.Tensor, *, pre: Optional[torch.Tensor] = None, res: Optional[torch.Tensor] = None,
+              out: torch.Tensor, *, pre: Optional[torch.Tensor] = None, h: Optional[torch.Tensor] = None, res: Optional[torch.Tensor] = None,
               res_hp: Optional[torch.Tensor] = None, out_hp: Optional[torch.Tensor] = None, hp_row0: int = 0,
               dropout: Optional[Tuple[int, float]] = None,
               norm: Optional[Tuple[torch.Tensor, torch.Tensor, Optional[torch.Tensor], float]] = None) -> torch.Tensor:
     """``out = res + drop(gelu(zn @ W1[g].T + b1[g]) @ W2[g].T + b2[g])`` in one kernel (MixedFFN.call, OT/model.py:149-163, with
     the residual / dropout of :198); the hidden activation never reaches HBM.  ``W1_f [G, F, d]``, ``W2_f [G, d, F]`` bf16;
-    ``pre [rows, F]`` receives the pre-activation for the backward pass; ``norm`` as in ``mixed_gemm``."""
+    ``pre [rows, F]`` receives the pre-activation for the backward pass and ``h [rows, F]`` (optional) ``gelu(pre)`` for the dW2
+    weight gradient - stored by TMA straight from the kernel's own h tile; ``norm`` as in ``mixed_gemm``."""
     for t, n in ((zn, 'zn'), (W1_f, 'W1'), (W2_f, 'W2'), (out, 'out')):
         _check_bf16(t, n)
     G, F, d = W1_f.shape
@@ -219,6 +220,9 @@ def ffn_fused(zn: torch.Tensor, W1_f: torch.Tensor, b1: torch.Tensor, W2_f: torc
     if pre is not None:
         _check_bf16(pre, 'pre')
         p.pre, p.ldpre = pre.data_ptr(), pre.stride(0)
+    if h is not None:
+        _check_bf16(h, 'h')
+        p.h, p.ldh = h.data_ptr(), h.stride(0)
     if res is not None:
         _check_bf16(res, 'res')
         flags |= L.OT_EPI_RESIDUAL
@@ -244,10 +248,36 @@ def ffn_fused(zn: torch.Tensor, W1_f: torch.Tensor, b1: torch.Tensor, W2_f: torc
     groups = sum((s[1] if s[4] else 1) for s in segs)
     # algorithmic bytes: zn in, y out (+ residual in, norm out), the saved pre-activation, the weights once per group
     n_io = 2 + (res is not None) + (norm is not None)
-    _run('ot_ffn_fwd', L.load().ot_ffn_fwd, p, f'd{d}_F{F}_f{flags}{"_pre" if pre is not None else ""}', 4.0 * rows * d * F,
-         n_io * rows * d * 2.0 + (rows * F * 2.0 if pre is not None else 0.0) + groups * 2.0 * d * F * 2.0,
+    n_f = (pre is not None) + (h is not None)
+    _run('ot_ffn_fwd', L.load().ot_ffn_fwd, p, f'd{d}_F{F}_f{flags}{"_pre" if pre is not None else ""}{"_h" if h is not None else ""}', 4.0 * rows * d * F,
+         n_io * rows * d * 2.0 + n_f * rows * F * 2.0 + groups * 2.0 * d * F * 2.0,
          min_bytes=(2 + (res is not None)) * rows * d * 2.0 + (rows * F * 2.0 if pre is not None else 0.0) + groups * 2.0 * d * F * 2.0)
     return out
+
+
+def ffn_fused_bwd(dy: torch.Tensor, W2_b: torch.Tensor, W1_b: torch.Tensor, pre: torch.Tensor, segs: Sequence[Seg], dpre: torch.Tensor,
+                  dzn: torch.Tensor) -> torch.Tensor:
+    """Input-gradient chain of the FFN in one kernel: ``dpre = (dy @ W2[g].T) * gelu'(pre)`` (written, the dW1 weight gradient reads
+    it) and ``dzn = dpre @ W1[g].T`` (returned).  ``W2_b [G, F, d]`` / ``W1_b [G, d, F]`` are plain bf16 casts of the masters."""
+    for t, n in ((dy, 'dy'), (W2_b, 'W2_b'), (W1_b, 'W1_b'), (pre, 'pre'), (dpre, 'dpre'), (dzn, 'dzn')):
+        _check_bf16(t, n)
+    G, F, d = W2_b.shape
+    assert W1_b.shape == (G, d, F) and dy.dim() == 2 and dy.shape[1] == d and pre.shape == dpre.shape == (dy.shape[0], F)
+    assert W2_b.stride(2) == 1 and W2_b.stride(0) == F * W2_b.stride(1) and W1_b.stride(2) == 1 and W1_b.stride(0) == d * W1_b.stride(1)
+    p = L.FfnParams()
+    p.zn, p.ldzn, p.W1, p.ldw1, p.W2, p.ldw2 = dy.data_ptr(), dy.stride(0), W2_b.data_ptr(), W2_b.stride(1), W1_b.data_ptr(), W1_b.stride(1)
+    p.n_groups, p.d, p.F, p.n_segs, p.flags = G, d, F, len(segs), 0
+    for i, s in enumerate(segs):
+        sg = p.segs[i]
+        sg.row_start, sg.n_units, sg.rows_per_unit, sg.group_start, sg.group_stride = s[:5]
+        sg.a_row_start = s[0]
+    p.out, p.ldo = dzn.data_ptr(), dzn.stride(0)
+    p.pre, p.ldpre, p.h, p.ldh = pre.data_ptr(), pre.stride(0), dpre.data_ptr(), dpre.stride(0)
+    rows = sum(s[1] * s[2] for s in segs)
+    groups = sum((s[1] if s[4] else 1) for s in segs)
+    _run('ot_ffn_bwd', L.load().ot_ffn_bwd, p, f'd{d}_F{F}', 4.0 * rows * d * F,
+         2.0 * rows * d * 2.0 + 2.0 * rows * F * 2.0 + groups * 2.0 * d * F * 2.0)
+    return dzn
 
 
 def can_fuse_norm(N: int) -> bool:

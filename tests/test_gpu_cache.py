@@ -42,11 +42,17 @@ def test_cached_attention_kernel(C, H, dh, Tq, Tn, Ls):
 
 @pytest.mark.parametrize('schedule,L_ns,layers', [('linear_to_ns', 16, 4), ('reference_ratio', 16, 6), ('halving', 8, 3)])
 def test_t8_cached_scoring_equals_uncached_forward(schedule, L_ns, layers):
+    """T8 against the ORACLE: the cached two-stage scoring and the uncached forward on the same C rows are each held to the
+    north_star bar (logits rel-L2 <= 1e-2 vs the fp32 oracle, identical bf16-representable weights).  The two bf16 evaluations are
+    also compared with each other, but only against the triangle bound of the two (2e-2): they round at different places (tile
+    packing, softmax block order, which norms ride in an epilogue), so their mutual distance is not a parity statement."""
     ocfg, cfg = make_configs(num_layers=layers, num_ns_tokens=L_ns, schedule=schedule)
     P = O.init_params(ocfg, seed=5)
     O.randomize_small_params(P, seed=6)
+    Pb = {k: (v.to(bf16).float() if (v.dim() >= 2 and 'ns_tokenizer' not in k and 'task_heads' not in k and 'sep_embedding' not in k) else v)
+          for k, v in P.items()}
     model = R.OneTransModel(cfg).cuda()
-    R.load_reference_style_params(model, P)
+    R.load_reference_style_params(model, Pb)
     C = 50
     non_seq, seq1, _ = O.synthetic_batch(ocfg, C, (60, 50, 40), seed=11)
     seq1 = {k: v[:1] for k, v in seq1.items()}                      # ONE user
@@ -56,27 +62,19 @@ def test_t8_cached_scoring_equals_uncached_forward(schedule, L_ns, layers):
         model.reset_kv_cache()
         cached = model(to_cuda(non_seq), to_cuda(seq1), use_kv_cache=True, return_logits=True)   # builds the cache
         again = model(to_cuda(non_seq), to_cuda(seq1), use_kv_cache=True, return_logits=True)    # reuses it
-    for t in cfg.tasks:
-        assert cached[t].shape == (C, 1)
-        # two bf16 evaluations of the same function (different tile packing / softmax block order); held to the same bar as
-        # either of them against the fp32 oracle (measured 0.24-0.66e-2)
-        print('cached vs uncached rel-L2', t, rel_l2(cached[t], full[t]))
-        assert rel_l2(cached[t], full[t]) <= LOGIT_TOL, (t, rel_l2(cached[t], full[t]))
-        assert torch.equal(cached[t], again[t])
-    # and against the fp32 oracle on the same C rows (uncached by construction)
     seq_o = {k: v.to(bf16).float() for k, v in seqC.items()}
     ocfg.pyramid_keep_lens = R.resolve_keep_lens(cfg, 60 + 50 + 40 + 2 + L_ns)
-    Pb = {k: (v.to(bf16).float() if (v.dim() >= 2 and 'ns_tokenizer' not in k and 'task_heads' not in k and 'sep_embedding' not in k) else v)
-          for k, v in P.items()}
-    R.load_reference_style_params(model, Pb)
-    with torch.no_grad():
-        model.reset_kv_cache()
-        cached = model(to_cuda(non_seq), to_cuda(seq1), use_kv_cache=True, return_logits=True)
     ref = O.model_forward(Pb, ocfg, non_seq, seq_o, return_logits=True)
-    lo = torch.cat([ref[t].flatten() for t in cfg.tasks])
-    lg = torch.cat([cached[t].flatten().float().cpu() for t in cfg.tasks])
-    print('cached vs fp32 oracle rel-L2', rel_l2(lg, lo))
-    assert rel_l2(lg, lo) <= LOGIT_TOL, rel_l2(lg, lo)                # north_star: logits rel err <= 1e-2 (measured 0.39-0.87e-2)
+    cat = lambda d: torch.cat([d[t].flatten().float().cpu() for t in cfg.tasks])
+    lo = cat(ref)
+    e_cached, e_full, e_mutual = rel_l2(cat(cached), lo), rel_l2(cat(full), lo), rel_l2(cat(cached), cat(full))
+    print(f'cached vs fp32 oracle rel-L2 {e_cached:.3e}   uncached vs fp32 oracle {e_full:.3e}   cached vs uncached {e_mutual:.3e}')
+    for t in cfg.tasks:
+        assert cached[t].shape == (C, 1)
+        assert torch.equal(cached[t], again[t])
+    assert e_cached <= LOGIT_TOL, e_cached              # north_star: logits rel err <= 1e-2, cached path
+    assert e_full <= LOGIT_TOL, e_full                  # ... and the uncached path on the same rows
+    assert e_mutual <= 2 * LOGIT_TOL, e_mutual
 
 
 def _cache_fp(cache):

@@ -359,11 +359,13 @@ def test_ffn_fused_forward(B, n_s, n_ns, F, opts):
     mask = None
     if drop:
         mask = ops.dropout_mask(torch.ones(rows, d, dtype=bf16, device='cuda'), drop[0], drop[1]).float()
-    ops.ffn_fused(zn, W1, b1, W2, b2, segs, y, pre=pre, res=res, res_hp=res_hp, out_hp=out_hp, hp_row0=hp0 if hp else 0,
+    hsave = torch.full((rows, F), float('nan'), dtype=bf16, device='cuda') if 'pre' in opts else None     # training keeps h too
+    ops.ffn_fused(zn, W1, b1, W2, b2, segs, y, pre=pre, h=hsave, res=res, res_hp=res_hp, out_hp=out_hp, hp_row0=hp0 if hp else 0,
                   dropout=drop, norm=(nout, gain, rstd, 1e-6) if nout is not None else None)
     pre_ref, y_ref = _ffn_ref(zn, W1, b1, W2, b2, segs, res, mask, res_hp, hp0)
     if pre is not None:
         close(pre, pre_ref)
+        close(hsave, torch.nn.functional.gelu(pre_ref))                  # the h tile, stored as the kernel holds it
     assert not torch.isnan(y.float()).any()
     assert ((y.float() - y_ref).abs().max() / y_ref.abs().max()).item() < 1e-2
     if hp:
@@ -432,3 +434,28 @@ def test_wgrad_with_gelu_of_p(B, n_s, n_ns):
     assert ((C1 - ref).abs().max() / ref.abs().max()).item() < 2e-3
     assert ((C2 - ref).abs().max() / ref.abs().max()).item() < 1e-2           # tanh-form GELU + bf16 rounding of h inside the kernel
     assert torch.allclose(cs1, cs2, rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.parametrize('B,n_s,n_ns,F', [(256, 3, 2, 1024), (40, 5, 3, 512), (128, 1, 0, 256), (200, 0, 4, 1024)])
+def test_ffn_fused_backward(B, n_s, n_ns, F):
+    """ot_ffn_bwd: dpre = (dy W2^T) o gelu'(pre) and dzn = dpre W1^T in one kernel against an fp32 reference and the two-GEMM path."""
+    d, G = 256, 1 + 5
+    rows = (n_s + n_ns) * B
+    dy, pre = rnd(rows, d, seed=71), rnd(rows, F, seed=72)
+    W2b, W1b = rnd(G, F, d, scale=0.05, seed=73), rnd(G, d, F, scale=0.05, seed=74)     # master layouts: W2 [F, d], W1 [d, F]
+    segs = ([(0, 1, n_s * B, 0, 0)] if n_s else []) + ([(n_s * B, n_ns, B, 2, 1)] if n_ns else [])
+    dpre = torch.full((rows, F), float('nan'), dtype=bf16, device='cuda')
+    dzn = torch.full((rows, d), float('nan'), dtype=bf16, device='cuda')
+    ops.ffn_fused_bwd(dy, W2b, W1b, pre, segs, dpre, dzn)
+    x = pre.float().requires_grad_(True)
+    torch.nn.functional.gelu(x).sum().backward()
+    dpre_ref = ref_rows_gemm(dy, W2b, segs) * x.grad
+    close(dpre, dpre_ref)
+    dzn_ref = ref_rows_gemm(dpre_ref.to(bf16), W1b, segs)
+    assert not torch.isnan(dzn.float()).any()
+    assert ((dzn.float() - dzn_ref).abs().max() / dzn_ref.abs().max()).item() < 1e-2
+    d2, z2 = torch.empty_like(dpre), torch.empty_like(dzn)
+    ops.mixed_gemm(dy, W2b, segs, d2, flags=OT_EPI_GELU_GRAD, aux=pre)
+    ops.mixed_gemm(d2, W1b, segs, z2)
+    close(dpre, d2.float(), 1e-2)
+    assert ((dzn.float() - z2.float()).abs().max() / dzn_ref.abs().max()).item() < 1e-2
