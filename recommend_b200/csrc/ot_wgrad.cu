@@ -6,7 +6,10 @@
 // (row-major activations); the contraction runs over rows, so both are MN-major UMMA operands:
 // a TMA box of [64 rows x 64 columns] (128-byte swizzle) is one MN-major slab, no transposes anywhere.
 //
-// Work split: one CTA per (output group, 128 x BN tile, row slice).  The row range of an output is cut
+// Work split: one CTA per (output group, MT x BN tile, row slice), MT = 128 or 256 output rows (two TMEM accumulators).  The
+// kernel is bound by L2 -> SM traffic, not by HBM (every CTA of a row slice re-reads the P / Q tiles of the other output tiles:
+// 48 KB per 64 rows and 128 x 256 tile against a 42 B/clk/SM L2 port), so the 256-row tile moves a third fewer bytes per FLOP.
+// One CTA per (output group, MT x BN tile, row slice).  The row range of an output is cut
 // into slices so that the launch fills the device about twice; every CTA keeps its accumulator in
 // TMEM for its whole slice and flushes once with fp32 atomics (the caller zeroes C).
 //   warp 0 lane*: TMA producer     warp 1 lane*: MMA issuer     all 4 warps: epilogue
@@ -58,11 +61,11 @@ __device__ __forceinline__ uint4 gelu_chunk(uint4 q) {
   return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
-template <int BN, int SWB>
+template <int BN, int SWB, int MT = 128>
 struct WgradCfg {
   static constexpr int SLAB_COLS = SWB / 2;                  // columns per MN-major slab
   static constexpr int SLAB_BYTES = WG_KROWS * SWB;          // 64 rows x SWB bytes
-  static constexpr int P_SLABS = 128 / SLAB_COLS;
+  static constexpr int P_SLABS = MT / SLAB_COLS;
   static constexpr int Q_SLABS = BN / SLAB_COLS;
   static constexpr int P_BYTES = P_SLABS * SLAB_BYTES;       // 16 KB
   static constexpr int Q_BYTES = Q_SLABS * SLAB_BYTES;
@@ -70,15 +73,17 @@ struct WgradCfg {
   static constexpr int STAGES_RAW = (227 * 1024 - 256) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256;   // barriers: (3 * STAGES + 1) * 8 + 4 bytes <= 256
-  static constexpr int TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+  static constexpr int ACC_COLS = (MT / 128) * BN;           // one [128 x BN] fp32 accumulator per 128 output rows
+  static constexpr int TMEM_COLS = ACC_COLS <= 32 ? 32 : ACC_COLS <= 64 ? 64 : ACC_COLS <= 128 ? 128 : ACC_COLS <= 256 ? 256 : 512;
 };
 
-template <int BN, int SWB, bool PGELU>
+template <int BN, int SWB, bool PGELU, int MT = 128>
 __global__ void __launch_bounds__(WG_THREADS + (PGELU ? WG_XFORM_THREADS : 0), 1)
 ot_wgrad_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constant__ CUtensorMap tmQ0,
                 const __grid_constant__ CUtensorMap tmP1, const __grid_constant__ CUtensorMap tmQ1,
                 const __grid_constant__ WgradKParams p) {
-  using Cfg = WgradCfg<BN, SWB>;
+  using Cfg = WgradCfg<BN, SWB, MT>;
+  static_assert(!PGELU || MT == 128, "the GELU transform is sized for a 128-column P tile");
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
@@ -151,7 +156,7 @@ ot_wgrad_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constant_
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
 #pragma unroll
           for (int i = 0; i < Cfg::P_SLABS; ++i)
-            tma_load_3d(sp + i * Cfg::SLAB_BYTES, tmP, &full_bar[stage], mt * 128 + i * Cfg::SLAB_COLS, r0, unit);
+            tma_load_3d(sp + i * Cfg::SLAB_BYTES, tmP, &full_bar[stage], mt * MT + i * Cfg::SLAB_COLS, r0, unit);
 #pragma unroll
           for (int i = 0; i < Cfg::Q_SLABS; ++i)
             tma_load_3d(sq + i * Cfg::SLAB_BYTES, tmQ, &full_bar[stage], nt * BN + i * Cfg::SLAB_COLS, r0, unit);
@@ -175,6 +180,14 @@ ot_wgrad_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constant_
           for (int k = 0; k < WG_KROWS / 16; ++k) {
             const uint64_t adv = static_cast<uint64_t>((16 * SWB) >> 4) * k;
             umma_bf16_ss(tmem_base, adesc + adv, bdesc + adv, idesc, (i | k) != 0 ? 1u : 0u);
+          }
+          if (MT == 256) {   // output rows 128..255: the next 128 P columns (slabs 128 / SLAB_COLS onwards), second accumulator
+            const uint64_t adesc2 = make_smem_desc<SWB>(sp + (128 / Cfg::SLAB_COLS) * Cfg::SLAB_BYTES, Cfg::SLAB_BYTES);
+#pragma unroll
+            for (int k = 0; k < WG_KROWS / 16; ++k) {
+              const uint64_t adv = static_cast<uint64_t>((16 * SWB) >> 4) * k;
+              umma_bf16_ss(tmem_base + BN, adesc2 + adv, bdesc + adv, idesc, (i | k) != 0 ? 1u : 0u);
+            }
           }
           umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -248,13 +261,15 @@ ot_wgrad_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constant_
     if (warp < 4) {
     mbar_wait(done_bar, 0);
     tc_fence_after();
-    const int m = mt * 128 + warp * 32 + lane;
+#pragma unroll 1
+    for (int mh = 0; mh < MT / 128; ++mh) {
+    const int m = mt * MT + mh * 128 + warp * 32 + lane;
     float* crow = p.C + (long long)group * p.c_group_stride + (long long)m * p.c_stride_m +
                   (long long)(nt * BN) * p.c_stride_n;
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       uint32_t v[32];
-      tmem_ld_x32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + c * 32, v);
+      tmem_ld_x32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + mh * BN + c * 32, v);
       tmem_ld_wait();
       if (p.vec_flush) {
 #pragma unroll
@@ -268,17 +283,18 @@ ot_wgrad_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constant_
       }
     }
     }
+    }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
-template <int BN, int SWB, bool PGELU = false>
+template <int BN, int SWB, bool PGELU = false, int MT = 128>
 static int launch_wgrad(const CUtensorMap* tm, const WgradKParams& kp, int items, cudaStream_t st) {
-  using Cfg = WgradCfg<BN, SWB>;
+  using Cfg = WgradCfg<BN, SWB, MT>;
   static bool attr_done = false;
-  auto kern = ot_wgrad_kernel<BN, SWB, PGELU>;
+  auto kern = ot_wgrad_kernel<BN, SWB, PGELU, MT>;
   if (!attr_done) {
     OT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_done = true;
@@ -302,7 +318,12 @@ int wgrad_impl(const ot_wgrad_params* p, cudaStream_t st) {
 
   WgradKParams kp;
   memset(&kp, 0, sizeof(kp));
-  kp.Mdim = p->Mdim; kp.Ndim = p->Ndim; kp.m_tiles = p->Mdim / 128; kp.n_tiles = p->Ndim / bn;
+  // 256-row output tiles (two accumulators) where the shape allows: a third less L2 -> SM traffic per FLOP (see the file header);
+  // measured on B200: no gain (dW1 1.83 vs 1.88 ms, the 256 x 256 gradients slower), so the 128-row tile stays the default and
+  // OT_WGRAD_MT=256 selects the wide tile for A/B runs
+  static const int mt_env = [] { const char* e = getenv("OT_WGRAD_MT"); return e ? atoi(e) : 128; }();
+  const int mt = (mt_env == 256 && !p->p_gelu && swb == 128 && bn == 256 && p->Mdim % 256 == 0) ? 256 : 128;
+  kp.Mdim = p->Mdim; kp.Ndim = p->Ndim; kp.m_tiles = p->Mdim / mt; kp.n_tiles = p->Ndim / bn;
   kp.n_segs = p->n_segs; kp.C = p->C;
   kp.c_group_stride = p->c_group_stride; kp.c_stride_m = p->c_stride_m; kp.c_stride_n = p->c_stride_n;
   kp.q_colsum = p->q_colsum; kp.q_colsum_group_stride = p->q_colsum_group_stride;
@@ -362,6 +383,7 @@ int wgrad_impl(const ot_wgrad_params* p, cudaStream_t st) {
     if (swb != 128 || bn != 256) OT_FAIL(OT_ERR_UNSUPPORTED_SHAPE, "ot_wgrad: p_gelu is built for block_n 256 with the 128-byte swizzle (Ndim=%d)", p->Ndim);
     return launch_wgrad<256, 128, true>(tm, kp, items, st);
   }
+  if (mt == 256) return launch_wgrad<256, 128, false, 256>(tm, kp, items, st);
   if (swb == 128) {
     if (bn == 256) return launch_wgrad<256, 128>(tm, kp, items, st);
     if (bn == 128) return launch_wgrad<128, 128>(tm, kp, items, st);
