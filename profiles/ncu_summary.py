@@ -21,7 +21,8 @@ FAMILY = {'ot_mixed_gemm_kernel': 'ot_mixed_gemm', 'ot_ffn_fused_kernel': 'ot_ff
           'rmsnorm_bwd_kernel': 'ot_rmsnorm_bwd'}
 
 rep, out_csv = sys.argv[1], sys.argv[2]
-raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+# `rep` is an .ncu-rep, or the `ncu -i rep --page raw --csv` export of one (reports over 64 MB do not travel back from the GPU box)
+raw = open(rep).read() if rep.endswith('.csv') else subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 hdr, units, data = rows[0], rows[1], rows[2:]
 cols = [m for m in METRICS if m in hdr]

@@ -122,9 +122,11 @@ ot_attn_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   uint32_t kv_uses[2] = {0, 0};
   const int off = p.Lk - p.Lq;
 
-  for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-    const int qt = p.n_qt - 1 - (item % p.n_qt);
-    const int bh = item / p.n_qt;
+  // whole (sample, head) pairs per CTA, query tiles back to back: shared K/V blocks are re-read from L2 (see ot_attn_fwd.cu)
+  for (int kk = 0;; ++kk) {
+    const int bh = blockIdx.x + (kk / p.n_qt) * gridDim.x;
+    if (bh >= p.B * p.H) break;
+    const int qt = p.n_qt - 1 - (kk % p.n_qt);
     const int h = bh % p.H;
     const int b = bh / p.H;
     const int q0 = qt * 128;
@@ -297,9 +299,11 @@ ot_attn_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint32_t q_uses[2] = {0, 0};
   const int off = p.Lk - p.Lq;
 
-  for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-    const int kt = item % p.n_kt;   // early key tiles are seen by the most query tiles -> first
-    const int bh = item / p.n_kt;
+  // whole (sample, head) pairs per CTA, key tiles back to back: the Q / dO tiles they share are re-read from L2
+  for (int kk = 0;; ++kk) {
+    const int bh = blockIdx.x + (kk / p.n_kt) * gridDim.x;
+    if (bh >= p.B * p.H) break;
+    const int kt = kk % p.n_kt;     // early key tiles are seen by the most query tiles -> first
     const int h = bh % p.H;
     const int b = bh / p.H;
     const int k0 = kt * 128;
@@ -427,11 +431,11 @@ static int launch_attn_bwd(const CUtensorMap* tm, AttnBwdKParams kp, cudaStream_
   }
   const int sms = num_sms();
   kp.total_items = kp.n_qt * kp.H * kp.B;
-  int grid = kp.total_items < sms ? kp.total_items : sms;
+  const int n_bh = kp.H * kp.B;
+  int grid = n_bh < sms ? n_bh : sms;
   kdq<<<grid, 256, AttnDqCfg<DH, SWB>::SMEM_BYTES, st>>>(tm[0], tm[1], tm[2], tm[3], kp);
   OT_CUDA_CHECK(cudaGetLastError());
   kp.total_items = kp.n_kt * kp.H * kp.B;
-  grid = kp.total_items < sms ? kp.total_items : sms;
   kdkv<<<grid, 256, AttnDkvCfg<DH, SWB>::SMEM_BYTES, st>>>(tm[0], tm[1], tm[2], tm[3], kp);
   OT_CUDA_CHECK(cudaGetLastError());
   return OT_OK;
