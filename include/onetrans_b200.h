@@ -7,8 +7,9 @@
  * module API (recommend_b200/model.py) binds them with ctypes (INTEGRATION.md shows the stub).
  *
  * Conventions
- *   - every pointer is a DEVICE pointer owned by the caller; the library never allocates or frees
- *     device memory and never synchronises the host;
+ *   - every pointer is a DEVICE pointer owned by the caller; the library never frees caller memory, never synchronises the
+ *     host and allocates no device memory on the hot path (its one allocation: a 4 KB ring of work counters per device
+ *     for the persistent kernels' dynamic tile schedule, made on first use and kept for the life of the process);
  *   - all work is enqueued on `stream` (a cudaStream_t passed as void*);
  *   - activations are bf16, row-major `[rows, cols]` with an element leading dimension (`ld*`);
  *     rows are TOKEN-MAJOR: row = token_position * B + sample  (DESIGN.md §3);

@@ -518,16 +518,19 @@ int attn_bwd_fused_impl(const ot_attn_params* p, cudaStream_t st) {
   kp.lse = p->lse; kp.delta = p->delta;
   kp.dq = (__nv_bfloat16*)p->dq; kp.lddq = p->lddq; kp.dk = (__nv_bfloat16*)p->dk; kp.lddk = p->lddk;
   kp.dv = (__nv_bfloat16*)p->dv; kp.lddv = p->lddv;
+  kp.dbg = 0;
+  kp.dbg_buf = nullptr;
+#ifdef OT_ATTN_BWD_DEBUG   // profiling builds only (-DOT_ATTN_BWD_DEBUG): the product launcher neither allocates nor synchronises
   {
     const char* e = getenv("OT_DEBUG_ATTN_BWD");
     kp.dbg = e ? atoi(e) : 0;
-    kp.dbg_buf = nullptr;
     if (kp.dbg & 2) {
       static unsigned long long* buf = nullptr;
       if (!buf) cudaMalloc(&buf, 64 * sizeof(unsigned long long));
       kp.dbg_buf = buf;
     }
   }
+#endif
 
   static bool attr_done = false;
   if (!attr_done) {
@@ -556,6 +559,7 @@ int attn_bwd_fused_impl(const ot_attn_params* p, cudaStream_t st) {
   const int grid = kp.total_items < sms ? kp.total_items : sms;
   ot_attn_bwd_fused_kernel<<<grid, FB_THREADS, AttnBwdFusedCfg::SMEM_BYTES, st>>>(tm[0], tm[1], tm[2], tm[3], kp);
   OT_CUDA_CHECK(cudaGetLastError());
+#ifdef OT_ATTN_BWD_DEBUG
   if (kp.dbg & 2) {   // debugging aid only: synchronises and prints the element-wise warps' phase timers
     unsigned long long h[64];
     cudaStreamSynchronize(st);
@@ -567,6 +571,7 @@ int attn_bwd_fused_impl(const ot_attn_params* p, cudaStream_t st) {
       fprintf(stderr, "\n");
     }
   }
+#endif
   return OT_OK;
 }
 

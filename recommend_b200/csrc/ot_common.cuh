@@ -371,8 +371,10 @@ __device__ __forceinline__ float ex2_approx(float x) {
 // for 2^f on [-0.5, 0.5] (max relative error 7.5e-5, i.e. 1/50 of a bf16 half-ulp; same bf16 value as the exact exp2 for 99.1 % of
 // inputs), exponent injected by an integer add.  8 FMA/ALU-pipe instructions against one instruction on the 16-lane XU pipe: meant
 // for a FRACTION of the elements of the attention softmax loops, whose element-wise phases are XU-bound (profiles/README.md, known
-// gap 1).  Arguments below -126 give 2^-126 (~1e-38, zero for a softmax).  NOT WIRED INTO ANY KERNEL YET: the constants and the
-// arithmetic are pinned by a bit-level fp32 emulation in tests/test_host.py::test_polynomial_exp2_building_block.
+// gap 1).  Arguments below -126 give 2^-126 (~1e-38, zero for a softmax).  Wired into the attention softmax loops behind the compile-time
+// switch OT_EX2_POLY_MODE (ex2_mixed below; default 0 = MUFU only).  Round-2 measurement: the loops are issue-bound, not XU-bound
+// (XU 29 %), so the extra FMA-pipe instructions make them SLOWER (forward 1.12 -> 1.64 ms with mode 1) - the switch stays off.  The
+// constants and the arithmetic are pinned by a bit-level fp32 emulation in tests/test_host.py::test_polynomial_exp2_building_block.
 #define OT_EX2_POLY_C0 0.9999280571937561f
 #define OT_EX2_POLY_C1 0.6932609677314758f
 #define OT_EX2_POLY_C2 0.2426111251115799f

@@ -213,41 +213,58 @@ __global__ void __launch_bounds__(256)
 ns_tokenizer_fwd_kernel(const float* __restrict__ x, int n_feat, const float* __restrict__ W, const float* __restrict__ bias,
                         __nv_bfloat16* __restrict__ out, long long ldo, long long row0, int B, int L_ns, int d,
                         float* __restrict__ out_hp) {
-  const long long total = (long long)B * L_ns * (d >> 3);
+  // one thread = 8 columns of one token for FOUR consecutive samples: the weight rows (11 x 32 B per thread, the dominant L1/L2
+  // traffic of the round-1 kernel, which re-read them for every sample) are loaded once and reused across the four rows
+  constexpr int RB = 4;
+  const int nch = d >> 3;
+  const int nbg = (B + RB - 1) / RB;
+  const long long total = (long long)nbg * L_ns * nch;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const int nch = d >> 3;
     const int c = (int)(idx % nch);
     const long long t = idx / nch;
-    const int b = (int)(t % B);
-    const int j = (int)(t / B);
+    const int b0 = (int)(t % nbg) * RB;
+    const int j = (int)(t / nbg);
     const long long col = (long long)j * d + c * 8;
-    float acc[8];
+    float acc[RB][8];
     {
-      const float4 b0 = *reinterpret_cast<const float4*>(bias + col), b1 = *reinterpret_cast<const float4*>(bias + col + 4);
-      acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w; acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
+      const float4 bb0 = *reinterpret_cast<const float4*>(bias + col), bb1 = *reinterpret_cast<const float4*>(bias + col + 4);
+#pragma unroll
+      for (int r = 0; r < RB; ++r) {
+        acc[r][0] = bb0.x; acc[r][1] = bb0.y; acc[r][2] = bb0.z; acc[r][3] = bb0.w;
+        acc[r][4] = bb1.x; acc[r][5] = bb1.y; acc[r][6] = bb1.z; acc[r][7] = bb1.w;
+      }
     }
     for (int f = 0; f < n_feat; ++f) {
-      const float xv = x[(long long)b * n_feat + f];
       const float* w = W + (long long)f * L_ns * d + col;
       const float4 w0 = *reinterpret_cast<const float4*>(w), w1 = *reinterpret_cast<const float4*>(w + 4);
-      acc[0] += xv * w0.x; acc[1] += xv * w0.y; acc[2] += xv * w0.z; acc[3] += xv * w0.w;
-      acc[4] += xv * w1.x; acc[5] += xv * w1.y; acc[6] += xv * w1.z; acc[7] += xv * w1.w;
+#pragma unroll
+      for (int r = 0; r < RB; ++r) {
+        const float xv = (b0 + r < B) ? x[(long long)(b0 + r) * n_feat + f] : 0.0f;
+        acc[r][0] += xv * w0.x; acc[r][1] += xv * w0.y; acc[r][2] += xv * w0.z; acc[r][3] += xv * w0.w;
+        acc[r][4] += xv * w1.x; acc[r][5] += xv * w1.y; acc[r][6] += xv * w1.z; acc[r][7] += xv * w1.w;
+      }
     }
-    *reinterpret_cast<uint4*>(out + (row0 + (long long)j * B + b) * ldo + c * 8) = pack8(acc);
-    if (out_hp != nullptr) {
-      float4* hp = reinterpret_cast<float4*>(out_hp + ((long long)j * B + b) * d + c * 8);
-      hp[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-      hp[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+#pragma unroll
+    for (int r = 0; r < RB; ++r) {
+      if (b0 + r >= B) break;
+      *reinterpret_cast<uint4*>(out + (row0 + (long long)j * B + b0 + r) * ldo + c * 8) = pack8(acc[r]);
+      if (out_hp != nullptr) {
+        float4* hp = reinterpret_cast<float4*>(out_hp + ((long long)j * B + b0 + r) * d + c * 8);
+        hp[0] = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+        hp[1] = make_float4(acc[r][4], acc[r][5], acc[r][6], acc[r][7]);
+      }
     }
   }
 }
 
 // dW[f, j*d+n] += sum_b x[b,f] * dout[(row0+j*B+b), n];  dbias[j*d+n] += sum_b dout[...]
-// grid: (ceil(L_ns*d/256), b_splits); each thread owns one column, loops over its slice of b.
+// grid: (ceil(L_ns*d/4/256), b_splits); each thread owns FOUR consecutive columns (8-byte loads) and loops over its slice of b with
+// four rows in flight.  Round 1 gave every thread one column and 256 rows: 2-byte loads in a 256-deep dependent loop, 236 us for
+// 33.5 MB (2 % of HBM, profiles/README.md); the slices are now 32 rows and the launch 512 CTAs.
 __global__ void __launch_bounds__(256)
 ns_tokenizer_bwd_kernel(const float* __restrict__ x, int n_feat, const __nv_bfloat16* __restrict__ dout, long long ldo,
                         long long row0, int B, int L_ns, int d, float* __restrict__ dW, float* __restrict__ dbias) {
-  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  const int col = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   const int b_per = (B + gridDim.y - 1) / gridDim.y;
   const int b_begin = blockIdx.y * b_per;
   const int b_end = min(B, b_begin + b_per);
@@ -255,22 +272,41 @@ ns_tokenizer_bwd_kernel(const float* __restrict__ x, int n_feat, const __nv_bflo
   for (int i = threadIdx.x; i < (b_end - b_begin) * n_feat; i += blockDim.x) s_x[i] = x[(long long)b_begin * n_feat + i];
   __syncthreads();
   if (col >= L_ns * d) return;
-  const int j = col / d, n = col - j * d;
-  float acc[MAX_NS_FEAT + 1];
+  const int j = col / d, n = col - j * d;       // d % 4 == 0: the four columns belong to one token
+  float acc[MAX_NS_FEAT + 1][4];
 #pragma unroll
-  for (int f = 0; f <= MAX_NS_FEAT; ++f) acc[f] = 0.0f;
-  for (int b = b_begin; b < b_end; ++b) {
-    const float g = __bfloat162float(dout[(row0 + (long long)j * B + b) * ldo + n]);
-    const float* xr = s_x + (b - b_begin) * n_feat;
+  for (int f = 0; f <= MAX_NS_FEAT; ++f)
 #pragma unroll
-    for (int f = 0; f < MAX_NS_FEAT; ++f)
-      if (f < n_feat) acc[f] += xr[f] * g;
-    acc[MAX_NS_FEAT] += g;
+    for (int e = 0; e < 4; ++e) acc[f][e] = 0.0f;
+  const __nv_bfloat16* base = dout + (row0 + (long long)j * B) * ldo + n;
+  for (int b0 = b_begin; b0 < b_end; b0 += 4) {
+    uint2 q[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) q[u] = (b0 + u < b_end) ? *reinterpret_cast<const uint2*>(base + (long long)(b0 + u) * ldo) : make_uint2(0u, 0u);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (b0 + u >= b_end) break;
+      const float g[4] = {bf16lo(q[u].x), bf16hi(q[u].x), bf16lo(q[u].y), bf16hi(q[u].y)};
+      const float* xr = s_x + (b0 + u - b_begin) * n_feat;
+#pragma unroll
+      for (int f = 0; f < MAX_NS_FEAT; ++f)
+        if (f < n_feat) {
+          const float xv = xr[f];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) acc[f][e] += xv * g[e];
+        }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[MAX_NS_FEAT][e] += g[e];
+    }
   }
 #pragma unroll
   for (int f = 0; f < MAX_NS_FEAT; ++f)
-    if (f < n_feat) atomicAdd(&dW[(long long)f * L_ns * d + col], acc[f]);
-  atomicAdd(&dbias[col], acc[MAX_NS_FEAT]);
+    if (f < n_feat) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) atomicAdd(&dW[(long long)f * L_ns * d + col + e], acc[f][e]);
+    }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) atomicAdd(&dbias[col + e], acc[MAX_NS_FEAT][e]);
 }
 
 // rows [row0, row0+n_rows) <- bf16(vec[d])   ([SEP] rows)
@@ -403,7 +439,7 @@ int rmsnorm_bwd_impl(const ot_rmsnorm_params* p, cudaStream_t st) {
 int ns_tokenizer_fwd_impl(const ot_ns_tokenizer_params* p, cudaStream_t st) {
   if (!p || !p->x || !p->W || !p->bias || !p->out) OT_FAIL(OT_ERR_INVALID_ARG, "ot_ns_tokenizer_fwd: null pointer");
   if (p->d % 8 || p->n_feat <= 0 || p->n_feat > MAX_NS_FEAT || (p->ldo % 8)) OT_FAIL(OT_ERR_UNSUPPORTED_SHAPE, "ot_ns_tokenizer_fwd: d=%d n_feat=%d", p->d, p->n_feat);
-  const long long total = (long long)p->B * p->L_ns * (p->d / 8);
+  const long long total = (long long)((p->B + 3) / 4) * p->L_ns * (p->d / 8);
   long long blocks = (total + 255) / 256;
   if (blocks > (long long)num_sms() * 32) blocks = (long long)num_sms() * 32;
   ns_tokenizer_fwd_kernel<<<(int)blocks, 256, 0, st>>>(p->x, p->n_feat, p->W, p->bias, (__nv_bfloat16*)p->out, p->ldo, p->row0, p->B, p->L_ns, p->d, p->out_hp);
@@ -415,10 +451,12 @@ int ns_tokenizer_bwd_impl(const ot_ns_tokenizer_params* p, cudaStream_t st) {
   if (!p || !p->x || !p->dout || !p->dW || !p->dbias) OT_FAIL(OT_ERR_INVALID_ARG, "ot_ns_tokenizer_bwd: null pointer");
   if (p->n_feat <= 0 || p->n_feat > MAX_NS_FEAT) OT_FAIL(OT_ERR_UNSUPPORTED_SHAPE, "ot_ns_tokenizer_bwd: n_feat=%d", p->n_feat);
   const int cols = p->L_ns * p->d;
-  int b_splits = (p->B + 255) / 256;
+  if (p->d % 4 || p->ldo % 4) OT_FAIL(OT_ERR_UNSUPPORTED_SHAPE, "ot_ns_tokenizer_bwd: d=%d ldo=%lld must be multiples of 4", p->d, (long long)p->ldo);
+  int b_splits = (p->B + 31) / 32;
   if (b_splits < 1) b_splits = 1;
+  if (b_splits > 65535) b_splits = 65535;
   const int b_per = (p->B + b_splits - 1) / b_splits;
-  dim3 grid((cols + 255) / 256, b_splits);
+  dim3 grid((cols / 4 + 255) / 256, b_splits);
   ns_tokenizer_bwd_kernel<<<grid, 256, (size_t)b_per * p->n_feat * sizeof(float), st>>>(p->x, p->n_feat, (const __nv_bfloat16*)p->dout, p->ldo, p->row0,
                                                                                        p->B, p->L_ns, p->d, p->dW, p->dbias);
   OT_CUDA_CHECK(cudaGetLastError());
