@@ -42,6 +42,9 @@ static constexpr int F2_SMEM_BYTES = F2_OFF_BARS + 512;
 static_assert(F2_SMEM_BYTES <= 227 * 1024, "shared memory budget");
 static constexpr uint32_t F2_T_S = 0, F2_T_O = 256;      // + tile * 128 / + tile * 64
 static constexpr float F2_TAU = 8.0f;                    // lazy rescale threshold, log2 units
+#ifndef OT_V2_ABLATE
+#define OT_V2_ABLATE 0     // timing experiments only (profiles/README.md): 1 no exponentials, 2 no maximum pass, 3 no P stores, 4 neither exp nor sums
+#endif
 
 struct __align__(16) F2StepInfo {
   int q0, j, b, h;       // q0 = first query row of tile A
@@ -256,6 +259,10 @@ ot_attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 #pragma unroll
         for (int c = 0; c < 4; ++c) vis[c] = (lim_lo + 31 < c * 32) ? 0 : (lim_lo >= c * 32 + 31) ? 2 : 1;
         float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#if OT_V2_ABLATE == 2
+        mx4[0] = 8.0f;
+        if (false)
+#endif
         {
           uint32_t va[32], vb[32];
           tmem_ld_x32(t_s, va);                                     // chunk 0 always holds key 0 .. visible to someone
@@ -327,26 +334,33 @@ ot_attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
             if (vis[c] == 0) {
 #pragma unroll
               for (int i = 0; i < 16; ++i) pk[i] = 0u;
-            } else if (vis[c] == 2) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const float e0 = ex2_mixed(fmaf(__uint_as_float(v[2 * i]), p.scale_log2, -mb), 2 * i);
-                const float e1 = ex2_mixed(fmaf(__uint_as_float(v[2 * i + 1]), p.scale_log2, -mb), 2 * i + 1);
-                rs4[i & 3] += e0 + e1;
-                pk[i] = pack_bf16x2(e0, e1);
-              }
             } else {
+              // Three phases over the chunk's 32 values - arguments, exponentials, sums / packs - instead of one fused loop: with two
+              // softmax warps per scheduler nothing hides the MUFU latency (~20 clk) if a result is consumed two instructions after
+              // it was issued, which is how ptxas scheduled the fused form (ncu: the hot stall was `wait` on the MUFU line).
+              float e[32];
+#pragma unroll
+              for (int i = 0; i < 32; ++i) e[i] = fmaf(__uint_as_float(v[i]), p.scale_log2, -mb);
+#if OT_V2_ABLATE != 1 && OT_V2_ABLATE != 4
+#pragma unroll
+              for (int i = 0; i < 32; ++i) e[i] = ex2_mixed(e[i], i);
+#endif
+              if (vis[c] == 1) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) e[i] = (c * 32 + i <= lim) ? e[i] : 0.0f;
+              }
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
-                float e0 = ex2_mixed(fmaf(__uint_as_float(v[2 * i]), p.scale_log2, -mb), 2 * i);
-                float e1 = ex2_mixed(fmaf(__uint_as_float(v[2 * i + 1]), p.scale_log2, -mb), 2 * i + 1);
-                e0 = (c * 32 + 2 * i <= lim) ? e0 : 0.0f;
-                e1 = (c * 32 + 2 * i + 1 <= lim) ? e1 : 0.0f;
-                rs4[i & 3] += e0 + e1;
-                pk[i] = pack_bf16x2(e0, e1);
+#if OT_V2_ABLATE != 4
+                rs4[i & 3] += e[2 * i] + e[2 * i + 1];
+#endif
+                pk[i] = pack_bf16x2(e[2 * i], e[2 * i + 1]);
               }
             }
             uint8_t* slab = myP + (c >> 1) * PT_SLAB_BYTES;
+#if OT_V2_ABLATE == 3
+            if (pk[0] == 0x12345678u)
+#endif
 #pragma unroll
             for (int ch = 0; ch < 4; ++ch)
               *reinterpret_cast<uint4*>(slab + swz_off<128>(row, (c & 1) * 4 + ch)) =
