@@ -266,6 +266,7 @@ int make_head_tmap(CUtensorMap* tm, const void* base, int cols, int B, int L, lo
 
 int attn_fwd_ws_impl(const ot_attn_params* p, cudaStream_t st);   // ot_attn_fwd_ws.cu (head_dim 64, round-1 structure)
 int attn_fwd_v2_impl(const ot_attn_params* p, cudaStream_t st);   // ot_attn_fwd_v2.cu (head_dim 64, round-2 structure)
+int attn_fwd_v3_impl(const ot_attn_params* p, cudaStream_t st);   // ot_attn_fwd_v3.cu (head_dim 64, P in tensor memory)
 
 int attn_fwd_impl(const ot_attn_params* p, cudaStream_t st) {
   if (!p || !p->q || !p->k || !p->v || !p->o || !p->lse) OT_FAIL(OT_ERR_INVALID_ARG, "ot_attn_fwd: null pointer");
@@ -275,12 +276,12 @@ int attn_fwd_impl(const ot_attn_params* p, cudaStream_t st) {
   if ((p->ldq % 8) || (p->ldk % 8) || (p->ldv % 8) || (p->ldo % 8)) OT_FAIL(OT_ERR_UNSUPPORTED_SHAPE, "ot_attn_fwd: leading dimensions must be multiples of 8");
   const int swb = (p->head_dim == 64 && p->swizzle != 64) ? 128 : 64;
   if (p->head_dim == 64 && swb == 128 && p->swizzle != 128) {   // swizzle=128 forces the simple kernel
-    // OT_ATTN_FWD_V2=0 keeps the round-1 warp-specialised kernel for A/B runs (read once)
-    // Measured on B200 (profiles/README.md, round 2): the two structures are within 10 % of each other; v2 (one thread per row,
-    // two tiles in lockstep) wins when a (sample, head) has at least two query tiles, the 16-warp round-1 kernel on short tails.
-    static const int v2 = [] { const char* e = getenv("OT_ATTN_FWD_V2"); return e ? atoi(e) : -1; }();     // 0 / 1 force, unset = by shape
-    const bool use_v2 = v2 < 0 ? (p->Lq > 128) : (v2 != 0);
-    return use_v2 ? attn_fwd_v2_impl(p, st) : attn_fwd_ws_impl(p, st);
+    // OT_ATTN_FWD_IMPL (read once) forces one structure for A/B runs: 1 = round-1 warp-specialised kernel, 2 = v2 (P through shared
+    // memory), 3 = v3 (P in tensor memory, TS-form P V).  Unset: v3.
+    static const int impl = [] { const char* e = getenv("OT_ATTN_FWD_IMPL"); return e ? atoi(e) : 0; }();
+    if (impl == 1) return attn_fwd_ws_impl(p, st);
+    if (impl == 2) return attn_fwd_v2_impl(p, st);
+    return attn_fwd_v3_impl(p, st);
   }
   const int cols = p->H * p->head_dim;
   CUtensorMap tq, tk, tv;
