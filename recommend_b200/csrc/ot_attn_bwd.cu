@@ -12,6 +12,7 @@
 //
 // 256 threads: thread (r, half) owns row r of the tile and half of its 128 score columns; the row
 // statistics (lse, delta) are inputs, so no cross-thread reduction is needed.
+#include <stdlib.h>
 #include "ot_attn.cuh"
 #include "ot_host.h"
 #include "../../include/onetrans_b200.h"
@@ -442,6 +443,7 @@ static int launch_attn_bwd(const CUtensorMap* tm, AttnBwdKParams kp, cudaStream_
 }
 
 int attn_bwd_fused_impl(const ot_attn_params* p, cudaStream_t st);   // ot_attn_bwd_fused.cu (head_dim 64)
+int attn_bwd_v2_impl(const ot_attn_params* p, cudaStream_t st);      // ot_attn_bwd_v2.cu (head_dim 64, key-major, P^T / dS^T in tensor memory)
 
 int attn_bwd_impl(const ot_attn_params* p, cudaStream_t st) {
   if (!p || !p->q || !p->k || !p->v || !p->o || !p->lse || !p->d_o || !p->dq || !p->dk || !p->dv || !p->delta)
@@ -452,7 +454,12 @@ int attn_bwd_impl(const ot_attn_params* p, cudaStream_t st) {
   if ((p->ldq % 8) || (p->ldk % 8) || (p->ldv % 8) || (p->ldo % 8) || (p->lddo % 8) || (p->lddq % 8) || (p->lddk % 8) || (p->lddv % 8))
     OT_FAIL(OT_ERR_UNSUPPORTED_SHAPE, "ot_attn_bwd: leading dimensions must be multiples of 8");
   const int swb = (p->head_dim == 64 && p->swizzle != 64) ? 128 : 64;
-  if (p->head_dim == 64 && swb == 128 && p->swizzle != 128) return attn_bwd_fused_impl(p, st);   // swizzle=128 forces the two-kernel path
+  if (p->head_dim == 64 && swb == 128 && p->swizzle != 128) {   // swizzle=128 forces the two-kernel path
+    // OT_ATTN_BWD_IMPL (read once) forces one structure for A/B runs: 1 = round-1 query-major kernel (P, dS through shared memory),
+    // 2 = key-major kernel with P^T / dS^T in tensor memory.  Unset: 2.
+    static const int impl = [] { const char* e = getenv("OT_ATTN_BWD_IMPL"); return e ? atoi(e) : 0; }();
+    return impl == 1 ? attn_bwd_fused_impl(p, st) : attn_bwd_v2_impl(p, st);
+  }
   const int cols = p->H * p->head_dim;
   CUtensorMap tm[4];
   int rc;

@@ -499,6 +499,30 @@ attn_delta_kernel(const __nv_bfloat16* __restrict__ o, long long ldo, const __nv
 
 int make_head_tmap(CUtensorMap* tm, const void* base, int cols, int B, int L, long long ld, int swb);
 
+// Shared by the head_dim-64 backward kernels: zero dQ (it is accumulated with reductions) and delta = rowsum(dO o O).
+int attn_bwd_prologue(const ot_attn_params* p, cudaStream_t st) {
+  const int cols = p->H * p->head_dim;
+  // dQ is accumulated with reductions: zero the [Lq*B, H*dh] block it covers (row by row when strided)
+  if (p->lddq == cols) {
+    OT_CUDA_CHECK(cudaMemsetAsync(p->dq, 0, (size_t)p->Lq * p->B * cols * 2, st));
+  } else {
+    OT_CUDA_CHECK(cudaMemset2DAsync(p->dq, (size_t)p->lddq * 2, 0, (size_t)cols * 2, (size_t)p->Lq * p->B, st));
+  }
+  {
+    const int lph = p->head_dim / 8;
+    const long long total = (long long)p->Lq * p->B * p->H * lph;
+    long long blocks = (total + 255) / 256;
+    if (blocks > (long long)num_sms() * 32) blocks = (long long)num_sms() * 32;
+#define OT_LAUNCH_DELTA(N) attn_delta_kernel<N><<<(int)blocks, 256, 0, st>>>((const __nv_bfloat16*)p->o, p->ldo, (const __nv_bfloat16*)p->d_o, \
+                                                                             p->lddo, p->delta, p->B, p->H, p->Lq)
+    if (lph == 8) OT_LAUNCH_DELTA(8); else if (lph == 4) OT_LAUNCH_DELTA(4); else if (lph == 16) OT_LAUNCH_DELTA(16);
+    else OT_FAIL(OT_ERR_UNSUPPORTED_SHAPE, "ot_attn_bwd: head_dim=%d", p->head_dim);
+#undef OT_LAUNCH_DELTA
+    OT_CUDA_CHECK(cudaGetLastError());
+  }
+  return OT_OK;
+}
+
 int attn_bwd_fused_impl(const ot_attn_params* p, cudaStream_t st) {
   const int cols = p->H * p->head_dim;
   CUtensorMap tm[4];
@@ -537,24 +561,7 @@ int attn_bwd_fused_impl(const ot_attn_params* p, cudaStream_t st) {
     OT_CUDA_CHECK(cudaFuncSetAttribute(ot_attn_bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnBwdFusedCfg::SMEM_BYTES));
     attr_done = true;
   }
-  // dQ is accumulated with reductions: zero the [Lq*B, H*dh] block it covers (row by row when strided)
-  if (p->lddq == cols) {
-    OT_CUDA_CHECK(cudaMemsetAsync(p->dq, 0, (size_t)p->Lq * p->B * cols * 2, st));
-  } else {
-    OT_CUDA_CHECK(cudaMemset2DAsync(p->dq, (size_t)p->lddq * 2, 0, (size_t)cols * 2, (size_t)p->Lq * p->B, st));
-  }
-  {
-    const int lph = p->head_dim / 8;
-    const long long total = (long long)p->Lq * p->B * p->H * lph;
-    long long blocks = (total + 255) / 256;
-    if (blocks > (long long)num_sms() * 32) blocks = (long long)num_sms() * 32;
-#define OT_LAUNCH_DELTA(N) attn_delta_kernel<N><<<(int)blocks, 256, 0, st>>>((const __nv_bfloat16*)p->o, p->ldo, (const __nv_bfloat16*)p->d_o, \
-                                                                             p->lddo, p->delta, p->B, p->H, p->Lq)
-    if (lph == 8) OT_LAUNCH_DELTA(8); else if (lph == 4) OT_LAUNCH_DELTA(4); else if (lph == 16) OT_LAUNCH_DELTA(16);
-    else OT_FAIL(OT_ERR_UNSUPPORTED_SHAPE, "ot_attn_bwd: head_dim=%d", p->head_dim);
-#undef OT_LAUNCH_DELTA
-    OT_CUDA_CHECK(cudaGetLastError());
-  }
+  if ((rc = attn_bwd_prologue(p, st))) return rc;
   const int sms = num_sms();
   const int grid = kp.total_items < sms ? kp.total_items : sms;
   ot_attn_bwd_fused_kernel<<<grid, FB_THREADS, AttnBwdFusedCfg::SMEM_BYTES, st>>>(tm[0], tm[1], tm[2], tm[3], kp);
