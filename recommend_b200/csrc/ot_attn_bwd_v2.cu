@@ -16,6 +16,7 @@
 // Warps: 0 loader (TMA + step ring), 1 MMA issuer, 2-3 row statistics (lse * log2 e, delta -> shared memory), 4-11 element-wise
 // (thread = one key row x 32 query columns of a half), 12-15 output (dQ by TMA reduce-add, dK / dV by TMA store).
 // TMEM: S^T halves 0 / 64, dP^T halves 128 / 192, dV 256, dK 320, dQ 384.
+#include <stdlib.h>
 #include <string.h>
 #include "ot_attn.cuh"
 #include "ot_host.h"
@@ -31,8 +32,11 @@ struct AttnBwdV2KParams {
   int* sched;          // dynamic work counter (zeroed by the launcher) or NULL = static round-robin
 };
 
-static constexpr int B2_THREADS = 512;
-static constexpr int B2_CTRL_REGS = 56, B2_OUT_REGS = 88, B2_EW_REGS = 184;   // 128 x (128-56) + 128 x (128-88) released = 256 x (184-128) taken
+// NCG = column groups per 64-query half = element-wise warps per TMEM lane quarter (2: thread = key row x 32 queries, 8 warps;
+// 4: thread = key row x 16 queries, 16 warps = four per scheduler, which hides the MUFU / FMA latencies the two-warp form exposed).
+template <int NCG> struct B2Cfg;
+template <> struct B2Cfg<2> { static constexpr int THREADS = 512, CTRL_REGS = 56, OUT_REGS = 88, EW_REGS = 184; };   // 128 regs at launch: 128*72 + 128*40 released = 256*56 taken
+template <> struct B2Cfg<4> { static constexpr int THREADS = 768, CTRL_REGS = 40, OUT_REGS = 88, EW_REGS = 88; };    //  80 regs at launch: 128*40 released = 128*8 + 512*8 taken
 static constexpr int B2_DH = 64;
 static constexpr int B2_TILE = 128 * B2_DH * 2;        // 16 KB
 static constexpr int B2_Q_STAGES = 3;
@@ -48,20 +52,24 @@ static constexpr int B2_OFF_INFO = B2_OFF_STATS + B2_Q_STAGES * 2 * 128 * 4;
 static constexpr int B2_OFF_BARS = B2_OFF_INFO + B2_INFO_SLOTS * 16;
 static constexpr int B2_SMEM_BYTES = B2_OFF_BARS + 512;
 static_assert(B2_SMEM_BYTES <= 227 * 1024, "shared memory budget");
-static constexpr uint32_t B2_T_S = 0, B2_T_DP = 128, B2_T_DV = 256, B2_T_DK = 320, B2_T_DQ = 384;
+static constexpr uint32_t B2_T_S = 0, B2_T_DP = 128, B2_T_DV = 256, B2_T_DK = 320, B2_T_DQ = 384, B2_T_K = 448, B2_T_V = 480;
+#ifndef OT_B2_KV_TMEM
+#define OT_B2_KV_TMEM 1     // 1: K_j / V_j are copied to tensor memory once per item (tcgen05.cp) and S^T / dP^T run in TS form; 0: SS form
+#endif
 enum : uint32_t {
   BB_KV = 0,         // [2] K_j, V_j landed                                  (loader -> MMA)
   BB_KVFREE = 16,    // [2] every product of the item is complete            (MMA commit -> loader)
   BB_Q = 32,         // [3] Q_i, dO_i landed and row statistics written      (loader + 2 statistics warps -> MMA, element-wise)
   BB_QFREE = 56,     // [3] dV / dK products of the step's second half done  (MMA commit -> loader)
   BB_S = 80,         // [2] S^T, dP^T of a half complete                     (MMA commit -> element-wise)
-  BB_PDS = 96,       // [2] P^T, dS^T of a half written                      (8 arrivals -> MMA)
+  BB_PDS = 96,       // [2] P^T, dS^T of a half written to TENSOR memory     (4 NCG arrivals -> MMA: dV / dK products may go)
+  BB_PDSS = 280,     // [2] dS^T of a half written to SHARED memory          (4 NCG arrivals -> MMA: dQ product may go)
   BB_DQ = 112,       //     dQ of the step complete                          (MMA commit -> output, element-wise)
   BB_DQFREE = 120,   //     dQ pulled out of TMEM                            (4 arrivals -> MMA)
   BB_ACC = 128,      //     dV, dK of the item complete                      (MMA commit -> output)
   BB_ACCFREE = 136,  //     dV, dK pulled out of TMEM                        (4 arrivals -> MMA)
   BB_IFULL = 144,    // [8] step info published                              (loader -> everybody)
-  BB_IFREE = 208,    // [8] step info read: MMA 1 + statistics 2 + element-wise 8 + output 4 = 15 arrivals -> loader
+  BB_IFREE = 208,    // [8] step info read: MMA 1 + statistics 2 + element-wise 4 NCG + output 4 arrivals -> loader
   BB_TMEM = 272
 };
 enum { SB_FIRST = 1, SB_LAST = 2, SB_END = 4, SB_KVBUF = 8 };
@@ -84,6 +92,10 @@ __device__ __forceinline__ void b2_wait(uint32_t bar, uint32_t parity) {
 }
 __device__ __forceinline__ void b2_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// shared memory -> tensor memory, 128 lanes x 32 bytes (one K = 16 step of a K-major bf16 operand); executes in issue order with the MMAs
+__device__ __forceinline__ void b2_tmem_cp_128x256b(uint32_t taddr, uint64_t sdesc) {
+  asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(taddr), "l"(sdesc) : "memory");
 }
 __device__ __forceinline__ void b2_tma_store(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
@@ -132,13 +144,17 @@ struct B2Cursor {
   __device__ __forceinline__ int q0() const { return (i_min + ii) * 128; }
 };
 
-__global__ void __launch_bounds__(B2_THREADS, 1)
+template <int NCG>
+__global__ void __launch_bounds__(B2Cfg<NCG>::THREADS, 1)
 ot_attn_bwd_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                       const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
                       const __grid_constant__ CUtensorMap tmdQ, const __grid_constant__ CUtensorMap tmdK,
                       const __grid_constant__ CUtensorMap tmdV, const __grid_constant__ AttnBwdV2KParams p) {
   constexpr int DH = B2_DH;
   constexpr int SWB = 128;
+  using Cfg = B2Cfg<NCG>;
+  constexpr int CW = 64 / NCG;                  // query columns per element-wise thread and half
+  constexpr int N_EW = 4 * NCG;                 // element-wise warps
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bars = sbase + B2_OFF_BARS;
@@ -153,8 +169,8 @@ ot_attn_bwd_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     auto init = [&](uint32_t off, int n, uint32_t count) {
       for (int i = 0; i < n; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bars + off + 8 * i), "r"(count));
     };
-    init(BB_KV, 2, 1); init(BB_KVFREE, 2, 1); init(BB_Q, 3, 3); init(BB_QFREE, 3, 1); init(BB_S, 2, 1); init(BB_PDS, 2, 8);
-    init(BB_DQ, 1, 1); init(BB_DQFREE, 1, 4); init(BB_ACC, 1, 1); init(BB_ACCFREE, 1, 4); init(BB_IFULL, 8, 1); init(BB_IFREE, 8, 15);
+    init(BB_KV, 2, 1); init(BB_KVFREE, 2, 1); init(BB_Q, 3, 3); init(BB_QFREE, 3, 1); init(BB_S, 2, 1); init(BB_PDS, 2, N_EW); init(BB_PDSS, 2, N_EW);
+    init(BB_DQ, 1, 1); init(BB_DQFREE, 1, 4); init(BB_ACC, 1, 1); init(BB_ACCFREE, 1, 4); init(BB_IFULL, 8, 1); init(BB_IFREE, 8, 7 + N_EW);
     fence_mbar_init();
   }
   if (warp == 1) { tmem_alloc(reinterpret_cast<uint32_t*>(smem + B2_OFF_BARS + BB_TMEM), 512); tmem_relinquish(); }
@@ -165,7 +181,7 @@ ot_attn_bwd_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   const int off = p.Lk - p.Lq;
 
   if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(B2_CTRL_REGS));
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(Cfg::CTRL_REGS));
     if (warp == 0) {
       // ============================== loader: step ring + TMA ==============================
       if (elect_one()) {
@@ -231,10 +247,24 @@ ot_attn_bwd_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           const uint64_t aK = tileK + addr14(sbase + B2_OFF_K + kb * B2_TILE), aV = tileK + addr14(sbase + B2_OFF_V + kb * B2_TILE);
           const uint64_t bQ = tileK + addr14(sbase + B2_OFF_Q + st * B2_TILE + hh * 8192);
           const uint64_t bdO = tileK + addr14(sbase + B2_OFF_DO + st * B2_TILE + hh * 8192);
+#if OT_B2_KV_TMEM
+          if (hh == 0 && (flags & SB_FIRST)) {      // new item: K_j, V_j into tensor memory behind the previous item's last S^T / dP^T products
+#pragma unroll
+            for (int kk = 0; kk < DH / 16; ++kk) {
+              b2_tmem_cp_128x256b(tmem_base + B2_T_K + 8 * kk, aK + 2 * kk);
+              b2_tmem_cp_128x256b(tmem_base + B2_T_V + 8 * kk, aV + 2 * kk);
+            }
+          }
+#pragma unroll
+          for (int kk = 0; kk < DH / 16; ++kk) umma_bf16_ts(tmem_base + B2_T_S + hh * 64, tmem_base + B2_T_K + 8 * kk, bQ + 2 * kk, idesc_sdp, kk != 0);
+#pragma unroll
+          for (int kk = 0; kk < DH / 16; ++kk) umma_bf16_ts(tmem_base + B2_T_DP + hh * 64, tmem_base + B2_T_V + 8 * kk, bdO + 2 * kk, idesc_sdp, kk != 0);
+#else
 #pragma unroll
           for (int kk = 0; kk < DH / 16; ++kk) umma_bf16_ss(tmem_base + B2_T_S + hh * 64, aK + 2 * kk, bQ + 2 * kk, idesc_sdp, kk != 0);
 #pragma unroll
           for (int kk = 0; kk < DH / 16; ++kk) umma_bf16_ss(tmem_base + B2_T_DP + hh * 64, aV + 2 * kk, bdO + 2 * kk, idesc_sdp, kk != 0);
+#endif
           b2_commit(bars + BB_S + 8 * hh);
         };
         auto issue_main = [&](const int4& si, int hh, uint32_t g) {   // dV += P^T dO, dK += dS^T Q over the 64 queries of half hh
@@ -248,14 +278,15 @@ ot_attn_bwd_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           const uint32_t fresh = (hh == 0 && (flags & SB_FIRST)) ? 1u : 0u;
           const uint64_t mdO = tileMN + addr14(sbase + B2_OFF_DO + st * B2_TILE + hh * 8192);
           const uint64_t mQ = tileMN + addr14(sbase + B2_OFF_Q + st * B2_TILE + hh * 8192);
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk)   // 16 queries per K step: columns 32 * (kk / 2) + 8 * (kk % 2) .. + 7 of the half's buffer
-            umma_bf16_ts(tmem_base + B2_T_DV, tmem_base + B2_T_S + hh * 64 + 32 * (kk >> 1) + 8 * (kk & 1), mdO + 128 * kk, idesc_ts,
-                         (fresh && kk == 0) ? 0u : 1u);
+          // 16 queries per K step; a thread's CW columns hold their CW / 2 packed columns at the start of its own column range
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
-            umma_bf16_ts(tmem_base + B2_T_DK, tmem_base + B2_T_DP + hh * 64 + 32 * (kk >> 1) + 8 * (kk & 1), mQ + 128 * kk, idesc_ts,
-                         (fresh && kk == 0) ? 0u : 1u);
+            umma_bf16_ts(tmem_base + B2_T_DV, tmem_base + B2_T_S + hh * 64 + CW * ((16 * kk) / CW) + 8 * (((16 * kk) % CW) / 16), mdO + 128 * kk,
+                         idesc_ts, (fresh && kk == 0) ? 0u : 1u);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            umma_bf16_ts(tmem_base + B2_T_DK, tmem_base + B2_T_DP + hh * 64 + CW * ((16 * kk) / CW) + 8 * (((16 * kk) % CW) / 16), mQ + 128 * kk,
+                         idesc_ts, (fresh && kk == 0) ? 0u : 1u);
         };
         uint32_t g = 0;
         int4 cur = fetch(0);
@@ -275,6 +306,8 @@ ot_attn_bwd_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           b2_commit(bars + BB_QFREE + 8 * st);        // Q_i / dO_i (and the statistics of the step) are no longer needed
           if (!end) issue_sdp(nxt, 1);
           // dQ_i = dS K_j over the whole query tile (both halves of dS^T are in shared memory)
+          b2_wait(bars + BB_PDSS, g & 1);
+          b2_wait(bars + BB_PDSS + 8, g & 1);
           if (g > 0) b2_wait(bars + BB_DQFREE, (g - 1) & 1);
           tc_fence_after();
           {
@@ -318,9 +351,9 @@ ot_attn_bwd_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         ++g;
       }
     }
-  } else if (warp < 12) {
-    // ============================== element-wise warps (4-11): thread = key row x 32 query columns of a half ==============================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(B2_EW_REGS));
+  } else if (warp < 4 + N_EW) {
+    // ============================== element-wise warps: thread = key row x CW query columns of a half ==============================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(Cfg::EW_REGS));
     const int ew = warp - 4;
     const int cg = ew >> 2;                            // column group inside the 64-query half
     const int wrow = (ew & 3) * 32;                    // first key row of this warp == first TMEM lane
@@ -341,27 +374,32 @@ ot_attn_bwd_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       const float* sl = reinterpret_cast<const float*>(smem + B2_OFF_STATS + st * 1024);
 #pragma unroll 1
       for (int hh = 0; hh < 2; ++hh) {
-        // column c (0..31) of this thread is query q0 + 64 hh + 32 cg + c; key k0 + row sees it iff c >= cmin
-        const int cmin_lo = k0 + wrow - off - q0 - 64 * hh - 32 * cg;      // lane 0 (lane 31: + 31)
+        // column c (0 .. CW-1) of this thread is query q0 + 64 hh + CW cg + c; key k0 + row sees it iff c >= cmin
+        const int cmin_lo = k0 + wrow - off - q0 - 64 * hh - CW * cg;      // lane 0 (lane 31: + 31)
         const int cmin = cmin_lo + lane;
-        const bool none = cmin_lo >= 32;                                   // the whole 32 x 32 block is hidden
+        const bool none = cmin_lo >= CW;                                   // the whole 32 x CW block is hidden
         const bool fast = cmin_lo + 31 <= 0;                               // entirely visible
-        const uint32_t t_s = t_lane + B2_T_S + hh * 64 + cg * 32, t_dp = t_lane + B2_T_DP + hh * 64 + cg * 32;
-        uint32_t pk[16], dk[16];
+        const uint32_t t_s = t_lane + B2_T_S + hh * 64 + cg * CW, t_dp = t_lane + B2_T_DP + hh * 64 + cg * CW;
+        uint32_t pk[CW / 2], dk[CW / 2];
         b2_wait(bars + BB_S + 8 * hh, g & 1);
         tc_fence_after();
         if (none) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) { pk[i] = 0u; dk[i] = 0u; }
+          for (int i = 0; i < CW / 2; ++i) { pk[i] = 0u; dk[i] = 0u; }
         } else {
-          uint32_t vs[32], vd[32];
-          tmem_ld_x32(t_s, vs);
-          tmem_ld_x32(t_dp, vd);
+          uint32_t vs[CW], vd[CW];
+          if (CW == 32) {
+            tmem_ld_x32(t_s, reinterpret_cast<uint32_t (&)[32]>(vs));
+            tmem_ld_x32(t_dp, reinterpret_cast<uint32_t (&)[32]>(vd));
+          } else {
+            tmem_ld_x16(t_s, reinterpret_cast<uint32_t (&)[16]>(vs));
+            tmem_ld_x16(t_dp, reinterpret_cast<uint32_t (&)[16]>(vd));
+          }
           tmem_ld_wait();
-          const float4* l4 = reinterpret_cast<const float4*>(sl + hh * 64 + cg * 32);
-          const float4* d4 = reinterpret_cast<const float4*>(sl + 128 + hh * 64 + cg * 32);
+          const float4* l4 = reinterpret_cast<const float4*>(sl + hh * 64 + cg * CW);
+          const float4* d4 = reinterpret_cast<const float4*>(sl + 128 + hh * 64 + cg * CW);
 #pragma unroll
-          for (int c4 = 0; c4 < 8; ++c4) {
+          for (int c4 = 0; c4 < CW / 4; ++c4) {
             const float4 ls = l4[c4];
             const float4 dl = d4[c4];
             float p0 = ex2_approx(fmaf(__uint_as_float(vs[4 * c4 + 0]), p.scale_log2, -ls.x));
@@ -384,31 +422,40 @@ ot_attn_bwd_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
             dk[2 * c4 + 1] = pack_bf16x2(s2, s3);
           }
         }
-        // P^T / dS^T replace the first 16 of this thread's own 32 S^T / dP^T columns (read out above); dS^T also goes to shared memory
-        tmem_st_x16(t_s, pk);
-        tmem_st_x16(t_dp, dk);
+        // P^T / dS^T replace the first CW / 2 of this thread's own CW S^T / dP^T columns (read out above): the dV / dK products may go
+        if (CW == 32) {
+          tmem_st_x16(t_s, reinterpret_cast<uint32_t (&)[16]>(pk));
+          tmem_st_x16(t_dp, reinterpret_cast<uint32_t (&)[16]>(dk));
+        } else {
+          tmem_st_x8(t_s, reinterpret_cast<uint32_t (&)[8]>(pk));
+          tmem_st_x8(t_dp, reinterpret_cast<uint32_t (&)[8]>(dk));
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) b2_arrive(bars + BB_PDS + 8 * hh);
+        // dS^T also goes to shared memory for the dQ product, off the critical path of the dV / dK products
         if (hh == 0 && g > 0) b2_wait(bars + BB_DQ, (g - 1) & 1);          // the previous step's dQ product has read the dS^T tile
         {
           uint8_t* slab = smem + B2_OFF_DS + hh * PT_SLAB_BYTES;
 #pragma unroll
-          for (int ch = 0; ch < 4; ++ch)
-            *reinterpret_cast<uint4*>(slab + swz_off<128>(row, cg * 4 + ch)) = make_uint4(dk[4 * ch], dk[4 * ch + 1], dk[4 * ch + 2], dk[4 * ch + 3]);
+          for (int ch = 0; ch < CW / 8; ++ch)
+            *reinterpret_cast<uint4*>(slab + swz_off<128>(row, cg * (CW / 8) + ch)) = make_uint4(dk[4 * ch], dk[4 * ch + 1], dk[4 * ch + 2], dk[4 * ch + 3]);
         }
-        tmem_st_wait();
         fence_proxy_async_smem();
-        tc_fence_before();
         __syncwarp();
-        if (lane == 0) b2_arrive(bars + BB_PDS + 8 * hh);
+        if (lane == 0) b2_arrive(bars + BB_PDSS + 8 * hh);
       }
       ++g;
     }
   } else {
-    // ============================== output warps (12-15) ==============================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(B2_OUT_REGS));
+    // ============================== output warps (the last four) ==============================
+    if (NCG == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(Cfg::OUT_REGS));
+    else asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(Cfg::OUT_REGS));
     const int wrow = (warp & 3) * 32;
     const int row = wrow + lane;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(wrow) << 16);
-    const int ot = tid - 384;
+    const int ot = tid - (Cfg::THREADS - 128);
     uint32_t g = 0, n_items = 0;
     bool end = false, pending = false;
     // TMEM accumulator tile (64 fp32 columns of this thread's row) x mul -> bf16 -> swizzled staging tile
@@ -498,15 +545,19 @@ int attn_bwd_v2_impl(const ot_attn_params* p, cudaStream_t st) {
   kp.scale = 1.0f / sqrtf((float)p->head_dim);
   kp.scale_log2 = kp.scale * 1.4426950408889634f;
   kp.lse = p->lse; kp.delta = p->delta;
+  // OT_ATTN_BWD_NCG (read once): element-wise warps per TMEM lane quarter, 2 or 4 (default 2: measured faster, profiles/README.md)
+  static const int ncg = [] { const char* e = getenv("OT_ATTN_BWD_NCG"); return (e && atoi(e) == 4) ? 4 : 2; }();
   static bool attr_done = false;
   if (!attr_done) {
-    OT_CUDA_CHECK(cudaFuncSetAttribute(ot_attn_bwd_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, B2_SMEM_BYTES));
+    OT_CUDA_CHECK(cudaFuncSetAttribute(ot_attn_bwd_v2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, B2_SMEM_BYTES));
+    OT_CUDA_CHECK(cudaFuncSetAttribute(ot_attn_bwd_v2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, B2_SMEM_BYTES));
     attr_done = true;
   }
   if ((rc = attn_bwd_prologue(p, st))) return rc;
   const int sms = num_sms();
   const int grid = kp.total_items < sms ? kp.total_items : sms;
-  ot_attn_bwd_v2_kernel<<<grid, B2_THREADS, B2_SMEM_BYTES, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], tm[6], kp);
+  if (ncg == 2) ot_attn_bwd_v2_kernel<2><<<grid, B2Cfg<2>::THREADS, B2_SMEM_BYTES, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], tm[6], kp);
+  else ot_attn_bwd_v2_kernel<4><<<grid, B2Cfg<4>::THREADS, B2_SMEM_BYTES, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], tm[6], kp);
   OT_CUDA_CHECK(cudaGetLastError());
   return OT_OK;
 }
