@@ -13,7 +13,7 @@
 // element-wise warps work on one half while the tensor pipe runs the products of the other.  The softmax scale is applied to dQ
 // and dK on the way out (a power of two for head_dim 64: exact).
 //
-// Warps: 0 loader (TMA + step ring), 1 MMA issuer, 2-3 row statistics (lse * log2 e, delta -> shared memory), 4-11 element-wise
+// Warps: 0 loader (TMA + step ring), 1 MMA issuer, 2-3 row statistics (-lse * log2 e, -delta -> shared memory), 4-11 element-wise
 // (thread = one key row x 32 query columns of a half), 12-15 output (dQ by TMA reduce-add, dK / dV by TMA store).
 // TMEM: S^T halves 0 / 64, dP^T halves 128 / 192, dV 256, dK 320, dQ 384.
 #include <stdlib.h>
@@ -63,7 +63,7 @@ enum : uint32_t {
   BB_QFREE = 56,     // [3] dV / dK products of the step's second half done  (MMA commit -> loader)
   BB_S = 80,         // [2] S^T, dP^T of a half complete                     (MMA commit -> element-wise)
   BB_PDS = 96,       // [2] P^T, dS^T of a half written to TENSOR memory     (4 NCG arrivals -> MMA: dV / dK products may go)
-  BB_PDSS = 280,     // [2] dS^T of a half written to SHARED memory          (4 NCG arrivals -> MMA: dQ product may go)
+  BB_PDSS = 280,     //     dS^T of the step written to SHARED memory        (4 NCG arrivals -> MMA: dQ product may go)
   BB_DQ = 112,       //     dQ of the step complete                          (MMA commit -> output, element-wise)
   BB_DQFREE = 120,   //     dQ pulled out of TMEM                            (4 arrivals -> MMA)
   BB_ACC = 128,      //     dV, dK of the item complete                      (MMA commit -> output)
@@ -169,7 +169,7 @@ ot_attn_bwd_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     auto init = [&](uint32_t off, int n, uint32_t count) {
       for (int i = 0; i < n; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bars + off + 8 * i), "r"(count));
     };
-    init(BB_KV, 2, 1); init(BB_KVFREE, 2, 1); init(BB_Q, 3, 3); init(BB_QFREE, 3, 1); init(BB_S, 2, 1); init(BB_PDS, 2, N_EW); init(BB_PDSS, 2, N_EW);
+    init(BB_KV, 2, 1); init(BB_KVFREE, 2, 1); init(BB_Q, 3, 3); init(BB_QFREE, 3, 1); init(BB_S, 2, 1); init(BB_PDS, 2, N_EW); init(BB_PDSS, 1, N_EW);
     init(BB_DQ, 1, 1); init(BB_DQFREE, 1, 4); init(BB_ACC, 1, 1); init(BB_ACCFREE, 1, 4); init(BB_IFULL, 8, 1); init(BB_IFREE, 8, 7 + N_EW);
     fence_mbar_init();
   }
@@ -304,10 +304,10 @@ ot_attn_bwd_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           }
           issue_main(cur, 1, g);
           b2_commit(bars + BB_QFREE + 8 * st);        // Q_i / dO_i (and the statistics of the step) are no longer needed
+          if (flags & SB_LAST) b2_commit(bars + BB_ACC);   // dV_j, dK_j are final
           if (!end) issue_sdp(nxt, 1);
           // dQ_i = dS K_j over the whole query tile (both halves of dS^T are in shared memory)
           b2_wait(bars + BB_PDSS, g & 1);
-          b2_wait(bars + BB_PDSS + 8, g & 1);
           if (g > 0) b2_wait(bars + BB_DQFREE, (g - 1) & 1);
           tc_fence_after();
           {
@@ -316,10 +316,7 @@ ot_attn_bwd_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
             for (int kk = 0; kk < 8; ++kk) umma_bf16_ss(tmem_base + B2_T_DQ, dS_mn + 128 * kk, mK + 128 * kk, idesc_dq, kk != 0);
           }
           b2_commit(bars + BB_DQ);
-          if (flags & SB_LAST) {
-            b2_commit(bars + BB_ACC);
-            b2_commit(bars + BB_KVFREE + 8 * kb);
-          }
+          if (flags & SB_LAST) b2_commit(bars + BB_KVFREE + 8 * kb);
           cur = nxt;
           ++g;
         }
@@ -343,8 +340,8 @@ ot_attn_bwd_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 #pragma unroll
         for (int r = i; r < 128; r += 64) {
           const bool ok = (q0 + r) < p.Lq;       // rows past the query tail: probability 0 (lse = +inf), delta 0
-          sl[r] = ok ? p.lse[base + r] * 1.4426950408889634f : INFINITY;
-          sl[128 + r] = ok ? p.delta[base + r] : 0.0f;
+          sl[r] = ok ? p.lse[base + r] * -1.4426950408889634f : -INFINITY;
+          sl[128 + r] = ok ? -p.delta[base + r] : 0.0f;
         }
         __syncwarp();
         if (lane == 0) b2_arrive(bars + BB_Q + 8 * st);     // release: publishes the 64 rows this warp wrote
@@ -371,8 +368,9 @@ ot_attn_bwd_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       end = (flags & SB_END) != 0;
       const int q0 = si.x & 0xffff, k0 = (si.x >> 16) & 0xffff;
       b2_wait(bars + BB_Q + 8 * st, (g / B2_Q_STAGES) & 1);         // row statistics of the step are in shared memory
-      const float* sl = reinterpret_cast<const float*>(smem + B2_OFF_STATS + st * 1024);
-#pragma unroll 1
+      const float* sl = reinterpret_cast<const float*>(smem + B2_OFF_STATS + st * 1024);   // -lse * log2 e [128], -delta [128]
+      uint32_t dk[2][CW / 2];                                       // dS^T of both halves, kept for the shared-memory copy at the end of the step
+#pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         // column c (0 .. CW-1) of this thread is query q0 + 64 hh + CW cg + c; key k0 + row sees it iff c >= cmin
         const int cmin_lo = k0 + wrow - off - q0 - 64 * hh - CW * cg;      // lane 0 (lane 31: + 31)
@@ -380,12 +378,12 @@ ot_attn_bwd_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         const bool none = cmin_lo >= CW;                                   // the whole 32 x CW block is hidden
         const bool fast = cmin_lo + 31 <= 0;                               // entirely visible
         const uint32_t t_s = t_lane + B2_T_S + hh * 64 + cg * CW, t_dp = t_lane + B2_T_DP + hh * 64 + cg * CW;
-        uint32_t pk[CW / 2], dk[CW / 2];
+        uint32_t pk[CW / 2];
         b2_wait(bars + BB_S + 8 * hh, g & 1);
         tc_fence_after();
         if (none) {
 #pragma unroll
-          for (int i = 0; i < CW / 2; ++i) { pk[i] = 0u; dk[i] = 0u; }
+          for (int i = 0; i < CW / 2; ++i) { pk[i] = 0u; dk[hh][i] = 0u; }
         } else {
           uint32_t vs[CW], vd[CW];
           if (CW == 32) {
@@ -398,54 +396,78 @@ ot_attn_bwd_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           tmem_ld_wait();
           const float4* l4 = reinterpret_cast<const float4*>(sl + hh * 64 + cg * CW);
           const float4* d4 = reinterpret_cast<const float4*>(sl + 128 + hh * 64 + cg * CW);
+          if (fast) {
+            // packed fp32 pairs: 2 FFMA2 + 4 MUFU + 2 FADD2 + 2 FMUL2 + 4 packs per four elements (the scalar form issued 12 + 4 + 4)
+            const f32x2 c2 = pk2(p.scale_log2);
 #pragma unroll
-          for (int c4 = 0; c4 < CW / 4; ++c4) {
-            const float4 ls = l4[c4];
-            const float4 dl = d4[c4];
-            float p0 = ex2_approx(fmaf(__uint_as_float(vs[4 * c4 + 0]), p.scale_log2, -ls.x));
-            float p1 = ex2_approx(fmaf(__uint_as_float(vs[4 * c4 + 1]), p.scale_log2, -ls.y));
-            float p2 = ex2_approx(fmaf(__uint_as_float(vs[4 * c4 + 2]), p.scale_log2, -ls.z));
-            float p3 = ex2_approx(fmaf(__uint_as_float(vs[4 * c4 + 3]), p.scale_log2, -ls.w));
-            if (!fast) {
+            for (int c4 = 0; c4 < CW / 4; ++c4) {
+              const float4 nl = l4[c4];
+              const float4 nd = d4[c4];
+              float a0, a1, a2, a3;
+              upk2(fma2(pk2(__uint_as_float(vs[4 * c4 + 0]), __uint_as_float(vs[4 * c4 + 1])), c2, pk2(nl.x, nl.y)), a0, a1);
+              upk2(fma2(pk2(__uint_as_float(vs[4 * c4 + 2]), __uint_as_float(vs[4 * c4 + 3])), c2, pk2(nl.z, nl.w)), a2, a3);
+              const float p0 = ex2_approx(a0), p1 = ex2_approx(a1), p2 = ex2_approx(a2), p3 = ex2_approx(a3);
+              const f32x2 t01 = add2(pk2(__uint_as_float(vd[4 * c4 + 0]), __uint_as_float(vd[4 * c4 + 1])), pk2(nd.x, nd.y));
+              const f32x2 t23 = add2(pk2(__uint_as_float(vd[4 * c4 + 2]), __uint_as_float(vd[4 * c4 + 3])), pk2(nd.z, nd.w));
+              float s0, s1, s2, s3;
+              upk2(mul2(pk2(p0, p1), t01), s0, s1);
+              upk2(mul2(pk2(p2, p3), t23), s2, s3);
+              pk[2 * c4] = pack_bf16x2(p0, p1);
+              pk[2 * c4 + 1] = pack_bf16x2(p2, p3);
+              dk[hh][2 * c4] = pack_bf16x2(s0, s1);
+              dk[hh][2 * c4 + 1] = pack_bf16x2(s2, s3);
+            }
+          } else {
+#pragma unroll
+            for (int c4 = 0; c4 < CW / 4; ++c4) {
+              const float4 nl = l4[c4];
+              const float4 nd = d4[c4];
+              float p0 = ex2_approx(fmaf(__uint_as_float(vs[4 * c4 + 0]), p.scale_log2, nl.x));
+              float p1 = ex2_approx(fmaf(__uint_as_float(vs[4 * c4 + 1]), p.scale_log2, nl.y));
+              float p2 = ex2_approx(fmaf(__uint_as_float(vs[4 * c4 + 2]), p.scale_log2, nl.z));
+              float p3 = ex2_approx(fmaf(__uint_as_float(vs[4 * c4 + 3]), p.scale_log2, nl.w));
               p0 = (4 * c4 + 0 >= cmin) ? p0 : 0.0f;
               p1 = (4 * c4 + 1 >= cmin) ? p1 : 0.0f;
               p2 = (4 * c4 + 2 >= cmin) ? p2 : 0.0f;
               p3 = (4 * c4 + 3 >= cmin) ? p3 : 0.0f;
+              const float s0 = p0 * (__uint_as_float(vd[4 * c4 + 0]) + nd.x);
+              const float s1 = p1 * (__uint_as_float(vd[4 * c4 + 1]) + nd.y);
+              const float s2 = p2 * (__uint_as_float(vd[4 * c4 + 2]) + nd.z);
+              const float s3 = p3 * (__uint_as_float(vd[4 * c4 + 3]) + nd.w);
+              pk[2 * c4] = pack_bf16x2(p0, p1);
+              pk[2 * c4 + 1] = pack_bf16x2(p2, p3);
+              dk[hh][2 * c4] = pack_bf16x2(s0, s1);
+              dk[hh][2 * c4 + 1] = pack_bf16x2(s2, s3);
             }
-            const float s0 = p0 * (__uint_as_float(vd[4 * c4 + 0]) - dl.x);
-            const float s1 = p1 * (__uint_as_float(vd[4 * c4 + 1]) - dl.y);
-            const float s2 = p2 * (__uint_as_float(vd[4 * c4 + 2]) - dl.z);
-            const float s3 = p3 * (__uint_as_float(vd[4 * c4 + 3]) - dl.w);
-            pk[2 * c4] = pack_bf16x2(p0, p1);
-            pk[2 * c4 + 1] = pack_bf16x2(p2, p3);
-            dk[2 * c4] = pack_bf16x2(s0, s1);
-            dk[2 * c4 + 1] = pack_bf16x2(s2, s3);
           }
         }
         // P^T / dS^T replace the first CW / 2 of this thread's own CW S^T / dP^T columns (read out above): the dV / dK products may go
         if (CW == 32) {
           tmem_st_x16(t_s, reinterpret_cast<uint32_t (&)[16]>(pk));
-          tmem_st_x16(t_dp, reinterpret_cast<uint32_t (&)[16]>(dk));
+          tmem_st_x16(t_dp, reinterpret_cast<uint32_t (&)[16]>(dk[hh]));
         } else {
           tmem_st_x8(t_s, reinterpret_cast<uint32_t (&)[8]>(pk));
-          tmem_st_x8(t_dp, reinterpret_cast<uint32_t (&)[8]>(dk));
+          tmem_st_x8(t_dp, reinterpret_cast<uint32_t (&)[8]>(dk[hh]));
         }
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) b2_arrive(bars + BB_PDS + 8 * hh);
-        // dS^T also goes to shared memory for the dQ product, off the critical path of the dV / dK products
-        if (hh == 0 && g > 0) b2_wait(bars + BB_DQ, (g - 1) & 1);          // the previous step's dQ product has read the dS^T tile
-        {
-          uint8_t* slab = smem + B2_OFF_DS + hh * PT_SLAB_BYTES;
-#pragma unroll
-          for (int ch = 0; ch < CW / 8; ++ch)
-            *reinterpret_cast<uint4*>(slab + swz_off<128>(row, cg * (CW / 8) + ch)) = make_uint4(dk[4 * ch], dk[4 * ch + 1], dk[4 * ch + 2], dk[4 * ch + 3]);
-        }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) b2_arrive(bars + BB_PDSS + 8 * hh);
       }
+      // dS^T of both halves also goes to shared memory for the dQ product: once per step, off the critical path of the dV / dK
+      // products, and late enough that the previous step's dQ product (the reader of the tile) is long complete
+      if (g > 0) b2_wait(bars + BB_DQ, (g - 1) & 1);
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        uint8_t* slab = smem + B2_OFF_DS + hh * PT_SLAB_BYTES;
+#pragma unroll
+        for (int ch = 0; ch < CW / 8; ++ch)
+          *reinterpret_cast<uint4*>(slab + swz_off<128>(row, cg * (CW / 8) + ch)) =
+              make_uint4(dk[hh][4 * ch], dk[hh][4 * ch + 1], dk[hh][4 * ch + 2], dk[hh][4 * ch + 3]);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) b2_arrive(bars + BB_PDSS);
       ++g;
     }
   } else {
@@ -499,12 +521,9 @@ ot_attn_bwd_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       const int flags = (si.z >> 8) & 0xff;
       end = (flags & SB_END) != 0;
       const int q0 = si.x & 0xffff, k0 = (si.x >> 16) & 0xffff, b = si.y, h = si.z & 0xff;
-      // dQ partial of this step: reduce-add into the zero-initialised dQ (rows past Lq are clipped by the tensor map)
-      b2_wait(bars + BB_DQ, g & 1);
-      tc_fence_after();
-      stage_tile(B2_T_DQ, p.scale, bars + BB_DQFREE);
-      if (ot == 0) { b2_tma_reduce_add(&tmdQ, sbase + B2_OFF_STG, h * DH, b, q0); bulk_commit(); }
       if (flags & SB_LAST) {
+        // end of an item: dV, dK first - the next item's first products wait for these columns, the dQ columns are not needed
+        // again before the end of the next step
         b2_wait(bars + BB_ACC, n_items & 1);
         tc_fence_after();
         stage_tile(B2_T_DV, 1.0f, 0);
@@ -513,6 +532,11 @@ ot_attn_bwd_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         if (ot == 0) { b2_tma_store(&tmdK, sbase + B2_OFF_STG, h * DH, b, k0); bulk_commit(); }
         ++n_items;
       }
+      // dQ partial of this step: reduce-add into the zero-initialised dQ (rows past Lq are clipped by the tensor map)
+      b2_wait(bars + BB_DQ, g & 1);
+      tc_fence_after();
+      stage_tile(B2_T_DQ, p.scale, bars + BB_DQFREE);
+      if (ot == 0) { b2_tma_reduce_add(&tmdQ, sbase + B2_OFF_STG, h * DH, b, q0); bulk_commit(); }
       ++g;
     }
     if (ot == 0) bulk_wait_all();
