@@ -277,11 +277,12 @@ int attn_fwd_impl(const ot_attn_params* p, cudaStream_t st) {
   const int swb = (p->head_dim == 64 && p->swizzle != 64) ? 128 : 64;
   if (p->head_dim == 64 && swb == 128 && p->swizzle != 128) {   // swizzle=128 forces the simple kernel
     // OT_ATTN_FWD_IMPL (read once) forces one structure for A/B runs: 1 = round-1 warp-specialised kernel, 2 = v2 (P through shared
-    // memory), 3 = v3 (P in tensor memory, TS-form P V).  Unset: v3.
+    // memory), 3 = v3 (P in tensor memory, TS-form P V).  Unset: v3 when a (sample, head) has more than one query tile, else 1.
     static const int impl = [] { const char* e = getenv("OT_ATTN_FWD_IMPL"); return e ? atoi(e) : 0; }();
     if (impl == 1) return attn_fwd_ws_impl(p, st);
     if (impl == 2) return attn_fwd_v2_impl(p, st);
-    return attn_fwd_v3_impl(p, st);
+    if (impl == 3) return attn_fwd_v3_impl(p, st);
+    return p->Lq > 128 ? attn_fwd_v3_impl(p, st) : attn_fwd_ws_impl(p, st);   // one query tile per (sample, head): the 16-warp round-1 kernel is faster (in-bench A/B)
   }
   const int cols = p->H * p->head_dim;
   CUtensorMap tq, tk, tv;

@@ -87,18 +87,22 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t src,
 }
 
 // One 32-column chunk of a score row -> probabilities (packed bf16 pairs) and partial row sums, software-pipelined in groups of
-// eight (arguments of group g+1 and sums / packs of group g-1 around the exponentials of group g).
+// eight (arguments of group g+1 and sums / packs of group g-1 around the exponentials of group g).  The mask-free form works on
+// packed fp32 pairs (FFMA2 for the arguments, FADD2 for the row sums: half the issue slots of the scalar form).
 template <bool MASK>
 __device__ __forceinline__ void f3_softmax_chunk(const uint32_t (&s)[32], uint32_t (&pk)[16], float scale_log2, float mb, int lim_rel,
-                                                 float (&rs)[4]) {
+                                                 f32x2 (&rs)[2]) {
   float a[32];
+  const f32x2 c2 = pk2(scale_log2), nmb2 = pk2(-mb);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) a[i] = fmaf(__uint_as_float(s[i]), scale_log2, -mb);
+  for (int i = 0; i < 4; ++i) upk2(fma2(pk2(__uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1])), c2, nmb2), a[2 * i], a[2 * i + 1]);
 #pragma unroll
   for (int g = 0; g < 5; ++g) {
     if (g + 1 < 4) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) a[(g + 1) * 8 + i] = fmaf(__uint_as_float(s[(g + 1) * 8 + i]), scale_log2, -mb);
+      for (int i = 0; i < 4; ++i)
+        upk2(fma2(pk2(__uint_as_float(s[(g + 1) * 8 + 2 * i]), __uint_as_float(s[(g + 1) * 8 + 2 * i + 1])), c2, nmb2), a[(g + 1) * 8 + 2 * i],
+             a[(g + 1) * 8 + 2 * i + 1]);
     }
     if (g < 4) {
 #pragma unroll
@@ -112,7 +116,7 @@ __device__ __forceinline__ void f3_softmax_chunk(const uint32_t (&s)[32], uint32
       }
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        rs[i] += a[b0 + 2 * i] + a[b0 + 2 * i + 1];
+        rs[i & 1] = add2(rs[i & 1], pk2(a[b0 + 2 * i], a[b0 + 2 * i + 1]));
         pk[(b0 >> 1) + i] = pack_bf16x2(a[b0 + 2 * i], a[b0 + 2 * i + 1]);
       }
     }
@@ -438,7 +442,7 @@ ot_attn_fwd_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       }
       // ---- p = 2^((s - m_ref) * scale * log2 e), row sums, packed bf16 pairs written back to TMEM chunk by chunk ----
       const float mb = m_ref * p.scale_log2;
-      float rs4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+      f32x2 rs4[2] = {pk2(0.0f), pk2(0.0f)};
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         if (c * 32 < ncols) {
@@ -464,7 +468,12 @@ ot_attn_fwd_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_s(bar_p);
-      l_run += (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
+      {
+        float r0, r1, r2, r3;
+        upk2(rs4[0], r0, r1);
+        upk2(rs4[1], r2, r3);
+        l_run += (r0 + r1) + (r2 + r3);
+      }
 
       if (last) {
         // hand the row statistics to the epilogue warpgroup and go on with the next tile
