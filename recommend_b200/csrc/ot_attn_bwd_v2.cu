@@ -41,6 +41,7 @@ static constexpr int B2_DH = 64;
 static constexpr int B2_TILE = 128 * B2_DH * 2;        // 16 KB
 static constexpr int B2_Q_STAGES = 3;
 static constexpr int B2_INFO_SLOTS = 8;
+static constexpr int B2_LOOKAHEAD = 5;       // steps the L2 prefetches run ahead of the TMA loads
 static constexpr int B2_OFF_K = 0;                                   // [2]
 static constexpr int B2_OFF_V = B2_OFF_K + 2 * B2_TILE;              // [2]
 static constexpr int B2_OFF_Q = B2_OFF_V + 2 * B2_TILE;              // [3]
@@ -76,6 +77,9 @@ enum { SB_FIRST = 1, SB_LAST = 2, SB_END = 4, SB_KVBUF = 8 };
 // step info (one query tile against the item's key tile), 16 bytes: x = q0 | k0 << 16, y = b, z = h | flags << 8 | stage << 16, w = 0
 
 __device__ __forceinline__ void b2_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+#ifndef OT_B2_WAIT_HINT_NS
+#define OT_B2_WAIT_HINT_NS 20000
+#endif
 __device__ __forceinline__ void b2_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}\n"
@@ -83,10 +87,15 @@ __device__ __forceinline__ void b2_wait(uint32_t bar, uint32_t parity) {
   if (ok) return;
   uint32_t spins = 0;
   do {
+#if OT_B2_WAIT_HINT_NS > 0
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.b32 %0, 1, 0, p;\n\t}\n"
-                 : "=r"(ok) : "r"(bar), "r"(parity), "r"(20000u) : "memory");
+                 : "=r"(ok) : "r"(bar), "r"(parity), "r"((uint32_t)OT_B2_WAIT_HINT_NS) : "memory");
+#else
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+#endif
 #if OT_HANG_GUARD
-    if (++spins > (1u << 17)) __trap();
+    if (++spins > (1u << 24)) __trap();
 #endif
   } while (!ok);
 }
@@ -97,6 +106,11 @@ __device__ __forceinline__ void b2_commit(uint32_t bar) {
 __device__ __forceinline__ void b2_tmem_cp_128x256b(uint32_t taddr, uint64_t sdesc) {
   asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(taddr), "l"(sdesc) : "memory");
 }
+__device__ __forceinline__ void b2_tma_prefetch_l2(const CUtensorMap* m, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1),
+               "r"(c2) : "memory");
+}
+__device__ __forceinline__ void b2_prefetch_l2(const void* ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
 __device__ __forceinline__ void b2_tma_store(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
                ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
@@ -107,11 +121,21 @@ __device__ __forceinline__ void b2_tma_reduce_add(const CUtensorMap* m, uint32_t
 }
 
 // Walks the (item, query tile) steps of one CTA in launch order (loader warp only): item = (key tile, head, sample).
+// Items after the first are drawn from a device-wide counter.  The loader runs a second, LOOK-AHEAD cursor a few steps in front of
+// the one that issues the TMA loads: it draws the items (and hands their ids to the main cursor through a small ring) and asks for
+// L2 prefetches of the tiles, so that the loads proper find their 128-byte rows (each in a different DRAM page: consecutive tokens
+// of a sample are B * ld elements apart) in L2.  ncu before: the element-wise warps waited 6 % on the step's Q / dO / statistics.
+struct B2ItemRing { int ids[8]; uint32_t w, r; };
 struct B2Cursor {
   int item, next_item, ii, n_i, i_min, h, b, k0, item_idx;
   bool valid;
-  __device__ __forceinline__ void fetch_next(const AttnBwdV2KParams& p) {
-    next_item = p.sched != nullptr ? (int)gridDim.x + atomicAdd(p.sched, 1) : item + (int)gridDim.x;
+  __device__ __forceinline__ void fetch_next(const AttnBwdV2KParams& p, B2ItemRing& ring, bool producer) {
+    if (producer) {
+      next_item = p.sched != nullptr ? (int)gridDim.x + atomicAdd(p.sched, 1) : item + (int)gridDim.x;
+      ring.ids[ring.w++ & 7] = next_item;
+    } else {
+      next_item = ring.ids[ring.r++ & 7];
+    }
   }
   __device__ __forceinline__ void load_item(const AttnBwdV2KParams& p) {
     valid = item < p.total_items;
@@ -126,19 +150,19 @@ struct B2Cursor {
     n_i = p.n_qt - i_min;
     ii = 0;
   }
-  __device__ __forceinline__ void init(const AttnBwdV2KParams& p) {
+  __device__ __forceinline__ void init(const AttnBwdV2KParams& p, B2ItemRing& ring, bool producer) {
     item = blockIdx.x;
     next_item = p.total_items;
     item_idx = 0;
     load_item(p);
-    if (valid) fetch_next(p);
+    if (valid) fetch_next(p, ring, producer);
   }
-  __device__ __forceinline__ void next(const AttnBwdV2KParams& p) {
+  __device__ __forceinline__ void next(const AttnBwdV2KParams& p, B2ItemRing& ring, bool producer) {
     if (++ii == n_i) {
       item = next_item;
       ++item_idx;
       load_item(p);
-      if (valid) fetch_next(p);
+      if (valid) fetch_next(p, ring, producer);
     }
   }
   __device__ __forceinline__ int q0() const { return (i_min + ii) * 128; }
@@ -185,17 +209,38 @@ ot_attn_bwd_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     if (warp == 0) {
       // ============================== loader: step ring + TMA ==============================
       if (elect_one()) {
-        B2Cursor c;
-        c.init(p);
-        uint32_t t = 0;
+        B2ItemRing ring;
+        ring.w = ring.r = 0;
+        B2Cursor pf, c;
+        pf.init(p, ring, true);
+        c.init(p, ring, false);
+        uint32_t t = 0, t_pf = 0;
         while (c.valid) {
+          // look-ahead: L2 prefetch of the tiles (and statistics) of the next steps
+          while (pf.valid && t_pf < t + B2_LOOKAHEAD) {
+            const int pq0 = pf.q0();
+            if (pf.ii == 0) {
+              b2_tma_prefetch_l2(&tmK, pf.h * DH, pf.b, pf.k0);
+              b2_tma_prefetch_l2(&tmV, pf.h * DH, pf.b, pf.k0);
+            }
+            b2_tma_prefetch_l2(&tmQ, pf.h * DH, pf.b, pq0);
+            b2_tma_prefetch_l2(&tmdO, pf.h * DH, pf.b, pq0);
+            const long long sb = ((long long)pf.b * p.H + pf.h) * p.Lq + pq0;
+#pragma unroll
+            for (int i = 0; i < 128; i += 32) {
+              if (pq0 + i < p.Lq) { b2_prefetch_l2(p.lse + sb + i); b2_prefetch_l2(p.delta + sb + i); }
+            }
+            pf.next(p, ring, true);
+            ++t_pf;
+          }
           const int st = t % B2_Q_STAGES;
           const int kb = c.item_idx & 1;
           const bool first = c.ii == 0, last = c.ii == c.n_i - 1;
           if (t >= B2_Q_STAGES) b2_wait(bars + BB_QFREE + 8 * st, ((t / B2_Q_STAGES) - 1) & 1);      // stage's previous step done
           if (first && c.item_idx >= 2) b2_wait(bars + BB_KVFREE + 8 * kb, ((c.item_idx >> 1) - 1) & 1);   // buffer's previous item done
           B2Cursor n = c;
-          n.next(p);
+          B2ItemRing ring_n = ring;             // peek: the copy's ring position is discarded
+          n.next(p, ring_n, false);
           const int is = t & (B2_INFO_SLOTS - 1);
           if (t >= B2_INFO_SLOTS) b2_wait(bars + BB_IFREE + 8 * is, ((t / B2_INFO_SLOTS) - 1) & 1);
           const int flags = (first ? SB_FIRST : 0) | (last ? SB_LAST : 0) | (n.valid ? 0 : SB_END) | (kb ? SB_KVBUF : 0);
@@ -212,7 +257,7 @@ ot_attn_bwd_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           mbar_arrive_expect_tx(bq, 2 * B2_TILE);
           load_head_tile<DH, SWB>(smem + B2_OFF_Q + st * B2_TILE, &tmQ, bq, c.h, c.b, q0);
           load_head_tile<DH, SWB>(smem + B2_OFF_DO + st * B2_TILE, &tmdO, bq, c.h, c.b, q0);
-          c = n;
+          c.next(p, ring, false);
           ++t;
         }
       }
