@@ -469,7 +469,7 @@ ot_attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
 template <int LPH>   // lanes per (row, head) = dh / 8: 8 (dh 64), 4 (dh 32), 16 (dh 128)
 __global__ void __launch_bounds__(256)
 attn_delta_kernel(const __nv_bfloat16* __restrict__ o, long long ldo, const __nv_bfloat16* __restrict__ d_o, long long lddo,
-                  float* __restrict__ delta, int B, int H, int Lq) {
+                  float* __restrict__ delta, int B, int H, int Lq, __nv_bfloat16* __restrict__ dq, long long lddq) {
   const long long total = (long long)Lq * B * H * LPH;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long idx0 = (long long)blockIdx.x * blockDim.x; idx0 < total; idx0 += stride) {   // warp-uniform trip count
@@ -486,6 +486,9 @@ attn_delta_kernel(const __nv_bfloat16* __restrict__ o, long long ldo, const __nv
       const uint4 g = reinterpret_cast<const uint4*>(d_o + rowi * lddo + h * (LPH * 8))[ch];
       acc = bf16lo(a.x) * bf16lo(g.x) + bf16hi(a.x) * bf16hi(g.x) + bf16lo(a.y) * bf16lo(g.y) + bf16hi(a.y) * bf16hi(g.y) +
             bf16lo(a.z) * bf16lo(g.z) + bf16hi(a.z) * bf16hi(g.z) + bf16lo(a.w) * bf16lo(g.w) + bf16hi(a.w) * bf16hi(g.w);
+      // dQ is accumulated with reductions by the main kernel: this pass, which walks the same (row, head, chunk) cells, zeroes it
+      // (a separate memset was one more launch, and a 2-D one - strided dQ - ran far below the copy rate)
+      reinterpret_cast<uint4*>(dq + rowi * lddq + h * (LPH * 8))[ch] = make_uint4(0u, 0u, 0u, 0u);
     }
 #pragma unroll
     for (int off = LPH / 2; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
@@ -499,22 +502,15 @@ attn_delta_kernel(const __nv_bfloat16* __restrict__ o, long long ldo, const __nv
 
 int make_head_tmap(CUtensorMap* tm, const void* base, int cols, int B, int L, long long ld, int swb);
 
-// Shared by the head_dim-64 backward kernels: zero dQ (it is accumulated with reductions) and delta = rowsum(dO o O).
+// Shared by the head_dim-64 backward kernels: delta = rowsum(dO o O), and dQ zeroed in the same pass.
 int attn_bwd_prologue(const ot_attn_params* p, cudaStream_t st) {
-  const int cols = p->H * p->head_dim;
-  // dQ is accumulated with reductions: zero the [Lq*B, H*dh] block it covers (row by row when strided)
-  if (p->lddq == cols) {
-    OT_CUDA_CHECK(cudaMemsetAsync(p->dq, 0, (size_t)p->Lq * p->B * cols * 2, st));
-  } else {
-    OT_CUDA_CHECK(cudaMemset2DAsync(p->dq, (size_t)p->lddq * 2, 0, (size_t)cols * 2, (size_t)p->Lq * p->B, st));
-  }
   {
     const int lph = p->head_dim / 8;
     const long long total = (long long)p->Lq * p->B * p->H * lph;
     long long blocks = (total + 255) / 256;
     if (blocks > (long long)num_sms() * 32) blocks = (long long)num_sms() * 32;
 #define OT_LAUNCH_DELTA(N) attn_delta_kernel<N><<<(int)blocks, 256, 0, st>>>((const __nv_bfloat16*)p->o, p->ldo, (const __nv_bfloat16*)p->d_o, \
-                                                                             p->lddo, p->delta, p->B, p->H, p->Lq)
+                                                                             p->lddo, p->delta, p->B, p->H, p->Lq, (__nv_bfloat16*)p->dq, p->lddq)
     if (lph == 8) OT_LAUNCH_DELTA(8); else if (lph == 4) OT_LAUNCH_DELTA(4); else if (lph == 16) OT_LAUNCH_DELTA(16);
     else OT_FAIL(OT_ERR_UNSUPPORTED_SHAPE, "ot_attn_bwd: head_dim=%d", p->head_dim);
 #undef OT_LAUNCH_DELTA

@@ -147,18 +147,18 @@ def mha_backward(dz: torch.Tensor, xn: torch.Tensor, saved, w: BlockWeights, Wqk
     ops.wgrad_rows(o, dz, [(0, 1, rows_t, 0, 0)], Wo_grad, 0, d, 1)
     do = torch.empty(rows_t, d, dtype=bf16, device=dev)
     ops.mixed_gemm(dz, w.Wo_b, [(0, 1, rows_t, 0, 0)], do)
-    # attention
-    dq = torch.empty(rows_t, d, dtype=bf16, device=dev)
-    dkv = torch.empty(rows, 2 * d, dtype=bf16, device=dev)
+    # attention: dq | dk | dv land in ONE [rows, 3d] buffer (dq in the tail rows, zero in the pruned head rows), so that the
+    # projections' weight gradient and input gradient are one launch each over K = 3d / N = 3d: xn and the gradient rows are
+    # read once, dxn is written once (it used to be written by the K|V product and read / re-written by the Q product)
+    dqkv = torch.empty(rows, 3 * d, dtype=bf16, device=dev)
+    if off > 0:
+        dqkv[:off, :d].zero_()
     delta = torch.empty(B * H * keep, dtype=torch.float32, device=dev)
-    ops.attn_bwd(q, kv[:, :d], kv[:, d:], o, lse, do, dq, dkv[:, :d], dkv[:, d:], delta, B, H, keep, cur, dh)
+    ops.attn_bwd(q, kv[:, :d], kv[:, d:], o, lse, do, dqkv[off:, :d], dqkv[:, d:2 * d], dqkv[:, 2 * d:], delta, B, H, keep, cur, dh)
     # projections:  q = xn_tail @ Wq[g],  k|v = xn @ Wkv[g]
-    G = Wqkv_grad.shape[0]
-    ops.wgrad_rows(xn[off:], dq, segs_tail, Wqkv_grad, d * 3 * d, 3 * d, 1)
-    ops.wgrad_rows(xn, dkv, segs_all, Wqkv_grad[:, :, d:], d * 3 * d, 3 * d, 1)
+    ops.wgrad_rows(xn, dqkv, segs_all, Wqkv_grad, d * 3 * d, 3 * d, 1)
     dxn = torch.empty(rows, d, dtype=bf16, device=dev)
-    ops.mixed_gemm(dkv, w.Wqkv_b[:, :, d:], segs_all, dxn)
-    ops.mixed_gemm(dq, w.Wqkv_b[:, :, :d], segs_tail, dxn[off:], flags=OT_EPI_RESIDUAL, res=dxn[off:])
+    ops.mixed_gemm(dqkv, w.Wqkv_b, segs_all, dxn)
     return dxn
 
 
