@@ -186,7 +186,8 @@ def config_dict(args, wl, B):
             'global_batch': B * args.gpus, 'seq_tokens': sum(wl['seq_lens']) + 2, 'ns_tokens': wl['L_ns'],
             'parallelism': f'dp{args.gpus}', 'dropout': args.dropout,
             'optimizer': 'clip_by_norm 90 + RMSprop inside the timed step' if args.optimizer else 'none (metric is fwd+bwd)',
-            'grad_allreduce': 'none (1 GPU)' if args.gpus == 1 else ('after the backward' if args.no_overlap else 'per block, under the backward of the blocks below'),
+            'grad_allreduce': 'none (1 GPU)' if args.gpus == 1 else (('after the backward' if args.no_overlap else 'per block, under the backward of the blocks below') +
+                                                                     f", exchanged as {os.environ.get('OT_GRAD_REDUCE_DTYPE', 'fp32')} (fp32 accumulation buffer)"),
             'inputs': 'pre-embedded events bf16 [B, L_i, 64] x3, 11 fp32 scalars, 2 fp32 labels per sample (pinned host buffers in the e2e arm)',
             'l2_policy': 'activations per step (>20 GB) far exceed the 126 MB L2; no explicit flush'}
 
@@ -501,8 +502,10 @@ def main():
             'e2e': {'value': e2e_value, 'unit': 'samples/s', 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': 4},
             'gpu_launches': launches,
             'loss': float(loss),
-            'grad_allreduce': None if ar_ms is None else {'ms': ar_ms, 'bytes': grads.flat.numel() * 4,
-                                                          'algbw_gbs': grads.flat.numel() * 4 / (ar_ms * 1e-3) / 1e9},
+            'grad_allreduce': None if ar_ms is None else {'ms': ar_ms, 'bytes': grads.flat.numel() * (2 if grads._low_precision() else 4),
+                                                          'exchange_dtype': 'bf16' if grads._low_precision() else 'fp32',
+                                                          'algbw_gbs': grads.flat.numel() * (2 if grads._low_precision() else 4) / (ar_ms * 1e-3) / 1e9,
+                                                          'note': 'the collective alone (with its fp32 <-> bf16 conversion passes when the exchange is bf16)'},
             'model_flops': {'algorithmic_tflop_per_step_per_gpu': step_tflop, 'achieved_tflops_per_gpu': step_tflop / (ms_step * 1e-3),
                             'frac_of_bf16_sustained_peak': step_tflop / (ms_step * 1e-3) / peaks['tf_sustained'], 'peak_source': peaks['src']},
         }

@@ -7,6 +7,7 @@ from __future__ import annotations
 
 from typing import Dict, Iterable, List, Optional, Tuple
 
+import os
 import torch
 import torch.distributed as dist
 
@@ -43,6 +44,15 @@ class FlatGradBuffer:
         self.flat = torch.zeros(off, dtype=torch.float32, device=dev)
         for p, o in zip(self.params, self.offsets):
             p.grad = self.flat[o:o + p.numel()].view(p.shape)
+        # Data-parallel exchange format (SURVEY 7.2 "measure"): 'bf16' sends a bf16 copy of each bucket through the collective and
+        # writes the average back into the fp32 buffer - half the bytes on NVLink and half the time NCCL's CTAs hold SMs that the
+        # one-CTA-per-SM persistent kernels of the backward want; the 2^-9 rounding of the AVERAGED gradient is far inside the
+        # run-to-run noise of the gradients themselves (fp32 atomics, bf16 dQ reductions: 0.7e-2, profiles/r2_dp_equivalence_2gpu.json).
+        # Measured on 2 x B200 (profiles/README.md): 38.9 ms/step with the bf16 exchange against 38.1 with fp32 - at two GPUs the
+        # collective alone takes 1.2 ms either way and the two conversion passes cost more than the halved payload saves, so fp32
+        # stays the default; OT_GRAD_REDUCE_DTYPE=bf16 selects the bf16 exchange (NCCL only: gloo has no bf16 AVG).
+        self.reduce_dtype = os.environ.get('OT_GRAD_REDUCE_DTYPE', 'fp32')
+        self._lowp: Optional[torch.Tensor] = None
 
     def zero(self) -> None:
         self.flat.zero_()
@@ -57,9 +67,23 @@ class FlatGradBuffer:
         op = dist.ReduceOp.AVG if nccl else dist.ReduceOp.SUM
         n_per = self.flat.numel() if bucket_bytes <= 0 else max(1, bucket_bytes // 4)
         for s in range(0, self.flat.numel(), n_per):
-            dist.all_reduce(self.flat[s:s + n_per], op=op)
+            if self._low_precision():
+                lp = self._lowp_view(s, min(s + n_per, self.flat.numel()))
+                lp.copy_(self.flat[s:s + n_per])
+                dist.all_reduce(lp, op=op)
+                self.flat[s:s + n_per].copy_(lp)
+            else:
+                dist.all_reduce(self.flat[s:s + n_per], op=op)
         if not nccl:
             self.flat.mul_(1.0 / world_size)
+
+    def _low_precision(self) -> bool:
+        return self.reduce_dtype == 'bf16' and dist.is_initialized() and dist.get_backend() == 'nccl'
+
+    def _lowp_view(self, s: int, e: int) -> torch.Tensor:
+        if self._lowp is None:
+            self._lowp = torch.empty(self.flat.numel(), dtype=torch.bfloat16, device=self.flat.device)
+        return self._lowp[s:e]
 
     # ---- overlapped reduction: one asynchronous all-reduce per block, issued as soon as the block's backward is enqueued ----
     def range_of(self, params: Iterable[torch.nn.Parameter]):
@@ -75,6 +99,7 @@ class FlatGradBuffer:
 
     def begin_overlapped_reduce(self, world_size: int) -> None:
         self._works, self._done, self._world = [], [], world_size
+        self._copy_back = []
 
     def reduce_range_async(self, rng) -> None:
         """Enqueue the all-reduce of flat[start:end] behind everything already on the current stream; later kernels of
@@ -83,7 +108,13 @@ class FlatGradBuffer:
         if rng is None or self._world <= 1:
             return
         nccl = dist.get_backend() == 'nccl'
-        self._works.append(dist.all_reduce(self.flat[rng[0]:rng[1]], op=dist.ReduceOp.AVG if nccl else dist.ReduceOp.SUM, async_op=True))
+        if self._low_precision():
+            lp = self._lowp_view(rng[0], rng[1])
+            lp.copy_(self.flat[rng[0]:rng[1]])          # fp32 -> bf16 on the current stream, behind the kernels that produced the bucket
+            self._works.append(dist.all_reduce(lp, op=dist.ReduceOp.AVG, async_op=True))
+            self._copy_back.append(rng)
+        else:
+            self._works.append(dist.all_reduce(self.flat[rng[0]:rng[1]], op=dist.ReduceOp.AVG if nccl else dist.ReduceOp.SUM, async_op=True))
         self._done.append(rng)
 
     def finish_overlapped_reduce(self) -> None:
@@ -96,9 +127,11 @@ class FlatGradBuffer:
                 pos = max(pos, e)
             for w in self._works:
                 w.wait()
+            for s, e in self._copy_back:                 # averaged bf16 buckets back into the fp32 gradient buffer
+                self.flat[s:e].copy_(self._lowp[s:e])
             if dist.get_backend() != 'nccl':
                 self.flat.mul_(1.0 / self._world)
-        self._works, self._done = [], []
+        self._works, self._done, self._copy_back = [], [], []
 
 
 class DevicePrefetcher:
