@@ -43,6 +43,9 @@ static constexpr int F3_SMEM_BYTES = F3_OFF_BARS + 512;
 static_assert(F3_SMEM_BYTES <= 227 * 1024, "shared memory budget");
 static constexpr uint32_t F3_T_S = 0, F3_T_O = 256, F3_T_P = 384;     // + tile * 128 / + tile * 64 / + tile * 64
 static constexpr float F3_TAU = 8.0f;                                  // lazy rescale threshold, log2 units
+#ifndef OT_F3_POLY
+#define OT_F3_POLY 0      // pairs (of the four in a group of eight exponentials) evaluated by the FMA-pipe polynomial: 0 .. 4
+#endif
 // mbarrier byte offsets inside the barrier block
 enum : uint32_t {
   B3_Q = 0,          // [2] Q tiles of an item landed                        (loader -> MMA)
@@ -105,8 +108,16 @@ __device__ __forceinline__ void f3_softmax_chunk(const uint32_t (&s)[32], uint32
              a[(g + 1) * 8 + 2 * i + 1]);
     }
     if (g < 4) {
+      // exponentials of group g: OT_F3_POLY of its four pairs go to the FMA-pipe polynomial, the rest to the XU pipe
 #pragma unroll
-      for (int i = 0; i < 8; ++i) a[g * 8 + i] = ex2_mixed(a[g * 8 + i], g * 8 + i);
+      for (int i = 0; i < 4; ++i) {
+        if (i >= 4 - OT_F3_POLY) {
+          upk2(ex2_poly2(pk2(a[g * 8 + 2 * i], a[g * 8 + 2 * i + 1])), a[g * 8 + 2 * i], a[g * 8 + 2 * i + 1]);
+        } else {
+          a[g * 8 + 2 * i] = ex2_approx(a[g * 8 + 2 * i]);
+          a[g * 8 + 2 * i + 1] = ex2_approx(a[g * 8 + 2 * i + 1]);
+        }
+      }
     }
     if (g >= 1) {
       const int b0 = (g - 1) * 8;

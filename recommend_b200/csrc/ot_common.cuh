@@ -416,6 +416,25 @@ __device__ __forceinline__ float ex2_poly(float x) {
   return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));   // p * 2^round(x)
 }
 
+// ex2_poly on a packed pair: 2 FMNMX + 6 packed FMA-pipe instructions + 2 integer ops for two results (the scalar form takes 8
+// per result).  Same constants and arithmetic per lane as ex2_poly (pinned by tests/test_host.py).  Used by the attention forward
+// v3 for a fraction of the exponentials: its two softmax warps per scheduler run their exponentials at the same time (lockstep
+// tiles) and queue for the 16-lane XU pipe, while the FMA pipe is a quarter busy (profiles/README.md, round 2 second session).
+__device__ __forceinline__ f32x2 ex2_poly2(f32x2 x) {
+  float x0, x1;
+  upk2(x, x0, x1);
+  x = pk2(fmaxf(x0, -126.0f), fmaxf(x1, -126.0f));
+  const f32x2 t = add2(x, pk2(12582912.0f));
+  const f32x2 f = fma2(add2(t, pk2(-12582912.0f)), pk2(-1.0f), x);     // x - round(x), in [-0.5, 0.5]
+  f32x2 p = fma2(f, pk2(OT_EX2_POLY_C3), pk2(OT_EX2_POLY_C2));
+  p = fma2(p, f, pk2(OT_EX2_POLY_C1));
+  p = fma2(p, f, pk2(OT_EX2_POLY_C0));
+  float p0, p1, t0, t1;
+  upk2(p, p0, p1);
+  upk2(t, t0, t1);
+  return pk2(__int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23)), __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23)));
+}
+
 // The i-th exponential of an unrolled softmax loop.  OT_EX2_POLY_MODE (compile time, default 0 = every exponential on the MUFU pipe,
 // the verified build): 1 sends every second one to ex2_poly, 2 every fourth.  An experiment switch for round 2
 // (OT_NVCC_EXTRA="-DOT_EX2_POLY_MODE=1" recommend_b200/csrc/build.sh); `i` is a compile-time constant after unrolling.
