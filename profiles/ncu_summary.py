@@ -16,7 +16,7 @@ METRICS = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.
            'smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio',
            'smsp__average_warps_issue_stalled_wait_per_issue_active.ratio']
 FAMILY = {'ot_mixed_gemm_kernel': 'ot_mixed_gemm', 'ot_ffn_fused_kernel': 'ot_ffn_fwd', 'ot_wgrad_kernel': 'ot_wgrad', 'ot_attn_fwd_ws_kernel': 'ot_attn_fwd',
-          'ot_attn_fwd_v2_kernel': 'ot_attn_fwd', 'ot_attn_cached_kernel': 'ot_attn_ns_cached_fwd', 'ot_attn_dkv_kernel': 'ot_attn_bwd', 'ot_attn_dq_kernel': 'ot_attn_bwd',
+          'ot_attn_fwd_v2_kernel': 'ot_attn_fwd', 'ot_attn_fwd_v3_kernel': 'ot_attn_fwd', 'ot_attn_bwd_v2_kernel': 'ot_attn_bwd', 'ot_attn_cached_kernel': 'ot_attn_ns_cached_fwd', 'ot_attn_dkv_kernel': 'ot_attn_bwd', 'ot_attn_dq_kernel': 'ot_attn_bwd',
           'ot_attn_fwd_kernel': 'ot_attn_fwd', 'ot_attn_bwd_fused_kernel': 'ot_attn_bwd', 'rmsnorm_fwd_kernel': 'ot_rmsnorm_fwd',
           'rmsnorm_bwd_kernel': 'ot_rmsnorm_bwd'}
 
@@ -66,3 +66,59 @@ if len(sys.argv) > 3:
     out['_note'] = 'dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, layer-0 shapes of C2 (profiles/prof_kernels.py)'
     json.dump(out, open(sys.argv[3], 'w'), indent=1)
     print('wrote', sys.argv[3])
+
+if len(sys.argv) > 5:
+    tp = 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active'
+    def row_of(kname):
+        return next(((i, r) for i, r in enumerate(data) if kname in r[hdr.index('Kernel Name')]), (None, None))
+    (i_f, r_f), (i_b, r_b) = row_of('ot_attn_fwd_v3_kernel'), row_of('ot_attn_bwd_v2_kernel')
+    if r_f and r_b and tp in hdr:
+        def ms(r):
+            return float(r[hdr.index('gpu__time_duration.sum')].replace(',', '')) * {'ms': 1.0, 'us': 1e-3, 'ns': 1e-6, 's': 1e3}[units[hdr.index('gpu__time_duration.sum')]]
+        f, b = float(r_f[hdr.index(tp)]), float(r_b[hdr.index(tp)])
+        json.dump({'attn_tensor_pipe_util_pct': {'ot_attn_fwd[Lq458_Lk544]': f, 'ot_attn_bwd[Lq458_Lk544]': b,
+                                                 'time_weighted': (f * ms(r_f) + b * ms(r_b)) / (ms(r_f) + ms(r_b)), 'metric': tp,
+                                                 'source': f'{out_csv} rows {i_f} and {i_b} (ot_attn_fwd_v3_kernel, ot_attn_bwd_v2_kernel; C2 layer 0: B 2048, H 4, '
+                                                           'Lq 458, Lk 544, head_dim 64), same build as the bench'}},
+                  open(sys.argv[5], 'w'), indent=1)
+        print('wrote', sys.argv[5])
+
+# ---- ordered join: the i-th library call of prof_kernels.py <-> its main kernel row of the capture (the delta pass of the attention
+# backward and the second kernel of the two-kernel head_dim-96 backward are attributed to the same call) ----
+if len(sys.argv) > 4:
+    MAIN = [('ot_mixed_gemm_kernel', ('ot_mixed_gemm',)), ('ot_ffn_fused_kernel', ('ot_ffn_fwd', 'ot_ffn_bwd')), ('ot_wgrad_kernel', ('ot_wgrad',)),
+            ('ot_attn_fwd_v3_kernel', ('ot_attn_fwd',)), ('ot_attn_fwd_ws_kernel', ('ot_attn_fwd',)), ('ot_attn_fwd_v2_kernel', ('ot_attn_fwd',)),
+            ('ot_attn_fwd_kernel', ('ot_attn_fwd',)), ('ot_attn_bwd_v2_kernel', ('ot_attn_bwd',)), ('ot_attn_bwd_fused_kernel', ('ot_attn_bwd',)),
+            ('ot_attn_dkv_kernel', ('ot_attn_bwd',)), ('rmsnorm_bwd_kernel', ('ot_rmsnorm_bwd',)), ('rmsnorm_fwd_kernel', ('ot_rmsnorm_fwd',)),
+            ('ot_attn_cached_kernel', ('ot_attn_ns_cached_fwd',))]
+    launches = json.load(open(sys.argv[4]))
+    out = json.load(open(sys.argv[3]))
+    def num(r, m):
+        return float(r[hdr.index(m)].replace(',', '')) if m in hdr and r[hdr.index(m)] not in ('', 'n/a') else None
+    def gbv(r, m):
+        v, u = float(r[hdr.index(m)].replace(',', '')), units[hdr.index(m)]
+        return v * {'Gbyte': 1e9, 'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1.0, 'Tbyte': 1e12}[u]
+    li = 0
+    for i, r in enumerate(data):
+        name = r[hdr.index('Kernel Name')]
+        fams = next((f for k, f in MAIN if k in name), None)
+        if fams is None:
+            continue
+        while li < len(launches) and launches[li]['kernel'] not in fams:
+            li += 1
+        if li == len(launches):
+            break
+        l = launches[li]
+        li += 1
+        t = gbv(r, 'dram__bytes_read.sum') + gbv(r, 'dram__bytes_write.sum')
+        out[f"{l['kernel']}[{l['tag']}]"] = {
+            'dram_bytes': t, 'algorithmic_bytes': l['bytes'], 'traffic_over_algorithmic': t / l['bytes'] if l['bytes'] else None,
+            'capture': f'{out_csv} row {i} (ncu --set full --clock-control none, profiles/prof_kernels.py all, PROF_ONCE=1; main kernel of the call)',
+            'time_ms': num(r, 'gpu__time_duration.sum') * {'ms': 1.0, 'us': 1e-3, 'ns': 1e-6, 's': 1e3}[units[hdr.index('gpu__time_duration.sum')]],
+            'tensor_pipe_pct': num(r, 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active'),
+            'xu_pipe_pct': num(r, 'sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active'),
+            'issue_active_pct': num(r, 'smsp__issue_active.avg.pct_of_peak_sustained_active'),
+            'lts_throughput_pct': num(r, 'lts__throughput.avg.pct_of_peak_sustained_elapsed'),
+            'l2_to_sm_read_bytes': gbv(r, 'l1tex__m_xbar2l1tex_read_bytes.sum') if 'l1tex__m_xbar2l1tex_read_bytes.sum' in hdr else None}
+    json.dump(out, open(sys.argv[3], 'w'), indent=1)
+    print('joined', li, 'of', len(launches), 'library calls')
