@@ -227,6 +227,34 @@ def test_attention_head_dim_32(B, H, Lq, Lk):
     test_attention_forward_backward(B, H, 32, Lq, Lk)
 
 
+@pytest.mark.parametrize('B,Lq,Lk', [(296, 458, 544), (160, 373, 458), (512, 117, 202)])
+def test_attention_repeatable(B, Lq, Lk):
+    """Race detector for the hand-rolled mbarrier pipelines of the attention kernels (forward v3, backward v2): many (sample, head)
+    items per CTA, repeated launches.  The forward and dK / dV have a fixed summation order, so every repeat must be BIT-identical
+    to the first; dQ is accumulated with bf16 reductions in item order and may only differ at the rounding level."""
+    H, dh = 4, 64
+    d = H * dh
+    q = rnd(Lq * B, d, seed=31)
+    kv = rnd(Lk * B, 2 * d, seed=32)
+    do = rnd(Lq * B, d, seed=33)
+    outs = []
+    for rep in range(6):
+        o = torch.empty(Lq * B, d, dtype=bf16, device='cuda')
+        lse = torch.empty(B * H * Lq, device='cuda')
+        ops.attn_fwd(q, kv[:, :d], kv[:, d:], o, lse, B, H, Lq, Lk, dh)
+        dq = torch.empty_like(q)
+        dkv = torch.full_like(kv, float('nan'))
+        delta = torch.empty(B * H * Lq, device='cuda')
+        ops.attn_bwd(q, kv[:, :d], kv[:, d:], o, lse, do, dq, dkv[:, :d], dkv[:, d:], delta, B, H, Lq, Lk, dh)
+        outs.append((o, lse, dkv, dq))
+    o0, lse0, dkv0, dq0 = outs[0]
+    assert torch.isfinite(dkv0.float()).all() and torch.isfinite(dq0.float()).all()
+    for o, lse, dkv, dq in outs[1:]:
+        assert torch.equal(o, o0) and torch.equal(lse, lse0)
+        assert torch.equal(dkv, dkv0)
+        assert ((dq.float() - dq0.float()).norm() / dq0.float().norm()).item() < 1e-2
+
+
 def test_unsupported_head_dim_is_an_error():
     q = rnd(8, 64, seed=1)
     o = torch.empty_like(q)
