@@ -220,6 +220,15 @@ def test_attention_forward_backward(B, H, dh, Lq, Lk):
         assert ((got.float() - ref).norm() / (ref.norm() + 1e-3 * do.float().norm())).item() < 2e-2
 
 
+@pytest.mark.parametrize('B,H,Lq,Lk', [(3, 8, 129, 129), (2, 4, 256, 256), (2, 4, 257, 300), (7, 1, 130, 515), (1, 2, 512, 513), (4, 4, 96, 1000),
+                                       (2, 4, 193, 193), (3, 4, 385, 400)])
+def test_attention_tile_boundaries(B, H, Lq, Lk):
+    """Shapes that sit on the edges of the head_dim-64 kernels' tiling: a second query tile of one row (forward v3 pair with an almost
+    empty tile B), exact multiples of 128, no causal offset (Lq == Lk), one head, eight heads, a short query tail over a long key
+    range (backward items of a single step), an odd number of query tiles.  Same checks as test_attention_forward_backward."""
+    test_attention_forward_backward(B, H, 64, Lq, Lk)
+
+
 @pytest.mark.parametrize('B,H,Lq,Lk', [(3, 4, 202, 288), (2, 4, 17, 21), (1, 8, 300, 300)])
 def test_attention_head_dim_32(B, H, Lq, Lk):
     """The reference's example scripts use hidden_dim 128 with 4 heads (OT/model.py:420-442, OT/examples/train_example.py:22-27):
