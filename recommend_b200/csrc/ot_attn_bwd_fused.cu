@@ -364,8 +364,7 @@ ot_attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       tc_fence_after();
       const StepInfo si = info[g & (Cfg::INFO_SLOTS - 1)];
       end = (si.flags & SI_END) != 0;
-      const bool first_of_item = si.flags & SI_FIRST, last_of_item = si.flags & SI_LAST;
-      const int q0 = si.q0, k0 = si.k0, b = si.b, h = si.h;
+      const int q0 = si.q0, k0 = si.k0;
       const bool row_valid = (q0 + row) < p.Lq;
       const int pq = off + q0 + row;
       const float lse2 = lse_raw * kLog2eF;
