@@ -2,6 +2,7 @@ import torch, sys
 sys.path.insert(0, ".")
 from recommend_b200 import ops
 bf16=torch.bfloat16
+import os
 for (Lq,Lk) in [(458,544),(373,458),(288,373),(202,288),(117,202),(32,117)]:
     B,H,dh=2048,4,64; d=H*dh
     g=torch.Generator(device="cuda").manual_seed(0)

@@ -267,6 +267,7 @@ int make_head_tmap(CUtensorMap* tm, const void* base, int cols, int B, int L, lo
 int attn_fwd_ws_impl(const ot_attn_params* p, cudaStream_t st);   // ot_attn_fwd_ws.cu (head_dim 64, round-1 structure)
 int attn_fwd_v2_impl(const ot_attn_params* p, cudaStream_t st);   // ot_attn_fwd_v2.cu (head_dim 64, round-2 structure)
 int attn_fwd_v3_impl(const ot_attn_params* p, cudaStream_t st);   // ot_attn_fwd_v3.cu (head_dim 64, P in tensor memory)
+int attn_fwd_v4_impl(const ot_attn_params* p, cudaStream_t st);   // ot_attn_fwd_v4.cu (head_dim 64, two independent tile streams per CTA)
 
 int attn_fwd_impl(const ot_attn_params* p, cudaStream_t st) {
   if (!p || !p->q || !p->k || !p->v || !p->o || !p->lse) OT_FAIL(OT_ERR_INVALID_ARG, "ot_attn_fwd: null pointer");
@@ -277,12 +278,16 @@ int attn_fwd_impl(const ot_attn_params* p, cudaStream_t st) {
   const int swb = (p->head_dim == 64 && p->swizzle != 64) ? 128 : 64;
   if (p->head_dim == 64 && swb == 128 && p->swizzle != 128) {   // swizzle=128 forces the simple kernel
     // OT_ATTN_FWD_IMPL (read once) forces one structure for A/B runs: 1 = round-1 warp-specialised kernel, 2 = v2 (P through shared
-    // memory), 3 = v3 (P in tensor memory, TS-form P V).  Unset: v3 when a (sample, head) has more than one query tile, else 1.
+    // memory), 3 = v3 (P in tensor memory, TS-form P V, two tiles of a (sample, head) in lockstep over a shared K/V stream), 4 = v4 (two
+    // independent tile streams per CTA).  Unset: v3 when a (sample, head) has more than one query tile - sharing the K/V stream halves
+    // the TMA row requests, and v4 measured slower there (1.09 vs 0.96 ms at layer 0) although its slots are balanced; v4 for one-tile
+    // shapes, where v3 would leave half of the CTA idle (0.18 vs 0.22 ms for the 16-warp round-1 kernel at Lq 117).
     static const int impl = [] { const char* e = getenv("OT_ATTN_FWD_IMPL"); return e ? atoi(e) : 0; }();
     if (impl == 1) return attn_fwd_ws_impl(p, st);
     if (impl == 2) return attn_fwd_v2_impl(p, st);
     if (impl == 3) return attn_fwd_v3_impl(p, st);
-    return p->Lq > 128 ? attn_fwd_v3_impl(p, st) : attn_fwd_ws_impl(p, st);   // one query tile per (sample, head): the 16-warp round-1 kernel is faster (in-bench A/B)
+    if (impl == 4) return attn_fwd_v4_impl(p, st);
+    return p->Lq > 128 ? attn_fwd_v3_impl(p, st) : attn_fwd_v4_impl(p, st);
   }
   const int cols = p->H * p->head_dim;
   CUtensorMap tq, tk, tv;

@@ -14,7 +14,7 @@
 // one (sample, head) share every K/V block).  Registers re-balanced with setmaxnreg (40 / 72 / 200).
 // TMEM: S_A 0, S_B 128, O_A 256, O_B 320, P_A 384, P_B 448 (64 columns hold 128 bf16 probabilities per row).
 // SMEM: Q 2 items x 2 tiles, K/V 4 stages, one 16 KB output staging tile, row statistics, step ring, mbarriers.
-#include "ot_attn.cuh"
+#include "ot_attn_fwd_common.cuh"
 #include "ot_host.h"
 #include "../../include/onetrans_b200.h"
 
@@ -42,10 +42,6 @@ static constexpr int F3_OFF_BARS = F3_OFF_INFO + F3_INFO_SLOTS * 16;
 static constexpr int F3_SMEM_BYTES = F3_OFF_BARS + 512;
 static_assert(F3_SMEM_BYTES <= 227 * 1024, "shared memory budget");
 static constexpr uint32_t F3_T_S = 0, F3_T_O = 256, F3_T_P = 384;     // + tile * 128 / + tile * 64 / + tile * 64
-static constexpr float F3_TAU = 8.0f;                                  // lazy rescale threshold, log2 units
-#ifndef OT_F3_POLY
-#define OT_F3_POLY 0      // pairs (of the four in a group of eight exponentials) evaluated by the FMA-pipe polynomial: 0 .. 4
-#endif
 // mbarrier byte offsets inside the barrier block
 enum : uint32_t {
   B3_Q = 0,          // [2] Q tiles of an item landed                        (loader -> MMA)
@@ -65,74 +61,6 @@ enum : uint32_t {
 enum { F3_FIRST = 1, F3_A = 2, F3_B = 4, F3_LAST_A = 8, F3_LAST_B = 16, F3_END = 32, F3_QBUF = 64 };
 // step info, 16 bytes: x = q0 | j << 16, y = b, z = h | flags << 8, w = nA | nB << 8
 //   nA / nB: key columns of this block that some row of tile A / B can see, rounded up to 16 (0: tile idle in this step)
-
-// ---- shared-memory-address forms of the mbarrier helpers (no generic-to-shared conversion in the inner loops) ----
-__device__ __forceinline__ void mbar_arrive_s(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_s(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}\n"
-               : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-  if (ok) return;
-  uint32_t spins = 0;
-  do {
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.b32 %0, 1, 0, p;\n\t}\n"
-                 : "=r"(ok) : "r"(bar), "r"(parity), "r"(20000u) : "memory");
-#if OT_HANG_GUARD
-    if (++spins > (1u << 17)) __trap();
-#endif
-  } while (!ok);
-}
-__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2) {
-  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
-               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
-
-// One 32-column chunk of a score row -> probabilities (packed bf16 pairs) and partial row sums, software-pipelined in groups of
-// eight (arguments of group g+1 and sums / packs of group g-1 around the exponentials of group g).  The mask-free form works on
-// packed fp32 pairs (FFMA2 for the arguments, FADD2 for the row sums: half the issue slots of the scalar form).
-template <bool MASK>
-__device__ __forceinline__ void f3_softmax_chunk(const uint32_t (&s)[32], uint32_t (&pk)[16], float scale_log2, float mb, int lim_rel,
-                                                 f32x2 (&rs)[2]) {
-  float a[32];
-  const f32x2 c2 = pk2(scale_log2), nmb2 = pk2(-mb);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) upk2(fma2(pk2(__uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1])), c2, nmb2), a[2 * i], a[2 * i + 1]);
-#pragma unroll
-  for (int g = 0; g < 5; ++g) {
-    if (g + 1 < 4) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-        upk2(fma2(pk2(__uint_as_float(s[(g + 1) * 8 + 2 * i]), __uint_as_float(s[(g + 1) * 8 + 2 * i + 1])), c2, nmb2), a[(g + 1) * 8 + 2 * i],
-             a[(g + 1) * 8 + 2 * i + 1]);
-    }
-    if (g < 4) {
-      // exponentials of group g: OT_F3_POLY of its four pairs go to the FMA-pipe polynomial, the rest to the XU pipe
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        if (i >= 4 - OT_F3_POLY) {
-          upk2(ex2_poly2(pk2(a[g * 8 + 2 * i], a[g * 8 + 2 * i + 1])), a[g * 8 + 2 * i], a[g * 8 + 2 * i + 1]);
-        } else {
-          a[g * 8 + 2 * i] = ex2_approx(a[g * 8 + 2 * i]);
-          a[g * 8 + 2 * i + 1] = ex2_approx(a[g * 8 + 2 * i + 1]);
-        }
-      }
-    }
-    if (g >= 1) {
-      const int b0 = (g - 1) * 8;
-      if (MASK) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) a[b0 + i] = (b0 + i <= lim_rel) ? a[b0 + i] : 0.0f;
-      }
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        rs[i & 1] = add2(rs[i & 1], pk2(a[b0 + 2 * i], a[b0 + 2 * i + 1]));
-        pk[(b0 >> 1) + i] = pack_bf16x2(a[b0 + 2 * i], a[b0 + 2 * i + 1]);
-      }
-    }
-  }
-}
 
 __global__ void __launch_bounds__(F3_THREADS, 1)
 ot_attn_fwd_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
