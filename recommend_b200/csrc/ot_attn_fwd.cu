@@ -268,6 +268,7 @@ int attn_fwd_ws_impl(const ot_attn_params* p, cudaStream_t st);   // ot_attn_fwd
 int attn_fwd_v2_impl(const ot_attn_params* p, cudaStream_t st);   // ot_attn_fwd_v2.cu (head_dim 64, round-2 structure)
 int attn_fwd_v3_impl(const ot_attn_params* p, cudaStream_t st);   // ot_attn_fwd_v3.cu (head_dim 64, P in tensor memory)
 int attn_fwd_v4_impl(const ot_attn_params* p, cudaStream_t st);   // ot_attn_fwd_v4.cu (head_dim 64, two independent tile streams per CTA)
+int attn_fwd_v5_impl(const ot_attn_params* p, cudaStream_t st);   // ot_attn_fwd_v5.cu (head_dim 64, v3 pipeline with a balanced step schedule)
 
 int attn_fwd_impl(const ot_attn_params* p, cudaStream_t st) {
   if (!p || !p->q || !p->k || !p->v || !p->o || !p->lse) OT_FAIL(OT_ERR_INVALID_ARG, "ot_attn_fwd: null pointer");
@@ -278,16 +279,18 @@ int attn_fwd_impl(const ot_attn_params* p, cudaStream_t st) {
   const int swb = (p->head_dim == 64 && p->swizzle != 64) ? 128 : 64;
   if (p->head_dim == 64 && swb == 128 && p->swizzle != 128) {   // swizzle=128 forces the simple kernel
     // OT_ATTN_FWD_IMPL (read once) forces one structure for A/B runs: 1 = round-1 warp-specialised kernel, 2 = v2 (P through shared
-    // memory), 3 = v3 (P in tensor memory, TS-form P V, two tiles of a (sample, head) in lockstep over a shared K/V stream), 4 = v4 (two
-    // independent tile streams per CTA).  Unset: v3 when a (sample, head) has more than one query tile - sharing the K/V stream halves
-    // the TMA row requests, and v4 measured slower there (1.09 vs 0.96 ms at layer 0) although its slots are balanced; v4 for one-tile
-    // shapes, where v3 would leave half of the CTA idle (0.18 vs 0.22 ms for the 16-warp round-1 kernel at Lq 117).
+    // memory), 3 = v3 (P in tensor memory, TS-form P V, tiles 2p / 2p+1 of a (sample, head) in lockstep over a shared K/V stream), 4 = v4
+    // (two independent tile streams per CTA), 5 = v5 (v3 with a balanced step schedule).  Unset, by the number of query tiles of a
+    // (sample, head), measured on one box (profiles/README.md): one tile -> v4 (v3 / v5 would idle half of the CTA); two tiles -> v3 (the
+    // schedules coincide, v5's per-step bookkeeping costs 7-12 %); three or more -> v5 (0.66 vs 0.76 ms at three tiles, 0.94 vs 0.96 at four).
     static const int impl = [] { const char* e = getenv("OT_ATTN_FWD_IMPL"); return e ? atoi(e) : 0; }();
     if (impl == 1) return attn_fwd_ws_impl(p, st);
     if (impl == 2) return attn_fwd_v2_impl(p, st);
     if (impl == 3) return attn_fwd_v3_impl(p, st);
     if (impl == 4) return attn_fwd_v4_impl(p, st);
-    return p->Lq > 128 ? attn_fwd_v3_impl(p, st) : attn_fwd_v4_impl(p, st);
+    if (impl == 5) return attn_fwd_v5_impl(p, st);
+    if (p->Lq <= 128) return attn_fwd_v4_impl(p, st);
+    return p->Lq <= 256 ? attn_fwd_v3_impl(p, st) : attn_fwd_v5_impl(p, st);
   }
   const int cols = p->H * p->head_dim;
   CUtensorMap tq, tk, tv;
