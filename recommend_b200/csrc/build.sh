@@ -4,6 +4,9 @@ set -e
 cd "$(dirname "$0")"
 mkdir -p ../lib obj
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC ${OT_NVCC_EXTRA}"
+# objects are rebuilt when a source is newer - and all of them when the flags differ from the last build's (a debug build with
+# OT_NVCC_EXTRA must not leave its objects behind for the next plain build)
+if [ ! -f obj/.flags ] || [ "$(cat obj/.flags)" != "$FLAGS" ]; then rm -f obj/*.o; echo "$FLAGS" > obj/.flags; fi
 pids=()
 for f in ot_api ot_gemm ot_ffn_fused ot_wgrad ot_attn_fwd ot_attn_fwd_ws ot_attn_fwd_v2 ot_attn_fwd_v3 ot_attn_fwd_v4 ot_attn_fwd_v5 ot_attn_bwd ot_attn_bwd_fused ot_attn_bwd_v2 ot_attn_cached ot_elementwise ot_optimizer ot_embedding ot_heads ot_metrics; do
   if [ -f $f.cu ]; then

@@ -10,6 +10,25 @@ static constexpr float F3_TAU = 8.0f;                                  // lazy r
 #define OT_F3_POLY 0      // pairs (of the four in a group of eight exponentials) evaluated by the FMA-pipe polynomial: 0 .. 4
 #endif
 
+// OT_HANG_DEBUG=1 (compile time, debugging only): a wait that runs into the hang guard records who waited for what in a device-side
+// record (first writer wins) and then carries on as if the wait had succeeded, so that the launch ends and the record can be read
+// (ot_debug_hang_read, exported by ot_attn_fwd_v4.cu) instead of the context dying in a trap.
+#ifndef OT_HANG_DEBUG
+#define OT_HANG_DEBUG 0
+#endif
+#if OT_HANG_DEBUG
+static __device__ unsigned int ot_hang_rec[64];     // [0] claiming block + 1, [1] entries, then (thread | what << 16, a, b) per entry of that block
+__device__ __forceinline__ void ot_hang_note(uint32_t what, uint32_t a, uint32_t b) {
+  if ((threadIdx.x & 31u) != 0u && what == 1u && __activemask() != 1u) return;   // one record per warp
+  const unsigned int me = blockIdx.x + 1u;
+  const unsigned int owner = atomicCAS(&ot_hang_rec[0], 0u, me);
+  if (owner == 0u || owner == me) {
+    const unsigned int i = atomicAdd(&ot_hang_rec[1], 1u);
+    if (i < 20u) { ot_hang_rec[2 + 3 * i] = threadIdx.x | (what << 16); ot_hang_rec[3 + 3 * i] = a; ot_hang_rec[4 + 3 * i] = b; }
+  }
+}
+#endif
+
 // ---- shared-memory-address forms of the mbarrier helpers (no generic-to-shared conversion in the inner loops) ----
 __device__ __forceinline__ void mbar_arrive_s(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -23,7 +42,9 @@ __device__ __forceinline__ void mbar_wait_s(uint32_t bar, uint32_t parity) {
   do {
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.b32 %0, 1, 0, p;\n\t}\n"
                  : "=r"(ok) : "r"(bar), "r"(parity), "r"(20000u) : "memory");
-#if OT_HANG_GUARD
+#if OT_HANG_DEBUG
+    if (++spins > (1u << 12)) { ot_hang_note(1u, bar, parity); return; }
+#elif OT_HANG_GUARD
     if (++spins > (1u << 17)) __trap();
 #endif
   } while (!ok);

@@ -204,17 +204,34 @@ ot_attn_fwd_v4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           umma_commit(bar_ptr(S4_KFREE + 8 * st));
           if (flags & G4_LAST) umma_commit(bar_ptr(S4_QFREE + 8 * qb));     // the tile's last S product: its Q buffer is free when this completes
         };
+        auto info_ready = [&](uint32_t t) { return mbar_test_s(sb + S4_IFULL + 8 * (t & 3), (t >> 2) & 1); };
         uint32_t t = 0;
         int4 cur = wait_info(0);
         if (!((cur.z >> 8) & G4_END)) {
           issue_s(cur, 0);
           while (true) {
             const int cf = (cur.z >> 8) & 0xff;
-            const int4 nxt = wait_info(t + 1);
-            const bool end = ((nxt.z >> 8) & G4_END) != 0;
-            // S of the next step as soon as this step's scores have left TMEM (it runs under this step's exponentials) ...
-            mbar_wait_s(sb + S4_SFREE, t & 1);
-            if (!end) issue_s(nxt, t + 1);
+            // S of the next step as soon as this step's scores have left TMEM (it runs under this step's exponentials) - but only if
+            // the loader has already published that step.  The issuer must never BLOCK on the next step's info before this step's
+            // P V is out: the loaders are coupled through the (sample, head) ring, so loader A can be held by loader B, B by its own
+            // slot, that slot by the epilogue, and the epilogue by the P V of slot A's finished tile - a cycle when that P V waits for
+            // loader A (seen with many one-step tiles per CTA: B 4096, Lq <= 24).
+            int4 nxt = make_int4(0, 0, 0, 0);
+            bool have_nxt = false, s_issued = false;
+            // So: poll for whichever comes first, the next step's info (normal case: its S goes out now) or this step's probabilities.
+            while (true) {
+              if (info_ready(t + 1)) {
+                nxt = wait_info(t + 1);
+                have_nxt = true;
+                if (!((nxt.z >> 8) & G4_END)) {
+                  mbar_wait_s(sb + S4_SFREE, t & 1);
+                  issue_s(nxt, t + 1);
+                  s_issued = true;
+                }
+                break;
+              }
+              if (mbar_test_s(sb + S4_P, t & 1)) break;
+            }
             // ... then P V of this step when its probabilities arrive
             mbar_wait_s(sb + S4_P, t & 1);
             if ((cf & G4_FIRST) && fin > 0) mbar_wait_s(sb + S4_OFREE, (fin - 1) & 1);     // the previous tile's O is out
@@ -230,7 +247,12 @@ ot_attn_fwd_v4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
             umma_commit(bar_ptr(S4_O));
             umma_commit(bar_ptr(S4_VFREE + 8 * (t & 1)));
             if (cf & G4_LAST) ++fin;
-            if (end) break;
+            if (!have_nxt) nxt = wait_info(t + 1);
+            if ((nxt.z >> 8) & G4_END) break;
+            if (!s_issued) {
+              mbar_wait_s(sb + S4_SFREE, t & 1);
+              issue_s(nxt, t + 1);
+            }
             cur = nxt;
             ++t;
           }
@@ -258,7 +280,9 @@ ot_attn_fwd_v4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           else if (!done[1] && mbar_test_s(bars + C4_SLOT0 + F4_SLOT_BARS + S4_STATS, fin[1] & 1)) sel = 1;
           else {
             __nanosleep(100);
-#if OT_HANG_GUARD
+#if OT_HANG_DEBUG
+            if (++spins > (1u << 18)) { ot_hang_note(2u, fin[0], fin[1]); sel = done[0] ? 1 : 0; }
+#elif OT_HANG_GUARD
             if (++spins > (1u << 25)) __trap();
 #endif
           }
@@ -365,7 +389,7 @@ ot_attn_fwd_v4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 
       bool waited_o = (n == 0);                                     // nothing to wait for before the very first P of this slot
       if (warp_valid) {
-        // ---- row maximum (four independent partial maxima; mask-free: an upper bound over the computed columns is a valid reference) ----
+        // ---- row maximum (four independent partial maxima) ----
         float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -373,12 +397,13 @@ ot_attn_fwd_v4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 #pragma unroll
             for (int i = 0; i < 32; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(s[c][i]));
           } else if (vis[c] == 1) {
+            // cut by the diagonal: only the columns this row may see enter the maximum (one compare per element on the one or two
+            // chunks of a block the diagonal crosses).  A maximum over hidden columns would also be a valid reference, and was 4 %
+            // faster, but it lets the rounding of a row depend on LATER keys - the bit-exact causality the tests pin (T6) is worth more
+            const int lim_c = lim - c * 32;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(s[c][i]));
-            if (c * 32 + 16 < ncols) {
-#pragma unroll
-              for (int i = 16; i < 32; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(s[c][i]));
-            }
+            for (int i = 0; i < 32; ++i)
+              if (i <= lim_c) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(s[c][i]));
           }
         }
         const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
@@ -464,6 +489,17 @@ ot_attn_fwd_v4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 }
 
 int make_head_tmap(CUtensorMap* tm, const void* base, int cols, int B, int L, long long ld, int swb);
+
+#if OT_HANG_DEBUG
+}  // namespace ot
+extern "C" int ot_debug_hang_read(unsigned int* out8 /* [64] */) {     // debugging builds only: the record of the first wait that gave up, then cleared
+  unsigned int z[64] = {0};
+  cudaDeviceSynchronize();
+  if (cudaMemcpyFromSymbol(out8, ot::ot_hang_rec, sizeof(z)) != cudaSuccess) return -1;
+  return cudaMemcpyToSymbol(ot::ot_hang_rec, z, sizeof(z)) == cudaSuccess ? 0 : -1;
+}
+namespace ot {
+#endif
 
 int attn_fwd_v4_impl(const ot_attn_params* p, cudaStream_t st) {
   const int cols = p->H * p->head_dim;

@@ -197,7 +197,10 @@ def attn_ref(q, k, v, B, H, Lq, Lk, dh):
 
 @pytest.mark.parametrize('B,H,dh,Lq,Lk', [(3, 4, 64, 202, 288), (2, 4, 64, 458, 544), (5, 4, 64, 13, 27), (1, 4, 64, 8, 13),
                                            (2, 4, 96, 224, 288), (2, 2, 64, 1, 1), (1, 4, 64, 1024, 2048), (3, 4, 64, 373, 458),
-                                           (40, 4, 64, 300, 300), (2, 4, 64, 640, 700)])
+                                           (40, 4, 64, 300, 300), (2, 4, 64, 640, 700),
+                                           # many one-step tiles per CTA (110 per CTA, two slots): the shapes that dead-locked forward v4's
+                                           # (sample, head) ring against its shared epilogue
+                                           (4096, 4, 64, 8, 24), (4096, 4, 64, 24, 40)])
 def test_attention_forward_backward(B, H, dh, Lq, Lk):
     d = H * dh
     q = rnd(Lq * B, d, seed=13)
