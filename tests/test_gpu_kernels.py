@@ -232,6 +232,28 @@ def test_attention_tile_boundaries(B, H, Lq, Lk):
     test_attention_forward_backward(B, H, 64, Lq, Lk)
 
 
+def _random_attention_shape(seed):
+    """Seeded shape for test_attention_random_shapes: query tails from 1 to 700 rows over key ranges up to 1200, batch sizes chosen
+    so that a CTA sees from one to a few hundred (sample, head) items, bounded by the fp32 reference's score tensor (64 M elements)."""
+    import random
+    r = random.Random(1000 + seed)
+    H = r.choice([1, 2, 4, 4, 4, 8])
+    Lq = r.choice([r.randint(1, 40), r.randint(41, 128), r.randint(129, 256), r.randint(257, 700)])
+    Lk = Lq + r.choice([0, r.randint(0, 16), r.randint(17, 200), r.randint(0, 500)])
+    cap = max(1, (64 << 20) // (H * Lq * Lk))
+    B = min(cap, r.choice([1, r.randint(2, 40), r.randint(100, 600), r.randint(1000, 5000)]))
+    return B, H, Lq, Lk
+
+
+@pytest.mark.parametrize('seed', range(32))
+def test_attention_random_shapes(seed):
+    """Shape sweep over the head_dim-64 attention kernels (forward v3 / v4 / v5 by tile count, backward v2): every role of these
+    kernels waits on hand-rolled mbarrier rings, and a protocol error can hide behind the shapes one happens to test (forward v4
+    dead-locked only with > 100 one-step tiles per CTA).  Same checks as test_attention_forward_backward."""
+    B, H, Lq, Lk = _random_attention_shape(seed)
+    test_attention_forward_backward(B, H, 64, Lq, Lk)
+
+
 @pytest.mark.parametrize('B,H,Lq,Lk', [(3, 4, 202, 288), (2, 4, 17, 21), (1, 8, 300, 300)])
 def test_attention_head_dim_32(B, H, Lq, Lk):
     """The reference's example scripts use hidden_dim 128 with 4 heads (OT/model.py:420-442, OT/examples/train_example.py:22-27):
