@@ -16,7 +16,7 @@ METRICS = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.
            'smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio',
            'smsp__average_warps_issue_stalled_wait_per_issue_active.ratio']
 FAMILY = {'ot_mixed_gemm_kernel': 'ot_mixed_gemm', 'ot_ffn_fused_kernel': 'ot_ffn_fwd', 'ot_wgrad_kernel': 'ot_wgrad', 'ot_attn_fwd_ws_kernel': 'ot_attn_fwd',
-          'ot_attn_fwd_v2_kernel': 'ot_attn_fwd', 'ot_attn_fwd_v3_kernel': 'ot_attn_fwd', 'ot_attn_bwd_v2_kernel': 'ot_attn_bwd', 'ot_attn_cached_kernel': 'ot_attn_ns_cached_fwd', 'ot_attn_dkv_kernel': 'ot_attn_bwd', 'ot_attn_dq_kernel': 'ot_attn_bwd',
+          'ot_attn_fwd_v2_kernel': 'ot_attn_fwd', 'ot_attn_fwd_v3_kernel': 'ot_attn_fwd', 'ot_attn_fwd_v4_kernel': 'ot_attn_fwd', 'ot_attn_fwd_v5_kernel': 'ot_attn_fwd', 'ot_attn_bwd_v2_kernel': 'ot_attn_bwd', 'ot_attn_cached_kernel': 'ot_attn_ns_cached_fwd', 'ot_attn_dkv_kernel': 'ot_attn_bwd', 'ot_attn_dq_kernel': 'ot_attn_bwd',
           'ot_attn_fwd_kernel': 'ot_attn_fwd', 'ot_attn_bwd_fused_kernel': 'ot_attn_bwd', 'rmsnorm_fwd_kernel': 'ot_rmsnorm_fwd',
           'rmsnorm_bwd_kernel': 'ot_rmsnorm_bwd'}
 
@@ -71,14 +71,15 @@ if len(sys.argv) > 5:
     tp = 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active'
     def row_of(kname):
         return next(((i, r) for i, r in enumerate(data) if kname in r[hdr.index('Kernel Name')]), (None, None))
-    (i_f, r_f), (i_b, r_b) = row_of('ot_attn_fwd_v3_kernel'), row_of('ot_attn_bwd_v2_kernel')
+    fwd_name = next((k for k in ('ot_attn_fwd_v5_kernel', 'ot_attn_fwd_v3_kernel') if row_of(k)[1]), 'ot_attn_fwd_v3_kernel')   # layer 0: v5 since the tile-count dispatch
+    (i_f, r_f), (i_b, r_b) = row_of(fwd_name), row_of('ot_attn_bwd_v2_kernel')
     if r_f and r_b and tp in hdr:
         def ms(r):
             return float(r[hdr.index('gpu__time_duration.sum')].replace(',', '')) * {'ms': 1.0, 'us': 1e-3, 'ns': 1e-6, 's': 1e3}[units[hdr.index('gpu__time_duration.sum')]]
         f, b = float(r_f[hdr.index(tp)]), float(r_b[hdr.index(tp)])
         json.dump({'attn_tensor_pipe_util_pct': {'ot_attn_fwd[Lq458_Lk544]': f, 'ot_attn_bwd[Lq458_Lk544]': b,
                                                  'time_weighted': (f * ms(r_f) + b * ms(r_b)) / (ms(r_f) + ms(r_b)), 'metric': tp,
-                                                 'source': f'{out_csv} rows {i_f} and {i_b} (ot_attn_fwd_v3_kernel, ot_attn_bwd_v2_kernel; C2 layer 0: B 2048, H 4, '
+                                                 'source': f'{out_csv} rows {i_f} and {i_b} ({fwd_name}, ot_attn_bwd_v2_kernel; C2 layer 0: B 2048, H 4, '
                                                            'Lq 458, Lk 544, head_dim 64), same build as the bench'}},
                   open(sys.argv[5], 'w'), indent=1)
         print('wrote', sys.argv[5])
@@ -87,7 +88,7 @@ if len(sys.argv) > 5:
 # backward and the second kernel of the two-kernel head_dim-96 backward are attributed to the same call) ----
 if len(sys.argv) > 4:
     MAIN = [('ot_mixed_gemm_kernel', ('ot_mixed_gemm',)), ('ot_ffn_fused_kernel', ('ot_ffn_fwd', 'ot_ffn_bwd')), ('ot_wgrad_kernel', ('ot_wgrad',)),
-            ('ot_attn_fwd_v3_kernel', ('ot_attn_fwd',)), ('ot_attn_fwd_ws_kernel', ('ot_attn_fwd',)), ('ot_attn_fwd_v2_kernel', ('ot_attn_fwd',)),
+            ('ot_attn_fwd_v5_kernel', ('ot_attn_fwd',)), ('ot_attn_fwd_v4_kernel', ('ot_attn_fwd',)), ('ot_attn_fwd_v3_kernel', ('ot_attn_fwd',)), ('ot_attn_fwd_ws_kernel', ('ot_attn_fwd',)), ('ot_attn_fwd_v2_kernel', ('ot_attn_fwd',)),
             ('ot_attn_fwd_kernel', ('ot_attn_fwd',)), ('ot_attn_bwd_v2_kernel', ('ot_attn_bwd',)), ('ot_attn_bwd_fused_kernel', ('ot_attn_bwd',)),
             ('ot_attn_dkv_kernel', ('ot_attn_bwd',)), ('rmsnorm_bwd_kernel', ('ot_rmsnorm_bwd',)), ('rmsnorm_fwd_kernel', ('ot_rmsnorm_fwd',)),
             ('ot_attn_cached_kernel', ('ot_attn_ns_cached_fwd',))]
