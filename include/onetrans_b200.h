@@ -207,7 +207,7 @@ typedef struct ot_attn_params {
   void* dv; int64_t lddv;
   float* delta;
   int32_t B, H, Lq, Lk;
-  int32_t head_dim;      /* 64 or 96 */
+  int32_t head_dim;      /* 32, 64 or 96 */
   int32_t swizzle;       /* 0 = default; 64 forces the 64-byte-swizzle variant for head_dim 64 */
 } ot_attn_params;
 
