@@ -397,13 +397,15 @@ ot_attn_fwd_v4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 #pragma unroll
             for (int i = 0; i < 32; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(s[c][i]));
           } else if (vis[c] == 1) {
-            // cut by the diagonal: only the columns this row may see enter the maximum (one compare per element on the one or two
-            // chunks of a block the diagonal crosses).  A maximum over hidden columns would also be a valid reference, and was 4 %
-            // faster, but it lets the rounding of a row depend on LATER keys - the bit-exact causality the tests pin (T6) is worth more
+            // cut by the diagonal: the scores this row may not see are replaced by -inf HERE, once - they then drop out of the maximum
+            // (a maximum over hidden columns would let the rounding of a row depend on LATER keys: the bit-exact causality the tests
+            // pin, T6) and give exactly 0 in the exponentials below, which therefore take the mask-free packed path for this chunk too
             const int lim_c = lim - c * 32;
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (i <= lim_c) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(s[c][i]));
+            for (int i = 0; i < 32; ++i) {
+              s[c][i] = (i <= lim_c) ? s[c][i] : 0xff800000u;
+              mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(s[c][i]));
+            }
           }
         }
         const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
@@ -438,10 +440,8 @@ ot_attn_fwd_v4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       for (int c = 0; c < 4; ++c) {
         if (c * 32 < ncols) {
           uint32_t pk[16];
-          if (vis[c] == 2) {
+          if (vis[c] != 0) {                                          // hidden scores of a cut chunk are -inf by now: 2^(-inf) = 0
             f3_softmax_chunk<false>(s[c], pk, p.scale_log2, mb, 0, rs4);
-          } else if (vis[c] == 1) {
-            f3_softmax_chunk<true>(s[c], pk, p.scale_log2, mb, lim - c * 32, rs4);
           } else {
 #pragma unroll
             for (int i = 0; i < 16; ++i) pk[i] = 0u;
