@@ -7,7 +7,8 @@ namespace ot {
 
 static constexpr float F3_TAU = 8.0f;                                  // lazy rescale threshold, log2 units
 #ifndef OT_F3_POLY
-#define OT_F3_POLY 0      // pairs (of the four in a group of eight exponentials) evaluated by the FMA-pipe polynomial: 0 .. 4
+#define OT_F3_POLY 0      // pairs (of the four in a group of eight exponentials) evaluated by the FMA-pipe polynomial: 0 .. 4 (experiment;
+                          // measured slower.  The kernels now pass -inf for hidden scores, which only ex2.approx maps to 0: keep it 0)
 #endif
 
 // OT_HANG_DEBUG=1 (compile time, debugging only): a wait that runs into the hang guard records who waited for what in a device-side
@@ -62,7 +63,9 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t src,
 
 // One 32-column chunk of a score row -> probabilities (packed bf16 pairs) and partial row sums, software-pipelined in groups of
 // eight (arguments of group g+1 and sums / packs of group g-1 around the exponentials of group g).  The mask-free form works on
-// packed fp32 pairs (FFMA2 for the arguments, FADD2 for the row sums: half the issue slots of the scalar form).
+// packed fp32 pairs (FFMA2 for the arguments, FADD2 for the row sums: half the issue slots of the scalar form).  Since the callers
+// overwrite the hidden scores of a chunk cut by the diagonal with -inf before the row maximum, they use the mask-free form for every
+// chunk; the MASK form is kept for reference.
 template <bool MASK>
 __device__ __forceinline__ void f3_softmax_chunk(const uint32_t (&s)[32], uint32_t (&pk)[16], float scale_log2, float mb, int lim_rel,
                                                  f32x2 (&rs)[2]) {
